@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — 8^3 leaves/sec, encode + decode roundtrip (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--leaves L]
+
+One "step" = one pass of the hot path over one batch: encode L leaves to uint8 indices, then decode
+those indices back to voxels.  At N=1 the workload is BASELINE.json configs[2] (1 M-leaf fp32
+FloatGrid roundtrip; configs[1], decode-only, is the second half of the same step and is reported
+in `parts`).  For N>1 every rank processes its own L leaves (leaf-range sharding, weak scaling) and
+the decoded blocks are gathered to rank 0 over NCCL for grid reassembly inside the timed region.
+
+Keys follow the driver contract; see DESIGN.md §Measurement for how each number is produced.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+# Algorithmic work per leaf: dense MACs x 2.
+FLOP_ENCODE = 26.40e6 + 4.19e6      # encoder + VQ distance GEMM
+FLOP_DECODE = 114.14e6
+BYTES_ENCODE = 2048 + 64
+BYTES_DECODE = 64 + 2048
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower() == "active":
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def gen_leaves_gpu(n, device, seed):
+    """Synthetic smoke: trilinear align_corners upsample of U[0,1] 3^3 control
+    grids to 8^3, clamped to [0,1]."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((n, 1, 8, 8, 8), dtype=torch.float32, device=device)
+    step = 131072
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        ctrl = torch.rand((hi - lo, 1, 3, 3, 3), generator=g, device=device)
+        out[lo:hi] = torch.nn.functional.interpolate(ctrl, size=(8, 8, 8), mode="trilinear", align_corners=True).clamp_(0, 1)
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (its LibTorch backend,
+    compiled unmodified into oracle/_ref), all host threads, batch 512, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    from oracle.pyoracle import COracle, RefCodec, ref_available
+    from vqvdb_b200 import synth
+    cores = os.cpu_count() or 1
+    sample = args.ref_sample
+    x = synth.smoke_leaves(sample, seed=0)
+    steps, warmup = args.steps, max(1, min(args.warmup, 2))
+    if ref_available():
+        kind = "reference"
+        ref = RefCodec("cpu", threads=cores)
+        tmp = tempfile.mkdtemp(prefix="vqvdb_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        path = os.path.join(tmp, "x.bin")
+        x.tofile(path)
+        ref.proc.stdin.write("bench roundtrip %s %d %d %d %d\n" % (path, sample, 512, steps, warmup))
+        ref.proc.stdin.flush()
+        resp = ref._readline().split()
+        assert resp[0] == "ok", resp
+        total = float(resp[1])
+        threads = ref.threads
+        ref.close()
+        os.remove(path); os.rmdir(tmp)
+    else:
+        kind = "port"
+        o = COracle(threads=cores)
+        threads = o.threads
+        for _ in range(warmup):
+            o.decode(o.encode(x))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            o.decode(o.encode(x))
+        total = time.perf_counter() - t0
+    value = sample * steps / total
+    line = {
+        "impl": "reference", "metric": "leaves_per_sec_encode_decode", "value": value, "unit": "leaves/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * total / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "roundtrip_1M_float_leaves", "leaves_per_gpu": args.leaves, "model": None,
+                   "note": "reference CPU backend (LibTorch, TorchBackend.cpp) timed on a %d-leaf sample per step, batch 512" % sample},
+        "cpu_baseline": {"value": value, "unit": "leaves/s", "cores": threads, "kind": kind,
+                         "sample": "%d smoke leaves x %d steps, batch 512, encode+decode" % (sample, steps)},
+        "e2e": {"value": value, "unit": "leaves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_baseline(sample, reference_gpu=True):
+    """Reference backend on the box's host cores (rank 0, N=1 only), plus — informational — the same
+    reference backend with Device::CUDA, i.e. 'the reference's own GPU backend' of the 10x target."""
+    from oracle.pyoracle import COracle, RefCodec, ref_available
+    from vqvdb_b200 import synth
+    cores = os.cpu_count() or 1
+    x = synth.smoke_leaves(sample, seed=0)
+    out = {}
+    if ref_available():
+        ref = RefCodec("cpu", threads=cores)
+        tmp = tempfile.mkdtemp(prefix="vqvdb_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        path = os.path.join(tmp, "x.bin")
+        x.tofile(path)
+        try:
+            ref.proc.stdin.write("bench roundtrip %s %d %d %d %d\n" % (path, sample, 512, 1, 1))
+            ref.proc.stdin.flush()
+            resp = ref._readline().split()
+            total = float(resp[1])
+            out["cpu_baseline"] = {"value": sample / total, "unit": "leaves/s", "cores": ref.threads, "kind": "reference",
+                                   "sample": "%d smoke leaves, batch 512, encode+decode, 1 warm-up pass" % sample}
+        finally:
+            ref.close()
+        if reference_gpu:
+            try:
+                big = 8 * sample
+                xb = synth.smoke_leaves(big, seed=1)
+                pb = os.path.join(tmp, "xb.bin")
+                xb.tofile(pb)
+                rg = RefCodec("cuda")
+                res = {}
+                for batch in (64, 8192):
+                    rg.proc.stdin.write("bench roundtrip %s %d %d %d %d\n" % (pb, big, batch, 2, 1))
+                    rg.proc.stdin.flush()
+                    resp = rg._readline().split()
+                    if resp[0] == "ok":
+                        res["batch_%d" % batch] = 2 * big / float(resp[1])
+                rg.close()
+                out["reference_gpu_backend"] = {"unit": "leaves/s", "leaves": big, **res,
+                                                "note": "reference TorchBackend Device::CUDA through its host-pointer API, torch defaults (TF32 conv allowed)"}
+                os.remove(pb)
+            except Exception as e:  # noqa: BLE001 — informational only
+                out["reference_gpu_backend"] = {"unavailable": str(e)[:200]}
+        os.remove(path); os.rmdir(tmp)
+    else:
+        o = COracle(threads=cores)
+        o.decode(o.encode(x[:256]))
+        t0 = time.perf_counter()
+        o.decode(o.encode(x))
+        out["cpu_baseline"] = {"value": sample / (time.perf_counter() - t0), "unit": "leaves/s", "cores": o.threads,
+                               "kind": "port", "sample": "%d smoke leaves, encode+decode" % sample}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--leaves", type=int, default=1_000_000, help="leaves per GPU per step")
+    ap.add_argument("--ref-sample", type=int, default=16384, help="leaves per step for the CPU reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decode-precision", default="default")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 backend has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    L = args.leaves
+
+    codec = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, device_index=local,
+                                           decode_precision=args.decode_precision), BackendType.B200)
+    if codec is None:
+        raise SystemExit("B200 backend failed to initialise")
+
+    x = gen_leaves_gpu(L, dev, seed=rank)
+    idx = torch.empty((L, 4, 4, 4), dtype=torch.uint8, device=dev)
+    vox = torch.empty((L, 1, 8, 8, 8), dtype=torch.float32, device=dev)
+    gathered = None
+    if world > 1 and rank == 0:
+        gathered = [torch.empty_like(vox) for _ in range(world)]
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    def step():
+        codec.encode_device(x, L, idx, sp)
+        codec.decode_device(idx, L, vox, sp)
+        if world > 1:  # grid reassembly on rank 0: decoded blocks travel over NVLink (north_star)
+            dist.gather(vox, gathered, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = codec.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(K):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = codec.kernel_launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-kernel durations (same stream, CUDA events), for the roofline of the dominant kernel
+    def time_kernel(fn, reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    enc_ms = time_kernel(lambda: codec.encode_device(x, L, idx, sp), K)
+    dec_ms = time_kernel(lambda: codec.decode_device(idx, L, vox, sp), K)
+
+    # end to end through the C-ABI with HOST buffers (pinned), H2D + D2H inside the timed region
+    hx = torch.empty((L, 1, 8, 8, 8), dtype=torch.float32, pin_memory=True)
+    hx.copy_(x)
+    hidx = torch.empty((L, 4, 4, 4), dtype=torch.uint8, pin_memory=True)
+    hvox = torch.empty((L, 1, 8, 8, 8), dtype=torch.float32, pin_memory=True)
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        codec.encode_into(hx, L, hidx)
+        codec.decode_into(hidx, L, hvox)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_checksum = float(hvox[:: max(1, L // 1024)].double().sum())
+
+    t = torch.tensor([ms, e2e_s * 1e3, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, enc_ms, dec_ms = [float(v) for v in t.tolist()]
+
+    if rank == 0:
+        peaks = measured_peaks()
+        value = L * world * K / (ms / 1e3)
+        dom = "decode" if dec_ms >= enc_ms else "encode"
+        dom_ms = max(dec_ms, enc_ms)
+        flop = FLOP_DECODE if dom == "decode" else FLOP_ENCODE
+        tensor_path = (dom == "decode" and codec.decode_path != "fp32")
+        achieved = flop * L / (dom_ms / 1e3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        line = {
+            "metric": "leaves_per_sec_encode_decode", "value": value, "unit": "leaves/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 encode+VQ, %s decode" % ("bf16 operands/f32 accumulate" if tensor_path else "f32"),
+            "data": "synthetic",
+            "config": {"workload": "roundtrip_1M_float_leaves", "leaves_per_gpu": L, "weights": "shipped float model C=1 D=128 K=256",
+                       "sharding": "leaf ranges, one rank per GPU" + (", NCCL gather of decoded blocks to rank 0" if world > 1 else ""),
+                       "l2": "inputs (%.2f GB/step) exceed the 126 MB L2; no explicit flush" % (L * 2048 / 1e9),
+                       "decode_path": codec.decode_path},
+            "parts": {"encode_ms": enc_ms, "decode_ms": dec_ms,
+                      "encode_leaves_per_s": L / (enc_ms / 1e3), "decode_leaves_per_s": L / (dec_ms / 1e3)},
+            "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % peaks["source"],
+                         "hbm_gbs_nonbinding": (BYTES_DECODE if dom == "decode" else BYTES_ENCODE) * L / (dom_ms / 1e3) / 1e9,
+                         "note": "compute-bound path (34 kFLOP/B); %s kernel runs on %s" % (dom, "tcgen05 bf16" if tensor_path else "fp32 FFMA (CUDA-core peak ~74 TFLOP/s)")},
+            "e2e": {"value": L * world * K / (e2e_ms / 1e3), "unit": "leaves/s",
+                    "h2d_bytes_per_step": L * (2048 + 64), "d2h_bytes_per_step": L * (64 + 2048),
+                    "api": "vqvdb_b200_encode + vqvdb_b200_decode on pinned host buffers", "checksum": e2e_checksum},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line.update(cpu_baseline(args.ref_sample))
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": "leaves/s", "cores": 0, "kind": "reference",
+                                        "sample": "failed: %s" % str(e)[:200]}
+        print(json.dumps(line))
+    codec.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,116 @@
+/* vqvdb_b200.h — C ABI of the B200-native VQ-VAE leaf codec.
+ *
+ * This is the drop-in boundary for the reference's backend interface
+ *     class IVQVAECodec        /root/reference/src/core/IVQVAECodec.hpp:99-137
+ * whose only callers are VQVAECodec::encodeBatch/decodeBatch
+ *     /root/reference/src/orchestrator/VQVAECodec.cpp:210,212
+ * A reference-side backend (`B200Backend final : IVQVAECodec`, see
+ * vqvdb_b200/cpp/B200Backend.{hpp,cpp} and INTEGRATION.md) forwards each virtual
+ * to exactly one entry point below.  Plain pointers and sizes only: no C++ types,
+ * no exceptions across the boundary, no torch/ORT types.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative vqvdb_b200_status;
+ *     vqvdb_b200_last_error() gives the message (per codec; pass NULL for the
+ *     calling thread's last create() failure).
+ *   - a codec is bound to ONE CUDA device and owns its streams and staging buffers;
+ *     calls on one codec must be serialised by the caller (the reference's batch
+ *     loop is single-threaded: VQVAECodec.cpp:108-127); different codecs are independent.
+ *   - there is NO CPU fallback: if the device or the sm_100a kernels are unavailable,
+ *     create() fails (the reference's TorchBackend.cpp:64-72 silently falls back; this does not).
+ *   - layouts are the reference's: leaves float32 [n, C, 8, 8, 8] with OpenVDB leaf-buffer
+ *     order (IVQVAECodec.hpp:116-121), indices uint8 [n, 4, 4, 4] (d-major), n may be 0.
+ */
+#ifndef VQVDB_B200_H
+#define VQVDB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define VQVDB_B200_API __declspec(dllexport)
+#else
+#define VQVDB_B200_API __attribute__((visibility("default")))
+#endif
+
+typedef struct vqvdb_b200_codec vqvdb_b200_codec;
+
+typedef enum vqvdb_b200_status {
+	VQVDB_B200_OK = 0,
+	VQVDB_B200_ERR_INVALID_ARGUMENT = -1,
+	VQVDB_B200_ERR_NO_DEVICE = -2,      /* no CUDA device / not an sm_100 part / kernels missing */
+	VQVDB_B200_ERR_BAD_WEIGHTS = -3,    /* weight pack missing, truncated or of an unknown architecture */
+	VQVDB_B200_ERR_CUDA = -4,           /* a CUDA runtime call failed; message has the cudaError string */
+	VQVDB_B200_ERR_OUT_OF_MEMORY = -5,
+	VQVDB_B200_ERR_UNSUPPORTED = -6
+} vqvdb_b200_status;
+
+/* Decoder arithmetic.  The encoder and the codebook argmin always run fp32-faithful
+ * (index parity with the reference is a bit-exactness requirement); the decoder may
+ * use BF16 tensor-core operands with fp32 accumulation. */
+typedef enum vqvdb_b200_decode_precision {
+	VQVDB_B200_DECODE_DEFAULT = 0, /* fastest path that meets the 0.1 dB PSNR budget */
+	VQVDB_B200_DECODE_FP32 = 1,    /* CUDA-core fp32 path (bring-up / checking) */
+	VQVDB_B200_DECODE_BF16_TC = 2  /* tcgen05 BF16 path */
+} vqvdb_b200_decode_precision;
+
+/* Replaces CodecConfig{device, source} (IVQVAECodec.hpp:85-89).  Zero-initialise, set
+ * struct_size = sizeof(vqvdb_b200_config), then fill what you need. */
+typedef struct vqvdb_b200_config {
+	uint32_t struct_size;
+	int32_t device;               /* CUDA ordinal (the reference hard-codes 0: OnnxBackend_Cuda.cpp:21) */
+	const void* weights_data;     /* VQVDBW01 pack in memory, or NULL */
+	uint64_t weights_size;
+	const char* weights_path;     /* VQVDBW01 pack on disk, or NULL.  Both NULL = the embedded float model
+	                                 (the reference's EmbeddedModel source, IVQVAECodec.hpp:27) */
+	uint32_t chunk_leaves;        /* leaves per internal pipeline chunk for the host-pointer calls; 0 = default */
+	uint32_t decode_precision;    /* vqvdb_b200_decode_precision */
+	uint32_t reserved[8];
+} vqvdb_b200_config;
+
+/* IVQVAECodec::create (IVQVAECodec.cpp:76-110).  On failure *out is NULL. */
+VQVDB_B200_API int vqvdb_b200_create(const vqvdb_b200_config* cfg, vqvdb_b200_codec** out);
+VQVDB_B200_API void vqvdb_b200_destroy(vqvdb_b200_codec* codec);
+
+/* IVQVAECodec::getLatentShape (IVQVAECodec.hpp:136): writes {4,4,4}. */
+VQVDB_B200_API int vqvdb_b200_latent_shape(const vqvdb_b200_codec* codec, int64_t out_dhw[3]);
+/* Channel count of the loaded model: 1 (FloatGrid) or 3 (Vec3fGrid). */
+VQVDB_B200_API int vqvdb_b200_in_channels(const vqvdb_b200_codec* codec);
+VQVDB_B200_API int vqvdb_b200_num_embeddings(const vqvdb_b200_codec* codec);
+
+/* IVQVAECodec::encode (IVQVAECodec.hpp:121; TorchBackend.cpp:133-164).
+ * host_leaves: n*C*512 floats, caller-owned HOST memory (pageable or pinned);
+ * host_indices: n*64 bytes, caller-owned HOST memory.  Synchronous. */
+VQVDB_B200_API int vqvdb_b200_encode(vqvdb_b200_codec* codec, const float* host_leaves, int64_t n_leaves,
+                                     uint8_t* host_indices);
+
+/* IVQVAECodec::decode (IVQVAECodec.hpp:130; TorchBackend.cpp:166-194).  Synchronous. */
+VQVDB_B200_API int vqvdb_b200_decode(vqvdb_b200_codec* codec, const uint8_t* host_indices, int64_t n_leaves,
+                                     float* host_voxels);
+
+/* Device-pointer variants for the pipelined batch loop and the multi-GPU path: buffers live
+ * on the codec's device, work is enqueued on `cuda_stream` (a cudaStream_t, used exactly as given:
+ * NULL is the CUDA legacy default stream) and the call returns without synchronising. */
+VQVDB_B200_API int vqvdb_b200_encode_device(vqvdb_b200_codec* codec, const float* dev_leaves, int64_t n_leaves,
+                                            uint8_t* dev_indices, void* cuda_stream);
+VQVDB_B200_API int vqvdb_b200_decode_device(vqvdb_b200_codec* codec, const uint8_t* dev_indices, int64_t n_leaves,
+                                            float* dev_voxels, void* cuda_stream);
+/* Blocks until the codec's own pipeline streams are idle (work enqueued on caller streams is the caller's). */
+VQVDB_B200_API int vqvdb_b200_synchronize(vqvdb_b200_codec* codec);
+
+/* Kernel launches issued by this codec since creation (bench.py's gpu_launches). */
+VQVDB_B200_API uint64_t vqvdb_b200_kernel_launches(const vqvdb_b200_codec* codec);
+/* Name of the decode path actually in use: "fp32" or "bf16_tc". */
+VQVDB_B200_API const char* vqvdb_b200_decode_path(const vqvdb_b200_codec* codec);
+
+VQVDB_B200_API const char* vqvdb_b200_last_error(const vqvdb_b200_codec* codec);
+VQVDB_B200_API const char* vqvdb_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQVDB_B200_H */

@@ -1,0 +1,151 @@
+"""GPU parity: the CUDA path, called through the C-ABI, against the reference's outputs."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import RECON_ATOL_FP32, assert_indices_match, golden
+from vqvdb_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "kat256": lambda: synth.kat_leaves(256),
+    "smoke1024_seed0": lambda: synth.smoke_leaves(1024, seed=0),
+    "sparse1024_seed1": lambda: synth.smoke_leaves(1024, seed=1, sparse=True),
+    "noise256_seed2": lambda: synth.noise_leaves(256, seed=2),
+    "fogsphere64": lambda: synth.fog_sphere_grid()[1],
+    "zeros4": lambda: np.zeros((4, 1, 8, 8, 8), np.float32),
+}
+
+
+@pytest.fixture(scope="module")
+def codec():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec
+    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, decode_precision="fp32"), BackendType.B200)
+    assert c is not None, "B200 backend failed to initialise (no fallback exists)"
+    yield c
+    c.close()
+
+
+def _encode(codec, x):
+    from vqvdb_b200 import DataType, TensorView
+    return codec.encode(TensorView(np.ascontiguousarray(x), list(x.shape), DataType.FLOAT32)).buffer
+
+
+def _decode(codec, idx):
+    from vqvdb_b200 import DataType, TensorView
+    return codec.decode(TensorView(np.ascontiguousarray(idx), list(idx.shape), DataType.UINT8)).buffer
+
+
+def test_latent_shape(codec):
+    assert codec.getLatentShape() == [4, 4, 4]      # TorchBackend.cpp:97-119 probe result
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_encode_indices_match_reference(codec, name):
+    g = golden(name)
+    idx = _encode(codec, CASES[name]())
+    assert idx.dtype == np.uint8 and idx.shape == g["indices"].shape
+    n_mm = assert_indices_match(idx, g["indices"], g["margins"])
+    print("%s: %d of %d indices differ (all at reference near-ties)" % (name, n_mm, idx.size))
+
+
+def test_known_answer_hash(codec):
+    # SURVEY Appendix C known-answer vector: SHA-256 of the 16 384 index bytes.
+    idx = _encode(codec, synth.kat_leaves(256))
+    g = golden("kat256")
+    if np.array_equal(idx, g["indices"]):
+        assert hashlib.sha256(idx.tobytes()).hexdigest() == \
+            "2d8b7f4f9c0866de2f4a0313768811ca4ddc31162a7de88ee461d2ce46b21bc3"
+    else:
+        assert_indices_match(idx, g["indices"], g["margins"])
+
+
+@pytest.mark.parametrize("name", ["kat256", "smoke1024_seed0", "sparse1024_seed1", "fogsphere64", "zeros4"])
+def test_decode_fp32_matches_reference(codec, name):
+    g = golden(name)
+    m = len(g["recon"])
+    rec = _decode(codec, g["indices"][:m])
+    assert rec.shape == g["recon"].shape
+    assert np.abs(rec - g["recon"]).max() <= RECON_ATOL_FP32
+    full = _decode(codec, g["indices"])
+    assert abs(float(full.astype(np.float64).sum()) - float(g["recon_sum"])) <= 1e-5 * full.size
+
+
+def test_decode_random_indices(codec):
+    g = golden("decode_random128_seed1234")
+    rec = _decode(codec, synth.random_indices(128, seed=1234))
+    assert np.abs(rec - g["recon"]).max() <= RECON_ATOL_FP32
+
+
+def test_gpu_matches_c_oracle_on_fresh_seed(codec, c_oracle):
+    x = synth.smoke_leaves(512, seed=77)
+    idx_o, margins = c_oracle.encode(x, with_margins=True)
+    idx = _encode(codec, x)
+    assert_indices_match(idx, idx_o, margins)
+    rec_o = c_oracle.decode(idx_o[:64])
+    assert np.abs(_decode(codec, idx_o[:64]) - rec_o).max() <= RECON_ATOL_FP32
+
+
+def test_edge_batch_sizes(codec):
+    # empty, single, ragged (not a multiple of anything), and more leaves than one pipeline chunk
+    from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec
+    x = synth.smoke_leaves(1024, seed=0)
+    g = golden("smoke1024_seed0")
+    assert _encode(codec, x[:0]).shape == (0, 4, 4, 4)
+    assert _decode(codec, g["indices"][:0]).shape == (0, 1, 8, 8, 8)
+    for n in (1, 2, 147, 149, 1000):
+        assert_indices_match(_encode(codec, x[:n]), g["indices"][:n], g["margins"][:n])
+    small = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, chunk_leaves=100, decode_precision="fp32"),
+                               BackendType.B200)
+    try:
+        idx = _encode(small, x)                       # 11 chunks through 3 slots, last one ragged
+        assert_indices_match(idx, g["indices"], g["margins"])
+        rec = _decode(small, g["indices"])
+        assert np.abs(rec[:64] - g["recon"]).max() <= RECON_ATOL_FP32
+        assert np.array_equal(rec, _decode(codec, g["indices"]))   # chunking does not change results
+    finally:
+        small.close()
+
+
+def test_batch_invariance_and_determinism(codec):
+    x = synth.smoke_leaves(300, seed=5)
+    a = _encode(codec, x)
+    b = np.concatenate([_encode(codec, x[:7]), _encode(codec, x[7:])])
+    assert np.array_equal(a, b) and np.array_equal(a, _encode(codec, x))
+
+
+def test_wrong_dtype_raises(codec):
+    from vqvdb_b200 import DataType, TensorView
+    x = synth.kat_leaves(2)
+    with pytest.raises(RuntimeError, match="encode expects FLOAT32"):
+        codec.encode(TensorView(x, list(x.shape), DataType.UINT8))
+    with pytest.raises(RuntimeError, match="decode expects UINT8"):
+        codec.decode(TensorView(x, [2, 4, 4, 4], DataType.FLOAT32))
+
+
+def test_device_pointer_api_matches_host_api(codec):
+    import torch
+    x = synth.smoke_leaves(600, seed=9)
+    idx_host = _encode(codec, x)
+    xd = torch.from_numpy(x).cuda()
+    idx_d = torch.empty((600, 4, 4, 4), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream()
+    codec.encode_device(xd, 600, idx_d, st.cuda_stream)
+    vox_d = torch.empty((600, 1, 8, 8, 8), dtype=torch.float32, device="cuda")
+    codec.decode_device(idx_d, 600, vox_d, st.cuda_stream)
+    st.synchronize()
+    assert np.array_equal(idx_d.cpu().numpy(), idx_host)
+    assert np.array_equal(vox_d.cpu().numpy(), _decode(codec, idx_host))
+
+
+def test_roundtrip_psnr_against_reference(codec):
+    # encode -> decode on the GPU vs the reference's own encode -> decode, same leaves
+    g = golden("smoke1024_seed0")
+    x = synth.smoke_leaves(1024, seed=0)[:64]
+    rec = _decode(codec, _encode(codec, x))
+    d = abs(synth.psnr(x, rec) - synth.psnr(x, g["recon"]))
+    assert d <= 0.1, "roundtrip PSNR differs from the reference by %.4f dB" % d

@@ -1,0 +1,251 @@
+"""ctypes binding of the C-ABI (include/vqvdb_b200.h) plus a Python mirror of the reference's
+backend interface, so tests and bench.py read like calls on the reference's IVQVAECodec
+(/root/reference/src/core/IVQVAECodec.hpp:99-137).
+
+There is no fallback of any kind here: if libvqvdb_b200.so is missing, cannot be loaded, or finds
+no sm_100 device, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Union
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvqvdb_b200.so")
+
+EXPORTS = [  # every symbol include/vqvdb_b200.h declares
+    "vqvdb_b200_create", "vqvdb_b200_destroy", "vqvdb_b200_latent_shape", "vqvdb_b200_in_channels",
+    "vqvdb_b200_num_embeddings", "vqvdb_b200_encode", "vqvdb_b200_decode", "vqvdb_b200_encode_device",
+    "vqvdb_b200_decode_device", "vqvdb_b200_synchronize", "vqvdb_b200_kernel_launches",
+    "vqvdb_b200_decode_path", "vqvdb_b200_last_error", "vqvdb_b200_version",
+]
+
+
+class _Config(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("device", C.c_int32),
+        ("weights_data", C.c_void_p),
+        ("weights_size", C.c_uint64),
+        ("weights_path", C.c_char_p),
+        ("chunk_leaves", C.c_uint32),
+        ("decode_precision", C.c_uint32),
+        ("reserved", C.c_uint32 * 8),
+    ]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads the in-tree shared library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libvqvdb_b200.so is not built (python -m vqvdb_b200.build); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.vqvdb_b200_create.argtypes = [C.POINTER(_Config), C.POINTER(C.c_void_p)]
+    L.vqvdb_b200_create.restype = C.c_int
+    L.vqvdb_b200_destroy.argtypes = [C.c_void_p]
+    L.vqvdb_b200_destroy.restype = None
+    L.vqvdb_b200_latent_shape.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.vqvdb_b200_in_channels.argtypes = [C.c_void_p]
+    L.vqvdb_b200_num_embeddings.argtypes = [C.c_void_p]
+    for fn in ("vqvdb_b200_encode", "vqvdb_b200_decode"):
+        getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        getattr(L, fn).restype = C.c_int
+    for fn in ("vqvdb_b200_encode_device", "vqvdb_b200_decode_device"):
+        getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        getattr(L, fn).restype = C.c_int
+    L.vqvdb_b200_synchronize.argtypes = [C.c_void_p]
+    L.vqvdb_b200_kernel_launches.argtypes = [C.c_void_p]
+    L.vqvdb_b200_kernel_launches.restype = C.c_uint64
+    L.vqvdb_b200_decode_path.argtypes = [C.c_void_p]
+    L.vqvdb_b200_decode_path.restype = C.c_char_p
+    L.vqvdb_b200_last_error.argtypes = [C.c_void_p]
+    L.vqvdb_b200_last_error.restype = C.c_char_p
+    L.vqvdb_b200_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+# ---- mirror of the reference's boundary types (IVQVAECodec.hpp:21-89) ----
+
+class BackendType(enum.Enum):
+    LibTorch = 0   # reference backends: not provided by this package
+    ONNX = 1
+    B200 = 2       # the backend this package adds
+
+
+class DataType(enum.Enum):
+    FLOAT32 = 0
+    UINT8 = 1
+
+
+class EmbeddedModel:
+    """Tag: use the model linked into the library (reference: IVQVAECodec.hpp:27)."""
+
+
+@dataclass
+class CodecConfig:
+    class Device(enum.Enum):
+        CPU = 0
+        CUDA = 1
+
+    device: "CodecConfig.Device" = None  # type: ignore[assignment]
+    source: Union[EmbeddedModel, str, os.PathLike] = field(default_factory=EmbeddedModel)
+    device_index: int = 0            # extension: which GPU (the reference hard-codes 0)
+    chunk_leaves: int = 0            # extension: pipeline chunk of the host-pointer calls
+    decode_precision: str = "default"  # "default" | "fp32" | "bf16_tc"
+
+    def __post_init__(self):
+        if self.device is None:
+            self.device = CodecConfig.Device.CPU
+
+
+@dataclass
+class TensorView:
+    """Non-owning view (IVQVAECodec.hpp:49-53): `data` is a C-contiguous numpy array."""
+    data: np.ndarray
+    shape: Sequence[int]
+    dtype: DataType
+
+
+@dataclass
+class Tensor:
+    """Owning result (IVQVAECodec.hpp:61-80)."""
+    buffer: np.ndarray
+    shape: Sequence[int]
+    dtype: DataType
+
+    def getData(self) -> np.ndarray:
+        return self.buffer
+
+
+_PRECISION = {"default": 0, "fp32": 1, "bf16_tc": 2}
+
+
+class B200Codec:
+    """IVQVAECodec implementation over the C-ABI.  Construct through IVQVAECodec.create()."""
+
+    def __init__(self, config: CodecConfig):
+        L = load_library()
+        if config.device != CodecConfig.Device.CUDA:
+            # The reference's TorchBackend falls back to CPU (TorchBackend.cpp:64-72); this backend must not.
+            raise RuntimeError("B200 backend requires CodecConfig.Device.CUDA; there is no CPU path")
+        cfg = _Config()
+        cfg.struct_size = C.sizeof(_Config)
+        cfg.device = int(config.device_index)
+        cfg.chunk_leaves = int(config.chunk_leaves)
+        cfg.decode_precision = _PRECISION[config.decode_precision]
+        self._keep = None
+        if isinstance(config.source, EmbeddedModel):
+            pass
+        elif isinstance(config.source, (bytes, bytearray)):
+            self._keep = C.create_string_buffer(bytes(config.source), len(config.source))
+            cfg.weights_data = C.cast(self._keep, C.c_void_p)
+            cfg.weights_size = len(config.source)
+        else:
+            self._keep = os.fspath(config.source).encode()
+            cfg.weights_path = self._keep
+        h = C.c_void_p()
+        rc = L.vqvdb_b200_create(C.byref(cfg), C.byref(h))
+        if rc != 0 or not h:
+            raise RuntimeError("vqvdb_b200_create failed (%d): %s" % (rc, L.vqvdb_b200_last_error(None).decode()))
+        self._L = L
+        self._h = h
+        shp = (C.c_int64 * 3)()
+        L.vqvdb_b200_latent_shape(h, shp)
+        self._latent = [int(v) for v in shp]
+        self.channels = int(L.vqvdb_b200_in_channels(h))
+
+    # -- lifecycle --
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.vqvdb_b200_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError("%s failed (%d): %s" % (what, rc, self._L.vqvdb_b200_last_error(self._h).decode()))
+
+    # -- IVQVAECodec --
+    def getLatentShape(self):
+        return list(self._latent)
+
+    def encode(self, leafBatch: TensorView) -> Tensor:
+        if leafBatch.dtype != DataType.FLOAT32:
+            raise RuntimeError("encode expects FLOAT32 data.")     # TorchBackend.cpp:134-136
+        x = leafBatch.data
+        n = int(leafBatch.shape[0])
+        out = np.empty((n, *self._latent), dtype=np.uint8)
+        self.encode_into(x, n, out)
+        return Tensor(out, list(out.shape), DataType.UINT8)
+
+    def decode(self, indices: TensorView) -> Tensor:
+        if indices.dtype != DataType.UINT8:
+            raise RuntimeError("decode expects UINT8 data.")       # TorchBackend.cpp:167-169
+        n = int(indices.shape[0])
+        out = np.empty((n, self.channels, 8, 8, 8), dtype=np.float32)
+        self.decode_into(indices.data, n, out)
+        return Tensor(out, list(out.shape), DataType.FLOAT32)
+
+    # -- raw-pointer forms (host numpy arrays or integer addresses) --
+    @staticmethod
+    def _addr(a) -> int:
+        if isinstance(a, np.ndarray):
+            if not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("array must be C-contiguous")
+            return a.ctypes.data
+        if hasattr(a, "data_ptr"):
+            return int(a.data_ptr())
+        return int(a)
+
+    def encode_into(self, host_leaves, n: int, host_indices):
+        self._check(self._L.vqvdb_b200_encode(self._h, self._addr(host_leaves), n, self._addr(host_indices)), "encode")
+
+    def decode_into(self, host_indices, n: int, host_voxels):
+        self._check(self._L.vqvdb_b200_decode(self._h, self._addr(host_indices), n, self._addr(host_voxels)), "decode")
+
+    def encode_device(self, dev_leaves, n: int, dev_indices, stream: int = 0):
+        self._check(self._L.vqvdb_b200_encode_device(self._h, self._addr(dev_leaves), n, self._addr(dev_indices),
+                                                     C.c_void_p(stream)), "encode_device")
+
+    def decode_device(self, dev_indices, n: int, dev_voxels, stream: int = 0):
+        self._check(self._L.vqvdb_b200_decode_device(self._h, self._addr(dev_indices), n, self._addr(dev_voxels),
+                                                     C.c_void_p(stream)), "decode_device")
+
+    def synchronize(self):
+        self._check(self._L.vqvdb_b200_synchronize(self._h), "synchronize")
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._L.vqvdb_b200_kernel_launches(self._h))
+
+    @property
+    def decode_path(self) -> str:
+        return self._L.vqvdb_b200_decode_path(self._h).decode()
+
+
+class IVQVAECodec:
+    """Factory with the reference's contract (IVQVAECodec.cpp:76-110): never raises, logs and
+    returns None on failure.  Only BackendType.B200 is served by this package."""
+
+    @staticmethod
+    def create(config: CodecConfig, type: BackendType = BackendType.B200) -> Optional[B200Codec]:
+        import sys
+        try:
+            if type != BackendType.B200:
+                raise RuntimeError("Requested backend type is not available or disabled in the build configuration.")
+            return B200Codec(config)
+        except Exception as e:  # noqa: BLE001 — mirrors the reference's catch-all
+            print("Failed to create VQ-VAE backend: %s" % e, file=sys.stderr)
+            return None

@@ -1,0 +1,440 @@
+// C-ABI of the B200 codec (include/vqvdb_b200.h): codec object, weight upload, and the chunked
+// host-pointer pipeline that replaces the reference's serial per-batch
+// H2D -> ~25 launches -> D2H -> memcpy sequence (TorchBackend.cpp:133-194).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/vqvdb_b200.h"
+#include "model.cuh"
+#include "weights.hpp"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct CudaError : std::runtime_error {
+	cudaError_t code;
+	CudaError(cudaError_t c, const char* what_call)
+	    : std::runtime_error(std::string(what_call) + ": " + cudaGetErrorString(c)), code(c) {}
+};
+#define CUDA_TRY(call)                                  \
+	do {                                                \
+		cudaError_t _e = (call);                        \
+		if (_e != cudaSuccess) throw CudaError(_e, #call); \
+	} while (0)
+
+constexpr int kSlots = 3;                   // pipeline depth of the host-pointer calls
+constexpr uint32_t kDefaultChunk = 16384;   // leaves per chunk: 32 MiB of voxels, 1 MiB of indices
+
+struct Slot {
+	cudaStream_t stream = nullptr;
+	cudaEvent_t done = nullptr;
+	float* d_vox = nullptr;      // chunk * C * 512 floats
+	uint8_t* d_idx = nullptr;    // chunk * 64 bytes
+	float* h_vox = nullptr;      // pinned staging
+	uint8_t* h_idx = nullptr;
+	int64_t pending_first = -1;  // leaf range whose results still sit in the staging buffers
+	int64_t pending_count = 0;
+};
+
+}  // namespace
+
+struct vqvdb_b200_codec {
+	int device = 0;
+	int num_sms = 0;
+	int channels = 1, D = 128, K = 256;
+	uint32_t chunk = kDefaultChunk;
+	std::string decode_path = "fp32";
+	std::string last_error;
+	std::atomic<uint64_t> launches{0};
+	cudaStream_t compute = nullptr;
+	float* arena = nullptr;  // every device weight table lives in this one allocation
+	vqvdb::EncoderWeights enc{};
+	vqvdb::DecoderWeights dec{};
+	Slot slots[kSlots];
+	bool staging_ready = false;
+
+	~vqvdb_b200_codec() {
+		cudaSetDevice(device);
+		for (auto& s : slots) {
+			if (s.stream) cudaStreamSynchronize(s.stream);
+			if (s.d_vox) cudaFree(s.d_vox);
+			if (s.d_idx) cudaFree(s.d_idx);
+			if (s.h_vox) cudaFreeHost(s.h_vox);
+			if (s.h_idx) cudaFreeHost(s.h_idx);
+			if (s.done) cudaEventDestroy(s.done);
+			if (s.stream) cudaStreamDestroy(s.stream);
+		}
+		if (compute) {
+			cudaStreamSynchronize(compute);
+			cudaStreamDestroy(compute);
+		}
+		if (arena) cudaFree(arena);
+	}
+};
+
+namespace {
+
+using vqvdb::PackTensor;
+using vqvdb::WeightPack;
+
+// Collects host tensors, then uploads them as one arena and patches the device pointers.
+struct ArenaBuilder {
+	std::vector<float> host;
+	std::vector<std::pair<const float**, size_t>> fixups;
+	void add(const float** slot, const float* data, size_t n) {
+		const size_t off = (host.size() + 63) & ~size_t(63);  // 256-byte aligned tables
+		host.resize(off + n);
+		std::memcpy(host.data() + off, data, n * sizeof(float));
+		fixups.emplace_back(slot, off);
+	}
+	void add(const float** slot, const std::vector<float>& v) { add(slot, v.data(), v.size()); }
+	void add(const float** slot, const PackTensor& t) { add(slot, t.data, t.numel()); }
+	float* upload() {
+		float* dev = nullptr;
+		CUDA_TRY(cudaMalloc(&dev, host.size() * sizeof(float)));
+		cudaError_t e = cudaMemcpy(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
+		if (e != cudaSuccess) {
+			cudaFree(dev);
+			throw CudaError(e, "cudaMemcpy(weights)");
+		}
+		for (auto& f : fixups) *f.first = dev + f.second;
+		return dev;
+	}
+};
+
+void expect_dims(const WeightPack& p, const char* name, std::initializer_list<int> dims) {
+	const PackTensor& t = p.get(name);
+	if (t.dims != std::vector<int>(dims)) throw std::runtime_error(std::string("weight pack: unexpected shape for ") + name);
+}
+
+void add_res(ArenaBuilder& ab, const WeightPack& p, const std::string& prefix, vqvdb::ResWeights& r) {
+	ab.add(&r.gn1_w, p.get(prefix + ".gn1.weight"));
+	ab.add(&r.gn1_b, p.get(prefix + ".gn1.bias"));
+	ab.add(&r.c1_w, vqvdb::transpose_conv_weight(p.get(prefix + ".conv1.weight")));
+	ab.add(&r.c1_b, p.get(prefix + ".conv1.bias"));
+	ab.add(&r.gn2_w, p.get(prefix + ".gn2.weight"));
+	ab.add(&r.gn2_b, p.get(prefix + ".gn2.bias"));
+	ab.add(&r.c2_w, vqvdb::transpose_conv_weight(p.get(prefix + ".conv2.weight")));
+	ab.add(&r.c2_b, p.get(prefix + ".conv2.bias"));
+}
+
+void upload_float_model(vqvdb_b200_codec& c, const WeightPack& p) {
+	// Architecture check: the kernels are specialised to the shipped float model.
+	expect_dims(p, "encoder.pre.0.weight", {16, 1, 3, 3, 3});
+	expect_dims(p, "encoder.pre.3.conv1.weight", {16, 16, 3, 3, 3});
+	expect_dims(p, "encoder.down.weight", {32, 16, 4, 4, 4});
+	expect_dims(p, "encoder.res_stack.0.conv1.weight", {32, 32, 3, 3, 3});
+	expect_dims(p, "encoder.attn.fc.0.weight", {8, 32});
+	expect_dims(p, "encoder.attn.fc.2.weight", {32, 8});
+	expect_dims(p, "encoder.proj.weight", {128, 32, 1, 1, 1});
+	expect_dims(p, "quantizer.embedding", {256, 128});
+	expect_dims(p, "decoder.stem.0.weight", {64, 128, 3, 3, 3});
+	expect_dims(p, "decoder.res_stack.0.conv1.weight", {64, 64, 3, 3, 3});
+	expect_dims(p, "decoder.attn.fc.0.weight", {16, 64});
+	expect_dims(p, "decoder.attn.fc.2.weight", {64, 16});
+	expect_dims(p, "decoder.up_conv.weight", {256, 64, 3, 3, 3});
+	expect_dims(p, "decoder.final.weight", {1, 32, 3, 3, 3});
+
+	ArenaBuilder ab;
+	auto& e = c.enc;
+	ab.add(&e.pre_w, vqvdb::transpose_conv_weight(p.get("encoder.pre.0.weight")));
+	ab.add(&e.pre_b, p.get("encoder.pre.0.bias"));
+	ab.add(&e.pre_gn_w, p.get("encoder.pre.1.weight"));
+	ab.add(&e.pre_gn_b, p.get("encoder.pre.1.bias"));
+	add_res(ab, p, "encoder.pre.3", e.res16);
+	ab.add(&e.down_w, vqvdb::transpose_conv_weight(p.get("encoder.down.weight")));
+	ab.add(&e.down_b, p.get("encoder.down.bias"));
+	add_res(ab, p, "encoder.res_stack.0", e.res32);
+	ab.add(&e.fc0, p.get("encoder.attn.fc.0.weight"));
+	ab.add(&e.fc2, p.get("encoder.attn.fc.2.weight"));
+	ab.add(&e.proj_w, vqvdb::transpose_conv_weight(p.get("encoder.proj.weight")));
+	ab.add(&e.proj_b, p.get("encoder.proj.bias"));
+	const PackTensor& emb = p.get("quantizer.embedding");
+	std::vector<float> emb_t((size_t)128 * 256), emb_sq(256);
+	for (int k = 0; k < 256; ++k) {
+		float s = 0.f;  // torch.sum(embedding ** 2, dim=1), save_for_inference.py:58
+		for (int d = 0; d < 128; ++d) {
+			const float v = emb.data[k * 128 + d];
+			emb_t[(size_t)d * 256 + k] = v;
+			s += v * v;
+		}
+		emb_sq[k] = s;
+	}
+	ab.add(&e.emb_t, emb_t);
+	ab.add(&e.emb_sq, emb_sq);
+
+	auto& d = c.dec;
+	ab.add(&d.emb, emb);
+	ab.add(&d.stem_w, vqvdb::transpose_conv_weight(p.get("decoder.stem.0.weight")));
+	ab.add(&d.stem_b, p.get("decoder.stem.0.bias"));
+	ab.add(&d.stem_gn_w, p.get("decoder.stem.1.weight"));
+	ab.add(&d.stem_gn_b, p.get("decoder.stem.1.bias"));
+	add_res(ab, p, "decoder.res_stack.0", d.res64);
+	ab.add(&d.fc0, p.get("decoder.attn.fc.0.weight"));
+	ab.add(&d.fc2, p.get("decoder.attn.fc.2.weight"));
+	ab.add(&d.up_w, vqvdb::transpose_conv_weight(p.get("decoder.up_conv.weight")));
+	ab.add(&d.up_b, p.get("decoder.up_conv.bias"));
+	ab.add(&d.fin_w, vqvdb::transpose_conv_weight(p.get("decoder.final.weight")));
+	ab.add(&d.fin_b, p.get("decoder.final.bias"));
+	c.arena = ab.upload();
+}
+
+void ensure_staging(vqvdb_b200_codec& c) {
+	if (c.staging_ready) return;
+	const size_t vox_bytes = (size_t)c.chunk * c.channels * 512 * sizeof(float);
+	const size_t idx_bytes = (size_t)c.chunk * 64;
+	for (auto& s : c.slots) {
+		CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+		CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+		CUDA_TRY(cudaMalloc(&s.d_vox, vox_bytes));
+		CUDA_TRY(cudaMalloc(&s.d_idx, idx_bytes));
+		CUDA_TRY(cudaMallocHost(&s.h_vox, vox_bytes));
+		CUDA_TRY(cudaMallocHost(&s.h_idx, idx_bytes));
+	}
+	c.staging_ready = true;
+}
+
+bool is_pinned_host(const void* p) {
+	cudaPointerAttributes a{};
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return a.type == cudaMemoryTypeHost;
+}
+
+int fail(vqvdb_b200_codec* c, int code, const std::string& msg) {
+	if (c) c->last_error = msg;
+	else g_create_error = msg;
+	return code;
+}
+
+int translate(vqvdb_b200_codec* c, const std::exception& e) {
+	if (auto* ce = dynamic_cast<const CudaError*>(&e))
+		return fail(c, ce->code == cudaErrorMemoryAllocation ? VQVDB_B200_ERR_OUT_OF_MEMORY : VQVDB_B200_ERR_CUDA, e.what());
+	return fail(c, VQVDB_B200_ERR_CUDA, e.what());
+}
+
+void launch_encode(vqvdb_b200_codec& c, const float* d_leaves, int64_t n, uint8_t* d_idx, cudaStream_t st) {
+	CUDA_TRY(vqvdb::launch_encode_fp32(c.enc, d_leaves, n, d_idx, c.num_sms, st));
+	if (n > 0) c.launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+void launch_decode(vqvdb_b200_codec& c, const uint8_t* d_idx, int64_t n, float* d_vox, cudaStream_t st) {
+	CUDA_TRY(vqvdb::launch_decode_fp32(c.dec, d_idx, n, d_vox, c.num_sms, st));
+	if (n > 0) c.launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+// Drains a slot: waits for its chunk and, if results were staged, copies them to the caller's buffer.
+template <class T>
+void retire(Slot& s, T* user_out, size_t elems_per_leaf, const T* staged, bool direct) {
+	if (s.pending_first < 0) return;
+	CUDA_TRY(cudaEventSynchronize(s.done));
+	if (!direct)
+		std::memcpy(user_out + (size_t)s.pending_first * elems_per_leaf, staged,
+		            (size_t)s.pending_count * elems_per_leaf * sizeof(T));
+	s.pending_first = -1;
+	s.pending_count = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vqvdb_b200_version(void) { return "vqvdb_b200 0.1 (sm_100a)"; }
+
+int vqvdb_b200_create(const vqvdb_b200_config* cfg, vqvdb_b200_codec** out) {
+	if (!out) return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "out is NULL");
+	*out = nullptr;
+	vqvdb_b200_config conf{};
+	if (cfg) {
+		if (cfg->struct_size < 32 || cfg->struct_size > sizeof(vqvdb_b200_config))
+			return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "vqvdb_b200_config.struct_size is not set");
+		std::memcpy(&conf, cfg, cfg->struct_size);
+	}
+	int n_dev = 0;
+	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+		cudaGetLastError();
+		return fail(nullptr, VQVDB_B200_ERR_NO_DEVICE, "no CUDA device is visible; this backend has no CPU fallback");
+	}
+	if (conf.device < 0 || conf.device >= n_dev)
+		return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+	std::unique_ptr<vqvdb_b200_codec> c(new vqvdb_b200_codec());
+	try {
+		c->device = conf.device;
+		CUDA_TRY(cudaSetDevice(c->device));
+		cudaDeviceProp prop{};
+		CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
+		if (prop.major != 10)
+			return fail(nullptr, VQVDB_B200_ERR_NO_DEVICE,
+			            std::string("device '") + prop.name + "' is not an sm_100 (Blackwell B200) part; kernels are built for sm_100a only");
+		c->num_sms = prop.multiProcessorCount;
+		c->chunk = conf.chunk_leaves ? conf.chunk_leaves : kDefaultChunk;
+
+		WeightPack pack;
+		try {
+			if (conf.weights_data && conf.weights_size) pack.parse(conf.weights_data, (size_t)conf.weights_size);
+			else if (conf.weights_path && conf.weights_path[0]) pack.load_file(conf.weights_path);
+			else pack.parse(vqvdb::vqvdb_b200_embedded_pack,
+				            (size_t)(vqvdb::vqvdb_b200_embedded_pack_end - vqvdb::vqvdb_b200_embedded_pack));
+			c->channels = pack.in_channels;
+			c->D = pack.embedding_dim;
+			c->K = pack.num_embeddings;
+			if (c->channels != 1 || c->D != 128 || c->K != 256)
+				return fail(nullptr, VQVDB_B200_ERR_UNSUPPORTED, "only the float model (C=1, D=128, K=256) is supported by this build");
+			upload_float_model(*c, pack);
+		} catch (const CudaError&) {
+			throw;
+		} catch (const std::exception& e) {
+			return fail(nullptr, VQVDB_B200_ERR_BAD_WEIGHTS, e.what());
+		}
+		if (conf.decode_precision == VQVDB_B200_DECODE_BF16_TC)
+			return fail(nullptr, VQVDB_B200_ERR_UNSUPPORTED, "bf16 tensor-core decode path is not built in");
+		c->decode_path = "fp32";
+		CUDA_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+		CUDA_TRY(vqvdb::configure_encode_fp32());
+		CUDA_TRY(vqvdb::configure_decode_fp32());
+	} catch (const std::exception& e) {
+		return translate(nullptr, e);
+	}
+	*out = c.release();
+	return VQVDB_B200_OK;
+}
+
+void vqvdb_b200_destroy(vqvdb_b200_codec* codec) { delete codec; }
+
+int vqvdb_b200_latent_shape(const vqvdb_b200_codec* codec, int64_t out_dhw[3]) {
+	if (!codec || !out_dhw) return VQVDB_B200_ERR_INVALID_ARGUMENT;
+	out_dhw[0] = out_dhw[1] = out_dhw[2] = 4;
+	return VQVDB_B200_OK;
+}
+
+int vqvdb_b200_in_channels(const vqvdb_b200_codec* codec) { return codec ? codec->channels : VQVDB_B200_ERR_INVALID_ARGUMENT; }
+int vqvdb_b200_num_embeddings(const vqvdb_b200_codec* codec) { return codec ? codec->K : VQVDB_B200_ERR_INVALID_ARGUMENT; }
+
+int vqvdb_b200_encode_device(vqvdb_b200_codec* c, const float* dev_leaves, int64_t n, uint8_t* dev_indices, void* stream) {
+	if (!c) return VQVDB_B200_ERR_INVALID_ARGUMENT;
+	if (n < 0 || (n > 0 && (!dev_leaves || !dev_indices))) return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "encode_device: bad arguments");
+	try {
+		CUDA_TRY(cudaSetDevice(c->device));
+		launch_encode(*c, dev_leaves, n, dev_indices, (cudaStream_t)stream);
+	} catch (const std::exception& e) {
+		return translate(c, e);
+	}
+	return VQVDB_B200_OK;
+}
+
+int vqvdb_b200_decode_device(vqvdb_b200_codec* c, const uint8_t* dev_indices, int64_t n, float* dev_voxels, void* stream) {
+	if (!c) return VQVDB_B200_ERR_INVALID_ARGUMENT;
+	if (n < 0 || (n > 0 && (!dev_indices || !dev_voxels))) return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "decode_device: bad arguments");
+	try {
+		CUDA_TRY(cudaSetDevice(c->device));
+		launch_decode(*c, dev_indices, n, dev_voxels, (cudaStream_t)stream);
+	} catch (const std::exception& e) {
+		return translate(c, e);
+	}
+	return VQVDB_B200_OK;
+}
+
+int vqvdb_b200_synchronize(vqvdb_b200_codec* c) {
+	if (!c) return VQVDB_B200_ERR_INVALID_ARGUMENT;
+	try {
+		CUDA_TRY(cudaSetDevice(c->device));
+		CUDA_TRY(cudaStreamSynchronize(c->compute));
+		if (c->staging_ready)
+			for (auto& s : c->slots) CUDA_TRY(cudaStreamSynchronize(s.stream));
+	} catch (const std::exception& e) {
+		return translate(c, e);
+	}
+	return VQVDB_B200_OK;
+}
+
+// Host-pointer encode: chunks of `chunk` leaves rotate through kSlots {stream, device buffers, pinned
+// staging}; chunk i+1's staging copy and H2D overlap chunk i's kernel and chunk i-1's D2H.
+int vqvdb_b200_encode(vqvdb_b200_codec* c, const float* host_leaves, int64_t n, uint8_t* host_indices) {
+	if (!c) return VQVDB_B200_ERR_INVALID_ARGUMENT;
+	if (n < 0 || (n > 0 && (!host_leaves || !host_indices))) return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "encode: bad arguments");
+	if (n == 0) return VQVDB_B200_OK;
+	try {
+		CUDA_TRY(cudaSetDevice(c->device));
+		ensure_staging(*c);
+		const size_t leaf_elems = (size_t)c->channels * 512;
+		const bool in_direct = is_pinned_host(host_leaves), out_direct = is_pinned_host(host_indices);
+		int64_t done = 0;
+		for (int i = 0; done < n; ++i) {
+			Slot& s = c->slots[i % kSlots];
+			retire<uint8_t>(s, host_indices, 64, s.h_idx, out_direct);
+			const int64_t cnt = std::min<int64_t>(c->chunk, n - done);
+			const float* src = host_leaves + (size_t)done * leaf_elems;
+			if (!in_direct) {
+				std::memcpy(s.h_vox, src, (size_t)cnt * leaf_elems * sizeof(float));
+				src = s.h_vox;
+			}
+			CUDA_TRY(cudaMemcpyAsync(s.d_vox, src, (size_t)cnt * leaf_elems * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+			launch_encode(*c, s.d_vox, cnt, s.d_idx, s.stream);
+			uint8_t* dst = out_direct ? host_indices + (size_t)done * 64 : s.h_idx;
+			CUDA_TRY(cudaMemcpyAsync(dst, s.d_idx, (size_t)cnt * 64, cudaMemcpyDeviceToHost, s.stream));
+			CUDA_TRY(cudaEventRecord(s.done, s.stream));
+			s.pending_first = done;
+			s.pending_count = cnt;
+			done += cnt;
+		}
+		for (auto& s : c->slots) retire<uint8_t>(s, host_indices, 64, s.h_idx, out_direct);
+	} catch (const std::exception& e) {
+		for (auto& s : c->slots) s.pending_first = -1;
+		return translate(c, e);
+	}
+	return VQVDB_B200_OK;
+}
+
+int vqvdb_b200_decode(vqvdb_b200_codec* c, const uint8_t* host_indices, int64_t n, float* host_voxels) {
+	if (!c) return VQVDB_B200_ERR_INVALID_ARGUMENT;
+	if (n < 0 || (n > 0 && (!host_indices || !host_voxels))) return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "decode: bad arguments");
+	if (n == 0) return VQVDB_B200_OK;
+	try {
+		CUDA_TRY(cudaSetDevice(c->device));
+		ensure_staging(*c);
+		const size_t leaf_elems = (size_t)c->channels * 512;
+		const bool in_direct = is_pinned_host(host_indices), out_direct = is_pinned_host(host_voxels);
+		int64_t done = 0;
+		for (int i = 0; done < n; ++i) {
+			Slot& s = c->slots[i % kSlots];
+			retire<float>(s, host_voxels, leaf_elems, s.h_vox, out_direct);
+			const int64_t cnt = std::min<int64_t>(c->chunk, n - done);
+			const uint8_t* src = host_indices + (size_t)done * 64;
+			if (!in_direct) {
+				std::memcpy(s.h_idx, src, (size_t)cnt * 64);
+				src = s.h_idx;
+			}
+			CUDA_TRY(cudaMemcpyAsync(s.d_idx, src, (size_t)cnt * 64, cudaMemcpyHostToDevice, s.stream));
+			launch_decode(*c, s.d_idx, cnt, s.d_vox, s.stream);
+			float* dst = out_direct ? host_voxels + (size_t)done * leaf_elems : s.h_vox;
+			CUDA_TRY(cudaMemcpyAsync(dst, s.d_vox, (size_t)cnt * leaf_elems * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+			CUDA_TRY(cudaEventRecord(s.done, s.stream));
+			s.pending_first = done;
+			s.pending_count = cnt;
+			done += cnt;
+		}
+		for (auto& s : c->slots) retire<float>(s, host_voxels, leaf_elems, s.h_vox, out_direct);
+	} catch (const std::exception& e) {
+		for (auto& s : c->slots) s.pending_first = -1;
+		return translate(c, e);
+	}
+	return VQVDB_B200_OK;
+}
+
+uint64_t vqvdb_b200_kernel_launches(const vqvdb_b200_codec* c) { return c ? c->launches.load() : 0; }
+const char* vqvdb_b200_decode_path(const vqvdb_b200_codec* c) { return c ? c->decode_path.c_str() : ""; }
+
+const char* vqvdb_b200_last_error(const vqvdb_b200_codec* c) { return c ? c->last_error.c_str() : g_create_error.c_str(); }
+
+}  // extern "C"
