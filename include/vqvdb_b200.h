@@ -55,7 +55,7 @@ typedef enum vqvdb_b200_status {
 typedef enum vqvdb_b200_decode_precision {
 	VQVDB_B200_DECODE_DEFAULT = 0, /* fastest path that meets the 0.1 dB PSNR budget */
 	VQVDB_B200_DECODE_FP32 = 1,    /* CUDA-core fp32 path (bring-up / checking) */
-	VQVDB_B200_DECODE_BF16_TC = 2  /* tcgen05 BF16 path */
+	VQVDB_B200_DECODE_BF16_TC = 2  /* tensor-core path: bf16 operands, fp32 accumulation */
 } vqvdb_b200_decode_precision;
 
 /* Replaces CodecConfig{device, source} (IVQVAECodec.hpp:85-89).  Zero-initialise, set
@@ -104,8 +104,13 @@ VQVDB_B200_API int vqvdb_b200_synchronize(vqvdb_b200_codec* codec);
 
 /* Kernel launches issued by this codec since creation (bench.py's gpu_launches). */
 VQVDB_B200_API uint64_t vqvdb_b200_kernel_launches(const vqvdb_b200_codec* codec);
-/* Name of the decode path actually in use: "fp32" or "bf16_tc". */
+/* Name of the decode path actually in use: "fp32" or "bf16_mma". */
 VQVDB_B200_API const char* vqvdb_b200_decode_path(const vqvdb_b200_codec* codec);
+
+/* Bring-up aid for the tensor-core decoder: runs it and also writes the fp32 activation after stage
+ * {0: stem+GroupNorm+ReLU, 1: residual block, 2: channel attention} as [n][64 ch][64 pos] to dev_tap. */
+VQVDB_B200_API int vqvdb_b200_debug_decode_tap(vqvdb_b200_codec* codec, const uint8_t* dev_indices, int64_t n_leaves,
+                                               int stage, float* dev_tap, float* dev_voxels, void* cuda_stream);
 
 VQVDB_B200_API const char* vqvdb_b200_last_error(const vqvdb_b200_codec* codec);
 VQVDB_B200_API const char* vqvdb_b200_version(void);

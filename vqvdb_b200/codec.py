@@ -22,7 +22,7 @@ EXPORTS = [  # every symbol include/vqvdb_b200.h declares
     "vqvdb_b200_create", "vqvdb_b200_destroy", "vqvdb_b200_latent_shape", "vqvdb_b200_in_channels",
     "vqvdb_b200_num_embeddings", "vqvdb_b200_encode", "vqvdb_b200_decode", "vqvdb_b200_encode_device",
     "vqvdb_b200_decode_device", "vqvdb_b200_synchronize", "vqvdb_b200_kernel_launches",
-    "vqvdb_b200_decode_path", "vqvdb_b200_last_error", "vqvdb_b200_version",
+    "vqvdb_b200_decode_path", "vqvdb_b200_last_error", "vqvdb_b200_version", "vqvdb_b200_debug_decode_tap",
 ]
 
 
@@ -63,6 +63,8 @@ def load_library() -> C.CDLL:
     for fn in ("vqvdb_b200_encode_device", "vqvdb_b200_decode_device"):
         getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         getattr(L, fn).restype = C.c_int
+    L.vqvdb_b200_debug_decode_tap.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.vqvdb_b200_debug_decode_tap.restype = C.c_int
     L.vqvdb_b200_synchronize.argtypes = [C.c_void_p]
     L.vqvdb_b200_kernel_launches.argtypes = [C.c_void_p]
     L.vqvdb_b200_kernel_launches.restype = C.c_uint64
@@ -222,6 +224,10 @@ class B200Codec:
     def decode_device(self, dev_indices, n: int, dev_voxels, stream: int = 0):
         self._check(self._L.vqvdb_b200_decode_device(self._h, self._addr(dev_indices), n, self._addr(dev_voxels),
                                                      C.c_void_p(stream)), "decode_device")
+
+    def debug_decode_tap(self, dev_indices, n: int, stage: int, dev_tap, dev_voxels, stream: int = 0):
+        self._check(self._L.vqvdb_b200_debug_decode_tap(self._h, self._addr(dev_indices), n, stage, self._addr(dev_tap),
+                                                        self._addr(dev_voxels), C.c_void_p(stream)), "debug_decode_tap")
 
     def synchronize(self):
         self._check(self._L.vqvdb_b200_synchronize(self._h), "synchronize")

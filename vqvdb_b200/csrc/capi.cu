@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/vqvdb_b200.h"
+#include "decode_mma.cuh"
 #include "model.cuh"
 #include "weights.hpp"
 
@@ -56,7 +57,10 @@ struct vqvdb_b200_codec {
 	std::string last_error;
 	std::atomic<uint64_t> launches{0};
 	cudaStream_t compute = nullptr;
-	float* arena = nullptr;  // every device weight table lives in this one allocation
+	float* arena = nullptr;  // every fp32 device weight table lives in this one allocation
+	uint8_t* mma_arena = nullptr;  // bf16 weight-unit stream + bf16 codebook of the tensor-core decoder
+	bool use_mma_decode = true;
+	vqvdb::DecoderMmaWeights dec_mma{};
 	vqvdb::EncoderWeights enc{};
 	vqvdb::DecoderWeights dec{};
 	Slot slots[kSlots];
@@ -78,6 +82,7 @@ struct vqvdb_b200_codec {
 			cudaStreamDestroy(compute);
 		}
 		if (arena) cudaFree(arena);
+		if (mma_arena) cudaFree(mma_arena);
 	}
 };
 
@@ -186,6 +191,25 @@ void upload_float_model(vqvdb_b200_codec& c, const WeightPack& p) {
 	ab.add(&d.fin_w, vqvdb::transpose_conv_weight(p.get("decoder.final.weight")));
 	ab.add(&d.fin_b, p.get("decoder.final.bias"));
 	c.arena = ab.upload();
+
+	// tensor-core decoder: bf16 unit stream + bf16 codebook; fp32 vectors are shared with the fp32 path
+	const std::vector<uint8_t> units = vqvdb::build_decoder_units(p);
+	const std::vector<uint16_t> cb = vqvdb::build_codebook_bf16(p);
+	CUDA_TRY(cudaMalloc(&c.mma_arena, units.size() + cb.size() * 2));
+	CUDA_TRY(cudaMemcpy(c.mma_arena, units.data(), units.size(), cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMemcpy(c.mma_arena + units.size(), cb.data(), cb.size() * 2, cudaMemcpyHostToDevice));
+	auto& m = c.dec_mma;
+	m.units = c.mma_arena;
+	m.emb_bf16 = reinterpret_cast<const __nv_bfloat16*>(c.mma_arena + units.size());
+	m.stem_b = d.stem_b;
+	m.stem_gn_w = d.stem_gn_w;
+	m.stem_gn_b = d.stem_gn_b;
+	m.res = d.res64;
+	m.fc0 = d.fc0;
+	m.fc2 = d.fc2;
+	m.up_b = d.up_b;
+	m.fin_w = d.fin_w;
+	m.fin_b = d.fin_b;
 }
 
 void ensure_staging(vqvdb_b200_codec& c) {
@@ -230,7 +254,8 @@ void launch_encode(vqvdb_b200_codec& c, const float* d_leaves, int64_t n, uint8_
 }
 
 void launch_decode(vqvdb_b200_codec& c, const uint8_t* d_idx, int64_t n, float* d_vox, cudaStream_t st) {
-	CUDA_TRY(vqvdb::launch_decode_fp32(c.dec, d_idx, n, d_vox, c.num_sms, st));
+	if (c.use_mma_decode) CUDA_TRY(vqvdb::launch_decode_mma(c.dec_mma, d_idx, n, d_vox, c.num_sms, st));
+	else CUDA_TRY(vqvdb::launch_decode_fp32(c.dec, d_idx, n, d_vox, c.num_sms, st));
 	if (n > 0) c.launches.fetch_add(1, std::memory_order_relaxed);
 }
 
@@ -297,12 +322,14 @@ int vqvdb_b200_create(const vqvdb_b200_config* cfg, vqvdb_b200_codec** out) {
 		} catch (const std::exception& e) {
 			return fail(nullptr, VQVDB_B200_ERR_BAD_WEIGHTS, e.what());
 		}
-		if (conf.decode_precision == VQVDB_B200_DECODE_BF16_TC)
-			return fail(nullptr, VQVDB_B200_ERR_UNSUPPORTED, "bf16 tensor-core decode path is not built in");
-		c->decode_path = "fp32";
+		if (conf.decode_precision > VQVDB_B200_DECODE_BF16_TC)
+			return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "unknown decode_precision");
+		c->use_mma_decode = conf.decode_precision != VQVDB_B200_DECODE_FP32;
+		c->decode_path = c->use_mma_decode ? "bf16_mma" : "fp32";
 		CUDA_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
 		CUDA_TRY(vqvdb::configure_encode_fp32());
 		CUDA_TRY(vqvdb::configure_decode_fp32());
+		CUDA_TRY(vqvdb::configure_decode_mma());
 	} catch (const std::exception& e) {
 		return translate(nullptr, e);
 	}
@@ -427,6 +454,20 @@ int vqvdb_b200_decode(vqvdb_b200_codec* c, const uint8_t* host_indices, int64_t 
 		for (auto& s : c->slots) retire<float>(s, host_voxels, leaf_elems, s.h_vox, out_direct);
 	} catch (const std::exception& e) {
 		for (auto& s : c->slots) s.pending_first = -1;
+		return translate(c, e);
+	}
+	return VQVDB_B200_OK;
+}
+
+int vqvdb_b200_debug_decode_tap(vqvdb_b200_codec* c, const uint8_t* dev_indices, int64_t n, int stage, float* dev_tap,
+                                float* dev_voxels, void* stream) {
+	if (!c) return VQVDB_B200_ERR_INVALID_ARGUMENT;
+	if (n < 0 || stage < 0 || stage > 2 || (n > 0 && (!dev_indices || !dev_tap || !dev_voxels)))
+		return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "debug_decode_tap: bad arguments");
+	try {
+		CUDA_TRY(cudaSetDevice(c->device));
+		CUDA_TRY(vqvdb::launch_decode_mma(c->dec_mma, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
+	} catch (const std::exception& e) {
 		return translate(c, e);
 	}
 	return VQVDB_B200_OK;

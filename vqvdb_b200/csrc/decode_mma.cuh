@@ -1,0 +1,44 @@
+// Weight tables and launcher of the tensor-core (warp-level MMA, bf16) decoder.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+#include "model.cuh"
+#include "weights.hpp"
+
+namespace vqvdb {
+
+// The conv weights are consumed as a fixed stream of 8 KB "units", each a [64 n][64 k] bf16 tile whose
+// 16-byte chunks are XOR-swizzled by (n & 7):
+//   stem.0    27 taps x 2 input-channel halves      54 units
+//   res conv1 27 taps                                27
+//   res conv2 27 taps                                27
+//   up_conv   4 output passes (64 ch) x 27 taps     108
+constexpr int kDecUnitsTotal = 216;
+
+struct DecoderMmaWeights {
+	const uint8_t* units;             // kDecUnitsTotal * 8192 bytes, consumption order
+	const __nv_bfloat16* emb_bf16;    // quantizer.embedding [256][128] as bf16
+	const float *stem_b, *stem_gn_w, *stem_gn_b;
+	ResWeights res;                   // only the fp32 vectors (gn*, c1_b, c2_b) are used
+	const float *fc0, *fc2;
+	const float *up_b;
+	const float *fin_w, *fin_b;       // decoder.final transposed [32][27]
+};
+
+// Builds the unit stream and the bf16 codebook on the host (round-to-nearest-even).
+std::vector<uint8_t> build_decoder_units(const WeightPack& pack);
+std::vector<uint16_t> build_codebook_bf16(const WeightPack& pack);
+
+cudaError_t configure_decode_mma();
+// tap_stage >= 0 additionally writes the activation after stage {0: stem+GN+ReLU, 1: residual block,
+// 2: attention} as fp32 [leaf][64 ch][64 pos] to tap_out (bring-up aid; -1 in production).
+cudaError_t launch_decode_mma(const DecoderMmaWeights& w, const uint8_t* dev_indices, int64_t n_leaves,
+                              float* dev_voxels, int num_sms, cudaStream_t stream, int tap_stage = -1,
+                              float* tap_out = nullptr);
+
+}  // namespace vqvdb
