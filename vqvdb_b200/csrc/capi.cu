@@ -62,6 +62,7 @@ struct vqvdb_b200_codec {
 	bool use_mma_decode = true;
 	vqvdb::DecoderMmaWeights dec_mma{};
 	vqvdb::EncoderWeights enc{};
+	vqvdb::EncoderUnits enc_units{};
 	vqvdb::DecoderWeights dec{};
 	Slot slots[kSlots];
 	bool staging_ready = false;
@@ -192,6 +193,30 @@ void upload_float_model(vqvdb_b200_codec& c, const WeightPack& p) {
 	ab.add(&d.fin_b, p.get("decoder.final.bias"));
 	c.arena = ab.upload();
 
+	// encoder weight-unit stream: slices of the transposed tables, in the order the kernel consumes them
+	{
+		auto& U = c.enc_units;
+		U.base = c.arena;
+		int n = 0;
+		auto add = [&](const float* table, size_t first_float, size_t n_floats) {
+			if (n >= vqvdb::kEncUnits) throw std::logic_error("encoder unit table overflow");
+			U.off[n] = (uint32_t)((table + first_float - c.arena) * sizeof(float));
+			U.bytes[n] = (uint32_t)(n_floats * sizeof(float));
+			if (U.bytes[n] > 8192 || (U.bytes[n] & 15) || (U.off[n] & 15)) throw std::logic_error("encoder unit misaligned");
+			++n;
+		};
+		add(e.pre_w, 0, 27 * 16);
+		for (const float* t : {e.res16.c1_w, e.res16.c2_w})
+			for (int q = 0; q < 4; ++q) add(t, (size_t)q * 4 * 27 * 16, 4 * 27 * 16);
+		for (int ic = 0; ic < 16; ++ic) add(e.down_w, (size_t)ic * 64 * 32, 64 * 32);
+		for (const float* t : {e.res32.c1_w, e.res32.c2_w})
+			for (int q = 0; q < 16; ++q) add(t, (size_t)q * 2 * 27 * 32, 2 * 27 * 32);
+		for (int q = 0; q < 2; ++q) add(e.proj_w, (size_t)q * 16 * 128, 16 * 128);
+		for (int pass = 0; pass < 2; ++pass)
+			for (int q = 0; q < 16; ++q) add(e.emb_t, (size_t)q * 8 * 256, 8 * 256);
+		if (n != vqvdb::kEncUnits) throw std::logic_error("encoder unit table size mismatch");
+	}
+
 	// tensor-core decoder: bf16 unit stream + bf16 codebook; fp32 vectors are shared with the fp32 path
 	const std::vector<uint8_t> units = vqvdb::build_decoder_units(p);
 	const std::vector<uint16_t> cb = vqvdb::build_codebook_bf16(p);
@@ -249,7 +274,7 @@ int translate(vqvdb_b200_codec* c, const std::exception& e) {
 }
 
 void launch_encode(vqvdb_b200_codec& c, const float* d_leaves, int64_t n, uint8_t* d_idx, cudaStream_t st) {
-	CUDA_TRY(vqvdb::launch_encode_fp32(c.enc, d_leaves, n, d_idx, c.num_sms, st));
+	CUDA_TRY(vqvdb::launch_encode_fp32(c.enc, c.enc_units, d_leaves, n, d_idx, c.num_sms, st));
 	if (n > 0) c.launches.fetch_add(1, std::memory_order_relaxed);
 }
 

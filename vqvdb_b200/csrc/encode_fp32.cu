@@ -3,12 +3,21 @@
 // Replaces, for one batch, everything TorchBackend::encode runs on the device
 // (/root/reference/src/backends/torch/TorchBackend.cpp:148-150): EncoderFloat.forward
 // (python/VQVAE_v2.py:231-250) followed by InferenceVectorQuantizer.get_indices
-// (python/save_for_inference.py:55-61) and the int64->uint8 cast.  The reference issues ~25
-// library launches with an HBM round trip between each; here a persistent CTA
-// keeps every activation of its leaf in shared memory and HBM sees 2048 B in + 64 B out per leaf.
+// (python/save_for_inference.py:55-61) and the int64->uint8 cast.  The reference issues ~25 library
+// launches with an HBM round trip between each; here HBM sees 2048 B in + 64 B out per leaf.
 //
-// Arithmetic is fp32 FFMA throughout — index parity with the reference is a bit-exactness
-// requirement and reduced-precision operands flip 0.2-2 % of indices.
+// Arithmetic is fp32 FFMA throughout: index parity with the reference is a bit-exactness requirement and
+// reduced-precision operands flip 0.2-2 % of indices.  The kernel is therefore bound by the
+// CUDA-core FMA pipe (measured 71 TFLOP/s on this part, tools/microbench/pipe_rates.cu), and the design
+// goal is to keep that pipe issuing:
+//   * a CTA (256 threads) carries TWO leaves so that the 4^3 layers still give every thread a register tile;
+//   * 8^3 layers: thread tile = one 8-voxel row x 8 output channels (64 accumulators); the residual stream
+//     stays in registers across the whole residual block, only the conv INPUT lives in shared memory;
+//   * weights stream from L2 through a 6-stage shared-memory ring (1-D TMA bulk copies, mbarrier
+//     complete_tx) in 91 fixed "units" that both leaves share; a warp reads them as broadcast LDS.128;
+//   * shared-memory layouts are chosen so every LDS.128 of activations is bank-conflict free
+//     (half-row swap keyed on bit 2 of the row index at 8^3; parity-split rows for the stride-2 conv).
+// Accumulation order per output is cin, kd, kh, kw ascending — the same as oracle/vqvae_oracle.c.
 #include "leaf_ops.cuh"
 #include "model.cuh"
 
@@ -16,204 +25,619 @@ namespace vqvdb {
 
 namespace {
 
-constexpr int kEncThreads = 256;
+constexpr int kThreads = 256;
+constexpr int kStages = 6;
+constexpr uint32_t kStageBytes = 8192;
 
-struct EncSmem {
-	// offsets in floats
-	static constexpr int in_halo = 0;                  // [1][10][10][10]
-	static constexpr int x16 = in_halo + 1000;         // [16][512]   residual stream at 8^3
-	static constexpr int h16 = x16 + 16 * 512;         // [16][10^3]  conv input at 8^3
-	static constexpr int t16 = h16 + 16 * 1000;        // [16][512]   conv1 output / z (aliased later)
-	static constexpr int x32 = t16 + 16 * 512;         // [32][64]    residual stream at 4^3
-	static constexpr int h32 = x32 + 32 * 64;          // [32][6^3]
-	static constexpr int t32 = h32 + 32 * 216;         // [32][64]
-	static constexpr int stats = t32 + 32 * 64;        // mean[8] rstd[8] tmp[48]
-	static constexpr int vq_dist = stats + 64;         // [4][64]
-	static constexpr int vq_idx = vq_dist + 256;       // [4][64] (int)
-	static constexpr int total = vq_idx + 256;
-	static constexpr int z = t16;                      // [128][64] latent, reuses t16 once the 8^3 stage is done
-};
-static_assert(EncSmem::total * 4 <= 227 * 1024, "encoder smem budget");
+// ---- shared memory map (floats unless noted) ----
+constexpr int kLeafR = 13440;                 // per-leaf slab of region R: H16 [16][10][10][8] (12800) or D16 (13440)
+constexpr int kROff = kStages * (int)kStageBytes / 4;   // region R starts after the ring
+constexpr int kRFloats = 2 * kLeafR;          // 26880
+constexpr int kH32Leaf1 = 4608 + 16;          // leaf 1's H32 slab is skewed by 16 words (bank de-conflict)
+constexpr int kX32s = kRFloats - 8192;        // [32 c][128 pos] staging for proj; later the argmin candidates
+constexpr int kInOff = kROff + kRFloats;      // in_halo: 2 x [10][10][8]
+constexpr int kRedOff = kInOff + 1600;        // GroupNorm partials: red[2][8][2], red2[2][8][2]
+constexpr int kAttOff = kRedOff + 64;         // att_mean[2][32], att_hid[2][8]
+constexpr int kBarOff = kAttOff + 80;         // 2*kStages mbarriers (8 B each)
+constexpr int kSmemFloats = kBarOff + 2 * kStages * 2;
+static_assert(kSmemFloats * 4 <= 227 * 1024, "encoder smem budget");
+static_assert(2 * 4608 + 16 <= kX32s && 16384 <= kX32s, "H32 / Z overlays stay clear of the X32 staging area");
 
-// ResidualBlock at spatial S with C channels: x += 0.1 * conv2(relu(gn2(conv1(relu(gn1(x))))))
-template <int C, int S, int TN>
-__device__ __forceinline__ void res_block(float* x, float* halo, float* tmp, float* s_mean, float* s_rstd,
-                                          const ResWeights& w) {
-	constexpr int NSP = S * S * S;
-	gn_stats<C, 8, NSP>(x, s_mean, s_rstd);
-	__syncthreads();
-	gn_relu_to_halo<C, 8, S>(x, halo, s_mean, s_rstd, w.gn1_w, w.gn1_b);
-	__syncthreads();
-	const float* c1b = w.c1_b;
-	conv_rows<C, C, S, 3, 1, TN>(halo, w.c1_w, [&](int oc0, int od, int oh, float (&acc)[TN][S]) {
-#pragma unroll
-		for (int n = 0; n < TN; ++n) {
-			const float b = __ldg(c1b + oc0 + n);
-#pragma unroll
-			for (int j = 0; j < S; ++j) tmp[(oc0 + n) * NSP + (od * S + oh) * S + j] = acc[n][j] + b;
-		}
-	});
-	__syncthreads();
-	gn_stats<C, 8, NSP>(tmp, s_mean, s_rstd);
-	__syncthreads();
-	gn_relu_to_halo<C, 8, S>(tmp, halo, s_mean, s_rstd, w.gn2_w, w.gn2_b);
-	__syncthreads();
-	const float* c2b = w.c2_b;
-	conv_rows<C, C, S, 3, 1, TN>(halo, w.c2_w, [&](int oc0, int od, int oh, float (&acc)[TN][S]) {
-#pragma unroll
-		for (int n = 0; n < TN; ++n) {
-			const float b = __ldg(c2b + oc0 + n);
-#pragma unroll
-			for (int j = 0; j < S; ++j) {
-				float* px = x + (oc0 + n) * NSP + (od * S + oh) * S + j;
-				*px = *px + kResScale * (acc[n][j] + b);
-			}
-		}
-	});
-	__syncthreads();
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "LAB_WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra LAB_DONE_%=;\n"
+	    "bra LAB_WAIT_%=;\n"
+	    "LAB_DONE_%=:\n"
+	    "}\n" ::"r"(bar),
+	    "r"(parity)
+	    : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+	uint32_t ok;
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+	    "selp.u32 %0, 1, 0, p;\n"
+	    "}\n"
+	    : "=r"(ok)
+	    : "r"(bar), "r"(parity)
+	    : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+	             "l"(src), "r"(bytes), "r"(bar)
+	             : "memory");
 }
 
-__global__ void __launch_bounds__(kEncThreads, 1)
-encode_fp32_kernel(const EncoderWeights w, const float* __restrict__ leaves, int64_t n_leaves,
-                   uint8_t* __restrict__ indices) {
-	extern __shared__ __align__(16) float smem[];
-	float* s_in = smem + EncSmem::in_halo;
-	float* x16 = smem + EncSmem::x16;
-	float* h16 = smem + EncSmem::h16;
-	float* t16 = smem + EncSmem::t16;
-	float* x32 = smem + EncSmem::x32;
-	float* h32 = smem + EncSmem::h32;
-	float* t32 = smem + EncSmem::t32;
-	float* s_mean = smem + EncSmem::stats;
-	float* s_rstd = s_mean + 8;
-	float* s_tmp = s_mean + 16;
-	float* vq_dist = smem + EncSmem::vq_dist;
-	int* vq_idx = reinterpret_cast<int*>(smem + EncSmem::vq_idx);
-	float* zbuf = smem + EncSmem::z;
-	const int tid = threadIdx.x;
+// Weight-unit stream.  Every warp consumes the same sequence; thread 0 is also the producer.
+struct Pipe {
+	uint32_t unit = 0, issued = 0, total = 0;
+	uint32_t ring = 0, bars = 0;
+	bool producer = false;
+	__device__ __forceinline__ uint32_t stage() const { return unit % kStages; }
+	__device__ __forceinline__ uint32_t phase() const { return (unit / kStages) & 1u; }
+	__device__ __forceinline__ void produce(const EncoderUnits& tab) {
+		if (!producer) return;
+		while (issued < total && issued < unit + kStages) {
+			const uint32_t s = issued % kStages, par = ((issued / kStages) & 1u) ^ 1u;
+			const uint32_t empty = bars + (kStages + s) * 8, full = bars + s * 8;
+			if (issued <= unit) mbar_wait(empty, par);
+			else if (!mbar_test(empty, par)) break;
+			const uint32_t u = issued % kEncUnits;
+			const uint32_t bytes = tab.bytes[u];
+			mbar_arrive_expect_tx(full, bytes);
+			tma_load_1d(ring + s * kStageBytes, reinterpret_cast<const uint8_t*>(tab.base) + tab.off[u], bytes, full);
+			++issued;
+		}
+	}
+	// returns the stage's base pointer once the unit has landed
+	__device__ __forceinline__ const float* acquire(const EncoderUnits& tab, const float* ring_ptr) {
+		produce(tab);
+		mbar_wait(bars + stage() * 8, phase());
+		return ring_ptr + stage() * (kStageBytes / 4);
+	}
+	__device__ __forceinline__ void release(int lane) {
+		__syncwarp();
+		if (lane == 0) mbar_arrive(bars + (kStages + stage()) * 8);
+		++unit;
+	}
+};
 
-	// Halo borders are written once and stay zero: every later write touches interiors only.
-	zero_smem<1000>(s_in);
-	zero_smem<16 * 1000>(h16);
-	zero_smem<32 * 216>(h32);
+// ---- 8^3 layers -------------------------------------------------------------------------------------
+// Conv input buffer per leaf: [C][10 d'][10 h'][8 w] (d', h' haloed with zero rows; the w halo is two zero
+// registers).  The two 16-byte halves of a row are swapped when bit 2 of h' is set, which makes the 8 rows
+// a quarter-warp touches (8 consecutive h') land in 8 distinct bank groups.
+__device__ __forceinline__ int h16_row(int c, int dp, int hp) { return ((c * 10 + dp) * 10 + hp) * 8; }
+
+// acc[n][j] += sum over (ic, kd, kh, kw) for this thread's row (d, h) and output channels och*8 .. och*8+7.
+template <int IC_PER_UNIT, int N_UNITS>
+__device__ __forceinline__ void conv8(float (&acc)[8][8], const float* hin, int d, int h, int och, Pipe& pipe,
+                                      const EncoderUnits& tab, const float* ring_ptr, int lane) {
+#pragma unroll
+	for (int n = 0; n < 8; ++n)
+#pragma unroll
+		for (int j = 0; j < 8; ++j) acc[n][j] = 0.f;
+#pragma unroll 1
+	for (int u = 0; u < N_UNITS; ++u) {
+		const float* wst = pipe.acquire(tab, ring_ptr);
+#pragma unroll 1
+		for (int i = 0; i < IC_PER_UNIT; ++i) {
+			const int ic = u * IC_PER_UNIT + i;
+#pragma unroll 1
+			for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+				for (int kh = 0; kh < 3; ++kh) {
+					const int hp = h + kh;
+					const float* row = hin + h16_row(ic, d + kd, hp);
+					const int sw = ((hp >> 2) & 1) * 4;
+					const float4 a = *reinterpret_cast<const float4*>(row + sw);
+					const float4 b = *reinterpret_cast<const float4*>(row + (sw ^ 4));
+					const float x[10] = {0.f, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0.f};
+					const float* wp = wst + ((i * 27 + (kd * 3 + kh) * 3) * 16 + och * 8);
+#pragma unroll
+					for (int kw = 0; kw < 3; ++kw) {
+						const float4 w0 = *reinterpret_cast<const float4*>(wp + kw * 16);
+						const float4 w1 = *reinterpret_cast<const float4*>(wp + kw * 16 + 4);
+						const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+						for (int j = 0; j < 8; ++j)
+#pragma unroll
+							for (int n = 0; n < 8; ++n) acc[n][j] = fmaf(x[j + kw], wv[n], acc[n][j]);
+					}
+				}
+			}
+		}
+		pipe.release(lane);
+	}
+}
+
+__device__ __forceinline__ void store_h16(const float (&v)[8][8], float* hbuf, int d, int h, int och) {
+	const int sw = (((h + 1) >> 2) & 1) * 4;
+#pragma unroll
+	for (int n = 0; n < 8; ++n) {
+		float* row = hbuf + h16_row(och * 8 + n, d + 1, h + 1);
+		*reinterpret_cast<float4*>(row + sw) = make_float4(v[n][0], v[n][1], v[n][2], v[n][3]);
+		*reinterpret_cast<float4*>(row + (sw ^ 4)) = make_float4(v[n][4], v[n][5], v[n][6], v[n][7]);
+	}
+}
+
+// Input of the stride-2 conv: rows split by the parity of d' and h' so that the rows one quarter-warp reads
+// (h' = 2*h4 + kh, d' = 2*d4 + kd) are 32 B apart in h4 and 84 words apart in d4 -> 8 distinct bank groups.
+__device__ __forceinline__ int d16_row(int c, int dp, int hp) {
+	return c * 840 + (dp & 1) * 420 + (dp >> 1) * 84 + (hp & 1) * 40 + (hp >> 1) * 8;
+}
+
+// GroupNorm over the 8^3 register tiles.  CPG = channels per group (4 for pre.1, 2 for the residual block);
+// a thread's 8 channels hold 8/CPG whole groups, each shared with the other warp that covers the remaining
+// 32 rows of the same leaf.  Two-pass variance; partials meet in shared memory (2 block barriers).
+template <int CPG>
+__device__ __forceinline__ void gn8(float (&v)[8][8], const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    float* red, int lf, int wl, int och, int lane) {
+	constexpr int NG = 8 / CPG;
+	constexpr float kInvCnt = 1.f / (CPG * 512);
+	float mean[NG], rstd[NG];
+	const int slot = wl & 1;
+#pragma unroll
+	for (int gi = 0; gi < NG; ++gi) {
+		float s = 0.f;
+#pragma unroll
+		for (int n = 0; n < CPG; ++n)
+#pragma unroll
+			for (int j = 0; j < 8; ++j) s += v[gi * CPG + n][j];
+		s = warp_sum(s);
+		if (lane == 0) red[((lf * 8 + och * NG + gi) << 1) + slot] = s;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int gi = 0; gi < NG; ++gi) {
+		const int b = (lf * 8 + och * NG + gi) << 1;
+		mean[gi] = (red[b] + red[b + 1]) * kInvCnt;
+		float q = 0.f;
+#pragma unroll
+		for (int n = 0; n < CPG; ++n)
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				const float dv = v[gi * CPG + n][j] - mean[gi];
+				q = fmaf(dv, dv, q);
+			}
+		q = warp_sum(q);
+		if (lane == 0) red[32 + b + slot] = q;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int gi = 0; gi < NG; ++gi) {
+		const int b = (lf * 8 + och * NG + gi) << 1;
+		rstd[gi] = 1.f / sqrtf((red[32 + b] + red[32 + b + 1]) * kInvCnt + kGnEps);
+	}
+#pragma unroll
+	for (int n = 0; n < 8; ++n) {
+		const int c = och * 8 + n, gi = n / CPG;
+		const float ga = __ldg(gamma + c), be = __ldg(beta + c);
+#pragma unroll
+		for (int j = 0; j < 8; ++j) v[n][j] = fmaxf((v[n][j] - mean[gi]) * rstd[gi] * ga + be, 0.f);
+	}
+}
+
+// ---- 4^3 layers -------------------------------------------------------------------------------------
+// lane = leaf*16 + d4*4 + h4 owns one 4-voxel row; warp og owns output channels og*4 .. og*4+3 (= GroupNorm
+// group og of the 32-channel layers), so every GroupNorm / attention reduction is a 16-lane shuffle.
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+	for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+__device__ __forceinline__ void gn4_relu(float (&v)[4][4], const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, int og) {
+	float s = 0.f;
+#pragma unroll
+	for (int n = 0; n < 4; ++n)
+#pragma unroll
+		for (int j = 0; j < 4; ++j) s += v[n][j];
+	const float mean = half_warp_sum(s) * (1.f / 256.f);
+	float q = 0.f;
+#pragma unroll
+	for (int n = 0; n < 4; ++n)
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const float dv = v[n][j] - mean;
+			q = fmaf(dv, dv, q);
+		}
+	const float rstd = 1.f / sqrtf(half_warp_sum(q) * (1.f / 256.f) + kGnEps);
+#pragma unroll
+	for (int n = 0; n < 4; ++n) {
+		const float ga = __ldg(gamma + og * 4 + n), be = __ldg(beta + og * 4 + n);
+#pragma unroll
+		for (int j = 0; j < 4; ++j) v[n][j] = fmaxf((v[n][j] - mean) * rstd * ga + be, 0.f);
+	}
+}
+
+__device__ __forceinline__ int h32_row(int c, int dp, int hp) { return (c * 6 + dp) * 24 + hp * 4; }
+
+// 3x3x3 conv at 4^3, 32 -> 32 channels: 16 units of 2 input channels.
+__device__ __forceinline__ void conv4(float (&acc)[4][4], const float* hin, int d4, int h4, int og, Pipe& pipe,
+                                      const EncoderUnits& tab, const float* ring_ptr, int lane) {
+#pragma unroll
+	for (int n = 0; n < 4; ++n)
+#pragma unroll
+		for (int j = 0; j < 4; ++j) acc[n][j] = 0.f;
+#pragma unroll 1
+	for (int u = 0; u < 16; ++u) {
+		const float* wst = pipe.acquire(tab, ring_ptr);
+#pragma unroll
+		for (int i = 0; i < 2; ++i) {
+			const int ic = u * 2 + i;
+#pragma unroll
+			for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+				for (int kh = 0; kh < 3; ++kh) {
+					const float4 a = *reinterpret_cast<const float4*>(hin + h32_row(ic, d4 + kd, h4 + kh));
+					const float x[6] = {0.f, a.x, a.y, a.z, a.w, 0.f};
+					const float* wp = wst + ((i * 27 + (kd * 3 + kh) * 3) * 32 + og * 4);
+#pragma unroll
+					for (int kw = 0; kw < 3; ++kw) {
+						const float4 w0 = *reinterpret_cast<const float4*>(wp + kw * 32);
+						const float wv[4] = {w0.x, w0.y, w0.z, w0.w};
+#pragma unroll
+						for (int j = 0; j < 4; ++j)
+#pragma unroll
+							for (int n = 0; n < 4; ++n) acc[n][j] = fmaf(x[j + kw], wv[n], acc[n][j]);
+					}
+				}
+			}
+		}
+		pipe.release(lane);
+	}
+}
+
+__device__ __forceinline__ void store_h32(const float (&v)[4][4], float* hbuf, int d4, int h4, int og) {
+#pragma unroll
+	for (int n = 0; n < 4; ++n)
+		*reinterpret_cast<float4*>(hbuf + h32_row(og * 4 + n, d4 + 1, h4 + 1)) = make_float4(v[n][0], v[n][1], v[n][2], v[n][3]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* __restrict__ leaves, int64_t n_leaves,
+                   uint8_t* __restrict__ indices) {
+	extern __shared__ __align__(1024) float smem[];
+	const float* ring_ptr = smem;
+	float* R = smem + kROff;
+	float* in_halo = smem + kInOff;
+	float* red = smem + kRedOff;
+	float* att_mean = smem + kAttOff;
+	float* att_hid = att_mean + 64;
+	const uint32_t bars = smem_u32(smem + kBarOff);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int64_t n_groups = (n_leaves + 1) / 2;
+
+	// in_halo borders are written once and stay zero (only interiors are overwritten per leaf)
+	for (int i = tid; i < 1600; i += kThreads) in_halo[i] = 0.f;
+	if (tid == 0) {
+		for (int s = 0; s < kStages; ++s) {
+			mbar_init(bars + s * 8, 1);
+			mbar_init(bars + (kStages + s) * 8, kThreads / 32);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	Pipe pipe;
+	pipe.ring = smem_u32(smem);
+	pipe.bars = bars;
+	pipe.producer = (tid == 0);
+	{
+		const int64_t mine = blockIdx.x < n_groups ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+		pipe.total = (uint32_t)(mine * kEncUnits);
+	}
 	__syncthreads();
 
-	for (int64_t leaf = blockIdx.x; leaf < n_leaves; leaf += gridDim.x) {
-		// ---- stage the leaf: 2048 B, 128-bit coalesced loads, into the haloed input ----
-		if (tid < 128) {
-			const float4 v = __ldcs(reinterpret_cast<const float4*>(leaves + leaf * 512) + tid);
-			const int p = tid * 4, d = p >> 6, h = (p >> 3) & 7, wq = p & 7;
-			float* dst = s_in + ((d + 1) * 10 + h + 1) * 10 + wq + 1;
-			dst[0] = v.x;
-			dst[1] = v.y;
-			dst[2] = v.z;
-			dst[3] = v.w;
-		}
-		__syncthreads();
+	// 8^3 mapping: half the CTA per leaf; warp-in-leaf wl -> (row half, channel half)
+	const int lf = tid >> 7, wl = (tid >> 5) & 3, och = wl >> 1;
+	const int row8 = (wl & 1) * 32 + lane, d8 = row8 >> 3, h8 = row8 & 7;
+	// 4^3 mapping
+	const int lf4 = lane >> 4, d4 = (lane >> 2) & 3, h4 = lane & 3, og = warp;
+	float* H16 = R + lf * kLeafR;
+	float* D16 = H16;
+	float* H32 = R + (lf4 ? kH32Leaf1 : 0);
+	float* X32s = R + kX32s;
+	float* Z = R;
 
-		// ---- pre.0: Conv3d(1,16,k3) -> t16 ; pre.1: GroupNorm(4,16) + ReLU -> x16 ----
+	for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+		// ---- stage the two leaves (2048 B each, 128-bit coalesced) and clear the conv-input borders ----
 		{
-			const float* pb = w.pre_b;
-			conv_rows<1, 16, 8, 3, 1, 4>(s_in, w.pre_w, [&](int oc0, int od, int oh, float (&acc)[4][8]) {
-#pragma unroll
-				for (int n = 0; n < 4; ++n) {
-					const float b = __ldg(pb + oc0 + n);
-#pragma unroll
-					for (int j = 0; j < 8; ++j) t16[(oc0 + n) * 512 + (od * 8 + oh) * 8 + j] = acc[n][j] + b;
-				}
-			});
-		}
-		__syncthreads();
-		gn_stats<16, 4, 512>(t16, s_mean, s_rstd);
-		__syncthreads();
-		for (int i = tid; i < 16 * 512; i += kEncThreads) {
-			const int c = i >> 9, g = c >> 2;
-			const float v = (t16[i] - s_mean[g]) * s_rstd[g] * __ldg(w.pre_gn_w + c) + __ldg(w.pre_gn_b + c);
-			x16[i] = fmaxf(v, 0.f);
+			int64_t leaf = grp * 2 + lf;
+			if (leaf >= n_leaves) leaf = grp * 2;  // odd tail: the second slot recomputes the first leaf, result discarded
+			const int lt = tid & 127;
+			const float4 v = __ldcs(reinterpret_cast<const float4*>(leaves + leaf * 512) + lt);
+			const int p = lt * 4, d = p >> 6, h = (p >> 3) & 7, half = (p >> 2) & 1;
+			const int hp = h + 1;
+			float* dst = in_halo + lf * 800 + ((d + 1) * 10 + hp) * 8 + ((half ^ ((hp >> 2) & 1)) * 4);
+			*reinterpret_cast<float4*>(dst) = v;
+			// H16 border rows of both leaves: 36 rows per channel (d' in {0,9} or h' in {0,9})
+			for (int i = tid; i < 2 * 16 * 36 * 2; i += kThreads) {
+				const int hf = i & 1, b = (i >> 1) % 36, c = ((i >> 1) / 36) & 15, l = (i >> 1) / (36 * 16);
+				int dp, hq;
+				if (b < 10) { dp = 0; hq = b; }
+				else if (b < 20) { dp = 9; hq = b - 10; }
+				else { dp = 1 + ((b - 20) >> 1); hq = ((b - 20) & 1) * 9; }
+				*reinterpret_cast<float4*>(R + l * kLeafR + h16_row(c, dp, hq) + hf * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+			}
 		}
 		__syncthreads();
 
-		// ---- pre.3: ResidualBlock(16) at 8^3 ----
-		res_block<16, 8, 4>(x16, h16, t16, s_mean, s_rstd, w.res16);
+		float xr[8][8];   // residual stream of this thread's tile (8 channels x 8 voxels)
+		float acc[8][8];
+		// ---- pre.0: Conv3d(1,16,k3) ; pre.1: GroupNorm(4,16) + ReLU ----
+		conv8<1, 1>(xr, in_halo + lf * 800, d8, h8, och, pipe, tab, ring_ptr, lane);
+#pragma unroll
+		for (int n = 0; n < 8; ++n) {
+			const float b = __ldg(w.pre_b + och * 8 + n);
+#pragma unroll
+			for (int j = 0; j < 8; ++j) xr[n][j] += b;
+		}
+		gn8<4>(xr, w.pre_gn_w, w.pre_gn_b, red, lf, wl, och, lane);
 
-		// ---- down: Conv3d(16,32,k4,s2,p1) : x16 (via halo) -> x32 ----
-		copy_to_halo<16, 8>(x16, h16);
+		// ---- pre.3: ResidualBlock(16) ----
+#pragma unroll
+		for (int n = 0; n < 8; ++n)
+#pragma unroll
+			for (int j = 0; j < 8; ++j) acc[n][j] = xr[n][j];
+		gn8<2>(acc, w.res16.gn1_w, w.res16.gn1_b, red, lf, wl, och, lane);
+		store_h16(acc, H16, d8, h8, och);
 		__syncthreads();
+		conv8<4, 4>(acc, H16, d8, h8, och, pipe, tab, ring_ptr, lane);
+#pragma unroll
+		for (int n = 0; n < 8; ++n) {
+			const float b = __ldg(w.res16.c1_b + och * 8 + n);
+#pragma unroll
+			for (int j = 0; j < 8; ++j) acc[n][j] += b;
+		}
+		gn8<2>(acc, w.res16.gn2_w, w.res16.gn2_b, red, lf, wl, och, lane);  // its barriers also fence conv1's reads of H16
+		store_h16(acc, H16, d8, h8, och);
+		__syncthreads();
+		conv8<4, 4>(acc, H16, d8, h8, och, pipe, tab, ring_ptr, lane);
+#pragma unroll
+		for (int n = 0; n < 8; ++n) {
+			const float b = __ldg(w.res16.c2_b + och * 8 + n);
+#pragma unroll
+			for (int j = 0; j < 8; ++j) xr[n][j] = xr[n][j] + kResScale * (acc[n][j] + b);
+		}
+		__syncthreads();  // every warp is done reading H16; the slab is re-laid-out for the stride-2 conv
+
+		// ---- down: Conv3d(16,32,k4,s2,p1).  Write x in the parity-split layout, borders zero. ----
+		for (int i = tid; i < 2 * 16 * 36 * 2; i += kThreads) {
+			const int hf = i & 1, b = (i >> 1) % 36, c = ((i >> 1) / 36) & 15, l = (i >> 1) / (36 * 16);
+			int dp, hq;
+			if (b < 10) { dp = 0; hq = b; }
+			else if (b < 20) { dp = 9; hq = b - 10; }
+			else { dp = 1 + ((b - 20) >> 1); hq = ((b - 20) & 1) * 9; }
+			*reinterpret_cast<float4*>(R + l * kLeafR + d16_row(c, dp, hq) + hf * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+#pragma unroll
+		for (int n = 0; n < 8; ++n) {
+			float* row = D16 + d16_row(och * 8 + n, d8 + 1, h8 + 1);
+			*reinterpret_cast<float4*>(row) = make_float4(xr[n][0], xr[n][1], xr[n][2], xr[n][3]);
+			*reinterpret_cast<float4*>(row + 4) = make_float4(xr[n][4], xr[n][5], xr[n][6], xr[n][7]);
+		}
+		__syncthreads();
+
+		float x32[4][4];  // residual stream at 4^3: 4 channels x 4 voxels
+		float a4[4][4];
 		{
-			const float* db = w.down_b;
-			conv_rows<16, 32, 4, 4, 2, 4>(h16, w.down_w, [&](int oc0, int od, int oh, float (&acc)[4][4]) {
 #pragma unroll
-				for (int n = 0; n < 4; ++n) {
-					const float b = __ldg(db + oc0 + n);
+			for (int n = 0; n < 4; ++n)
 #pragma unroll
-					for (int j = 0; j < 4; ++j) x32[(oc0 + n) * 64 + (od * 4 + oh) * 4 + j] = acc[n][j] + b;
-				}
-			});
-		}
-		__syncthreads();
-
-		// ---- res_stack.0: ResidualBlock(32) at 4^3 ; attn: ChannelAttention(32) ----
-		res_block<32, 4, 4>(x32, h32, t32, s_mean, s_rstd, w.res32);
-		channel_attention<32, 8, 64>(x32, w.fc0, w.fc2, s_tmp);
-
-		// ---- proj: Conv3d(32,128,k1) -> z [128][64] ----
-		for (int i = tid; i < 128 * 64; i += kEncThreads) {
-			const int oc = i >> 6, p = i & 63;
-			float a = 0.f;
-#pragma unroll 8
-			for (int ic = 0; ic < 32; ++ic) a = fmaf(x32[ic * 64 + p], __ldg(w.proj_w + ic * 128 + oc), a);
-			zbuf[i] = a + __ldg(w.proj_b + oc);
-		}
-		__syncthreads();
-
-		// ---- VQ: argmin_k (|z|^2 + |e_k|^2) - 2 z.e_k, first minimum wins ----
-		{
-			const int p = tid & 63, q = tid >> 6;  // q is warp-uniform: 64 positions = 2 warps
-			float dot[64];
-#pragma unroll
-			for (int k = 0; k < 64; ++k) dot[k] = 0.f;
-			float zz = 0.f;
-			const float* et = w.emb_t + q * 64;
+				for (int j = 0; j < 4; ++j) x32[n][j] = 0.f;
+			const float* din = R + lf4 * kLeafR;
 #pragma unroll 1
-			for (int d = 0; d < 128; ++d) {
-				const float zv = zbuf[d * 64 + p];
-				zz = fmaf(zv, zv, zz);
-				const float4* e4 = reinterpret_cast<const float4*>(et + d * 256);
+			for (int ic = 0; ic < 16; ++ic) {
+				const float* wst = pipe.acquire(tab, ring_ptr);
+#pragma unroll 1
+				for (int kd = 0; kd < 4; ++kd) {
 #pragma unroll
-				for (int k4 = 0; k4 < 16; ++k4) {
-					const float4 e = __ldg(e4 + k4);
-					dot[4 * k4] = fmaf(zv, e.x, dot[4 * k4]);
-					dot[4 * k4 + 1] = fmaf(zv, e.y, dot[4 * k4 + 1]);
-					dot[4 * k4 + 2] = fmaf(zv, e.z, dot[4 * k4 + 2]);
-					dot[4 * k4 + 3] = fmaf(zv, e.w, dot[4 * k4 + 3]);
-				}
-			}
-			float best = INFINITY;
-			int bi = 0;
+					for (int kh = 0; kh < 4; ++kh) {
+						const float* row = din + d16_row(ic, 2 * d4 + kd, 2 * h4 + kh);
+						const float4 a = *reinterpret_cast<const float4*>(row);
+						const float4 b = *reinterpret_cast<const float4*>(row + 4);
+						const float x[10] = {0.f, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0.f};
+						const float* wp = wst + ((kd * 4 + kh) * 4) * 32 + og * 4;
 #pragma unroll
-			for (int k = 0; k < 64; ++k) {
-				const float dist = (zz + __ldg(w.emb_sq + q * 64 + k)) - 2.f * dot[k];
-				if (dist < best) {
-					best = dist;
-					bi = q * 64 + k;
+						for (int kw = 0; kw < 4; ++kw) {
+							const float4 w0 = *reinterpret_cast<const float4*>(wp + kw * 32);
+							const float wv[4] = {w0.x, w0.y, w0.z, w0.w};
+#pragma unroll
+							for (int j = 0; j < 4; ++j)
+#pragma unroll
+								for (int n = 0; n < 4; ++n) x32[n][j] = fmaf(x[2 * j + kw], wv[n], x32[n][j]);
+						}
+					}
 				}
+				pipe.release(lane);
 			}
-			vq_dist[q * 64 + p] = best;
-			vq_idx[q * 64 + p] = bi;
+#pragma unroll
+			for (int n = 0; n < 4; ++n) {
+				const float b = __ldg(w.down_b + og * 4 + n);
+#pragma unroll
+				for (int j = 0; j < 4; ++j) x32[n][j] += b;
+			}
+		}
+		__syncthreads();  // D16 is dead; region R now holds the 4^3 buffers
+
+		// ---- res_stack.0: ResidualBlock(32) ----
+		for (int i = tid; i < 2 * 32 * 20; i += kThreads) {  // H32 border rows: 20 per channel
+			const int b = i % 20, c = (i / 20) & 31, l = i / (20 * 32);
+			int dp, hq;
+			if (b < 6) { dp = 0; hq = b; }
+			else if (b < 12) { dp = 5; hq = b - 6; }
+			else { dp = 1 + ((b - 12) >> 1); hq = ((b - 12) & 1) * 5; }
+			*reinterpret_cast<float4*>(R + (l ? kH32Leaf1 : 0) + h32_row(c, dp, hq)) = make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+#pragma unroll
+		for (int n = 0; n < 4; ++n)
+#pragma unroll
+			for (int j = 0; j < 4; ++j) a4[n][j] = x32[n][j];
+		gn4_relu(a4, w.res32.gn1_w, w.res32.gn1_b, og);
+		store_h32(a4, H32, d4, h4, og);
+		__syncthreads();
+		conv4(a4, H32, d4, h4, og, pipe, tab, ring_ptr, lane);
+#pragma unroll
+		for (int n = 0; n < 4; ++n) {
+			const float b = __ldg(w.res32.c1_b + og * 4 + n);
+#pragma unroll
+			for (int j = 0; j < 4; ++j) a4[n][j] += b;
+		}
+		gn4_relu(a4, w.res32.gn2_w, w.res32.gn2_b, og);
+		__syncthreads();  // conv1's reads of H32 are complete everywhere
+		store_h32(a4, H32, d4, h4, og);
+		__syncthreads();
+		conv4(a4, H32, d4, h4, og, pipe, tab, ring_ptr, lane);
+#pragma unroll
+		for (int n = 0; n < 4; ++n) {
+			const float b = __ldg(w.res32.c2_b + og * 4 + n);
+#pragma unroll
+			for (int j = 0; j < 4; ++j) x32[n][j] = x32[n][j] + kResScale * (a4[n][j] + b);
+		}
+
+		// ---- attn: ChannelAttention(32) ----
+#pragma unroll
+		for (int n = 0; n < 4; ++n) {
+			const float s = half_warp_sum((x32[n][0] + x32[n][1]) + (x32[n][2] + x32[n][3]));
+			if ((lane & 15) == 0) att_mean[lf4 * 32 + og * 4 + n] = s * (1.f / 64.f);
 		}
 		__syncthreads();
-		if (tid < 64) {
-			float best = vq_dist[tid];
-			int bi = vq_idx[tid];
+		if (tid < 16) {
+			const int l = tid >> 3, j = tid & 7;
+			float s = 0.f;
+#pragma unroll 8
+			for (int c = 0; c < 32; ++c) s = fmaf(__ldg(w.fc0 + j * 32 + c), att_mean[l * 32 + c], s);
+			att_hid[l * 8 + j] = fmaxf(s, 0.f);
+		}
+		__syncthreads();
 #pragma unroll
-			for (int q = 1; q < 4; ++q) {
-				const float dq = vq_dist[q * 64 + tid];
-				if (dq < best) {
-					best = dq;
-					bi = vq_idx[q * 64 + tid];
+		for (int n = 0; n < 4; ++n) {
+			float s = 0.f;
+#pragma unroll
+			for (int j = 0; j < 8; ++j) s = fmaf(__ldg(w.fc2 + (og * 4 + n) * 8 + j), att_hid[lf4 * 8 + j], s);
+			const float y = sigmoid_f(s);
+			*reinterpret_cast<float4*>(X32s + (og * 4 + n) * 128 + lf4 * 64 + (d4 * 4 + h4) * 4) =
+			    make_float4(x32[n][0] * y, x32[n][1] * y, x32[n][2] * y, x32[n][3] * y);
+		}
+		__syncthreads();
+
+		// ---- proj: Conv3d(32,128,k1): lane -> 4 positions (of the 128 of both leaves), warp -> 16 channels ----
+		{
+			float z[16][4];
+#pragma unroll
+			for (int n = 0; n < 16; ++n)
+#pragma unroll
+				for (int j = 0; j < 4; ++j) z[n][j] = 0.f;
+#pragma unroll 1
+			for (int u = 0; u < 2; ++u) {
+				const float* wst = pipe.acquire(tab, ring_ptr);
+#pragma unroll 4
+				for (int i = 0; i < 16; ++i) {
+					const float4 xv = *reinterpret_cast<const float4*>(X32s + (u * 16 + i) * 128 + lane * 4);
+					const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+					for (int q = 0; q < 4; ++q) {
+						const float4 w0 = *reinterpret_cast<const float4*>(wst + i * 128 + warp * 16 + q * 4);
+						const float wv[4] = {w0.x, w0.y, w0.z, w0.w};
+#pragma unroll
+						for (int n = 0; n < 4; ++n)
+#pragma unroll
+							for (int j = 0; j < 4; ++j) z[q * 4 + n][j] = fmaf(x[j], wv[n], z[q * 4 + n][j]);
+					}
+				}
+				pipe.release(lane);
+			}
+#pragma unroll
+			for (int n = 0; n < 16; ++n) {
+				const float b = __ldg(w.proj_b + warp * 16 + n);
+				*reinterpret_cast<float4*>(Z + (warp * 16 + n) * 128 + lane * 4) = make_float4(z[n][0] + b, z[n][1] + b, z[n][2] + b, z[n][3] + b);
+			}
+		}
+		__syncthreads();
+
+		// ---- VQ: argmin_k (|z|^2 + |e_k|^2) - 2 z.e_k (save_for_inference.py:55-61), first minimum wins.
+		//      Two passes; in pass p warp `warp` scores codes warp*32 + p*16 .. +15 for all 128 positions. ----
+		float* cand_d = X32s;                                     // [16 code groups][128 pos]
+		int* cand_i = reinterpret_cast<int*>(X32s + 16 * 128);
+#pragma unroll 1
+		for (int pass = 0; pass < 2; ++pass) {
+			const int c0 = warp * 32 + pass * 16;
+			float dot[16][4];
+#pragma unroll
+			for (int n = 0; n < 16; ++n)
+#pragma unroll
+				for (int j = 0; j < 4; ++j) dot[n][j] = 0.f;
+			float zz[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+			for (int u = 0; u < 16; ++u) {
+				const float* wst = pipe.acquire(tab, ring_ptr);
+#pragma unroll 2
+				for (int i = 0; i < 8; ++i) {
+					const float4 zv = *reinterpret_cast<const float4*>(Z + (u * 8 + i) * 128 + lane * 4);
+					const float zq[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+					for (int j = 0; j < 4; ++j) zz[j] = fmaf(zq[j], zq[j], zz[j]);
+#pragma unroll
+					for (int q = 0; q < 4; ++q) {
+						const float4 e0 = *reinterpret_cast<const float4*>(wst + i * 256 + c0 + q * 4);
+						const float ev[4] = {e0.x, e0.y, e0.z, e0.w};
+#pragma unroll
+						for (int n = 0; n < 4; ++n)
+#pragma unroll
+							for (int j = 0; j < 4; ++j) dot[q * 4 + n][j] = fmaf(zq[j], ev[n], dot[q * 4 + n][j]);
+					}
+				}
+				pipe.release(lane);
+			}
+			float best[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+			int bi[4] = {0, 0, 0, 0};
+#pragma unroll
+			for (int n = 0; n < 16; ++n) {
+				const float esq = __ldg(w.emb_sq + c0 + n);
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const float dist = (zz[j] + esq) - 2.f * dot[n][j];
+					if (dist < best[j]) {
+						best[j] = dist;
+						bi[j] = c0 + n;
+					}
 				}
 			}
-			indices[leaf * 64 + tid] = (uint8_t)bi;  // latent position p = (d*4+h)*4+w, matching view(B,4,4,4)
+			const int cg = warp * 2 + pass;  // ascending code order across candidate groups
+			*reinterpret_cast<float4*>(cand_d + cg * 128 + lane * 4) = make_float4(best[0], best[1], best[2], best[3]);
+			*reinterpret_cast<int4*>(cand_i + cg * 128 + lane * 4) = make_int4(bi[0], bi[1], bi[2], bi[3]);
+		}
+		__syncthreads();
+		if (tid < 128) {
+			float best = cand_d[tid];
+			int bi = cand_i[tid];
+#pragma unroll
+			for (int cg = 1; cg < 16; ++cg) {
+				const float dv = cand_d[cg * 128 + tid];
+				if (dv < best) {
+					best = dv;
+					bi = cand_i[cg * 128 + tid];
+				}
+			}
+			const int64_t leaf = grp * 2 + (tid >> 6);
+			if (leaf < n_leaves) indices[leaf * 64 + (tid & 63)] = (uint8_t)bi;  // p = (d*4+h)*4+w == view(B,4,4,4)
 		}
 		__syncthreads();
 	}
@@ -223,15 +647,15 @@ encode_fp32_kernel(const EncoderWeights w, const float* __restrict__ leaves, int
 
 cudaError_t configure_encode_fp32() {
 	return cudaFuncSetAttribute(encode_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                            EncSmem::total * (int)sizeof(float));
+	                            kSmemFloats * (int)sizeof(float));
 }
 
-cudaError_t launch_encode_fp32(const EncoderWeights& w, const float* dev_leaves, int64_t n_leaves,
-                               uint8_t* dev_indices, int num_sms, cudaStream_t stream) {
+cudaError_t launch_encode_fp32(const EncoderWeights& w, const EncoderUnits& units, const float* dev_leaves,
+                               int64_t n_leaves, uint8_t* dev_indices, int num_sms, cudaStream_t stream) {
 	if (n_leaves <= 0) return cudaSuccess;
-	const int grid = (int)(n_leaves < (int64_t)num_sms ? n_leaves : (int64_t)num_sms);
-	encode_fp32_kernel<<<grid, kEncThreads, EncSmem::total * sizeof(float), stream>>>(w, dev_leaves, n_leaves,
-	                                                                                  dev_indices);
+	const int64_t groups = (n_leaves + 1) / 2;
+	const int grid = (int)(groups < (int64_t)num_sms ? groups : (int64_t)num_sms);
+	encode_fp32_kernel<<<grid, kThreads, kSmemFloats * sizeof(float), stream>>>(w, units, dev_leaves, n_leaves, dev_indices);
 	return cudaGetLastError();
 }
 

@@ -24,6 +24,17 @@ struct EncoderWeights {
 	const float *emb_sq;               // sum(embedding**2, dim=1) [256]
 };
 
+// The encoder consumes its weights as a fixed stream of "units" (<= 8 KB slices of the transposed tables
+// above) through a shared-memory ring: pre.0 (1), res16 conv1/conv2 (4+4, 4 input channels each), down (16,
+// one input channel each), res32 conv1/conv2 (16+16, 2 input channels each), proj (2, 16 input channels
+// each), then the transposed codebook twice (16+16, 8 embedding dims each; one pass per half of the codes).
+constexpr int kEncUnits = 91;
+struct EncoderUnits {
+	const float* base;         // the fp32 weight arena
+	uint32_t off[kEncUnits];   // byte offset of each unit from base (16-byte aligned)
+	uint32_t bytes[kEncUnits]; // multiple of 16, <= 8192
+};
+
 struct DecoderWeights {
 	const float *emb;                  // quantizer.embedding [256][128]
 	const float *stem_w, *stem_b;      // decoder.stem.0     [128][27][64]
@@ -35,8 +46,8 @@ struct DecoderWeights {
 };
 
 // fp32 CUDA-core kernels (encode_fp32.cu / decode_fp32.cu).  Return the cudaError of the launch.
-cudaError_t launch_encode_fp32(const EncoderWeights& w, const float* dev_leaves, int64_t n_leaves,
-                               uint8_t* dev_indices, int num_sms, cudaStream_t stream);
+cudaError_t launch_encode_fp32(const EncoderWeights& w, const EncoderUnits& units, const float* dev_leaves,
+                               int64_t n_leaves, uint8_t* dev_indices, int num_sms, cudaStream_t stream);
 cudaError_t launch_decode_fp32(const DecoderWeights& w, const uint8_t* dev_indices, int64_t n_leaves,
                                float* dev_voxels, int num_sms, cudaStream_t stream);
 cudaError_t configure_encode_fp32();
