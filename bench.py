@@ -236,6 +236,7 @@ def main():
     import torch
     import torch.distributed as dist
     from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec
+    from vqvdb_b200.sharding import gather_blocks
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -260,7 +261,7 @@ def main():
     vox = torch.empty((L, 1, 8, 8, 8), dtype=torch.float32, device=dev)
     gathered = None
     if world > 1 and rank == 0:
-        gathered = [torch.empty_like(vox) for _ in range(world)]
+        gathered = torch.empty((L * world, 1, 8, 8, 8), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
 
@@ -268,7 +269,7 @@ def main():
         codec.encode_device(x, L, idx, sp)
         codec.decode_device(idx, L, vox, sp)
         if world > 1:  # grid reassembly on rank 0: decoded blocks travel over NVLink (north_star)
-            dist.gather(vox, gathered, dst=0)
+            gather_blocks(vox, L * world, dst=0, out=gathered)
 
     def barrier():
         if world > 1:
@@ -340,11 +341,27 @@ def main():
         tensor_path = (dom == "decode" and codec.decode_path != "fp32")
         achieved = flop * L / (dom_ms / 1e3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
+        ffma_peak = 71.0   # TFLOP/s, measured on this part with tools/microbench/pipe_rates.cu (nominal 74.4)
+        hmma_peak = 555.0  # TFLOP/s, legacy mma.sync bf16 path, same micro-benchmark
+        enc_tf = FLOP_ENCODE * L / (enc_ms / 1e3) / 1e12
+        dec_tf = FLOP_DECODE * L / (dec_ms / 1e3) / 1e12
+        kernels = {
+            "encode_fp32_kernel": {"ms": enc_ms, "share_of_step": enc_ms / (enc_ms + dec_ms), "achieved_tflops": enc_tf,
+                                   "pipe": "fp32 FFMA", "pipe_peak_tflops": ffma_peak, "frac_of_pipe_peak": enc_tf / ffma_peak,
+                                   "frac_of_bf16_tensor_peak": enc_tf / peak, "algorithmic_mflop_per_leaf": FLOP_ENCODE / 1e6,
+                                   "hbm_gbs": BYTES_ENCODE * L / (enc_ms / 1e3) / 1e9},
+            "decode_mma_kernel": {"ms": dec_ms, "share_of_step": dec_ms / (enc_ms + dec_ms), "achieved_tflops": dec_tf,
+                                  "pipe": "tensor (mma.sync bf16)" if tensor_path else "fp32 FFMA",
+                                  "pipe_peak_tflops": hmma_peak if tensor_path else ffma_peak,
+                                  "frac_of_pipe_peak": dec_tf / (hmma_peak if tensor_path else ffma_peak),
+                                  "frac_of_bf16_tensor_peak": dec_tf / peak, "algorithmic_mflop_per_leaf": FLOP_DECODE / 1e6,
+                                  "hbm_gbs": BYTES_DECODE * L / (dec_ms / 1e3) / 1e9},
+        }
         line = {
             "metric": "leaves_per_sec_encode_decode", "value": value, "unit": "leaves/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 encode+VQ, %s decode" % ("bf16 operands/f32 accumulate" if tensor_path else "f32"),
+            "dtype": "f32 encode+VQ, %s decode" % ("bf16 operands/f32 accumulate" if codec.decode_path != "fp32" else "f32"),
             "data": "synthetic",
             "config": {"workload": "roundtrip_1M_float_leaves", "leaves_per_gpu": L, "weights": "shipped float model C=1 D=128 K=256",
                        "sharding": "leaf ranges, one rank per GPU" + (", NCCL gather of decoded blocks to rank 0" if world > 1 else ""),
@@ -356,7 +373,8 @@ def main():
                          "frac": achieved / peak, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % peaks["source"],
                          "hbm_gbs_nonbinding": (BYTES_DECODE if dom == "decode" else BYTES_ENCODE) * L / (dom_ms / 1e3) / 1e9,
-                         "note": "compute-bound path (34 kFLOP/B); %s kernel runs on %s" % (dom, "tcgen05 bf16" if tensor_path else "fp32 FFMA (CUDA-core peak ~74 TFLOP/s)")},
+                         "note": "compute-bound path (34 kFLOP/B); %s kernel runs on %s" % (dom, "bf16 tensor cores" if tensor_path else "fp32 FFMA (measured CUDA-core peak 71 TFLOP/s, so frac of ITS pipe is %.2f)" % (achieved / ffma_peak)),
+                         "kernels": kernels},
             "e2e": {"value": L * world * K / (e2e_ms / 1e3), "unit": "leaves/s",
                     "h2d_bytes_per_step": L * (2048 + 64), "d2h_bytes_per_step": L * (64 + 2048),
                     "api": "vqvdb_b200_encode + vqvdb_b200_decode on pinned host buffers", "checksum": e2e_checksum},

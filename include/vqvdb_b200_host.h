@@ -1,0 +1,55 @@
+/* vqvdb_b200_host.h — C ABI of the host layer (libvqvdb_b200_host.so): the .vqvdb v3 container and the
+ * OpenVDB-free compress/decompress batch loops, for callers that are not C++ (tests use it through ctypes).
+ *
+ * Replaces, above the backend boundary:
+ *   VDBStreamWriter / VDBStreamReader     /root/reference/src/Utils/VQVDB_Reader.cpp:20-162, 168-335
+ *   VQVAECodec::compress / decompress     /root/reference/src/orchestrator/VQVAECodec.cpp:78-134, 137-208
+ * A grid is passed as the flat result of the reference's leaf walk: origins int32[n][3] (openvdb::Coord) and
+ * voxels float32[n][512] (leaf.buffer().data()).  Every function returns 0 or a negative code; the message of
+ * the calling thread's last failure is vqvdb_host_last_error().
+ */
+#ifndef VQVDB_B200_HOST_H
+#define VQVDB_B200_HOST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQVDB_HOST_API __attribute__((visibility("default")))
+
+typedef struct vqvdb_host_reader vqvdb_host_reader;
+
+/* ---- container only (no GPU) ---- */
+/* Writes one file holding n_grids grids of already-encoded indices. names[g] NUL-terminated; transforms
+ * float[n_grids][16]; latent_shape int64[3]; counts[g] leaves; origins[g] int32[counts[g]][3]; indices[g]
+ * uint8[counts[g]][64]. */
+VQVDB_HOST_API int vqvdb_host_write_file(const char* path, int n_grids, const char* const* names, const float* transforms,
+                                         const int64_t* latent_shape, uint32_t num_embeddings, const int64_t* counts,
+                                         const int32_t* const* origins, const uint8_t* const* indices);
+VQVDB_HOST_API int vqvdb_host_reader_open(const char* path, vqvdb_host_reader** out);
+VQVDB_HOST_API void vqvdb_host_reader_close(vqvdb_host_reader* r);
+VQVDB_HOST_API int vqvdb_host_reader_num_grids(const vqvdb_host_reader* r);
+VQVDB_HOST_API uint32_t vqvdb_host_reader_num_embeddings(const vqvdb_host_reader* r);
+/* Advances to the next grid and reports its metadata. name_buf may be NULL. */
+VQVDB_HOST_API int vqvdb_host_reader_next_grid(vqvdb_host_reader* r, char* name_buf, int name_cap, float transform[16],
+                                               int64_t latent_shape[3], int64_t* n_blocks);
+/* Reads up to max_blocks records of the current grid; returns the count read (>= 0) or a negative code. */
+VQVDB_HOST_API int64_t vqvdb_host_reader_next_batch(vqvdb_host_reader* r, int64_t max_blocks, int32_t* origins, uint8_t* indices);
+
+/* ---- batch loops through the B200 backend (needs a GPU; no CPU fallback) ---- */
+VQVDB_HOST_API int vqvdb_host_compress(int cuda_device, const char* out_path, int n_grids, const char* const* names,
+                                       const float* transforms, const int64_t* counts, const int32_t* const* origins,
+                                       const float* const* voxels, int64_t batch_size);
+/* Decodes every grid of in_path.  Two-step: call with voxels == NULL to learn n_grids/counts (counts_cap entries),
+ * then again with voxels[g] / origins[g] buffers sized from counts. */
+VQVDB_HOST_API int vqvdb_host_decompress(int cuda_device, const char* in_path, int* n_grids, int64_t* counts, int counts_cap,
+                                         int32_t* const* origins, float* const* voxels, int64_t batch_size, int fp32_decode);
+
+VQVDB_HOST_API const char* vqvdb_host_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,34 @@
+"""Small driver for ncu captures: runs the encode and decode kernels a few times on synthetic leaves.
+
+    ncu --set full --clock-control none --import-source on -k regex:encode_fp32 -s 2 -c 1 \
+        -o gpurun_out/prof_encode python tools/profile_kernels.py --leaves 59200
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch  # noqa: E402
+
+from bench import gen_leaves_gpu  # noqa: E402
+from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--leaves", type=int, default=59200)   # 148 SMs x 400
+ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--decode-precision", default="default")
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+codec = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, decode_precision=a.decode_precision), BackendType.B200)
+assert codec is not None
+x = gen_leaves_gpu(a.leaves, dev, seed=0)
+idx = torch.empty((a.leaves, 4, 4, 4), dtype=torch.uint8, device=dev)
+vox = torch.empty((a.leaves, 1, 8, 8, 8), dtype=torch.float32, device=dev)
+sp = torch.cuda.current_stream().cuda_stream
+for _ in range(a.iters):
+    codec.encode_device(x, a.leaves, idx, sp)
+    codec.decode_device(idx, a.leaves, vox, sp)
+torch.cuda.synchronize()
+print("profiled %d leaves x %d iters, decode path %s" % (a.leaves, a.iters, codec.decode_path))
+codec.close()

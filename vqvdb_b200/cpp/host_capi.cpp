@@ -1,0 +1,156 @@
+// C ABI of the host layer (include/vqvdb_b200_host.h).
+#include "../../include/vqvdb_b200_host.h"
+
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "VQVAECodec.hpp"
+#include "vqvdb_file.hpp"
+
+namespace {
+thread_local std::string g_err;
+int fail(const std::exception& e) {
+	g_err = e.what();
+	return -1;
+}
+}  // namespace
+
+struct vqvdb_host_reader {
+	std::unique_ptr<vqvdb::VqvdbReader> reader;
+	std::vector<uint8_t> idx;
+	std::vector<vqvdb::LeafOrigin> org;
+};
+
+extern "C" {
+
+const char* vqvdb_host_last_error(void) { return g_err.c_str(); }
+
+int vqvdb_host_write_file(const char* path, int n_grids, const char* const* names, const float* transforms,
+                          const int64_t* latent_shape, uint32_t num_embeddings, const int64_t* counts,
+                          const int32_t* const* origins, const uint8_t* const* indices) {
+	try {
+		vqvdb::VqvdbWriter w(path);
+		for (int g = 0; g < n_grids; ++g) {
+			vqvdb::GridMetadata m;
+			m.name = names[g];
+			m.numEmbeddings = num_embeddings;
+			m.latentShape = {latent_shape[0], latent_shape[1], latent_shape[2]};
+			m.totalBlocks = (size_t)counts[g];
+			std::memcpy(m.transform, transforms + 16 * g, 64);
+			w.startGrid(m);
+			w.writeBatch(indices[g], reinterpret_cast<const vqvdb::LeafOrigin*>(origins[g]), (size_t)counts[g]);
+			w.endGrid();
+		}
+		w.close();
+		return 0;
+	} catch (const std::exception& e) {
+		return fail(e);
+	}
+}
+
+int vqvdb_host_reader_open(const char* path, vqvdb_host_reader** out) {
+	try {
+		auto r = std::make_unique<vqvdb_host_reader>();
+		r->reader = std::make_unique<vqvdb::VqvdbReader>(path);
+		*out = r.release();
+		return 0;
+	} catch (const std::exception& e) {
+		*out = nullptr;
+		return fail(e);
+	}
+}
+
+void vqvdb_host_reader_close(vqvdb_host_reader* r) { delete r; }
+int vqvdb_host_reader_num_grids(const vqvdb_host_reader* r) { return r ? (int)r->reader->numGrids() : -1; }
+uint32_t vqvdb_host_reader_num_embeddings(const vqvdb_host_reader* r) { return r ? r->reader->numEmbeddings() : 0; }
+
+int vqvdb_host_reader_next_grid(vqvdb_host_reader* r, char* name_buf, int name_cap, float transform[16],
+                                int64_t latent_shape[3], int64_t* n_blocks) {
+	try {
+		const vqvdb::GridMetadata m = r->reader->nextGridMetadata();
+		if (name_buf && name_cap > 0) {
+			std::strncpy(name_buf, m.name.c_str(), (size_t)name_cap - 1);
+			name_buf[name_cap - 1] = 0;
+		}
+		std::memcpy(transform, m.transform, 64);
+		for (int i = 0; i < 3; ++i) latent_shape[i] = i < (int)m.latentShape.size() ? m.latentShape[i] : 1;
+		*n_blocks = (int64_t)m.totalBlocks;
+		return 0;
+	} catch (const std::exception& e) {
+		return fail(e);
+	}
+}
+
+int64_t vqvdb_host_reader_next_batch(vqvdb_host_reader* r, int64_t max_blocks, int32_t* origins, uint8_t* indices) {
+	try {
+		const size_t n = r->reader->nextBatch((size_t)max_blocks, r->idx, r->org);
+		if (n) {
+			std::memcpy(origins, r->org.data(), n * sizeof(vqvdb::LeafOrigin));
+			std::memcpy(indices, r->idx.data(), r->idx.size());
+		}
+		return (int64_t)n;
+	} catch (const std::exception& e) {
+		return fail(e);
+	}
+}
+
+int vqvdb_host_compress(int cuda_device, const char* out_path, int n_grids, const char* const* names, const float* transforms,
+                        const int64_t* counts, const int32_t* const* origins, const float* const* voxels, int64_t batch_size) {
+	try {
+		CodecConfig cfg;
+		cfg.device = CodecConfig::Device::CUDA;
+		cfg.cudaDevice = cuda_device;
+		VQVAECodec codec(IVQVAECodec::create(cfg, BackendType::B200));
+		std::vector<LeafGrid> grids((size_t)n_grids);
+		for (int g = 0; g < n_grids; ++g) {
+			grids[g].name = names[g];
+			std::memcpy(grids[g].transform, transforms + 16 * g, 64);
+			const auto* o = reinterpret_cast<const vqvdb::LeafOrigin*>(origins[g]);
+			grids[g].origins.assign(o, o + counts[g]);
+			grids[g].voxels.assign(voxels[g], voxels[g] + (size_t)counts[g] * 512);
+		}
+		codec.compress(grids, out_path, (size_t)batch_size);
+		return 0;
+	} catch (const std::exception& e) {
+		return fail(e);
+	}
+}
+
+int vqvdb_host_decompress(int cuda_device, const char* in_path, int* n_grids, int64_t* counts, int counts_cap,
+                          int32_t* const* origins, float* const* voxels, int64_t batch_size, int fp32_decode) {
+	try {
+		if (!voxels) {  // size query: container only, no GPU needed
+			vqvdb::VqvdbReader rd(in_path);
+			int g = 0;
+			while (rd.hasNextGrid()) {
+				const vqvdb::GridMetadata m = rd.nextGridMetadata();
+				if (g < counts_cap) counts[g] = (int64_t)m.totalBlocks;
+				++g;
+				std::vector<uint8_t> i;
+				std::vector<vqvdb::LeafOrigin> o;
+				while (rd.hasNext()) rd.nextBatch(1 << 20, i, o);
+			}
+			*n_grids = g;
+			return 0;
+		}
+		CodecConfig cfg;
+		cfg.device = CodecConfig::Device::CUDA;
+		cfg.cudaDevice = cuda_device;
+		cfg.fp32Decode = fp32_decode != 0;
+		VQVAECodec codec(IVQVAECodec::create(cfg, BackendType::B200));
+		std::vector<LeafGrid> grids;
+		codec.decompress(in_path, grids, (size_t)batch_size);
+		*n_grids = (int)grids.size();
+		for (size_t g = 0; g < grids.size() && (int)g < counts_cap; ++g) {
+			counts[g] = (int64_t)grids[g].leafCount();
+			std::memcpy(origins[g], grids[g].origins.data(), grids[g].origins.size() * sizeof(vqvdb::LeafOrigin));
+			std::memcpy(voxels[g], grids[g].voxels.data(), grids[g].voxels.size() * sizeof(float));
+		}
+		return 0;
+	} catch (const std::exception& e) {
+		return fail(e);
+	}
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+"""Leaf-range sharding across the GPUs of one box, one process per GPU.
+
+Leaves are independent (GroupNorm and attention are per leaf), so rank r of G simply owns the contiguous
+range [r*N/G, (r+1)*N/G): origins and indices stay in file order and reassembly is a concatenation.  The
+only exchange step on the path is the gather of decoded blocks (2048 B/leaf) — or of indices (64 B/leaf) on
+the encode side — to the rank that rebuilds the grid; it runs over torch.distributed (NCCL over NVLink on
+GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def leaf_range(rank: int, world: int, n_leaves: int) -> Tuple[int, int]:
+    """Contiguous, balanced: sizes differ by at most one leaf and concatenate to [0, n)."""
+    if not 0 <= rank < world:
+        raise ValueError("rank %d outside world of %d" % (rank, world))
+    return (rank * n_leaves) // world, ((rank + 1) * n_leaves) // world
+
+
+def shard_sizes(world: int, n_leaves: int) -> List[int]:
+    return [leaf_range(r, world, n_leaves)[1] - leaf_range(r, world, n_leaves)[0] for r in range(world)]
+
+
+def gather_blocks(local: torch.Tensor, n_leaves: int, dst: int = 0, group=None,
+                  out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Gathers per-rank shards (leading dim = this rank's leaf count) into file order on `dst`.
+
+    Ragged shards are handled by padding to the largest shard for the collective and slicing on arrival,
+    so a single gather call moves everything.  Returns the [n_leaves, ...] tensor on dst, None elsewhere.
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = shard_sizes(world, n_leaves)
+    if local.shape[0] != sizes[rank]:
+        raise ValueError("rank %d holds %d leaves, expected %d" % (rank, local.shape[0], sizes[rank]))
+    biggest = max(sizes)
+    if min(sizes) == biggest:  # equal shards: receive straight into slices of the result, no staging copy
+        if rank == dst and out is None:
+            out = local.new_empty((n_leaves,) + tuple(local.shape[1:]))
+        bufs = [out[r * biggest:(r + 1) * biggest] for r in range(world)] if rank == dst else None
+        dist.gather(local.contiguous(), bufs, dst=dst, group=group)
+        return out if rank == dst else None
+    send = local
+    if local.shape[0] != biggest:
+        send = local.new_zeros((biggest,) + tuple(local.shape[1:]))
+        send[: local.shape[0]] = local
+    bufs = None
+    if rank == dst:
+        bufs = [local.new_empty((biggest,) + tuple(local.shape[1:])) for _ in range(world)]
+    dist.gather(send.contiguous(), bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    if out is None:
+        out = local.new_empty((n_leaves,) + tuple(local.shape[1:]))
+    for r in range(world):
+        lo, hi = leaf_range(r, world, n_leaves)
+        out[lo:hi] = bufs[r][: hi - lo]
+    return out
