@@ -338,7 +338,8 @@ def main():
         dom = "decode" if dec_ms >= enc_ms else "encode"
         dom_ms = max(dec_ms, enc_ms)
         flop = FLOP_DECODE if dom == "decode" else FLOP_ENCODE
-        tensor_path = (dom == "decode" and codec.decode_path != "fp32")
+        tensor_path = codec.decode_path != "fp32"
+        dom_on_tensor = (dom == "decode" and tensor_path)
         achieved = flop * L / (dom_ms / 1e3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         ffma_peak = 71.0   # TFLOP/s, measured on this part with tools/microbench/pipe_rates.cu (nominal 74.4)
@@ -373,7 +374,7 @@ def main():
                          "frac": achieved / peak, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % peaks["source"],
                          "hbm_gbs_nonbinding": (BYTES_DECODE if dom == "decode" else BYTES_ENCODE) * L / (dom_ms / 1e3) / 1e9,
-                         "note": "compute-bound path (34 kFLOP/B); %s kernel runs on %s" % (dom, "bf16 tensor cores" if tensor_path else "fp32 FFMA (measured CUDA-core peak 71 TFLOP/s, so frac of ITS pipe is %.2f)" % (achieved / ffma_peak)),
+                         "note": "compute-bound path (34 kFLOP/B); %s kernel runs on %s" % (dom, "bf16 tensor cores" if dom_on_tensor else "fp32 FFMA (measured CUDA-core peak 71 TFLOP/s, so frac of ITS pipe is %.2f)" % (achieved / ffma_peak)),
                          "kernels": kernels},
             "e2e": {"value": L * world * K / (e2e_ms / 1e3), "unit": "leaves/s",
                     "h2d_bytes_per_step": L * (2048 + 64), "d2h_bytes_per_step": L * (64 + 2048),
