@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -175,8 +176,16 @@ void upload_float_model(vqvdb_b200_codec& c, const WeightPack& p) {
 		}
 		emb_sq[k] = s;
 	}
+	std::vector<float> emb_norm(256);
+	for (int k = 0; k < 256; ++k) {
+		double s2 = 0.0;
+		for (int d = 0; d < 128; ++d) s2 += (double)emb.data[k * 128 + d] * emb.data[k * 128 + d];
+		emb_norm[k] = std::nextafter((float)std::sqrt(s2), INFINITY);  // never under-estimates |e_k|
+	}
 	ab.add(&e.emb_t, emb_t);
 	ab.add(&e.emb_sq, emb_sq);
+	ab.add(&e.emb_norm, emb_norm);
+	ab.add(&e.emb, emb);
 
 	auto& d = c.dec;
 	ab.add(&d.emb, emb);
@@ -193,36 +202,39 @@ void upload_float_model(vqvdb_b200_codec& c, const WeightPack& p) {
 	ab.add(&d.fin_b, p.get("decoder.final.bias"));
 	c.arena = ab.upload();
 
-	// encoder weight-unit stream: slices of the transposed tables, in the order the kernel consumes them
-	{
-		auto& U = c.enc_units;
-		U.base = c.arena;
-		int n = 0;
-		auto add = [&](const float* table, size_t first_float, size_t n_floats) {
-			if (n >= vqvdb::kEncUnits) throw std::logic_error("encoder unit table overflow");
-			U.off[n] = (uint32_t)((table + first_float - c.arena) * sizeof(float));
-			U.bytes[n] = (uint32_t)(n_floats * sizeof(float));
-			if (U.bytes[n] > 8192 || (U.bytes[n] & 15) || (U.off[n] & 15)) throw std::logic_error("encoder unit misaligned");
-			++n;
-		};
-		add(e.pre_w, 0, 27 * 16);
-		for (const float* t : {e.res16.c1_w, e.res16.c2_w})
-			for (int q = 0; q < 4; ++q) add(t, (size_t)q * 4 * 27 * 16, 4 * 27 * 16);
-		for (int ic = 0; ic < 16; ++ic) add(e.down_w, (size_t)ic * 64 * 32, 64 * 32);
-		for (const float* t : {e.res32.c1_w, e.res32.c2_w})
-			for (int q = 0; q < 16; ++q) add(t, (size_t)q * 2 * 27 * 32, 2 * 27 * 32);
-		for (int q = 0; q < 2; ++q) add(e.proj_w, (size_t)q * 16 * 128, 16 * 128);
-		for (int pass = 0; pass < 2; ++pass)
-			for (int q = 0; q < 16; ++q) add(e.emb_t, (size_t)q * 8 * 256, 8 * 256);
-		if (n != vqvdb::kEncUnits) throw std::logic_error("encoder unit table size mismatch");
-	}
-
-	// tensor-core decoder: bf16 unit stream + bf16 codebook; fp32 vectors are shared with the fp32 path
+	// tensor-core decoder: bf16 unit stream + bf16 codebook; fp32 vectors are shared with the fp32 path.
+	// The encoder's VQ shortlist pass reads the codebook as 8 more bf16 units from the same allocation.
 	const std::vector<uint8_t> units = vqvdb::build_decoder_units(p);
 	const std::vector<uint16_t> cb = vqvdb::build_codebook_bf16(p);
-	CUDA_TRY(cudaMalloc(&c.mma_arena, units.size() + cb.size() * 2));
+	const std::vector<uint8_t> cb_units = vqvdb::build_codebook_units(p);
+	CUDA_TRY(cudaMalloc(&c.mma_arena, units.size() + cb.size() * 2 + cb_units.size()));
 	CUDA_TRY(cudaMemcpy(c.mma_arena, units.data(), units.size(), cudaMemcpyHostToDevice));
 	CUDA_TRY(cudaMemcpy(c.mma_arena + units.size(), cb.data(), cb.size() * 2, cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMemcpy(c.mma_arena + units.size() + cb.size() * 2, cb_units.data(), cb_units.size(), cudaMemcpyHostToDevice));
+
+	// encoder weight-unit stream: slices of the transposed fp32 tables, then the bf16 codebook tiles,
+	// in the order the kernel consumes them
+	{
+		auto& U = c.enc_units;
+		int n = 0;
+		auto add = [&](const void* ptr, size_t bytes) {
+			if (n >= vqvdb::kEncUnits) throw std::logic_error("encoder unit table overflow");
+			U.ptr[n] = ptr;
+			U.bytes[n] = (uint32_t)bytes;
+			if (bytes > 8192 || (bytes & 15) || (reinterpret_cast<uintptr_t>(ptr) & 15)) throw std::logic_error("encoder unit misaligned");
+			++n;
+		};
+		add(e.pre_w, 27 * 16 * 4);
+		for (const float* t : {e.res16.c1_w, e.res16.c2_w})
+			for (int q = 0; q < 4; ++q) add(t + (size_t)q * 4 * 27 * 16, 4 * 27 * 16 * 4);
+		for (int ic = 0; ic < 16; ++ic) add(e.down_w + (size_t)ic * 64 * 32, 64 * 32 * 4);
+		for (const float* t : {e.res32.c1_w, e.res32.c2_w})
+			for (int q = 0; q < 16; ++q) add(t + (size_t)q * 2 * 27 * 32, 2 * 27 * 32 * 4);
+		for (int q = 0; q < 2; ++q) add(e.proj_w + (size_t)q * 16 * 128, 16 * 128 * 4);
+		const uint8_t* cbu = c.mma_arena + units.size() + cb.size() * 2;
+		for (int q = 0; q < 8; ++q) add(cbu + (size_t)q * 8192, 8192);
+		if (n != vqvdb::kEncUnits) throw std::logic_error("encoder unit table size mismatch");
+	}
 	auto& m = c.dec_mma;
 	m.units = c.mma_arena;
 	m.emb_bf16 = reinterpret_cast<const __nv_bfloat16*>(c.mma_arena + units.size());

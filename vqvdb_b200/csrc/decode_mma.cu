@@ -22,6 +22,7 @@
 
 #include "decode_mma.cuh"
 #include "leaf_ops.cuh"
+#include "ptx_utils.cuh"
 
 namespace vqvdb {
 
@@ -44,67 +45,6 @@ constexpr uint32_t kOffScratch = kOffFinW + 864 * 4;                // per warp:
 constexpr uint32_t kScratchBytes = 96 * 4;
 constexpr uint32_t kSmemBytes = kOffScratch + kLeavesPerCta * kScratchBytes;
 static_assert(kSmemBytes <= 227 * 1024, "decode_mma smem budget");
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-	asm volatile(
-	    "{\n"
-	    ".reg .pred p;\n"
-	    "LAB_WAIT_%=:\n"
-	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-	    "@p bra LAB_DONE_%=;\n"
-	    "bra LAB_WAIT_%=;\n"
-	    "LAB_DONE_%=:\n"
-	    "}\n" ::"r"(bar),
-	    "r"(parity)
-	    : "memory");
-}
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-	uint32_t ok;
-	asm volatile(
-	    "{\n"
-	    ".reg .pred p;\n"
-	    "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-	    "selp.u32 %0, 1, 0, p;\n"
-	    "}\n"
-	    : "=r"(ok)
-	    : "r"(bar), "r"(parity)
-	    : "memory");
-	return ok != 0;
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-	             "l"(src), "r"(bytes), "r"(bar)
-	             : "memory");
-}
-__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-	asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-	             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-	             : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                         uint32_t b1) {
-	asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-	             : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-	             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-	__nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-	return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ float2 unpack_bf16(uint32_t w) {
-	return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w));
-}
 
 // Position in the weight-unit stream.  Every warp consumes the same sequence; `unit` counts units since
 // kernel start, so stage = unit % kStages and the mbarrier parity = (unit / kStages) & 1.
@@ -303,7 +243,7 @@ decode_mma_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices
 			mbar_init(bars + s * 8, 1);                          // full: one expect_tx arrival by the producer
 			mbar_init(bars + (kStages + s) * 8, kLeavesPerCta);  // empty: one arrival per consumer warp
 		}
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		mbar_fence_init();
 	}
 	__syncthreads();
 

@@ -33,6 +33,9 @@ struct DecoderMmaWeights {
 // Builds the unit stream and the bf16 codebook on the host (round-to-nearest-even).
 std::vector<uint8_t> build_decoder_units(const WeightPack& pack);
 std::vector<uint16_t> build_codebook_bf16(const WeightPack& pack);
+// The codebook as 8 weight units [64 codes][64 dims] (code group major, then dim half) for the encoder's
+// tensor-core VQ shortlist pass: same tile format as the decoder's units.
+std::vector<uint8_t> build_codebook_units(const WeightPack& pack);
 
 cudaError_t configure_decode_mma();
 // tap_stage >= 0 additionally writes the activation after stage {0: stem+GN+ReLU, 1: residual block,

@@ -43,6 +43,21 @@ std::vector<uint8_t> build_decoder_units(const WeightPack& p) {
 	return out;
 }
 
+std::vector<uint8_t> build_codebook_units(const WeightPack& p) {
+	const PackTensor& e = p.get("quantizer.embedding");  // [256][128]
+	std::vector<uint8_t> out((size_t)8 * 8192);
+	uint8_t* u = out.data();
+	for (int cg = 0; cg < 4; ++cg)
+		for (int dh = 0; dh < 2; ++dh, u += 8192)
+			for (int n = 0; n < 64; ++n)
+				for (int k = 0; k < 64; ++k) {
+					const uint16_t b = f32_to_bf16_rn(e.data[(size_t)(cg * 64 + n) * 128 + dh * 64 + k]);
+					const size_t off = (size_t)n * 128 + ((size_t)((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
+					std::memcpy(u + off, &b, 2);
+				}
+	return out;
+}
+
 std::vector<uint16_t> build_codebook_bf16(const WeightPack& p) {
 	const PackTensor& e = p.get("quantizer.embedding");
 	std::vector<uint16_t> out(e.numel());

@@ -14,11 +14,12 @@
 //   * 8^3 layers: thread tile = one 8-voxel row x 8 output channels (64 accumulators); the residual stream
 //     stays in registers across the whole residual block, only the conv INPUT lives in shared memory;
 //   * weights stream from L2 through a 6-stage shared-memory ring (1-D TMA bulk copies, mbarrier
-//     complete_tx) in 91 fixed "units" that both leaves share; a warp reads them as broadcast LDS.128;
+//     complete_tx) in 67 fixed "units" that both leaves share; a warp reads them as broadcast LDS.128;
 //   * shared-memory layouts are chosen so every LDS.128 of activations is bank-conflict free
 //     (half-row swap keyed on bit 2 of the row index at 8^3; parity-split rows for the stride-2 conv).
 // Accumulation order per output is cin, kd, kh, kw ascending — the same as oracle/vqvae_oracle.c.
 #include "leaf_ops.cuh"
+#include "ptx_utils.cuh"
 #include "model.cuh"
 
 namespace vqvdb {
@@ -43,48 +44,6 @@ constexpr int kSmemFloats = kBarOff + 2 * kStages * 2;
 static_assert(kSmemFloats * 4 <= 227 * 1024, "encoder smem budget");
 static_assert(2 * 4608 + 16 <= kX32s && 16384 <= kX32s, "H32 / Z overlays stay clear of the X32 staging area");
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-	asm volatile(
-	    "{\n"
-	    ".reg .pred p;\n"
-	    "LAB_WAIT_%=:\n"
-	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-	    "@p bra LAB_DONE_%=;\n"
-	    "bra LAB_WAIT_%=;\n"
-	    "LAB_DONE_%=:\n"
-	    "}\n" ::"r"(bar),
-	    "r"(parity)
-	    : "memory");
-}
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-	uint32_t ok;
-	asm volatile(
-	    "{\n"
-	    ".reg .pred p;\n"
-	    "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-	    "selp.u32 %0, 1, 0, p;\n"
-	    "}\n"
-	    : "=r"(ok)
-	    : "r"(bar), "r"(parity)
-	    : "memory");
-	return ok != 0;
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-	             "l"(src), "r"(bytes), "r"(bar)
-	             : "memory");
-}
-
 // Weight-unit stream.  Every warp consumes the same sequence; thread 0 is also the producer.
 struct Pipe {
 	uint32_t unit = 0, issued = 0, total = 0;
@@ -102,7 +61,7 @@ struct Pipe {
 			const uint32_t u = issued % kEncUnits;
 			const uint32_t bytes = tab.bytes[u];
 			mbar_arrive_expect_tx(full, bytes);
-			tma_load_1d(ring + s * kStageBytes, reinterpret_cast<const uint8_t*>(tab.base) + tab.off[u], bytes, full);
+			tma_load_1d(ring + s * kStageBytes, tab.ptr[u], bytes, full);
 			++issued;
 		}
 	}
@@ -333,7 +292,7 @@ encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* 
 			mbar_init(bars + s * 8, 1);
 			mbar_init(bars + (kStages + s) * 8, kThreads / 32);
 		}
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		mbar_fence_init();
 	}
 	Pipe pipe;
 	pipe.ring = smem_u32(smem);
@@ -573,71 +532,148 @@ encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* 
 		__syncthreads();
 
 		// ---- VQ: argmin_k (|z|^2 + |e_k|^2) - 2 z.e_k (save_for_inference.py:55-61), first minimum wins.
-		//      Two passes; in pass p warp `warp` scores codes warp*32 + p*16 .. +15 for all 128 positions. ----
-		float* cand_d = X32s;                                     // [16 code groups][128 pos]
-		int* cand_i = reinterpret_cast<int*>(X32s + 16 * 128);
-#pragma unroll 1
-		for (int pass = 0; pass < 2; ++pass) {
-			const int c0 = warp * 32 + pass * 16;
-			float dot[16][4];
+		// Two stages that give exactly the fp32 result at a fraction of its cost:
+		//  1. approximate scores a_k = |e_k|^2 - 2 bf16(z).bf16(e_k) for all 128 x 256 (position, code) pairs on the
+		//     tensor cores (one m16n8k16 pass, fp32 accumulate), with the rigorous bound
+		//     |a_k - (true score)| <= B_k = 2^-7 * 1.07 * |z| * |e_k| + 1e-4  (bf16 unit roundoff 2^-9 per operand);
+		//  2. every code whose lower bound a_k - B_k does not exceed min_j (a_j + B_j) is re-scored with the
+		//     reference's fp32 formula, sequential in d.  The fp32 arg-min and all its fp32 ties are provably in
+		//     that shortlist (1-20 codes per position), so the index equals a full fp32 scan's.
+		{
+			uint8_t* Zb = reinterpret_cast<uint8_t*>(X32s);  // bf16 [128 pos][128 d], 256-B rows, 16-B chunks swizzled
+			for (int i = tid; i < 128 * 16; i += kThreads) {
+				const int pos = i & 127, c = i >> 7;
+				float v[8];
 #pragma unroll
-			for (int n = 0; n < 16; ++n)
+				for (int q = 0; q < 8; ++q) v[q] = Z[(c * 8 + q) * 128 + pos];
+				uint4 pk;
+				pk.x = pack_bf16(v[0], v[1]);
+				pk.y = pack_bf16(v[2], v[3]);
+				pk.z = pack_bf16(v[4], v[5]);
+				pk.w = pack_bf16(v[6], v[7]);
+				const int pc = (c & 8) | ((c & 7) ^ (pos & 7));
+				*reinterpret_cast<uint4*>(Zb + pos * 256 + pc * 16) = pk;
+			}
+			__syncthreads();
+
+			const int g = lane >> 2, t = lane & 3;
+			const int m0 = warp * 16;
+			float sc[32][4];  // sc[nt][e]: e=0,1 -> row m0+g, codes nt*8+2t+{0,1}; e=2,3 -> row m0+g+8
 #pragma unroll
-				for (int j = 0; j < 4; ++j) dot[n][j] = 0.f;
-			float zz[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-			for (int u = 0; u < 16; ++u) {
-				const float* wst = pipe.acquire(tab, ring_ptr);
-#pragma unroll 2
-				for (int i = 0; i < 8; ++i) {
-					const float4 zv = *reinterpret_cast<const float4*>(Z + (u * 8 + i) * 128 + lane * 4);
-					const float zq[4] = {zv.x, zv.y, zv.z, zv.w};
+			for (int nt = 0; nt < 32; ++nt)
 #pragma unroll
-					for (int j = 0; j < 4; ++j) zz[j] = fmaf(zq[j], zq[j], zz[j]);
+				for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f;
+			{
+				const uint32_t zb_base = smem_u32(Zb);
+				const uint32_t arow = m0 + (lane & 15), khalf = lane >> 4;
+				const uint32_t bn = ((lane >> 4) << 3) + (lane & 7), bpar = (lane >> 3) & 1;
 #pragma unroll
-					for (int q = 0; q < 4; ++q) {
-						const float4 e0 = *reinterpret_cast<const float4*>(wst + i * 256 + c0 + q * 4);
-						const float ev[4] = {e0.x, e0.y, e0.z, e0.w};
+				for (int cg = 0; cg < 4; ++cg) {
 #pragma unroll
-						for (int n = 0; n < 4; ++n)
+					for (int dh = 0; dh < 2; ++dh) {
+						const uint32_t wbase = smem_u32(pipe.acquire(tab, ring_ptr));
 #pragma unroll
-							for (int j = 0; j < 4; ++j) dot[q * 4 + n][j] = fmaf(zq[j], ev[n], dot[q * 4 + n][j]);
+						for (int kk = 0; kk < 4; ++kk) {
+							const uint32_t c = dh * 8 + kk * 2 + khalf;
+							uint32_t a0, a1, a2, a3;
+							ldmatrix_x4(zb_base + arow * 256 + (((c & 8) | ((c & 7) ^ (arow & 7))) << 4), a0, a1, a2, a3);
+#pragma unroll
+							for (int j = 0; j < 4; ++j) {
+								const uint32_t n = j * 16 + bn, bchunk = kk * 2 + bpar;
+								uint32_t b0, b1, b2, b3;
+								ldmatrix_x4(wbase + n * 128 + ((bchunk ^ (n & 7u)) << 4), b0, b1, b2, b3);
+								mma_bf16(sc[cg * 8 + 2 * j], a0, a1, a2, a3, b0, b1);
+								mma_bf16(sc[cg * 8 + 2 * j + 1], a0, a1, a2, a3, b2, b3);
+							}
+						}
+						pipe.release(lane);
 					}
 				}
-				pipe.release(lane);
 			}
-			float best[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-			int bi[4] = {0, 0, 0, 0};
+			// exact |z|^2 of this lane's two rows, sequential in d like the re-scoring below
+			const int p0 = m0 + g, p1 = p0 + 8;
+			float zz0 = 0.f, zz1 = 0.f;
+#pragma unroll 8
+			for (int d = 0; d < 128; ++d) {
+				const float q0 = Z[d * 128 + p0], q1 = Z[d * 128 + p1];
+				zz0 = fmaf(q0, q0, zz0);
+				zz1 = fmaf(q1, q1, zz1);
+			}
+			const float cb0 = 0.0078125f * 1.07f * sqrtf(zz0), cb1 = 0.0078125f * 1.07f * sqrtf(zz1);
+			// scores -> a_k, and the row-wise minimum of the upper bounds
+			float umin0 = INFINITY, umin1 = INFINITY;
 #pragma unroll
-			for (int n = 0; n < 16; ++n) {
-				const float esq = __ldg(w.emb_sq + c0 + n);
+			for (int nt = 0; nt < 32; ++nt) {
+				const float2 esq = __ldg(reinterpret_cast<const float2*>(w.emb_sq + nt * 8 + 2 * t));
+				const float2 eno = __ldg(reinterpret_cast<const float2*>(w.emb_norm + nt * 8 + 2 * t));
+				sc[nt][0] = esq.x - 2.f * sc[nt][0];
+				sc[nt][1] = esq.y - 2.f * sc[nt][1];
+				sc[nt][2] = esq.x - 2.f * sc[nt][2];
+				sc[nt][3] = esq.y - 2.f * sc[nt][3];
+				umin0 = fminf(umin0, fminf(sc[nt][0] + (cb0 * eno.x + 1e-4f), sc[nt][1] + (cb0 * eno.y + 1e-4f)));
+				umin1 = fminf(umin1, fminf(sc[nt][2] + (cb1 * eno.x + 1e-4f), sc[nt][3] + (cb1 * eno.y + 1e-4f)));
+			}
+			umin0 = fminf(umin0, __shfl_xor_sync(0xffffffffu, umin0, 1));
+			umin0 = fminf(umin0, __shfl_xor_sync(0xffffffffu, umin0, 2));
+			umin1 = fminf(umin1, __shfl_xor_sync(0xffffffffu, umin1, 1));
+			umin1 = fminf(umin1, __shfl_xor_sync(0xffffffffu, umin1, 2));
+			// shortlist masks: bit (nt*2 + e) of mask0 / mask1
+			unsigned long long mask0 = 0ull, mask1 = 0ull;
 #pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					const float dist = (zz[j] + esq) - 2.f * dot[n][j];
-					if (dist < best[j]) {
-						best[j] = dist;
-						bi[j] = c0 + n;
+			for (int nt = 0; nt < 32; ++nt) {
+				const float2 eno = __ldg(reinterpret_cast<const float2*>(w.emb_norm + nt * 8 + 2 * t));
+				if (sc[nt][0] - (cb0 * eno.x + 1e-4f) <= umin0) mask0 |= 1ull << (nt * 2);
+				if (sc[nt][1] - (cb0 * eno.y + 1e-4f) <= umin0) mask0 |= 1ull << (nt * 2 + 1);
+				if (sc[nt][2] - (cb1 * eno.x + 1e-4f) <= umin1) mask1 |= 1ull << (nt * 2);
+				if (sc[nt][3] - (cb1 * eno.y + 1e-4f) <= umin1) mask1 |= 1ull << (nt * 2 + 1);
+			}
+			// exact fp32 re-scoring of the shortlist (ascending code order within the lane)
+			float best0 = INFINITY, best1 = INFINITY;
+			int bi0 = 0x7fffffff, bi1 = 0x7fffffff;
+#pragma unroll 1
+			for (int rr = 0; rr < 2; ++rr) {
+				unsigned long long mask = rr ? mask1 : mask0;
+				const int pos = rr ? p1 : p0;
+				const float zz = rr ? zz1 : zz0;
+				float best = INFINITY;
+				int bi = 0x7fffffff;
+				while (mask) {
+					const int b = __ffsll((long long)mask) - 1;
+					mask &= mask - 1;
+					const int code = (b >> 1) * 8 + 2 * t + (b & 1);
+					const float4* er = reinterpret_cast<const float4*>(w.emb + code * 128);
+					float dot = 0.f;
+#pragma unroll 4
+					for (int d4i = 0; d4i < 32; ++d4i) {
+						const float4 e = __ldg(er + d4i);
+						dot = fmaf(Z[(d4i * 4 + 0) * 128 + pos], e.x, dot);
+						dot = fmaf(Z[(d4i * 4 + 1) * 128 + pos], e.y, dot);
+						dot = fmaf(Z[(d4i * 4 + 2) * 128 + pos], e.z, dot);
+						dot = fmaf(Z[(d4i * 4 + 3) * 128 + pos], e.w, dot);
+					}
+					const float dist = (zz + __ldg(w.emb_sq + code)) - 2.f * dot;
+					if (dist < best) {  // codes ascend within the lane, so strict < keeps the first minimum
+						best = dist;
+						bi = code;
 					}
 				}
+				if (rr) { best1 = best; bi1 = bi; } else { best0 = best; bi0 = bi; }
 			}
-			const int cg = warp * 2 + pass;  // ascending code order across candidate groups
-			*reinterpret_cast<float4*>(cand_d + cg * 128 + lane * 4) = make_float4(best[0], best[1], best[2], best[3]);
-			*reinterpret_cast<int4*>(cand_i + cg * 128 + lane * 4) = make_int4(bi[0], bi[1], bi[2], bi[3]);
-		}
-		__syncthreads();
-		if (tid < 128) {
-			float best = cand_d[tid];
-			int bi = cand_i[tid];
+			// combine the four lanes of a quad: smallest distance, then smallest code (torch.argmin's first minimum)
 #pragma unroll
-			for (int cg = 1; cg < 16; ++cg) {
-				const float dv = cand_d[cg * 128 + tid];
-				if (dv < best) {
-					best = dv;
-					bi = cand_i[cg * 128 + tid];
-				}
+			for (int o = 1; o <= 2; o <<= 1) {
+				float ob = __shfl_xor_sync(0xffffffffu, best0, o);
+				int oi = __shfl_xor_sync(0xffffffffu, bi0, o);
+				if (ob < best0 || (ob == best0 && oi < bi0)) { best0 = ob; bi0 = oi; }
+				ob = __shfl_xor_sync(0xffffffffu, best1, o);
+				oi = __shfl_xor_sync(0xffffffffu, bi1, o);
+				if (ob < best1 || (ob == best1 && oi < bi1)) { best1 = ob; bi1 = oi; }
 			}
-			const int64_t leaf = grp * 2 + (tid >> 6);
-			if (leaf < n_leaves) indices[leaf * 64 + (tid & 63)] = (uint8_t)bi;  // p = (d*4+h)*4+w == view(B,4,4,4)
+			if (t == 0) {
+				const int64_t l0 = grp * 2 + (p0 >> 6), l1 = grp * 2 + (p1 >> 6);
+				if (l0 < n_leaves) indices[l0 * 64 + (p0 & 63)] = (uint8_t)bi0;  // p = (d*4+h)*4+w == view(B,4,4,4)
+				if (l1 < n_leaves) indices[l1 * 64 + (p1 & 63)] = (uint8_t)bi1;
+			}
 		}
 		__syncthreads();
 	}

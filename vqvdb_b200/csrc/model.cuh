@@ -22,17 +22,19 @@ struct EncoderWeights {
 	const float *proj_w, *proj_b;      // encoder.proj       transposed [32][128]
 	const float *emb_t;                // quantizer.embedding transposed [128][256]
 	const float *emb_sq;               // sum(embedding**2, dim=1) [256]
+	const float *emb_norm;             // |e_k| [256], rounded up: only used in the shortlist bound
+	const float *emb;                  // quantizer.embedding [256][128] fp32 (exact re-scoring)
 };
 
-// The encoder consumes its weights as a fixed stream of "units" (<= 8 KB slices of the transposed tables
-// above) through a shared-memory ring: pre.0 (1), res16 conv1/conv2 (4+4, 4 input channels each), down (16,
-// one input channel each), res32 conv1/conv2 (16+16, 2 input channels each), proj (2, 16 input channels
-// each), then the transposed codebook twice (16+16, 8 embedding dims each; one pass per half of the codes).
-constexpr int kEncUnits = 91;
+// The encoder consumes its weights as a fixed stream of "units" (<= 8 KB) through a shared-memory ring:
+// pre.0 (1), res16 conv1/conv2 (4+4, 4 input channels each), down (16, one input channel each), res32
+// conv1/conv2 (16+16, 2 input channels each), proj (2, 16 input channels each) — slices of the transposed
+// fp32 tables above — then the codebook as 8 bf16 tiles [64 codes][64 dims] (pre-swizzled like the decoder's
+// weight units) for the tensor-core shortlist pass of the VQ.
+constexpr int kEncUnits = 67;
 struct EncoderUnits {
-	const float* base;         // the fp32 weight arena
-	uint32_t off[kEncUnits];   // byte offset of each unit from base (16-byte aligned)
-	uint32_t bytes[kEncUnits]; // multiple of 16, <= 8192
+	const void* ptr[kEncUnits];   // 16-byte aligned
+	uint32_t bytes[kEncUnits];    // multiple of 16, <= 8192
 };
 
 struct DecoderWeights {
