@@ -25,6 +25,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr", "-Xptxas", "-v",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unknown-pragmas"] + ARCH
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall"]
+if os.environ.get("VQVDB_ENC_LEAVES"):  # tuning knob: leaves per encoder CTA (2 or 3); the source default is used otherwise
+    NVCC_FLAGS.append("-DVQVDB_ENC_LEAVES=" + os.environ["VQVDB_ENC_LEAVES"])
 
 
 def _nvcc() -> str:

@@ -227,12 +227,14 @@ void upload_float_model(vqvdb_b200_codec& c, const WeightPack& p) {
 		add(e.pre_w, 27 * 16 * 4);
 		for (const float* t : {e.res16.c1_w, e.res16.c2_w})
 			for (int q = 0; q < 4; ++q) add(t + (size_t)q * 4 * 27 * 16, 4 * 27 * 16 * 4);
+		add(e.pre_w, 27 * 16 * 4);  // the 8^3 residual is re-derived from the input leaf after conv2
 		for (int ic = 0; ic < 16; ++ic) add(e.down_w + (size_t)ic * 64 * 32, 64 * 32 * 4);
 		for (const float* t : {e.res32.c1_w, e.res32.c2_w})
 			for (int q = 0; q < 16; ++q) add(t + (size_t)q * 2 * 27 * 32, 2 * 27 * 32 * 4);
 		for (int q = 0; q < 2; ++q) add(e.proj_w + (size_t)q * 16 * 128, 16 * 128 * 4);
 		const uint8_t* cbu = c.mma_arena + units.size() + cb.size() * 2;
-		for (int q = 0; q < 8; ++q) add(cbu + (size_t)q * 8192, 8192);
+		for (int round = 0; round < 2; ++round)
+			for (int q = 0; q < 8; ++q) add(cbu + (size_t)q * 8192, 8192);
 		if (n != vqvdb::kEncUnits) throw std::logic_error("encoder unit table size mismatch");
 	}
 	auto& m = c.dec_mma;

@@ -444,8 +444,13 @@ decode_mma_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices
 							f = unpack_bf16(raw.w); xr[7] = f.x; xr[8] = f.y;
 							const float wk0 = wf[(kd * 3 + kh) * 3], wk1 = wf[(kd * 3 + kh) * 3 + 1], wk2 = wf[(kd * 3 + kh) * 3 + 2];
 #pragma unroll
-							for (int j = 0; j < 8; ++j)
-								out[rr][j] = fmaf(xr[j + 2], wk2, fmaf(xr[j + 1], wk1, fmaf(xr[j], wk0, out[rr][j])));
+							for (int j = 0; j < 8; ++j) {  // xr[0] and xr[9] are the exact-zero w halo: their taps are skipped
+								float o = out[rr][j];
+								if (j > 0) o = fmaf(xr[j], wk0, o);
+								o = fmaf(xr[j + 1], wk1, o);
+								if (j < 7) o = fmaf(xr[j + 2], wk2, o);
+								out[rr][j] = o;
+							}
 						}
 					}
 				}

@@ -10,13 +10,17 @@
 // reduced-precision operands flip 0.2-2 % of indices.  The kernel is therefore bound by the
 // CUDA-core FMA pipe (measured 71 TFLOP/s on this part, tools/microbench/pipe_rates.cu), and the design
 // goal is to keep that pipe issuing:
-//   * a CTA (256 threads) carries TWO leaves so that the 4^3 layers still give every thread a register tile;
-//   * 8^3 layers: thread tile = one 8-voxel row x 8 output channels (64 accumulators); the residual stream
-//     stays in registers across the whole residual block, only the conv INPUT lives in shared memory;
+//   * a CTA (384 threads = 3 warps per SM sub-partition) carries THREE leaves, so that the 4^3 layers still
+//     give every thread a register tile and each scheduler has three warps to hide LDS latency with;
+//   * 8^3 layers: thread tile = one 8-voxel row x 8 output channels (64 accumulators).  To stay under the 168
+//     registers that 12 warps/SM allow, the residual x of the 8^3 block is NOT kept live across its two convs:
+//     it is re-derived at the end from the haloed input leaf (27 FMAs per value, 3 % of the block) using the
+//     saved GroupNorm statistics, bit-identically to the first evaluation;
 //   * weights stream from L2 through a 6-stage shared-memory ring (1-D TMA bulk copies, mbarrier
-//     complete_tx) in 67 fixed "units" that both leaves share; a warp reads them as broadcast LDS.128;
+//     complete_tx) in 68 fixed "units" that the three leaves share; a warp reads them as broadcast LDS.128;
 //   * shared-memory layouts are chosen so every LDS.128 of activations is bank-conflict free
-//     (half-row swap keyed on bit 2 of the row index at 8^3; parity-split rows for the stride-2 conv).
+//     (half-row swap keyed on bit 2 of the row index at 8^3; parity-split rows for the stride-2 conv;
+//     48-word depth pitch at 4^3).
 // Accumulation order per output is cin, kd, kh, kw ascending — the same as oracle/vqvae_oracle.c.
 #include "leaf_ops.cuh"
 #include "ptx_utils.cuh"
@@ -26,23 +30,33 @@ namespace vqvdb {
 
 namespace {
 
-constexpr int kThreads = 256;
+#ifndef VQVDB_ENC_LEAVES
+#define VQVDB_ENC_LEAVES 3
+#endif
+constexpr int kLeaves = VQVDB_ENC_LEAVES;     // leaves per CTA (2 or 3)
+constexpr int kThreads = 128 * kLeaves;       // 384
+constexpr int kWarps = kThreads / 32;         // 12
+constexpr int kPos = 64 * kLeaves;            // 192 latent positions per CTA pass
 constexpr int kStages = 6;
 constexpr uint32_t kStageBytes = 8192;
 
 // ---- shared memory map (floats unless noted) ----
 constexpr int kLeafR = 13440;                 // per-leaf slab of region R: H16 [16][10][10][8] (12800) or D16 (13440)
 constexpr int kROff = kStages * (int)kStageBytes / 4;   // region R starts after the ring
-constexpr int kRFloats = 2 * kLeafR;          // 26880
-constexpr int kH32Leaf1 = 4608 + 16;          // leaf 1's H32 slab is skewed by 16 words (bank de-conflict)
-constexpr int kX32s = kRFloats - 8192;        // [32 c][128 pos] staging for proj; later the argmin candidates
-constexpr int kInOff = kROff + kRFloats;      // in_halo: 2 x [10][10][8]
-constexpr int kRedOff = kInOff + 1600;        // GroupNorm partials: red[2][8][2], red2[2][8][2]
-constexpr int kAttOff = kRedOff + 64;         // att_mean[2][32], att_hid[2][8]
-constexpr int kBarOff = kAttOff + 80;         // 2*kStages mbarriers (8 B each)
+constexpr int kRFloats = kLeaves * kLeafR;    // 40320
+constexpr int kH32Leaf = 32 * 6 * 48;         // 4^3 conv input per leaf: [32 c][6 d'][48-word pitch: 6 h' x 4 w + pad]
+constexpr int kX32s = kRFloats - 32 * kPos;   // [32 c][192 pos] staging for proj
+constexpr int kZFloats = 128 * kPos;          // z [128 d][192 pos] at the start of R
+constexpr int kZbOff = kZFloats;              // bf16 [192 pos][128 d] right after z (overlaps the dead X32 staging)
+constexpr int kInOff = kROff + kRFloats;      // in_halo: 3 x [10][10][8]
+constexpr int kRedOff = kInOff + 800 * kLeaves;   // GroupNorm partials: 2 x [leaves][8][2]
+constexpr int kAttOff = kRedOff + 32 * kLeaves;   // att_mean[leaves][32], att_hid[leaves][8]
+constexpr int kBarOff = kAttOff + 40 * kLeaves + (40 * kLeaves) % 2;  // 2*kStages mbarriers (8 B each, 8-byte aligned)
 constexpr int kSmemFloats = kBarOff + 2 * kStages * 2;
 static_assert(kSmemFloats * 4 <= 227 * 1024, "encoder smem budget");
-static_assert(2 * 4608 + 16 <= kX32s && 16384 <= kX32s, "H32 / Z overlays stay clear of the X32 staging area");
+static_assert(kLeaves * kH32Leaf <= kX32s && kZFloats <= kX32s, "H32 / Z overlays stay clear of the X32 staging area");
+static_assert(kZbOff + kPos * 64 + 3 * 16 * kWarps <= kRFloats, "bf16 z and the pair-exchange arrays fit behind z");
+static_assert(kLeaves == 2 || kLeaves == 3, "thread mappings assume 2 or 3 leaves per CTA");
 
 // Weight-unit stream.  Every warp consumes the same sequence; thread 0 is also the producer.
 struct Pipe {
@@ -115,9 +129,12 @@ __device__ __forceinline__ void conv8(float (&acc)[8][8], const float* hin, int 
 						const float4 w1 = *reinterpret_cast<const float4*>(wp + kw * 16 + 4);
 						const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-						for (int j = 0; j < 8; ++j)
+						for (int j = 0; j < 8; ++j) {
+							if (j + kw != 0 && j + kw != 9) {  // w-halo taps multiply an exact zero: dropped at compile time
 #pragma unroll
-							for (int n = 0; n < 8; ++n) acc[n][j] = fmaf(x[j + kw], wv[n], acc[n][j]);
+								for (int n = 0; n < 8; ++n) acc[n][j] = fmaf(x[j + kw], wv[n], acc[n][j]);
+							}
+						}
 					}
 				}
 			}
@@ -147,10 +164,10 @@ __device__ __forceinline__ int d16_row(int c, int dp, int hp) {
 // 32 rows of the same leaf.  Two-pass variance; partials meet in shared memory (2 block barriers).
 template <int CPG>
 __device__ __forceinline__ void gn8(float (&v)[8][8], const float* __restrict__ gamma, const float* __restrict__ beta,
-                                    float* red, int lf, int wl, int och, int lane) {
+                                    float* red, int lf, int wl, int och, int lane, float (&mean)[8 / CPG],
+                                    float (&rstd)[8 / CPG]) {
 	constexpr int NG = 8 / CPG;
 	constexpr float kInvCnt = 1.f / (CPG * 512);
-	float mean[NG], rstd[NG];
 	const int slot = wl & 1;
 #pragma unroll
 	for (int gi = 0; gi < NG; ++gi) {
@@ -176,13 +193,13 @@ __device__ __forceinline__ void gn8(float (&v)[8][8], const float* __restrict__ 
 				q = fmaf(dv, dv, q);
 			}
 		q = warp_sum(q);
-		if (lane == 0) red[32 + b + slot] = q;
+		if (lane == 0) red[16 * kLeaves + b + slot] = q;
 	}
 	__syncthreads();
 #pragma unroll
 	for (int gi = 0; gi < NG; ++gi) {
 		const int b = (lf * 8 + och * NG + gi) << 1;
-		rstd[gi] = 1.f / sqrtf((red[32 + b] + red[32 + b + 1]) * kInvCnt + kGnEps);
+		rstd[gi] = 1.f / sqrtf((red[16 * kLeaves + b] + red[16 * kLeaves + b + 1]) * kInvCnt + kGnEps);
 	}
 #pragma unroll
 	for (int n = 0; n < 8; ++n) {
@@ -194,8 +211,9 @@ __device__ __forceinline__ void gn8(float (&v)[8][8], const float* __restrict__ 
 }
 
 // ---- 4^3 layers -------------------------------------------------------------------------------------
-// lane = leaf*16 + d4*4 + h4 owns one 4-voxel row; warp og owns output channels og*4 .. og*4+3 (= GroupNorm
-// group og of the 32-channel layers), so every GroupNorm / attention reduction is a 16-lane shuffle.
+// warp = (leaf, pair of channel groups); lane = (og & 1)*16 + d4*4 + h4 owns one 4-voxel row and the output channels
+// og*4 .. og*4+3 (= GroupNorm group og of the 32-channel layers), so every GroupNorm / attention reduction is
+// a 16-lane shuffle.
 __device__ __forceinline__ float half_warp_sum(float v) {
 #pragma unroll
 	for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -227,7 +245,7 @@ __device__ __forceinline__ void gn4_relu(float (&v)[4][4], const float* __restri
 	}
 }
 
-__device__ __forceinline__ int h32_row(int c, int dp, int hp) { return (c * 6 + dp) * 24 + hp * 4; }
+__device__ __forceinline__ int h32_row(int c, int dp, int hp) { return (c * 6 + dp) * 48 + hp * 4; }
 
 // 3x3x3 conv at 4^3, 32 -> 32 channels: 16 units of 2 input channels.
 __device__ __forceinline__ void conv4(float (&acc)[4][4], const float* hin, int d4, int h4, int og, Pipe& pipe,
@@ -254,9 +272,12 @@ __device__ __forceinline__ void conv4(float (&acc)[4][4], const float* hin, int 
 						const float4 w0 = *reinterpret_cast<const float4*>(wp + kw * 32);
 						const float wv[4] = {w0.x, w0.y, w0.z, w0.w};
 #pragma unroll
-						for (int j = 0; j < 4; ++j)
+						for (int j = 0; j < 4; ++j) {
+							if (j + kw != 0 && j + kw != 5) {  // w-halo taps
 #pragma unroll
-							for (int n = 0; n < 4; ++n) acc[n][j] = fmaf(x[j + kw], wv[n], acc[n][j]);
+								for (int n = 0; n < 4; ++n) acc[n][j] = fmaf(x[j + kw], wv[n], acc[n][j]);
+							}
+						}
 					}
 				}
 			}
@@ -271,6 +292,59 @@ __device__ __forceinline__ void store_h32(const float (&v)[4][4], float* hbuf, i
 		*reinterpret_cast<float4*>(hbuf + h32_row(og * 4 + n, d4 + 1, h4 + 1)) = make_float4(v[n][0], v[n][1], v[n][2], v[n][3]);
 }
 
+// Residual of the 8^3 block, re-derived instead of kept in registers:  x = relu(GroupNorm(4,16)(pre.0(leaf) + b)).
+// Evaluated channel by channel with exactly the operation order of the first pass (kd, kh, kw ascending FMAs, bias
+// add, then (v - mean) * rstd * gamma + beta), so it reproduces the values the statistics were taken from bit for
+// bit, and adds them into v (which holds 0.1 * (conv2 + bias)).
+__device__ __forceinline__ void add_recomputed_residual(float (&v)[8][8], const float* in_halo, const float* wst, int d,
+                                                        int h, int och, const EncoderWeights& w, const float (&mean)[2],
+                                                        const float (&rstd)[2]) {
+#pragma unroll
+	for (int n = 0; n < 8; ++n) {  // fully unrolled: v[n] must stay in registers
+		const int c = och * 8 + n;
+		float t[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) t[j] = 0.f;
+#pragma unroll
+		for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+			for (int kh = 0; kh < 3; ++kh) {
+				const int hp = h + kh;
+				const float* row = in_halo + h16_row(0, d + kd, hp);
+				const int sw = ((hp >> 2) & 1) * 4;
+				const float4 a = *reinterpret_cast<const float4*>(row + sw);
+				const float4 b = *reinterpret_cast<const float4*>(row + (sw ^ 4));
+				const float x[10] = {0.f, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0.f};
+#pragma unroll
+				for (int kw = 0; kw < 3; ++kw) {
+					const float wv = wst[((kd * 3 + kh) * 3 + kw) * 16 + c];
+#pragma unroll
+					for (int j = 0; j < 8; ++j) {
+						if (j + kw != 0 && j + kw != 9) t[j] = fmaf(x[j + kw], wv, t[j]);  // same skip as conv8: bit-identical
+					}
+				}
+			}
+		}
+		const float bias = __ldg(w.pre_b + c), ga = __ldg(w.pre_gn_w + c), be = __ldg(w.pre_gn_b + c);
+		const float m = mean[n >> 2], r = rstd[n >> 2];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) v[n][j] += fmaxf(((t[j] + bias) - m) * r * ga + be, 0.f);
+	}
+}
+
+__device__ __forceinline__ void zero_halo_borders(float* R, int tid, bool parity_split) {
+	// 36 border rows per channel (d' in {0,9} or h' in {0,9}), 16 channels, kLeaves leaves, two float4 per row
+	for (int i = tid; i < kLeaves * 16 * 36 * 2; i += kThreads) {
+		const int hf = i & 1, b = (i >> 1) % 36, c = ((i >> 1) / 36) & 15, l = (i >> 1) / (36 * 16);
+		int dp, hq;
+		if (b < 10) { dp = 0; hq = b; }
+		else if (b < 20) { dp = 9; hq = b - 10; }
+		else { dp = 1 + ((b - 20) >> 1); hq = ((b - 20) & 1) * 9; }
+		const int row = parity_split ? d16_row(c, dp, hq) : h16_row(c, dp, hq);
+		*reinterpret_cast<float4*>(R + l * kLeafR + row + hf * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+	}
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* __restrict__ leaves, int64_t n_leaves,
                    uint8_t* __restrict__ indices) {
@@ -280,17 +354,17 @@ encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* 
 	float* in_halo = smem + kInOff;
 	float* red = smem + kRedOff;
 	float* att_mean = smem + kAttOff;
-	float* att_hid = att_mean + 64;
+	float* att_hid = att_mean + 32 * kLeaves;
 	const uint32_t bars = smem_u32(smem + kBarOff);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const int64_t n_groups = (n_leaves + 1) / 2;
+	const int64_t n_groups = (n_leaves + kLeaves - 1) / kLeaves;
 
 	// in_halo borders are written once and stay zero (only interiors are overwritten per leaf)
-	for (int i = tid; i < 1600; i += kThreads) in_halo[i] = 0.f;
+	for (int i = tid; i < 800 * kLeaves; i += kThreads) in_halo[i] = 0.f;
 	if (tid == 0) {
 		for (int s = 0; s < kStages; ++s) {
 			mbar_init(bars + s * 8, 1);
-			mbar_init(bars + (kStages + s) * 8, kThreads / 32);
+			mbar_init(bars + (kStages + s) * 8, kWarps);
 		}
 		mbar_fence_init();
 	}
@@ -304,93 +378,82 @@ encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* 
 	}
 	__syncthreads();
 
-	// 8^3 mapping: half the CTA per leaf; warp-in-leaf wl -> (row half, channel half)
+	// 8^3 mapping: 128 threads per leaf; warp-in-leaf wl -> (row half, channel half)
 	const int lf = tid >> 7, wl = (tid >> 5) & 3, och = wl >> 1;
 	const int row8 = (wl & 1) * 32 + lane, d8 = row8 >> 3, h8 = row8 & 7;
-	// 4^3 mapping
-	const int lf4 = lane >> 4, d4 = (lane >> 2) & 3, h4 = lane & 3, og = warp;
+	// 4^3 mapping: warp -> (leaf, pair of channel groups); lane -> (group parity, row)
+	const int lf4 = warp >> 2, og = (warp & 3) * 2 + (lane >> 4), d4 = (lane >> 2) & 3, h4 = lane & 3;
 	float* H16 = R + lf * kLeafR;
 	float* D16 = H16;
-	float* H32 = R + (lf4 ? kH32Leaf1 : 0);
+	float* H32 = R + lf4 * kH32Leaf;
 	float* X32s = R + kX32s;
 	float* Z = R;
 
 	for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-		// ---- stage the two leaves (2048 B each, 128-bit coalesced) and clear the conv-input borders ----
+		// ---- stage the leaves (2048 B each, 128-bit coalesced) and clear the conv-input borders ----
 		{
-			int64_t leaf = grp * 2 + lf;
-			if (leaf >= n_leaves) leaf = grp * 2;  // odd tail: the second slot recomputes the first leaf, result discarded
+			int64_t leaf = grp * kLeaves + lf;
+			if (leaf >= n_leaves) leaf = grp * kLeaves;  // ragged tail: spare slots recompute the first leaf, result discarded
 			const int lt = tid & 127;
 			const float4 v = __ldcs(reinterpret_cast<const float4*>(leaves + leaf * 512) + lt);
 			const int p = lt * 4, d = p >> 6, h = (p >> 3) & 7, half = (p >> 2) & 1;
 			const int hp = h + 1;
 			float* dst = in_halo + lf * 800 + ((d + 1) * 10 + hp) * 8 + ((half ^ ((hp >> 2) & 1)) * 4);
 			*reinterpret_cast<float4*>(dst) = v;
-			// H16 border rows of both leaves: 36 rows per channel (d' in {0,9} or h' in {0,9})
-			for (int i = tid; i < 2 * 16 * 36 * 2; i += kThreads) {
-				const int hf = i & 1, b = (i >> 1) % 36, c = ((i >> 1) / 36) & 15, l = (i >> 1) / (36 * 16);
-				int dp, hq;
-				if (b < 10) { dp = 0; hq = b; }
-				else if (b < 20) { dp = 9; hq = b - 10; }
-				else { dp = 1 + ((b - 20) >> 1); hq = ((b - 20) & 1) * 9; }
-				*reinterpret_cast<float4*>(R + l * kLeafR + h16_row(c, dp, hq) + hf * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-			}
+			zero_halo_borders(R, tid, false);
 		}
 		__syncthreads();
 
-		float xr[8][8];   // residual stream of this thread's tile (8 channels x 8 voxels)
 		float acc[8][8];
+		float pre_mean[2], pre_rstd[2];  // GroupNorm(4,16) statistics of this thread's two groups, kept for the residual
 		// ---- pre.0: Conv3d(1,16,k3) ; pre.1: GroupNorm(4,16) + ReLU ----
-		conv8<1, 1>(xr, in_halo + lf * 800, d8, h8, och, pipe, tab, ring_ptr, lane);
+		conv8<1, 1>(acc, in_halo + lf * 800, d8, h8, och, pipe, tab, ring_ptr, lane);
 #pragma unroll
 		for (int n = 0; n < 8; ++n) {
 			const float b = __ldg(w.pre_b + och * 8 + n);
 #pragma unroll
-			for (int j = 0; j < 8; ++j) xr[n][j] += b;
-		}
-		gn8<4>(xr, w.pre_gn_w, w.pre_gn_b, red, lf, wl, och, lane);
-
-		// ---- pre.3: ResidualBlock(16) ----
-#pragma unroll
-		for (int n = 0; n < 8; ++n)
-#pragma unroll
-			for (int j = 0; j < 8; ++j) acc[n][j] = xr[n][j];
-		gn8<2>(acc, w.res16.gn1_w, w.res16.gn1_b, red, lf, wl, och, lane);
-		store_h16(acc, H16, d8, h8, och);
-		__syncthreads();
-		conv8<4, 4>(acc, H16, d8, h8, och, pipe, tab, ring_ptr, lane);
-#pragma unroll
-		for (int n = 0; n < 8; ++n) {
-			const float b = __ldg(w.res16.c1_b + och * 8 + n);
-#pragma unroll
 			for (int j = 0; j < 8; ++j) acc[n][j] += b;
 		}
-		gn8<2>(acc, w.res16.gn2_w, w.res16.gn2_b, red, lf, wl, och, lane);  // its barriers also fence conv1's reads of H16
-		store_h16(acc, H16, d8, h8, och);
-		__syncthreads();
-		conv8<4, 4>(acc, H16, d8, h8, och, pipe, tab, ring_ptr, lane);
+		gn8<4>(acc, w.pre_gn_w, w.pre_gn_b, red, lf, wl, och, lane, pre_mean, pre_rstd);
+
+		// ---- pre.3: ResidualBlock(16): x + 0.1 * conv2(relu(gn2(conv1(relu(gn1(x)))))) ----
+		{
+			float m4[4], r4[4];
+			gn8<2>(acc, w.res16.gn1_w, w.res16.gn1_b, red, lf, wl, och, lane, m4, r4);
+			store_h16(acc, H16, d8, h8, och);
+			__syncthreads();
+			conv8<4, 4>(acc, H16, d8, h8, och, pipe, tab, ring_ptr, lane);
 #pragma unroll
-		for (int n = 0; n < 8; ++n) {
-			const float b = __ldg(w.res16.c2_b + och * 8 + n);
+			for (int n = 0; n < 8; ++n) {
+				const float b = __ldg(w.res16.c1_b + och * 8 + n);
 #pragma unroll
-			for (int j = 0; j < 8; ++j) xr[n][j] = xr[n][j] + kResScale * (acc[n][j] + b);
+				for (int j = 0; j < 8; ++j) acc[n][j] += b;
+			}
+			gn8<2>(acc, w.res16.gn2_w, w.res16.gn2_b, red, lf, wl, och, lane, m4, r4);  // its barriers also fence conv1's reads of H16
+			store_h16(acc, H16, d8, h8, och);
+			__syncthreads();
+			conv8<4, 4>(acc, H16, d8, h8, och, pipe, tab, ring_ptr, lane);
+#pragma unroll
+			for (int n = 0; n < 8; ++n) {
+				const float b = __ldg(w.res16.c2_b + och * 8 + n);
+#pragma unroll
+				for (int j = 0; j < 8; ++j) acc[n][j] = kResScale * (acc[n][j] + b);
+			}
+			{
+				const float* wst = pipe.acquire(tab, ring_ptr);  // pre.0 weights again
+				add_recomputed_residual(acc, in_halo + lf * 800, wst, d8, h8, och, w, pre_mean, pre_rstd);
+				pipe.release(lane);
+			}
 		}
 		__syncthreads();  // every warp is done reading H16; the slab is re-laid-out for the stride-2 conv
 
 		// ---- down: Conv3d(16,32,k4,s2,p1).  Write x in the parity-split layout, borders zero. ----
-		for (int i = tid; i < 2 * 16 * 36 * 2; i += kThreads) {
-			const int hf = i & 1, b = (i >> 1) % 36, c = ((i >> 1) / 36) & 15, l = (i >> 1) / (36 * 16);
-			int dp, hq;
-			if (b < 10) { dp = 0; hq = b; }
-			else if (b < 20) { dp = 9; hq = b - 10; }
-			else { dp = 1 + ((b - 20) >> 1); hq = ((b - 20) & 1) * 9; }
-			*reinterpret_cast<float4*>(R + l * kLeafR + d16_row(c, dp, hq) + hf * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-		}
+		zero_halo_borders(R, tid, true);
 #pragma unroll
 		for (int n = 0; n < 8; ++n) {
 			float* row = D16 + d16_row(och * 8 + n, d8 + 1, h8 + 1);
-			*reinterpret_cast<float4*>(row) = make_float4(xr[n][0], xr[n][1], xr[n][2], xr[n][3]);
-			*reinterpret_cast<float4*>(row + 4) = make_float4(xr[n][4], xr[n][5], xr[n][6], xr[n][7]);
+			*reinterpret_cast<float4*>(row) = make_float4(acc[n][0], acc[n][1], acc[n][2], acc[n][3]);
+			*reinterpret_cast<float4*>(row + 4) = make_float4(acc[n][4], acc[n][5], acc[n][6], acc[n][7]);
 		}
 		__syncthreads();
 
@@ -419,9 +482,12 @@ encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* 
 							const float4 w0 = *reinterpret_cast<const float4*>(wp + kw * 32);
 							const float wv[4] = {w0.x, w0.y, w0.z, w0.w};
 #pragma unroll
-							for (int j = 0; j < 4; ++j)
+							for (int j = 0; j < 4; ++j) {
+								if (2 * j + kw != 0 && 2 * j + kw != 9) {  // w-halo taps
 #pragma unroll
-								for (int n = 0; n < 4; ++n) x32[n][j] = fmaf(x[2 * j + kw], wv[n], x32[n][j]);
+									for (int n = 0; n < 4; ++n) x32[n][j] = fmaf(x[2 * j + kw], wv[n], x32[n][j]);
+								}
+							}
 						}
 					}
 				}
@@ -437,13 +503,13 @@ encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* 
 		__syncthreads();  // D16 is dead; region R now holds the 4^3 buffers
 
 		// ---- res_stack.0: ResidualBlock(32) ----
-		for (int i = tid; i < 2 * 32 * 20; i += kThreads) {  // H32 border rows: 20 per channel
+		for (int i = tid; i < kLeaves * 32 * 20; i += kThreads) {  // H32 border rows: 20 per channel
 			const int b = i % 20, c = (i / 20) & 31, l = i / (20 * 32);
 			int dp, hq;
 			if (b < 6) { dp = 0; hq = b; }
 			else if (b < 12) { dp = 5; hq = b - 6; }
 			else { dp = 1 + ((b - 12) >> 1); hq = ((b - 12) & 1) * 5; }
-			*reinterpret_cast<float4*>(R + (l ? kH32Leaf1 : 0) + h32_row(c, dp, hq)) = make_float4(0.f, 0.f, 0.f, 0.f);
+			*reinterpret_cast<float4*>(R + l * kH32Leaf + h32_row(c, dp, hq)) = make_float4(0.f, 0.f, 0.f, 0.f);
 		}
 #pragma unroll
 		for (int n = 0; n < 4; ++n)
@@ -478,7 +544,7 @@ encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* 
 			if ((lane & 15) == 0) att_mean[lf4 * 32 + og * 4 + n] = s * (1.f / 64.f);
 		}
 		__syncthreads();
-		if (tid < 16) {
+		if (tid < 8 * kLeaves) {
 			const int l = tid >> 3, j = tid & 7;
 			float s = 0.f;
 #pragma unroll 8
@@ -492,13 +558,14 @@ encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* 
 #pragma unroll
 			for (int j = 0; j < 8; ++j) s = fmaf(__ldg(w.fc2 + (og * 4 + n) * 8 + j), att_hid[lf4 * 8 + j], s);
 			const float y = sigmoid_f(s);
-			*reinterpret_cast<float4*>(X32s + (og * 4 + n) * 128 + lf4 * 64 + (d4 * 4 + h4) * 4) =
+			*reinterpret_cast<float4*>(X32s + (og * 4 + n) * kPos + lf4 * 64 + (d4 * 4 + h4) * 4) =
 			    make_float4(x32[n][0] * y, x32[n][1] * y, x32[n][2] * y, x32[n][3] * y);
 		}
 		__syncthreads();
 
-		// ---- proj: Conv3d(32,128,k1): lane -> 4 positions (of the 128 of both leaves), warp -> 16 channels ----
+		// ---- proj: Conv3d(32,128,k1): thread -> 4 positions (of the 192) x 16 output channels ----
 		{
+			const int pg = tid % (kPos / 4), ocg = tid / (kPos / 4);
 			float z[16][4];
 #pragma unroll
 			for (int n = 0; n < 16; ++n)
@@ -509,11 +576,11 @@ encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* 
 				const float* wst = pipe.acquire(tab, ring_ptr);
 #pragma unroll 4
 				for (int i = 0; i < 16; ++i) {
-					const float4 xv = *reinterpret_cast<const float4*>(X32s + (u * 16 + i) * 128 + lane * 4);
+					const float4 xv = *reinterpret_cast<const float4*>(X32s + (u * 16 + i) * kPos + pg * 4);
 					const float x[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
 					for (int q = 0; q < 4; ++q) {
-						const float4 w0 = *reinterpret_cast<const float4*>(wst + i * 128 + warp * 16 + q * 4);
+						const float4 w0 = *reinterpret_cast<const float4*>(wst + i * 128 + ocg * 16 + q * 4);
 						const float wv[4] = {w0.x, w0.y, w0.z, w0.w};
 #pragma unroll
 						for (int n = 0; n < 4; ++n)
@@ -523,29 +590,30 @@ encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* 
 				}
 				pipe.release(lane);
 			}
+			__syncthreads();  // all reads of the X32 staging (and of H32 under z) are done before z lands on top of them
 #pragma unroll
 			for (int n = 0; n < 16; ++n) {
-				const float b = __ldg(w.proj_b + warp * 16 + n);
-				*reinterpret_cast<float4*>(Z + (warp * 16 + n) * 128 + lane * 4) = make_float4(z[n][0] + b, z[n][1] + b, z[n][2] + b, z[n][3] + b);
+				const float b = __ldg(w.proj_b + ocg * 16 + n);
+				*reinterpret_cast<float4*>(Z + (ocg * 16 + n) * kPos + pg * 4) = make_float4(z[n][0] + b, z[n][1] + b, z[n][2] + b, z[n][3] + b);
 			}
 		}
 		__syncthreads();
 
 		// ---- VQ: argmin_k (|z|^2 + |e_k|^2) - 2 z.e_k (save_for_inference.py:55-61), first minimum wins.
 		// Two stages that give exactly the fp32 result at a fraction of its cost:
-		//  1. approximate scores a_k = |e_k|^2 - 2 bf16(z).bf16(e_k) for all 128 x 256 (position, code) pairs on the
+		//  1. approximate scores a_k = |e_k|^2 - 2 bf16(z).bf16(e_k) for all 192 x 256 (position, code) pairs on the
 		//     tensor cores (one m16n8k16 pass, fp32 accumulate), with the rigorous bound
 		//     |a_k - (true score)| <= B_k = 2^-7 * 1.07 * |z| * |e_k| + 1e-4  (bf16 unit roundoff 2^-9 per operand);
 		//  2. every code whose lower bound a_k - B_k does not exceed min_j (a_j + B_j) is re-scored with the
 		//     reference's fp32 formula, sequential in d.  The fp32 arg-min and all its fp32 ties are provably in
 		//     that shortlist (1-20 codes per position), so the index equals a full fp32 scan's.
 		{
-			uint8_t* Zb = reinterpret_cast<uint8_t*>(X32s);  // bf16 [128 pos][128 d], 256-B rows, 16-B chunks swizzled
-			for (int i = tid; i < 128 * 16; i += kThreads) {
-				const int pos = i & 127, c = i >> 7;
+			uint8_t* Zb = reinterpret_cast<uint8_t*>(R + kZbOff);  // bf16 [192 pos][128 d], 256-B rows, 16-B chunks swizzled
+			for (int i = tid; i < kPos * 16; i += kThreads) {
+				const int pos = i % kPos, c = i / kPos;
 				float v[8];
 #pragma unroll
-				for (int q = 0; q < 8; ++q) v[q] = Z[(c * 8 + q) * 128 + pos];
+				for (int q = 0; q < 8; ++q) v[q] = Z[(c * 8 + q) * kPos + pos];
 				uint4 pk;
 				pk.x = pack_bf16(v[0], v[1]);
 				pk.y = pack_bf16(v[2], v[3]);
@@ -556,123 +624,158 @@ encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* 
 			}
 			__syncthreads();
 
+			// Two rounds of kPos/2 positions.  In a round, warp pair (w, w+kHalf) shares a 16-row block: warp w scores codes
+			// 0..127, warp w+6 codes 128..255 (64 score registers each); row minima and winners meet in shared memory.
 			const int g = lane >> 2, t = lane & 3;
-			const int m0 = warp * 16;
-			float sc[32][4];  // sc[nt][e]: e=0,1 -> row m0+g, codes nt*8+2t+{0,1}; e=2,3 -> row m0+g+8
+			constexpr int kHalf = kWarps / 2;    // warps per code half = 16-row blocks per round
+			const int ch = warp / kHalf;         // code half of this warp
+			float* xch_u = R + kZbOff + kPos * 64;   // [warps][16 rows] upper-bound minima
+			float* xch_d = xch_u + 16 * kWarps;      // [warps][16] best exact distance
+			int* xch_i = reinterpret_cast<int*>(xch_d + 16 * kWarps);
+			const uint32_t zb_base = smem_u32(Zb);
+			const uint32_t khalf = lane >> 4;
+			const uint32_t bn = ((lane >> 4) << 3) + (lane & 7), bpar = (lane >> 3) & 1;
+#pragma unroll 1
+			for (int round = 0; round < 2; ++round) {
+				const int m0 = (round * kHalf + warp % kHalf) * 16;
+				float sc[16][4];  // sc[nt][e]: e=0,1 -> row m0+g, codes ch*128 + nt*8+2t+{0,1}; e=2,3 -> row m0+g+8
 #pragma unroll
-			for (int nt = 0; nt < 32; ++nt)
+				for (int nt = 0; nt < 16; ++nt)
 #pragma unroll
-				for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f;
-			{
-				const uint32_t zb_base = smem_u32(Zb);
-				const uint32_t arow = m0 + (lane & 15), khalf = lane >> 4;
-				const uint32_t bn = ((lane >> 4) << 3) + (lane & 7), bpar = (lane >> 3) & 1;
+					for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f;
+				const uint32_t arow = m0 + (lane & 15);
 #pragma unroll
 				for (int cg = 0; cg < 4; ++cg) {
 #pragma unroll
 					for (int dh = 0; dh < 2; ++dh) {
 						const uint32_t wbase = smem_u32(pipe.acquire(tab, ring_ptr));
+						if ((cg >> 1) == ch) {  // warp-uniform
 #pragma unroll
-						for (int kk = 0; kk < 4; ++kk) {
-							const uint32_t c = dh * 8 + kk * 2 + khalf;
-							uint32_t a0, a1, a2, a3;
-							ldmatrix_x4(zb_base + arow * 256 + (((c & 8) | ((c & 7) ^ (arow & 7))) << 4), a0, a1, a2, a3);
+							for (int kk = 0; kk < 4; ++kk) {
+								const uint32_t c = dh * 8 + kk * 2 + khalf;
+								uint32_t a0, a1, a2, a3;
+								ldmatrix_x4(zb_base + arow * 256 + (((c & 8) | ((c & 7) ^ (arow & 7))) << 4), a0, a1, a2, a3);
 #pragma unroll
-							for (int j = 0; j < 4; ++j) {
-								const uint32_t n = j * 16 + bn, bchunk = kk * 2 + bpar;
-								uint32_t b0, b1, b2, b3;
-								ldmatrix_x4(wbase + n * 128 + ((bchunk ^ (n & 7u)) << 4), b0, b1, b2, b3);
-								mma_bf16(sc[cg * 8 + 2 * j], a0, a1, a2, a3, b0, b1);
-								mma_bf16(sc[cg * 8 + 2 * j + 1], a0, a1, a2, a3, b2, b3);
+								for (int j = 0; j < 4; ++j) {
+									const uint32_t n = j * 16 + bn, bchunk = kk * 2 + bpar;
+									uint32_t b0, b1, b2, b3;
+									ldmatrix_x4(wbase + n * 128 + ((bchunk ^ (n & 7u)) << 4), b0, b1, b2, b3);
+									mma_bf16(sc[(cg & 1) * 8 + 2 * j], a0, a1, a2, a3, b0, b1);
+									mma_bf16(sc[(cg & 1) * 8 + 2 * j + 1], a0, a1, a2, a3, b2, b3);
+								}
 							}
 						}
 						pipe.release(lane);
 					}
 				}
-			}
-			// exact |z|^2 of this lane's two rows, sequential in d like the re-scoring below
-			const int p0 = m0 + g, p1 = p0 + 8;
-			float zz0 = 0.f, zz1 = 0.f;
+				// exact |z|^2 of this lane's two rows, sequential in d like the re-scoring below
+				const int p0 = m0 + g, p1 = p0 + 8;
+				float zz0 = 0.f, zz1 = 0.f;
 #pragma unroll 8
-			for (int d = 0; d < 128; ++d) {
-				const float q0 = Z[d * 128 + p0], q1 = Z[d * 128 + p1];
-				zz0 = fmaf(q0, q0, zz0);
-				zz1 = fmaf(q1, q1, zz1);
-			}
-			const float cb0 = 0.0078125f * 1.07f * sqrtf(zz0), cb1 = 0.0078125f * 1.07f * sqrtf(zz1);
-			// scores -> a_k, and the row-wise minimum of the upper bounds
-			float umin0 = INFINITY, umin1 = INFINITY;
-#pragma unroll
-			for (int nt = 0; nt < 32; ++nt) {
-				const float2 esq = __ldg(reinterpret_cast<const float2*>(w.emb_sq + nt * 8 + 2 * t));
-				const float2 eno = __ldg(reinterpret_cast<const float2*>(w.emb_norm + nt * 8 + 2 * t));
-				sc[nt][0] = esq.x - 2.f * sc[nt][0];
-				sc[nt][1] = esq.y - 2.f * sc[nt][1];
-				sc[nt][2] = esq.x - 2.f * sc[nt][2];
-				sc[nt][3] = esq.y - 2.f * sc[nt][3];
-				umin0 = fminf(umin0, fminf(sc[nt][0] + (cb0 * eno.x + 1e-4f), sc[nt][1] + (cb0 * eno.y + 1e-4f)));
-				umin1 = fminf(umin1, fminf(sc[nt][2] + (cb1 * eno.x + 1e-4f), sc[nt][3] + (cb1 * eno.y + 1e-4f)));
-			}
-			umin0 = fminf(umin0, __shfl_xor_sync(0xffffffffu, umin0, 1));
-			umin0 = fminf(umin0, __shfl_xor_sync(0xffffffffu, umin0, 2));
-			umin1 = fminf(umin1, __shfl_xor_sync(0xffffffffu, umin1, 1));
-			umin1 = fminf(umin1, __shfl_xor_sync(0xffffffffu, umin1, 2));
-			// shortlist masks: bit (nt*2 + e) of mask0 / mask1
-			unsigned long long mask0 = 0ull, mask1 = 0ull;
-#pragma unroll
-			for (int nt = 0; nt < 32; ++nt) {
-				const float2 eno = __ldg(reinterpret_cast<const float2*>(w.emb_norm + nt * 8 + 2 * t));
-				if (sc[nt][0] - (cb0 * eno.x + 1e-4f) <= umin0) mask0 |= 1ull << (nt * 2);
-				if (sc[nt][1] - (cb0 * eno.y + 1e-4f) <= umin0) mask0 |= 1ull << (nt * 2 + 1);
-				if (sc[nt][2] - (cb1 * eno.x + 1e-4f) <= umin1) mask1 |= 1ull << (nt * 2);
-				if (sc[nt][3] - (cb1 * eno.y + 1e-4f) <= umin1) mask1 |= 1ull << (nt * 2 + 1);
-			}
-			// exact fp32 re-scoring of the shortlist (ascending code order within the lane)
-			float best0 = INFINITY, best1 = INFINITY;
-			int bi0 = 0x7fffffff, bi1 = 0x7fffffff;
-#pragma unroll 1
-			for (int rr = 0; rr < 2; ++rr) {
-				unsigned long long mask = rr ? mask1 : mask0;
-				const int pos = rr ? p1 : p0;
-				const float zz = rr ? zz1 : zz0;
-				float best = INFINITY;
-				int bi = 0x7fffffff;
-				while (mask) {
-					const int b = __ffsll((long long)mask) - 1;
-					mask &= mask - 1;
-					const int code = (b >> 1) * 8 + 2 * t + (b & 1);
-					const float4* er = reinterpret_cast<const float4*>(w.emb + code * 128);
-					float dot = 0.f;
-#pragma unroll 4
-					for (int d4i = 0; d4i < 32; ++d4i) {
-						const float4 e = __ldg(er + d4i);
-						dot = fmaf(Z[(d4i * 4 + 0) * 128 + pos], e.x, dot);
-						dot = fmaf(Z[(d4i * 4 + 1) * 128 + pos], e.y, dot);
-						dot = fmaf(Z[(d4i * 4 + 2) * 128 + pos], e.z, dot);
-						dot = fmaf(Z[(d4i * 4 + 3) * 128 + pos], e.w, dot);
-					}
-					const float dist = (zz + __ldg(w.emb_sq + code)) - 2.f * dot;
-					if (dist < best) {  // codes ascend within the lane, so strict < keeps the first minimum
-						best = dist;
-						bi = code;
-					}
+				for (int d = 0; d < 128; ++d) {
+					const float q0 = Z[d * kPos + p0], q1 = Z[d * kPos + p1];
+					zz0 = fmaf(q0, q0, zz0);
+					zz1 = fmaf(q1, q1, zz1);
 				}
-				if (rr) { best1 = best; bi1 = bi; } else { best0 = best; bi0 = bi; }
-			}
-			// combine the four lanes of a quad: smallest distance, then smallest code (torch.argmin's first minimum)
+				const float cb0 = 0.0078125f * 1.07f * sqrtf(zz0), cb1 = 0.0078125f * 1.07f * sqrtf(zz1);
+				const int code0 = ch * 128 + 2 * t;
+				// scores -> a_k, and the row-wise minimum of the upper bounds
+				float umin0 = INFINITY, umin1 = INFINITY;
 #pragma unroll
-			for (int o = 1; o <= 2; o <<= 1) {
-				float ob = __shfl_xor_sync(0xffffffffu, best0, o);
-				int oi = __shfl_xor_sync(0xffffffffu, bi0, o);
-				if (ob < best0 || (ob == best0 && oi < bi0)) { best0 = ob; bi0 = oi; }
-				ob = __shfl_xor_sync(0xffffffffu, best1, o);
-				oi = __shfl_xor_sync(0xffffffffu, bi1, o);
-				if (ob < best1 || (ob == best1 && oi < bi1)) { best1 = ob; bi1 = oi; }
-			}
-			if (t == 0) {
-				const int64_t l0 = grp * 2 + (p0 >> 6), l1 = grp * 2 + (p1 >> 6);
-				if (l0 < n_leaves) indices[l0 * 64 + (p0 & 63)] = (uint8_t)bi0;  // p = (d*4+h)*4+w == view(B,4,4,4)
-				if (l1 < n_leaves) indices[l1 * 64 + (p1 & 63)] = (uint8_t)bi1;
+				for (int nt = 0; nt < 16; ++nt) {
+					const float2 esq = __ldg(reinterpret_cast<const float2*>(w.emb_sq + code0 + nt * 8));
+					const float2 eno = __ldg(reinterpret_cast<const float2*>(w.emb_norm + code0 + nt * 8));
+					sc[nt][0] = esq.x - 2.f * sc[nt][0];
+					sc[nt][1] = esq.y - 2.f * sc[nt][1];
+					sc[nt][2] = esq.x - 2.f * sc[nt][2];
+					sc[nt][3] = esq.y - 2.f * sc[nt][3];
+					umin0 = fminf(umin0, fminf(sc[nt][0] + (cb0 * eno.x + 1e-4f), sc[nt][1] + (cb0 * eno.y + 1e-4f)));
+					umin1 = fminf(umin1, fminf(sc[nt][2] + (cb1 * eno.x + 1e-4f), sc[nt][3] + (cb1 * eno.y + 1e-4f)));
+				}
+				umin0 = fminf(umin0, __shfl_xor_sync(0xffffffffu, umin0, 1));
+				umin0 = fminf(umin0, __shfl_xor_sync(0xffffffffu, umin0, 2));
+				umin1 = fminf(umin1, __shfl_xor_sync(0xffffffffu, umin1, 1));
+				umin1 = fminf(umin1, __shfl_xor_sync(0xffffffffu, umin1, 2));
+				if (t == 0) {
+					xch_u[warp * 16 + g] = umin0;
+					xch_u[warp * 16 + g + 8] = umin1;
+				}
+				__syncthreads();
+				{
+					const int partner = ch ? warp - kHalf : warp + kHalf;
+					umin0 = fminf(umin0, xch_u[partner * 16 + g]);
+					umin1 = fminf(umin1, xch_u[partner * 16 + g + 8]);
+				}
+				// shortlist masks: bit (nt*2 + e)
+				uint32_t mask0 = 0u, mask1 = 0u;
+#pragma unroll
+				for (int nt = 0; nt < 16; ++nt) {
+					const float2 eno = __ldg(reinterpret_cast<const float2*>(w.emb_norm + code0 + nt * 8));
+					if (sc[nt][0] - (cb0 * eno.x + 1e-4f) <= umin0) mask0 |= 1u << (nt * 2);
+					if (sc[nt][1] - (cb0 * eno.y + 1e-4f) <= umin0) mask0 |= 1u << (nt * 2 + 1);
+					if (sc[nt][2] - (cb1 * eno.x + 1e-4f) <= umin1) mask1 |= 1u << (nt * 2);
+					if (sc[nt][3] - (cb1 * eno.y + 1e-4f) <= umin1) mask1 |= 1u << (nt * 2 + 1);
+				}
+				// exact fp32 re-scoring of the shortlist (ascending code order within the lane)
+				float best0 = INFINITY, best1 = INFINITY;
+				int bi0 = 0x7fffffff, bi1 = 0x7fffffff;
+#pragma unroll 1
+				for (int rr = 0; rr < 2; ++rr) {
+					uint32_t mask = rr ? mask1 : mask0;
+					const int pos = rr ? p1 : p0;
+					const float zz = rr ? zz1 : zz0;
+					float best = INFINITY;
+					int bi = 0x7fffffff;
+					while (mask) {
+						const int b = __ffs((int)mask) - 1;
+						mask &= mask - 1;
+						const int code = code0 + (b >> 1) * 8 + (b & 1);
+						const float4* er = reinterpret_cast<const float4*>(w.emb + code * 128);
+						float dot = 0.f;
+#pragma unroll 4
+						for (int d4i = 0; d4i < 32; ++d4i) {
+							const float4 e = __ldg(er + d4i);
+							dot = fmaf(Z[(d4i * 4 + 0) * kPos + pos], e.x, dot);
+							dot = fmaf(Z[(d4i * 4 + 1) * kPos + pos], e.y, dot);
+							dot = fmaf(Z[(d4i * 4 + 2) * kPos + pos], e.z, dot);
+							dot = fmaf(Z[(d4i * 4 + 3) * kPos + pos], e.w, dot);
+						}
+						const float dist = (zz + __ldg(w.emb_sq + code)) - 2.f * dot;
+						if (dist < best) {  // codes ascend within the lane, so strict < keeps the first minimum
+							best = dist;
+							bi = code;
+						}
+					}
+					if (rr) { best1 = best; bi1 = bi; } else { best0 = best; bi0 = bi; }
+				}
+				// combine the four lanes of a quad: smallest distance, then smallest code (torch.argmin's first minimum)
+#pragma unroll
+				for (int o = 1; o <= 2; o <<= 1) {
+					float ob = __shfl_xor_sync(0xffffffffu, best0, o);
+					int oi = __shfl_xor_sync(0xffffffffu, bi0, o);
+					if (ob < best0 || (ob == best0 && oi < bi0)) { best0 = ob; bi0 = oi; }
+					ob = __shfl_xor_sync(0xffffffffu, best1, o);
+					oi = __shfl_xor_sync(0xffffffffu, bi1, o);
+					if (ob < best1 || (ob == best1 && oi < bi1)) { best1 = ob; bi1 = oi; }
+				}
+				// ... then the two code halves: the upper-half warp hands its winners to the lower-half warp
+				if (ch == 1 && t == 0) {
+					xch_d[warp * 16 + g] = best0;
+					xch_i[warp * 16 + g] = bi0;
+					xch_d[warp * 16 + g + 8] = best1;
+					xch_i[warp * 16 + g + 8] = bi1;
+				}
+				__syncthreads();
+				if (ch == 0 && t == 0) {
+					const int pw = warp + kHalf;
+					float ob = xch_d[pw * 16 + g];
+					if (ob < best0) bi0 = xch_i[pw * 16 + g];  // equal distances keep the lower code, which is ours
+					ob = xch_d[pw * 16 + g + 8];
+					if (ob < best1) bi1 = xch_i[pw * 16 + g + 8];
+					const int64_t l0 = grp * kLeaves + (p0 >> 6), l1 = grp * kLeaves + (p1 >> 6);
+					if (l0 < n_leaves) indices[l0 * 64 + (p0 & 63)] = (uint8_t)bi0;  // p = (d*4+h)*4+w == view(B,4,4,4)
+					if (l1 < n_leaves) indices[l1 * 64 + (p1 & 63)] = (uint8_t)bi1;
+				}
 			}
 		}
 		__syncthreads();
@@ -689,7 +792,7 @@ cudaError_t configure_encode_fp32() {
 cudaError_t launch_encode_fp32(const EncoderWeights& w, const EncoderUnits& units, const float* dev_leaves,
                                int64_t n_leaves, uint8_t* dev_indices, int num_sms, cudaStream_t stream) {
 	if (n_leaves <= 0) return cudaSuccess;
-	const int64_t groups = (n_leaves + 1) / 2;
+	const int64_t groups = (n_leaves + kLeaves - 1) / kLeaves;
 	const int grid = (int)(groups < (int64_t)num_sms ? groups : (int64_t)num_sms);
 	encode_fp32_kernel<<<grid, kThreads, kSmemFloats * sizeof(float), stream>>>(w, units, dev_leaves, n_leaves, dev_indices);
 	return cudaGetLastError();

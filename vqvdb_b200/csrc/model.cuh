@@ -27,11 +27,12 @@ struct EncoderWeights {
 };
 
 // The encoder consumes its weights as a fixed stream of "units" (<= 8 KB) through a shared-memory ring:
-// pre.0 (1), res16 conv1/conv2 (4+4, 4 input channels each), down (16, one input channel each), res32
+// pre.0 (1), res16 conv1/conv2 (4+4, 4 input channels each), pre.0 again (1, for the re-derived residual),
+// down (16, one input channel each), res32
 // conv1/conv2 (16+16, 2 input channels each), proj (2, 16 input channels each) — slices of the transposed
 // fp32 tables above — then the codebook as 8 bf16 tiles [64 codes][64 dims] (pre-swizzled like the decoder's
-// weight units) for the tensor-core shortlist pass of the VQ.
-constexpr int kEncUnits = 67;
+// weight units) for the tensor-core shortlist pass of the VQ, streamed twice (one round per 96 positions).
+constexpr int kEncUnits = 76;
 struct EncoderUnits {
 	const void* ptr[kEncUnits];   // 16-byte aligned
 	uint32_t bytes[kEncUnits];    // multiple of 16, <= 8192
