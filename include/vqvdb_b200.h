@@ -55,8 +55,10 @@ typedef enum vqvdb_b200_status {
 typedef enum vqvdb_b200_decode_precision {
 	VQVDB_B200_DECODE_DEFAULT = 0, /* fastest path that meets the 0.1 dB PSNR budget */
 	VQVDB_B200_DECODE_FP32 = 1,    /* CUDA-core fp32 path (bring-up / checking) */
-	VQVDB_B200_DECODE_BF16_TC = 2  /* tensor-core path: bf16 operands, fp32 accumulation */
+	VQVDB_B200_DECODE_BF16_TC = 2, /* tcgen05.mma + TMEM accumulators: bf16 operands, fp32 accumulation */
+	VQVDB_B200_DECODE_BF16_MMA = 3 /* same arithmetic on the legacy warp-level mma.sync path */
 } vqvdb_b200_decode_precision;
+#define VQVDB_B200_DECODE_DEFAULT_KIND VQVDB_B200_DECODE_BF16_MMA
 
 /* Replaces CodecConfig{device, source} (IVQVAECodec.hpp:85-89).  Zero-initialise, set
  * struct_size = sizeof(vqvdb_b200_config), then fill what you need. */
@@ -104,7 +106,7 @@ VQVDB_B200_API int vqvdb_b200_synchronize(vqvdb_b200_codec* codec);
 
 /* Kernel launches issued by this codec since creation (bench.py's gpu_launches). */
 VQVDB_B200_API uint64_t vqvdb_b200_kernel_launches(const vqvdb_b200_codec* codec);
-/* Name of the decode path actually in use: "fp32" or "bf16_mma". */
+/* Name of the decode path actually in use: "fp32", "bf16_tcgen05" or "bf16_mma". */
 VQVDB_B200_API const char* vqvdb_b200_decode_path(const vqvdb_b200_codec* codec);
 
 /* Bring-up aid for the tensor-core decoder: runs it and also writes the fp32 activation after stage

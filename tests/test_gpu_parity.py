@@ -161,12 +161,13 @@ TC_MIN_PSNR_VS_REF = 55.0
 TC_MAX_ABS = 2e-2
 
 
-@pytest.fixture(scope="module")
-def codec_tc():
+@pytest.fixture(scope="module", params=["bf16_tc", "bf16_mma"])
+def codec_tc(request):
+    """Both tensor-core decoders: tcgen05/TMEM ("bf16_tc") and warp-level mma.sync ("bf16_mma")."""
     from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec
-    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, decode_precision="bf16_tc"), BackendType.B200)
+    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, decode_precision=request.param), BackendType.B200)
     assert c is not None
-    assert c.decode_path.startswith("bf16")
+    assert c.decode_path == {"bf16_tc": "bf16_tcgen05", "bf16_mma": "bf16_mma"}[request.param]
     yield c
     c.close()
 

@@ -104,7 +104,7 @@ class CodecConfig:
     source: Union[EmbeddedModel, str, os.PathLike] = field(default_factory=EmbeddedModel)
     device_index: int = 0            # extension: which GPU (the reference hard-codes 0)
     chunk_leaves: int = 0            # extension: pipeline chunk of the host-pointer calls
-    decode_precision: str = "default"  # "default" | "fp32" | "bf16_tc"
+    decode_precision: str = "default"  # "default" | "fp32" | "bf16_tc" (tcgen05) | "bf16_mma" (mma.sync)
 
     def __post_init__(self):
         if self.device is None:
@@ -130,7 +130,7 @@ class Tensor:
         return self.buffer
 
 
-_PRECISION = {"default": 0, "fp32": 1, "bf16_tc": 2}
+_PRECISION = {"default": 0, "fp32": 1, "bf16_tc": 2, "bf16_mma": 3}
 
 
 class B200Codec:

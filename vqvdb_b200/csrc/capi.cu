@@ -60,7 +60,7 @@ struct vqvdb_b200_codec {
 	cudaStream_t compute = nullptr;
 	float* arena = nullptr;  // every fp32 device weight table lives in this one allocation
 	uint8_t* mma_arena = nullptr;  // bf16 weight-unit stream + bf16 codebook of the tensor-core decoder
-	bool use_mma_decode = true;
+	int decode_kind = 2;  // 1 = fp32 FFMA, 2 = bf16 tcgen05/TMEM, 3 = bf16 mma.sync
 	vqvdb::DecoderMmaWeights dec_mma{};
 	vqvdb::EncoderWeights enc{};
 	vqvdb::EncoderUnits enc_units{};
@@ -293,7 +293,8 @@ void launch_encode(vqvdb_b200_codec& c, const float* d_leaves, int64_t n, uint8_
 }
 
 void launch_decode(vqvdb_b200_codec& c, const uint8_t* d_idx, int64_t n, float* d_vox, cudaStream_t st) {
-	if (c.use_mma_decode) CUDA_TRY(vqvdb::launch_decode_mma(c.dec_mma, d_idx, n, d_vox, c.num_sms, st));
+	if (c.decode_kind == 2) CUDA_TRY(vqvdb::launch_decode_tc(c.dec_mma, d_idx, n, d_vox, c.num_sms, st));
+	else if (c.decode_kind == 3) CUDA_TRY(vqvdb::launch_decode_mma(c.dec_mma, d_idx, n, d_vox, c.num_sms, st));
 	else CUDA_TRY(vqvdb::launch_decode_fp32(c.dec, d_idx, n, d_vox, c.num_sms, st));
 	if (n > 0) c.launches.fetch_add(1, std::memory_order_relaxed);
 }
@@ -361,14 +362,15 @@ int vqvdb_b200_create(const vqvdb_b200_config* cfg, vqvdb_b200_codec** out) {
 		} catch (const std::exception& e) {
 			return fail(nullptr, VQVDB_B200_ERR_BAD_WEIGHTS, e.what());
 		}
-		if (conf.decode_precision > VQVDB_B200_DECODE_BF16_TC)
+		if (conf.decode_precision > VQVDB_B200_DECODE_BF16_MMA)
 			return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "unknown decode_precision");
-		c->use_mma_decode = conf.decode_precision != VQVDB_B200_DECODE_FP32;
-		c->decode_path = c->use_mma_decode ? "bf16_mma" : "fp32";
+		c->decode_kind = conf.decode_precision == VQVDB_B200_DECODE_DEFAULT ? (int)VQVDB_B200_DECODE_DEFAULT_KIND : (int)conf.decode_precision;
+		c->decode_path = c->decode_kind == 2 ? "bf16_tcgen05" : c->decode_kind == 3 ? "bf16_mma" : "fp32";
 		CUDA_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
 		CUDA_TRY(vqvdb::configure_encode_fp32());
 		CUDA_TRY(vqvdb::configure_decode_fp32());
 		CUDA_TRY(vqvdb::configure_decode_mma());
+		CUDA_TRY(vqvdb::configure_decode_tc());
 	} catch (const std::exception& e) {
 		return translate(nullptr, e);
 	}
@@ -505,7 +507,8 @@ int vqvdb_b200_debug_decode_tap(vqvdb_b200_codec* c, const uint8_t* dev_indices,
 		return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "debug_decode_tap: bad arguments");
 	try {
 		CUDA_TRY(cudaSetDevice(c->device));
-		CUDA_TRY(vqvdb::launch_decode_mma(c->dec_mma, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
+		if (c->decode_kind == 3) CUDA_TRY(vqvdb::launch_decode_mma(c->dec_mma, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
+		else CUDA_TRY(vqvdb::launch_decode_tc(c->dec_mma, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
 	} catch (const std::exception& e) {
 		return translate(c, e);
 	}

@@ -44,4 +44,10 @@ cudaError_t launch_decode_mma(const DecoderMmaWeights& w, const uint8_t* dev_ind
                               float* dev_voxels, int num_sms, cudaStream_t stream, int tap_stage = -1,
                               float* tap_out = nullptr);
 
+// tcgen05 / TMEM version of the same decoder (decode_tc.cu); same weights, same arguments.
+cudaError_t configure_decode_tc();
+cudaError_t launch_decode_tc(const DecoderMmaWeights& w, const uint8_t* dev_indices, int64_t n_leaves,
+                             float* dev_voxels, int num_sms, cudaStream_t stream, int tap_stage = -1,
+                             float* tap_out = nullptr);
+
 }  // namespace vqvdb
