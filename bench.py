@@ -351,10 +351,11 @@ def main():
                                    "pipe": "fp32 FFMA", "pipe_peak_tflops": ffma_peak, "frac_of_pipe_peak": enc_tf / ffma_peak,
                                    "frac_of_bf16_tensor_peak": enc_tf / peak, "algorithmic_mflop_per_leaf": FLOP_ENCODE / 1e6,
                                    "hbm_gbs": BYTES_ENCODE * L / (enc_ms / 1e3) / 1e9},
-            "decode_mma_kernel": {"ms": dec_ms, "share_of_step": dec_ms / (enc_ms + dec_ms), "achieved_tflops": dec_tf,
-                                  "pipe": "tensor (mma.sync bf16)" if tensor_path else "fp32 FFMA",
-                                  "pipe_peak_tflops": hmma_peak if tensor_path else ffma_peak,
-                                  "frac_of_pipe_peak": dec_tf / (hmma_peak if tensor_path else ffma_peak),
+            ("decode_tc_kernel" if codec.decode_path == "bf16_tcgen05" else "decode_mma_kernel" if tensor_path else "decode_fp32_kernel"): {"ms": dec_ms, "share_of_step": dec_ms / (enc_ms + dec_ms), "achieved_tflops": dec_tf,
+                                  "pipe": ("tensor (tcgen05.mma bf16, TMEM accumulators)" if codec.decode_path == "bf16_tcgen05" else
+                                           "tensor (mma.sync bf16)" if tensor_path else "fp32 FFMA"),
+                                  "pipe_peak_tflops": (peak if codec.decode_path == "bf16_tcgen05" else hmma_peak if tensor_path else ffma_peak),
+                                  "frac_of_pipe_peak": dec_tf / (peak if codec.decode_path == "bf16_tcgen05" else hmma_peak if tensor_path else ffma_peak),
                                   "frac_of_bf16_tensor_peak": dec_tf / peak, "algorithmic_mflop_per_leaf": FLOP_DECODE / 1e6,
                                   "hbm_gbs": BYTES_DECODE * L / (dec_ms / 1e3) / 1e9},
         }

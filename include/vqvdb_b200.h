@@ -58,7 +58,7 @@ typedef enum vqvdb_b200_decode_precision {
 	VQVDB_B200_DECODE_BF16_TC = 2, /* tcgen05.mma + TMEM accumulators: bf16 operands, fp32 accumulation */
 	VQVDB_B200_DECODE_BF16_MMA = 3 /* same arithmetic on the legacy warp-level mma.sync path */
 } vqvdb_b200_decode_precision;
-#define VQVDB_B200_DECODE_DEFAULT_KIND VQVDB_B200_DECODE_BF16_MMA
+#define VQVDB_B200_DECODE_DEFAULT_KIND VQVDB_B200_DECODE_BF16_TC
 
 /* Replaces CodecConfig{device, source} (IVQVAECodec.hpp:85-89).  Zero-initialise, set
  * struct_size = sizeof(vqvdb_b200_config), then fill what you need. */

@@ -503,7 +503,7 @@ int vqvdb_b200_decode(vqvdb_b200_codec* c, const uint8_t* host_indices, int64_t 
 int vqvdb_b200_debug_decode_tap(vqvdb_b200_codec* c, const uint8_t* dev_indices, int64_t n, int stage, float* dev_tap,
                                 float* dev_voxels, void* stream) {
 	if (!c) return VQVDB_B200_ERR_INVALID_ARGUMENT;
-	if (n < 0 || stage < 0 || stage > 2 || (n > 0 && (!dev_indices || !dev_tap || !dev_voxels)))
+	if (n < 0 || stage < 0 || (stage > 2 && stage != 100) || (n > 0 && (!dev_indices || !dev_tap || !dev_voxels)))
 		return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "debug_decode_tap: bad arguments");
 	try {
 		CUDA_TRY(cudaSetDevice(c->device));

@@ -120,14 +120,19 @@ struct Worker {
 	uint32_t unit = 0;              // units staged so far (same sequence in every worker and in the control thread)
 	uint32_t passes = 0;            // accumulator hand-overs so far (parity of d_full)
 	uint32_t bars, tmem_lane;       // mbarrier base; tmem base + (quad*32 << 16)
+	long long t_wait = 0, t_stage = 0, t_acc = 0;  // kProf only: cycles waiting for a free A buffer / staging / waiting for d_full
 };
+template <bool P> __device__ __forceinline__ long long prof_clock() { return P ? clock64() : 0; }
 
 // Stage one A unit: this thread's row (64 bf16 channels = 32 words) -> its TMEM lane, then hand the buffer to the MMA.
+template <bool kProf>
 __device__ __forceinline__ void stage_unit(Worker& wk, bool valid, uint32_t src_row /*smem addr of the 128-B half row*/, uint32_t swz) {
 	const uint32_t buf = wk.unit & 1u;
+	const long long c0 = prof_clock<kProf>();
 	if (wk.lane == 0) mbar_wait(bar_a_empty(wk.bars, wk.tile, buf), ((wk.unit >> 1) & 1u) ^ 1u);
 	__syncwarp();
 	tc_fence_after();
+	const long long c1 = prof_clock<kProf>();
 	uint32_t r[32];
 	if (valid) {
 #pragma unroll
@@ -145,10 +150,14 @@ __device__ __forceinline__ void stage_unit(Worker& wk, bool valid, uint32_t src_
 	__syncwarp();
 	if (wk.lane == 0) mbar_arrive(bar_a_full(wk.bars, wk.tile, buf));
 	++wk.unit;
+	if (kProf) {
+		wk.t_wait += c1 - c0;
+		wk.t_stage += prof_clock<kProf>() - c1;
+	}
 }
 
 // One 3x3x3 conv: stage 27 * HALVES units from the leaf's activation rows (ROW_BYTES = HALVES * 128).
-template <int HALVES>
+template <int HALVES, bool kProf>
 __device__ __forceinline__ void stage_conv(Worker& wk, uint32_t act_base) {
 	constexpr uint32_t ROW_BYTES = HALVES * 128;
 #pragma unroll 1
@@ -157,15 +166,18 @@ __device__ __forceinline__ void stage_conv(Worker& wk, uint32_t act_base) {
 		const bool ok = (unsigned)(wk.d + td - 1) < 4u && (unsigned)(wk.h + th - 1) < 4u && (unsigned)(wk.w + tw - 1) < 4u;
 		const int p2 = wk.pos + (td - 1) * 16 + (th - 1) * 4 + (tw - 1);
 #pragma unroll
-		for (int half = 0; half < HALVES; ++half) stage_unit(wk, ok, act_base + (uint32_t)p2 * ROW_BYTES + half * 128, (uint32_t)p2 & 7u);
+		for (int half = 0; half < HALVES; ++half) stage_unit<kProf>(wk, ok, act_base + (uint32_t)p2 * ROW_BYTES + half * 128, (uint32_t)p2 & 7u);
 	}
 }
 
 // Wait until this tile's accumulator holds the finished layer.
+template <bool kProf>
 __device__ __forceinline__ void wait_accumulator(Worker& wk) {
+	const long long c0 = prof_clock<kProf>();
 	mbar_wait(bar_d_full(wk.bars, wk.tile), wk.passes & 1u);
 	tc_fence_after();
 	++wk.passes;
+	if (kProf) wk.t_acc += prof_clock<kProf>() - c0;
 }
 
 // Sum `n` per-thread values over the 64 rows of this thread's leaf (2 warps): butterfly + one exchange.
@@ -236,6 +248,7 @@ __device__ __forceinline__ void gn_stats_from_tmem(const Worker& wk, const float
 	}
 }
 
+template <bool kProf>
 __global__ void __launch_bounds__(kThreads, 1)
 decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices, int64_t n_leaves, float* __restrict__ voxels,
                  int tap_stage, float* __restrict__ tap_out) {
@@ -280,6 +293,8 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 		if (lane == 0) {
 			const uint32_t t = warp - kWorkWarps;
 			uint32_t unit = 0;
+			long long tw = 0, ta = 0, ti = 0;
+			const long long tstart = prof_clock<kProf>();
 			for (int64_t g = 0; g < my_groups; ++g) {
 #pragma unroll 1
 				for (int u = 0; u < kDecUnitsTotal; ++u) {
@@ -287,9 +302,12 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 					// position of this unit inside its layer pass: stem = 54 units, then six passes of 27
 					const int in_pass = u < 54 ? u : (u - 54) % 27;
 					const bool last = u < 54 ? (u == 53) : (in_pass == 26);
+					const long long c0 = prof_clock<kProf>();
 					mbar_wait(bar_w_full(bars, s), (unit / kStages) & 1u);
+					const long long c1 = prof_clock<kProf>();
 					mbar_wait(bar_a_full(bars, t, buf), (unit >> 1) & 1u);
 					tc_fence_after();
+					const long long c2 = prof_clock<kProf>();
 					const uint64_t bdesc = make_desc_sw128(ring + s * kUnitBytes);
 #pragma unroll
 					for (uint32_t kk = 0; kk < 4; ++kk)
@@ -299,7 +317,16 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 					if (last) tc_commit(bar_d_full(bars, t));
 					tc_commit(bar_w_empty(bars, s));
 					++unit;
+					if (kProf) {
+						tw += c1 - c0;
+						ta += c2 - c1;
+						ti += prof_clock<kProf>() - c2;
+					}
 				}
+			}
+			if (kProf && tap_out) {
+				float* o = tap_out + ((size_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+				o[0] = (float)tw; o[1] = (float)ta; o[2] = (float)ti; o[3] = (float)(prof_clock<kProf>() - tstart);
 			}
 		} else if (lane == 1 && warp == kWorkWarps) {
 #pragma unroll 1
@@ -359,8 +386,8 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 
 			float mean[8], rstd[8];
 			// ---- stem.0 (128->64) ; stem.1 GroupNorm + ReLU -> x ; gn1 + ReLU -> conv1 input ----
-			stage_conv<2>(wk, a_base);
-			wait_accumulator(wk);  // all stem MMAs done => every read of Q is done too
+			stage_conv<2, kProf>(wk, a_base);
+			wait_accumulator<kProf>(wk);  // all stem MMAs done => every read of Q is done too
 			gn_stats_from_tmem(wk, w.stem_b, exch, mean, rstd);
 			{
 				float st[16];
@@ -406,8 +433,8 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 			named_bar_sync(1 + wk.leaf_slot, 64);  // both warps' rows of the conv input are in place
 
 			// ---- res conv1 ; gn2 + ReLU -> conv2 input ----
-			stage_conv<1>(wk, a_base);
-			wait_accumulator(wk);
+			stage_conv<1, kProf>(wk, a_base);
+			wait_accumulator<kProf>(wk);
 			gn_stats_from_tmem(wk, w.res.c1_b, exch, mean, rstd);
 #pragma unroll
 			for (int half = 0; half < 2; ++half) {
@@ -424,8 +451,8 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 			named_bar_sync(1 + wk.leaf_slot, 64);
 
 			// ---- res conv2 ; x + 0.1 * (.) ; ChannelAttention(64) -> up_conv input ----
-			stage_conv<1>(wk, a_base);
-			wait_accumulator(wk);
+			stage_conv<1, kProf>(wk, a_base);
+			wait_accumulator<kProf>(wk);
 			{
 				// x' = x + 0.1 (acc + b), written back into this thread's x row
 #pragma unroll
@@ -493,8 +520,8 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 			for (int j = 0; j < 8; ++j) out[j] = 0.f;
 #pragma unroll 1
 			for (int np = 0; np < 4; ++np) {
-				stage_conv<1>(wk, a_base);
-				wait_accumulator(wk);
+				stage_conv<1, kProf>(wk, a_base);
+				wait_accumulator<kProf>(wk);
 				// channel c = np*64 + cc = oc*8 + rd*4 + rh*2 + rw  ->  oc_local = cc>>3, (rd, rh, rw) = bits of cc&7
 				// P[oc_local][(2d+rd)][(2h+rh)][(2w+rw)] bf16 in the x region (8 KB per leaf)
 #pragma unroll
@@ -563,6 +590,10 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 				__stcs(dst + 1, o1);
 			}
 		}
+		if (kProf && tap_out) {
+			float* o = tap_out + ((size_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+			o[0] = (float)wk.t_wait; o[1] = (float)wk.t_stage; o[2] = (float)wk.t_acc; o[3] = 0.f;
+		}
 	}
 
 	// ---- teardown: everybody is done with TMEM before the owner frees it ----
@@ -574,7 +605,9 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 }  // namespace
 
 cudaError_t configure_decode_tc() {
-	return cudaFuncSetAttribute(decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+	cudaError_t e = cudaFuncSetAttribute(decode_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+	if (e != cudaSuccess) return e;
+	return cudaFuncSetAttribute(decode_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
 }
 
 cudaError_t launch_decode_tc(const DecoderMmaWeights& w, const uint8_t* dev_indices, int64_t n_leaves, float* dev_voxels,
@@ -582,7 +615,10 @@ cudaError_t launch_decode_tc(const DecoderMmaWeights& w, const uint8_t* dev_indi
 	if (n_leaves <= 0) return cudaSuccess;
 	const int64_t groups = (n_leaves + kLeavesPerCta - 1) / kLeavesPerCta;
 	const int grid = (int)(groups < (int64_t)num_sms ? groups : (int64_t)num_sms);
-	decode_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, tap_stage, tap_out);
+	if (tap_stage == 100)  // timing instrumentation: tap_out receives 4 floats per thread (see tools/tc_pipeline_prof.py)
+		decode_tc_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, -1, tap_out);
+	else
+		decode_tc_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, tap_stage, tap_out);
 	return cudaGetLastError();
 }
 

@@ -20,17 +20,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Blocking wait.  The suspend-time hint lets the hardware park the thread until the phase completes (or the hint
+// expires) instead of re-issuing the probe: spinning waiters otherwise eat a third of the issue slots of a
+// warp-specialised kernel.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 	asm volatile(
 	    "{\n"
 	    ".reg .pred p;\n"
 	    "LAB_WAIT_%=:\n"
-	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
 	    "@p bra LAB_DONE_%=;\n"
 	    "bra LAB_WAIT_%=;\n"
 	    "LAB_DONE_%=:\n"
 	    "}\n" ::"r"(bar),
-	    "r"(parity)
+	    "r"(parity), "r"(0x989680)
 	    : "memory");
 }
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
