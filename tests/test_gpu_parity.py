@@ -220,3 +220,59 @@ def test_tc_decode_ragged_and_deterministic(codec_tc, codec):
         assert np.array_equal(_decode(codec_tc, idx[:n]), full[:n])
     ref32 = _decode(codec, idx[:256])
     assert synth.psnr(full[:256], ref32) >= TC_MIN_PSNR_VS_REF
+
+
+# ---------------------------------------------------------------------------------------------
+# Config 4: the reference's vec3 architecture (EncoderVec3 / DecoderVec3) with the seeded weight pack of
+# tools/weights_pack.py vec3, through the same C-ABI (CodecConfig.source = path of the pack).
+# Goldens come from the reference's own Python classes (tools/make_goldens.py).
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def codec_vec3():
+    import os
+    import subprocess
+    import sys
+    from conftest import REPO
+    from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec
+    pack = os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw")
+    if not os.path.exists(pack):
+        subprocess.check_call([sys.executable, os.path.join(REPO, "tools", "weights_pack.py"), "vec3"])
+    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack), BackendType.B200)
+    assert c is not None and c.channels == 3
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name,gen", [("vec3_smoke256_seed5", lambda: synth.smoke_leaves(256, seed=5, channels=3)),
+                                      ("vec3_noise64_seed6", lambda: synth.noise_leaves(64, seed=6, channels=3))])
+def test_vec3_matches_reference_classes(codec_vec3, name, gen):
+    import hashlib
+    g = golden(name)
+    x = gen()
+    assert hashlib.sha256(x.tobytes()).hexdigest() == str(g["input_sha256"])
+    idx = _encode(codec_vec3, x)
+    assert_indices_match(idx, g["indices"], g["margins"])
+    m = len(g["recon"])
+    rec = _decode(codec_vec3, g["indices"][:m])
+    assert rec.shape == (m, 3, 8, 8, 8)
+    assert np.abs(rec - g["recon"]).max() <= 5e-5       # fp32 path; tanh outputs in (-1, 1)
+
+
+def test_vec3_matches_c_oracle_and_chunking(codec_vec3):
+    import os
+    from conftest import REPO
+    from oracle.pyoracle import COracle
+    from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec
+    pack = os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw")
+    o = COracle(pack)
+    x = synth.smoke_leaves(96, seed=21, channels=3, sparse=True)
+    idx_o, margins = o.encode(x, with_margins=True)
+    idx = _encode(codec_vec3, x)
+    assert_indices_match(idx, idx_o, margins)
+    assert np.abs(_decode(codec_vec3, idx_o[:24]) - o.decode(idx_o[:24])).max() <= 5e-5
+    small = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack, chunk_leaves=20), BackendType.B200)
+    try:
+        assert np.array_equal(_encode(small, x), idx)           # 5 chunks through 3 slots share no scratch
+        assert np.array_equal(_decode(small, idx), _decode(codec_vec3, idx))
+    finally:
+        small.close()

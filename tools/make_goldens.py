@@ -74,6 +74,20 @@ def main():
                             n=np.array(x.shape[0]))
         print("%-20s n=%5d codes=%3d min_margin=%.3e  %s" % (
             name, x.shape[0], len(np.unique(idx)), float(margins.min()), path))
+    # config 4: the reference's vec3 architecture (python/VQVAE_v2.py:278-325) with the seeded weights of
+    # tools/weights_pack.py vec3 — the reference classes themselves, imported, run on CPU fp32.
+    vec3_pack = os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw")
+    if not os.path.exists(vec3_pack):
+        wp.main(["vec3"])
+    vmod = wp.load_vec3_reference_module(vec3_pack)
+    vmeta, _ = wp.read_pack(vec3_pack)
+    for name, x, n_recon in (("vec3_smoke256_seed5", synth.smoke_leaves(256, seed=5, channels=3), 32),
+                             ("vec3_noise64_seed6", synth.noise_leaves(64, seed=6, channels=3), 16)):
+        idx, margins, recon, rsum = reference_outputs(vmod, x, n_recon)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), input_sha256=np.array(hashlib.sha256(x.tobytes()).hexdigest()),
+                            indices=idx, margins=margins, recon=recon, recon_sum=np.array(rsum), n=np.array(x.shape[0]),
+                            pack_sha256=np.array(vmeta["sha256"]))
+        print("%-20s n=%5d codes=%3d min_margin=%.3e" % (name, x.shape[0], len(np.unique(idx)), float(margins.min())))
     # decode-only golden: random indices straight into the reference decoder (config 2)
     ridx = synth.random_indices(128, seed=1234)
     with torch.no_grad():

@@ -26,9 +26,9 @@ Usage:
     python tools/weights_pack.py float  [--out vqvdb_b200/weights/vqvae_float.vqw]
     python tools/weights_pack.py vec3   [--out vqvdb_b200/weights/vqvae_vec3_seed0.vqw]
 
-`float` needs /root/reference (this container only); `vec3` builds
-VQVAE(3, 128, 256, 0.25) from python/VQVAE_v2.py:328-345 with
-torch.manual_seed(0) because the reference ships no vec3 weights.
+`float` needs /root/reference (this container only); `vec3` draws seeded random
+weights for the reference's vec3 architecture (python/VQVAE_v2.py:278-325) with numpy
+only, because the reference ships no vec3 weights — reproducible anywhere.
 """
 from __future__ import annotations
 
@@ -129,12 +129,65 @@ def load_reference_module():
     return torch.jit.load(io.BytesIO(extract_reference_blob()), map_location="cpu").eval()
 
 
-def make_vec3_module(seed: int = 0, embedding_dim: int = 128, num_embeddings: int = 256):
+def vec3_state_dict(seed: int = 0, embedding_dim: int = 128, num_embeddings: int = 256) -> "OrderedDict[str, np.ndarray]":
+    """Seeded random weights for the reference's vec3 architecture (EncoderVec3 / DecoderVec3,
+    python/VQVAE_v2.py:278-325).  The reference ships no vec3 weights, so any fixed
+    weights of that architecture serve; they are drawn with numpy only, so the pack can be regenerated
+    bit-identically anywhere (including the GPU box, which has no reference tree).  Names and shapes are
+    exactly those of VQVAE(3, D, K).state_dict()."""
+    rng = np.random.default_rng(seed)
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+
+    def conv(name, cout, cin, k):
+        fan_in = cin * k ** 3
+        sd[name + ".weight"] = (rng.standard_normal((cout, cin, k, k, k)) * np.sqrt(2.0 / fan_in)).astype("<f4")
+        sd[name + ".bias"] = (rng.standard_normal(cout) * 0.05).astype("<f4")
+
+    def gn(name, c):
+        sd[name + ".weight"] = (1.0 + 0.1 * rng.standard_normal(c)).astype("<f4")
+        sd[name + ".bias"] = (0.1 * rng.standard_normal(c)).astype("<f4")
+
+    def res(name, c):
+        gn(name + ".gn1", c)
+        conv(name + ".conv1", c, c, 3)
+        gn(name + ".gn2", c)
+        conv(name + ".conv2", c, c, 3)
+
+    def attn(name, c, r=4):
+        sd[name + ".fc.0.weight"] = (rng.standard_normal((c // r, c)) * np.sqrt(2.0 / c)).astype("<f4")
+        sd[name + ".fc.2.weight"] = (rng.standard_normal((c, c // r)) * np.sqrt(2.0 / (c // r))).astype("<f4")
+
+    conv("encoder.pre.0", 64, 3, 3)
+    gn("encoder.pre.1", 64)
+    res("encoder.pre.3", 64)
+    conv("encoder.down1", 128, 64, 3)
+    res("encoder.res_stack.0", 128)
+    res("encoder.res_stack.1", 128)
+    attn("encoder.attn", 128)
+    conv("encoder.proj", embedding_dim, 128, 1)
+    emb = rng.standard_normal((num_embeddings, embedding_dim))
+    sd["quantizer.embedding"] = (emb / np.linalg.norm(emb, axis=1, keepdims=True) * 4.0).astype("<f4")
+    conv("decoder.stem.0", 128, embedding_dim, 3)
+    gn("decoder.stem.1", 128)
+    res("decoder.res_stack.0", 128)
+    res("decoder.res_stack.1", 128)
+    attn("decoder.attn", 128)
+    conv("decoder.up_conv", 256, 128, 3)
+    conv("decoder.final", 3, 32, 3)
+    return sd
+
+
+def load_vec3_reference_module(pack_path: str):
+    """The reference's own VQVAE(3, D, K) (python/VQVAE_v2.py:328-345, imported, never copied) carrying the pack's
+    weights — the oracle for config 4.  Needs /root/reference."""
     import torch
     sys.path.insert(0, os.path.join(REFERENCE_ROOT, "python"))
-    import VQVAE_v2  # noqa: E402  (reference model definition, imported, never copied)
-    torch.manual_seed(seed)
-    return VQVAE_v2.VQVAE(3, embedding_dim, num_embeddings, 0.25).eval()
+    import VQVAE_v2  # noqa: E402
+    meta, tensors = read_pack(pack_path)
+    m = VQVAE_v2.VQVAE(3, meta["embedding_dim"], meta["num_embeddings"], 0.25).eval()
+    missing, unexpected = m.load_state_dict({k: torch.from_numpy(v) for k, v in tensors.items()}, strict=False)
+    assert not unexpected and all(k.startswith("quantizer.") for k in missing), (missing, unexpected)
+    return m
 
 
 def main(argv=None):
@@ -148,9 +201,12 @@ def main(argv=None):
         cin = 1
         out = args.out or os.path.join(here, "vqvdb_b200", "weights", "vqvae_float.vqw")
     else:
-        mod = make_vec3_module()
-        cin = 3
         out = args.out or os.path.join(here, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw")
+        keep = vec3_state_dict(0)
+        emb = keep["quantizer.embedding"]
+        sha = write_pack(out, keep, 3, emb.shape[1], emb.shape[0])
+        print("%s  %d tensors  sha256=%s" % (out, len(keep), sha))
+        return
     sd = mod.state_dict()
     keep = OrderedDict()
     for k, v in sd.items():

@@ -15,6 +15,7 @@
 
 #include "../../include/vqvdb_b200.h"
 #include "decode_mma.cuh"
+#include "generic_model.cuh"
 #include "model.cuh"
 #include "weights.hpp"
 
@@ -62,6 +63,10 @@ struct vqvdb_b200_codec {
 	uint8_t* mma_arena = nullptr;  // bf16 weight-unit stream + bf16 codebook of the tensor-core decoder
 	int decode_kind = 2;  // 1 = fp32 FFMA, 2 = bf16 tcgen05/TMEM, 3 = bf16 mma.sync
 	vqvdb::DecoderMmaWeights dec_mma{};
+	bool generic = false;            // architecture-generic kernels (vec3 model) instead of the specialised ones
+	vqvdb::GenericModel gen{};
+	float* gen_scratch = nullptr;
+	int gen_grid = 0;
 	vqvdb::EncoderWeights enc{};
 	vqvdb::EncoderUnits enc_units{};
 	vqvdb::DecoderWeights dec{};
@@ -85,6 +90,7 @@ struct vqvdb_b200_codec {
 		}
 		if (arena) cudaFree(arena);
 		if (mma_arena) cudaFree(mma_arena);
+		if (gen_scratch) cudaFree(gen_scratch);
 	}
 };
 
@@ -251,6 +257,78 @@ void upload_float_model(vqvdb_b200_codec& c, const WeightPack& p) {
 	m.fin_b = d.fin_b;
 }
 
+void add_gres(ArenaBuilder& ab, const WeightPack& p, const std::string& prefix, vqvdb::GenericRes& r) {
+	ab.add(&r.gn1_w, p.get(prefix + ".gn1.weight"));
+	ab.add(&r.gn1_b, p.get(prefix + ".gn1.bias"));
+	ab.add(&r.c1_w, vqvdb::transpose_conv_weight(p.get(prefix + ".conv1.weight")));
+	ab.add(&r.c1_b, p.get(prefix + ".conv1.bias"));
+	ab.add(&r.gn2_w, p.get(prefix + ".gn2.weight"));
+	ab.add(&r.gn2_b, p.get(prefix + ".gn2.bias"));
+	ab.add(&r.c2_w, vqvdb::transpose_conv_weight(p.get(prefix + ".conv2.weight")));
+	ab.add(&r.c2_b, p.get(prefix + ".conv2.bias"));
+}
+
+// The reference's vec3 architecture (EncoderVec3 / DecoderVec3, python/VQVAE_v2.py:278-325), described at run time.
+void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
+	auto& m = c.gen;
+	m.cin = p.in_channels;
+	m.D = p.embedding_dim;
+	m.K = p.num_embeddings;
+	const bool vec3 = m.cin != 1;
+	const std::string down = vec3 ? "encoder.down1" : "encoder.down";
+	const PackTensor& dw = p.get(down + ".weight");
+	m.e_c0 = dw.dims[1];
+	m.e_c1 = dw.dims[0];
+	m.e_down_k = dw.dims[2];
+	m.e_gn0 = vec3 ? 8 : 4;
+	m.e_nres = vec3 ? 2 : 1;
+	m.e_red = p.get("encoder.attn.fc.0.weight").dims[0];
+	m.d_c = p.get("decoder.stem.0.weight").dims[0];
+	m.d_nres = vec3 ? 2 : 1;
+	m.d_red = p.get("decoder.attn.fc.0.weight").dims[0];
+	if (m.e_c0 > 64 || m.e_c1 > 128 || m.D > 128 || m.d_c > 128 || m.K % 4 || m.K > 256 || m.e_red > 64 || m.d_red > 64 ||
+	    p.get("decoder.up_conv.weight").dims[0] != 256)
+		throw std::runtime_error("weight pack: architecture outside the generic kernels' limits");
+	ArenaBuilder ab;
+	ab.add(&m.e_pre_w, vqvdb::transpose_conv_weight(p.get("encoder.pre.0.weight")));
+	ab.add(&m.e_pre_b, p.get("encoder.pre.0.bias"));
+	ab.add(&m.e_gn_w, p.get("encoder.pre.1.weight"));
+	ab.add(&m.e_gn_b, p.get("encoder.pre.1.bias"));
+	add_gres(ab, p, "encoder.pre.3", m.e_res0);
+	ab.add(&m.e_down_w, vqvdb::transpose_conv_weight(dw));
+	ab.add(&m.e_down_b, p.get(down + ".bias"));
+	for (int r = 0; r < m.e_nres; ++r) add_gres(ab, p, "encoder.res_stack." + std::to_string(r), m.e_res[r]);
+	ab.add(&m.e_fc0, p.get("encoder.attn.fc.0.weight"));
+	ab.add(&m.e_fc2, p.get("encoder.attn.fc.2.weight"));
+	ab.add(&m.e_proj_w, vqvdb::transpose_conv_weight(p.get("encoder.proj.weight")));
+	ab.add(&m.e_proj_b, p.get("encoder.proj.bias"));
+	const PackTensor& emb = p.get("quantizer.embedding");
+	std::vector<float> emb_sq((size_t)m.K);
+	for (int k = 0; k < m.K; ++k) {
+		float s = 0.f;
+		for (int d = 0; d < m.D; ++d) s += emb.data[(size_t)k * m.D + d] * emb.data[(size_t)k * m.D + d];
+		emb_sq[k] = s;
+	}
+	ab.add(&m.emb, emb);
+	ab.add(&m.emb_sq, emb_sq);
+	ab.add(&m.d_stem_w, vqvdb::transpose_conv_weight(p.get("decoder.stem.0.weight")));
+	ab.add(&m.d_stem_b, p.get("decoder.stem.0.bias"));
+	ab.add(&m.d_gn_w, p.get("decoder.stem.1.weight"));
+	ab.add(&m.d_gn_b, p.get("decoder.stem.1.bias"));
+	for (int r = 0; r < m.d_nres; ++r) add_gres(ab, p, "decoder.res_stack." + std::to_string(r), m.d_res[r]);
+	ab.add(&m.d_fc0, p.get("decoder.attn.fc.0.weight"));
+	ab.add(&m.d_fc2, p.get("decoder.attn.fc.2.weight"));
+	ab.add(&m.d_up_w, vqvdb::transpose_conv_weight(p.get("decoder.up_conv.weight")));
+	ab.add(&m.d_up_b, p.get("decoder.up_conv.bias"));
+	ab.add(&m.d_fin_w, vqvdb::transpose_conv_weight(p.get("decoder.final.weight")));
+	ab.add(&m.d_fin_b, p.get("decoder.final.bias"));
+	c.arena = ab.upload();
+	c.gen_grid = 2 * c.num_sms;
+	// one scratch area per pipeline slot plus one for the device-pointer entry points (slot index kSlots)
+	CUDA_TRY(cudaMalloc(&c.gen_scratch, (kSlots + 1) * vqvdb::generic_scratch_floats(c.gen_grid) * sizeof(float)));
+	c.generic = true;
+}
+
 void ensure_staging(vqvdb_b200_codec& c) {
 	if (c.staging_ready) return;
 	const size_t vox_bytes = (size_t)c.chunk * c.channels * 512 * sizeof(float);
@@ -287,12 +365,24 @@ int translate(vqvdb_b200_codec* c, const std::exception& e) {
 	return fail(c, VQVDB_B200_ERR_CUDA, e.what());
 }
 
-void launch_encode(vqvdb_b200_codec& c, const float* d_leaves, int64_t n, uint8_t* d_idx, cudaStream_t st) {
+void launch_encode(vqvdb_b200_codec& c, const float* d_leaves, int64_t n, uint8_t* d_idx, cudaStream_t st, int slot = kSlots) {
+	if (c.generic) {
+		float* scratch = c.gen_scratch + (size_t)slot * vqvdb::generic_scratch_floats(c.gen_grid);
+		CUDA_TRY(vqvdb::launch_encode_generic(c.gen, d_leaves, n, d_idx, scratch, c.gen_grid, st));
+		if (n > 0) c.launches.fetch_add(1, std::memory_order_relaxed);
+		return;
+	}
 	CUDA_TRY(vqvdb::launch_encode_fp32(c.enc, c.enc_units, d_leaves, n, d_idx, c.num_sms, st));
 	if (n > 0) c.launches.fetch_add(1, std::memory_order_relaxed);
 }
 
-void launch_decode(vqvdb_b200_codec& c, const uint8_t* d_idx, int64_t n, float* d_vox, cudaStream_t st) {
+void launch_decode(vqvdb_b200_codec& c, const uint8_t* d_idx, int64_t n, float* d_vox, cudaStream_t st, int slot = kSlots) {
+	if (c.generic) {
+		float* scratch = c.gen_scratch + (size_t)slot * vqvdb::generic_scratch_floats(c.gen_grid);
+		CUDA_TRY(vqvdb::launch_decode_generic(c.gen, d_idx, n, d_vox, scratch, c.gen_grid, st));
+		if (n > 0) c.launches.fetch_add(1, std::memory_order_relaxed);
+		return;
+	}
 	if (c.decode_kind == 2) CUDA_TRY(vqvdb::launch_decode_tc(c.dec_mma, d_idx, n, d_vox, c.num_sms, st));
 	else if (c.decode_kind == 3) CUDA_TRY(vqvdb::launch_decode_mma(c.dec_mma, d_idx, n, d_vox, c.num_sms, st));
 	else CUDA_TRY(vqvdb::launch_decode_fp32(c.dec, d_idx, n, d_vox, c.num_sms, st));
@@ -354,9 +444,9 @@ int vqvdb_b200_create(const vqvdb_b200_config* cfg, vqvdb_b200_codec** out) {
 			c->channels = pack.in_channels;
 			c->D = pack.embedding_dim;
 			c->K = pack.num_embeddings;
-			if (c->channels != 1 || c->D != 128 || c->K != 256)
-				return fail(nullptr, VQVDB_B200_ERR_UNSUPPORTED, "only the float model (C=1, D=128, K=256) is supported by this build");
-			upload_float_model(*c, pack);
+			if (c->channels == 1 && c->D == 128 && c->K == 256) upload_float_model(*c, pack);
+			else if (c->channels == 3) upload_generic_model(*c, pack);  // vec3 architecture: generic fp32 kernels
+			else return fail(nullptr, VQVDB_B200_ERR_UNSUPPORTED, "unsupported model: expected the float (C=1, D=128, K=256) or vec3 (C=3) architecture");
 		} catch (const CudaError&) {
 			throw;
 		} catch (const std::exception& e) {
@@ -365,7 +455,7 @@ int vqvdb_b200_create(const vqvdb_b200_config* cfg, vqvdb_b200_codec** out) {
 		if (conf.decode_precision > VQVDB_B200_DECODE_BF16_MMA)
 			return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "unknown decode_precision");
 		c->decode_kind = conf.decode_precision == VQVDB_B200_DECODE_DEFAULT ? (int)VQVDB_B200_DECODE_DEFAULT_KIND : (int)conf.decode_precision;
-		c->decode_path = c->decode_kind == 2 ? "bf16_tcgen05" : c->decode_kind == 3 ? "bf16_mma" : "fp32";
+		c->decode_path = c->generic ? "fp32_generic" : c->decode_kind == 2 ? "bf16_tcgen05" : c->decode_kind == 3 ? "bf16_mma" : "fp32";
 		CUDA_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
 		CUDA_TRY(vqvdb::configure_encode_fp32());
 		CUDA_TRY(vqvdb::configure_decode_fp32());
@@ -448,7 +538,7 @@ int vqvdb_b200_encode(vqvdb_b200_codec* c, const float* host_leaves, int64_t n, 
 				src = s.h_vox;
 			}
 			CUDA_TRY(cudaMemcpyAsync(s.d_vox, src, (size_t)cnt * leaf_elems * sizeof(float), cudaMemcpyHostToDevice, s.stream));
-			launch_encode(*c, s.d_vox, cnt, s.d_idx, s.stream);
+			launch_encode(*c, s.d_vox, cnt, s.d_idx, s.stream, i % kSlots);
 			uint8_t* dst = out_direct ? host_indices + (size_t)done * 64 : s.h_idx;
 			CUDA_TRY(cudaMemcpyAsync(dst, s.d_idx, (size_t)cnt * 64, cudaMemcpyDeviceToHost, s.stream));
 			CUDA_TRY(cudaEventRecord(s.done, s.stream));
@@ -484,7 +574,7 @@ int vqvdb_b200_decode(vqvdb_b200_codec* c, const uint8_t* host_indices, int64_t 
 				src = s.h_idx;
 			}
 			CUDA_TRY(cudaMemcpyAsync(s.d_idx, src, (size_t)cnt * 64, cudaMemcpyHostToDevice, s.stream));
-			launch_decode(*c, s.d_idx, cnt, s.d_vox, s.stream);
+			launch_decode(*c, s.d_idx, cnt, s.d_vox, s.stream, i % kSlots);
 			float* dst = out_direct ? host_voxels + (size_t)done * leaf_elems : s.h_vox;
 			CUDA_TRY(cudaMemcpyAsync(dst, s.d_vox, (size_t)cnt * leaf_elems * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
 			CUDA_TRY(cudaEventRecord(s.done, s.stream));
