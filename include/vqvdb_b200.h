@@ -60,6 +60,16 @@ typedef enum vqvdb_b200_decode_precision {
 } vqvdb_b200_decode_precision;
 #define VQVDB_B200_DECODE_DEFAULT_KIND VQVDB_B200_DECODE_BF16_TC
 
+/* Encoder arithmetic.  Both paths are fp32-faithful (index parity with the reference is a bit-exactness requirement):
+ * the tensor-core path splits every operand into two fp16 planes (22 significant bits, three products, fp32
+ * accumulation) and re-scores the codebook shortlist in exact fp32. */
+typedef enum vqvdb_b200_encode_precision {
+	VQVDB_B200_ENCODE_DEFAULT = 0,
+	VQVDB_B200_ENCODE_FP32 = 1,      /* CUDA-core fp32 FFMA path */
+	VQVDB_B200_ENCODE_FP16X2_TC = 2  /* tcgen05.mma + TMEM accumulators on split-fp16 operands */
+} vqvdb_b200_encode_precision;
+#define VQVDB_B200_ENCODE_DEFAULT_KIND VQVDB_B200_ENCODE_FP16X2_TC
+
 /* Replaces CodecConfig{device, source} (IVQVAECodec.hpp:85-89).  Zero-initialise, set
  * struct_size = sizeof(vqvdb_b200_config), then fill what you need. */
 typedef struct vqvdb_b200_config {
@@ -71,7 +81,8 @@ typedef struct vqvdb_b200_config {
 	                                 (the reference's EmbeddedModel source, IVQVAECodec.hpp:27) */
 	uint32_t chunk_leaves;        /* leaves per internal pipeline chunk for the host-pointer calls; 0 = default */
 	uint32_t decode_precision;    /* vqvdb_b200_decode_precision */
-	uint32_t reserved[8];
+	uint32_t encode_precision;    /* vqvdb_b200_encode_precision */
+	uint32_t reserved[7];
 } vqvdb_b200_config;
 
 /* IVQVAECodec::create (IVQVAECodec.cpp:76-110).  On failure *out is NULL. */
@@ -113,6 +124,15 @@ VQVDB_B200_API const char* vqvdb_b200_decode_path(const vqvdb_b200_codec* codec)
  * {0: stem+GroupNorm+ReLU, 1: residual block, 2: channel attention} as [n][64 ch][64 pos] to dev_tap. */
 VQVDB_B200_API int vqvdb_b200_debug_decode_tap(vqvdb_b200_codec* codec, const uint8_t* dev_indices, int64_t n_leaves,
                                                int stage, float* dev_tap, float* dev_voxels, void* cuda_stream);
+
+/* Name of the encode path in use: "fp32" or "fp16x2_tcgen05". */
+VQVDB_B200_API const char* vqvdb_b200_encode_path(const vqvdb_b200_codec* codec);
+/* Bring-up aid for the tensor-core encoder: runs it and also writes an fp32 activation to dev_tap — stage 0: pre
+ * (GroupNorm+ReLU) [n][16][512], 6: first residual block's conv1 [n][16][512], 1: first residual block [n][16][512],
+ * 2: down [n][32][64], 7: res_stack.0 conv1 [n][32][64], 3: residual stack [n][32][64], 4: channel attention
+ * [n][32][64], 5: z [n][128][64]. */
+VQVDB_B200_API int vqvdb_b200_debug_encode_tap(vqvdb_b200_codec* codec, const float* dev_leaves, int64_t n_leaves, int stage,
+                                               float* dev_tap, uint8_t* dev_indices, void* cuda_stream);
 
 VQVDB_B200_API const char* vqvdb_b200_last_error(const vqvdb_b200_codec* codec);
 VQVDB_B200_API const char* vqvdb_b200_version(void);

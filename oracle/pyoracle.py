@@ -44,6 +44,7 @@ class COracle:
         L.vqo_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.vqo_encode_latents.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.vqo_decode_tap.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+        L.vqo_encode_tap.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
         self.h = L.vqo_load(pack.encode())
         if not self.h:
             raise RuntimeError("vqo_load failed for %s" % pack)
@@ -71,6 +72,14 @@ class COracle:
         z = np.empty((n, 128, 4, 4, 4), dtype=np.float32)
         assert self.lib.vqo_encode_latents(self.h, x.ctypes.data, n, z.ctypes.data) == 0
         return z
+
+    def encode_tap(self, leaves: np.ndarray, stage: int, c0: int = 16, c1: int = 32) -> np.ndarray:
+        x = np.ascontiguousarray(leaves, dtype=np.float32)
+        n = x.shape[0]
+        shape = (n, c0, 8, 8, 8) if stage in (0, 1, 6) else (n, c1, 4, 4, 4)
+        out = np.empty(shape, dtype=np.float32)
+        assert self.lib.vqo_encode_tap(self.h, x.ctypes.data, n, stage, out.ctypes.data) == 0
+        return out
 
     def decode(self, indices: np.ndarray) -> np.ndarray:
         idx = np.ascontiguousarray(indices, dtype=np.uint8)
@@ -164,6 +173,14 @@ class RefCodec:
     def encode(self, leaves: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(leaves, dtype=np.float32)
         return self._call("encode", x, (x.shape[0], 4, 4, 4), np.uint8)
+
+    def encode_tap(self, leaves: np.ndarray, stage: int, c0: int = 16, c1: int = 32) -> np.ndarray:
+        x = np.ascontiguousarray(leaves, dtype=np.float32)
+        n = x.shape[0]
+        shape = (n, c0, 8, 8, 8) if stage in (0, 1, 6) else (n, c1, 4, 4, 4)
+        out = np.empty(shape, dtype=np.float32)
+        assert self.lib.vqo_encode_tap(self.h, x.ctypes.data, n, stage, out.ctypes.data) == 0
+        return out
 
     def decode(self, indices: np.ndarray) -> np.ndarray:
         idx = np.ascontiguousarray(indices, dtype=np.uint8)

@@ -274,15 +274,17 @@ static void groupnorm(float* x, int C, int n_sp, int groups, const float* gamma,
 }
 
 /* ResidualBlock.forward, VQVAE_v2.py:204-210: x + 0.1*conv2(relu(gn2(conv1(relu(gn1(x)))))), groups=8. */
-static void resblock(float* x, int C, int S, const vqo_res* r, float* t0, float* t1) {
+static void resblock_tap(float* x, int C, int S, const vqo_res* r, float* t0, float* t1, float* conv1_tap) {
 	const int n_sp = S * S * S;
 	memcpy(t0, x, sizeof(float) * (size_t)C * n_sp);
 	groupnorm(t0, C, n_sp, 8, r->gn1_w, r->gn1_b, 1);
 	conv3d(t0, C, S, r->c1_w, r->c1_b, C, 3, 1, 1, t1);
+	if (conv1_tap) memcpy(conv1_tap, t1, sizeof(float) * (size_t)C * n_sp);
 	groupnorm(t1, C, n_sp, 8, r->gn2_w, r->gn2_b, 1);
 	conv3d(t1, C, S, r->c2_w, r->c2_b, C, 3, 1, 1, t0);
 	for (int i = 0; i < C * n_sp; ++i) x[i] = x[i] + 0.1f * t0[i];
 }
+static void resblock(float* x, int C, int S, const vqo_res* r, float* t0, float* t1) { resblock_tap(x, C, S, r, t0, t1, NULL); }
 
 static float sigmoidf(float v) { return 1.f / (1.f + expf(-v)); }
 
@@ -308,15 +310,26 @@ static void channel_attention(float* x, int C, int n_sp, const float* fc0, const
 }
 
 /* EncoderFloat.forward VQVAE_v2.py:245-250 / EncoderVec3.forward :293-299.  z is [D][4][4][4]. */
-static void encoder_forward(const vqo_model* m, const float* leaf, float* z, float* s0, float* s1, float* s2) {
+/* tap_stage (kernel bring-up): 0 = pre (GN+ReLU) [c0][8^3], 1 = first res block out [c0][8^3], 2 = down out [c1][4^3],
+ * 3 = res stack out, 4 = after attention, 6 = first res block's conv1 out (+bias) [c0][8^3], 7 = res_stack.0 conv1 out [c1][4^3]. */
+static void encoder_forward_tap(const vqo_model* m, const float* leaf, float* z, float* s0, float* s1, float* s2, int tap_stage,
+                                float* tap) {
 	const int c0 = m->e_c0, c1 = m->e_c1;
 	conv3d(leaf, m->cin, 8, m->e_pre_w, m->e_pre_b, c0, 3, 1, 1, s0);
 	groupnorm(s0, c0, 512, m->e_gn0, m->e_gn_w, m->e_gn_b, 1);
-	resblock(s0, c0, 8, &m->e_res0, s1, s2);
+	if (tap_stage == 0) memcpy(tap, s0, sizeof(float) * (size_t)c0 * 512);
+	resblock_tap(s0, c0, 8, &m->e_res0, s1, s2, tap_stage == 6 ? tap : NULL);
+	if (tap_stage == 1) memcpy(tap, s0, sizeof(float) * (size_t)c0 * 512);
 	conv3d(s0, c0, 8, m->e_down_w, m->e_down_b, c1, m->e_down_k, 2, 1, s1); /* -> [c1][4][4][4] */
-	for (int r = 0; r < m->e_nres; ++r) resblock(s1, c1, 4, &m->e_res[r], s0, s2);
+	if (tap_stage == 2) memcpy(tap, s1, sizeof(float) * (size_t)c1 * 64);
+	for (int r = 0; r < m->e_nres; ++r) resblock_tap(s1, c1, 4, &m->e_res[r], s0, s2, (tap_stage == 7 && r == 0) ? tap : NULL);
+	if (tap_stage == 3) memcpy(tap, s1, sizeof(float) * (size_t)c1 * 64);
 	channel_attention(s1, c1, 64, m->e_fc0, m->e_fc2, m->e_red);
+	if (tap_stage == 4) memcpy(tap, s1, sizeof(float) * (size_t)c1 * 64);
 	conv3d(s1, c1, 4, m->e_proj_w, m->e_proj_b, m->D, 1, 1, 0, z);
+}
+static void encoder_forward(const vqo_model* m, const float* leaf, float* z, float* s0, float* s1, float* s2) {
+	encoder_forward_tap(m, leaf, z, s0, s1, s2, -1, NULL);
 }
 
 /* InferenceVectorQuantizer.get_indices, save_for_inference.py:55-61:
@@ -414,7 +427,7 @@ typedef struct {
 	float* margins;
 	float* fout; /* latents / voxels */
 	float* tap;
-	int mode;    /* 0 encode, 1 latents, 2 decode */
+	int mode;    /* 0 encode, 1 latents, 2 decode, 3 encoder tap */
 	int stage;
 	int64_t n;
 	int64_t next; /* atomic cursor */
@@ -439,6 +452,11 @@ static void* worker(void* arg) {
 			} else if (j->mode == 1) {
 				encoder_forward(m, j->leaves + i * leaf_sz, j->fout + i * (size_t)m->D * 64, s, s + SCRATCH_FLOATS,
 				                s + 2 * SCRATCH_FLOATS);
+			} else if (j->mode == 3) {
+				const int big = (j->stage == 0 || j->stage == 1 || j->stage == 6);
+				const size_t esz = big ? (size_t)m->e_c0 * 512 : (size_t)m->e_c1 * 64;
+				encoder_forward_tap(m, j->leaves + i * leaf_sz, z, s, s + SCRATCH_FLOATS, s + 2 * SCRATCH_FLOATS, j->stage,
+				                    j->tap + i * esz);
 			} else {
 				decoder_forward(m, j->idx_in + i * 64, j->fout ? j->fout + i * leaf_sz : vox, s, s + SCRATCH_FLOATS,
 				                s + 2 * SCRATCH_FLOATS, j->stage, j->tap ? j->tap + i * tap_sz : NULL);
@@ -474,6 +492,12 @@ int vqo_encode(const vqo_model* m, const float* leaves, int64_t n, uint8_t* indi
 
 int vqo_encode_latents(const vqo_model* m, const float* leaves, int64_t n, float* zout) {
 	vqo_job j = {m, leaves, NULL, NULL, NULL, zout, NULL, 1, -1, n, 0};
+	return run_job(&j);
+}
+
+int vqo_encode_tap(const vqo_model* m, const float* leaves, int64_t n, int stage, float* out) {
+	if (!(stage >= 0 && stage <= 4) && stage != 6 && stage != 7) return -1;
+	vqo_job j = {m, leaves, NULL, NULL, NULL, NULL, out, 3, stage, n, 0};
 	return run_job(&j);
 }
 

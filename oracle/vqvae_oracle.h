@@ -39,6 +39,11 @@ int vqo_decode(const vqo_model* m, const uint8_t* indices, int64_t n, float* vox
 /* Encoder output before quantisation, [n, D, 4, 4, 4] fp32 (debug tap). */
 int vqo_encode_latents(const vqo_model* m, const float* leaves, int64_t n, float* z);
 
+/* Encoder activation taps for kernel bring-up: stage 0 = pre (GN+ReLU) [c0,8,8,8], 1 = first residual block out
+ * [c0,8,8,8], 2 = down out [c1,4,4,4], 3 = residual stack out, 4 = after attention, 6 = first residual block's conv1
+ * out [c0,8,8,8], 7 = res_stack.0 conv1 out [c1,4,4,4]. */
+int vqo_encode_tap(const vqo_model* m, const float* leaves, int64_t n, int stage, float* out);
+
 /* Decoder activation taps for kernel bring-up: stage 0 = stem (post GN+ReLU) [64,4,4,4],
  * 1 = after res block, 2 = after attention, 3 = up_conv+pixel-shuffle [32,8,8,8]. */
 int vqo_decode_tap(const vqo_model* m, const uint8_t* indices, int64_t n, int stage, float* out);

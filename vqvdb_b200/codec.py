@@ -23,6 +23,7 @@ EXPORTS = [  # every symbol include/vqvdb_b200.h declares
     "vqvdb_b200_num_embeddings", "vqvdb_b200_encode", "vqvdb_b200_decode", "vqvdb_b200_encode_device",
     "vqvdb_b200_decode_device", "vqvdb_b200_synchronize", "vqvdb_b200_kernel_launches",
     "vqvdb_b200_decode_path", "vqvdb_b200_last_error", "vqvdb_b200_version", "vqvdb_b200_debug_decode_tap",
+    "vqvdb_b200_encode_path", "vqvdb_b200_debug_encode_tap",
 ]
 
 
@@ -35,7 +36,8 @@ class _Config(C.Structure):
         ("weights_path", C.c_char_p),
         ("chunk_leaves", C.c_uint32),
         ("decode_precision", C.c_uint32),
-        ("reserved", C.c_uint32 * 8),
+        ("encode_precision", C.c_uint32),
+        ("reserved", C.c_uint32 * 7),
     ]
 
 
@@ -65,6 +67,10 @@ def load_library() -> C.CDLL:
         getattr(L, fn).restype = C.c_int
     L.vqvdb_b200_debug_decode_tap.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.vqvdb_b200_debug_decode_tap.restype = C.c_int
+    L.vqvdb_b200_debug_encode_tap.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.vqvdb_b200_debug_encode_tap.restype = C.c_int
+    L.vqvdb_b200_encode_path.argtypes = [C.c_void_p]
+    L.vqvdb_b200_encode_path.restype = C.c_char_p
     L.vqvdb_b200_synchronize.argtypes = [C.c_void_p]
     L.vqvdb_b200_kernel_launches.argtypes = [C.c_void_p]
     L.vqvdb_b200_kernel_launches.restype = C.c_uint64
@@ -105,6 +111,7 @@ class CodecConfig:
     device_index: int = 0            # extension: which GPU (the reference hard-codes 0)
     chunk_leaves: int = 0            # extension: pipeline chunk of the host-pointer calls
     decode_precision: str = "default"  # "default" | "fp32" | "bf16_tc" (tcgen05) | "bf16_mma" (mma.sync)
+    encode_precision: str = "default"  # "default" | "fp32" (FFMA) | "fp16x2_tc" (tcgen05, split-fp16 operands)
 
     def __post_init__(self):
         if self.device is None:
@@ -131,6 +138,7 @@ class Tensor:
 
 
 _PRECISION = {"default": 0, "fp32": 1, "bf16_tc": 2, "bf16_mma": 3}
+_ENC_PRECISION = {"default": 0, "fp32": 1, "fp16x2_tc": 2}
 
 
 class B200Codec:
@@ -146,6 +154,7 @@ class B200Codec:
         cfg.device = int(config.device_index)
         cfg.chunk_leaves = int(config.chunk_leaves)
         cfg.decode_precision = _PRECISION[config.decode_precision]
+        cfg.encode_precision = _ENC_PRECISION[config.encode_precision]
         self._keep = None
         if isinstance(config.source, EmbeddedModel):
             pass
@@ -229,6 +238,10 @@ class B200Codec:
         self._check(self._L.vqvdb_b200_debug_decode_tap(self._h, self._addr(dev_indices), n, stage, self._addr(dev_tap),
                                                         self._addr(dev_voxels), C.c_void_p(stream)), "debug_decode_tap")
 
+    def debug_encode_tap(self, dev_leaves, n: int, stage: int, dev_tap, dev_indices, stream: int = 0):
+        self._check(self._L.vqvdb_b200_debug_encode_tap(self._h, self._addr(dev_leaves), n, stage, self._addr(dev_tap),
+                                                        self._addr(dev_indices), C.c_void_p(stream)), "debug_encode_tap")
+
     def synchronize(self):
         self._check(self._L.vqvdb_b200_synchronize(self._h), "synchronize")
 
@@ -239,6 +252,10 @@ class B200Codec:
     @property
     def decode_path(self) -> str:
         return self._L.vqvdb_b200_decode_path(self._h).decode()
+
+    @property
+    def encode_path(self) -> str:
+        return self._L.vqvdb_b200_encode_path(self._h).decode()
 
 
 class IVQVAECodec:

@@ -15,6 +15,7 @@
 
 #include "../../include/vqvdb_b200.h"
 #include "decode_mma.cuh"
+#include "encode_tc.cuh"
 #include "generic_model.cuh"
 #include "model.cuh"
 #include "weights.hpp"
@@ -62,6 +63,10 @@ struct vqvdb_b200_codec {
 	float* arena = nullptr;  // every fp32 device weight table lives in this one allocation
 	uint8_t* mma_arena = nullptr;  // bf16 weight-unit stream + bf16 codebook of the tensor-core decoder
 	int decode_kind = 2;  // 1 = fp32 FFMA, 2 = bf16 tcgen05/TMEM, 3 = bf16 mma.sync
+	int encode_kind = 2;  // 1 = fp32 FFMA, 2 = fp16x2 split on tcgen05/TMEM (fp32-level accuracy)
+	std::string encode_path = "fp32";
+	uint8_t* enc_tc_arena = nullptr;  // fp16 hi/lo weight-unit stream of the tensor-core encoder
+	vqvdb::EncoderTcStream enc_tc{};
 	vqvdb::DecoderMmaWeights dec_mma{};
 	bool generic = false;            // architecture-generic kernels (vec3 model) instead of the specialised ones
 	vqvdb::GenericModel gen{};
@@ -90,6 +95,7 @@ struct vqvdb_b200_codec {
 		}
 		if (arena) cudaFree(arena);
 		if (mma_arena) cudaFree(mma_arena);
+		if (enc_tc_arena) cudaFree(enc_tc_arena);
 		if (gen_scratch) cudaFree(gen_scratch);
 	}
 };
@@ -243,6 +249,13 @@ void upload_float_model(vqvdb_b200_codec& c, const WeightPack& p) {
 			for (int q = 0; q < 8; ++q) add(cbu + (size_t)q * 8192, 8192);
 		if (n != vqvdb::kEncUnits) throw std::logic_error("encoder unit table size mismatch");
 	}
+	// tensor-core encoder: fp16 hi/lo unit stream (encode_tc.cuh)
+	{
+		const std::vector<uint8_t> eu = vqvdb::build_encoder_tc_units(p, c.enc_tc);
+		CUDA_TRY(cudaMalloc(&c.enc_tc_arena, eu.size()));
+		CUDA_TRY(cudaMemcpy(c.enc_tc_arena, eu.data(), eu.size(), cudaMemcpyHostToDevice));
+		c.enc_tc.units = c.enc_tc_arena;
+	}
 	auto& m = c.dec_mma;
 	m.units = c.mma_arena;
 	m.emb_bf16 = reinterpret_cast<const __nv_bfloat16*>(c.mma_arena + units.size());
@@ -372,7 +385,8 @@ void launch_encode(vqvdb_b200_codec& c, const float* d_leaves, int64_t n, uint8_
 		if (n > 0) c.launches.fetch_add(1, std::memory_order_relaxed);
 		return;
 	}
-	CUDA_TRY(vqvdb::launch_encode_fp32(c.enc, c.enc_units, d_leaves, n, d_idx, c.num_sms, st));
+	if (c.encode_kind == 2) CUDA_TRY(vqvdb::launch_encode_tc(c.enc, c.enc_tc, d_leaves, n, d_idx, c.num_sms, st));
+	else CUDA_TRY(vqvdb::launch_encode_fp32(c.enc, c.enc_units, d_leaves, n, d_idx, c.num_sms, st));
 	if (n > 0) c.launches.fetch_add(1, std::memory_order_relaxed);
 }
 
@@ -455,9 +469,14 @@ int vqvdb_b200_create(const vqvdb_b200_config* cfg, vqvdb_b200_codec** out) {
 		if (conf.decode_precision > VQVDB_B200_DECODE_BF16_MMA)
 			return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "unknown decode_precision");
 		c->decode_kind = conf.decode_precision == VQVDB_B200_DECODE_DEFAULT ? (int)VQVDB_B200_DECODE_DEFAULT_KIND : (int)conf.decode_precision;
+		if (conf.encode_precision > VQVDB_B200_ENCODE_FP16X2_TC)
+			return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "unknown encode_precision");
+		c->encode_kind = conf.encode_precision == VQVDB_B200_ENCODE_DEFAULT ? (int)VQVDB_B200_ENCODE_DEFAULT_KIND : (int)conf.encode_precision;
+		c->encode_path = c->generic ? "fp32_generic" : c->encode_kind == 2 ? "fp16x2_tcgen05" : "fp32";
 		c->decode_path = c->generic ? "fp32_generic" : c->decode_kind == 2 ? "bf16_tcgen05" : c->decode_kind == 3 ? "bf16_mma" : "fp32";
 		CUDA_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
 		CUDA_TRY(vqvdb::configure_encode_fp32());
+		CUDA_TRY(vqvdb::configure_encode_tc());
 		CUDA_TRY(vqvdb::configure_decode_fp32());
 		CUDA_TRY(vqvdb::configure_decode_mma());
 		CUDA_TRY(vqvdb::configure_decode_tc());
@@ -605,8 +624,24 @@ int vqvdb_b200_debug_decode_tap(vqvdb_b200_codec* c, const uint8_t* dev_indices,
 	return VQVDB_B200_OK;
 }
 
+int vqvdb_b200_debug_encode_tap(vqvdb_b200_codec* c, const float* dev_leaves, int64_t n, int stage, float* dev_tap,
+                                uint8_t* dev_indices, void* stream) {
+	if (!c) return VQVDB_B200_ERR_INVALID_ARGUMENT;
+	if (n < 0 || stage < 0 || (stage > 7 && stage != 100) || (n > 0 && (!dev_leaves || !dev_tap || !dev_indices)))
+		return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "debug_encode_tap: bad arguments");
+	if (c->generic) return fail(c, VQVDB_B200_ERR_UNSUPPORTED, "debug_encode_tap: float model only");
+	try {
+		CUDA_TRY(cudaSetDevice(c->device));
+		CUDA_TRY(vqvdb::launch_encode_tc(c->enc, c->enc_tc, dev_leaves, n, dev_indices, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
+	} catch (const std::exception& e) {
+		return translate(c, e);
+	}
+	return VQVDB_B200_OK;
+}
+
 uint64_t vqvdb_b200_kernel_launches(const vqvdb_b200_codec* c) { return c ? c->launches.load() : 0; }
 const char* vqvdb_b200_decode_path(const vqvdb_b200_codec* c) { return c ? c->decode_path.c_str() : ""; }
+const char* vqvdb_b200_encode_path(const vqvdb_b200_codec* c) { return c ? c->encode_path.c_str() : ""; }
 
 const char* vqvdb_b200_last_error(const vqvdb_b200_codec* c) { return c ? c->last_error.c_str() : g_create_error.c_str(); }
 

@@ -1,0 +1,157 @@
+// Host-side preparation of the tensor-core encoder's weight stream (see encode_tc.cuh).
+#include <cstring>
+#include <stdexcept>
+
+#include "encode_tc_stream.hpp"
+
+namespace vqvdb {
+
+namespace {
+
+// IEEE binary32 -> binary16, round to nearest even, subnormals kept.
+uint16_t f32_to_f16_rn(float f) {
+	uint32_t x;
+	std::memcpy(&x, &f, 4);
+	const uint32_t sign = (x >> 16) & 0x8000u;
+	const uint32_t abs = x & 0x7fffffffu;
+	if (abs >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (abs > 0x7f800000u ? 0x200u : 0u));
+	if (abs >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);  // >= 65520 rounds to infinity
+	if (abs <= 0x33000000u) return (uint16_t)sign;              // <= 2^-25 rounds to zero (tie goes to even)
+	const int exp = (int)(abs >> 23) - 127;
+	const uint32_t mant = (abs & 0x7fffffu) | 0x800000u;
+	if (exp < -14) {  // subnormal result: units of 2^-24
+		const int shift = (-14 - exp) + 13;
+		uint32_t q = mant >> shift;
+		const uint32_t rem = mant & ((1u << shift) - 1u), half = 1u << (shift - 1);
+		if (rem > half || (rem == half && (q & 1u))) ++q;
+		return (uint16_t)(sign | q);
+	}
+	uint32_t q = ((uint32_t)(exp + 15) << 10) | ((mant & 0x7fffffu) >> 13);
+	const uint32_t rem = mant & 0x1fffu;
+	if (rem > 0x1000u || (rem == 0x1000u && (q & 1u))) ++q;  // a carry moves into the exponent field correctly
+	return (uint16_t)(sign | q);
+}
+
+float f16_to_f32(uint16_t h) {
+	const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+	uint32_t exp = (h >> 10) & 0x1fu, mant = h & 0x3ffu, out;
+	if (exp == 0) {
+		if (mant == 0) out = sign;
+		else {
+			int e = -1;
+			do {
+				mant <<= 1;
+				++e;
+			} while (!(mant & 0x400u));
+			out = sign | ((uint32_t)(127 - 15 - e) << 23) | ((mant & 0x3ffu) << 13);
+		}
+	} else if (exp == 31) out = sign | 0x7f800000u | (mant << 13);
+	else out = sign | ((exp - 15 + 127) << 23) | (mant << 13);
+	float f;
+	std::memcpy(&f, &out, 4);
+	return f;
+}
+
+uint16_t f32_to_bf16_rn(float f) {
+	uint32_t u;
+	std::memcpy(&u, &f, 4);
+	if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
+	u += 0x7fffu + ((u >> 16) & 1u);
+	return (uint16_t)(u >> 16);
+}
+
+// part 0: fp16(w); part 1: fp16((w - fp16(w)) * 2048)
+uint16_t split_part(float w, int part) {
+	const uint16_t hi = f32_to_f16_rn(w);
+	if (part == 0) return hi;
+	return f32_to_f16_rn((w - f16_to_f32(hi)) * 2048.f);
+}
+
+// element (n, k) of one [2][N][16 B] operand block
+inline void put(uint8_t* block, int N, int n, int k, uint16_t v) {
+	std::memcpy(block + ((size_t)(k >> 3) * N + n) * 16 + (size_t)(k & 7) * 2, &v, 2);
+}
+
+}  // namespace
+
+std::vector<uint8_t> build_encoder_tc_units(const WeightPack& p, EncoderTcStream& tab) {
+	std::vector<uint8_t> out;
+	int nu = 0;
+	auto begin_unit = [&](size_t bytes) -> uint8_t* {
+		if (nu >= kEncTcUnits || bytes > kEncTcStageBytes || (bytes & 15)) throw std::logic_error("encoder tc unit table overflow");
+		const size_t off = out.size();
+		out.resize(off + bytes, 0);
+		tab.off[nu] = (uint32_t)off;
+		tab.bytes[nu] = (uint32_t)bytes;
+		++nu;
+		return out.data() + off;
+	};
+	out.reserve(512 * 1024);
+	// res16 conv1 / conv2: weight [16][16][3][3][3]
+	for (const char* name : {"encoder.pre.3.conv1.weight", "encoder.pre.3.conv2.weight"}) {
+		const float* w = p.get(name).data;
+		for (int kd = 0; kd < 3; ++kd) {
+			uint8_t* u = begin_unit(3 * 3072);
+			for (int kh = 0; kh < 3; ++kh)
+				for (int part = 0; part < 2; ++part)
+					for (int kw = 0; kw < 3; ++kw)
+						for (int co = 0; co < 16; ++co)
+							for (int ci = 0; ci < 16; ++ci)
+								put(u + kh * 3072, 96, part * 48 + kw * 16 + co, ci,
+								    split_part(w[((co * 16 + ci) * 27) + (kd * 3 + kh) * 3 + kw], part));
+		}
+	}
+	// down: weight [32][16][4][4][4]; k = 2t + r per axis (t = tap of the 2x2x2 form, r = parity class of the input)
+	{
+		const float* w = p.get("encoder.down.weight").data;
+		for (int tap = 0; tap < 8; ++tap) {
+			uint8_t* u = begin_unit(8 * 2048);
+			const int td = tap >> 2, th = (tap >> 1) & 1, tw = tap & 1;
+			for (int pc = 0; pc < 8; ++pc) {
+				const int rd = pc >> 2, rh = (pc >> 1) & 1, rw = pc & 1;
+				const int kd = 2 * td + rd, kh = 2 * th + rh, kw = 2 * tw + rw;
+				for (int part = 0; part < 2; ++part)
+					for (int co = 0; co < 32; ++co)
+						for (int ci = 0; ci < 16; ++ci)
+							put(u + pc * 2048, 64, part * 32 + co, ci, split_part(w[((co * 16 + ci) * 64) + (kd * 4 + kh) * 4 + kw], part));
+			}
+		}
+	}
+	// res32 conv1 / conv2: weight [32][32][3][3][3]
+	for (const char* name : {"encoder.res_stack.0.conv1.weight", "encoder.res_stack.0.conv2.weight"}) {
+		const float* w = p.get(name).data;
+		for (int kk = 0; kk < 9; ++kk) {
+			uint8_t* u = begin_unit(2 * 6144);
+			for (int ks = 0; ks < 2; ++ks)
+				for (int part = 0; part < 2; ++part)
+					for (int kw = 0; kw < 3; ++kw)
+						for (int co = 0; co < 32; ++co)
+							for (int k = 0; k < 16; ++k)
+								put(u + ks * 6144, 192, part * 96 + kw * 32 + co, k,
+								    split_part(w[((co * 32 + ks * 16 + k) * 27) + kk * 3 + kw], part));
+		}
+	}
+	// proj: weight [128][32][1][1][1]
+	{
+		const float* w = p.get("encoder.proj.weight").data;
+		uint8_t* u = begin_unit(2 * 8192);
+		for (int ks = 0; ks < 2; ++ks)
+			for (int part = 0; part < 2; ++part)
+				for (int co = 0; co < 128; ++co)
+					for (int k = 0; k < 16; ++k) put(u + ks * 8192, 256, part * 128 + co, k, split_part(w[co * 32 + ks * 16 + k], part));
+	}
+	// codebook [256][128] as bf16, 8 k-steps of 16 dims
+	{
+		const float* e = p.get("quantizer.embedding").data;
+		for (int q = 0; q < 4; ++q) {
+			uint8_t* u = begin_unit(2 * 8192);
+			for (int kl = 0; kl < 2; ++kl)
+				for (int code = 0; code < 256; ++code)
+					for (int k = 0; k < 16; ++k) put(u + kl * 8192, 256, code, k, f32_to_bf16_rn(e[code * 128 + (q * 2 + kl) * 16 + k]));
+		}
+	}
+	if (nu != kEncTcUnits) throw std::logic_error("encoder tc unit count mismatch");
+	return out;
+}
+
+}  // namespace vqvdb

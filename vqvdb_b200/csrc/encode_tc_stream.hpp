@@ -1,0 +1,34 @@
+// Weight stream of the tensor-core (tcgen05 / TMEM) encoder: plain C++ part shared by the host-side builder
+// (encode_tc_host.cpp) and the kernel launcher (encode_tc.cuh / encode_tc.cu).
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+#include "weights.hpp"
+
+namespace vqvdb {
+
+// The encoder's GEMM-shaped layers consume their weights as a fixed stream of "units" (<= 16 KB) through a
+// shared-memory ring.  Every unit is a sequence of B operands in the canonical no-swizzle K-major UMMA layout
+// [k-chunk (2)][n][8 elements = 16 B]; conv weights are split into two fp16 planes, w ~= w_hi + w_lo / 2048:
+//   res16 conv1 / conv2 : 3 units each (one per kd) = 3 (kh) x [2][96][16 B], n = part*48 + kw*16 + cout
+//   down                : 8 units (one per 2x2x2 tap of the space-to-depth form) = 8 parity classes x [2][64][16 B],
+//                         n = part*32 + cout
+//   res32 conv1 / conv2 : 9 units each (one per (kd, kh)) = 2 k-steps x [2][192][16 B], n = part*96 + kw*32 + cout
+//   proj                : 1 unit = 2 k-steps x [2][256][16 B], n = part*128 + cout
+//   codebook (bf16)     : 4 units = 2 k-steps each x [2][256][16 B], n = code
+// (part 0 = w_hi, part 1 = w_lo).
+constexpr int kEncTcUnits = 37;
+constexpr uint32_t kEncTcStageBytes = 16384;
+
+struct EncoderTcStream {
+	const uint8_t* units;            // device pointer, 16-byte aligned
+	uint32_t off[kEncTcUnits];       // byte offset of each unit
+	uint32_t bytes[kEncTcUnits];     // multiple of 16, <= kEncTcStageBytes
+};
+
+// Builds the unit stream on the host and fills table.off / table.bytes (table.units is set by the caller after upload).
+std::vector<uint8_t> build_encoder_tc_units(const WeightPack& pack, EncoderTcStream& table);
+
+}  // namespace vqvdb
