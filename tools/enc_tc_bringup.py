@@ -40,6 +40,27 @@ for stage in (0, 6, 1, 2, 7, 3, 4, 5):
         rc = 1
         w = np.argwhere((err > 2e-4) | bad)
         print("   first bad entries (leaf, ch, pos):", w[:6].tolist(), " got", got[tuple(w[0])], "ref", ref[tuple(w[0])])
+# who is right at `down`?  fp64 convolution of the oracle's stage-1 activation, weights from the pack
+try:
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    import weights_pack as wp
+    _meta, tens = wp.read_pack(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vqvdb_b200", "weights", "vqvae_float.vqw"))
+    wd = torch.from_numpy(np.asarray(tens["encoder.down.weight"])).double()
+    bd = torch.from_numpy(np.asarray(tens["encoder.down.bias"])).double()
+    x1 = torch.from_numpy(oracle.encode_tap(x, 1)).double()
+    ref64 = torch.nn.functional.conv3d(x1, wd, bd, stride=2, padding=1).numpy().reshape(n, 32, 64)
+    tap = torch.zeros((n, 32, 64), dtype=torch.float32, device="cuda")
+    tc.debug_encode_tap(xd, n, 2, tap, idx)
+    torch.cuda.synchronize()
+    got = tap.cpu().numpy()
+    orc = oracle.encode_tap(x, 2).reshape(n, 32, 64)
+    for nm, a in (("tcgen05", got), ("C oracle", orc)):
+        e = a - ref64
+        print("down vs fp64: %-8s max err %.3e rms %.3e mean (bias) %.3e" % (nm, np.abs(e).max(), np.sqrt((e ** 2).mean()), e.mean()))
+    sgn = np.sign(ref64)
+    print("   tcgen05 error projected on sign(ref) (negative = truncation toward zero): %.3e" % float(((got - ref64) * sgn).mean()))
+except Exception as ex:  # diagnostic only
+    print("fp64 down check skipped:", ex)
 idx_o, margins = oracle.encode(x, with_margins=True)
 idx_tc = tc.encode(TensorView(x, list(x.shape), DataType.FLOAT32)).buffer
 idx_ff = ff.encode(TensorView(x, list(x.shape), DataType.FLOAT32)).buffer

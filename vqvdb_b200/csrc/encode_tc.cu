@@ -11,8 +11,9 @@
 // fp32 FMA chain's (tools/microbench/umma_conv16_f16x2.cu: max 1.2e-6 vs 2.7e-6 on the 16->16 conv).
 //
 // Machine mapping
-//   * one leaf per CTA pass.  128 "row" threads (4 warps = the 4 TMEM lane quadrants) own one GEMM row each per
-//     128-row tile; one elected thread issues every tcgen05.mma; one more thread streams weights by TMA.
+//   * one leaf per CTA pass.  16 "row" warps: warp = g * 4 + quadrant owns TMEM lanes quadrant * 32 .. + 31 (one GEMM
+//     row per lane and 128-row tile) and channel group g of 4 (4 of 16 channels at 8^3, 8 of 32 at 4^3, 32 of the
+//     128 latent dims, 64 of the 256 codes).  One elected thread issues every tcgen05.mma; one more streams weights by TMA.
 //   * im2col is never materialised and nothing is gathered: activations live in shared memory FLATTENED with zero
 //     halos — 8^3: q = d*72 + h*8 + w (a ninth all-zero row block per d slab, zero slabs around the leaf);
 //     4^3: q = d*20 + h*4 + w; the stride-2 conv in its space-to-depth form (2x2x2 taps over a 5^3 grid of 8 parity
@@ -21,7 +22,9 @@
 //   * the three kw taps of a 3x3x3 conv are concatenated along N (one A read serves three taps, N = 96/48 or
 //     192/96); the kw shift is applied in the epilogue as a lane shuffle that never crosses a warp (w = lane & 7 or
 //     lane & 3), which also supplies the zero padding along w.
-//   * per-leaf reductions (GroupNorm statistics, channel attention) are warp shuffles + one 128-thread named barrier.
+//   * per-leaf reductions (GroupNorm statistics, channel attention) are warp shuffles + one 512-thread named barrier.
+//   * the tensor core truncates its fp32 accumulator after every MMA (measured: a bias toward zero that grows with
+//     the chain length); the 64-step chain of the stride-2 conv is split over four accumulators added in the epilogue.
 //   * pre.0 (Cin = 1, K = 27) stays on FFMA in fp32 (raw voxel values are unbounded; it is 1.4 % of the MACs).
 //   * VQ: bf16 tensor-core scores for all 256 codes with a rigorous error bound, then exact fp32 re-scoring of the
 //     shortlist with the reference's formula and tie-break — the same two-stage scheme as encode_fp32.cu, so the
@@ -39,11 +42,15 @@ namespace vqvdb {
 
 namespace {
 
-constexpr int kRowThreads = 128;
-constexpr int kThreads = 192;            // 4 row warps + MMA issuer warp + TMA producer warp
+constexpr int kGroups = 4;                        // row warps per TMEM lane quadrant: they split the channels of a row
+constexpr int kRowWarps = 4 * kGroups;            // 16
+constexpr int kRowThreads = 32 * kRowWarps;       // 512
+constexpr int kIssuerWarp = kRowWarps, kProducerWarp = kRowWarps + 1;
+constexpr int kThreads = kRowThreads + 64;        // + MMA issuer warp + TMA producer warp
 constexpr int kStages = 3;
 constexpr uint32_t kStageBytes = kEncTcStageBytes;
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+constexpr int kDownChains = 4;                    // independent accumulators of `down` (see the issuer)
 
 // ---- shared-memory activation buffers (all UMMA A operands: [precision][8-channel plane][row][16 B]) ----
 constexpr int kA8Margin = 80, kA8Rows = 800;                    // 8^3, 16 channels: rows -80 .. 719 around q = d*72 + h*8 + w
@@ -65,15 +72,16 @@ constexpr uint32_t kOffZb = kOffY + 34816;                      // 1 KB-aligned,
 constexpr uint32_t kOffH = kOffY + kYBytes;                     // 182 272
 constexpr uint32_t kOffIn = kOffH + kHBytes;                    // in_halo [10][10][10] fp32 (4096 reserved)
 constexpr uint32_t kOffPreW = kOffIn + 4096;                    // pre.0 weights [27][16] fp32
-constexpr uint32_t kOffX32 = kOffPreW + 1728;                   // residual of the 4^3 block [64][36] fp32
-constexpr uint32_t kOffRed = kOffX32 + 64 * kX32Pitch * 4;      // GroupNorm partials [2][4][8]
-constexpr uint32_t kOffAtt = kOffRed + 256;                     // attention: part [4][32], hid [8], scale [32]
+constexpr uint32_t kOffX32 = kOffPreW + 1728;                   // residual of the 4^3 block [64][36] fp32; later the VQ exchange
+constexpr uint32_t kOffRed = kOffX32 + 64 * kX32Pitch * 4;      // GroupNorm partials [2 slots][16 warps][2]
+constexpr uint32_t kOffAtt = kOffRed + 256;                     // attention: part [16 warps][8], hid [8], scale [32]
 constexpr uint32_t kOffCb = kOffAtt + (128 + 8 + 32) * 4;       // emb_sq [256], emb_norm [256]
 constexpr uint32_t kOffBar = kOffCb + 2048;                     // mbarriers
 constexpr uint32_t kNumBars = 2 * kStages + 2;
 constexpr uint32_t kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemSlot + 16;
 static_assert(kZsBytes <= 34816 && 34816 + kZbBytes <= kYBytes, "z overlays fit inside the Y region");
+static_assert(4 * 4 * 128 * 4 <= 64 * kX32Pitch * 4, "VQ exchange arrays fit in the dead x32 staging area");
 static_assert(kSmemBytes <= 227 * 1024, "encode_tc smem budget");
 static_assert(kOffBar % 8 == 0 && kOffA8 % 1024 == 0 && kOffY % 1024 == 0 && kOffH % 1024 == 0 && kOffZb % 1024 == 0, "alignment");
 
@@ -88,7 +96,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
 	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// instruction descriptor: D = f32, A/B = f16 (bf16 with kBf16), both K-major, M = 128, N = n
+// instruction descriptor: D = f32, A/B = f16 (or bf16), both K-major, M = 128, N = n
 __host__ __device__ constexpr uint32_t idesc_f16(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
 __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t n) { return idesc_f16(n) | (1u << 7) | (1u << 10); }
 // shared-memory descriptor, K-major, no swizzle: 8-row core matrices of 128 contiguous bytes; SBO = stride between
@@ -104,7 +112,13 @@ __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint3
 	    "l"(a), "l"(b), "r"(id), "r"(acc)
 	    : "memory");
 }
-// TMEM -> registers, 32 lanes x 8 / 16 / 32 consecutive columns; issue only (tmem_wait_ld() before use)
+// TMEM -> registers, 32 lanes x 4 / 8 / 32 consecutive columns; issue only (tmem_wait_ld() before use)
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, float (&v)[4]) {
+	uint32_t o[4];
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(taddr));
+#pragma unroll
+	for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(o[j]);
+}
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&v)[8]) {
 	uint32_t o[8];
 	asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -137,34 +151,21 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32])
 	for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(o[j]);
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
-	asm volatile(
-	    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-	    "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-	    "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-	    "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-	    "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-	    : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void row_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void row_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
 	asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint2 v) {
+	asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
 
-// 8 fp32 values -> one 16-byte chunk of the hi plane and one of the lo plane
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-	uint32_t h[4], l[4];
-#pragma unroll
-	for (int i = 0; i < 4; ++i) {
-		const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-		const float2 hf = __half22float2(hh);
-		const __half2 ll = __floats2half2_rn((v[2 * i] - hf.x) * kLoScale, (v[2 * i + 1] - hf.y) * kLoScale);
-		h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-		l[i] = *reinterpret_cast<const uint32_t*>(&ll);
-	}
-	hi = make_uint4(h[0], h[1], h[2], h[3]);
-	lo = make_uint4(l[0], l[1], l[2], l[3]);
+// two fp32 values -> packed fp16 hi pair and fp16 lo pair (v ~= hi + lo / 2048)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+	const __half2 hh = __floats2half2_rn(a, b);
+	const float2 hf = __half22float2(hh);
+	const __half2 ll = __floats2half2_rn((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);
+	hi = *reinterpret_cast<const uint32_t*>(&hh);
+	lo = *reinterpret_cast<const uint32_t*>(&ll);
 }
 
 // The row threads hand the freshly written A operand (and the drained accumulators) to the MMA issuer.
@@ -176,8 +177,8 @@ __device__ __forceinline__ void signal_a_ready(uint32_t bars, int lane) {
 }
 
 struct RowCtx {
-	int tid, warp, lane;
-	uint32_t bars, tlane;   // mbarrier base; TMEM base + (warp * 32 << 16)
+	int warp, lane, g;      // g = channel group of this warp (warp >> 2); TMEM lane quadrant = warp & 3
+	uint32_t bars, tlane;   // mbarrier base; TMEM base + (quadrant * 32 << 16)
 	uint32_t d_count = 0;   // accumulator hand-overs so far (parity of d_full)
 	float* red;
 };
@@ -187,40 +188,43 @@ __device__ __forceinline__ void wait_accumulator(RowCtx& rc) {
 	++rc.d_count;
 }
 
-// Sum NG per-thread values over the 128 row threads (warp shuffle, then 4 partials through shared memory).
+// Sum NG (<= 2) per-thread values over the 128 row threads of this thread's channel group: warp shuffle, then the
+// group's four warp partials through shared memory.
 template <int NG>
-__device__ __forceinline__ void row_allreduce(float (&s)[NG], const RowCtx& rc, int slot) {
+__device__ __forceinline__ void group_allreduce(float (&s)[NG], const RowCtx& rc, int slot) {
 #pragma unroll
-	for (int g = 0; g < NG; ++g) s[g] = warp_sum(s[g]);
+	for (int i = 0; i < NG; ++i) s[i] = warp_sum(s[i]);
 	float* red = rc.red + slot * 32;
 	if (rc.lane == 0) {
 #pragma unroll
-		for (int g = 0; g < NG; ++g) red[rc.warp * 8 + g] = s[g];
+		for (int i = 0; i < NG; ++i) red[rc.warp * 2 + i] = s[i];
 	}
 	row_bar();
+	const float* r = red + rc.g * 8;  // warps 4g .. 4g+3
 #pragma unroll
-	for (int g = 0; g < NG; ++g) s[g] = (red[g] + red[8 + g]) + (red[16 + g] + red[24 + g]);
+	for (int i = 0; i < NG; ++i) s[i] = (r[i] + r[2 + i]) + (r[4 + i] + r[6 + i]);
 }
 
-// GroupNorm statistics of register-resident values v[R][C] (rows with a clear bit in `valid` do not count).
+// GroupNorm statistics of register-resident values v[R][C] (rows with a clear bit in `valid` do not count); the
+// thread's C channels are C / CPG whole groups.
 template <int R, int C, int CPG>
 __device__ __forceinline__ void gn_stats_regs(const float (&v)[R][C], uint32_t valid, float inv_cnt, const RowCtx& rc,
                                               float (&mean)[C / CPG], float (&rstd)[C / CPG]) {
 	constexpr int NG = C / CPG;
 	float s[NG];
 #pragma unroll
-	for (int g = 0; g < NG; ++g) s[g] = 0.f;
+	for (int i = 0; i < NG; ++i) s[i] = 0.f;
 #pragma unroll
 	for (int t = 0; t < R; ++t)
 		if (valid & (1u << t)) {
 #pragma unroll
 			for (int c = 0; c < C; ++c) s[c / CPG] += v[t][c];
 		}
-	row_allreduce<NG>(s, rc, 0);
+	group_allreduce<NG>(s, rc, 0);
 #pragma unroll
-	for (int g = 0; g < NG; ++g) {
-		mean[g] = s[g] * inv_cnt;
-		s[g] = 0.f;
+	for (int i = 0; i < NG; ++i) {
+		mean[i] = s[i] * inv_cnt;
+		s[i] = 0.f;
 	}
 #pragma unroll
 	for (int t = 0; t < R; ++t)
@@ -231,9 +235,9 @@ __device__ __forceinline__ void gn_stats_regs(const float (&v)[R][C], uint32_t v
 				s[c / CPG] = fmaf(dv, dv, s[c / CPG]);
 			}
 		}
-	row_allreduce<NG>(s, rc, 1);
+	group_allreduce<NG>(s, rc, 1);
 #pragma unroll
-	for (int g = 0; g < NG; ++g) rstd[g] = 1.f / sqrtf(s[g] * inv_cnt + kGnEps);
+	for (int i = 0; i < NG; ++i) rstd[i] = 1.f / sqrtf(s[i] * inv_cnt + kGnEps);
 }
 
 // Flattened 8^3 row q -> voxel; false for halo / padding rows.
@@ -245,73 +249,63 @@ __device__ __forceinline__ bool row8(int q, int& d, int& h, int& w) {
 	return q < 576 && h < 8;
 }
 
-// Combined output of one 128-row tile of a kw-concatenated 16-channel conv: loads the tile's 96 accumulator
-// columns [hh kw0 | hh kw1 | hh kw2 | hl kw0 | hl kw1 | hl kw2] (16 each), folds hi/lo, applies the kw shift.
-__device__ __forceinline__ void conv16_tile_out(uint32_t tcol, int w, float (&o)[16]) {
+// Output of one 128-row tile of a kw-concatenated 16-channel conv for channels 4g .. 4g+3: the tile's 96 accumulator
+// columns are [hh kw0 | hh kw1 | hh kw2 | hl kw0 | hl kw1 | hl kw2] (16 each); folds hi/lo, applies the kw shift.
+__device__ __forceinline__ void conv16_tile_out(uint32_t tcol, int g, int w, float (&o)[4]) {
+	float hh0[4], hh1[4], hh2[4], hl0[4], hl1[4], hl2[4];
+	tmem_ld4_nowait(tcol + g * 4, hh0);
+	tmem_ld4_nowait(tcol + 16 + g * 4, hh1);
+	tmem_ld4_nowait(tcol + 32 + g * 4, hh2);
+	tmem_ld4_nowait(tcol + 48 + g * 4, hl0);
+	tmem_ld4_nowait(tcol + 64 + g * 4, hl1);
+	tmem_ld4_nowait(tcol + 80 + g * 4, hl2);
+	tmem_wait_ld();
 #pragma unroll
-	for (int half = 0; half < 2; ++half) {
-		float hh0[8], hh1[8], hh2[8], hl0[8], hl1[8], hl2[8];
-		tmem_ld8_nowait(tcol + half * 8, hh0);
-		tmem_ld8_nowait(tcol + 16 + half * 8, hh1);
-		tmem_ld8_nowait(tcol + 32 + half * 8, hh2);
-		tmem_ld8_nowait(tcol + 48 + half * 8, hl0);
-		tmem_ld8_nowait(tcol + 64 + half * 8, hl1);
-		tmem_ld8_nowait(tcol + 80 + half * 8, hl2);
-		tmem_wait_ld();
-#pragma unroll
-		for (int c = 0; c < 8; ++c) {
-			const float p0 = fmaf(hl0[c], kLoInv, hh0[c]);
-			const float p1 = fmaf(hl1[c], kLoInv, hh1[c]);
-			const float p2 = fmaf(hl2[c], kLoInv, hh2[c]);
-			const float up = __shfl_up_sync(0xffffffffu, p0, 1), dn = __shfl_down_sync(0xffffffffu, p2, 1);
-			o[half * 8 + c] = ((w > 0 ? up : 0.f) + p1) + (w < 7 ? dn : 0.f);
-		}
+	for (int c = 0; c < 4; ++c) {
+		const float p0 = fmaf(hl0[c], kLoInv, hh0[c]);
+		const float p1 = fmaf(hl1[c], kLoInv, hh1[c]);
+		const float p2 = fmaf(hl2[c], kLoInv, hh2[c]);
+		const float up = __shfl_up_sync(0xffffffffu, p0, 1), dn = __shfl_down_sync(0xffffffffu, p2, 1);
+		o[c] = ((w > 0 ? up : 0.f) + p1) + (w < 7 ? dn : 0.f);
 	}
 }
-// Same for a 32-channel conv at 4^3: 192 columns [hh kw0..2 (32 each) | hl kw0..2 (32 each)], w = lane & 3.
-__device__ __forceinline__ void conv32_tile_out(uint32_t tcol, int w, float (&o)[32]) {
+// Same for a 32-channel conv at 4^3, channels 8g .. 8g+7: 192 columns [hh kw0..2 (32 each) | hl kw0..2 (32 each)].
+__device__ __forceinline__ void conv32_tile_out(uint32_t tcol, int g, int w, float (&o)[8]) {
+	float hh0[8], hh1[8], hh2[8], hl0[8], hl1[8], hl2[8];
+	tmem_ld8_nowait(tcol + g * 8, hh0);
+	tmem_ld8_nowait(tcol + 32 + g * 8, hh1);
+	tmem_ld8_nowait(tcol + 64 + g * 8, hh2);
+	tmem_ld8_nowait(tcol + 96 + g * 8, hl0);
+	tmem_ld8_nowait(tcol + 128 + g * 8, hl1);
+	tmem_ld8_nowait(tcol + 160 + g * 8, hl2);
+	tmem_wait_ld();
 #pragma unroll
-	for (int cg = 0; cg < 4; ++cg) {
-		float hh0[8], hh1[8], hh2[8], hl0[8], hl1[8], hl2[8];
-		tmem_ld8_nowait(tcol + cg * 8, hh0);
-		tmem_ld8_nowait(tcol + 32 + cg * 8, hh1);
-		tmem_ld8_nowait(tcol + 64 + cg * 8, hh2);
-		tmem_ld8_nowait(tcol + 96 + cg * 8, hl0);
-		tmem_ld8_nowait(tcol + 128 + cg * 8, hl1);
-		tmem_ld8_nowait(tcol + 160 + cg * 8, hl2);
-		tmem_wait_ld();
-#pragma unroll
-		for (int c = 0; c < 8; ++c) {
-			const float p0 = fmaf(hl0[c], kLoInv, hh0[c]);
-			const float p1 = fmaf(hl1[c], kLoInv, hh1[c]);
-			const float p2 = fmaf(hl2[c], kLoInv, hh2[c]);
-			const float up = __shfl_up_sync(0xffffffffu, p0, 1), dn = __shfl_down_sync(0xffffffffu, p2, 1);
-			o[cg * 8 + c] = ((w > 0 ? up : 0.f) + p1) + (w < 3 ? dn : 0.f);
-		}
+	for (int c = 0; c < 8; ++c) {
+		const float p0 = fmaf(hl0[c], kLoInv, hh0[c]);
+		const float p1 = fmaf(hl1[c], kLoInv, hh1[c]);
+		const float p2 = fmaf(hl2[c], kLoInv, hh2[c]);
+		const float up = __shfl_up_sync(0xffffffffu, p0, 1), dn = __shfl_down_sync(0xffffffffu, p2, 1);
+		o[c] = ((w > 0 ? up : 0.f) + p1) + (w < 3 ? dn : 0.f);
 	}
 }
 
-// 16 channels of one 8^3 row -> A8 (hi and lo planes)
-__device__ __forceinline__ void store_a8_row(uint32_t a8, int q, const float (&v)[16]) {
-#pragma unroll
-	for (int j = 0; j < 2; ++j) {
-		uint4 hi, lo;
-		split8(&v[j * 8], hi, lo);
-		const uint32_t a = a8 + j * kA8Plane + (uint32_t)(kA8Margin + q) * 16;
-		st_shared_v4(a, hi);
-		st_shared_v4(a + kA8Prec, lo);
-	}
+// channels 4g .. 4g+3 of one 8^3 row -> hi and lo planes (8 bytes each) at byte address `a` (plane, row, half chunk)
+__device__ __forceinline__ void store_split4(uint32_t a, uint32_t prec_stride, const float (&v)[4]) {
+	uint2 hi, lo;
+	split2(v[0], v[1], hi.x, lo.x);
+	split2(v[2], v[3], hi.y, lo.y);
+	st_shared_v2(a, hi);
+	st_shared_v2(a + prec_stride, lo);
 }
-// 32 channels of one 4^3 row -> H32
-__device__ __forceinline__ void store_h32_row(uint32_t hb, int r, const float (&v)[32]) {
-#pragma unroll
-	for (int j = 0; j < 4; ++j) {
-		uint4 hi, lo;
-		split8(&v[j * 8], hi, lo);
-		const uint32_t a = hb + j * kHPlane + (uint32_t)(kHMargin + r) * 16;
-		st_shared_v4(a, hi);
-		st_shared_v4(a + kHPrec, lo);
-	}
+// channels 8g .. 8g+7 of one 4^3 row -> one 16-byte chunk of the hi plane and one of the lo plane
+__device__ __forceinline__ void store_split8(uint32_t a, uint32_t prec_stride, const float (&v)[8]) {
+	uint4 hi, lo;
+	split2(v[0], v[1], hi.x, lo.x);
+	split2(v[2], v[3], hi.y, lo.y);
+	split2(v[4], v[5], hi.z, lo.z);
+	split2(v[6], v[7], hi.w, lo.w);
+	st_shared_v4(a, hi);
+	st_shared_v4(a + prec_stride, lo);
 }
 
 template <bool kProf> __device__ __forceinline__ long long prof_clock() { return kProf ? clock64() : 0; }
@@ -347,11 +341,11 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			mbar_init(bar_w_full(bars, s), 1);
 			mbar_init(bar_w_empty(bars, s), 1);
 		}
-		mbar_init(bar_a_ready(bars), 4);
+		mbar_init(bar_a_ready(bars), kRowWarps);
 		mbar_init(bar_d_full(bars), 1);
 		mbar_fence_init();
 	}
-	if (warp == 4) {
+	if (warp == kIssuerWarp) {
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
 	}
@@ -361,7 +355,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 	const uint32_t tmem = *tmem_slot;
 	const int64_t my_leaves = blockIdx.x < n_leaves ? (n_leaves - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-	if (warp == 5) {
+	if (warp == kProducerWarp) {
 		// ===================== TMA producer =====================
 		if (lane == 0) {
 			const uint32_t total = (uint32_t)(my_leaves * kEncTcUnits);
@@ -374,7 +368,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			}
 		}
 		__syncwarp();
-	} else if (warp == 4) {
+	} else if (warp == kIssuerWarp) {
 		// ===================== MMA issuer =====================
 		if (lane == 0) {
 			uint32_t unit = 0, a_count = 0;
@@ -429,19 +423,23 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					}
 					tc_commit(bar_d_full(bars));
 				}
-				// ---- down: 8 taps x 8 parity classes x {N = 64, N = 32} ----
+				// ---- down: 8 taps x 8 parity classes x {N = 64, N = 32}.  The tensor core truncates its fp32 accumulator
+				//      after every MMA, a bias that grows with the length of the accumulation chain; the 64 k-steps are
+				//      therefore split over kDownChains independent accumulators that the epilogue adds in fp32. ----
 				wait_a();
 #pragma unroll 1
 				for (int tap = 0; tap < 8; ++tap) {
 					const uint32_t wb = wait_w();
 					const long long c0 = prof_clock<kProf>();
 					const int s = (tap >> 2) * 25 + ((tap >> 1) & 1) * 5 + (tap & 1);
+					const uint32_t dcol = tmem + (uint32_t)(tap / (8 / kDownChains)) * 64;
+					const bool first = tap % (8 / kDownChains) == 0;
 #pragma unroll
 					for (int pc = 0; pc < 8; ++pc) {
 						const uint64_t ad = y_d + (uint64_t)(s + pc * 2 * (int)(kYPlane >> 4));
 						const uint64_t bd = make_desc(wb + pc * 2048, 64 * 16, 128);
-						mma_ss(tmem, ad, bd, idesc_f16(64), (tap > 0 || pc > 0) ? 1u : 0u);
-						mma_ss(tmem + 32, ad + (kYPrec >> 4), bd, idesc_f16(32), 1u);
+						mma_ss(dcol, ad, bd, idesc_f16(64), (!first || pc > 0) ? 1u : 0u);
+						mma_ss(dcol + 32, ad + (kYPrec >> 4), bd, idesc_f16(32), 1u);
 					}
 					release_w();
 					if (kProf) t_issue += prof_clock<kProf>() - c0;
@@ -509,11 +507,13 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 		__syncwarp();
 	} else {
 		// ===================== row threads: FFMA pre.0, epilogues, VQ =====================
+		// warp = g * 4 + quadrant: TMEM row = quadrant * 32 + lane; channel group g of kGroups.
 		RowCtx rc;
-		rc.tid = tid; rc.warp = warp; rc.lane = lane;
+		rc.warp = warp; rc.lane = lane; rc.g = warp >> 2;
 		rc.bars = bars;
-		rc.tlane = tmem + ((uint32_t)(warp * 32) << 16);
+		rc.tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 		rc.red = reinterpret_cast<float*>(smem + kOffRed);
+		const int g = rc.g, row = (warp & 3) * 32 + lane;
 		long long prof[16];
 #pragma unroll
 		for (int i = 0; i < 16; ++i) prof[i] = 0;
@@ -525,45 +525,50 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				pc0 = c;
 			}
 		};
-		// 4^3 row of this thread (res32 / proj / VQ tiles): q4 = tid
-		const int d4 = tid / 20, h4 = (tid - d4 * 20) >> 2, w4 = tid & 3;
-		const bool valid4 = tid < 80 && h4 < 4;
+		// 4^3 row of this thread (res32 / proj / VQ tiles): q4 = row
+		const int d4 = row / 20, h4 = (row - d4 * 20) >> 2, w4 = row & 3;
+		const bool valid4 = row < 80 && h4 < 4;
 		const int p4 = d4 * 16 + h4 * 4 + w4;
-		// `down` output row of this thread: q' = tid over the 5^3 grid
-		const int jd = tid / 25, jh = (tid - jd * 25) / 5, jw = tid % 5;
-		const bool validd = tid < 100 && jh < 4 && jw < 4;
+		// `down` output row of this thread: q' = row over the 5^3 grid
+		const int jd = row / 25, jh = (row - jd * 25) / 5, jw = row % 5;
+		const bool validd = row < 100 && jh < 4 && jw < 4;
 		const int pd = jd * 16 + jh * 4 + jw;
+		// VQ exchange arrays (overlay the x32 staging, dead by then): [4 groups][128 rows]
+		float* vq_zz = x32s;
+		float* vq_umin = x32s + 512;
+		float* vq_best = x32s + 1024;
+		int* vq_bidx = reinterpret_cast<int*>(x32s + 1536);
 
 #pragma unroll 1
 		for (int64_t it = 0; it < my_leaves; ++it) {
 			const int64_t leaf = blockIdx.x + it * gridDim.x;
 			// ---- stage the leaf (2048 B, 128-bit coalesced) into the haloed fp32 buffer; clear Y (z overlays dirtied it) ----
-			if (it > 0) row_bar();  // every row thread is done with the previous leaf's z rows
-			{
+			if (it > 0) {
+				row_bar();  // every row thread is done with the previous leaf's z rows
+				for (uint32_t i = tid; i < kYBytes / 16; i += kRowThreads) reinterpret_cast<uint4*>(smem + kOffY)[i] = make_uint4(0, 0, 0, 0);
+			}
+			if (tid < 128) {
 				const float4 v = __ldcs(reinterpret_cast<const float4*>(leaves + leaf * 512) + tid);
 				const int p = tid * 4, d = p >> 6, h = (p >> 3) & 7, w0 = p & 7;
 				float* dst = in_halo + (d + 1) * 100 + (h + 1) * 10 + w0 + 1;
 				dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-				if (it > 0) {
-					for (uint32_t i = tid; i < kYBytes / 16; i += kRowThreads) reinterpret_cast<uint4*>(smem + kOffY)[i] = make_uint4(0, 0, 0, 0);
-				}
 			}
 			row_bar();
 			lap(0);
 
-			// ---- pre.0: Conv3d(1,16,k3) on FFMA ; pre.1: GroupNorm(4,16) + ReLU -> x (kept in registers) ----
-			float xr[5][16];
+			// ---- pre.0: Conv3d(1,16,k3) on FFMA, channels 4g..4g+3 ; pre.1: GroupNorm(4,16) + ReLU -> x (kept in registers) ----
+			float xr[5][4];
 			uint32_t valid8 = 0;
 			{
 				int base[5];
 #pragma unroll
 				for (int t = 0; t < 5; ++t) {
 					int d, h, w8;
-					const bool ok = row8(t * 128 + tid, d, h, w8);
+					const bool ok = row8(t * 128 + row, d, h, w8);
 					valid8 |= ok ? (1u << t) : 0u;
 					base[t] = ok ? d * 100 + h * 10 + w8 : 0;
 #pragma unroll
-					for (int c = 0; c < 16; ++c) xr[t][c] = 0.f;
+					for (int c = 0; c < 4; ++c) xr[t][c] = 0.f;
 				}
 #pragma unroll 1
 				for (int kd = 0; kd < 3; ++kd) {
@@ -572,54 +577,56 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 #pragma unroll
 						for (int kw = 0; kw < 3; ++kw) {
 							const int tap = (kd * 3 + kh) * 3 + kw;
-							float wv[16];
-#pragma unroll
-							for (int q = 0; q < 4; ++q) {
-								const float4 f = *reinterpret_cast<const float4*>(s_prew + tap * 16 + q * 4);
-								wv[4 * q] = f.x; wv[4 * q + 1] = f.y; wv[4 * q + 2] = f.z; wv[4 * q + 3] = f.w;
-							}
+							const float4 f = *reinterpret_cast<const float4*>(s_prew + tap * 16 + g * 4);
+							const float wv[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
 							for (int t = 0; t < 5; ++t) {
 								const float xv = in_halo[base[t] + kd * 100 + kh * 10 + kw];
 #pragma unroll
-								for (int c = 0; c < 16; ++c) xr[t][c] = fmaf(xv, wv[c], xr[t][c]);
+								for (int c = 0; c < 4; ++c) xr[t][c] = fmaf(xv, wv[c], xr[t][c]);
 							}
 						}
 					}
 				}
 #pragma unroll
-				for (int c = 0; c < 16; ++c) {
-					const float b = __ldg(w.pre_b + c);
+				for (int c = 0; c < 4; ++c) {
+					const float b = __ldg(w.pre_b + g * 4 + c);
 #pragma unroll
 					for (int t = 0; t < 5; ++t) xr[t][c] += b;
 				}
-				float mean[4], rstd[4];
-				gn_stats_regs<5, 16, 4>(xr, valid8, 1.f / 2048.f, rc, mean, rstd);
+				float mean[1], rstd[1];  // this thread's 4 channels are exactly GroupNorm group g
+				gn_stats_regs<5, 4, 4>(xr, valid8, 1.f / 2048.f, rc, mean, rstd);
 #pragma unroll
-				for (int c = 0; c < 16; ++c) {
-					const float ga = __ldg(w.pre_gn_w + c), be = __ldg(w.pre_gn_b + c);
+				for (int c = 0; c < 4; ++c) {
+					const float ga = __ldg(w.pre_gn_w + g * 4 + c), be = __ldg(w.pre_gn_b + g * 4 + c);
 #pragma unroll
-					for (int t = 0; t < 5; ++t) xr[t][c] = fmaxf((xr[t][c] - mean[c >> 2]) * rstd[c >> 2] * ga + be, 0.f);
+					for (int t = 0; t < 5; ++t) xr[t][c] = fmaxf((xr[t][c] - mean[0]) * rstd[0] * ga + be, 0.f);
 				}
 			}
 			lap(1);
 			// ---- res16.gn1 + ReLU -> A8 (conv1 input) ----
+			const uint32_t a8_mine = a8 + (uint32_t)(g >> 1) * kA8Plane + (uint32_t)(kA8Margin + row) * 16 + (uint32_t)(g & 1) * 8;
 			{
-				float mean[8], rstd[8];
-				gn_stats_regs<5, 16, 2>(xr, valid8, 1.f / 1024.f, rc, mean, rstd);
+				float mean[2], rstd[2];
+				gn_stats_regs<5, 4, 2>(xr, valid8, 1.f / 1024.f, rc, mean, rstd);
+				float ga[4], be[4];
+#pragma unroll
+				for (int c = 0; c < 4; ++c) {
+					ga[c] = __ldg(w.res16.gn1_w + g * 4 + c);
+					be[c] = __ldg(w.res16.gn1_b + g * 4 + c);
+				}
 #pragma unroll
 				for (int t = 0; t < 5; ++t) {
-					int d, h, w8;
-					const bool ok = row8(t * 128 + tid, d, h, w8);
-					if (ok) {
-						float a[16];
+					if (valid8 & (1u << t)) {
+						float a[4];
 #pragma unroll
-						for (int c = 0; c < 16; ++c)
-							a[c] = fmaxf((xr[t][c] - mean[c >> 1]) * rstd[c >> 1] * __ldg(w.res16.gn1_w + c) + __ldg(w.res16.gn1_b + c), 0.f);
-						store_a8_row(a8, t * 128 + tid, a);
+						for (int c = 0; c < 4; ++c) a[c] = fmaxf((xr[t][c] - mean[c >> 1]) * rstd[c >> 1] * ga[c] + be[c], 0.f);
+						store_split4(a8_mine + t * 2048, kA8Prec, a);
 						if (tap_stage == 0) {
+							int d, h, w8;
+							row8(t * 128 + row, d, h, w8);
 #pragma unroll
-							for (int c = 0; c < 16; ++c) tap_out[(leaf * 16 + c) * 512 + d * 64 + h * 8 + w8] = xr[t][c];
+							for (int c = 0; c < 4; ++c) tap_out[(leaf * 16 + g * 4 + c) * 512 + d * 64 + h * 8 + w8] = xr[t][c];
 						}
 					}
 				}
@@ -627,66 +634,40 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			signal_a_ready(bars, lane);
 			lap(2);
 
-			// ---- conv1 epilogue: + bias, res16.gn2 + ReLU -> A8 (conv2 input).  The combined fp32 outputs are parked
-			//      in the tile's own (already consumed) TMEM columns between the statistics passes. ----
+			// ---- conv1 epilogue: + bias, res16.gn2 + ReLU -> A8 (conv2 input) ----
 			wait_accumulator(rc);
 			lap(3);
 			{
-				float s[8];
+				float v[5][4];
+				float bs[4];
 #pragma unroll
-				for (int g = 0; g < 8; ++g) s[g] = 0.f;
-#pragma unroll 1
+				for (int c = 0; c < 4; ++c) bs[c] = __ldg(w.res16.c1_b + g * 4 + c);
+#pragma unroll
 				for (int t = 0; t < 5; ++t) {
-					float o[16];
-					conv16_tile_out(rc.tlane + t * 96, lane & 7, o);
+					conv16_tile_out(rc.tlane + t * 96, g, lane & 7, v[t]);
 #pragma unroll
-					for (int c = 0; c < 16; ++c) o[c] += __ldg(w.res16.c1_b + c);
-					tmem_st16(rc.tlane + t * 96, o);
-					if (valid8 & (1u << t)) {
+					for (int c = 0; c < 4; ++c) v[t][c] += bs[c];
+					if (tap_stage == 6 && (valid8 & (1u << t))) {
+						int d, h, w8;
+						row8(t * 128 + row, d, h, w8);
 #pragma unroll
-						for (int c = 0; c < 16; ++c) s[c >> 1] += o[c];
-						if (tap_stage == 6) {
-							int d, h, w8;
-							row8(t * 128 + tid, d, h, w8);
-#pragma unroll
-							for (int c = 0; c < 16; ++c) tap_out[(leaf * 16 + c) * 512 + d * 64 + h * 8 + w8] = o[c];
-						}
+						for (int c = 0; c < 4; ++c) tap_out[(leaf * 16 + g * 4 + c) * 512 + d * 64 + h * 8 + w8] = v[t][c];
 					}
 				}
-				tmem_wait_st();
-				row_allreduce<8>(s, rc, 0);
-				float mean[8], rstd[8];
+				float mean[2], rstd[2];
+				gn_stats_regs<5, 4, 2>(v, valid8, 1.f / 1024.f, rc, mean, rstd);
+				float ga[4], be[4];
 #pragma unroll
-				for (int g = 0; g < 8; ++g) {
-					mean[g] = s[g] * (1.f / 1024.f);
-					s[g] = 0.f;
+				for (int c = 0; c < 4; ++c) {
+					ga[c] = __ldg(w.res16.gn2_w + g * 4 + c);
+					be[c] = __ldg(w.res16.gn2_b + g * 4 + c);
 				}
-#pragma unroll 1
+#pragma unroll
 				for (int t = 0; t < 5; ++t) {
-					float o[16];
-					tmem_ld16_nowait(rc.tlane + t * 96, o);
-					tmem_wait_ld();
 					if (valid8 & (1u << t)) {
 #pragma unroll
-						for (int c = 0; c < 16; ++c) {
-							const float dv = o[c] - mean[c >> 1];
-							s[c >> 1] = fmaf(dv, dv, s[c >> 1]);
-						}
-					}
-				}
-				row_allreduce<8>(s, rc, 1);
-#pragma unroll
-				for (int g = 0; g < 8; ++g) rstd[g] = 1.f / sqrtf(s[g] * (1.f / 1024.f) + kGnEps);
-#pragma unroll 1
-				for (int t = 0; t < 5; ++t) {
-					float o[16];
-					tmem_ld16_nowait(rc.tlane + t * 96, o);
-					tmem_wait_ld();
-					if (valid8 & (1u << t)) {
-#pragma unroll
-						for (int c = 0; c < 16; ++c)
-							o[c] = fmaxf((o[c] - mean[c >> 1]) * rstd[c >> 1] * __ldg(w.res16.gn2_w + c) + __ldg(w.res16.gn2_b + c), 0.f);
-						store_a8_row(a8, t * 128 + tid, o);
+						for (int c = 0; c < 4; ++c) v[t][c] = fmaxf((v[t][c] - mean[c >> 1]) * rstd[c >> 1] * ga[c] + be[c], 0.f);
+						store_split4(a8_mine + t * 2048, kA8Prec, v[t]);
 					}
 				}
 			}
@@ -696,87 +677,97 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			// ---- conv2 epilogue: x2 = x + 0.1 (conv2 + b) -> Y, the space-to-depth input of `down` ----
 			wait_accumulator(rc);
 			lap(5);
+			{
+				float bs[4];
 #pragma unroll
-			for (int t = 0; t < 5; ++t) {
-				float o[16];
-				conv16_tile_out(rc.tlane + t * 96, lane & 7, o);
-				int d, h, w8;
-				const bool ok = row8(t * 128 + tid, d, h, w8);
-				if (ok) {
+				for (int c = 0; c < 4; ++c) bs[c] = __ldg(w.res16.c2_b + g * 4 + c);
 #pragma unroll
-					for (int c = 0; c < 16; ++c) o[c] = xr[t][c] + kResScale * (o[c] + __ldg(w.res16.c2_b + c));
-					if (tap_stage == 1) {
+				for (int t = 0; t < 5; ++t) {
+					float o[4];
+					conv16_tile_out(rc.tlane + t * 96, g, lane & 7, o);
+					int d, h, w8;
+					const bool ok = row8(t * 128 + row, d, h, w8);
+					if (ok) {
 #pragma unroll
-						for (int c = 0; c < 16; ++c) tap_out[(leaf * 16 + c) * 512 + d * 64 + h * 8 + w8] = o[c];
-					}
-					const int pcl = (((d + 1) & 1) << 2) | (((h + 1) & 1) << 1) | ((w8 + 1) & 1);
-					const int qy = ((d + 1) >> 1) * 25 + ((h + 1) >> 1) * 5 + ((w8 + 1) >> 1);
+						for (int c = 0; c < 4; ++c) o[c] = xr[t][c] + kResScale * (o[c] + bs[c]);
+						if (tap_stage == 1) {
 #pragma unroll
-					for (int j = 0; j < 2; ++j) {
-						uint4 hi, lo;
-						split8(&o[j * 8], hi, lo);
-						const uint32_t a = yb + (uint32_t)(pcl * 2 + j) * kYPlane + (uint32_t)qy * 16;
-						st_shared_v4(a, hi);
-						st_shared_v4(a + kYPrec, lo);
+							for (int c = 0; c < 4; ++c) tap_out[(leaf * 16 + g * 4 + c) * 512 + d * 64 + h * 8 + w8] = o[c];
+						}
+						const int pcl = (((d + 1) & 1) << 2) | (((h + 1) & 1) << 1) | ((w8 + 1) & 1);
+						const int qy = ((d + 1) >> 1) * 25 + ((h + 1) >> 1) * 5 + ((w8 + 1) >> 1);
+						store_split4(yb + (uint32_t)(pcl * 2 + (g >> 1)) * kYPlane + (uint32_t)qy * 16 + (uint32_t)(g & 1) * 8, kYPrec, o);
 					}
 				}
 			}
 			signal_a_ready(bars, lane);
 			lap(6);
 
-			// ---- down epilogue: + bias -> x32 (residual, to shared memory) ; res32.gn1 + ReLU -> H32 ----
+			// ---- down epilogue: sum the accumulation chains, + bias -> x32 (residual, to shared memory) ; res32.gn1 + ReLU -> H32 ----
 			wait_accumulator(rc);
 			lap(7);
 			{
-				float v[1][32];
+				float v[1][8];
 				{
-					float hh[32], hl[32];
-					tmem_ld32_nowait(rc.tlane, hh);
-					tmem_ld32_nowait(rc.tlane + 32, hl);
-					tmem_wait_ld();
+					float hh[8], hl[8];
 #pragma unroll
-					for (int c = 0; c < 32; ++c) v[0][c] = fmaf(hl[c], kLoInv, hh[c]) + __ldg(w.down_b + c);
+					for (int pr = 0; pr < kDownChains / 2; ++pr) {
+						float a0[8], a1[8], b0[8], b1[8];
+						tmem_ld8_nowait(rc.tlane + (2 * pr) * 64 + g * 8, a0);
+						tmem_ld8_nowait(rc.tlane + (2 * pr) * 64 + 32 + g * 8, b0);
+						tmem_ld8_nowait(rc.tlane + (2 * pr + 1) * 64 + g * 8, a1);
+						tmem_ld8_nowait(rc.tlane + (2 * pr + 1) * 64 + 32 + g * 8, b1);
+						tmem_wait_ld();
+#pragma unroll
+						for (int c = 0; c < 8; ++c) {
+							const float sa = a0[c] + a1[c], sb = b0[c] + b1[c];
+							hh[c] = pr == 0 ? sa : hh[c] + sa;
+							hl[c] = pr == 0 ? sb : hl[c] + sb;
+						}
+					}
+#pragma unroll
+					for (int c = 0; c < 8; ++c) v[0][c] = fmaf(hl[c], kLoInv, hh[c]) + __ldg(w.down_b + g * 8 + c);
 				}
 				if (validd) {
-#pragma unroll
-					for (int q = 0; q < 8; ++q)
-						*reinterpret_cast<float4*>(x32s + pd * kX32Pitch + q * 4) = make_float4(v[0][4 * q], v[0][4 * q + 1], v[0][4 * q + 2], v[0][4 * q + 3]);
+					*reinterpret_cast<float4*>(x32s + pd * kX32Pitch + g * 8) = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
+					*reinterpret_cast<float4*>(x32s + pd * kX32Pitch + g * 8 + 4) = make_float4(v[0][4], v[0][5], v[0][6], v[0][7]);
 					if (tap_stage == 2) {
 #pragma unroll
-						for (int c = 0; c < 32; ++c) tap_out[(leaf * 32 + c) * 64 + pd] = v[0][c];
+						for (int c = 0; c < 8; ++c) tap_out[(leaf * 32 + g * 8 + c) * 64 + pd] = v[0][c];
 					}
 				}
-				float mean[8], rstd[8];
-				gn_stats_regs<1, 32, 4>(v, validd ? 1u : 0u, 1.f / 256.f, rc, mean, rstd);
+				float mean[2], rstd[2];
+				gn_stats_regs<1, 8, 4>(v, validd ? 1u : 0u, 1.f / 256.f, rc, mean, rstd);
 				if (validd) {
 #pragma unroll
-					for (int c = 0; c < 32; ++c)
-						v[0][c] = fmaxf((v[0][c] - mean[c >> 2]) * rstd[c >> 2] * __ldg(w.res32.gn1_w + c) + __ldg(w.res32.gn1_b + c), 0.f);
-					store_h32_row(hb, jd * 20 + jh * 4 + jw, v[0]);
+					for (int c = 0; c < 8; ++c)
+						v[0][c] = fmaxf((v[0][c] - mean[c >> 2]) * rstd[c >> 2] * __ldg(w.res32.gn1_w + g * 8 + c) + __ldg(w.res32.gn1_b + g * 8 + c), 0.f);
+					store_split8(hb + (uint32_t)g * kHPlane + (uint32_t)(kHMargin + jd * 20 + jh * 4 + jw) * 16, kHPrec, v[0]);
 				}
 			}
 			signal_a_ready(bars, lane);
 			lap(8);
 
 			// ---- res32 conv1 epilogue: + bias, gn2 + ReLU -> H32 ----
+			const uint32_t h_mine = hb + (uint32_t)g * kHPlane + (uint32_t)(kHMargin + row) * 16;
 			wait_accumulator(rc);
 			lap(9);
 			{
-				float v[1][32];
-				conv32_tile_out(rc.tlane, w4, v[0]);
+				float v[1][8];
+				conv32_tile_out(rc.tlane, g, w4, v[0]);
 #pragma unroll
-				for (int c = 0; c < 32; ++c) v[0][c] += __ldg(w.res32.c1_b + c);
+				for (int c = 0; c < 8; ++c) v[0][c] += __ldg(w.res32.c1_b + g * 8 + c);
 				if (valid4 && tap_stage == 7) {
 #pragma unroll
-					for (int c = 0; c < 32; ++c) tap_out[(leaf * 32 + c) * 64 + p4] = v[0][c];
+					for (int c = 0; c < 8; ++c) tap_out[(leaf * 32 + g * 8 + c) * 64 + p4] = v[0][c];
 				}
-				float mean[8], rstd[8];
-				gn_stats_regs<1, 32, 4>(v, valid4 ? 1u : 0u, 1.f / 256.f, rc, mean, rstd);
+				float mean[2], rstd[2];
+				gn_stats_regs<1, 8, 4>(v, valid4 ? 1u : 0u, 1.f / 256.f, rc, mean, rstd);
 				if (valid4) {
 #pragma unroll
-					for (int c = 0; c < 32; ++c)
-						v[0][c] = fmaxf((v[0][c] - mean[c >> 2]) * rstd[c >> 2] * __ldg(w.res32.gn2_w + c) + __ldg(w.res32.gn2_b + c), 0.f);
-					store_h32_row(hb, tid, v[0]);
+					for (int c = 0; c < 8; ++c)
+						v[0][c] = fmaxf((v[0][c] - mean[c >> 2]) * rstd[c >> 2] * __ldg(w.res32.gn2_w + g * 8 + c) + __ldg(w.res32.gn2_b + g * 8 + c), 0.f);
+					store_split8(h_mine, kHPrec, v[0]);
 				}
 			}
 			signal_a_ready(bars, lane);
@@ -786,36 +777,34 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			wait_accumulator(rc);
 			lap(11);
 			{
-				float v[32];
-				conv32_tile_out(rc.tlane, w4, v);
+				float v[8];
+				conv32_tile_out(rc.tlane, g, w4, v);
 				if (valid4) {
+					const float4 x0 = *reinterpret_cast<const float4*>(x32s + p4 * kX32Pitch + g * 8);
+					const float4 x1 = *reinterpret_cast<const float4*>(x32s + p4 * kX32Pitch + g * 8 + 4);
+					const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-					for (int q = 0; q < 8; ++q) {
-						const float4 xv = *reinterpret_cast<const float4*>(x32s + p4 * kX32Pitch + q * 4);
-						v[4 * q] = xv.x + kResScale * (v[4 * q] + __ldg(w.res32.c2_b + 4 * q));
-						v[4 * q + 1] = xv.y + kResScale * (v[4 * q + 1] + __ldg(w.res32.c2_b + 4 * q + 1));
-						v[4 * q + 2] = xv.z + kResScale * (v[4 * q + 2] + __ldg(w.res32.c2_b + 4 * q + 2));
-						v[4 * q + 3] = xv.w + kResScale * (v[4 * q + 3] + __ldg(w.res32.c2_b + 4 * q + 3));
-					}
+					for (int c = 0; c < 8; ++c) v[c] = xv[c] + kResScale * (v[c] + __ldg(w.res32.c2_b + g * 8 + c));
 					if (tap_stage == 3) {
 #pragma unroll
-						for (int c = 0; c < 32; ++c) tap_out[(leaf * 32 + c) * 64 + p4] = v[c];
+						for (int c = 0; c < 8; ++c) tap_out[(leaf * 32 + g * 8 + c) * 64 + p4] = v[c];
 					}
 				}
-				float* part = att;          // [4 warps][32]
+				float* part = att;          // [16 warps][8]
 				float* hid = att + 128;     // [8]
 				float* scale = att + 136;   // [32]
 #pragma unroll
-				for (int c = 0; c < 32; ++c) {
+				for (int c = 0; c < 8; ++c) {
 					const float s = warp_sum(valid4 ? v[c] : 0.f);
-					if (lane == 0) part[warp * 32 + c] = s;
+					if (lane == 0) part[warp * 8 + c] = s;
 				}
 				row_bar();
 				if (tid < 8) {
 					float s = 0.f;
 #pragma unroll 8
 					for (int c = 0; c < 32; ++c) {
-						const float m = ((part[c] + part[32 + c]) + (part[64 + c] + part[96 + c])) * (1.f / 64.f);
+						const float* pp = part + (c >> 3) * 32 + (c & 7);  // channel c = 8 g' + i lives in warps 4g' .. 4g'+3
+						const float m = ((pp[0] + pp[8]) + (pp[16] + pp[24])) * (1.f / 64.f);
 						s = fmaf(__ldg(w.fc0 + tid * 32 + c), m, s);
 					}
 					hid[tid] = fmaxf(s, 0.f);
@@ -830,50 +819,54 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				row_bar();
 				if (valid4) {
 #pragma unroll
-					for (int c = 0; c < 32; ++c) v[c] *= scale[c];
+					for (int c = 0; c < 8; ++c) v[c] *= scale[g * 8 + c];
 					if (tap_stage == 4) {
 #pragma unroll
-						for (int c = 0; c < 32; ++c) tap_out[(leaf * 32 + c) * 64 + p4] = v[c];
+						for (int c = 0; c < 8; ++c) tap_out[(leaf * 32 + g * 8 + c) * 64 + p4] = v[c];
 					}
-					store_h32_row(hb, tid, v);
+					store_split8(h_mine, kHPrec, v);
 				}
 			}
 			signal_a_ready(bars, lane);
 			lap(12);
 
-			// ---- proj epilogue: z = acc + b -> fp32 rows (exact re-scoring) and bf16 A operand of the VQ GEMM ----
+			// ---- proj epilogue: z (channels 32g .. 32g+31) = acc + b -> fp32 rows (exact re-scoring) and the bf16 A operand
+			//      of the VQ GEMM; |z|^2 as four per-group partial sums, each sequential in d ----
 			wait_accumulator(rc);
 			lap(13);
-			float zz = 0.f;
-#pragma unroll 1
-			for (int i = 0; i < 4; ++i) {
-				float hh[32], hl[32];
-				tmem_ld32_nowait(rc.tlane + i * 32, hh);
-				tmem_ld32_nowait(rc.tlane + 128 + i * 32, hl);
-				tmem_wait_ld();
+			{
+				float zzp = 0.f;
 #pragma unroll
-				for (int c = 0; c < 32; ++c) {
-					hh[c] = fmaf(hl[c], kLoInv, hh[c]) + __ldg(w.proj_b + i * 32 + c);
-					zz = fmaf(hh[c], hh[c], zz);  // sequential in d, like the exact re-scoring
-				}
-				if (valid4) {
+				for (int half = 0; half < 2; ++half) {
+					float hh[16], hl[16];
+					tmem_ld16_nowait(rc.tlane + g * 32 + half * 16, hh);
+					tmem_ld16_nowait(rc.tlane + 128 + g * 32 + half * 16, hl);
+					tmem_wait_ld();
 #pragma unroll
-					for (int q = 0; q < 8; ++q)
-						*reinterpret_cast<float4*>(zs + p4 * kZsPitch + i * 32 + q * 4) = make_float4(hh[4 * q], hh[4 * q + 1], hh[4 * q + 2], hh[4 * q + 3]);
-					if (tap_stage == 5) {
+					for (int c = 0; c < 16; ++c) {
+						hh[c] = fmaf(hl[c], kLoInv, hh[c]) + __ldg(w.proj_b + g * 32 + half * 16 + c);
+						zzp = fmaf(hh[c], hh[c], zzp);
+					}
+					if (valid4) {
 #pragma unroll
-						for (int c = 0; c < 32; ++c) tap_out[(leaf * 128 + i * 32 + c) * 64 + p4] = hh[c];
+						for (int q = 0; q < 4; ++q)
+							*reinterpret_cast<float4*>(zs + p4 * kZsPitch + g * 32 + half * 16 + q * 4) = make_float4(hh[4 * q], hh[4 * q + 1], hh[4 * q + 2], hh[4 * q + 3]);
+						if (tap_stage == 5) {
+#pragma unroll
+							for (int c = 0; c < 16; ++c) tap_out[(leaf * 128 + g * 32 + half * 16 + c) * 64 + p4] = hh[c];
+						}
+					}
+#pragma unroll
+					for (int j = 0; j < 2; ++j) {
+						uint4 pk;
+						pk.x = pack_bf16(hh[8 * j], hh[8 * j + 1]);
+						pk.y = pack_bf16(hh[8 * j + 2], hh[8 * j + 3]);
+						pk.z = pack_bf16(hh[8 * j + 4], hh[8 * j + 5]);
+						pk.w = pack_bf16(hh[8 * j + 6], hh[8 * j + 7]);
+						st_shared_v4(zb + (uint32_t)(g * 4 + half * 2 + j) * kZbPlane + (uint32_t)row * 16, pk);
 					}
 				}
-#pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					uint4 pk;
-					pk.x = pack_bf16(hh[8 * j], hh[8 * j + 1]);
-					pk.y = pack_bf16(hh[8 * j + 2], hh[8 * j + 3]);
-					pk.z = pack_bf16(hh[8 * j + 4], hh[8 * j + 5]);
-					pk.w = pack_bf16(hh[8 * j + 6], hh[8 * j + 7]);
-					st_shared_v4(zb + (uint32_t)(i * 4 + j) * kZbPlane + (uint32_t)tid * 16, pk);
-				}
+				vq_zz[g * 128 + row] = zzp;
 			}
 			signal_a_ready(bars, lane);
 			lap(14);
@@ -883,62 +876,77 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			//     |a_k - (true score - |z|^2)| <= B_k = 2^-7 * 1.07 * |z| * |e_k| + 1e-4  (bf16 unit roundoff 2^-9 per operand);
 			//  2. every code whose lower bound a_k - B_k does not exceed min_j (a_j + B_j) is re-scored with the
 			//     reference's fp32 formula, sequential in d: the fp32 arg-min and all its ties are in that shortlist.
+			//  The four threads of a row take 64 codes each; tcgen05.ld is warp-collective, so every lane runs the loads.
 			wait_accumulator(rc);
+			row_bar();  // z rows and |z|^2 partials of all four groups are in place
 			lap(15);
 			{
-				// tcgen05.ld is warp-collective: every lane runs the loads, only valid rows do the arithmetic
+				const float zz = (vq_zz[row] + vq_zz[128 + row]) + (vq_zz[256 + row] + vq_zz[384 + row]);
 				const float cb = 0.0078125f * 1.07f * sqrtf(zz);
+				float sc[64];
+				tmem_ld32_nowait(rc.tlane + g * 64, *reinterpret_cast<float(*)[32]>(&sc[0]));
+				tmem_ld32_nowait(rc.tlane + g * 64 + 32, *reinterpret_cast<float(*)[32]>(&sc[32]));
+				tmem_wait_ld();
 				float umin = INFINITY;
-#pragma unroll 1
-				for (int i = 0; i < 8; ++i) {
-					float sc[32];
-					tmem_ld32_nowait(rc.tlane + i * 32, sc);
-					tmem_wait_ld();
 #pragma unroll
-					for (int j = 0; j < 32; ++j) {
-						const float a = s_esq[i * 32 + j] - 2.f * sc[j];
-						umin = fminf(umin, a + (cb * s_eno[i * 32 + j] + 1e-4f));
-					}
+				for (int j = 0; j < 64; ++j) {
+					sc[j] = s_esq[g * 64 + j] - 2.f * sc[j];
+					umin = fminf(umin, sc[j] + (cb * s_eno[g * 64 + j] + 1e-4f));
 				}
+				vq_umin[g * 128 + row] = umin;
+				row_bar();
+				umin = fminf(fminf(vq_umin[row], vq_umin[128 + row]), fminf(vq_umin[256 + row], vq_umin[384 + row]));
+				unsigned long long mask = 0ull;
+#pragma unroll
+				for (int j = 0; j < 64; ++j)
+					if (sc[j] - (cb * s_eno[g * 64 + j] + 1e-4f) <= umin) mask |= 1ull << j;
+				if (!valid4) mask = 0ull;
 				float best = INFINITY;
-				int bi = 0;
+				int bi = 0x7fffffff;
 				const float* zrow = zs + (valid4 ? p4 : 0) * kZsPitch;
-#pragma unroll 1
-				for (int i = 0; i < 8; ++i) {
-					float sc[32];
-					__syncwarp();
-					tmem_ld32_nowait(rc.tlane + i * 32, sc);
-					tmem_wait_ld();
-					uint32_t mask = 0u;
-#pragma unroll
-					for (int j = 0; j < 32; ++j) {
-						const float a = s_esq[i * 32 + j] - 2.f * sc[j];
-						if (a - (cb * s_eno[i * 32 + j] + 1e-4f) <= umin) mask |= 1u << j;
-					}
-					if (!valid4) mask = 0u;
-					while (mask) {
-						const int b = __ffs((int)mask) - 1;
-						mask &= mask - 1;
-						const int code = i * 32 + b;
-						const float4* er = reinterpret_cast<const float4*>(w.emb + code * 128);
-						float dot = 0.f;
+				while (mask) {  // two candidates per trip: two independent FMA chains
+					const int b0 = __ffsll((long long)mask) - 1;
+					mask &= mask - 1;
+					const bool two = mask != 0ull;
+					const int b1 = two ? __ffsll((long long)mask) - 1 : b0;
+					mask &= mask - 1;  // no-op on zero
+					const int code0 = g * 64 + b0, code1 = g * 64 + b1;
+					const float4* e0 = reinterpret_cast<const float4*>(w.emb + code0 * 128);
+					const float4* e1 = reinterpret_cast<const float4*>(w.emb + code1 * 128);
+					float dot0 = 0.f, dot1 = 0.f;
 #pragma unroll 4
-						for (int q = 0; q < 32; ++q) {
-							const float4 e = __ldg(er + q);
-							const float4 zv = *reinterpret_cast<const float4*>(zrow + q * 4);
-							dot = fmaf(zv.x, e.x, dot);
-							dot = fmaf(zv.y, e.y, dot);
-							dot = fmaf(zv.z, e.z, dot);
-							dot = fmaf(zv.w, e.w, dot);
-						}
-						const float dist = (zz + s_esq[code]) - 2.f * dot;
-						if (dist < best) {  // codes ascend, so strict < keeps the first minimum
-							best = dist;
-							bi = code;
-						}
+					for (int q = 0; q < 32; ++q) {
+						const float4 ea = __ldg(e0 + q), eb = __ldg(e1 + q);
+						const float4 zv = *reinterpret_cast<const float4*>(zrow + q * 4);
+						dot0 = fmaf(zv.x, ea.x, dot0); dot1 = fmaf(zv.x, eb.x, dot1);
+						dot0 = fmaf(zv.y, ea.y, dot0); dot1 = fmaf(zv.y, eb.y, dot1);
+						dot0 = fmaf(zv.z, ea.z, dot0); dot1 = fmaf(zv.z, eb.z, dot1);
+						dot0 = fmaf(zv.w, ea.w, dot0); dot1 = fmaf(zv.w, eb.w, dot1);
+					}
+					const float dist0 = (zz + s_esq[code0]) - 2.f * dot0, dist1 = (zz + s_esq[code1]) - 2.f * dot1;
+					if (dist0 < best) {  // codes ascend, so strict < keeps the first minimum
+						best = dist0;
+						bi = code0;
+					}
+					if (two && dist1 < best) {
+						best = dist1;
+						bi = code1;
 					}
 				}
-				if (valid4) indices[leaf * 64 + p4] = (uint8_t)bi;  // p = (d*4+h)*4+w == view(B,4,4,4)
+				vq_best[g * 128 + row] = best;
+				vq_bidx[g * 128 + row] = bi;
+				row_bar();
+				if (g == 0 && valid4) {
+#pragma unroll
+					for (int o = 1; o < 4; ++o) {  // ascending code ranges: strict < keeps the lowest code among equal distances
+						const float ob = vq_best[o * 128 + row];
+						if (ob < best) {
+							best = ob;
+							bi = vq_bidx[o * 128 + row];
+						}
+					}
+					indices[leaf * 64 + p4] = (uint8_t)bi;  // p = (d*4+h)*4+w == view(B,4,4,4)
+				}
 			}
 			tc_fence_before();  // this leaf's TMEM reads are ordered before the next leaf's first MMAs (via a_ready)
 			lap(0);
@@ -953,7 +961,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 	// ---- teardown ----
 	tc_fence_before();
 	__syncthreads();
-	if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+	if (warp == kIssuerWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
 }  // namespace
