@@ -228,6 +228,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=16384, help="leaves per step for the CPU reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--decode-precision", default="default")
+    ap.add_argument("--encode-precision", default="default", help="default | fp32 (FFMA) | fp16x2_tc (tcgen05)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -252,7 +253,8 @@ def main():
     L = args.leaves
 
     codec = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, device_index=local,
-                                           decode_precision=args.decode_precision), BackendType.B200)
+                                           decode_precision=args.decode_precision,
+                                           encode_precision=args.encode_precision), BackendType.B200)
     if codec is None:
         raise SystemExit("B200 backend failed to initialise")
 
@@ -339,18 +341,26 @@ def main():
         dom_ms = max(dec_ms, enc_ms)
         flop = FLOP_DECODE if dom == "decode" else FLOP_ENCODE
         tensor_path = codec.decode_path != "fp32"
-        dom_on_tensor = (dom == "decode" and tensor_path)
+        dom_on_tensor = (dom == "decode" and tensor_path) or (dom == "encode" and codec.encode_path == "fp16x2_tcgen05")
         achieved = flop * L / (dom_ms / 1e3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         ffma_peak = 71.0   # TFLOP/s, measured on this part with tools/microbench/pipe_rates.cu (nominal 74.4)
         hmma_peak = 555.0  # TFLOP/s, legacy mma.sync bf16 path, same micro-benchmark
         enc_tf = FLOP_ENCODE * L / (enc_ms / 1e3) / 1e12
         dec_tf = FLOP_DECODE * L / (dec_ms / 1e3) / 1e12
+        enc_tc = codec.encode_path == "fp16x2_tcgen05"
+        # tensor-core encoder: every conv is three fp16 products (hi*hi, hi*lo, lo*hi) and the VQ scores one bf16 product,
+        # pre.0 stays on FFMA: MACs issued to the tensor pipe per leaf = 3 * (13 197 824 - 221 184) + 2 097 152
+        enc_issued_tf = (3 * (13197824 - 221184) + 2097152) * 2 * L / (enc_ms / 1e3) / 1e12
         kernels = {
-            "encode_fp32_kernel": {"ms": enc_ms, "share_of_step": enc_ms / (enc_ms + dec_ms), "achieved_tflops": enc_tf,
-                                   "pipe": "fp32 FFMA", "pipe_peak_tflops": ffma_peak, "frac_of_pipe_peak": enc_tf / ffma_peak,
-                                   "frac_of_bf16_tensor_peak": enc_tf / peak, "algorithmic_mflop_per_leaf": FLOP_ENCODE / 1e6,
-                                   "hbm_gbs": BYTES_ENCODE * L / (enc_ms / 1e3) / 1e9},
+            ("encode_tc_kernel" if enc_tc else "encode_fp32_kernel"): {
+                "ms": enc_ms, "share_of_step": enc_ms / (enc_ms + dec_ms), "achieved_tflops": enc_tf,
+                "pipe": "tensor (tcgen05.mma, fp16 2-way split operands = 3 products, fp32 accumulate in TMEM)" if enc_tc else "fp32 FFMA",
+                "pipe_peak_tflops": peak if enc_tc else ffma_peak,
+                "frac_of_pipe_peak": (enc_issued_tf if enc_tc else enc_tf) / (peak if enc_tc else ffma_peak),
+                "issued_tflops": enc_issued_tf if enc_tc else enc_tf,
+                "frac_of_bf16_tensor_peak": enc_tf / peak, "algorithmic_mflop_per_leaf": FLOP_ENCODE / 1e6,
+                "hbm_gbs": BYTES_ENCODE * L / (enc_ms / 1e3) / 1e9},
             ("decode_tc_kernel" if codec.decode_path == "bf16_tcgen05" else "decode_mma_kernel" if tensor_path else "decode_fp32_kernel"): {"ms": dec_ms, "share_of_step": dec_ms / (enc_ms + dec_ms), "achieved_tflops": dec_tf,
                                   "pipe": ("tensor (tcgen05.mma bf16, TMEM accumulators)" if codec.decode_path == "bf16_tcgen05" else
                                            "tensor (mma.sync bf16)" if tensor_path else "fp32 FFMA"),
@@ -363,19 +373,21 @@ def main():
             "metric": "leaves_per_sec_encode_decode", "value": value, "unit": "leaves/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 encode+VQ, %s decode" % ("bf16 operands/f32 accumulate" if codec.decode_path != "fp32" else "f32"),
+            "dtype": "%s encode+VQ, %s decode" % (
+                "f16x2-split operands/f32 accumulate (f32-level)" if codec.encode_path == "fp16x2_tcgen05" else "f32",
+                "bf16 operands/f32 accumulate" if codec.decode_path != "fp32" else "f32"),
             "data": "synthetic",
             "config": {"workload": "roundtrip_1M_float_leaves", "leaves_per_gpu": L, "weights": "shipped float model C=1 D=128 K=256",
                        "sharding": "leaf ranges, one rank per GPU" + (", NCCL gather of decoded blocks to rank 0" if world > 1 else ""),
                        "l2": "inputs (%.2f GB/step) exceed the 126 MB L2; no explicit flush" % (L * 2048 / 1e9),
-                       "decode_path": codec.decode_path},
+                       "encode_path": codec.encode_path, "decode_path": codec.decode_path},
             "parts": {"encode_ms": enc_ms, "decode_ms": dec_ms,
                       "encode_leaves_per_s": L / (enc_ms / 1e3), "decode_leaves_per_s": L / (dec_ms / 1e3)},
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % peaks["source"],
                          "hbm_gbs_nonbinding": (BYTES_DECODE if dom == "decode" else BYTES_ENCODE) * L / (dom_ms / 1e3) / 1e9,
-                         "note": "compute-bound path (34 kFLOP/B); %s kernel runs on %s" % (dom, "bf16 tensor cores" if dom_on_tensor else "fp32 FFMA (measured CUDA-core peak 71 TFLOP/s, so frac of ITS pipe is %.2f)" % (achieved / ffma_peak)),
+                         "note": "compute-bound path (34 kFLOP/B); achieved = ALGORITHMIC flops / time; %s kernel runs on %s" % (dom, "tensor cores (the encoder issues 3 fp16 products per algorithmic MAC, see kernels.*.issued_tflops)" if dom_on_tensor else "fp32 FFMA (measured CUDA-core peak 71 TFLOP/s, so frac of ITS pipe is %.2f)" % (achieved / ffma_peak)),
                          "kernels": kernels},
             "e2e": {"value": L * world * K / (e2e_ms / 1e3), "unit": "leaves/s",
                     "h2d_bytes_per_step": L * (2048 + 64), "d2h_bytes_per_step": L * (64 + 2048),

@@ -33,7 +33,7 @@ def test_version_string(lib):
 
 def test_config_struct_matches_header():
     from vqvdb_b200.codec import _Config
-    # uint32 + int32 + ptr + u64 + ptr + 2*u32 + 8*u32 on LP64
+    # uint32 + int32 + ptr + u64 + ptr + 3*u32 + 7*u32 on LP64
     assert C.sizeof(_Config) == 4 + 4 + 8 + 8 + 8 + 4 + 4 + 32
 
 

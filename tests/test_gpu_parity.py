@@ -276,3 +276,86 @@ def test_vec3_matches_c_oracle_and_chunking(codec_vec3):
         assert np.array_equal(_decode(small, idx), _decode(codec_vec3, idx))
     finally:
         small.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# Both encoders — the tensor-core one (tcgen05.mma on fp16 2-way split operands, fp32-level accuracy; the default)
+# and the CUDA-core fp32 FFMA one — against the reference goldens, the C oracle and each other.  Indices are integer
+# work: equal to the reference's except at reference near-ties (conftest.TIE_MARGIN), every mismatch checked.
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module", params=["fp16x2_tc", "fp32"])
+def codec_enc(request):
+    from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec
+    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, encode_precision=request.param), BackendType.B200)
+    assert c is not None
+    assert c.encode_path == {"fp16x2_tc": "fp16x2_tcgen05", "fp32": "fp32"}[request.param]
+    yield c
+    c.close()
+
+
+def test_default_encoder_is_the_tensor_core_one(codec):
+    assert codec.encode_path == "fp16x2_tcgen05"
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_both_encoders_match_reference_goldens(codec_enc, name):
+    g = golden(name)
+    idx = _encode(codec_enc, CASES[name]())
+    n_mm = assert_indices_match(idx, g["indices"], g["margins"])
+    print("%s / %s: %d of %d indices differ (reference near-ties)" % (codec_enc.encode_path, name, n_mm, idx.size))
+
+
+def test_both_encoders_ragged_sizes_and_determinism(codec_enc):
+    x = synth.smoke_leaves(1024, seed=0)
+    g = golden("smoke1024_seed0")
+    full = _encode(codec_enc, x)
+    assert_indices_match(full, g["indices"], g["margins"])
+    for n in (1, 2, 147, 148, 149, 297, 1000):                  # around the 148-SM grid: one leaf per CTA pass
+        assert np.array_equal(_encode(codec_enc, x[:n]), full[:n])
+    assert np.array_equal(_encode(codec_enc, x), full)
+
+
+def test_encoders_agree_on_mixed_inputs(c_oracle):
+    # smooth, sparse, noise, constant, large-magnitude and tiny-magnitude leaves through both encoders
+    from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec
+    x = np.concatenate([synth.smoke_leaves(1500, seed=31), synth.smoke_leaves(1500, seed=32, sparse=True),
+                        synth.noise_leaves(600, seed=33), np.full((8, 1, 8, 8, 8), 0.37, np.float32),
+                        1.0e4 * synth.smoke_leaves(200, seed=34), 1.0e-4 * synth.smoke_leaves(200, seed=35),
+                        synth.smoke_leaves(200, seed=36) - 0.5])
+    idx_o, margins = c_oracle.encode(x, with_margins=True)
+    got = {}
+    for prec in ("fp16x2_tc", "fp32"):
+        c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, encode_precision=prec), BackendType.B200)
+        try:
+            got[prec] = _encode(c, x)
+        finally:
+            c.close()
+        n_mm = assert_indices_match(got[prec], idx_o, margins)
+        print("%s vs C oracle: %d of %d differ" % (prec, n_mm, idx_o.size))
+    both = got["fp16x2_tc"] != got["fp32"]
+    assert (not both.any()) or float(margins[both].max()) <= 1e-4
+
+
+# stage -> (oracle tap, channels, positions, max abs error vs the fp32 oracle)
+ENC_TAPS = {0: (16, 512, 1e-5), 6: (16, 512, 1e-5), 1: (16, 512, 1e-5), 2: (32, 64, 3e-5), 7: (32, 64, 1e-5), 3: (32, 64, 3e-5),
+            4: (32, 64, 3e-5), 5: (128, 64, 2e-5)}
+
+
+@pytest.mark.parametrize("stage", sorted(ENC_TAPS))
+def test_tc_encoder_stage_taps_match_oracle(codec, c_oracle, stage):
+    # per-layer activations of the tensor-core encoder vs the C oracle: fp32-level agreement at every stage
+    import torch
+    ch, npos, tol = ENC_TAPS[stage]
+    x = np.concatenate([synth.smoke_leaves(150, seed=41), synth.smoke_leaves(150, seed=42, sparse=True)])
+    n = x.shape[0]
+    want = (c_oracle.latents(x) if stage == 5 else c_oracle.encode_tap(x, stage)).reshape(n, ch, npos)
+    xd = torch.from_numpy(x).cuda()
+    tap = torch.full((n, ch, npos), float("nan"), dtype=torch.float32, device="cuda")
+    idx = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
+    codec.debug_encode_tap(xd, n, stage, tap, idx, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = tap.cpu().numpy()
+    assert np.isfinite(got).all()
+    err = float(np.abs(got - want).max())
+    assert err <= tol, "stage %d: max err %.3e" % (stage, err)
+    assert np.array_equal(idx.cpu().numpy().reshape(n, 4, 4, 4), _encode(codec, x))   # the tap launch encodes too

@@ -22,15 +22,14 @@ for _ in range(2):
 torch.cuda.synchronize()
 p = prof.cpu().numpy()
 leaves = n / 148.0
-names = ["stage leaf + idle tail", "pre.0 FFMA + GN pre.1", "gn1 + split -> A8", "wait conv1 MMA", "conv1 epilogue (GN, split)",
+names = ["stage next leaf (+ clear Y)", "pre.0 FFMA + GN pre.1", "gn1 + split -> A8", "wait conv1 MMA", "conv1 epilogue (GN, split)",
          "wait conv2 MMA", "conv2 epilogue (residual, -> Y)", "wait down MMA", "down epilogue (GN, -> H32)", "wait res32.c1 MMA",
          "res32.c1 epilogue", "wait res32.c2 MMA", "res32.c2 epilogue + attention", "wait proj MMA", "proj epilogue (z, bf16)",
-         "wait VQ MMA"]
+         "wait VQ MMA", "VQ scores -> bounds, row minimum", "VQ shortlist + exact re-scoring", "VQ combine + store"]
 tot = 0.0
 for i, nm in enumerate(names):
     c = p[:, i].mean() / leaves
     tot += c
     print("%-36s %8.0f cyc/leaf" % (nm, c))
-print("(slot 0 also holds the VQ scan + re-scoring of the previous leaf)")
 print("%-36s %8.0f cyc/leaf" % ("row thread total", tot))
 print("issuer: wait a_ready %.0f  wait w_full %.0f  issue+commit %.0f  total %.0f cyc/leaf" % tuple(p[:, 32 + i].mean() / leaves for i in range(4)))

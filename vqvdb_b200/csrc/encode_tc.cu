@@ -514,9 +514,9 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 		rc.tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 		rc.red = reinterpret_cast<float*>(smem + kOffRed);
 		const int g = rc.g, row = (warp & 3) * 32 + lane;
-		long long prof[16];
+		long long prof[20];
 #pragma unroll
-		for (int i = 0; i < 16; ++i) prof[i] = 0;
+		for (int i = 0; i < 20; ++i) prof[i] = 0;
 		long long pc0 = prof_clock<kProf>();
 		auto lap = [&](int slot) {
 			if (kProf) {
@@ -895,6 +895,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				}
 				vq_umin[g * 128 + row] = umin;
 				row_bar();
+				lap(16);
 				umin = fminf(fminf(vq_umin[row], vq_umin[128 + row]), fminf(vq_umin[256 + row], vq_umin[384 + row]));
 				unsigned long long mask = 0ull;
 #pragma unroll
@@ -933,6 +934,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 						bi = code1;
 					}
 				}
+				lap(17);
 				vq_best[g * 128 + row] = best;
 				vq_bidx[g * 128 + row] = bi;
 				row_bar();
@@ -949,12 +951,12 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				}
 			}
 			tc_fence_before();  // this leaf's TMEM reads are ordered before the next leaf's first MMAs (via a_ready)
-			lap(0);
+			lap(18);
 		}
 		if (kProf && tap_out && tid == 0) {
 			float* o = tap_out + (size_t)blockIdx.x * 64;
 #pragma unroll
-			for (int i = 0; i < 16; ++i) o[i] = (float)prof[i];
+			for (int i = 0; i < 20; ++i) o[i] = (float)prof[i];
 		}
 	}
 
