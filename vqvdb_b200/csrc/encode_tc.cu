@@ -26,11 +26,11 @@
 //   * the tensor core truncates its fp32 accumulator after every MMA (measured: a bias toward zero that grows with
 //     the chain length); the 64-step chain of the stride-2 conv is split over four accumulators added in the epilogue.
 //   * pre.0 (Cin = 1, K = 27) stays on FFMA in fp32 (raw voxel values are unbounded; it is 1.4 % of the MACs).
-//   * VQ: bf16 tensor-core scores for all 256 codes with a rigorous error bound, then exact fp32 re-scoring of the
-//     shortlist with the reference's formula and tie-break — the same two-stage scheme as encode_fp32.cu, so the
-//     index equals a full fp32 scan's.
-//   * weights (484 KB per leaf as fp16 hi/lo planes, L2-resident) stream through a 3 x 16 KB shared-memory ring as
-//     37 units by 1-D TMA bulk copies; ring slots are released by tcgen05.commit.
+//   * VQ: split-fp16 tensor-core scores for all 256 codes with a rigorous error bound (~5e-4), then exact fp32
+//     re-scoring of the shortlist with the reference's formula and tie-break — the two-stage scheme of encode_fp32.cu
+//     with a 500x tighter first stage, so the shortlist is a single code except at near-ties (~1 % of the rows).
+//   * weights (548 KB per leaf as fp16 hi/lo planes, L2-resident) stream through a 3 x 16 KB shared-memory ring as
+//     41 units by 1-D TMA bulk copies; ring slots are released by tcgen05.commit.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -59,16 +59,16 @@ constexpr int kYRows = 160;                                     // space-to-dept
 constexpr uint32_t kYPlane = kYRows * 16, kYPrec = 16 * kYPlane, kYBytes = 2 * kYPrec;           // 81 920
 constexpr int kHMargin = 24, kHRows = 176;                      // 4^3, 32 channels: rows -24 .. 151 around q = d*20 + h*4 + w
 constexpr uint32_t kHPlane = kHRows * 16, kHPrec = 4 * kHPlane, kHBytes = 2 * kHPrec;            // 22 528
-constexpr int kZsPitch = 132;                                   // fp32 z rows (exact re-scoring), overlays Y
+constexpr int kZsPitch = 132;                                   // fp32 z rows (exact re-scoring), overlays the head of A8
 constexpr uint32_t kZsBytes = 64 * kZsPitch * 4;                // 33 792
-constexpr uint32_t kZbPlane = 128 * 16, kZbBytes = 16 * kZbPlane;   // bf16 z as the VQ A operand: 32 768
+constexpr uint32_t kZhPlane = 128 * 16, kZhPrec = 16 * kZhPlane, kZhBytes = 2 * kZhPrec;   // split-fp16 z, the VQ A operand: 65 536, overlays Y
 constexpr int kX32Pitch = 36;
 
 constexpr uint32_t kOffRing = 0;
 constexpr uint32_t kOffA8 = kOffRing + kStages * kStageBytes;   // 49 152
 constexpr uint32_t kOffY = kOffA8 + kA8Bytes;                   // 100 352
-constexpr uint32_t kOffZs = kOffY;
-constexpr uint32_t kOffZb = kOffY + 34816;                      // 1 KB-aligned, behind zs
+constexpr uint32_t kOffZs = kOffA8;                             // both overlays are cleared again at the start of every leaf
+constexpr uint32_t kOffZh = kOffY;
 constexpr uint32_t kOffH = kOffY + kYBytes;                     // 182 272
 constexpr uint32_t kOffIn = kOffH + kHBytes;                    // in_halo [10][10][10] fp32 (4096 reserved)
 constexpr uint32_t kOffPreW = kOffIn + 4096;                    // pre.0 weights [27][16] fp32
@@ -80,10 +80,10 @@ constexpr uint32_t kOffBar = kOffCb + 2048;                     // mbarriers
 constexpr uint32_t kNumBars = 2 * kStages + 2;
 constexpr uint32_t kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemSlot + 16;
-static_assert(kZsBytes <= 34816 && 34816 + kZbBytes <= kYBytes, "z overlays fit inside the Y region");
+static_assert(kZsBytes <= kA8Bytes && kZhBytes <= kYBytes, "z overlays fit inside the A8 / Y regions");
 static_assert(4 * 4 * 128 * 4 <= 64 * kX32Pitch * 4, "VQ exchange arrays fit in the dead x32 staging area");
 static_assert(kSmemBytes <= 227 * 1024, "encode_tc smem budget");
-static_assert(kOffBar % 8 == 0 && kOffA8 % 1024 == 0 && kOffY % 1024 == 0 && kOffH % 1024 == 0 && kOffZb % 1024 == 0, "alignment");
+static_assert(kOffBar % 8 == 0 && kOffA8 % 1024 == 0 && kOffY % 1024 == 0 && kOffH % 1024 == 0, "alignment");
 
 __device__ __forceinline__ uint32_t bar_w_full(uint32_t bars, uint32_t s) { return bars + s * 8; }
 __device__ __forceinline__ uint32_t bar_w_empty(uint32_t bars, uint32_t s) { return bars + (kStages + s) * 8; }
@@ -96,9 +96,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
 	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// instruction descriptor: D = f32, A/B = f16 (or bf16), both K-major, M = 128, N = n
+// instruction descriptor: D = f32, A/B = f16, both K-major, M = 128, N = n
 __host__ __device__ constexpr uint32_t idesc_f16(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
-__host__ __device__ constexpr uint32_t idesc_bf16(uint32_t n) { return idesc_f16(n) | (1u << 7) | (1u << 10); }
 // shared-memory descriptor, K-major, no swizzle: 8-row core matrices of 128 contiguous bytes; SBO = stride between
 // 8-row groups, LBO = stride between the two 8-element K chunks of one K = 16 step
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -112,7 +111,7 @@ __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint3
 	    "l"(a), "l"(b), "r"(id), "r"(acc)
 	    : "memory");
 }
-// TMEM -> registers, 32 lanes x 4 / 8 / 32 consecutive columns; issue only (tmem_wait_ld() before use)
+// TMEM -> registers, 32 lanes x 4 / 8 / 16 consecutive columns; issue only (tmem_wait_ld() before use)
 __device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, float (&v)[4]) {
 	uint32_t o[4];
 	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(taddr));
@@ -136,19 +135,6 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16])
 	    : "r"(taddr));
 #pragma unroll
 	for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(o[j]);
-}
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
-	uint32_t o[32];
-	asm volatile(
-	    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-	    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-	    : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]), "=r"(o[9]),
-	      "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15]), "=r"(o[16]), "=r"(o[17]), "=r"(o[18]), "=r"(o[19]),
-	      "=r"(o[20]), "=r"(o[21]), "=r"(o[22]), "=r"(o[23]), "=r"(o[24]), "=r"(o[25]), "=r"(o[26]), "=r"(o[27]), "=r"(o[28]), "=r"(o[29]),
-	      "=r"(o[30]), "=r"(o[31])
-	    : "r"(taddr));
-#pragma unroll
-	for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(o[j]);
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void row_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
@@ -317,7 +303,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 	extern __shared__ __align__(1024) uint8_t smem[];
 	const uint32_t s_base = smem_u32(smem);
 	const uint32_t ring = s_base + kOffRing, bars = s_base + kOffBar;
-	const uint32_t a8 = s_base + kOffA8, yb = s_base + kOffY, hb = s_base + kOffH, zb = s_base + kOffZb;
+	const uint32_t a8 = s_base + kOffA8, yb = s_base + kOffY, hb = s_base + kOffH, zh = s_base + kOffZh;
 	float* in_halo = reinterpret_cast<float*>(smem + kOffIn);
 	float* s_prew = reinterpret_cast<float*>(smem + kOffPreW);
 	float* x32s = reinterpret_cast<float*>(smem + kOffX32);
@@ -377,7 +363,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			const uint64_t a8_d = make_desc(a8 + kA8Margin * 16, kA8Plane, 128);
 			const uint64_t y_d = make_desc(yb, kYPlane, 128);
 			const uint64_t h_d = make_desc(hb + kHMargin * 16, kHPlane, 128);
-			const uint64_t z_d = make_desc(zb, kZbPlane, 128);
+			const uint64_t z_d = make_desc(zh, kZhPlane, 128);
 			auto wait_a = [&]() {
 				const long long c0 = prof_clock<kProf>();
 				mbar_wait(bar_a_ready(bars), a_count & 1u);
@@ -482,18 +468,17 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					if (kProf) t_issue += prof_clock<kProf>() - c0;
 				}
 				tc_commit(bar_d_full(bars));
-				// ---- VQ scores: 8 k-steps x N = 256 (bf16) ----
+				// ---- VQ scores: 8 k-steps x {z_hi.e_hi -> cols 0..255 ; z_hi.e_lo + z_lo.e_hi -> cols 256..511}, N = 256 ----
 				wait_a();
 #pragma unroll 1
-				for (int q = 0; q < 4; ++q) {
+				for (int ks = 0; ks < 8; ++ks) {
 					const uint32_t wb = wait_w();
 					const long long c0 = prof_clock<kProf>();
-#pragma unroll
-					for (int kl = 0; kl < 2; ++kl) {
-						const uint64_t ad = z_d + (uint64_t)((q * 2 + kl) * 2 * (int)(kZbPlane >> 4));
-						const uint64_t bd = make_desc(wb + kl * 8192, 256 * 16, 128);
-						mma_ss(tmem, ad, bd, idesc_bf16(256), (q > 0 || kl > 0) ? 1u : 0u);
-					}
+					const uint64_t ad = z_d + (uint64_t)(ks * 2 * (int)(kZhPlane >> 4));
+					const uint64_t bh = make_desc(wb, 256 * 16, 128), bl = make_desc(wb + 8192, 256 * 16, 128);
+					mma_ss(tmem, ad, bh, idesc_f16(256), ks > 0 ? 1u : 0u);
+					mma_ss(tmem + 256, ad, bl, idesc_f16(256), ks > 0 ? 1u : 0u);
+					mma_ss(tmem + 256, ad + (kZhPrec >> 4), bh, idesc_f16(256), 1u);
 					release_w();
 					if (kProf) t_issue += prof_clock<kProf>() - c0;
 				}
@@ -542,10 +527,11 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 #pragma unroll 1
 		for (int64_t it = 0; it < my_leaves; ++it) {
 			const int64_t leaf = blockIdx.x + it * gridDim.x;
-			// ---- stage the leaf (2048 B, 128-bit coalesced) into the haloed fp32 buffer; clear Y (z overlays dirtied it) ----
+			// ---- stage the leaf (2048 B, 128-bit coalesced) into the haloed fp32 buffer; clear what the z overlays dirtied ----
 			if (it > 0) {
 				row_bar();  // every row thread is done with the previous leaf's z rows
 				for (uint32_t i = tid; i < kYBytes / 16; i += kRowThreads) reinterpret_cast<uint4*>(smem + kOffY)[i] = make_uint4(0, 0, 0, 0);
+				for (uint32_t i = tid; i < kZsBytes / 16; i += kRowThreads) reinterpret_cast<uint4*>(smem + kOffZs)[i] = make_uint4(0, 0, 0, 0);
 			}
 			if (tid < 128) {
 				const float4 v = __ldcs(reinterpret_cast<const float4*>(leaves + leaf * 512) + tid);
@@ -830,8 +816,8 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			signal_a_ready(bars, lane);
 			lap(12);
 
-			// ---- proj epilogue: z (channels 32g .. 32g+31) = acc + b -> fp32 rows (exact re-scoring) and the bf16 A operand
-			//      of the VQ GEMM; |z|^2 as four per-group partial sums, each sequential in d ----
+			// ---- proj epilogue: z (channels 32g .. 32g+31) = acc + b -> fp32 rows (exact re-scoring) and the split-fp16 A
+			//      operand of the VQ GEMM; |z|^2 as four per-group partial sums, each sequential in d ----
 			wait_accumulator(rc);
 			lap(13);
 			{
@@ -858,12 +844,10 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					}
 #pragma unroll
 					for (int j = 0; j < 2; ++j) {
-						uint4 pk;
-						pk.x = pack_bf16(hh[8 * j], hh[8 * j + 1]);
-						pk.y = pack_bf16(hh[8 * j + 2], hh[8 * j + 3]);
-						pk.z = pack_bf16(hh[8 * j + 4], hh[8 * j + 5]);
-						pk.w = pack_bf16(hh[8 * j + 6], hh[8 * j + 7]);
-						st_shared_v4(zb + (uint32_t)(g * 4 + half * 2 + j) * kZbPlane + (uint32_t)row * 16, pk);
+						float z8[8];
+#pragma unroll
+						for (int c = 0; c < 8; ++c) z8[c] = hh[8 * j + c];
+						store_split8(zh + (uint32_t)(g * 4 + half * 2 + j) * kZhPlane + (uint32_t)row * 16, kZhPrec, z8);
 					}
 				}
 				vq_zz[g * 128 + row] = zzp;
@@ -872,26 +856,34 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			lap(14);
 
 			// ---- VQ: argmin_k (|z|^2 + |e_k|^2) - 2 z.e_k (save_for_inference.py:55-61), first minimum wins ----
-			//  1. a_k = |e_k|^2 - 2 bf16(z).bf16(e_k) from the tensor cores, with the rigorous bound
-			//     |a_k - (true score - |z|^2)| <= B_k = 2^-7 * 1.07 * |z| * |e_k| + 1e-4  (bf16 unit roundoff 2^-9 per operand);
-			//  2. every code whose lower bound a_k - B_k does not exceed min_j (a_j + B_j) is re-scored with the
-			//     reference's fp32 formula, sequential in d: the fp32 arg-min and all its ties are in that shortlist.
+			//  1. a_k = |e_k|^2 - 2 (z_hi.e_hi + (z_hi.e_lo + z_lo.e_hi) / 2048) from the tensor cores.  Each operand keeps 22
+			//     significant bits, so |a_k - (exact score - |z|^2)| <= 2 * (3 * 2^-22 [split + dropped lo.lo term] + 8 * 2^-22
+			//     [accumulator truncation, 8 steps]) * sum|z_d e_kd| <= 5.3e-6 |z| |e_k|; used bound B_k = 8e-6 |z| |e_k| + 1e-4,
+			//     the 1e-4 covering the fp32 evaluation noise of the reference formula itself.
+			//  2. every code whose lower bound a_k - B_k does not exceed min_j (a_j + B_j) is re-scored with the reference's
+			//     fp32 formula, sequential in d; the fp32 arg-min and all its ties are in that shortlist.  It has a second
+			//     entry for about 1 % of the rows (near-ties); a single entry needs no re-scoring at all.
 			//  The four threads of a row take 64 codes each; tcgen05.ld is warp-collective, so every lane runs the loads.
 			wait_accumulator(rc);
 			row_bar();  // z rows and |z|^2 partials of all four groups are in place
 			lap(15);
 			{
 				const float zz = (vq_zz[row] + vq_zz[128 + row]) + (vq_zz[256 + row] + vq_zz[384 + row]);
-				const float cb = 0.0078125f * 1.07f * sqrtf(zz);
+				const float cb = 8e-6f * sqrtf(zz);
 				float sc[64];
-				tmem_ld32_nowait(rc.tlane + g * 64, *reinterpret_cast<float(*)[32]>(&sc[0]));
-				tmem_ld32_nowait(rc.tlane + g * 64 + 32, *reinterpret_cast<float(*)[32]>(&sc[32]));
-				tmem_wait_ld();
 				float umin = INFINITY;
 #pragma unroll
-				for (int j = 0; j < 64; ++j) {
-					sc[j] = s_esq[g * 64 + j] - 2.f * sc[j];
-					umin = fminf(umin, sc[j] + (cb * s_eno[g * 64 + j] + 1e-4f));
+				for (int ch = 0; ch < 4; ++ch) {
+					float hh[16], mx[16];
+					tmem_ld16_nowait(rc.tlane + g * 64 + ch * 16, hh);
+					tmem_ld16_nowait(rc.tlane + 256 + g * 64 + ch * 16, mx);
+					tmem_wait_ld();
+#pragma unroll
+					for (int j = 0; j < 16; ++j) {
+						const int k = g * 64 + ch * 16 + j;
+						sc[ch * 16 + j] = s_esq[k] - 2.f * fmaf(mx[j], kLoInv, hh[j]);
+						umin = fminf(umin, sc[ch * 16 + j] + (cb * s_eno[k] + 1e-4f));
+					}
 				}
 				vq_umin[g * 128 + row] = umin;
 				row_bar();
@@ -904,6 +896,15 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				if (!valid4) mask = 0ull;
 				float best = INFINITY;
 				int bi = 0x7fffffff;
+				int* vq_cnt = reinterpret_cast<int*>(vq_zz);  // |z|^2 partials were consumed before the previous barrier
+				vq_cnt[g * 128 + row] = __popcll(mask);       // shortlist sizes of the row's four threads
+				row_bar();
+				const int n_cand = (vq_cnt[row] + vq_cnt[128 + row]) + (vq_cnt[256 + row] + vq_cnt[384 + row]);
+				if (n_cand == 1 && mask) {  // the only code that can be the fp32 arg-min: nothing to re-score
+					bi = g * 64 + __ffsll((long long)mask) - 1;
+					best = -INFINITY;
+					mask = 0ull;
+				}
 				const float* zrow = zs + (valid4 ? p4 : 0) * kZsPitch;
 				while (mask) {  // two candidates per trip: two independent FMA chains
 					const int b0 = __ffsll((long long)mask) - 1;

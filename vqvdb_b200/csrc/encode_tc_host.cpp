@@ -52,14 +52,6 @@ float f16_to_f32(uint16_t h) {
 	return f;
 }
 
-uint16_t f32_to_bf16_rn(float f) {
-	uint32_t u;
-	std::memcpy(&u, &f, 4);
-	if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
-	u += 0x7fffu + ((u >> 16) & 1u);
-	return (uint16_t)(u >> 16);
-}
-
 // part 0: fp16(w); part 1: fp16((w - fp16(w)) * 2048)
 uint16_t split_part(float w, int part) {
 	const uint16_t hi = f32_to_f16_rn(w);
@@ -140,14 +132,14 @@ std::vector<uint8_t> build_encoder_tc_units(const WeightPack& p, EncoderTcStream
 				for (int co = 0; co < 128; ++co)
 					for (int k = 0; k < 16; ++k) put(u + ks * 8192, 256, part * 128 + co, k, split_part(w[co * 32 + ks * 16 + k], part));
 	}
-	// codebook [256][128] as bf16, 8 k-steps of 16 dims
+	// codebook [256][128], split like the conv weights: per 16-dim k-step one e_hi block and one e_lo block
 	{
 		const float* e = p.get("quantizer.embedding").data;
-		for (int q = 0; q < 4; ++q) {
+		for (int ks = 0; ks < 8; ++ks) {
 			uint8_t* u = begin_unit(2 * 8192);
-			for (int kl = 0; kl < 2; ++kl)
+			for (int part = 0; part < 2; ++part)
 				for (int code = 0; code < 256; ++code)
-					for (int k = 0; k < 16; ++k) put(u + kl * 8192, 256, code, k, f32_to_bf16_rn(e[code * 128 + (q * 2 + kl) * 16 + k]));
+					for (int k = 0; k < 16; ++k) put(u + part * 8192, 256, code, k, split_part(e[code * 128 + ks * 16 + k], part));
 		}
 	}
 	if (nu != kEncTcUnits) throw std::logic_error("encoder tc unit count mismatch");

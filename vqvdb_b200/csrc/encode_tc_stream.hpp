@@ -17,9 +17,9 @@ namespace vqvdb {
 //                         n = part*32 + cout
 //   res32 conv1 / conv2 : 9 units each (one per (kd, kh)) = 2 k-steps x [2][192][16 B], n = part*96 + kw*32 + cout
 //   proj                : 1 unit = 2 k-steps x [2][256][16 B], n = part*128 + cout
-//   codebook (bf16)     : 4 units = 2 k-steps each x [2][256][16 B], n = code
+//   codebook            : 8 units (one per 16-dim k-step) = [2][256][16 B] e_hi then [2][256][16 B] e_lo, n = code
 // (part 0 = w_hi, part 1 = w_lo).
-constexpr int kEncTcUnits = 37;
+constexpr int kEncTcUnits = 41;
 constexpr uint32_t kEncTcStageBytes = 16384;
 
 struct EncoderTcStream {
