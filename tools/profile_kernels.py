@@ -18,9 +18,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--leaves", type=int, default=59200)   # 148 SMs x 400
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--decode-precision", default="default")
+ap.add_argument("--encode-precision", default="default")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
-codec = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, decode_precision=a.decode_precision), BackendType.B200)
+codec = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, decode_precision=a.decode_precision, encode_precision=a.encode_precision), BackendType.B200)
 assert codec is not None
 x = gen_leaves_gpu(a.leaves, dev, seed=0)
 idx = torch.empty((a.leaves, 4, 4, 4), dtype=torch.uint8, device=dev)

@@ -51,6 +51,13 @@ constexpr int kStages = 3;
 constexpr uint32_t kStageBytes = kEncTcStageBytes;
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 constexpr int kDownChains = 4;                    // independent accumulators of `down` (see the issuer)
+// offsets (floats) of the per-channel parameter vectors staged in shared memory: a global (L2) load at the head of
+// every epilogue costs ~300 cycles of exposed latency, there being almost no L1 left beside 222 KB of shared memory
+namespace par {
+constexpr int pre_b = 0, pre_gn_w = 16, pre_gn_b = 32, r16_gn1_w = 48, r16_gn1_b = 64, r16_c1_b = 80, r16_gn2_w = 96, r16_gn2_b = 112,
+              r16_c2_b = 128, down_b = 144, r32_gn1_w = 176, r32_gn1_b = 208, r32_c1_b = 240, r32_gn2_w = 272, r32_gn2_b = 304,
+              r32_c2_b = 336, proj_b = 368, fc0 = 496, fc2 = 752;  // 1008 floats in all
+}
 
 // ---- shared-memory activation buffers (all UMMA A operands: [precision][8-channel plane][row][16 B]) ----
 constexpr int kA8Margin = 80, kA8Rows = 800;                    // 8^3, 16 channels: rows -80 .. 719 around q = d*72 + h*8 + w
@@ -76,7 +83,9 @@ constexpr uint32_t kOffX32 = kOffPreW + 1728;                   // residual of t
 constexpr uint32_t kOffRed = kOffX32 + 64 * kX32Pitch * 4;      // GroupNorm partials [2 slots][16 warps][2]
 constexpr uint32_t kOffAtt = kOffRed + 256;                     // attention: part [16 warps][8], hid [8], scale [32]
 constexpr uint32_t kOffCb = kOffAtt + (128 + 8 + 32) * 4;       // emb_sq [256], emb_norm [256]
-constexpr uint32_t kOffBar = kOffCb + 2048;                     // mbarriers
+constexpr uint32_t kOffPar = kOffCb + 2048;                     // per-channel parameter vectors (ParOff), 1008 floats
+constexpr uint32_t kOffXq = kOffPar + 1008 * 4;                 // `down` epilogue: lane-0 values handed to the previous quadrant [4][4][8]
+constexpr uint32_t kOffBar = kOffXq + 512;                      // mbarriers
 constexpr uint32_t kNumBars = 2 * kStages + 2;
 constexpr uint32_t kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemSlot + 16;
@@ -310,6 +319,9 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 	float* att = reinterpret_cast<float*>(smem + kOffAtt);
 	float* s_esq = reinterpret_cast<float*>(smem + kOffCb);
 	float* s_eno = s_esq + 256;
+	const float* __restrict__ sp_c = reinterpret_cast<const float*>(smem + kOffPar);
+	float* sp = reinterpret_cast<float*>(smem + kOffPar);
+	float* xq = reinterpret_cast<float*>(smem + kOffXq);
 	float* zs = reinterpret_cast<float*>(smem + kOffZs);
 	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmemSlot);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -321,6 +333,29 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 	for (int i = tid; i < 256; i += kThreads) {
 		s_esq[i] = __ldg(w.emb_sq + i);
 		s_eno[i] = __ldg(w.emb_norm + i);
+		sp[par::fc0 + i] = __ldg(w.fc0 + i);
+		sp[par::fc2 + i] = __ldg(w.fc2 + i);
+	}
+	if (tid < 128) sp[par::proj_b + tid] = __ldg(w.proj_b + tid);
+	if (tid < 32) {
+		sp[par::down_b + tid] = __ldg(w.down_b + tid);
+		sp[par::r32_gn1_w + tid] = __ldg(w.res32.gn1_w + tid);
+		sp[par::r32_gn1_b + tid] = __ldg(w.res32.gn1_b + tid);
+		sp[par::r32_c1_b + tid] = __ldg(w.res32.c1_b + tid);
+		sp[par::r32_gn2_w + tid] = __ldg(w.res32.gn2_w + tid);
+		sp[par::r32_gn2_b + tid] = __ldg(w.res32.gn2_b + tid);
+		sp[par::r32_c2_b + tid] = __ldg(w.res32.c2_b + tid);
+	}
+	if (tid < 16) {
+		sp[par::pre_b + tid] = __ldg(w.pre_b + tid);
+		sp[par::pre_gn_w + tid] = __ldg(w.pre_gn_w + tid);
+		sp[par::pre_gn_b + tid] = __ldg(w.pre_gn_b + tid);
+		sp[par::r16_gn1_w + tid] = __ldg(w.res16.gn1_w + tid);
+		sp[par::r16_gn1_b + tid] = __ldg(w.res16.gn1_b + tid);
+		sp[par::r16_c1_b + tid] = __ldg(w.res16.c1_b + tid);
+		sp[par::r16_gn2_w + tid] = __ldg(w.res16.gn2_w + tid);
+		sp[par::r16_gn2_b + tid] = __ldg(w.res16.gn2_b + tid);
+		sp[par::r16_c2_b + tid] = __ldg(w.res16.c2_b + tid);
 	}
 	if (tid == 0) {
 		for (uint32_t s = 0; s < kStages; ++s) {
@@ -409,23 +444,25 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					}
 					tc_commit(bar_d_full(bars));
 				}
-				// ---- down: 8 taps x 8 parity classes x {N = 64, N = 32}.  The tensor core truncates its fp32 accumulator
-				//      after every MMA, a bias that grows with the length of the accumulation chain; the 64 k-steps are
-				//      therefore split over kDownChains independent accumulators that the epilogue adds in fp32. ----
+				// ---- down: 4 (td, th) tap pairs x 8 parity classes x {N = 128, N = 64}; the two tw taps of a pair are
+				//      concatenated along N like the kw taps of the 3x3x3 convs (their row shift of 1 is applied in the
+				//      epilogue).  The tensor core truncates its fp32 accumulator after every MMA, a bias that grows with
+				//      the length of the accumulation chain; every tap pair therefore has its own accumulator
+				//      (kDownChains chains of 8 steps) and the epilogue adds them in fp32. ----
 				wait_a();
 #pragma unroll 1
-				for (int tap = 0; tap < 8; ++tap) {
+				for (int u = 0; u < 8; ++u) {  // u = (td, th) tap pair * 2 + half of the parity classes
 					const uint32_t wb = wait_w();
 					const long long c0 = prof_clock<kProf>();
-					const int s = (tap >> 2) * 25 + ((tap >> 1) & 1) * 5 + (tap & 1);
-					const uint32_t dcol = tmem + (uint32_t)(tap / (8 / kDownChains)) * 64;
-					const bool first = tap % (8 / kDownChains) == 0;
+					const int pair = u >> 1, half = u & 1;
+					const int s = (pair >> 1) * 25 + (pair & 1) * 5;
+					const uint32_t dcol = tmem + (uint32_t)pair * 128;
 #pragma unroll
-					for (int pc = 0; pc < 8; ++pc) {
-						const uint64_t ad = y_d + (uint64_t)(s + pc * 2 * (int)(kYPlane >> 4));
-						const uint64_t bd = make_desc(wb + pc * 2048, 64 * 16, 128);
-						mma_ss(dcol, ad, bd, idesc_f16(64), (!first || pc > 0) ? 1u : 0u);
-						mma_ss(dcol + 32, ad + (kYPrec >> 4), bd, idesc_f16(32), 1u);
+					for (int pcl = 0; pcl < 4; ++pcl) {
+						const uint64_t ad = y_d + (uint64_t)(s + (half * 4 + pcl) * 2 * (int)(kYPlane >> 4));
+						const uint64_t bd = make_desc(wb + pcl * 4096, 128 * 16, 128);
+						mma_ss(dcol, ad, bd, idesc_f16(128), (half > 0 || pcl > 0) ? 1u : 0u);
+						mma_ss(dcol + 64, ad + (kYPrec >> 4), bd, idesc_f16(64), 1u);
 					}
 					release_w();
 					if (kProf) t_issue += prof_clock<kProf>() - c0;
@@ -576,7 +613,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				}
 #pragma unroll
 				for (int c = 0; c < 4; ++c) {
-					const float b = __ldg(w.pre_b + g * 4 + c);
+					const float b = sp_c[par::pre_b + g * 4 + c];
 #pragma unroll
 					for (int t = 0; t < 5; ++t) xr[t][c] += b;
 				}
@@ -584,7 +621,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				gn_stats_regs<5, 4, 4>(xr, valid8, 1.f / 2048.f, rc, mean, rstd);
 #pragma unroll
 				for (int c = 0; c < 4; ++c) {
-					const float ga = __ldg(w.pre_gn_w + g * 4 + c), be = __ldg(w.pre_gn_b + g * 4 + c);
+					const float ga = sp_c[par::pre_gn_w + g * 4 + c], be = sp_c[par::pre_gn_b + g * 4 + c];
 #pragma unroll
 					for (int t = 0; t < 5; ++t) xr[t][c] = fmaxf((xr[t][c] - mean[0]) * rstd[0] * ga + be, 0.f);
 				}
@@ -598,8 +635,8 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				float ga[4], be[4];
 #pragma unroll
 				for (int c = 0; c < 4; ++c) {
-					ga[c] = __ldg(w.res16.gn1_w + g * 4 + c);
-					be[c] = __ldg(w.res16.gn1_b + g * 4 + c);
+					ga[c] = sp_c[par::r16_gn1_w + g * 4 + c];
+					be[c] = sp_c[par::r16_gn1_b + g * 4 + c];
 				}
 #pragma unroll
 				for (int t = 0; t < 5; ++t) {
@@ -627,7 +664,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				float v[5][4];
 				float bs[4];
 #pragma unroll
-				for (int c = 0; c < 4; ++c) bs[c] = __ldg(w.res16.c1_b + g * 4 + c);
+				for (int c = 0; c < 4; ++c) bs[c] = sp_c[par::r16_c1_b + g * 4 + c];
 #pragma unroll
 				for (int t = 0; t < 5; ++t) {
 					conv16_tile_out(rc.tlane + t * 96, g, lane & 7, v[t]);
@@ -645,8 +682,8 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				float ga[4], be[4];
 #pragma unroll
 				for (int c = 0; c < 4; ++c) {
-					ga[c] = __ldg(w.res16.gn2_w + g * 4 + c);
-					be[c] = __ldg(w.res16.gn2_b + g * 4 + c);
+					ga[c] = sp_c[par::r16_gn2_w + g * 4 + c];
+					be[c] = sp_c[par::r16_gn2_b + g * 4 + c];
 				}
 #pragma unroll
 				for (int t = 0; t < 5; ++t) {
@@ -666,7 +703,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			{
 				float bs[4];
 #pragma unroll
-				for (int c = 0; c < 4; ++c) bs[c] = __ldg(w.res16.c2_b + g * 4 + c);
+				for (int c = 0; c < 4; ++c) bs[c] = sp_c[par::r16_c2_b + g * 4 + c];
 #pragma unroll
 				for (int t = 0; t < 5; ++t) {
 					float o[4];
@@ -695,24 +732,41 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			{
 				float v[1][8];
 				{
-					float hh[8], hl[8];
+					// chain c holds [hh tw0 | hh tw1 | hl tw0 | hl tw1] (32 columns each) in columns c*128 ..
+					float h0[8], h1[8], l0[8], l1[8];
 #pragma unroll
-					for (int pr = 0; pr < kDownChains / 2; ++pr) {
+					for (int c = 0; c < kDownChains; ++c) {
 						float a0[8], a1[8], b0[8], b1[8];
-						tmem_ld8_nowait(rc.tlane + (2 * pr) * 64 + g * 8, a0);
-						tmem_ld8_nowait(rc.tlane + (2 * pr) * 64 + 32 + g * 8, b0);
-						tmem_ld8_nowait(rc.tlane + (2 * pr + 1) * 64 + g * 8, a1);
-						tmem_ld8_nowait(rc.tlane + (2 * pr + 1) * 64 + 32 + g * 8, b1);
+						tmem_ld8_nowait(rc.tlane + c * 128 + g * 8, a0);
+						tmem_ld8_nowait(rc.tlane + c * 128 + 32 + g * 8, a1);
+						tmem_ld8_nowait(rc.tlane + c * 128 + 64 + g * 8, b0);
+						tmem_ld8_nowait(rc.tlane + c * 128 + 96 + g * 8, b1);
 						tmem_wait_ld();
 #pragma unroll
-						for (int c = 0; c < 8; ++c) {
-							const float sa = a0[c] + a1[c], sb = b0[c] + b1[c];
-							hh[c] = pr == 0 ? sa : hh[c] + sa;
-							hl[c] = pr == 0 ? sb : hl[c] + sb;
+						for (int i = 0; i < 8; ++i) {
+							h0[i] = c == 0 ? a0[i] : h0[i] + a0[i];
+							h1[i] = c == 0 ? a1[i] : h1[i] + a1[i];
+							l0[i] = c == 0 ? b0[i] : l0[i] + b0[i];
+							l1[i] = c == 0 ? b1[i] : l1[i] + b1[i];
 						}
 					}
+					// out[q'] = P_tw0[q'] + P_tw1[q' + 1]: lane + 1, or lane 0 of the next quadrant through shared memory
 #pragma unroll
-					for (int c = 0; c < 8; ++c) v[0][c] = fmaf(hl[c], kLoInv, hh[c]) + __ldg(w.down_b + g * 8 + c);
+					for (int i = 0; i < 8; ++i) {
+						h0[i] = fmaf(l0[i], kLoInv, h0[i]);
+						h1[i] = fmaf(l1[i], kLoInv, h1[i]);
+					}
+					if (lane == 0) {
+#pragma unroll
+						for (int i = 0; i < 8; ++i) xq[((warp & 3) * 4 + g) * 8 + i] = h1[i];
+					}
+					row_bar();
+#pragma unroll
+					for (int i = 0; i < 8; ++i) {
+						float nx = __shfl_down_sync(0xffffffffu, h1[i], 1);
+						if (lane == 31) nx = xq[((((warp & 3) + 1) & 3) * 4 + g) * 8 + i];  // row 127 never matters
+						v[0][i] = (h0[i] + nx) + sp_c[par::down_b + g * 8 + i];
+					}
 				}
 				if (validd) {
 					*reinterpret_cast<float4*>(x32s + pd * kX32Pitch + g * 8) = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
@@ -727,7 +781,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				if (validd) {
 #pragma unroll
 					for (int c = 0; c < 8; ++c)
-						v[0][c] = fmaxf((v[0][c] - mean[c >> 2]) * rstd[c >> 2] * __ldg(w.res32.gn1_w + g * 8 + c) + __ldg(w.res32.gn1_b + g * 8 + c), 0.f);
+						v[0][c] = fmaxf((v[0][c] - mean[c >> 2]) * rstd[c >> 2] * sp_c[par::r32_gn1_w + g * 8 + c] + sp_c[par::r32_gn1_b + g * 8 + c], 0.f);
 					store_split8(hb + (uint32_t)g * kHPlane + (uint32_t)(kHMargin + jd * 20 + jh * 4 + jw) * 16, kHPrec, v[0]);
 				}
 			}
@@ -742,7 +796,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				float v[1][8];
 				conv32_tile_out(rc.tlane, g, w4, v[0]);
 #pragma unroll
-				for (int c = 0; c < 8; ++c) v[0][c] += __ldg(w.res32.c1_b + g * 8 + c);
+				for (int c = 0; c < 8; ++c) v[0][c] += sp_c[par::r32_c1_b + g * 8 + c];
 				if (valid4 && tap_stage == 7) {
 #pragma unroll
 					for (int c = 0; c < 8; ++c) tap_out[(leaf * 32 + g * 8 + c) * 64 + p4] = v[0][c];
@@ -752,7 +806,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				if (valid4) {
 #pragma unroll
 					for (int c = 0; c < 8; ++c)
-						v[0][c] = fmaxf((v[0][c] - mean[c >> 2]) * rstd[c >> 2] * __ldg(w.res32.gn2_w + g * 8 + c) + __ldg(w.res32.gn2_b + g * 8 + c), 0.f);
+						v[0][c] = fmaxf((v[0][c] - mean[c >> 2]) * rstd[c >> 2] * sp_c[par::r32_gn2_w + g * 8 + c] + sp_c[par::r32_gn2_b + g * 8 + c], 0.f);
 					store_split8(h_mine, kHPrec, v[0]);
 				}
 			}
@@ -770,7 +824,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					const float4 x1 = *reinterpret_cast<const float4*>(x32s + p4 * kX32Pitch + g * 8 + 4);
 					const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-					for (int c = 0; c < 8; ++c) v[c] = xv[c] + kResScale * (v[c] + __ldg(w.res32.c2_b + g * 8 + c));
+					for (int c = 0; c < 8; ++c) v[c] = xv[c] + kResScale * (v[c] + sp_c[par::r32_c2_b + g * 8 + c]);
 					if (tap_stage == 3) {
 #pragma unroll
 						for (int c = 0; c < 8; ++c) tap_out[(leaf * 32 + g * 8 + c) * 64 + p4] = v[c];
@@ -791,7 +845,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					for (int c = 0; c < 32; ++c) {
 						const float* pp = part + (c >> 3) * 32 + (c & 7);  // channel c = 8 g' + i lives in warps 4g' .. 4g'+3
 						const float m = ((pp[0] + pp[8]) + (pp[16] + pp[24])) * (1.f / 64.f);
-						s = fmaf(__ldg(w.fc0 + tid * 32 + c), m, s);
+						s = fmaf(sp_c[par::fc0 + tid * 32 + c], m, s);
 					}
 					hid[tid] = fmaxf(s, 0.f);
 				}
@@ -799,7 +853,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				if (tid < 32) {
 					float s = 0.f;
 #pragma unroll
-					for (int j = 0; j < 8; ++j) s = fmaf(__ldg(w.fc2 + tid * 8 + j), hid[j], s);
+					for (int j = 0; j < 8; ++j) s = fmaf(sp_c[par::fc2 + tid * 8 + j], hid[j], s);
 					scale[tid] = sigmoid_f(s);
 				}
 				row_bar();
@@ -830,7 +884,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					tmem_wait_ld();
 #pragma unroll
 					for (int c = 0; c < 16; ++c) {
-						hh[c] = fmaf(hl[c], kLoInv, hh[c]) + __ldg(w.proj_b + g * 32 + half * 16 + c);
+						hh[c] = fmaf(hl[c], kLoInv, hh[c]) + sp_c[par::proj_b + g * 32 + half * 16 + c];
 						zzp = fmaf(hh[c], hh[c], zzp);
 					}
 					if (valid4) {

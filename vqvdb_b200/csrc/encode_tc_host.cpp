@@ -93,19 +93,25 @@ std::vector<uint8_t> build_encoder_tc_units(const WeightPack& p, EncoderTcStream
 								    split_part(w[((co * 16 + ci) * 27) + (kd * 3 + kh) * 3 + kw], part));
 		}
 	}
-	// down: weight [32][16][4][4][4]; k = 2t + r per axis (t = tap of the 2x2x2 form, r = parity class of the input)
+	// down: weight [32][16][4][4][4]; k = 2t + r per axis (t = tap of the 2x2x2 form, r = parity class of the input).
+	// The two tw taps of a (td, th) pair are concatenated along N; one unit = 4 of the 8 parity classes of a pair.
 	{
 		const float* w = p.get("encoder.down.weight").data;
-		for (int tap = 0; tap < 8; ++tap) {
-			uint8_t* u = begin_unit(8 * 2048);
-			const int td = tap >> 2, th = (tap >> 1) & 1, tw = tap & 1;
-			for (int pc = 0; pc < 8; ++pc) {
-				const int rd = pc >> 2, rh = (pc >> 1) & 1, rw = pc & 1;
-				const int kd = 2 * td + rd, kh = 2 * th + rh, kw = 2 * tw + rw;
-				for (int part = 0; part < 2; ++part)
-					for (int co = 0; co < 32; ++co)
-						for (int ci = 0; ci < 16; ++ci)
-							put(u + pc * 2048, 64, part * 32 + co, ci, split_part(w[((co * 16 + ci) * 64) + (kd * 4 + kh) * 4 + kw], part));
+		for (int pair = 0; pair < 4; ++pair) {
+			const int td = pair >> 1, th = pair & 1;
+			for (int half = 0; half < 2; ++half) {
+				uint8_t* u = begin_unit(4 * 4096);
+				for (int pcl = 0; pcl < 4; ++pcl) {
+					const int pc = half * 4 + pcl, rd = pc >> 2, rh = (pc >> 1) & 1, rw = pc & 1;
+					for (int part = 0; part < 2; ++part)
+						for (int tw = 0; tw < 2; ++tw) {
+							const int kd = 2 * td + rd, kh = 2 * th + rh, kw = 2 * tw + rw;
+							for (int co = 0; co < 32; ++co)
+								for (int ci = 0; ci < 16; ++ci)
+									put(u + pcl * 4096, 128, part * 64 + tw * 32 + co, ci,
+									    split_part(w[((co * 16 + ci) * 64) + (kd * 4 + kh) * 4 + kw], part));
+						}
+				}
 			}
 		}
 	}
