@@ -66,16 +66,18 @@ constexpr int kYRows = 160;                                     // space-to-dept
 constexpr uint32_t kYPlane = kYRows * 16, kYPrec = 16 * kYPlane, kYBytes = 2 * kYPrec;           // 81 920
 constexpr int kHMargin = 24, kHRows = 176;                      // 4^3, 32 channels: rows -24 .. 151 around q = d*20 + h*4 + w
 constexpr uint32_t kHPlane = kHRows * 16, kHPrec = 4 * kHPlane, kHBytes = 2 * kHPrec;            // 22 528
-constexpr int kZsPitch = 132;                                   // fp32 z rows (exact re-scoring), overlays the head of A8
+constexpr int kZsPitch = 132;                                   // fp32 z rows (exact re-scoring), overlay Y
 constexpr uint32_t kZsBytes = 64 * kZsPitch * 4;                // 33 792
-constexpr uint32_t kZhPlane = 128 * 16, kZhPrec = 16 * kZhPlane, kZhBytes = 2 * kZhPrec;   // split-fp16 z, the VQ A operand: 65 536, overlays Y
+// split-fp16 z, the VQ A operand, overlays Y behind zs: 64 dense rows (latent positions) per 8-channel plane; the MMA's
+// rows 64..127 read the following plane (or 1 KB past the last one) and only feed accumulator rows nobody reads
+constexpr uint32_t kZhPlane = 64 * 16, kZhPrec = 16 * kZhPlane, kZhBytes = 2 * kZhPrec + 1024;   // 33 792
 constexpr int kX32Pitch = 36;
 
 constexpr uint32_t kOffRing = 0;
 constexpr uint32_t kOffA8 = kOffRing + kStages * kStageBytes;   // 49 152
 constexpr uint32_t kOffY = kOffA8 + kA8Bytes;                   // 100 352
-constexpr uint32_t kOffZs = kOffA8;                             // both overlays are cleared again at the start of every leaf
-constexpr uint32_t kOffZh = kOffY;
+constexpr uint32_t kOffZs = kOffY;                              // Y is cleared again once the leaf's indices are out
+constexpr uint32_t kOffZh = kOffY + 34816;
 constexpr uint32_t kOffH = kOffY + kYBytes;                     // 182 272
 constexpr uint32_t kOffIn = kOffH + kHBytes;                    // in_halo [10][10][10] fp32 (4096 reserved)
 constexpr uint32_t kOffPreW = kOffIn + 4096;                    // pre.0 weights [27][16] fp32
@@ -89,7 +91,7 @@ constexpr uint32_t kOffBar = kOffXq + 512;                      // mbarriers
 constexpr uint32_t kNumBars = 2 * kStages + 2;
 constexpr uint32_t kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemSlot + 16;
-static_assert(kZsBytes <= kA8Bytes && kZhBytes <= kYBytes, "z overlays fit inside the A8 / Y regions");
+static_assert(kZsBytes <= 34816 && 34816 + kZhBytes <= kYBytes, "z overlays fit inside the Y region");
 static_assert(4 * 4 * 128 * 4 <= 64 * kX32Pitch * 4, "VQ exchange arrays fit in the dead x32 staging area");
 static_assert(kSmemBytes <= 227 * 1024, "encode_tc smem budget");
 static_assert(kOffBar % 8 == 0 && kOffA8 % 1024 == 0 && kOffY % 1024 == 0 && kOffH % 1024 == 0, "alignment");
@@ -561,15 +563,21 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 		float* vq_best = x32s + 1024;
 		int* vq_bidx = reinterpret_cast<int*>(x32s + 1536);
 
-#pragma unroll 1
-		for (int64_t it = 0; it < my_leaves; ++it) {
-			const int64_t leaf = blockIdx.x + it * gridDim.x;
-			// ---- stage the leaf (2048 B, 128-bit coalesced) into the haloed fp32 buffer; clear what the z overlays dirtied ----
-			if (it > 0) {
-				row_bar();  // every row thread is done with the previous leaf's z rows
-				for (uint32_t i = tid; i < kYBytes / 16; i += kRowThreads) reinterpret_cast<uint4*>(smem + kOffY)[i] = make_uint4(0, 0, 0, 0);
-				for (uint32_t i = tid; i < kZsBytes / 16; i += kRowThreads) reinterpret_cast<uint4*>(smem + kOffZs)[i] = make_uint4(0, 0, 0, 0);
-			}
+		// Rows of this thread in the five 8^3 tiles (the same for every leaf).
+		uint32_t valid8 = 0;
+		int base8[5];
+#pragma unroll
+		for (int t = 0; t < 5; ++t) {
+			int d, h, w8;
+			const bool ok = row8(t * 128 + row, d, h, w8);
+			valid8 |= ok ? (1u << t) : 0u;
+			base8[t] = ok ? d * 100 + h * 10 + w8 : 0;
+		}
+		const uint32_t a8_mine = a8 + (uint32_t)(g >> 1) * kA8Plane + (uint32_t)(kA8Margin + row) * 16 + (uint32_t)(g & 1) * 8;
+
+		// ---- the front of a leaf, software-pipelined into the MMA waits of the previous leaf ----
+		// (a) stage the leaf (2048 B, 128-bit coalesced) into the haloed fp32 buffer
+		auto front_load = [&](int64_t leaf) {
 			if (tid < 128) {
 				const float4 v = __ldcs(reinterpret_cast<const float4*>(leaves + leaf * 512) + tid);
 				const int p = tid * 4, d = p >> 6, h = (p >> 3) & 7, w0 = p & 7;
@@ -577,85 +585,95 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
 			}
 			row_bar();
-			lap(0);
-
-			// ---- pre.0: Conv3d(1,16,k3) on FFMA, channels 4g..4g+3 ; pre.1: GroupNorm(4,16) + ReLU -> x (kept in registers) ----
-			float xr[5][4];
-			uint32_t valid8 = 0;
-			{
-				int base[5];
+		};
+		// (b) pre.0: Conv3d(1,16,k3) on FFMA, channels 4g..4g+3, + bias
+		auto front_pre0 = [&](float (&x)[5][4]) {
 #pragma unroll
-				for (int t = 0; t < 5; ++t) {
-					int d, h, w8;
-					const bool ok = row8(t * 128 + row, d, h, w8);
-					valid8 |= ok ? (1u << t) : 0u;
-					base[t] = ok ? d * 100 + h * 10 + w8 : 0;
+			for (int t = 0; t < 5; ++t)
 #pragma unroll
-					for (int c = 0; c < 4; ++c) xr[t][c] = 0.f;
-				}
+				for (int c = 0; c < 4; ++c) x[t][c] = 0.f;
 #pragma unroll 1
-				for (int kd = 0; kd < 3; ++kd) {
+			for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
-					for (int kh = 0; kh < 3; ++kh) {
+				for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-						for (int kw = 0; kw < 3; ++kw) {
-							const int tap = (kd * 3 + kh) * 3 + kw;
-							const float4 f = *reinterpret_cast<const float4*>(s_prew + tap * 16 + g * 4);
-							const float wv[4] = {f.x, f.y, f.z, f.w};
+					for (int kw = 0; kw < 3; ++kw) {
+						const int tap = (kd * 3 + kh) * 3 + kw;
+						const float4 f = *reinterpret_cast<const float4*>(s_prew + tap * 16 + g * 4);
+						const float wv[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-							for (int t = 0; t < 5; ++t) {
-								const float xv = in_halo[base[t] + kd * 100 + kh * 10 + kw];
+						for (int t = 0; t < 5; ++t) {
+							const float xv = in_halo[base8[t] + kd * 100 + kh * 10 + kw];
 #pragma unroll
-								for (int c = 0; c < 4; ++c) xr[t][c] = fmaf(xv, wv[c], xr[t][c]);
-							}
-						}
-					}
-				}
-#pragma unroll
-				for (int c = 0; c < 4; ++c) {
-					const float b = sp_c[par::pre_b + g * 4 + c];
-#pragma unroll
-					for (int t = 0; t < 5; ++t) xr[t][c] += b;
-				}
-				float mean[1], rstd[1];  // this thread's 4 channels are exactly GroupNorm group g
-				gn_stats_regs<5, 4, 4>(xr, valid8, 1.f / 2048.f, rc, mean, rstd);
-#pragma unroll
-				for (int c = 0; c < 4; ++c) {
-					const float ga = sp_c[par::pre_gn_w + g * 4 + c], be = sp_c[par::pre_gn_b + g * 4 + c];
-#pragma unroll
-					for (int t = 0; t < 5; ++t) xr[t][c] = fmaxf((xr[t][c] - mean[0]) * rstd[0] * ga + be, 0.f);
-				}
-			}
-			lap(1);
-			// ---- res16.gn1 + ReLU -> A8 (conv1 input) ----
-			const uint32_t a8_mine = a8 + (uint32_t)(g >> 1) * kA8Plane + (uint32_t)(kA8Margin + row) * 16 + (uint32_t)(g & 1) * 8;
-			{
-				float mean[2], rstd[2];
-				gn_stats_regs<5, 4, 2>(xr, valid8, 1.f / 1024.f, rc, mean, rstd);
-				float ga[4], be[4];
-#pragma unroll
-				for (int c = 0; c < 4; ++c) {
-					ga[c] = sp_c[par::r16_gn1_w + g * 4 + c];
-					be[c] = sp_c[par::r16_gn1_b + g * 4 + c];
-				}
-#pragma unroll
-				for (int t = 0; t < 5; ++t) {
-					if (valid8 & (1u << t)) {
-						float a[4];
-#pragma unroll
-						for (int c = 0; c < 4; ++c) a[c] = fmaxf((xr[t][c] - mean[c >> 1]) * rstd[c >> 1] * ga[c] + be[c], 0.f);
-						store_split4(a8_mine + t * 2048, kA8Prec, a);
-						if (tap_stage == 0) {
-							int d, h, w8;
-							row8(t * 128 + row, d, h, w8);
-#pragma unroll
-							for (int c = 0; c < 4; ++c) tap_out[(leaf * 16 + g * 4 + c) * 512 + d * 64 + h * 8 + w8] = xr[t][c];
+							for (int c = 0; c < 4; ++c) x[t][c] = fmaf(xv, wv[c], x[t][c]);
 						}
 					}
 				}
 			}
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				const float b = sp_c[par::pre_b + g * 4 + c];
+#pragma unroll
+				for (int t = 0; t < 5; ++t) x[t][c] += b;
+			}
+		};
+		// (c) pre.1: GroupNorm(4,16) + ReLU -> x (the residual, kept in registers)
+		auto front_gn_pre1 = [&](float (&x)[5][4]) {
+			float mean[1], rstd[1];  // this thread's 4 channels are exactly GroupNorm group g
+			gn_stats_regs<5, 4, 4>(x, valid8, 1.f / 2048.f, rc, mean, rstd);
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				const float ga = sp_c[par::pre_gn_w + g * 4 + c], be = sp_c[par::pre_gn_b + g * 4 + c];
+#pragma unroll
+				for (int t = 0; t < 5; ++t) x[t][c] = fmaxf((x[t][c] - mean[0]) * rstd[0] * ga + be, 0.f);
+			}
+		};
+		// (d) res16.gn1 + ReLU -> A8 (conv1 input)
+		auto front_gn1_to_a8 = [&](const float (&x)[5][4], int64_t leaf) {
+			float mean[2], rstd[2];
+			gn_stats_regs<5, 4, 2>(x, valid8, 1.f / 1024.f, rc, mean, rstd);
+			float ga[4], be[4];
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				ga[c] = sp_c[par::r16_gn1_w + g * 4 + c];
+				be[c] = sp_c[par::r16_gn1_b + g * 4 + c];
+			}
+#pragma unroll
+			for (int t = 0; t < 5; ++t) {
+				if (valid8 & (1u << t)) {
+					float a[4];
+#pragma unroll
+					for (int c = 0; c < 4; ++c) a[c] = fmaxf((x[t][c] - mean[c >> 1]) * rstd[c >> 1] * ga[c] + be[c], 0.f);
+					store_split4(a8_mine + t * 2048, kA8Prec, a);
+					if (tap_stage == 0) {
+						int d, h, w8;
+						row8(t * 128 + row, d, h, w8);
+#pragma unroll
+						for (int c = 0; c < 4; ++c) tap_out[(leaf * 16 + g * 4 + c) * 512 + d * 64 + h * 8 + w8] = x[t][c];
+					}
+				}
+			}
+		};
+
+		float xn[5][4];  // x of the leaf whose front is in progress
+		if (my_leaves > 0) {
+			front_load(blockIdx.x);
+			front_pre0(xn);
+			front_gn_pre1(xn);
+			front_gn1_to_a8(xn, blockIdx.x);
 			signal_a_ready(bars, lane);
-			lap(2);
+		}
+		lap(1);
+
+#pragma unroll 1
+		for (int64_t it = 0; it < my_leaves; ++it) {
+			const int64_t leaf = blockIdx.x + it * gridDim.x;
+			const bool has_next = it + 1 < my_leaves;
+			float xr[5][4];
+#pragma unroll
+			for (int t = 0; t < 5; ++t)
+#pragma unroll
+				for (int c = 0; c < 4; ++c) xr[t][c] = xn[t][c];
 
 			// ---- conv1 epilogue: + bias, res16.gn2 + ReLU -> A8 (conv2 input) ----
 			wait_accumulator(rc);
@@ -725,6 +743,11 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			}
 			signal_a_ready(bars, lane);
 			lap(6);
+			if (has_next) {  // the `down` MMAs run for ~6 k cycles: stage the next leaf and run its pre.0
+				front_load(leaf + gridDim.x);
+				front_pre0(xn);
+			}
+			lap(0);
 
 			// ---- down epilogue: sum the accumulation chains, + bias -> x32 (residual, to shared memory) ; res32.gn1 + ReLU -> H32 ----
 			wait_accumulator(rc);
@@ -787,6 +810,8 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			}
 			signal_a_ready(bars, lane);
 			lap(8);
+			if (has_next) front_gn_pre1(xn);
+			lap(1);
 
 			// ---- res32 conv1 epilogue: + bias, gn2 + ReLU -> H32 ----
 			const uint32_t h_mine = hb + (uint32_t)g * kHPlane + (uint32_t)(kHMargin + row) * 16;
@@ -812,6 +837,8 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			}
 			signal_a_ready(bars, lane);
 			lap(10);
+			if (has_next) front_gn1_to_a8(xn, leaf + gridDim.x);  // A8 has been free since conv2's MMAs completed
+			lap(2);
 
 			// ---- res32 conv2 epilogue: x3 = x32 + 0.1 (conv2 + b) ; ChannelAttention(32) -> H32 (proj input) ----
 			wait_accumulator(rc);
@@ -896,15 +923,17 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 							for (int c = 0; c < 16; ++c) tap_out[(leaf * 128 + g * 32 + half * 16 + c) * 64 + p4] = hh[c];
 						}
 					}
+					if (valid4) {  // VQ GEMM rows are the dense latent positions p = (d*4+h)*4+w
 #pragma unroll
-					for (int j = 0; j < 2; ++j) {
-						float z8[8];
+						for (int j = 0; j < 2; ++j) {
+							float z8[8];
 #pragma unroll
-						for (int c = 0; c < 8; ++c) z8[c] = hh[8 * j + c];
-						store_split8(zh + (uint32_t)(g * 4 + half * 2 + j) * kZhPlane + (uint32_t)row * 16, kZhPrec, z8);
+							for (int c = 0; c < 8; ++c) z8[c] = hh[8 * j + c];
+							store_split8(zh + (uint32_t)(g * 4 + half * 2 + j) * kZhPlane + (uint32_t)p4 * 16, kZhPrec, z8);
+						}
 					}
 				}
-				vq_zz[g * 128 + row] = zzp;
+				if (valid4) vq_zz[g * 128 + p4] = zzp;
 			}
 			signal_a_ready(bars, lane);
 			lap(14);
@@ -917,7 +946,9 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			//  2. every code whose lower bound a_k - B_k does not exceed min_j (a_j + B_j) is re-scored with the reference's
 			//     fp32 formula, sequential in d; the fp32 arg-min and all its ties are in that shortlist.  It has a second
 			//     entry for about 1 % of the rows (near-ties); a single entry needs no re-scoring at all.
-			//  The four threads of a row take 64 codes each; tcgen05.ld is warp-collective, so every lane runs the loads.
+			//  GEMM row = latent position (rows 64..127 are unused).  The four threads of a row take 64 codes each;
+			//  tcgen05.ld is warp-collective, so every lane runs the loads.
+			const bool validv = row < 64;
 			wait_accumulator(rc);
 			row_bar();  // z rows and |z|^2 partials of all four groups are in place
 			lap(15);
@@ -947,7 +978,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 #pragma unroll
 				for (int j = 0; j < 64; ++j)
 					if (sc[j] - (cb * s_eno[g * 64 + j] + 1e-4f) <= umin) mask |= 1ull << j;
-				if (!valid4) mask = 0ull;
+				if (!validv) mask = 0ull;
 				float best = INFINITY;
 				int bi = 0x7fffffff;
 				int* vq_cnt = reinterpret_cast<int*>(vq_zz);  // |z|^2 partials were consumed before the previous barrier
@@ -959,7 +990,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					best = -INFINITY;
 					mask = 0ull;
 				}
-				const float* zrow = zs + (valid4 ? p4 : 0) * kZsPitch;
+				const float* zrow = zs + (validv ? row : 0) * kZsPitch;
 				while (mask) {  // two candidates per trip: two independent FMA chains
 					const int b0 = __ffsll((long long)mask) - 1;
 					mask &= mask - 1;
@@ -993,7 +1024,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				vq_best[g * 128 + row] = best;
 				vq_bidx[g * 128 + row] = bi;
 				row_bar();
-				if (g == 0 && valid4) {
+				if (g == 0 && validv) {
 #pragma unroll
 					for (int o = 1; o < 4; ++o) {  // ascending code ranges: strict < keeps the lowest code among equal distances
 						const float ob = vq_best[o * 128 + row];
@@ -1002,10 +1033,16 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 							bi = vq_bidx[o * 128 + row];
 						}
 					}
-					indices[leaf * 64 + p4] = (uint8_t)bi;  // p = (d*4+h)*4+w == view(B,4,4,4)
+					indices[leaf * 64 + row] = (uint8_t)bi;  // row = (d*4+h)*4+w == view(B,4,4,4)
 				}
 			}
-			tc_fence_before();  // this leaf's TMEM reads are ordered before the next leaf's first MMAs (via a_ready)
+			// ---- leaf done: Y (dirtied by the z overlays) is cleared for the next conv2 epilogue, and the next leaf's conv1 —
+			//      its input has been in A8 since the res32 phase — may start now that the accumulators are drained ----
+			if (has_next) {
+				row_bar();  // every row thread is done with z and with the TMEM scores
+				for (uint32_t i = tid; i < kYBytes / 16; i += kRowThreads) reinterpret_cast<uint4*>(smem + kOffY)[i] = make_uint4(0, 0, 0, 0);
+				signal_a_ready(bars, lane);
+			}
 			lap(18);
 		}
 		if (kProf && tap_out && tid == 0) {
