@@ -422,29 +422,34 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			};
 #pragma unroll 1
 			for (int64_t it = 0; it < my_leaves; ++it) {
-				// ---- res16 conv1, conv2: 5 tiles x 9 (kd, kh) x {N = 96, N = 48} ----
+				// ---- res16 conv1, conv2: 5 tiles x 9 (kd, kh) x {N = 96, N = 48}, in two tile groups (0-2, 3-4) with their own
+				//      completion signal: the row threads drain the first group while the second group's MMAs run ----
 #pragma unroll 1
 				for (int layer = 0; layer < 2; ++layer) {
 					wait_a();
 #pragma unroll 1
-					for (int kd = 0; kd < 3; ++kd) {
-						const uint32_t wb = wait_w();
-						const long long c0 = prof_clock<kProf>();
+					for (int tg = 0; tg < 2; ++tg) {
+						const int t0 = tg ? 3 : 0, t1 = tg ? 5 : 3;
 #pragma unroll 1
-						for (int t = 0; t < 5; ++t) {
+						for (int kd = 0; kd < 3; ++kd) {
+							const uint32_t wb = wait_w();
+							const long long c0 = prof_clock<kProf>();
+#pragma unroll 1
+							for (int t = t0; t < t1; ++t) {
 #pragma unroll
-							for (int kh = 0; kh < 3; ++kh) {
-								const int s = (kd - 1) * 72 + (kh - 1) * 8 + 128 * t;
-								const uint64_t ad = a8_d + (uint64_t)(int64_t)s;
-								const uint64_t bd = make_desc(wb + kh * 3072, 96 * 16, 128);
-								mma_ss(tmem + t * 96, ad, bd, idesc_f16(96), (kd > 0 || kh > 0) ? 1u : 0u);
-								mma_ss(tmem + t * 96 + 48, ad + (kA8Prec >> 4), bd, idesc_f16(48), 1u);
+								for (int kh = 0; kh < 3; ++kh) {
+									const int s = (kd - 1) * 72 + (kh - 1) * 8 + 128 * t;
+									const uint64_t ad = a8_d + (uint64_t)(int64_t)s;
+									const uint64_t bd = make_desc(wb + kh * 3072, 96 * 16, 128);
+									mma_ss(tmem + t * 96, ad, bd, idesc_f16(96), (kd > 0 || kh > 0) ? 1u : 0u);
+									mma_ss(tmem + t * 96 + 48, ad + (kA8Prec >> 4), bd, idesc_f16(48), 1u);
+								}
 							}
+							release_w();
+							if (kProf) t_issue += prof_clock<kProf>() - c0;
 						}
-						release_w();
-						if (kProf) t_issue += prof_clock<kProf>() - c0;
+						tc_commit(bar_d_full(bars));
 					}
-					tc_commit(bar_d_full(bars));
 				}
 				// ---- down: 4 (td, th) tap pairs x 8 parity classes x {N = 128, N = 64}; the two tw taps of a pair are
 				//      concatenated along N like the kw taps of the 3x3x3 convs (their row shift of 1 is applied in the
@@ -577,9 +582,8 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 
 		// ---- the front of a leaf, software-pipelined into the MMA waits of the previous leaf ----
 		// (a) stage the leaf (2048 B, 128-bit coalesced) into the haloed fp32 buffer
-		auto front_load = [&](int64_t leaf) {
+		auto front_load = [&](const float4& v) {
 			if (tid < 128) {
-				const float4 v = __ldcs(reinterpret_cast<const float4*>(leaves + leaf * 512) + tid);
 				const int p = tid * 4, d = p >> 6, h = (p >> 3) & 7, w0 = p & 7;
 				float* dst = in_halo + (d + 1) * 100 + (h + 1) * 10 + w0 + 1;
 				dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
@@ -657,7 +661,9 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 
 		float xn[5][4];  // x of the leaf whose front is in progress
 		if (my_leaves > 0) {
-			front_load(blockIdx.x);
+			float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (tid < 128) v0 = __ldcs(reinterpret_cast<const float4*>(leaves + (int64_t)blockIdx.x * 512) + tid);
+			front_load(v0);
 			front_pre0(xn);
 			front_gn_pre1(xn);
 			front_gn1_to_a8(xn, blockIdx.x);
@@ -669,6 +675,8 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 		for (int64_t it = 0; it < my_leaves; ++it) {
 			const int64_t leaf = blockIdx.x + it * gridDim.x;
 			const bool has_next = it + 1 < my_leaves;
+			float4 nx_v = make_float4(0.f, 0.f, 0.f, 0.f);  // the next leaf's voxels: in flight while this leaf's 8^3 layers run
+			if (has_next && tid < 128) nx_v = __ldcs(reinterpret_cast<const float4*>(leaves + (leaf + gridDim.x) * 512) + tid);
 			float xr[5][4];
 #pragma unroll
 			for (int t = 0; t < 5; ++t)
@@ -685,6 +693,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				for (int c = 0; c < 4; ++c) bs[c] = sp_c[par::r16_c1_b + g * 4 + c];
 #pragma unroll
 				for (int t = 0; t < 5; ++t) {
+					if (t == 3) wait_accumulator(rc);  // second tile group
 					conv16_tile_out(rc.tlane + t * 96, g, lane & 7, v[t]);
 #pragma unroll
 					for (int c = 0; c < 4; ++c) v[t][c] += bs[c];
@@ -724,6 +733,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				for (int c = 0; c < 4; ++c) bs[c] = sp_c[par::r16_c2_b + g * 4 + c];
 #pragma unroll
 				for (int t = 0; t < 5; ++t) {
+					if (t == 3) wait_accumulator(rc);  // second tile group
 					float o[4];
 					conv16_tile_out(rc.tlane + t * 96, g, lane & 7, o);
 					int d, h, w8;
@@ -744,7 +754,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			signal_a_ready(bars, lane);
 			lap(6);
 			if (has_next) {  // the `down` MMAs run for ~6 k cycles: stage the next leaf and run its pre.0
-				front_load(leaf + gridDim.x);
+				front_load(nx_v);
 				front_pre0(xn);
 			}
 			lap(0);
@@ -955,9 +965,8 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			{
 				const float zz = (vq_zz[row] + vq_zz[128 + row]) + (vq_zz[256 + row] + vq_zz[384 + row]);
 				const float cb = 8e-6f * sqrtf(zz);
-				float sc[64];
 				float umin = INFINITY;
-#pragma unroll
+#pragma unroll 1
 				for (int ch = 0; ch < 4; ++ch) {
 					float hh[16], mx[16];
 					tmem_ld16_nowait(rc.tlane + g * 64 + ch * 16, hh);
@@ -966,8 +975,8 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 #pragma unroll
 					for (int j = 0; j < 16; ++j) {
 						const int k = g * 64 + ch * 16 + j;
-						sc[ch * 16 + j] = s_esq[k] - 2.f * fmaf(mx[j], kLoInv, hh[j]);
-						umin = fminf(umin, sc[ch * 16 + j] + (cb * s_eno[k] + 1e-4f));
+						const float a = s_esq[k] - 2.f * fmaf(mx[j], kLoInv, hh[j]);
+						umin = fminf(umin, a + (cb * s_eno[k] + 1e-4f));
 					}
 				}
 				vq_umin[g * 128 + row] = umin;
@@ -975,9 +984,21 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				lap(16);
 				umin = fminf(fminf(vq_umin[row], vq_umin[128 + row]), fminf(vq_umin[256 + row], vq_umin[384 + row]));
 				unsigned long long mask = 0ull;
+#pragma unroll 1
+				for (int ch = 0; ch < 4; ++ch) {  // the scores are read again rather than kept in 64 registers
+					float hh[16], mx[16];
+					tmem_ld16_nowait(rc.tlane + g * 64 + ch * 16, hh);
+					tmem_ld16_nowait(rc.tlane + 256 + g * 64 + ch * 16, mx);
+					tmem_wait_ld();
+					uint32_t m16 = 0u;
 #pragma unroll
-				for (int j = 0; j < 64; ++j)
-					if (sc[j] - (cb * s_eno[g * 64 + j] + 1e-4f) <= umin) mask |= 1ull << j;
+					for (int j = 0; j < 16; ++j) {
+						const int k = g * 64 + ch * 16 + j;
+						const float a = s_esq[k] - 2.f * fmaf(mx[j], kLoInv, hh[j]);
+						if (a - (cb * s_eno[k] + 1e-4f) <= umin) m16 |= 1u << j;
+					}
+					mask |= (unsigned long long)m16 << (ch * 16);
+				}
 				if (!validv) mask = 0ull;
 				float best = INFINITY;
 				int bi = 0x7fffffff;

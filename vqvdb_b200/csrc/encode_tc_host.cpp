@@ -82,6 +82,7 @@ std::vector<uint8_t> build_encoder_tc_units(const WeightPack& p, EncoderTcStream
 	// res16 conv1 / conv2: weight [16][16][3][3][3]
 	for (const char* name : {"encoder.pre.3.conv1.weight", "encoder.pre.3.conv2.weight"}) {
 		const float* w = p.get(name).data;
+		for (int pass = 0; pass < 2; ++pass)  // one pass per tile group
 		for (int kd = 0; kd < 3; ++kd) {
 			uint8_t* u = begin_unit(3 * 3072);
 			for (int kh = 0; kh < 3; ++kh)

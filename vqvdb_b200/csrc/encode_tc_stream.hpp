@@ -12,14 +12,15 @@ namespace vqvdb {
 // The encoder's GEMM-shaped layers consume their weights as a fixed stream of "units" (<= 16 KB) through a
 // shared-memory ring.  Every unit is a sequence of B operands in the canonical no-swizzle K-major UMMA layout
 // [k-chunk (2)][n][8 elements = 16 B]; conv weights are split into two fp16 planes, w ~= w_hi + w_lo / 2048:
-//   res16 conv1 / conv2 : 3 units each (one per kd) = 3 (kh) x [2][96][16 B], n = part*48 + kw*16 + cout
+//   res16 conv1 / conv2 : 3 units (one per kd) = 3 (kh) x [2][96][16 B], n = part*48 + kw*16 + cout; streamed TWICE per conv
+//                         (tiles 0-2, then tiles 3-4, so the first group's epilogue overlaps the second group's MMAs)
 //   down                : 8 units (2x2x2-tap space-to-depth form; one per (td, th) tap pair and half of the 8 input
 //                         parity classes) = 4 parity classes x [2][128][16 B], n = part*64 + tw*32 + cout
 //   res32 conv1 / conv2 : 9 units each (one per (kd, kh)) = 2 k-steps x [2][192][16 B], n = part*96 + kw*32 + cout
 //   proj                : 1 unit = 2 k-steps x [2][256][16 B], n = part*128 + cout
 //   codebook            : 8 units (one per 16-dim k-step) = [2][256][16 B] e_hi then [2][256][16 B] e_lo, n = code
 // (part 0 = w_hi, part 1 = w_lo).
-constexpr int kEncTcUnits = 41;
+constexpr int kEncTcUnits = 47;
 constexpr uint32_t kEncTcStageBytes = 16384;
 
 struct EncoderTcStream {
