@@ -22,6 +22,7 @@ B200Backend::B200Backend(const CodecConfig& config) {
 	c.device = config.cudaDevice;
 	c.chunk_leaves = config.chunkLeaves;
 	c.decode_precision = config.fp32Decode ? VQVDB_B200_DECODE_FP32 : VQVDB_B200_DECODE_DEFAULT;
+	c.encode_precision = config.fp32Encode ? VQVDB_B200_ENCODE_FP32 : VQVDB_B200_ENCODE_DEFAULT;
 	std::string path;
 	if (std::holds_alternative<std::filesystem::path>(config.source)) {
 		path = std::get<std::filesystem::path>(config.source).string();
@@ -35,8 +36,8 @@ B200Backend::B200Backend(const CodecConfig& config) {
 	vqvdb_b200_latent_shape(handle_, dhw);
 	latentShape_.assign(dhw, dhw + 3);
 	channels_ = vqvdb_b200_in_channels(handle_);
-	std::cout << "B200Backend: " << vqvdb_b200_version() << ", device " << c.device << ", decode path "
-	          << vqvdb_b200_decode_path(handle_) << std::endl;
+	std::cout << "B200Backend: " << vqvdb_b200_version() << ", device " << c.device << ", encode path "
+	          << vqvdb_b200_encode_path(handle_) << ", decode path " << vqvdb_b200_decode_path(handle_) << std::endl;
 }
 
 B200Backend::~B200Backend() { vqvdb_b200_destroy(handle_); }

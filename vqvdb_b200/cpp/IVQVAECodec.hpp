@@ -55,6 +55,7 @@ struct CodecConfig {
 	int cudaDevice = 0;             // the reference hard-codes device 0 (OnnxBackend_Cuda.cpp:21)
 	uint32_t chunkLeaves = 0;       // leaves per internal pipeline chunk, 0 = default
 	bool fp32Decode = false;        // CUDA-core fp32 decoder instead of the bf16 tensor-core one
+	bool fp32Encode = false;        // CUDA-core fp32 FFMA encoder instead of the split-fp16 tensor-core one
 };
 
 class IVQVAECodec {
