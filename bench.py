@@ -229,6 +229,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--decode-precision", default="default")
     ap.add_argument("--encode-precision", default="default", help="default | fp32 (FFMA) | fp16x2_tc (tcgen05)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N>1: decode straight into rank 0's buffer over NVLink (CUDA IPC peer stores), or decode locally + NCCL gather")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -237,7 +239,7 @@ def main():
     import torch
     import torch.distributed as dist
     from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec
-    from vqvdb_b200.sharding import gather_blocks
+    from vqvdb_b200.sharding import PeerGather, gather_blocks
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -246,7 +248,13 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the B200 backend has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    json_fd = None
     if world > 1:
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set: park fd 1 on stderr for the run and print
+        # the one JSON line through the saved descriptor, so stdout carries that line only
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K = max(1, args.steps)
@@ -261,17 +269,22 @@ def main():
     x = gen_leaves_gpu(L, dev, seed=rank)
     idx = torch.empty((L, 4, 4, 4), dtype=torch.uint8, device=dev)
     vox = torch.empty((L, 1, 8, 8, 8), dtype=torch.float32, device=dev)
-    gathered = None
-    if world > 1 and rank == 0:
+    gathered, peer = None, None
+    if world > 1 and args.gather == "peer":
+        peer = PeerGather(codec, L * world, dst=0)     # rank 0 owns [L*world, 512] fp32; the others map it over NVLink
+    elif world > 1 and rank == 0:
         gathered = torch.empty((L * world, 1, 8, 8, 8), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
 
     def step():
         codec.encode_device(x, L, idx, sp)
-        codec.decode_device(idx, L, vox, sp)
-        if world > 1:  # grid reassembly on rank 0: decoded blocks travel over NVLink (north_star)
-            gather_blocks(vox, L * world, dst=0, out=gathered)
+        if peer is not None:  # grid reassembly on rank 0: the decode kernel's stores land in rank 0's HBM over NVLink
+            codec.decode_device(idx, L, peer.my_slice_ptr, sp)
+        else:
+            codec.decode_device(idx, L, vox, sp)
+            if world > 1:     # ... or decode locally and gather the blocks with NCCL
+                gather_blocks(vox, L * world, dst=0, out=gathered)
 
     def barrier():
         if world > 1:
@@ -378,7 +391,7 @@ def main():
                 "bf16 operands/f32 accumulate" if codec.decode_path != "fp32" else "f32"),
             "data": "synthetic",
             "config": {"workload": "roundtrip_1M_float_leaves", "leaves_per_gpu": L, "weights": "shipped float model C=1 D=128 K=256",
-                       "sharding": "leaf ranges, one rank per GPU" + (", NCCL gather of decoded blocks to rank 0" if world > 1 else ""),
+                       "sharding": "leaf ranges, one rank per GPU" + ((", decode kernels store straight into rank 0's buffer over NVLink (CUDA IPC)" if peer is not None else ", NCCL gather of decoded blocks to rank 0") if world > 1 else ""),
                        "l2": "inputs (%.2f GB/step) exceed the 126 MB L2; no explicit flush" % (L * 2048 / 1e9),
                        "encode_path": codec.encode_path, "decode_path": codec.decode_path},
             "parts": {"encode_ms": enc_ms, "decode_ms": dec_ms,
@@ -401,7 +414,12 @@ def main():
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "leaves/s", "cores": 0, "kind": "reference",
                                         "sample": "failed: %s" % str(e)[:200]}
-        print(json.dumps(line))
+        if json_fd is not None:
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line))
+    if peer is not None:
+        peer.close()
     codec.close()
     if world > 1:
         dist.destroy_process_group()

@@ -115,6 +115,19 @@ VQVDB_B200_API int vqvdb_b200_decode_device(vqvdb_b200_codec* codec, const uint8
 /* Blocks until the codec's own pipeline streams are idle (work enqueued on caller streams is the caller's). */
 VQVDB_B200_API int vqvdb_b200_synchronize(vqvdb_b200_codec* codec);
 
+/* Multi-GPU reassembly without a staging copy (leaves shard across the GPUs of one box, decoded blocks
+ * travel to the rank that rebuilds the grid — the step the reference's single-GPU loop, VQVAECodec.cpp:166-200, does
+ * not have).  The reassembly rank creates the gathered buffer on its device and exports a CUDA IPC handle; every other
+ * rank (one process per GPU) opens it and passes `base + leaf_offset * 2048` as dev_voxels to vqvdb_b200_decode_device,
+ * so the decode kernel's own epilogue stores land in the owner's HBM over NVLink: compute and gather are one kernel.
+ *   create: cudaMalloc on the codec's device; handle_out receives the 64-byte cudaIpcMemHandle_t.
+ *   open  : maps a peer's buffer into this process (lazy peer access); not valid in the creating process.
+ *   close : unmaps (opened != 0) or frees (opened == 0). */
+VQVDB_B200_API int vqvdb_b200_peer_buffer_create(vqvdb_b200_codec* codec, uint64_t bytes, void** dev_ptr_out,
+                                                 unsigned char handle_out[64]);
+VQVDB_B200_API int vqvdb_b200_peer_buffer_open(vqvdb_b200_codec* codec, const unsigned char handle[64], void** dev_ptr_out);
+VQVDB_B200_API int vqvdb_b200_peer_buffer_close(vqvdb_b200_codec* codec, void* dev_ptr, int opened);
+
 /* Kernel launches issued by this codec since creation (bench.py's gpu_launches). */
 VQVDB_B200_API uint64_t vqvdb_b200_kernel_launches(const vqvdb_b200_codec* codec);
 /* Name of the decode path actually in use: "fp32", "bf16_tcgen05" or "bf16_mma". */

@@ -82,7 +82,16 @@ def _gpu_worker(rank, world, port, n, q):
         full_idx = gather_blocks(idx, n, dst=0)
         full_vox = gather_blocks(vox, n, dst=0)
         torch.cuda.synchronize()
+        # fused form: every rank's decode kernel stores straight into rank 0's buffer (CUDA IPC, NVLink)
+        from vqvdb_b200.sharding import PeerGather
+        pg = PeerGather(codec, n, dst=0)
+        codec.decode_device(idx, hi - lo, pg.my_slice_ptr, sp)
+        fused = pg.finish()
         if rank == 0:
+            fused = fused.view(n, 1, 8, 8, 8).clone()
+        pg.close()
+        if rank == 0:
+            assert torch.equal(fused, full_vox), "peer-store gather differs from the NCCL gather"
             # single-GPU answer for the whole array on this rank's device
             xi = x.cuda()
             ref_idx = torch.empty((n, 4, 4, 4), dtype=torch.uint8, device="cuda")

@@ -24,6 +24,7 @@ EXPORTS = [  # every symbol include/vqvdb_b200.h declares
     "vqvdb_b200_decode_device", "vqvdb_b200_synchronize", "vqvdb_b200_kernel_launches",
     "vqvdb_b200_decode_path", "vqvdb_b200_last_error", "vqvdb_b200_version", "vqvdb_b200_debug_decode_tap",
     "vqvdb_b200_encode_path", "vqvdb_b200_debug_encode_tap",
+    "vqvdb_b200_peer_buffer_create", "vqvdb_b200_peer_buffer_open", "vqvdb_b200_peer_buffer_close",
 ]
 
 
@@ -71,6 +72,12 @@ def load_library() -> C.CDLL:
     L.vqvdb_b200_debug_encode_tap.restype = C.c_int
     L.vqvdb_b200_encode_path.argtypes = [C.c_void_p]
     L.vqvdb_b200_encode_path.restype = C.c_char_p
+    L.vqvdb_b200_peer_buffer_create.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]
+    L.vqvdb_b200_peer_buffer_create.restype = C.c_int
+    L.vqvdb_b200_peer_buffer_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.vqvdb_b200_peer_buffer_open.restype = C.c_int
+    L.vqvdb_b200_peer_buffer_close.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.vqvdb_b200_peer_buffer_close.restype = C.c_int
     L.vqvdb_b200_synchronize.argtypes = [C.c_void_p]
     L.vqvdb_b200_kernel_launches.argtypes = [C.c_void_p]
     L.vqvdb_b200_kernel_launches.restype = C.c_uint64
@@ -241,6 +248,22 @@ class B200Codec:
     def debug_encode_tap(self, dev_leaves, n: int, stage: int, dev_tap, dev_indices, stream: int = 0):
         self._check(self._L.vqvdb_b200_debug_encode_tap(self._h, self._addr(dev_leaves), n, stage, self._addr(dev_tap),
                                                         self._addr(dev_indices), C.c_void_p(stream)), "debug_encode_tap")
+
+    # -- multi-GPU reassembly buffer (CUDA IPC): see include/vqvdb_b200.h --
+    def peer_buffer_create(self, nbytes: int):
+        """cudaMalloc on this codec's device; returns (device pointer, 64-byte IPC handle)."""
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self._check(self._L.vqvdb_b200_peer_buffer_create(self._h, int(nbytes), C.byref(ptr), handle), "peer_buffer_create")
+        return int(ptr.value), handle.raw
+
+    def peer_buffer_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        self._check(self._L.vqvdb_b200_peer_buffer_open(self._h, C.create_string_buffer(handle, 64), C.byref(ptr)), "peer_buffer_open")
+        return int(ptr.value)
+
+    def peer_buffer_close(self, ptr: int, opened: bool):
+        self._check(self._L.vqvdb_b200_peer_buffer_close(self._h, C.c_void_p(ptr), 1 if opened else 0), "peer_buffer_close")
 
     def synchronize(self):
         self._check(self._L.vqvdb_b200_synchronize(self._h), "synchronize")

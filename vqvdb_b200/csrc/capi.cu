@@ -639,6 +639,57 @@ int vqvdb_b200_debug_encode_tap(vqvdb_b200_codec* c, const float* dev_leaves, in
 	return VQVDB_B200_OK;
 }
 
+int vqvdb_b200_peer_buffer_create(vqvdb_b200_codec* c, uint64_t bytes, void** dev_ptr_out, unsigned char handle_out[64]) {
+	if (!c) return VQVDB_B200_ERR_INVALID_ARGUMENT;
+	if (!bytes || !dev_ptr_out || !handle_out) return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "peer_buffer_create: bad arguments");
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+	try {
+		CUDA_TRY(cudaSetDevice(c->device));
+		void* p = nullptr;
+		CUDA_TRY(cudaMalloc(&p, bytes));
+		cudaIpcMemHandle_t h;
+		cudaError_t e = cudaIpcGetMemHandle(&h, p);
+		if (e != cudaSuccess) {
+			cudaFree(p);
+			throw CudaError(e, "cudaIpcGetMemHandle");
+		}
+		std::memcpy(handle_out, &h, 64);
+		*dev_ptr_out = p;
+	} catch (const std::exception& e) {
+		return translate(c, e);
+	}
+	return VQVDB_B200_OK;
+}
+
+int vqvdb_b200_peer_buffer_open(vqvdb_b200_codec* c, const unsigned char handle[64], void** dev_ptr_out) {
+	if (!c) return VQVDB_B200_ERR_INVALID_ARGUMENT;
+	if (!handle || !dev_ptr_out) return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "peer_buffer_open: bad arguments");
+	try {
+		CUDA_TRY(cudaSetDevice(c->device));
+		cudaIpcMemHandle_t h;
+		std::memcpy(&h, handle, 64);
+		void* p = nullptr;
+		CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		*dev_ptr_out = p;
+	} catch (const std::exception& e) {
+		return translate(c, e);
+	}
+	return VQVDB_B200_OK;
+}
+
+int vqvdb_b200_peer_buffer_close(vqvdb_b200_codec* c, void* dev_ptr, int opened) {
+	if (!c) return VQVDB_B200_ERR_INVALID_ARGUMENT;
+	if (!dev_ptr) return VQVDB_B200_OK;
+	try {
+		CUDA_TRY(cudaSetDevice(c->device));
+		if (opened) CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+		else CUDA_TRY(cudaFree(dev_ptr));
+	} catch (const std::exception& e) {
+		return translate(c, e);
+	}
+	return VQVDB_B200_OK;
+}
+
 uint64_t vqvdb_b200_kernel_launches(const vqvdb_b200_codec* c) { return c ? c->launches.load() : 0; }
 const char* vqvdb_b200_decode_path(const vqvdb_b200_codec* c) { return c ? c->decode_path.c_str() : ""; }
 const char* vqvdb_b200_encode_path(const vqvdb_b200_codec* c) { return c ? c->encode_path.c_str() : ""; }
