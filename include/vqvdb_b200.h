@@ -77,12 +77,16 @@ typedef struct vqvdb_b200_config {
 	int32_t device;               /* CUDA ordinal (the reference hard-codes 0: OnnxBackend_Cuda.cpp:21) */
 	const void* weights_data;     /* VQVDBW01 pack in memory, or NULL */
 	uint64_t weights_size;
-	const char* weights_path;     /* VQVDBW01 pack on disk, or NULL.  Both NULL = the embedded float model
-	                                 (the reference's EmbeddedModel source, IVQVAECodec.hpp:27) */
+	const char* weights_path;     /* VQVDBW01 pack on disk, or a directory holding encoder.onnx + decoder.onnx (the reference's
+	                                 model-directory source, OnnxBackendFactory.cpp:97-119), or NULL.  All sources NULL = the
+	                                 embedded float model (the reference's EmbeddedModel source, IVQVAECodec.hpp:27) */
 	uint32_t chunk_leaves;        /* leaves per internal pipeline chunk for the host-pointer calls; 0 = default */
 	uint32_t decode_precision;    /* vqvdb_b200_decode_precision */
 	uint32_t encode_precision;    /* vqvdb_b200_encode_precision */
-	uint32_t reserved[7];
+	uint32_t reserved0;
+	const char* onnx_encoder_path; /* the reference's OnnxModelPaths source (IVQVAECodec.hpp:29-33): the two graphs written by */
+	const char* onnx_decoder_path; /* python/to_onnx.py; only their initializers (weights) are read — no ONNX Runtime involved */
+	uint32_t reserved[2];
 } vqvdb_b200_config;
 
 /* IVQVAECodec::create (IVQVAECodec.cpp:76-110).  On failure *out is NULL. */
@@ -146,6 +150,10 @@ VQVDB_B200_API const char* vqvdb_b200_encode_path(const vqvdb_b200_codec* codec)
  * [n][32][64], 5: z [n][128][64]. */
 VQVDB_B200_API int vqvdb_b200_debug_encode_tap(vqvdb_b200_codec* codec, const float* dev_leaves, int64_t n_leaves, int stage,
                                                float* dev_tap, uint8_t* dev_indices, void* cuda_stream);
+
+/* Host-only tool (no device needed): reads the weights out of encoder.onnx + decoder.onnx and writes them as a VQVDBW01
+ * pack.  On failure the message is vqvdb_b200_last_error(NULL). */
+VQVDB_B200_API int vqvdb_b200_convert_onnx(const char* encoder_onnx_path, const char* decoder_onnx_path, const char* out_pack_path);
 
 VQVDB_B200_API const char* vqvdb_b200_last_error(const vqvdb_b200_codec* codec);
 VQVDB_B200_API const char* vqvdb_b200_version(void);

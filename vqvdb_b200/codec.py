@@ -25,6 +25,7 @@ EXPORTS = [  # every symbol include/vqvdb_b200.h declares
     "vqvdb_b200_decode_path", "vqvdb_b200_last_error", "vqvdb_b200_version", "vqvdb_b200_debug_decode_tap",
     "vqvdb_b200_encode_path", "vqvdb_b200_debug_encode_tap",
     "vqvdb_b200_peer_buffer_create", "vqvdb_b200_peer_buffer_open", "vqvdb_b200_peer_buffer_close",
+    "vqvdb_b200_convert_onnx",
 ]
 
 
@@ -38,7 +39,10 @@ class _Config(C.Structure):
         ("chunk_leaves", C.c_uint32),
         ("decode_precision", C.c_uint32),
         ("encode_precision", C.c_uint32),
-        ("reserved", C.c_uint32 * 7),
+        ("reserved0", C.c_uint32),
+        ("onnx_encoder_path", C.c_char_p),
+        ("onnx_decoder_path", C.c_char_p),
+        ("reserved", C.c_uint32 * 2),
     ]
 
 
@@ -78,6 +82,8 @@ def load_library() -> C.CDLL:
     L.vqvdb_b200_peer_buffer_open.restype = C.c_int
     L.vqvdb_b200_peer_buffer_close.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.vqvdb_b200_peer_buffer_close.restype = C.c_int
+    L.vqvdb_b200_convert_onnx.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+    L.vqvdb_b200_convert_onnx.restype = C.c_int
     L.vqvdb_b200_synchronize.argtypes = [C.c_void_p]
     L.vqvdb_b200_kernel_launches.argtypes = [C.c_void_p]
     L.vqvdb_b200_kernel_launches.restype = C.c_uint64
@@ -108,13 +114,28 @@ class EmbeddedModel:
 
 
 @dataclass
+class OnnxModelPaths:
+    """The reference's two-graph source (IVQVAECodec.hpp:29-33); only the initializers (weights) are read."""
+    encoder: str
+    decoder: str
+
+
+def convert_onnx(encoder_onnx: str, decoder_onnx: str, out_pack: str) -> None:
+    """encoder.onnx + decoder.onnx -> VQVDBW01 weight pack (host-only, no device needed)."""
+    L = load_library()
+    rc = L.vqvdb_b200_convert_onnx(os.fspath(encoder_onnx).encode(), os.fspath(decoder_onnx).encode(), os.fspath(out_pack).encode())
+    if rc != 0:
+        raise RuntimeError("vqvdb_b200_convert_onnx failed (%d): %s" % (rc, L.vqvdb_b200_last_error(None).decode()))
+
+
+@dataclass
 class CodecConfig:
     class Device(enum.Enum):
         CPU = 0
         CUDA = 1
 
     device: "CodecConfig.Device" = None  # type: ignore[assignment]
-    source: Union[EmbeddedModel, str, os.PathLike] = field(default_factory=EmbeddedModel)
+    source: Union[EmbeddedModel, "OnnxModelPaths", str, os.PathLike] = field(default_factory=EmbeddedModel)
     device_index: int = 0            # extension: which GPU (the reference hard-codes 0)
     chunk_leaves: int = 0            # extension: pipeline chunk of the host-pointer calls
     decode_precision: str = "default"  # "default" | "fp32" | "bf16_tc" (tcgen05) | "bf16_mma" (mma.sync)
@@ -165,6 +186,9 @@ class B200Codec:
         self._keep = None
         if isinstance(config.source, EmbeddedModel):
             pass
+        elif isinstance(config.source, OnnxModelPaths):
+            self._keep = (os.fspath(config.source.encoder).encode(), os.fspath(config.source.decoder).encode())
+            cfg.onnx_encoder_path, cfg.onnx_decoder_path = self._keep
         elif isinstance(config.source, (bytes, bytearray)):
             self._keep = C.create_string_buffer(bytes(config.source), len(config.source))
             cfg.weights_data = C.cast(self._keep, C.c_void_p)

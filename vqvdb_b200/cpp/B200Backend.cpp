@@ -23,12 +23,15 @@ B200Backend::B200Backend(const CodecConfig& config) {
 	c.chunk_leaves = config.chunkLeaves;
 	c.decode_precision = config.fp32Decode ? VQVDB_B200_DECODE_FP32 : VQVDB_B200_DECODE_DEFAULT;
 	c.encode_precision = config.fp32Encode ? VQVDB_B200_ENCODE_FP32 : VQVDB_B200_ENCODE_DEFAULT;
-	std::string path;
+	std::string path, path2;
 	if (std::holds_alternative<std::filesystem::path>(config.source)) {
-		path = std::get<std::filesystem::path>(config.source).string();
+		path = std::get<std::filesystem::path>(config.source).string();   // a VQVDBW01 pack, or a directory with encoder.onnx + decoder.onnx
 		c.weights_path = path.c_str();
-	} else if (std::holds_alternative<OnnxModelPaths>(config.source)) {
-		throw std::runtime_error("B200 backend reads VQVDBW01 weight packs, not ONNX graphs");
+	} else if (std::holds_alternative<OnnxModelPaths>(config.source)) {  // weights are read from the graphs' initializers
+		path = std::get<OnnxModelPaths>(config.source).encoder_path.string();
+		path2 = std::get<OnnxModelPaths>(config.source).decoder_path.string();
+		c.onnx_encoder_path = path.c_str();
+		c.onnx_decoder_path = path2.c_str();
 	}
 	if (vqvdb_b200_create(&c, &handle_) != VQVDB_B200_OK || !handle_)
 		throw std::runtime_error(std::string("vqvdb_b200_create: ") + vqvdb_b200_last_error(nullptr));

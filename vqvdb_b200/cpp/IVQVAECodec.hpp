@@ -23,7 +23,8 @@ struct OnnxModelPaths {
 	std::filesystem::path encoder_path;
 	std::filesystem::path decoder_path;
 };
-// For BackendType::B200 a std::filesystem::path names a VQVDBW01 weight pack (tools/weights_pack.py).
+// For BackendType::B200 a std::filesystem::path names a VQVDBW01 weight pack (tools/weights_pack.py) or a directory holding
+// encoder.onnx + decoder.onnx; OnnxModelPaths names the two graphs; only their initializers (weights) are read.
 using ModelSource = std::variant<EmbeddedModel, std::filesystem::path, OnnxModelPaths>;
 
 enum class DataType { FLOAT32, UINT8 };

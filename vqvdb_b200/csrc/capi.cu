@@ -8,6 +8,8 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <filesystem>
+#include <fstream>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -452,7 +454,14 @@ int vqvdb_b200_create(const vqvdb_b200_config* cfg, vqvdb_b200_codec** out) {
 		WeightPack pack;
 		try {
 			if (conf.weights_data && conf.weights_size) pack.parse(conf.weights_data, (size_t)conf.weights_size);
-			else if (conf.weights_path && conf.weights_path[0]) pack.load_file(conf.weights_path);
+			else if (conf.onnx_encoder_path && conf.onnx_decoder_path) {
+				const auto blob = vqvdb::onnx_to_pack(vqvdb::read_file_bytes(conf.onnx_encoder_path), vqvdb::read_file_bytes(conf.onnx_decoder_path));
+				pack.parse(blob.data(), blob.size());
+			} else if (conf.weights_path && conf.weights_path[0] && std::filesystem::is_directory(conf.weights_path)) {
+				const std::filesystem::path dir(conf.weights_path);  // OnnxBackendFactory.cpp:97-119: <dir>/encoder.onnx + <dir>/decoder.onnx
+				const auto blob = vqvdb::onnx_to_pack(vqvdb::read_file_bytes((dir / "encoder.onnx").string()), vqvdb::read_file_bytes((dir / "decoder.onnx").string()));
+				pack.parse(blob.data(), blob.size());
+			} else if (conf.weights_path && conf.weights_path[0]) pack.load_file(conf.weights_path);
 			else pack.parse(vqvdb::vqvdb_b200_embedded_pack,
 				            (size_t)(vqvdb::vqvdb_b200_embedded_pack_end - vqvdb::vqvdb_b200_embedded_pack));
 			c->channels = pack.in_channels;
@@ -686,6 +695,20 @@ int vqvdb_b200_peer_buffer_close(vqvdb_b200_codec* c, void* dev_ptr, int opened)
 		else CUDA_TRY(cudaFree(dev_ptr));
 	} catch (const std::exception& e) {
 		return translate(c, e);
+	}
+	return VQVDB_B200_OK;
+}
+
+int vqvdb_b200_convert_onnx(const char* enc_path, const char* dec_path, const char* out_path) {
+	if (!enc_path || !dec_path || !out_path) return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "convert_onnx: bad arguments");
+	try {
+		const auto blob = vqvdb::onnx_to_pack(vqvdb::read_file_bytes(enc_path), vqvdb::read_file_bytes(dec_path));
+		WeightPack check;
+		check.parse(blob.data(), blob.size());
+		std::ofstream f(out_path, std::ios::binary);
+		if (!f || !f.write(reinterpret_cast<const char*>(blob.data()), (std::streamsize)blob.size())) throw std::runtime_error(std::string("cannot write ") + out_path);
+	} catch (const std::exception& e) {
+		return fail(nullptr, VQVDB_B200_ERR_BAD_WEIGHTS, e.what());
 	}
 	return VQVDB_B200_OK;
 }

@@ -42,6 +42,10 @@ struct WeightPack {
 extern "C" const unsigned char vqvdb_b200_embedded_pack[];
 extern "C" const unsigned char vqvdb_b200_embedded_pack_end[];
 
+// ONNX-initializer reader (weights_onnx.cpp): the two graphs python/to_onnx.py writes -> VQVDBW01 pack bytes.
+std::vector<unsigned char> onnx_to_pack(const std::vector<unsigned char>& encoder_onnx, const std::vector<unsigned char>& decoder_onnx);
+std::vector<unsigned char> read_file_bytes(const std::string& path);
+
 // Conv weight [cout][cin][k][k][k] -> [cin][k][k][k][cout]
 std::vector<float> transpose_conv_weight(const PackTensor& w);
 
