@@ -338,7 +338,7 @@ void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
 	ab.add(&m.d_fin_w, vqvdb::transpose_conv_weight(p.get("decoder.final.weight")));
 	ab.add(&m.d_fin_b, p.get("decoder.final.bias"));
 	c.arena = ab.upload();
-	c.gen_grid = 2 * c.num_sms;
+	c.gen_grid = 3 * c.num_sms;  // 80 registers x 256 threads: three CTAs per SM
 	// one scratch area per pipeline slot plus one for the device-pointer entry points (slot index kSlots)
 	CUDA_TRY(cudaMalloc(&c.gen_scratch, (kSlots + 1) * vqvdb::generic_scratch_floats(c.gen_grid) * sizeof(float)));
 	c.generic = true;
