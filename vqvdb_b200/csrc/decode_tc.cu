@@ -363,12 +363,22 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 		uint32_t* s_idx = reinterpret_cast<uint32_t*>(scratch + 160);  // 16 words
 		const float* s_finw = reinterpret_cast<const float*>(smem + kOffFinW);
 		const int tl = wk.wil * 32 + lane;  // thread index within the leaf, 0..63 (== pos)
+		long long ep[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // kProf only: cycles per epilogue section of this thread
+		long long ep0 = prof_clock<kProf>();
+		auto lap = [&](int slot) {
+			if (kProf) {
+				const long long c = prof_clock<kProf>();
+				ep[slot] += c - ep0;
+				ep0 = c;
+			}
+		};
 
 		for (int64_t g = 0; g < my_groups; ++g) {
 			const int64_t grp = blockIdx.x + g * gridDim.x;
 			const int64_t leaf = grp * kLeavesPerCta + wk.leaf_slot;
 			const bool leaf_ok = leaf < n_leaves;
 
+			lap(7);
 			// ---- gather: Q[pos][0..127] = codebook_bf16[idx[pos]] (64 threads per leaf; spare slots decode code 0) ----
 			if (tl < 16) s_idx[tl] = leaf_ok ? __ldcs(reinterpret_cast<const uint32_t*>(indices + leaf * 64) + tl) : 0u;
 			named_bar_sync(1 + wk.leaf_slot, 64);
@@ -385,9 +395,11 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 			named_bar_sync(1 + wk.leaf_slot, 64);
 
 			float mean[8], rstd[8];
+			lap(0);
 			// ---- stem.0 (128->64) ; stem.1 GroupNorm + ReLU -> x ; gn1 + ReLU -> conv1 input ----
 			stage_conv<2, kProf>(wk, a_base);
 			wait_accumulator<kProf>(wk);  // all stem MMAs done => every read of Q is done too
+			lap(6);
 			gn_stats_from_tmem(wk, w.stem_b, exch, mean, rstd);
 			{
 				float st[16];
@@ -432,9 +444,11 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 			tc_fence_before();
 			named_bar_sync(1 + wk.leaf_slot, 64);  // both warps' rows of the conv input are in place
 
+			lap(1);
 			// ---- res conv1 ; gn2 + ReLU -> conv2 input ----
 			stage_conv<1, kProf>(wk, a_base);
 			wait_accumulator<kProf>(wk);
+			lap(6);
 			gn_stats_from_tmem(wk, w.res.c1_b, exch, mean, rstd);
 #pragma unroll
 			for (int half = 0; half < 2; ++half) {
@@ -450,9 +464,11 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 			tc_fence_before();
 			named_bar_sync(1 + wk.leaf_slot, 64);
 
+			lap(2);
 			// ---- res conv2 ; x + 0.1 * (.) ; ChannelAttention(64) -> up_conv input ----
 			stage_conv<1, kProf>(wk, a_base);
 			wait_accumulator<kProf>(wk);
+			lap(6);
 			{
 				// x' = x + 0.1 (acc + b), written back into this thread's x row
 #pragma unroll
@@ -518,10 +534,12 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 			float out[8];
 #pragma unroll
 			for (int j = 0; j < 8; ++j) out[j] = 0.f;
+			lap(3);
 #pragma unroll 1
 			for (int np = 0; np < 4; ++np) {
 				stage_conv<1, kProf>(wk, a_base);
 				wait_accumulator<kProf>(wk);
+				lap(6);
 				// channel c = np*64 + cc = oc*8 + rd*4 + rh*2 + rw  ->  oc_local = cc>>3, (rd, rh, rw) = bits of cc&7
 				// P[oc_local][(2d+rd)][(2h+rh)][(2w+rw)] bf16 in the x region (8 KB per leaf)
 #pragma unroll
@@ -538,6 +556,7 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 				}
 				tc_fence_before();
 				named_bar_sync(1 + wk.leaf_slot, 64);
+				lap(4);
 				{
 					const int D = tl >> 3, H = tl & 7;
 #pragma unroll 1
@@ -577,6 +596,7 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 					}
 				}
 				named_bar_sync(1 + wk.leaf_slot, 64);  // all reads of this pass's P are done before the next pass overwrites it
+				lap(5);
 			}
 
 			// ---- sigmoid + store: one 32-byte row segment per thread ----
@@ -593,6 +613,11 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 		if (kProf && tap_out) {
 			float* o = tap_out + ((size_t)blockIdx.x * kThreads + threadIdx.x) * 4;
 			o[0] = (float)wk.t_wait; o[1] = (float)wk.t_stage; o[2] = (float)wk.t_acc; o[3] = 0.f;
+			if (threadIdx.x == 0) {  // epilogue sections of thread 0, behind the per-thread records
+				float* e = tap_out + (size_t)gridDim.x * kThreads * 4 + (size_t)blockIdx.x * 8;
+#pragma unroll
+				for (int i = 0; i < 8; ++i) e[i] = (float)ep[i];
+			}
 		}
 	}
 
