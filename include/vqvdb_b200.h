@@ -56,7 +56,8 @@ typedef enum vqvdb_b200_decode_precision {
 	VQVDB_B200_DECODE_DEFAULT = 0, /* fastest path that meets the 0.1 dB PSNR budget */
 	VQVDB_B200_DECODE_FP32 = 1,    /* CUDA-core fp32 path (bring-up / checking) */
 	VQVDB_B200_DECODE_BF16_TC = 2, /* tcgen05.mma + TMEM accumulators: bf16 operands, fp32 accumulation */
-	VQVDB_B200_DECODE_BF16_MMA = 3 /* same arithmetic on the legacy warp-level mma.sync path */
+	VQVDB_B200_DECODE_BF16_MMA = 3, /* same arithmetic on the legacy warp-level mma.sync path */
+	VQVDB_B200_DECODE_BF16_TC2 = 4  /* tcgen05.mma, kw taps concatenated along N (N = 192): a third of the operand staging */
 } vqvdb_b200_decode_precision;
 #define VQVDB_B200_DECODE_DEFAULT_KIND VQVDB_B200_DECODE_BF16_TC
 

@@ -50,4 +50,11 @@ cudaError_t launch_decode_tc(const DecoderMmaWeights& w, const uint8_t* dev_indi
                              float* dev_voxels, int num_sms, cudaStream_t stream, int tap_stage = -1,
                              float* tap_out = nullptr);
 
+// Second-generation tcgen05 decoder (decode_tc2.cu): kw taps concatenated along N (one A unit per (kd, kh) pair, N = 192),
+// eight worker warps per 128-row tile; same weights, same arguments.
+cudaError_t configure_decode_tc2();
+cudaError_t launch_decode_tc2(const DecoderMmaWeights& w, const uint8_t* dev_indices, int64_t n_leaves,
+                              float* dev_voxels, int num_sms, cudaStream_t stream, int tap_stage = -1,
+                              float* tap_out = nullptr);
+
 }  // namespace vqvdb
