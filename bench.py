@@ -29,6 +29,14 @@ if REPO not in sys.path:
 # Algorithmic work per leaf: dense MACs x 2.
 FLOP_ENCODE = 26.40e6 + 4.19e6      # encoder + VQ distance GEMM
 FLOP_DECODE = 114.14e6
+# decoder with the linear tail folded (decode_mma.cuh): stem 28.31 + res convs 2 x 14.16 + folded tail conv 14.16 MFLOP;
+# what the tensor pipe actually executes on the *_fold path (the reference's algorithm stays the yardstick for `achieved`)
+FLOP_DECODE_FOLDED = (128 * 64 + 3 * 64 * 64) * 27 * 64 * 2.0
+
+
+def dec_kernel_name(path: str) -> str:
+    return {"bf16_tcgen05_n192_fold": "decode_tc2_kernel<fold>", "bf16_tcgen05_n192": "decode_tc2_kernel", "bf16_tcgen05": "decode_tc_kernel",
+            "bf16_mma": "decode_mma_kernel"}.get(path, "decode_fp32_kernel")
 BYTES_ENCODE = 2048 + 64
 BYTES_DECODE = 64 + 2048
 
@@ -362,6 +370,10 @@ def main():
         enc_tf = FLOP_ENCODE * L / (enc_ms / 1e3) / 1e12
         dec_tf = FLOP_DECODE * L / (dec_ms / 1e3) / 1e12
         enc_tc = codec.encode_path == "fp16x2_tcgen05"
+        dec_tc = codec.decode_path.startswith("bf16_tcgen05")
+        dec_peak = peak if dec_tc else hmma_peak if tensor_path else ffma_peak
+        dec_issued_flop = FLOP_DECODE_FOLDED if codec.decode_path.endswith("_fold") else FLOP_DECODE
+        dec_issued_tf = dec_issued_flop * L / (dec_ms / 1e3) / 1e12
         # tensor-core encoder: every conv is three fp16 products (hi*hi, hi*lo, lo*hi) and the VQ scores one bf16 product,
         # pre.0 stays on FFMA: MACs issued to the tensor pipe per leaf = 3 * (13 197 824 - 221 184) + 2 097 152
         enc_issued_tf = (3 * (13197824 - 221184) + 2097152) * 2 * L / (enc_ms / 1e3) / 1e12
@@ -374,13 +386,16 @@ def main():
                 "issued_tflops": enc_issued_tf if enc_tc else enc_tf,
                 "frac_of_bf16_tensor_peak": enc_tf / peak, "algorithmic_mflop_per_leaf": FLOP_ENCODE / 1e6,
                 "hbm_gbs": BYTES_ENCODE * L / (enc_ms / 1e3) / 1e9},
-            ("decode_tc_kernel" if codec.decode_path == "bf16_tcgen05" else "decode_mma_kernel" if tensor_path else "decode_fp32_kernel"): {"ms": dec_ms, "share_of_step": dec_ms / (enc_ms + dec_ms), "achieved_tflops": dec_tf,
-                                  "pipe": ("tensor (tcgen05.mma bf16, TMEM accumulators)" if codec.decode_path == "bf16_tcgen05" else
-                                           "tensor (mma.sync bf16)" if tensor_path else "fp32 FFMA"),
-                                  "pipe_peak_tflops": (peak if codec.decode_path == "bf16_tcgen05" else hmma_peak if tensor_path else ffma_peak),
-                                  "frac_of_pipe_peak": dec_tf / (peak if codec.decode_path == "bf16_tcgen05" else hmma_peak if tensor_path else ffma_peak),
-                                  "frac_of_bf16_tensor_peak": dec_tf / peak, "algorithmic_mflop_per_leaf": FLOP_DECODE / 1e6,
-                                  "hbm_gbs": BYTES_DECODE * L / (dec_ms / 1e3) / 1e9},
+            dec_kernel_name(codec.decode_path): {
+                "ms": dec_ms, "share_of_step": dec_ms / (enc_ms + dec_ms), "achieved_tflops": dec_tf,
+                "pipe": ("tensor (tcgen05.mma bf16, TMEM accumulators)" if dec_tc else "tensor (mma.sync bf16)" if tensor_path else "fp32 FFMA"),
+                "pipe_peak_tflops": dec_peak,
+                # folded tail: up_conv -> PixelShuffle3D -> final run as one 64->64 conv, so fewer flops are ISSUED than the
+                # reference's algorithm counts; the pipe fraction uses the issued ones
+                "issued_tflops": dec_issued_tf, "issued_mflop_per_leaf": dec_issued_flop / 1e6,
+                "frac_of_pipe_peak": dec_issued_tf / dec_peak,
+                "frac_of_bf16_tensor_peak": dec_tf / peak, "algorithmic_mflop_per_leaf": FLOP_DECODE / 1e6,
+                "hbm_gbs": BYTES_DECODE * L / (dec_ms / 1e3) / 1e9},
         }
         line = {
             "metric": "leaves_per_sec_encode_decode", "value": value, "unit": "leaves/s",

@@ -57,9 +57,12 @@ typedef enum vqvdb_b200_decode_precision {
 	VQVDB_B200_DECODE_FP32 = 1,    /* CUDA-core fp32 path (bring-up / checking) */
 	VQVDB_B200_DECODE_BF16_TC = 2, /* tcgen05.mma + TMEM accumulators: bf16 operands, fp32 accumulation */
 	VQVDB_B200_DECODE_BF16_MMA = 3, /* same arithmetic on the legacy warp-level mma.sync path */
-	VQVDB_B200_DECODE_BF16_TC2 = 4  /* tcgen05.mma, kw taps concatenated along N (N = 192): a third of the operand staging */
+	VQVDB_B200_DECODE_BF16_TC2 = 4, /* tcgen05.mma, kw taps concatenated along N (N = 192): a third of the operand staging */
+	VQVDB_B200_DECODE_BF16_TC2_FOLD = 5 /* the same, with up_conv -> PixelShuffle3D -> final folded on the host into one
+	                                      * 64 -> 64 convolution + an 8-term gather per voxel (exact algebra, zero padding
+	                                      * at both resolutions included; weights folded in double, rounded to bf16 once) */
 } vqvdb_b200_decode_precision;
-#define VQVDB_B200_DECODE_DEFAULT_KIND VQVDB_B200_DECODE_BF16_TC
+#define VQVDB_B200_DECODE_DEFAULT_KIND VQVDB_B200_DECODE_BF16_TC2_FOLD
 
 /* Encoder arithmetic.  Both paths are fp32-faithful (index parity with the reference is a bit-exactness requirement):
  * the tensor-core path splits every operand into two fp16 planes (22 significant bits, three products, fp32

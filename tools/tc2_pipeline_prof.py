@@ -11,7 +11,9 @@ import torch  # noqa: E402
 from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 4 * 50
-codec = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, decode_precision="bf16_tc2"), BackendType.B200)
+prec = sys.argv[2] if len(sys.argv) > 2 else "bf16_tc2_fold"
+upg = 45 if prec.endswith("fold") else 72
+codec = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, decode_precision=prec), BackendType.B200)
 idx = torch.randint(0, 256, (n, 4, 4, 4), dtype=torch.uint8, device="cuda")
 vox = torch.empty((n, 1, 8, 8, 8), dtype=torch.float32, device="cuda")
 threads = 608
@@ -24,10 +26,10 @@ pall = prof.cpu().numpy()
 p = pall[:148 * threads * 4].reshape(148, threads, 4)
 groups = n / 4 / 148
 ep = pall[148 * threads * 4:].reshape(148, 8).mean(axis=0) / groups
-units = groups * 72
+units = groups * upg
 w = p[:, :512, :]
 iss = p[:, 512:576:32, :]
-print("groups per CTA: %.0f (4 leaves each, 72 units)" % groups)
+print("%s: groups per CTA: %.0f (4 leaves each, %d units)" % (prec, groups, upg))
 print("worker per unit: wait a_empty %.0f  stage %.0f  | wait d_full per group (7 passes) %.0f" % (
     w[..., 0].mean() / units, w[..., 1].mean() / units, w[..., 2].mean() / groups))
 print("issuer per unit: wait w_full %.0f  wait a_full %.0f  issue %.0f  total %.0f" % (

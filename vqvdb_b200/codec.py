@@ -165,7 +165,7 @@ class Tensor:
         return self.buffer
 
 
-_PRECISION = {"default": 0, "fp32": 1, "bf16_tc": 2, "bf16_mma": 3, "bf16_tc2": 4}
+_PRECISION = {"default": 0, "fp32": 1, "bf16_tc": 2, "bf16_mma": 3, "bf16_tc2": 4, "bf16_tc2_fold": 5}
 _ENC_PRECISION = {"default": 0, "fp32": 1, "fp16x2_tc": 2}
 
 

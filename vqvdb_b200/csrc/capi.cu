@@ -214,11 +214,17 @@ void upload_float_model(vqvdb_b200_codec& c, const WeightPack& p) {
 	ab.add(&d.up_b, p.get("decoder.up_conv.bias"));
 	ab.add(&d.fin_w, vqvdb::transpose_conv_weight(p.get("decoder.final.weight")));
 	ab.add(&d.fin_b, p.get("decoder.final.bias"));
+	{
+		std::vector<float> wg, bg;
+		vqvdb::build_decoder_fold(p, wg, bg);
+		ab.add(&c.dec_mma.fold_b, bg);
+	}
 	c.arena = ab.upload();
 
 	// tensor-core decoder: bf16 unit stream + bf16 codebook; fp32 vectors are shared with the fp32 path.
 	// The encoder's VQ shortlist pass reads the codebook as 8 more bf16 units from the same allocation.
 	const std::vector<uint8_t> units = vqvdb::build_decoder_units(p);
+	if (units.size() != (size_t)vqvdb::kDecUnitsWithFold * 8192) throw std::logic_error("decoder unit stream size mismatch");
 	const std::vector<uint16_t> cb = vqvdb::build_codebook_bf16(p);
 	const std::vector<uint8_t> cb_units = vqvdb::build_codebook_units(p);
 	CUDA_TRY(cudaMalloc(&c.mma_arena, units.size() + cb.size() * 2 + cb_units.size()));
@@ -399,7 +405,7 @@ void launch_decode(vqvdb_b200_codec& c, const uint8_t* d_idx, int64_t n, float* 
 		if (n > 0) c.launches.fetch_add(1, std::memory_order_relaxed);
 		return;
 	}
-	if (c.decode_kind == 4) CUDA_TRY(vqvdb::launch_decode_tc2(c.dec_mma, d_idx, n, d_vox, c.num_sms, st));
+	if (c.decode_kind >= 4) CUDA_TRY(vqvdb::launch_decode_tc2(c.dec_mma, d_idx, n, d_vox, c.num_sms, st, c.decode_kind == 5));
 	else if (c.decode_kind == 2) CUDA_TRY(vqvdb::launch_decode_tc(c.dec_mma, d_idx, n, d_vox, c.num_sms, st));
 	else if (c.decode_kind == 3) CUDA_TRY(vqvdb::launch_decode_mma(c.dec_mma, d_idx, n, d_vox, c.num_sms, st));
 	else CUDA_TRY(vqvdb::launch_decode_fp32(c.dec, d_idx, n, d_vox, c.num_sms, st));
@@ -476,14 +482,14 @@ int vqvdb_b200_create(const vqvdb_b200_config* cfg, vqvdb_b200_codec** out) {
 		} catch (const std::exception& e) {
 			return fail(nullptr, VQVDB_B200_ERR_BAD_WEIGHTS, e.what());
 		}
-		if (conf.decode_precision > VQVDB_B200_DECODE_BF16_TC2)
+		if (conf.decode_precision > VQVDB_B200_DECODE_BF16_TC2_FOLD)
 			return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "unknown decode_precision");
 		c->decode_kind = conf.decode_precision == VQVDB_B200_DECODE_DEFAULT ? (int)VQVDB_B200_DECODE_DEFAULT_KIND : (int)conf.decode_precision;
 		if (conf.encode_precision > VQVDB_B200_ENCODE_FP16X2_TC)
 			return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "unknown encode_precision");
 		c->encode_kind = conf.encode_precision == VQVDB_B200_ENCODE_DEFAULT ? (int)VQVDB_B200_ENCODE_DEFAULT_KIND : (int)conf.encode_precision;
 		c->encode_path = c->generic ? "fp32_generic" : c->encode_kind == 2 ? "fp16x2_tcgen05" : "fp32";
-		c->decode_path = c->generic ? "fp32_generic" : c->decode_kind == 4 ? "bf16_tcgen05_n192" : c->decode_kind == 2 ? "bf16_tcgen05" : c->decode_kind == 3 ? "bf16_mma" : "fp32";
+		c->decode_path = c->generic ? "fp32_generic" : c->decode_kind == 5 ? "bf16_tcgen05_n192_fold" : c->decode_kind == 4 ? "bf16_tcgen05_n192" : c->decode_kind == 2 ? "bf16_tcgen05" : c->decode_kind == 3 ? "bf16_mma" : "fp32";
 		CUDA_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
 		CUDA_TRY(vqvdb::configure_encode_fp32());
 		CUDA_TRY(vqvdb::configure_encode_tc());
@@ -628,7 +634,7 @@ int vqvdb_b200_debug_decode_tap(vqvdb_b200_codec* c, const uint8_t* dev_indices,
 	try {
 		CUDA_TRY(cudaSetDevice(c->device));
 		if (c->decode_kind == 3) CUDA_TRY(vqvdb::launch_decode_mma(c->dec_mma, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
-		else if (c->decode_kind == 4) CUDA_TRY(vqvdb::launch_decode_tc2(c->dec_mma, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
+		else if (c->decode_kind >= 4) CUDA_TRY(vqvdb::launch_decode_tc2(c->dec_mma, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, c->decode_kind == 5, stage, dev_tap));
 		else CUDA_TRY(vqvdb::launch_decode_tc(c->dec_mma, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
 	} catch (const std::exception& e) {
 		return translate(c, e);

@@ -18,7 +18,18 @@ namespace vqvdb {
 //   res conv1 27 taps                                27
 //   res conv2 27 taps                                27
 //   up_conv   4 output passes (64 ch) x 27 taps     108
+//   folded tail 27 taps (decode_tc2.cu, see below)   27
 constexpr int kDecUnitsTotal = 216;
+constexpr int kDecUnitsWithFold = kDecUnitsTotal + 27;
+// The decoder's tail up_conv -> PixelShuffle3D(2) -> final has no nonlinearity in it (python/VQVAE_v2.py:272-275), so it
+// is ONE linear map of the attention output a[64][4^3], zero padding at both resolutions included: for output voxel
+// V = 2p + r (p in the 4^3 grid, r in {0,1}^3) every tap s2 of `final` reads the shuffled volume at U = V + s2, i.e. the
+// up_conv output of cell p + e, e in {-1, 0, +1}^3 (per axis e = 0 or the one neighbour on r's side), and U is inside
+// the 8^3 volume exactly when p + e is inside the 4^3 grid.  Grouping the taps by e gives
+//     out[2p + r] = sigmoid(final.bias + sum_{eps in {0,1}^3, p + e(r, eps) in grid} G[p + e(r, eps)][r*8 + eps])
+//     G = conv3x3x3(a; Wg) + bg,   Wg[r*8 + eps][ci][s1] = sum_{s2 -> (r, eps)} sum_oc final.w[oc][s2] * up.w[oc*8 + rU(r, s2)][ci][s1]
+// a 64 -> 64 convolution on the 4^3 grid (a quarter of up_conv's MACs) followed by an 8-term gather per voxel; the
+// weights are folded in double precision on the host (build_decoder_fold) and rounded to bf16 once.
 
 struct DecoderMmaWeights {
 	const uint8_t* units;             // kDecUnitsTotal * 8192 bytes, consumption order
@@ -28,10 +39,12 @@ struct DecoderMmaWeights {
 	const float *fc0, *fc2;
 	const float *up_b;
 	const float *fin_w, *fin_b;       // decoder.final transposed [32][27]
+	const float* fold_b;              // bias of the folded tail conv [64] (r*8 + eps)
 };
 
 // Builds the unit stream and the bf16 codebook on the host (round-to-nearest-even).
 std::vector<uint8_t> build_decoder_units(const WeightPack& pack);
+void build_decoder_fold(const WeightPack& pack, std::vector<float>& wg /*[64][64][27]*/, std::vector<float>& bg /*[64]*/);
 std::vector<uint16_t> build_codebook_bf16(const WeightPack& pack);
 // The codebook as 8 weight units [64 codes][64 dims] (code group major, then dim half) for the encoder's
 // tensor-core VQ shortlist pass: same tile format as the decoder's units.
@@ -53,8 +66,9 @@ cudaError_t launch_decode_tc(const DecoderMmaWeights& w, const uint8_t* dev_indi
 // Second-generation tcgen05 decoder (decode_tc2.cu): kw taps concatenated along N (one A unit per (kd, kh) pair, N = 192),
 // eight worker warps per 128-row tile; same weights, same arguments.
 cudaError_t configure_decode_tc2();
+// fold = true runs the tail as the folded conv + gather described above (45 units per group instead of 72).
 cudaError_t launch_decode_tc2(const DecoderMmaWeights& w, const uint8_t* dev_indices, int64_t n_leaves,
-                              float* dev_voxels, int num_sms, cudaStream_t stream, int tap_stage = -1,
+                              float* dev_voxels, int num_sms, cudaStream_t stream, bool fold, int tap_stage = -1,
                               float* tap_out = nullptr);
 
 }  // namespace vqvdb

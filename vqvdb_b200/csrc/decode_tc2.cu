@@ -39,7 +39,9 @@ constexpr int kThreads = (kWorkWarps + kCtrlWarps) * 32;   // 608
 constexpr int kStages = 4;
 constexpr uint32_t kSrcUnitBytes = 8192;                   // one [64 n][64 k] tile of the weight stream
 constexpr uint32_t kUnitBytes = 3 * kSrcUnitBytes;         // [3 kw x 64 n][64 k]
-constexpr int kUnitsPerGroup = 18 + 9 + 9 + 4 * 9;         // stem (2 input halves), res conv1, res conv2, 4 up_conv passes
+// units per group of leaves: stem (2 input halves), res conv1, res conv2, then either the 4 up_conv passes or the
+// folded tail conv (decode_mma.cuh: up_conv -> PixelShuffle3D -> final as one 64 -> 64 conv + an 8-term gather)
+template <bool kFold> __host__ __device__ constexpr int units_per_group() { return kFold ? 18 + 9 + 9 + 9 : 18 + 9 + 9 + 4 * 9; }
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kDCols = 192;                           // tile t accumulator: columns [t*192, t*192 + 192)
 constexpr uint32_t kColA = kTiles * kDCols;                // tile t A buffers: columns 384 + t*64 + buf*32
@@ -50,7 +52,7 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((192u >> 3) <<
 // per-channel parameters staged in shared memory (float offsets)
 namespace par {
 constexpr int stem_b = 0, stem_gn_w = 64, stem_gn_b = 128, gn1_w = 192, gn1_b = 256, c1_b = 320, gn2_w = 384, gn2_b = 448,
-              c2_b = 512, up_b = 576, fin_w = 832, fin_b = 1696, fc0 = 1700, fc2 = fc0 + 16 * 72, total = fc2 + 64 * 17;
+              c2_b = 512, up_b = 576, fin_w = 832, fin_b = 1696, fc0 = 1700, fc2 = fc0 + 16 * 72, fold_b = fc2 + 64 * 17, total = fold_b + 64;
 constexpr int fc0_pitch = 72, fc2_pitch = 17;
 }
 
@@ -285,10 +287,11 @@ __device__ __forceinline__ float column_sums(float (&v)[32], int lane) {
 	return v[0];
 }
 
-template <bool kProf>
+template <bool kFold, bool kProf>
 __global__ void __launch_bounds__(kThreads, 1)
 decode_tc2_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices, int64_t n_leaves, float* __restrict__ voxels,
                   int tap_stage, float* __restrict__ tap_out) {
+	constexpr int kUnitsPerGroup = units_per_group<kFold>();
 	extern __shared__ __align__(1024) uint8_t smem[];
 	const uint32_t s_base = smem_u32(smem);
 	const uint32_t ring = s_base + kOffRing;
@@ -309,6 +312,7 @@ decode_tc2_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices
 		s_par[par::gn2_w + i] = __ldg(w.res.gn2_w + i);
 		s_par[par::gn2_b + i] = __ldg(w.res.gn2_b + i);
 		s_par[par::c2_b + i] = __ldg(w.res.c2_b + i);
+		s_par[par::fold_b + i] = __ldg(w.fold_b + i);
 	}
 	for (int i = threadIdx.x; i < 256; i += kThreads) s_par[par::up_b + i] = __ldg(w.up_b + i);
 	for (int i = threadIdx.x; i < 864; i += kThreads) s_par[par::fin_w + i] = __ldg(w.fin_w + i);
@@ -403,7 +407,8 @@ decode_tc2_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices
 						tma_load_1d(dst + kw * kSrcUnitBytes, w.units + (size_t)((pair * 3 + kw) * 2 + half) * kSrcUnitBytes, kSrcUnitBytes,
 						            bar_w_full(bars, s));
 				} else {
-					tma_load_1d(dst, w.units + (size_t)(54 + (u - 18) * 3) * kSrcUnitBytes, kUnitBytes, bar_w_full(bars, s));
+					const uint32_t src = (kFold && u >= 36) ? (uint32_t)kDecUnitsTotal + (u - 36) * 3 : 54 + (u - 18) * 3;
+					tma_load_1d(dst, w.units + (size_t)src * kSrcUnitBytes, kUnitBytes, bar_w_full(bars, s));
 				}
 			}
 		}
@@ -569,6 +574,53 @@ decode_tc2_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices
 			half_bar(wk);
 			lap(3);
 
+			if constexpr (kFold) {
+				// ---- folded tail: G = conv(a; Wg) + bg, then out[2p + r] = sigmoid(fin_b + sum over the in-grid cells
+				// p + e(r, eps) of G[p + e][r*8 + eps]) ----
+				stage_conv<1, kProf>(wk, a_base);
+				wait_accumulator<kProf>(wk);  // all reads of the conv input are done: the whole leaf region is free
+				lap(6);
+				load_conv32(wk, v);
+				// G as fp32 [64 pos][64 ch] over the leaf region (256-B rows; 16-B chunks swizzled by pos & 7 inside each half row)
+#pragma unroll
+				for (int q = 0; q < 8; ++q) {
+					const uint32_t a = a_base + (uint32_t)wk.pos * 256 + ((((uint32_t)wk.chalf * 8u) | ((uint32_t)q ^ ((uint32_t)wk.pos & 7u))) << 4);
+					sts128(a, __float_as_uint(v[4 * q] + s_par[par::fold_b + c0 + 4 * q]), __float_as_uint(v[4 * q + 1] + s_par[par::fold_b + c0 + 4 * q + 1]),
+					       __float_as_uint(v[4 * q + 2] + s_par[par::fold_b + c0 + 4 * q + 2]), __float_as_uint(v[4 * q + 3] + s_par[par::fold_b + c0 + 4 * q + 3]));
+				}
+				leaf_bar(wk);
+				lap(4);
+				// this thread: output row R = pos (D = R>>3, H = R&7), voxels W = chalf*4 .. +3
+				{
+					const int D = wk.pos >> 3, H = wk.pos & 7;
+					const int rd = D & 1, rh = H & 1, pd = D >> 1, ph = H >> 1;
+					const float fb = s_par[par::fin_b];
+					float o[4];
+#pragma unroll
+					for (int j = 0; j < 4; ++j) {
+						const int rw = j & 1, pw = wk.chalf * 2 + (j >> 1);
+						const int r = rd * 4 + rh * 2 + rw;
+						float sum = fb;
+#pragma unroll
+						for (int eps = 0; eps < 8; ++eps) {
+							const int ed = (eps >> 2) & 1, eh = (eps >> 1) & 1, ew = eps & 1;
+							const int qd = pd + (ed ? (rd ? 1 : -1) : 0), qh = ph + (eh ? (rh ? 1 : -1) : 0), qw = pw + (ew ? (rw ? 1 : -1) : 0);
+							const bool ok = (unsigned)qd < 4u && (unsigned)qh < 4u && (unsigned)qw < 4u;
+							const int row = qd * 16 + qh * 4 + qw;
+							const int chunk = r * 2 + ed;  // channel r*8 + eps -> 16-byte chunk (4 floats)
+							const uint32_t a = a_base + (uint32_t)row * 256 + ((uint32_t)((chunk & 8) | ((chunk & 7) ^ (row & 7))) << 4) + (uint32_t)(eh * 2 + ew) * 4;
+							if (ok) {
+								float g;
+								asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g) : "r"(a));
+								sum += g;
+							}
+						}
+						o[j] = sigmoid_f(sum);
+					}
+					if (leaf_ok) __stcs(reinterpret_cast<float4*>(voxels + leaf * 512 + wk.pos * 8 + wk.chalf * 4), make_float4(o[0], o[1], o[2], o[3]));
+				}
+				lap(5);
+			} else {
 			// ---- up_conv in four 64-channel passes ; PixelShuffle3D on the store ; final conv accumulated on FFMA ----
 			// Pass np produces up channels np*64 + cc, cc = ocl*8 + rd*4 + rh*2 + rw: eight complete planes oc = np*8 + ocl of
 			// the 8^3 volume, P[ocl][2d+rd][2h+rh][2w+rw] bf16 in the x region.  This thread converts channels c0 .. c0+31
@@ -652,6 +704,7 @@ decode_tc2_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices
 				__stcs(dst, o0);
 				__stcs(dst + 1, o1);
 			}
+			}  // !kFold
 		}
 		lap(7);
 		if (kProf && tap_out) {
@@ -674,20 +727,25 @@ decode_tc2_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices
 }  // namespace
 
 cudaError_t configure_decode_tc2() {
-	cudaError_t e = cudaFuncSetAttribute(decode_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-	if (e != cudaSuccess) return e;
-	return cudaFuncSetAttribute(decode_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+	cudaError_t e = cudaFuncSetAttribute(decode_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+	return e;
 }
 
 cudaError_t launch_decode_tc2(const DecoderMmaWeights& w, const uint8_t* dev_indices, int64_t n_leaves, float* dev_voxels,
-                              int num_sms, cudaStream_t stream, int tap_stage, float* tap_out) {
+                              int num_sms, cudaStream_t stream, bool fold, int tap_stage, float* tap_out) {
 	if (n_leaves <= 0) return cudaSuccess;
 	const int64_t groups = (n_leaves + kLeavesPerCta - 1) / kLeavesPerCta;
 	const int grid = (int)(groups < (int64_t)num_sms ? groups : (int64_t)num_sms);
-	if (tap_stage == 100)  // timing instrumentation: 4 floats per thread + 8 per CTA (tools/tc2_pipeline_prof.py)
-		decode_tc2_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, -1, tap_out);
-	else
-		decode_tc2_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, tap_stage, tap_out);
+	if (tap_stage == 100) {  // timing instrumentation: 4 floats per thread + 8 per CTA (tools/tc2_pipeline_prof.py)
+		if (fold) decode_tc2_kernel<true, true><<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, -1, tap_out);
+		else decode_tc2_kernel<false, true><<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, -1, tap_out);
+	} else {
+		if (fold) decode_tc2_kernel<true, false><<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, tap_stage, tap_out);
+		else decode_tc2_kernel<false, false><<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, tap_stage, tap_out);
+	}
 	return cudaGetLastError();
 }
 
