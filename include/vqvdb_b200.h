@@ -138,13 +138,19 @@ VQVDB_B200_API int vqvdb_b200_peer_buffer_close(vqvdb_b200_codec* codec, void* d
 
 /* Kernel launches issued by this codec since creation (bench.py's gpu_launches). */
 VQVDB_B200_API uint64_t vqvdb_b200_kernel_launches(const vqvdb_b200_codec* codec);
-/* Name of the decode path actually in use: "fp32", "bf16_tcgen05" or "bf16_mma". */
+/* Name of the decode path actually in use: "fp32", "bf16_tcgen05_n192_fold", "bf16_tcgen05_n192", "bf16_tcgen05" or "bf16_mma". */
 VQVDB_B200_API const char* vqvdb_b200_decode_path(const vqvdb_b200_codec* codec);
 
 /* Bring-up aid for the tensor-core decoder: runs it and also writes the fp32 activation after stage
  * {0: stem+GroupNorm+ReLU, 1: residual block, 2: channel attention} as [n][64 ch][64 pos] to dev_tap. */
 VQVDB_B200_API int vqvdb_b200_debug_decode_tap(vqvdb_b200_codec* codec, const uint8_t* dev_indices, int64_t n_leaves,
                                                int stage, float* dev_tap, float* dev_voxels, void* cuda_stream);
+
+/* Host-only checker hook (no device needed): the folded decoder tail of the weight pack at `weights_path` (NULL or ""
+ * = the embedded pack) — conv weights [64 (r*8+eps)][64 cin][27 taps] and bias [64] in fp32, exactly what the
+ * *_FOLD decode path rounds to bf16 (see VQVDB_B200_DECODE_BF16_TC2_FOLD; tests/test_decoder_fold.py compares it with
+ * up_conv -> PixelShuffle3D -> final of python/VQVAE_v2.py:266-275 evaluated layer by layer). */
+VQVDB_B200_API int vqvdb_b200_debug_fold_decoder_tail(const char* weights_path, float* weights_out, float* bias_out);
 
 /* Name of the encode path in use: "fp32" or "fp16x2_tcgen05". */
 VQVDB_B200_API const char* vqvdb_b200_encode_path(const vqvdb_b200_codec* codec);

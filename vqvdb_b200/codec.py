@@ -25,7 +25,7 @@ EXPORTS = [  # every symbol include/vqvdb_b200.h declares
     "vqvdb_b200_decode_path", "vqvdb_b200_last_error", "vqvdb_b200_version", "vqvdb_b200_debug_decode_tap",
     "vqvdb_b200_encode_path", "vqvdb_b200_debug_encode_tap",
     "vqvdb_b200_peer_buffer_create", "vqvdb_b200_peer_buffer_open", "vqvdb_b200_peer_buffer_close",
-    "vqvdb_b200_convert_onnx",
+    "vqvdb_b200_convert_onnx", "vqvdb_b200_debug_fold_decoder_tail",
 ]
 
 
@@ -84,6 +84,8 @@ def load_library() -> C.CDLL:
     L.vqvdb_b200_peer_buffer_close.restype = C.c_int
     L.vqvdb_b200_convert_onnx.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
     L.vqvdb_b200_convert_onnx.restype = C.c_int
+    L.vqvdb_b200_debug_fold_decoder_tail.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p]
+    L.vqvdb_b200_debug_fold_decoder_tail.restype = C.c_int
     L.vqvdb_b200_synchronize.argtypes = [C.c_void_p]
     L.vqvdb_b200_kernel_launches.argtypes = [C.c_void_p]
     L.vqvdb_b200_kernel_launches.restype = C.c_uint64
@@ -118,6 +120,19 @@ class OnnxModelPaths:
     """The reference's two-graph source (IVQVAECodec.hpp:29-33); only the initializers (weights) are read."""
     encoder: str
     decoder: str
+
+
+def fold_decoder_tail(weights_path: str = ""):
+    """The folded decoder tail (up_conv -> PixelShuffle3D -> final as one conv) the *_fold decode path uses:
+    (weights [64][64][3][3][3], bias [64]) as fp32 numpy arrays.  Host-only."""
+    import numpy as np
+    L = load_library()
+    w = np.empty((64, 64, 3, 3, 3), dtype=np.float32)
+    b = np.empty((64,), dtype=np.float32)
+    rc = L.vqvdb_b200_debug_fold_decoder_tail(os.fspath(weights_path).encode(), w.ctypes.data, b.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("vqvdb_b200_debug_fold_decoder_tail failed (%d): %s" % (rc, L.vqvdb_b200_last_error(None).decode()))
+    return w, b
 
 
 def convert_onnx(encoder_onnx: str, decoder_onnx: str, out_pack: str) -> None:

@@ -723,6 +723,22 @@ int vqvdb_b200_convert_onnx(const char* enc_path, const char* dec_path, const ch
 }
 
 uint64_t vqvdb_b200_kernel_launches(const vqvdb_b200_codec* c) { return c ? c->launches.load() : 0; }
+int vqvdb_b200_debug_fold_decoder_tail(const char* weights_path, float* weights_out, float* bias_out) {
+	if (!weights_out || !bias_out) return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "debug_fold_decoder_tail: null output");
+	try {
+		WeightPack pack;
+		if (weights_path && weights_path[0]) pack.load_file(weights_path);
+		else pack.parse(vqvdb::vqvdb_b200_embedded_pack, (size_t)(vqvdb::vqvdb_b200_embedded_pack_end - vqvdb::vqvdb_b200_embedded_pack));
+		std::vector<float> wg, bg;
+		vqvdb::build_decoder_fold(pack, wg, bg);
+		std::memcpy(weights_out, wg.data(), wg.size() * sizeof(float));
+		std::memcpy(bias_out, bg.data(), bg.size() * sizeof(float));
+	} catch (const std::exception& e) {
+		return fail(nullptr, VQVDB_B200_ERR_BAD_WEIGHTS, e.what());
+	}
+	return VQVDB_B200_OK;
+}
+
 const char* vqvdb_b200_decode_path(const vqvdb_b200_codec* c) { return c ? c->decode_path.c_str() : ""; }
 const char* vqvdb_b200_encode_path(const vqvdb_b200_codec* c) { return c ? c->encode_path.c_str() : ""; }
 
