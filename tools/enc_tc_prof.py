@@ -24,8 +24,8 @@ p = prof.cpu().numpy()
 leaves = n / 148.0
 names = ["stage next leaf (+ clear Y)", "pre.0 FFMA + GN pre.1", "gn1 + split -> A8", "wait conv1 MMA", "conv1 epilogue (GN, split)",
          "wait conv2 MMA", "conv2 epilogue (residual, -> Y)", "wait down MMA", "down epilogue (GN, -> H32)", "wait res32.c1 MMA",
-         "res32.c1 epilogue", "wait res32.c2 MMA", "res32.c2 epilogue + attention", "wait proj MMA", "proj epilogue (z, bf16)",
-         "wait VQ MMA", "VQ scores -> bounds, row minimum", "VQ shortlist + exact re-scoring", "VQ combine + store"]
+         "res32.c1 epilogue", "wait res32.c2 MMA", "res32.c2 epilogue + attention", "(proj: folded into the codebook)", "(proj epilogue: none)",
+         "wait VQ MMA", "VQ scores -> bounds, two smallest", "VQ decision (+ near-tie rows: z, shortlist, exact re-scoring)", "clear Y"]
 tot = 0.0
 for i, nm in enumerate(names):
     c = p[:, i].mean() / leaves

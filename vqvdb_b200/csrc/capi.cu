@@ -199,6 +199,12 @@ void upload_float_model(vqvdb_b200_codec& c, const WeightPack& p) {
 	ab.add(&e.emb_t, emb_t);
 	ab.add(&e.emb_sq, emb_sq);
 	ab.add(&e.emb_norm, emb_norm);
+	{
+		std::vector<float> fm, fesq, fnorm;
+		vqvdb::build_encoder_vq_fold(p, fm, fesq, fnorm);
+		ab.add(&e.fold_esq, fesq);
+		ab.add(&e.fold_norm, fnorm);
+	}
 	ab.add(&e.emb, emb);
 
 	auto& d = c.dec;

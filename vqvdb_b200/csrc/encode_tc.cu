@@ -26,11 +26,13 @@
 //   * the tensor core truncates its fp32 accumulator after every MMA (measured: a bias toward zero that grows with
 //     the chain length); the 64-step chain of the stride-2 conv is split over four accumulators added in the epilogue.
 //   * pre.0 (Cin = 1, K = 27) stays on FFMA in fp32 (raw voxel values are unbounded; it is 1.4 % of the MACs).
-//   * VQ: split-fp16 tensor-core scores for all 256 codes with a rigorous error bound (~5e-4), then exact fp32
-//     re-scoring of the shortlist with the reference's formula and tie-break — the two-stage scheme of encode_fp32.cu
-//     with a 500x tighter first stage, so the shortlist is a single code except at near-ties (~1 % of the rows).
+//   * proj + VQ: proj feeds nothing but the codebook distances, so it is folded into the codebook on the host
+//     (encode_tc_stream.hpp): split-fp16 tensor-core scores x.M_k for all 256 codes straight from the attention output
+//     (K = 32 instead of 128 + the proj GEMM), with a rigorous error bound, then — only for rows whose shortlist holds
+//     more than one code (near-ties, ~1 % of the rows) — z = W x + b in fp32 and exact re-scoring with the reference's
+//     formula and tie-break: the two-stage scheme of encode_fp32.cu with a 500x tighter first stage.
 //   * weights (548 KB per leaf as fp16 hi/lo planes, L2-resident) stream through a 3 x 16 KB shared-memory ring as
-//     41 units by 1-D TMA bulk copies; ring slots are released by tcgen05.commit.
+//     40 units by 1-D TMA bulk copies; ring slots are released by tcgen05.commit.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -66,33 +68,36 @@ constexpr int kYRows = 160;                                     // space-to-dept
 constexpr uint32_t kYPlane = kYRows * 16, kYPrec = 16 * kYPlane, kYBytes = 2 * kYPrec;           // 81 920
 constexpr int kHMargin = 24, kHRows = 176;                      // 4^3, 32 channels: rows -24 .. 151 around q = d*20 + h*4 + w
 constexpr uint32_t kHPlane = kHRows * 16, kHPrec = 4 * kHPlane, kHBytes = 2 * kHPrec;            // 22 528
-constexpr int kZsPitch = 132;                                   // fp32 z rows (exact re-scoring), overlay Y
+// Overlays of Y, which is idle between the `down` MMAs of a leaf and the conv2 epilogue of the next one (and cleared in
+// between): proj.weight transposed [32][128] fp32, the attention output rows [64][36] fp32, and — near-tie rows only —
+// the fp32 z rows [64][132] for the exact re-scoring
+constexpr uint32_t kWpBytes = 32 * 128 * 4;                     // 16 384
+constexpr int kXsPitch = 36;
+constexpr uint32_t kXsBytes = 64 * kXsPitch * 4;                // 9 216
+constexpr int kZsPitch = 132;
 constexpr uint32_t kZsBytes = 64 * kZsPitch * 4;                // 33 792
-// split-fp16 z, the VQ A operand, overlays Y behind zs: 64 dense rows (latent positions) per 8-channel plane; the MMA's
-// rows 64..127 read the following plane (or 1 KB past the last one) and only feed accumulator rows nobody reads
-constexpr uint32_t kZhPlane = 64 * 16, kZhPrec = 16 * kZhPlane, kZhBytes = 2 * kZhPrec + 1024;   // 33 792
 constexpr int kX32Pitch = 36;
 
 constexpr uint32_t kOffRing = 0;
 constexpr uint32_t kOffA8 = kOffRing + kStages * kStageBytes;   // 49 152
 constexpr uint32_t kOffY = kOffA8 + kA8Bytes;                   // 100 352
-constexpr uint32_t kOffZs = kOffY;                              // Y is cleared again once the leaf's indices are out
-constexpr uint32_t kOffZh = kOffY + 34816;
+constexpr uint32_t kOffWp = kOffY;                              // Y is cleared again once the leaf's indices are out
+constexpr uint32_t kOffXs = kOffWp + kWpBytes;
+constexpr uint32_t kOffZs = kOffXs + kXsBytes;
 constexpr uint32_t kOffH = kOffY + kYBytes;                     // 182 272
 constexpr uint32_t kOffIn = kOffH + kHBytes;                    // in_halo [10][10][10] fp32 (4096 reserved)
 constexpr uint32_t kOffPreW = kOffIn + 4096;                    // pre.0 weights [27][16] fp32
 constexpr uint32_t kOffX32 = kOffPreW + 1728;                   // residual of the 4^3 block [64][36] fp32; later the VQ exchange
 constexpr uint32_t kOffRed = kOffX32 + 64 * kX32Pitch * 4;      // GroupNorm partials [2 slots][16 warps][2]
 constexpr uint32_t kOffAtt = kOffRed + 256;                     // attention: part [16 warps][8], hid [8], scale [32]
-constexpr uint32_t kOffCb = kOffAtt + (128 + 8 + 32) * 4;       // emb_sq [256], emb_norm [256]
-constexpr uint32_t kOffPar = kOffCb + 2048;                     // per-channel parameter vectors (ParOff), 1008 floats
+constexpr uint32_t kOffCb = kOffAtt + (128 + 8 + 32) * 4;       // emb_sq [256], fold_esq [256], fold_norm [256]
+constexpr uint32_t kOffPar = kOffCb + 3072;                     // per-channel parameter vectors (ParOff), 1008 floats
 constexpr uint32_t kOffXq = kOffPar + 1008 * 4;                 // `down` epilogue: lane-0 values handed to the previous quadrant [4][4][8]
 constexpr uint32_t kOffBar = kOffXq + 512;                      // mbarriers
 constexpr uint32_t kNumBars = 2 * kStages + 2;
 constexpr uint32_t kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemSlot + 16;
-static_assert(kZsBytes <= 34816 && 34816 + kZhBytes <= kYBytes, "z overlays fit inside the Y region");
-static_assert(4 * 4 * 128 * 4 <= 64 * kX32Pitch * 4, "VQ exchange arrays fit in the dead x32 staging area");
+static_assert(kOffZs + kZsBytes <= kOffY + kYBytes, "the VQ overlays fit inside the Y region");
 static_assert(kSmemBytes <= 227 * 1024, "encode_tc smem budget");
 static_assert(kOffBar % 8 == 0 && kOffA8 % 1024 == 0 && kOffY % 1024 == 0 && kOffH % 1024 == 0, "alignment");
 
@@ -314,13 +319,16 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 	extern __shared__ __align__(1024) uint8_t smem[];
 	const uint32_t s_base = smem_u32(smem);
 	const uint32_t ring = s_base + kOffRing, bars = s_base + kOffBar;
-	const uint32_t a8 = s_base + kOffA8, yb = s_base + kOffY, hb = s_base + kOffH, zh = s_base + kOffZh;
+	const uint32_t a8 = s_base + kOffA8, yb = s_base + kOffY, hb = s_base + kOffH;
 	float* in_halo = reinterpret_cast<float*>(smem + kOffIn);
 	float* s_prew = reinterpret_cast<float*>(smem + kOffPreW);
 	float* x32s = reinterpret_cast<float*>(smem + kOffX32);
 	float* att = reinterpret_cast<float*>(smem + kOffAtt);
 	float* s_esq = reinterpret_cast<float*>(smem + kOffCb);
-	float* s_eno = s_esq + 256;
+	float* s_esq2 = s_esq + 256;  // |e_k|^2 - 2 b.e_k (shortlist scores)
+	float* s_mno = s_esq + 512;   // |M_k|, rounded up (shortlist bound)
+	float* s_wp = reinterpret_cast<float*>(smem + kOffWp);
+	float* xs = reinterpret_cast<float*>(smem + kOffXs);
 	const float* __restrict__ sp_c = reinterpret_cast<const float*>(smem + kOffPar);
 	float* sp = reinterpret_cast<float*>(smem + kOffPar);
 	float* xq = reinterpret_cast<float*>(smem + kOffXq);
@@ -334,7 +342,8 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 	for (int i = tid; i < 432; i += kThreads) s_prew[i] = __ldg(w.pre_w + i);
 	for (int i = tid; i < 256; i += kThreads) {
 		s_esq[i] = __ldg(w.emb_sq + i);
-		s_eno[i] = __ldg(w.emb_norm + i);
+		s_esq2[i] = __ldg(w.fold_esq + i);
+		s_mno[i] = __ldg(w.fold_norm + i);
 		sp[par::fc0 + i] = __ldg(w.fc0 + i);
 		sp[par::fc2 + i] = __ldg(w.fc2 + i);
 	}
@@ -400,7 +409,6 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			const uint64_t a8_d = make_desc(a8 + kA8Margin * 16, kA8Plane, 128);
 			const uint64_t y_d = make_desc(yb, kYPlane, 128);
 			const uint64_t h_d = make_desc(hb + kHMargin * 16, kHPlane, 128);
-			const uint64_t z_d = make_desc(zh, kZhPlane, 128);
 			auto wait_a = [&]() {
 				const long long c0 = prof_clock<kProf>();
 				mbar_wait(bar_a_ready(bars), a_count & 1u);
@@ -496,33 +504,18 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					}
 					tc_commit(bar_d_full(bars));
 				}
-				// ---- proj: 2 k-steps x {N = 256, N = 128} ----
-				wait_a();
-				{
-					const uint32_t wb = wait_w();
-					const long long c0 = prof_clock<kProf>();
-#pragma unroll
-					for (int ks = 0; ks < 2; ++ks) {
-						const uint64_t ad = h_d + (uint64_t)(ks * 2 * (int)(kHPlane >> 4));
-						const uint64_t bd = make_desc(wb + ks * 8192, 256 * 16, 128);
-						mma_ss(tmem, ad, bd, idesc_f16(256), ks > 0 ? 1u : 0u);
-						mma_ss(tmem + 128, ad + (kHPrec >> 4), bd, idesc_f16(128), 1u);
-					}
-					release_w();
-					if (kProf) t_issue += prof_clock<kProf>() - c0;
-				}
-				tc_commit(bar_d_full(bars));
-				// ---- VQ scores: 8 k-steps x {z_hi.e_hi -> cols 0..255 ; z_hi.e_lo + z_lo.e_hi -> cols 256..511}, N = 256 ----
+				// ---- VQ scores straight from the attention output (proj folded into the codebook): 2 k-steps x
+				//      {x_hi.M_hi -> cols 0..255 ; x_hi.M_lo + x_lo.M_hi -> cols 256..511}, N = 256 ----
 				wait_a();
 #pragma unroll 1
-				for (int ks = 0; ks < 8; ++ks) {
+				for (int ks = 0; ks < 2; ++ks) {
 					const uint32_t wb = wait_w();
 					const long long c0 = prof_clock<kProf>();
-					const uint64_t ad = z_d + (uint64_t)(ks * 2 * (int)(kZhPlane >> 4));
+					const uint64_t ad = h_d + (uint64_t)(ks * 2 * (int)(kHPlane >> 4));
 					const uint64_t bh = make_desc(wb, 256 * 16, 128), bl = make_desc(wb + 8192, 256 * 16, 128);
 					mma_ss(tmem, ad, bh, idesc_f16(256), ks > 0 ? 1u : 0u);
 					mma_ss(tmem + 256, ad, bl, idesc_f16(256), ks > 0 ? 1u : 0u);
-					mma_ss(tmem + 256, ad + (kZhPrec >> 4), bh, idesc_f16(256), 1u);
+					mma_ss(tmem + 256, ad + (kHPrec >> 4), bh, idesc_f16(256), 1u);
 					release_w();
 					if (kProf) t_issue += prof_clock<kProf>() - c0;
 				}
@@ -563,10 +556,13 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 		const bool validd = row < 100 && jh < 4 && jw < 4;
 		const int pd = jd * 16 + jh * 4 + jw;
 		// VQ exchange arrays (overlay the x32 staging, dead by then): [4 groups][128 rows]
-		float* vq_zz = x32s;
-		float* vq_umin = x32s + 512;
-		float* vq_best = x32s + 1024;
-		int* vq_bidx = reinterpret_cast<int*>(x32s + 1536);
+		float* vq_umin = x32s;        // row minimum of the upper bounds; later the re-scored minima
+		float* vq_lo1 = x32s + 512;   // smallest / second-smallest lower bound of a thread's 64 codes
+		float* vq_lo2 = x32s + 1024;
+		int* vq_k1 = reinterpret_cast<int*>(x32s + 1536);  // code of lo1; later the re-scored arg-min
+		static_assert(4 * 512 * 4 <= 64 * kX32Pitch * 4, "VQ exchange arrays fit in the dead x32 staging area");
+		// the four per-group partials of |x|^2 (and of |z|^2) of a row live in the padding of its xs (zs) row
+		static_assert(kXsPitch >= 32 + 4 && kZsPitch >= 128 + 4, "row padding holds the four partial sums");
 
 		// Rows of this thread in the five 8^3 tiles (the same for every leaf).
 		uint32_t valid8 = 0;
@@ -762,6 +758,9 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			// ---- down epilogue: sum the accumulation chains, + bias -> x32 (residual, to shared memory) ; res32.gn1 + ReLU -> H32 ----
 			wait_accumulator(rc);
 			lap(7);
+			// the `down` MMAs were the last readers of Y: proj.weight (transposed, fp32) goes there for the near-tie rows of the VQ
+			const float4 wp0 = __ldg(reinterpret_cast<const float4*>(w.proj_w) + tid);
+			const float4 wp1 = __ldg(reinterpret_cast<const float4*>(w.proj_w) + 512 + tid);
 			{
 				float v[1][8];
 				{
@@ -819,6 +818,8 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				}
 			}
 			signal_a_ready(bars, lane);
+			reinterpret_cast<float4*>(s_wp)[tid] = wp0;
+			reinterpret_cast<float4*>(s_wp)[512 + tid] = wp1;
 			lap(8);
 			if (has_next) front_gn_pre1(xn);
 			lap(1);
@@ -902,70 +903,40 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 						for (int c = 0; c < 8; ++c) tap_out[(leaf * 32 + g * 8 + c) * 64 + p4] = v[c];
 					}
 					store_split8(h_mine, kHPrec, v);
+					// fp32 copy of the row (z = W x + b of the near-tie rows) and this thread's share of |x|^2 (shortlist bound)
+					*reinterpret_cast<float4*>(xs + p4 * kXsPitch + g * 8) = make_float4(v[0], v[1], v[2], v[3]);
+					*reinterpret_cast<float4*>(xs + p4 * kXsPitch + g * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+					float xxp = 0.f;
+#pragma unroll
+					for (int c = 0; c < 8; ++c) xxp = fmaf(v[c], v[c], xxp);
+					xs[p4 * kXsPitch + 32 + g] = xxp;
 				}
 			}
 			signal_a_ready(bars, lane);
 			lap(12);
 
-			// ---- proj epilogue: z (channels 32g .. 32g+31) = acc + b -> fp32 rows (exact re-scoring) and the split-fp16 A
-			//      operand of the VQ GEMM; |z|^2 as four per-group partial sums, each sequential in d ----
-			wait_accumulator(rc);
-			lap(13);
-			{
-				float zzp = 0.f;
-#pragma unroll
-				for (int half = 0; half < 2; ++half) {
-					float hh[16], hl[16];
-					tmem_ld16_nowait(rc.tlane + g * 32 + half * 16, hh);
-					tmem_ld16_nowait(rc.tlane + 128 + g * 32 + half * 16, hl);
-					tmem_wait_ld();
-#pragma unroll
-					for (int c = 0; c < 16; ++c) {
-						hh[c] = fmaf(hl[c], kLoInv, hh[c]) + sp_c[par::proj_b + g * 32 + half * 16 + c];
-						zzp = fmaf(hh[c], hh[c], zzp);
-					}
-					if (valid4) {
-#pragma unroll
-						for (int q = 0; q < 4; ++q)
-							*reinterpret_cast<float4*>(zs + p4 * kZsPitch + g * 32 + half * 16 + q * 4) = make_float4(hh[4 * q], hh[4 * q + 1], hh[4 * q + 2], hh[4 * q + 3]);
-						if (tap_stage == 5) {
-#pragma unroll
-							for (int c = 0; c < 16; ++c) tap_out[(leaf * 128 + g * 32 + half * 16 + c) * 64 + p4] = hh[c];
-						}
-					}
-					if (valid4) {  // VQ GEMM rows are the dense latent positions p = (d*4+h)*4+w
-#pragma unroll
-						for (int j = 0; j < 2; ++j) {
-							float z8[8];
-#pragma unroll
-							for (int c = 0; c < 8; ++c) z8[c] = hh[8 * j + c];
-							store_split8(zh + (uint32_t)(g * 4 + half * 2 + j) * kZhPlane + (uint32_t)p4 * 16, kZhPrec, z8);
-						}
-					}
-				}
-				if (valid4) vq_zz[g * 128 + p4] = zzp;
-			}
-			signal_a_ready(bars, lane);
-			lap(14);
-
-			// ---- VQ: argmin_k (|z|^2 + |e_k|^2) - 2 z.e_k (save_for_inference.py:55-61), first minimum wins ----
-			//  1. a_k = |e_k|^2 - 2 (z_hi.e_hi + (z_hi.e_lo + z_lo.e_hi) / 2048) from the tensor cores.  Each operand keeps 22
-			//     significant bits, so |a_k - (exact score - |z|^2)| <= 2 * (3 * 2^-22 [split + dropped lo.lo term] + 8 * 2^-22
-			//     [accumulator truncation, 8 steps]) * sum|z_d e_kd| <= 5.3e-6 |z| |e_k|; used bound B_k = 8e-6 |z| |e_k| + 1e-4,
-			//     the 1e-4 covering the fp32 evaluation noise of the reference formula itself.
-			//  2. every code whose lower bound a_k - B_k does not exceed min_j (a_j + B_j) is re-scored with the reference's
-			//     fp32 formula, sequential in d; the fp32 arg-min and all its ties are in that shortlist.  It has a second
-			//     entry for about 1 % of the rows (near-ties); a single entry needs no re-scoring at all.
-			//  GEMM row = latent position (rows 64..127 are unused).  The four threads of a row take 64 codes each;
+			// ---- VQ: argmin_k (|z|^2 + |e_k|^2) - 2 z.e_k (save_for_inference.py:55-61), first minimum wins ; z = W x + b ----
+			//  1. a_k = (|e_k|^2 - 2 b.e_k) - 2 (x_hi.M_hi + (x_hi.M_lo + x_lo.M_hi) / 2048) from the tensor cores, M = proj.weight^T e
+			//     folded on the host in double.  Each operand keeps 22 significant bits, so |a_k - (exact score - |z|^2)| <=
+			//     2 * (3 * 2^-22 [split + dropped lo.lo term] + 2 * 2^-22 [accumulator truncation, 2 steps]) * sum|x_c M_kc|
+			//     <= 2.4e-6 |x| |M_k|; used bound B_k = 4e-6 |x| |M_k| + 1e-4, the 1e-4 covering the fp32 evaluation noise of the
+			//     reference's own z and distance formula.
+			//  2. one pass over the scores keeps, per thread, the minimum upper bound a_k + B_k and the two smallest lower
+			//     bounds a_k - B_k.  A row whose second-smallest lower bound exceeds the minimum upper bound has exactly one
+			//     code that can be the fp32 arg-min: done (~99 % of the rows).
+			//  3. otherwise (near-tie): z = W x + b in fp32 for that row, every code with a_k - B_k <= min_j (a_j + B_j) is
+			//     re-scored with the reference's fp32 formula, sequential in d; the fp32 arg-min and all its ties are in that
+			//     shortlist.  The step is entered by the whole CTA when any of its 64 rows needs it.
+			//  GEMM row = flattened 4^3 row (as in the res32 tiles).  The four threads of a row take 64 codes each;
 			//  tcgen05.ld is warp-collective, so every lane runs the loads.
-			const bool validv = row < 64;
 			wait_accumulator(rc);
-			row_bar();  // z rows and |z|^2 partials of all four groups are in place
+			row_bar();  // the |x|^2 partials and fp32 x rows of all four groups are in place
 			lap(15);
 			{
-				const float zz = (vq_zz[row] + vq_zz[128 + row]) + (vq_zz[256 + row] + vq_zz[384 + row]);
-				const float cb = 8e-6f * sqrtf(zz);
-				float umin = INFINITY;
+				const float* xp = xs + (valid4 ? p4 : 0) * kXsPitch + 32;
+				const float cb = 4e-6f * sqrtf((xp[0] + xp[1]) + (xp[2] + xp[3]));
+				float umin = INFINITY, lo1 = INFINITY, lo2 = INFINITY;
+				int k1 = 0;
 #pragma unroll 1
 				for (int ch = 0; ch < 4; ++ch) {
 					float hh[16], mx[16];
@@ -975,89 +946,149 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 #pragma unroll
 					for (int j = 0; j < 16; ++j) {
 						const int k = g * 64 + ch * 16 + j;
-						const float a = s_esq[k] - 2.f * fmaf(mx[j], kLoInv, hh[j]);
-						umin = fminf(umin, a + (cb * s_eno[k] + 1e-4f));
+						const float a = s_esq2[k] - 2.f * fmaf(mx[j], kLoInv, hh[j]);
+						const float bnd = fmaf(cb, s_mno[k], 1e-4f);
+						umin = fminf(umin, a + bnd);
+						const float lo = a - bnd;
+						if (lo < lo1) {  // codes ascend: strict < keeps the lowest code among equal bounds
+							lo2 = lo1;
+							lo1 = lo;
+							k1 = k;
+						} else {
+							lo2 = fminf(lo2, lo);
+						}
 					}
 				}
 				vq_umin[g * 128 + row] = umin;
+				vq_lo1[g * 128 + row] = lo1;
+				vq_lo2[g * 128 + row] = lo2;
+				vq_k1[g * 128 + row] = k1;
 				row_bar();
 				lap(16);
 				umin = fminf(fminf(vq_umin[row], vq_umin[128 + row]), fminf(vq_umin[256 + row], vq_umin[384 + row]));
-				unsigned long long mask = 0ull;
+				float l1 = INFINITY, l2 = INFINITY;
+				int kbest = 0;
+#pragma unroll
+				for (int o = 0; o < 4; ++o) {  // ascending code ranges
+					const float a1 = vq_lo1[o * 128 + row], a2 = vq_lo2[o * 128 + row];
+					if (a1 < l1) {
+						l2 = l1;
+						l1 = a1;
+						kbest = vq_k1[o * 128 + row];
+					} else {
+						l2 = fminf(l2, a1);
+					}
+					l2 = fminf(l2, a2);
+				}
+				// non-finite scores (inf / nan inputs) fail `l2 > umin` and take the exact path
+				const bool amb = valid4 && (!(l2 > umin) || tap_stage == 5);
+				uint32_t any_amb;
+				asm volatile(
+				    "{\n.reg .pred p, q;\nsetp.ne.u32 q, %1, 0;\nbar.red.or.pred p, 1, 512, q;\nselp.u32 %0, 1, 0, p;\n}\n"
+				    : "=r"(any_amb)
+				    : "r"((uint32_t)amb)
+				    : "memory");  // also: every thread is done reading the exchange arrays
+				if (!any_amb) {
+					if (g == 0 && valid4) indices[leaf * 64 + p4] = (uint8_t)kbest;  // p4 = (d*4+h)*4+w == view(B,4,4,4)
+					lap(17);
+				} else {
+					// z rows of this warp's near-tie rows: lane l computes dim 32g + l, sequential in c from the bias
+					for (uint32_t m = __ballot_sync(0xffffffffu, amb); m; m &= m - 1) {
+						const int r = __ffs((int)m) - 1;
+						const int rp = __shfl_sync(0xffffffffu, p4, r);
+						const float* xr = xs + rp * kXsPitch;
+						float acc = sp_c[par::proj_b + g * 32 + lane];
+#pragma unroll 8
+						for (int c = 0; c < 32; ++c) acc = fmaf(xr[c], s_wp[c * 128 + g * 32 + lane], acc);
+						zs[rp * kZsPitch + g * 32 + lane] = acc;
+					}
+					row_bar();
+					if (amb) {  // |z|^2 as four per-group partial sums, each sequential in d
+						float zzp = 0.f;
+#pragma unroll 8
+						for (int d = 0; d < 32; ++d) {
+							const float zv = zs[p4 * kZsPitch + g * 32 + d];
+							zzp = fmaf(zv, zv, zzp);
+							if (tap_stage == 5) tap_out[(leaf * 128 + g * 32 + d) * 64 + p4] = zv;
+						}
+						zs[p4 * kZsPitch + 128 + g] = zzp;
+					}
+					unsigned long long mask = 0ull;
+					if (__any_sync(0xffffffffu, amb)) {
 #pragma unroll 1
-				for (int ch = 0; ch < 4; ++ch) {  // the scores are read again rather than kept in 64 registers
-					float hh[16], mx[16];
-					tmem_ld16_nowait(rc.tlane + g * 64 + ch * 16, hh);
-					tmem_ld16_nowait(rc.tlane + 256 + g * 64 + ch * 16, mx);
-					tmem_wait_ld();
-					uint32_t m16 = 0u;
+						for (int ch = 0; ch < 4; ++ch) {  // the scores are read again rather than kept in 64 registers
+							float hh[16], mx[16];
+							tmem_ld16_nowait(rc.tlane + g * 64 + ch * 16, hh);
+							tmem_ld16_nowait(rc.tlane + 256 + g * 64 + ch * 16, mx);
+							tmem_wait_ld();
+							uint32_t m16 = 0u;
 #pragma unroll
-					for (int j = 0; j < 16; ++j) {
-						const int k = g * 64 + ch * 16 + j;
-						const float a = s_esq[k] - 2.f * fmaf(mx[j], kLoInv, hh[j]);
-						if (a - (cb * s_eno[k] + 1e-4f) <= umin) m16 |= 1u << j;
-					}
-					mask |= (unsigned long long)m16 << (ch * 16);
-				}
-				if (!validv) mask = 0ull;
-				float best = INFINITY;
-				int bi = 0x7fffffff;
-				int* vq_cnt = reinterpret_cast<int*>(vq_zz);  // |z|^2 partials were consumed before the previous barrier
-				vq_cnt[g * 128 + row] = __popcll(mask);       // shortlist sizes of the row's four threads
-				row_bar();
-				const int n_cand = (vq_cnt[row] + vq_cnt[128 + row]) + (vq_cnt[256 + row] + vq_cnt[384 + row]);
-				if (n_cand == 1 && mask) {  // the only code that can be the fp32 arg-min: nothing to re-score
-					bi = g * 64 + __ffsll((long long)mask) - 1;
-					best = -INFINITY;
-					mask = 0ull;
-				}
-				const float* zrow = zs + (validv ? row : 0) * kZsPitch;
-				while (mask) {  // two candidates per trip: two independent FMA chains
-					const int b0 = __ffsll((long long)mask) - 1;
-					mask &= mask - 1;
-					const bool two = mask != 0ull;
-					const int b1 = two ? __ffsll((long long)mask) - 1 : b0;
-					mask &= mask - 1;  // no-op on zero
-					const int code0 = g * 64 + b0, code1 = g * 64 + b1;
-					const float4* e0 = reinterpret_cast<const float4*>(w.emb + code0 * 128);
-					const float4* e1 = reinterpret_cast<const float4*>(w.emb + code1 * 128);
-					float dot0 = 0.f, dot1 = 0.f;
-#pragma unroll 4
-					for (int q = 0; q < 32; ++q) {
-						const float4 ea = __ldg(e0 + q), eb = __ldg(e1 + q);
-						const float4 zv = *reinterpret_cast<const float4*>(zrow + q * 4);
-						dot0 = fmaf(zv.x, ea.x, dot0); dot1 = fmaf(zv.x, eb.x, dot1);
-						dot0 = fmaf(zv.y, ea.y, dot0); dot1 = fmaf(zv.y, eb.y, dot1);
-						dot0 = fmaf(zv.z, ea.z, dot0); dot1 = fmaf(zv.z, eb.z, dot1);
-						dot0 = fmaf(zv.w, ea.w, dot0); dot1 = fmaf(zv.w, eb.w, dot1);
-					}
-					const float dist0 = (zz + s_esq[code0]) - 2.f * dot0, dist1 = (zz + s_esq[code1]) - 2.f * dot1;
-					if (dist0 < best) {  // codes ascend, so strict < keeps the first minimum
-						best = dist0;
-						bi = code0;
-					}
-					if (two && dist1 < best) {
-						best = dist1;
-						bi = code1;
-					}
-				}
-				lap(17);
-				vq_best[g * 128 + row] = best;
-				vq_bidx[g * 128 + row] = bi;
-				row_bar();
-				if (g == 0 && validv) {
-#pragma unroll
-					for (int o = 1; o < 4; ++o) {  // ascending code ranges: strict < keeps the lowest code among equal distances
-						const float ob = vq_best[o * 128 + row];
-						if (ob < best) {
-							best = ob;
-							bi = vq_bidx[o * 128 + row];
+							for (int j = 0; j < 16; ++j) {
+								const int k = g * 64 + ch * 16 + j;
+								const float a = s_esq2[k] - 2.f * fmaf(mx[j], kLoInv, hh[j]);
+								if (!(a - fmaf(cb, s_mno[k], 1e-4f) > umin)) m16 |= 1u << j;
+							}
+							mask |= (unsigned long long)m16 << (ch * 16);
 						}
 					}
-					indices[leaf * 64 + row] = (uint8_t)bi;  // row = (d*4+h)*4+w == view(B,4,4,4)
+					if (!amb) mask = 0ull;
+					row_bar();
+					const float* zrow = zs + (amb ? p4 : 0) * kZsPitch;
+					const float zz = (zrow[128] + zrow[129]) + (zrow[130] + zrow[131]);
+					float best = INFINITY;
+					int bi = 0x7fffffff;
+					while (mask) {  // two candidates per trip: two independent FMA chains
+						const int b0 = __ffsll((long long)mask) - 1;
+						mask &= mask - 1;
+						const bool two = mask != 0ull;
+						const int b1 = two ? __ffsll((long long)mask) - 1 : b0;
+						mask &= mask - 1;  // no-op on zero
+						const int code0 = g * 64 + b0, code1 = g * 64 + b1;
+						const float4* e0 = reinterpret_cast<const float4*>(w.emb + code0 * 128);
+						const float4* e1 = reinterpret_cast<const float4*>(w.emb + code1 * 128);
+						float dot0 = 0.f, dot1 = 0.f;
+#pragma unroll 4
+						for (int q = 0; q < 32; ++q) {
+							const float4 ea = __ldg(e0 + q), eb = __ldg(e1 + q);
+							const float4 zv = *reinterpret_cast<const float4*>(zrow + q * 4);
+							dot0 = fmaf(zv.x, ea.x, dot0); dot1 = fmaf(zv.x, eb.x, dot1);
+							dot0 = fmaf(zv.y, ea.y, dot0); dot1 = fmaf(zv.y, eb.y, dot1);
+							dot0 = fmaf(zv.z, ea.z, dot0); dot1 = fmaf(zv.z, eb.z, dot1);
+							dot0 = fmaf(zv.w, ea.w, dot0); dot1 = fmaf(zv.w, eb.w, dot1);
+						}
+						const float dist0 = (zz + s_esq[code0]) - 2.f * dot0, dist1 = (zz + s_esq[code1]) - 2.f * dot1;
+						if (dist0 < best) {  // codes ascend, so strict < keeps the first minimum
+							best = dist0;
+							bi = code0;
+						}
+						if (two && dist1 < best) {
+							best = dist1;
+							bi = code1;
+						}
+					}
+					lap(17);
+					vq_umin[g * 128 + row] = best;
+					vq_k1[g * 128 + row] = bi;
+					row_bar();
+					if (g == 0 && valid4) {
+						if (amb) {
+#pragma unroll
+							for (int o = 1; o < 4; ++o) {  // ascending code ranges: strict < keeps the lowest code among equal distances
+								const float ob = vq_umin[o * 128 + row];
+								if (ob < best) {
+									best = ob;
+									bi = vq_k1[o * 128 + row];
+								}
+							}
+							if (bi == 0x7fffffff) bi = kbest;  // every distance was nan: keep the shortlist's choice
+						} else {
+							bi = kbest;
+						}
+						indices[leaf * 64 + p4] = (uint8_t)bi;
+					}
 				}
 			}
-			// ---- leaf done: Y (dirtied by the z overlays) is cleared for the next conv2 epilogue, and the next leaf's conv1 —
+			// ---- leaf done: Y (dirtied by the VQ overlays) is cleared for the next conv2 epilogue, and the next leaf's conv1 —
 			//      its input has been in A8 since the res32 phase — may start now that the accumulators are drained ----
 			if (has_next) {
 				row_bar();  // every row thread is done with z and with the TMEM scores

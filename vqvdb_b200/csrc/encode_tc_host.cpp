@@ -1,4 +1,5 @@
 // Host-side preparation of the tensor-core encoder's weight stream (see encode_tc.cuh).
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 
@@ -66,6 +67,32 @@ inline void put(uint8_t* block, int N, int n, int k, uint16_t v) {
 
 }  // namespace
 
+void build_encoder_vq_fold(const WeightPack& p, std::vector<float>& m, std::vector<float>& esq_fold, std::vector<float>& m_norm) {
+	const PackTensor& e = p.get("quantizer.embedding");    // [256][128]
+	const PackTensor& w = p.get("encoder.proj.weight");    // [128][32][1][1][1]
+	const PackTensor& b = p.get("encoder.proj.bias");      // [128]
+	if (e.numel() != (size_t)256 * 128 || w.numel() != (size_t)128 * 32 || b.numel() != 128)
+		throw std::runtime_error("encoder VQ fold: unexpected proj / codebook shapes");
+	m.assign((size_t)256 * 32, 0.f);
+	esq_fold.assign(256, 0.f);
+	m_norm.assign(256, 0.f);
+	for (int k = 0; k < 256; ++k) {
+		double e2 = 0.0, be = 0.0, n2 = 0.0;
+		for (int d = 0; d < 128; ++d) {
+			e2 += (double)e.data[k * 128 + d] * e.data[k * 128 + d];
+			be += (double)e.data[k * 128 + d] * b.data[d];
+		}
+		for (int c = 0; c < 32; ++c) {
+			double s = 0.0;
+			for (int d = 0; d < 128; ++d) s += (double)e.data[k * 128 + d] * w.data[d * 32 + c];
+			m[(size_t)k * 32 + c] = (float)s;
+			n2 += s * s;
+		}
+		esq_fold[k] = (float)(e2 - 2.0 * be);
+		m_norm[k] = std::nextafter((float)std::sqrt(n2), INFINITY);  // never under-estimates |M_k|
+	}
+}
+
 std::vector<uint8_t> build_encoder_tc_units(const WeightPack& p, EncoderTcStream& tab) {
 	std::vector<uint8_t> out;
 	int nu = 0;
@@ -130,23 +157,16 @@ std::vector<uint8_t> build_encoder_tc_units(const WeightPack& p, EncoderTcStream
 								    split_part(w[((co * 32 + ks * 16 + k) * 27) + kk * 3 + kw], part));
 		}
 	}
-	// proj: weight [128][32][1][1][1]
+	// proj folded into the codebook (encode_tc_stream.hpp): M [256][32], split like the conv weights: per 16-channel k-step
+	// one M_hi block and one M_lo block
 	{
-		const float* w = p.get("encoder.proj.weight").data;
-		uint8_t* u = begin_unit(2 * 8192);
-		for (int ks = 0; ks < 2; ++ks)
-			for (int part = 0; part < 2; ++part)
-				for (int co = 0; co < 128; ++co)
-					for (int k = 0; k < 16; ++k) put(u + ks * 8192, 256, part * 128 + co, k, split_part(w[co * 32 + ks * 16 + k], part));
-	}
-	// codebook [256][128], split like the conv weights: per 16-dim k-step one e_hi block and one e_lo block
-	{
-		const float* e = p.get("quantizer.embedding").data;
-		for (int ks = 0; ks < 8; ++ks) {
+		std::vector<float> m, esq, mno;
+		build_encoder_vq_fold(p, m, esq, mno);
+		for (int ks = 0; ks < 2; ++ks) {
 			uint8_t* u = begin_unit(2 * 8192);
 			for (int part = 0; part < 2; ++part)
 				for (int code = 0; code < 256; ++code)
-					for (int k = 0; k < 16; ++k) put(u + part * 8192, 256, code, k, split_part(e[code * 128 + ks * 16 + k], part));
+					for (int k = 0; k < 16; ++k) put(u + part * 8192, 256, code, k, split_part(m[code * 32 + ks * 16 + k], part));
 		}
 	}
 	if (nu != kEncTcUnits) throw std::logic_error("encoder tc unit count mismatch");

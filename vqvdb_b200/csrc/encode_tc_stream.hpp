@@ -17,10 +17,16 @@ namespace vqvdb {
 //   down                : 8 units (2x2x2-tap space-to-depth form; one per (td, th) tap pair and half of the 8 input
 //                         parity classes) = 4 parity classes x [2][128][16 B], n = part*64 + tw*32 + cout
 //   res32 conv1 / conv2 : 9 units each (one per (kd, kh)) = 2 k-steps x [2][192][16 B], n = part*96 + kw*32 + cout
-//   proj                : 1 unit = 2 k-steps x [2][256][16 B], n = part*128 + cout
-//   codebook            : 8 units (one per 16-dim k-step) = [2][256][16 B] e_hi then [2][256][16 B] e_lo, n = code
+//   proj x codebook     : 2 units (one per 16-channel k-step) = [2][256][16 B] M_hi then [2][256][16 B] M_lo, n = code
 // (part 0 = w_hi, part 1 = w_lo).
-constexpr int kEncTcUnits = 47;
+//
+// proj (1x1 conv, 32 -> 128) feeds nothing but the codebook distances, and z.e_k = (W x + b).e_k = x.(W^T e_k) + b.e_k, so
+// the two GEMMs [64 x 32] x [32 x 128] and [64 x 128] x [128 x 256] are ONE [64 x 32] x [32 x 256] with
+//     M[k][c] = sum_d e[k][d] W[d][c],      score_k = |e_k|^2 - 2 b.e_k - 2 x.M_k  (= |z - e_k|^2 - |z|^2)
+// folded in double precision on the host (build_encoder_vq_fold).  The tensor-core scores only SHORTLIST (rigorous error
+// bound in encode_tc.cu); rows whose shortlist has more than one code compute z = W x + b in fp32 and are re-scored
+// with the reference's own formula (python/save_for_inference.py:55-61) exactly as before.
+constexpr int kEncTcUnits = 40;
 constexpr uint32_t kEncTcStageBytes = 16384;
 
 struct EncoderTcStream {
@@ -31,5 +37,7 @@ struct EncoderTcStream {
 
 // Builds the unit stream on the host and fills table.off / table.bytes (table.units is set by the caller after upload).
 std::vector<uint8_t> build_encoder_tc_units(const WeightPack& pack, EncoderTcStream& table);
+// m [256][32] fp32, esq_fold[k] = |e_k|^2 - 2 b.e_k, m_norm[k] >= |M_k| (rounded up; only used in the shortlist bound)
+void build_encoder_vq_fold(const WeightPack& pack, std::vector<float>& m, std::vector<float>& esq_fold, std::vector<float>& m_norm);
 
 }  // namespace vqvdb

@@ -24,6 +24,8 @@ struct EncoderWeights {
 	const float *emb_sq;               // sum(embedding**2, dim=1) [256]
 	const float *emb_norm;             // |e_k| [256], rounded up: only used in the shortlist bound
 	const float *emb;                  // quantizer.embedding [256][128] fp32 (exact re-scoring)
+	const float *fold_esq;             // |e_k|^2 - 2 proj.bias.e_k [256]   (tensor-core encoder: proj folded into the codebook)
+	const float *fold_norm;            // |proj.weight^T e_k| [256], rounded up: only used in the shortlist bound
 };
 
 // The encoder consumes its weights as a fixed stream of "units" (<= 8 KB) through a shared-memory ring:
