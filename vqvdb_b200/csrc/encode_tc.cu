@@ -91,7 +91,7 @@ constexpr uint32_t kOffX32 = kOffPreW + 1728;                   // residual of t
 constexpr uint32_t kOffRed = kOffX32 + 64 * kX32Pitch * 4;      // GroupNorm partials [2 slots][16 warps][2]
 constexpr uint32_t kOffAtt = kOffRed + 256;                     // attention: part [16 warps][8], hid [8], scale [32]
 constexpr uint32_t kOffCb = kOffAtt + (128 + 8 + 32) * 4;       // emb_sq [256], fold_esq [256], fold_norm [256]
-constexpr uint32_t kOffPar = kOffCb + 3072;                     // per-channel parameter vectors (ParOff), 1008 floats
+constexpr uint32_t kOffPar = kOffCb + 3088;                     // fold_norm has a 257th entry: its maximum                     // per-channel parameter vectors (ParOff), 1008 floats
 constexpr uint32_t kOffXq = kOffPar + 1008 * 4;                 // `down` epilogue: lane-0 values handed to the previous quadrant [4][4][8]
 constexpr uint32_t kOffBar = kOffXq + 512;                      // mbarriers
 constexpr uint32_t kNumBars = 2 * kStages + 2;
@@ -344,6 +344,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 		s_esq[i] = __ldg(w.emb_sq + i);
 		s_esq2[i] = __ldg(w.fold_esq + i);
 		s_mno[i] = __ldg(w.fold_norm + i);
+		if (i == 0) s_mno[256] = __ldg(w.fold_norm + 256);
 		sp[par::fc0 + i] = __ldg(w.fc0 + i);
 		sp[par::fc2 + i] = __ldg(w.fc2 + i);
 	}
@@ -556,7 +557,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 		const bool validd = row < 100 && jh < 4 && jw < 4;
 		const int pd = jd * 16 + jh * 4 + jw;
 		// VQ exchange arrays (overlay the x32 staging, dead by then): [4 groups][128 rows]
-		float* vq_umin = x32s;        // row minimum of the upper bounds; later the re-scored minima
+		float* vq_umin = x32s;        // near-tie rows: the re-scored minima
 		float* vq_lo1 = x32s + 512;   // smallest / second-smallest lower bound of a thread's 64 codes
 		float* vq_lo2 = x32s + 1024;
 		int* vq_k1 = reinterpret_cast<int*>(x32s + 1536);  // code of lo1; later the re-scored arg-min
@@ -921,12 +922,13 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			//     2 * (3 * 2^-22 [split + dropped lo.lo term] + 2 * 2^-22 [accumulator truncation, 2 steps]) * sum|x_c M_kc|
 			//     <= 2.4e-6 |x| |M_k|; used bound B_k = 4e-6 |x| |M_k| + 1e-4, the 1e-4 covering the fp32 evaluation noise of the
 			//     reference's own z and distance formula.
-			//  2. one pass over the scores keeps, per thread, the minimum upper bound a_k + B_k and the two smallest lower
-			//     bounds a_k - B_k.  A row whose second-smallest lower bound exceeds the minimum upper bound has exactly one
-			//     code that can be the fp32 arg-min: done (~99 % of the rows).
-			//  3. otherwise (near-tie): z = W x + b in fp32 for that row, every code with a_k - B_k <= min_j (a_j + B_j) is
-			//     re-scored with the reference's fp32 formula, sequential in d; the fp32 arg-min and all its ties are in that
-			//     shortlist.  The step is entered by the whole CTA when any of its 64 rows needs it.
+			//  2. one pass over the scores keeps, per thread, the two smallest a_k and the code of the smallest.  With
+			//     Bmax = max_k B_k, every code that can be the fp32 arg-min has a_k <= min_j a_j + 2 Bmax; a row whose
+			//     second-smallest score exceeds that has exactly one such code: done (~99 % of the rows).
+			//  3. otherwise (near-tie): z = W x + b in fp32 for that row, every code with a_k - B_k <= min_j a_j + Bmax
+			//     (a superset of {a_k - B_k <= min_j (a_j + B_j)}) is re-scored with the reference's fp32 formula, sequential
+			//     in d; the fp32 arg-min and all its ties are in that shortlist.  The step is entered by the whole CTA when
+			//     any of its 64 rows needs it.
 			//  GEMM row = flattened 4^3 row (as in the res32 tiles).  The four threads of a row take 64 codes each;
 			//  tcgen05.ld is warp-collective, so every lane runs the loads.
 			wait_accumulator(rc);
@@ -934,8 +936,10 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			lap(15);
 			{
 				const float* xp = xs + (valid4 ? p4 : 0) * kXsPitch + 32;
-				const float cb = 4e-6f * sqrtf((xp[0] + xp[1]) + (xp[2] + xp[3]));
-				float umin = INFINITY, lo1 = INFINITY, lo2 = INFINITY;
+				const float xx = (xp[0] + xp[1]) + (xp[2] + xp[3]);
+				const float cb = 4e-6f * sqrtf(xx);
+				const float bmax = fmaf(cb, s_mno[256], 1e-4f);
+				float a1 = INFINITY, a2 = INFINITY;
 				int k1 = 0;
 #pragma unroll 1
 				for (int ch = 0; ch < 4; ++ch) {
@@ -947,41 +951,33 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					for (int j = 0; j < 16; ++j) {
 						const int k = g * 64 + ch * 16 + j;
 						const float a = s_esq2[k] - 2.f * fmaf(mx[j], kLoInv, hh[j]);
-						const float bnd = fmaf(cb, s_mno[k], 1e-4f);
-						umin = fminf(umin, a + bnd);
-						const float lo = a - bnd;
-						if (lo < lo1) {  // codes ascend: strict < keeps the lowest code among equal bounds
-							lo2 = lo1;
-							lo1 = lo;
-							k1 = k;
-						} else {
-							lo2 = fminf(lo2, lo);
-						}
+						k1 = a < a1 ? k : k1;  // codes ascend: strict < keeps the lowest code among equal scores
+						a2 = fminf(a2, fmaxf(a1, a));
+						a1 = fminf(a1, a);
 					}
 				}
-				vq_umin[g * 128 + row] = umin;
-				vq_lo1[g * 128 + row] = lo1;
-				vq_lo2[g * 128 + row] = lo2;
+				vq_lo1[g * 128 + row] = a1;
+				vq_lo2[g * 128 + row] = a2;
 				vq_k1[g * 128 + row] = k1;
 				row_bar();
 				lap(16);
-				umin = fminf(fminf(vq_umin[row], vq_umin[128 + row]), fminf(vq_umin[256 + row], vq_umin[384 + row]));
 				float l1 = INFINITY, l2 = INFINITY;
 				int kbest = 0;
 #pragma unroll
 				for (int o = 0; o < 4; ++o) {  // ascending code ranges
-					const float a1 = vq_lo1[o * 128 + row], a2 = vq_lo2[o * 128 + row];
-					if (a1 < l1) {
+					const float b1 = vq_lo1[o * 128 + row], b2 = vq_lo2[o * 128 + row];
+					if (b1 < l1) {
 						l2 = l1;
-						l1 = a1;
+						l1 = b1;
 						kbest = vq_k1[o * 128 + row];
 					} else {
-						l2 = fminf(l2, a1);
+						l2 = fminf(l2, b1);
 					}
-					l2 = fminf(l2, a2);
+					l2 = fminf(l2, b2);
 				}
-				// non-finite scores (inf / nan inputs) fail `l2 > umin` and take the exact path
-				const bool amb = valid4 && (!(l2 > umin) || tap_stage == 5);
+				const float umin = l1 + bmax;  // >= min_j (a_j + B_j)
+				// a non-finite row (inf / nan inputs; fminf would skip a nan score) takes the exact path
+				const bool amb = valid4 && (!(l2 > umin + bmax) || !(xx < INFINITY) || tap_stage == 5);
 				uint32_t any_amb;
 				asm volatile(
 				    "{\n.reg .pred p, q;\nsetp.ne.u32 q, %1, 0;\nbar.red.or.pred p, 1, 512, q;\nselp.u32 %0, 1, 0, p;\n}\n"
@@ -1092,7 +1088,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			//      its input has been in A8 since the res32 phase — may start now that the accumulators are drained ----
 			if (has_next) {
 				row_bar();  // every row thread is done with z and with the TMEM scores
-				for (uint32_t i = tid; i < kYBytes / 16; i += kRowThreads) reinterpret_cast<uint4*>(smem + kOffY)[i] = make_uint4(0, 0, 0, 0);
+				for (uint32_t i = tid; i < (kOffZs - kOffY + kZsBytes) / 16; i += kRowThreads) reinterpret_cast<uint4*>(smem + kOffY)[i] = make_uint4(0, 0, 0, 0);
 				signal_a_ready(bars, lane);
 			}
 			lap(18);

@@ -75,7 +75,7 @@ void build_encoder_vq_fold(const WeightPack& p, std::vector<float>& m, std::vect
 		throw std::runtime_error("encoder VQ fold: unexpected proj / codebook shapes");
 	m.assign((size_t)256 * 32, 0.f);
 	esq_fold.assign(256, 0.f);
-	m_norm.assign(256, 0.f);
+	m_norm.assign(257, 0.f);  // [256] = the maximum
 	for (int k = 0; k < 256; ++k) {
 		double e2 = 0.0, be = 0.0, n2 = 0.0;
 		for (int d = 0; d < 128; ++d) {
@@ -90,6 +90,7 @@ void build_encoder_vq_fold(const WeightPack& p, std::vector<float>& m, std::vect
 		}
 		esq_fold[k] = (float)(e2 - 2.0 * be);
 		m_norm[k] = std::nextafter((float)std::sqrt(n2), INFINITY);  // never under-estimates |M_k|
+		m_norm[256] = m_norm[k] > m_norm[256] ? m_norm[k] : m_norm[256];
 	}
 }
 

@@ -37,7 +37,7 @@ struct EncoderTcStream {
 
 // Builds the unit stream on the host and fills table.off / table.bytes (table.units is set by the caller after upload).
 std::vector<uint8_t> build_encoder_tc_units(const WeightPack& pack, EncoderTcStream& table);
-// m [256][32] fp32, esq_fold[k] = |e_k|^2 - 2 b.e_k, m_norm[k] >= |M_k| (rounded up; only used in the shortlist bound)
+// m [256][32] fp32, esq_fold[k] = |e_k|^2 - 2 b.e_k, m_norm[k] >= |M_k| (rounded up; only used in the shortlist bound), m_norm[256] = max_k
 void build_encoder_vq_fold(const WeightPack& pack, std::vector<float>& m, std::vector<float>& esq_fold, std::vector<float>& m_norm);
 
 }  // namespace vqvdb

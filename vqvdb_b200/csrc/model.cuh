@@ -25,7 +25,7 @@ struct EncoderWeights {
 	const float *emb_norm;             // |e_k| [256], rounded up: only used in the shortlist bound
 	const float *emb;                  // quantizer.embedding [256][128] fp32 (exact re-scoring)
 	const float *fold_esq;             // |e_k|^2 - 2 proj.bias.e_k [256]   (tensor-core encoder: proj folded into the codebook)
-	const float *fold_norm;            // |proj.weight^T e_k| [256], rounded up: only used in the shortlist bound
+	const float *fold_norm;            // |proj.weight^T e_k| [256] + their maximum [1], rounded up: only used in the shortlist bound
 };
 
 // The encoder consumes its weights as a fixed stream of "units" (<= 8 KB) through a shared-memory ring:
