@@ -76,6 +76,10 @@ constexpr int kXsPitch = 36;
 constexpr uint32_t kXsBytes = 64 * kXsPitch * 4;                // 9 216
 constexpr int kZsPitch = 132;
 constexpr uint32_t kZsBytes = 64 * kZsPitch * 4;                // 33 792
+// the VQ GEMM's A operand: the attention output split into fp16 hi / lo planes, 64 DENSE rows (latent positions) stored
+// twice — MMA rows 64..127 repeat rows 0..63, so all four TMEM lane quadrants (= all four SM sub-partitions) share the
+// score pass: rows 0..63 take codes 0..127, rows 64..127 codes 128..255
+constexpr uint32_t kXhPlane = 128 * 16, kXhPrec = 4 * kXhPlane, kXhBytes = 2 * kXhPrec;          // 16 384
 constexpr int kX32Pitch = 36;
 
 constexpr uint32_t kOffRing = 0;
@@ -84,6 +88,7 @@ constexpr uint32_t kOffY = kOffA8 + kA8Bytes;                   // 100 352
 constexpr uint32_t kOffWp = kOffY;                              // Y is cleared again once the leaf's indices are out
 constexpr uint32_t kOffXs = kOffWp + kWpBytes;
 constexpr uint32_t kOffZs = kOffXs + kXsBytes;
+constexpr uint32_t kOffXh = kOffZs + kZsBytes;
 constexpr uint32_t kOffH = kOffY + kYBytes;                     // 182 272
 constexpr uint32_t kOffIn = kOffH + kHBytes;                    // in_halo [10][10][10] fp32 (4096 reserved)
 constexpr uint32_t kOffPreW = kOffIn + 4096;                    // pre.0 weights [27][16] fp32
@@ -97,7 +102,7 @@ constexpr uint32_t kOffBar = kOffXq + 512;                      // mbarriers
 constexpr uint32_t kNumBars = 2 * kStages + 2;
 constexpr uint32_t kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemSlot + 16;
-static_assert(kOffZs + kZsBytes <= kOffY + kYBytes, "the VQ overlays fit inside the Y region");
+static_assert(kOffXh + kXhBytes <= kOffY + kYBytes && kOffXh % 16 == 0, "the VQ overlays fit inside the Y region");
 static_assert(kSmemBytes <= 227 * 1024, "encode_tc smem budget");
 static_assert(kOffBar % 8 == 0 && kOffA8 % 1024 == 0 && kOffY % 1024 == 0 && kOffH % 1024 == 0, "alignment");
 
@@ -319,7 +324,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 	extern __shared__ __align__(1024) uint8_t smem[];
 	const uint32_t s_base = smem_u32(smem);
 	const uint32_t ring = s_base + kOffRing, bars = s_base + kOffBar;
-	const uint32_t a8 = s_base + kOffA8, yb = s_base + kOffY, hb = s_base + kOffH;
+	const uint32_t a8 = s_base + kOffA8, yb = s_base + kOffY, hb = s_base + kOffH, xh = s_base + kOffXh;
 	float* in_halo = reinterpret_cast<float*>(smem + kOffIn);
 	float* s_prew = reinterpret_cast<float*>(smem + kOffPreW);
 	float* x32s = reinterpret_cast<float*>(smem + kOffX32);
@@ -410,6 +415,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			const uint64_t a8_d = make_desc(a8 + kA8Margin * 16, kA8Plane, 128);
 			const uint64_t y_d = make_desc(yb, kYPlane, 128);
 			const uint64_t h_d = make_desc(hb + kHMargin * 16, kHPlane, 128);
+			const uint64_t xh_d = make_desc(xh, kXhPlane, 128);
 			auto wait_a = [&]() {
 				const long long c0 = prof_clock<kProf>();
 				mbar_wait(bar_a_ready(bars), a_count & 1u);
@@ -512,11 +518,11 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				for (int ks = 0; ks < 2; ++ks) {
 					const uint32_t wb = wait_w();
 					const long long c0 = prof_clock<kProf>();
-					const uint64_t ad = h_d + (uint64_t)(ks * 2 * (int)(kHPlane >> 4));
+					const uint64_t ad = xh_d + (uint64_t)(ks * 2 * (int)(kXhPlane >> 4));
 					const uint64_t bh = make_desc(wb, 256 * 16, 128), bl = make_desc(wb + 8192, 256 * 16, 128);
 					mma_ss(tmem, ad, bh, idesc_f16(256), ks > 0 ? 1u : 0u);
 					mma_ss(tmem + 256, ad, bl, idesc_f16(256), ks > 0 ? 1u : 0u);
-					mma_ss(tmem + 256, ad + (kHPrec >> 4), bh, idesc_f16(256), 1u);
+					mma_ss(tmem + 256, ad + (kXhPrec >> 4), bh, idesc_f16(256), 1u);
 					release_w();
 					if (kProf) t_issue += prof_clock<kProf>() - c0;
 				}
@@ -903,8 +909,10 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 #pragma unroll
 						for (int c = 0; c < 8; ++c) tap_out[(leaf * 32 + g * 8 + c) * 64 + p4] = v[c];
 					}
-					store_split8(h_mine, kHPrec, v);
-					// fp32 copy of the row (z = W x + b of the near-tie rows) and this thread's share of |x|^2 (shortlist bound)
+					// the VQ GEMM's A operand (dense rows, stored twice) ...
+					store_split8(xh + (uint32_t)g * kXhPlane + (uint32_t)p4 * 16, kXhPrec, v);
+					store_split8(xh + (uint32_t)g * kXhPlane + (uint32_t)(64 + p4) * 16, kXhPrec, v);
+					// ... an fp32 copy of the row (z = W x + b of the near-tie rows) and this thread's share of |x|^2 (shortlist bound)
 					*reinterpret_cast<float4*>(xs + p4 * kXsPitch + g * 8) = make_float4(v[0], v[1], v[2], v[3]);
 					*reinterpret_cast<float4*>(xs + p4 * kXsPitch + g * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
 					float xxp = 0.f;
@@ -929,47 +937,49 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			//     (a superset of {a_k - B_k <= min_j (a_j + B_j)}) is re-scored with the reference's fp32 formula, sequential
 			//     in d; the fp32 arg-min and all its ties are in that shortlist.  The step is entered by the whole CTA when
 			//     any of its 64 rows needs it.
-			//  GEMM row = flattened 4^3 row (as in the res32 tiles).  The four threads of a row take 64 codes each;
-			//  tcgen05.ld is warp-collective, so every lane runs the loads.
+			//  GEMM row r = latent position r & 63; the eight threads of a position (4 channel groups x 2 row copies) take 32
+			//  codes each, ascending with o8 = (r >> 6) * 4 + g.  tcgen05.ld is warp-collective, so every lane runs the loads.
+			const int vp = row & 63, o8 = (row >> 6) * 4 + g, kb = o8 * 32;
 			wait_accumulator(rc);
 			row_bar();  // the |x|^2 partials and fp32 x rows of all four groups are in place
 			lap(15);
 			{
-				const float* xp = xs + (valid4 ? p4 : 0) * kXsPitch + 32;
+				const float* xp = xs + vp * kXsPitch + 32;
 				const float xx = (xp[0] + xp[1]) + (xp[2] + xp[3]);
 				const float cb = 4e-6f * sqrtf(xx);
 				const float bmax = fmaf(cb, s_mno[256], 1e-4f);
 				float a1 = INFINITY, a2 = INFINITY;
 				int k1 = 0;
-#pragma unroll 1
-				for (int ch = 0; ch < 4; ++ch) {
-					float hh[16], mx[16];
-					tmem_ld16_nowait(rc.tlane + g * 64 + ch * 16, hh);
-					tmem_ld16_nowait(rc.tlane + 256 + g * 64 + ch * 16, mx);
+				{
+					float hh[2][16], mx[2][16];
+					tmem_ld16_nowait(rc.tlane + kb, hh[0]);
+					tmem_ld16_nowait(rc.tlane + 256 + kb, mx[0]);
+					tmem_ld16_nowait(rc.tlane + kb + 16, hh[1]);
+					tmem_ld16_nowait(rc.tlane + 256 + kb + 16, mx[1]);
 					tmem_wait_ld();
 #pragma unroll
-					for (int j = 0; j < 16; ++j) {
-						const int k = g * 64 + ch * 16 + j;
-						const float a = s_esq2[k] - 2.f * fmaf(mx[j], kLoInv, hh[j]);
+					for (int j = 0; j < 32; ++j) {
+						const int k = kb + j;
+						const float a = s_esq2[k] - 2.f * fmaf(mx[j >> 4][j & 15], kLoInv, hh[j >> 4][j & 15]);
 						k1 = a < a1 ? k : k1;  // codes ascend: strict < keeps the lowest code among equal scores
 						a2 = fminf(a2, fmaxf(a1, a));
 						a1 = fminf(a1, a);
 					}
 				}
-				vq_lo1[g * 128 + row] = a1;
-				vq_lo2[g * 128 + row] = a2;
-				vq_k1[g * 128 + row] = k1;
+				vq_lo1[o8 * 64 + vp] = a1;
+				vq_lo2[o8 * 64 + vp] = a2;
+				vq_k1[o8 * 64 + vp] = k1;
 				row_bar();
 				lap(16);
 				float l1 = INFINITY, l2 = INFINITY;
 				int kbest = 0;
 #pragma unroll
-				for (int o = 0; o < 4; ++o) {  // ascending code ranges
-					const float b1 = vq_lo1[o * 128 + row], b2 = vq_lo2[o * 128 + row];
+				for (int o = 0; o < 8; ++o) {  // ascending code ranges
+					const float b1 = vq_lo1[o * 64 + vp], b2 = vq_lo2[o * 64 + vp];
 					if (b1 < l1) {
 						l2 = l1;
 						l1 = b1;
-						kbest = vq_k1[o * 128 + row];
+						kbest = vq_k1[o * 64 + vp];
 					} else {
 						l2 = fminf(l2, b1);
 					}
@@ -977,7 +987,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				}
 				const float umin = l1 + bmax;  // >= min_j (a_j + B_j)
 				// a non-finite row (inf / nan inputs; fminf would skip a nan score) takes the exact path
-				const bool amb = valid4 && (!(l2 > umin + bmax) || !(xx < INFINITY) || tap_stage == 5);
+				const bool amb = !(l2 > umin + bmax) || !(xx < INFINITY) || tap_stage == 5;
 				uint32_t any_amb;
 				asm volatile(
 				    "{\n.reg .pred p, q;\nsetp.ne.u32 q, %1, 0;\nbar.red.or.pred p, 1, 512, q;\nselp.u32 %0, 1, 0, p;\n}\n"
@@ -985,61 +995,61 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				    : "r"((uint32_t)amb)
 				    : "memory");  // also: every thread is done reading the exchange arrays
 				if (!any_amb) {
-					if (g == 0 && valid4) indices[leaf * 64 + p4] = (uint8_t)kbest;  // p4 = (d*4+h)*4+w == view(B,4,4,4)
+					if (o8 == 0) indices[leaf * 64 + vp] = (uint8_t)kbest;  // vp = (d*4+h)*4+w == view(B,4,4,4)
 					lap(17);
 				} else {
-					// z rows of this warp's near-tie rows: lane l computes dim 32g + l, sequential in c from the bias
-					for (uint32_t m = __ballot_sync(0xffffffffu, amb); m; m &= m - 1) {
-						const int r = __ffs((int)m) - 1;
-						const int rp = __shfl_sync(0xffffffffu, p4, r);
-						const float* xr = xs + rp * kXsPitch;
-						float acc = sp_c[par::proj_b + g * 32 + lane];
+					// z rows of the near-tie positions (the warps of row copy 0): lane l computes dim 32g + l, sequential in c
+					// from the bias
+					if (row < 64) {
+						for (uint32_t m = __ballot_sync(0xffffffffu, amb); m; m &= m - 1) {
+							const int r = __ffs((int)m) - 1;
+							const int rp = __shfl_sync(0xffffffffu, vp, r);
+							const float* xr = xs + rp * kXsPitch;
+							float acc = sp_c[par::proj_b + g * 32 + lane];
 #pragma unroll 8
-						for (int c = 0; c < 32; ++c) acc = fmaf(xr[c], s_wp[c * 128 + g * 32 + lane], acc);
-						zs[rp * kZsPitch + g * 32 + lane] = acc;
+							for (int c = 0; c < 32; ++c) acc = fmaf(xr[c], s_wp[c * 128 + g * 32 + lane], acc);
+							zs[rp * kZsPitch + g * 32 + lane] = acc;
+						}
 					}
 					row_bar();
-					if (amb) {  // |z|^2 as four per-group partial sums, each sequential in d
+					if (amb && row < 64) {  // |z|^2 as four per-group partial sums, each sequential in d
 						float zzp = 0.f;
 #pragma unroll 8
 						for (int d = 0; d < 32; ++d) {
-							const float zv = zs[p4 * kZsPitch + g * 32 + d];
+							const float zv = zs[vp * kZsPitch + g * 32 + d];
 							zzp = fmaf(zv, zv, zzp);
-							if (tap_stage == 5) tap_out[(leaf * 128 + g * 32 + d) * 64 + p4] = zv;
+							if (tap_stage == 5) tap_out[(leaf * 128 + g * 32 + d) * 64 + vp] = zv;
 						}
-						zs[p4 * kZsPitch + 128 + g] = zzp;
+						zs[vp * kZsPitch + 128 + g] = zzp;
 					}
-					unsigned long long mask = 0ull;
-					if (__any_sync(0xffffffffu, amb)) {
-#pragma unroll 1
-						for (int ch = 0; ch < 4; ++ch) {  // the scores are read again rather than kept in 64 registers
-							float hh[16], mx[16];
-							tmem_ld16_nowait(rc.tlane + g * 64 + ch * 16, hh);
-							tmem_ld16_nowait(rc.tlane + 256 + g * 64 + ch * 16, mx);
-							tmem_wait_ld();
-							uint32_t m16 = 0u;
+					uint32_t mask = 0u;
+					if (__any_sync(0xffffffffu, amb)) {  // the scores are read again rather than kept in registers
+						float hh[2][16], mx[2][16];
+						tmem_ld16_nowait(rc.tlane + kb, hh[0]);
+						tmem_ld16_nowait(rc.tlane + 256 + kb, mx[0]);
+						tmem_ld16_nowait(rc.tlane + kb + 16, hh[1]);
+						tmem_ld16_nowait(rc.tlane + 256 + kb + 16, mx[1]);
+						tmem_wait_ld();
 #pragma unroll
-							for (int j = 0; j < 16; ++j) {
-								const int k = g * 64 + ch * 16 + j;
-								const float a = s_esq2[k] - 2.f * fmaf(mx[j], kLoInv, hh[j]);
-								if (!(a - fmaf(cb, s_mno[k], 1e-4f) > umin)) m16 |= 1u << j;
-							}
-							mask |= (unsigned long long)m16 << (ch * 16);
+						for (int j = 0; j < 32; ++j) {
+							const int k = kb + j;
+							const float a = s_esq2[k] - 2.f * fmaf(mx[j >> 4][j & 15], kLoInv, hh[j >> 4][j & 15]);
+							if (!(a - fmaf(cb, s_mno[k], 1e-4f) > umin)) mask |= 1u << j;
 						}
 					}
-					if (!amb) mask = 0ull;
+					if (!amb) mask = 0u;
 					row_bar();
-					const float* zrow = zs + (amb ? p4 : 0) * kZsPitch;
+					const float* zrow = zs + vp * kZsPitch;
 					const float zz = (zrow[128] + zrow[129]) + (zrow[130] + zrow[131]);
 					float best = INFINITY;
 					int bi = 0x7fffffff;
 					while (mask) {  // two candidates per trip: two independent FMA chains
-						const int b0 = __ffsll((long long)mask) - 1;
+						const int b0 = __ffs((int)mask) - 1;
 						mask &= mask - 1;
-						const bool two = mask != 0ull;
-						const int b1 = two ? __ffsll((long long)mask) - 1 : b0;
+						const bool two = mask != 0u;
+						const int b1 = two ? __ffs((int)mask) - 1 : b0;
 						mask &= mask - 1;  // no-op on zero
-						const int code0 = g * 64 + b0, code1 = g * 64 + b1;
+						const int code0 = kb + b0, code1 = kb + b1;
 						const float4* e0 = reinterpret_cast<const float4*>(w.emb + code0 * 128);
 						const float4* e1 = reinterpret_cast<const float4*>(w.emb + code1 * 128);
 						float dot0 = 0.f, dot1 = 0.f;
@@ -1063,24 +1073,24 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 						}
 					}
 					lap(17);
-					vq_umin[g * 128 + row] = best;
-					vq_k1[g * 128 + row] = bi;
+					vq_umin[o8 * 64 + vp] = best;
+					vq_k1[o8 * 64 + vp] = bi;
 					row_bar();
-					if (g == 0 && valid4) {
+					if (o8 == 0) {
 						if (amb) {
 #pragma unroll
-							for (int o = 1; o < 4; ++o) {  // ascending code ranges: strict < keeps the lowest code among equal distances
-								const float ob = vq_umin[o * 128 + row];
+							for (int o = 1; o < 8; ++o) {  // ascending code ranges: strict < keeps the lowest code among equal distances
+								const float ob = vq_umin[o * 64 + vp];
 								if (ob < best) {
 									best = ob;
-									bi = vq_k1[o * 128 + row];
+									bi = vq_k1[o * 64 + vp];
 								}
 							}
 							if (bi == 0x7fffffff) bi = kbest;  // every distance was nan: keep the shortlist's choice
 						} else {
 							bi = kbest;
 						}
-						indices[leaf * 64 + p4] = (uint8_t)bi;
+						indices[leaf * 64 + vp] = (uint8_t)bi;
 					}
 				}
 			}
@@ -1088,7 +1098,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			//      its input has been in A8 since the res32 phase — may start now that the accumulators are drained ----
 			if (has_next) {
 				row_bar();  // every row thread is done with z and with the TMEM scores
-				for (uint32_t i = tid; i < (kOffZs - kOffY + kZsBytes) / 16; i += kRowThreads) reinterpret_cast<uint4*>(smem + kOffY)[i] = make_uint4(0, 0, 0, 0);
+				for (uint32_t i = tid; i < (kOffXh - kOffY + kXhBytes) / 16; i += kRowThreads) reinterpret_cast<uint4*>(smem + kOffY)[i] = make_uint4(0, 0, 0, 0);
 				signal_a_ready(bars, lane);
 			}
 			lap(18);
