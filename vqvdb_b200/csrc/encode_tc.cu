@@ -1098,8 +1098,10 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			//      its input has been in A8 since the res32 phase — may start now that the accumulators are drained ----
 			if (has_next) {
 				row_bar();  // every row thread is done with z and with the TMEM scores
-				for (uint32_t i = tid; i < (kOffXh - kOffY + kXhBytes) / 16; i += kRowThreads) reinterpret_cast<uint4*>(smem + kOffY)[i] = make_uint4(0, 0, 0, 0);
 				signal_a_ready(bars, lane);
+				// the clear runs under conv1's MMAs; the GroupNorm barriers of the conv1 epilogue order it before the conv2
+				// epilogue's stores into Y
+				for (uint32_t i = tid; i < (kOffXh - kOffY + kXhBytes) / 16; i += kRowThreads) reinterpret_cast<uint4*>(smem + kOffY)[i] = make_uint4(0, 0, 0, 0);
 			}
 			lap(18);
 		}
