@@ -120,6 +120,32 @@ def gen_leaves_gpu(n, device, seed):
     return out
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """One process per GPU: run this rank's host threads — and therefore allocate its pinned staging buffers — on the
+    NUMA node the GPU's PCIe root hangs off, so the H2D / D2H streams of the 8 ranks do not cross the socket
+    interconnect.  Returns a short description for the JSON line, or None when the topology cannot be read."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "node %d (%d cpus)" % (node, len(cpus))
+    except Exception:
+        return None
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (its LibTorch backend,
     compiled unmodified into oracle/_ref), all host threads, batch 512, bounded sample per step."""
@@ -256,6 +282,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the B200 backend has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     json_fd = None
     if world > 1:
         # NCCL prints its version banner on stdout when NCCL_DEBUG is set: park fd 1 on stderr for the run and print
@@ -408,6 +435,7 @@ def main():
             "config": {"workload": "roundtrip_1M_float_leaves", "leaves_per_gpu": L, "weights": "shipped float model C=1 D=128 K=256",
                        "sharding": "leaf ranges, one rank per GPU" + ((", decode kernels store straight into rank 0's buffer over NVLink (CUDA IPC)" if peer is not None else ", NCCL gather of decoded blocks to rank 0") if world > 1 else ""),
                        "l2": "inputs (%.2f GB/step) exceed the 126 MB L2; no explicit flush" % (L * 2048 / 1e9),
+                       "numa": ("rank 0 bound to its GPU's NUMA " + numa) if numa else "not bound",
                        "encode_path": codec.encode_path, "decode_path": codec.decode_path},
             "parts": {"encode_ms": enc_ms, "decode_ms": dec_ms,
                       "encode_leaves_per_s": L / (enc_ms / 1e3), "decode_leaves_per_s": L / (dec_ms / 1e3)},
