@@ -401,9 +401,10 @@ def main():
         dec_peak = peak if dec_tc else hmma_peak if tensor_path else ffma_peak
         dec_issued_flop = FLOP_DECODE_FOLDED if codec.decode_path.endswith("_fold") else FLOP_DECODE
         dec_issued_tf = dec_issued_flop * L / (dec_ms / 1e3) / 1e12
-        # tensor-core encoder: every conv is three fp16 products (hi*hi, hi*lo, lo*hi) and the VQ scores one bf16 product,
-        # pre.0 stays on FFMA: MACs issued to the tensor pipe per leaf = 3 * (13 197 824 - 221 184) + 2 097 152
-        enc_issued_tf = (3 * (13197824 - 221184) + 2097152) * 2 * L / (enc_ms / 1e3) / 1e12
+        # tensor-core encoder: every GEMM is three fp16 products (hi*hi, hi*lo, lo*hi); pre.0 (221 184 MAC) stays on FFMA and
+        # proj (262 144 MAC) is folded into the codebook, whose score GEMM shrinks from 64x128x256 to 64x32x256 (524 288 MAC):
+        # MACs issued to the tensor pipe per leaf = 3 * (13 197 824 - 221 184 - 262 144 + 524 288)
+        enc_issued_tf = 3 * (13197824 - 221184 - 262144 + 524288) * 2 * L / (enc_ms / 1e3) / 1e12
         kernels = {
             ("encode_tc_kernel" if enc_tc else "encode_fp32_kernel"): {
                 "ms": enc_ms, "share_of_step": enc_ms / (enc_ms + dec_ms), "achieved_tflops": enc_tf,
