@@ -1,12 +1,30 @@
-import sys, os
+"""Small encode + decode through the default (tcgen05) paths for compute-sanitizer:
+
+    compute-sanitizer --tool memcheck  python tools/sanitizer_run.py 300
+    compute-sanitizer --tool racecheck python tools/sanitizer_run.py 300
+
+Also drives the encoder's near-tie path on every row (debug tap stage 5) and the unfolded N = 192 decoder."""
+import os
+import sys
+
 sys.path.insert(0, os.getcwd())
-import numpy as np, torch
-from vqvdb_b200 import BackendType, CodecConfig, DataType, IVQVAECodec, TensorView, synth
+import numpy as np  # noqa: E402,F401
+import torch  # noqa: E402
+
+from vqvdb_b200 import BackendType, CodecConfig, DataType, IVQVAECodec, TensorView, synth  # noqa: E402
+
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 x = synth.smoke_leaves(n, seed=5)
-for prec in ("fp16x2_tc",):
-    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, encode_precision=prec), BackendType.B200)
+for dec in ("default", "bf16_tc2"):
+    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, encode_precision="fp16x2_tc", decode_precision=dec), BackendType.B200)
     idx = c.encode(TensorView(x, list(x.shape), DataType.FLOAT32)).buffer
     rec = c.decode(TensorView(idx, list(idx.shape), DataType.UINT8)).buffer
-    print(prec, idx.sum(), float(rec.sum()))
+    print(c.encode_path, c.decode_path, idx.sum(), float(rec.sum()))
+    if dec == "default":  # exact (near-tie) path of the VQ on every row
+        xd = torch.from_numpy(x).cuda()
+        tap = torch.zeros((n, 128, 64), dtype=torch.float32, device="cuda")
+        idx_d = torch.empty((n, 4, 4, 4), dtype=torch.uint8, device="cuda")
+        c.debug_encode_tap(xd, n, 5, tap, idx_d, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        print("forced exact path: indices equal", bool((idx_d.cpu().numpy() == idx).all()))
     c.close()

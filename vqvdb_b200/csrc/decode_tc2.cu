@@ -581,6 +581,10 @@ decode_tc2_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices
 				wait_accumulator<kProf>(wk);  // all reads of the conv input are done: the whole leaf region is free
 				lap(6);
 				load_conv32(wk, v);
+				// The accumulator hand-over already orders every staging read of this leaf's rows before the stores below (a
+				// unit's loads feed the tcgen05.st that precedes its a_full arrival); the barrier states the same thing in
+				// terms compute-sanitizer's racecheck can follow, and costs nothing: all 128 threads just left the same wait.
+				leaf_bar(wk);
 				// G as fp32 [64 pos][64 ch] over the leaf region (256-B rows; 16-B chunks swizzled by pos & 7 inside each half row)
 #pragma unroll
 				for (int q = 0; q < 8; ++q) {
