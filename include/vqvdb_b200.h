@@ -152,6 +152,12 @@ VQVDB_B200_API int vqvdb_b200_debug_decode_tap(vqvdb_b200_codec* codec, const ui
  * up_conv -> PixelShuffle3D -> final of python/VQVAE_v2.py:266-275 evaluated layer by layer). */
 VQVDB_B200_API int vqvdb_b200_debug_fold_decoder_tail(const char* weights_path, float* weights_out, float* bias_out);
 
+/* Host-only checker hook (no device needed): the tensor-core encoder's `proj x codebook` fold of the weight pack at
+ * `weights_path` (NULL or "" = the embedded pack) — m_out [256][32] = E . proj.weight, esq_out [256] = |e_k|^2 - 2 proj.bias.e_k,
+ * norm_out [257] = |M_k| rounded up and their maximum (csrc/encode_tc_stream.hpp; tests/test_encoder_fold.py checks
+ * |W x + b - e_k|^2 - |W x + b|^2 == esq_k - 2 x.M_k against python/save_for_inference.py:55-61 evaluated directly). */
+VQVDB_B200_API int vqvdb_b200_debug_fold_encoder_vq(const char* weights_path, float* m_out, float* esq_out, float* norm_out);
+
 /* Name of the encode path in use: "fp32" or "fp16x2_tcgen05". */
 VQVDB_B200_API const char* vqvdb_b200_encode_path(const vqvdb_b200_codec* codec);
 /* Bring-up aid for the tensor-core encoder: runs it and also writes an fp32 activation to dev_tap — stage 0: pre

@@ -25,7 +25,7 @@ EXPORTS = [  # every symbol include/vqvdb_b200.h declares
     "vqvdb_b200_decode_path", "vqvdb_b200_last_error", "vqvdb_b200_version", "vqvdb_b200_debug_decode_tap",
     "vqvdb_b200_encode_path", "vqvdb_b200_debug_encode_tap",
     "vqvdb_b200_peer_buffer_create", "vqvdb_b200_peer_buffer_open", "vqvdb_b200_peer_buffer_close",
-    "vqvdb_b200_convert_onnx", "vqvdb_b200_debug_fold_decoder_tail",
+    "vqvdb_b200_convert_onnx", "vqvdb_b200_debug_fold_decoder_tail", "vqvdb_b200_debug_fold_encoder_vq",
 ]
 
 
@@ -86,6 +86,8 @@ def load_library() -> C.CDLL:
     L.vqvdb_b200_convert_onnx.restype = C.c_int
     L.vqvdb_b200_debug_fold_decoder_tail.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p]
     L.vqvdb_b200_debug_fold_decoder_tail.restype = C.c_int
+    L.vqvdb_b200_debug_fold_encoder_vq.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.vqvdb_b200_debug_fold_encoder_vq.restype = C.c_int
     L.vqvdb_b200_synchronize.argtypes = [C.c_void_p]
     L.vqvdb_b200_kernel_launches.argtypes = [C.c_void_p]
     L.vqvdb_b200_kernel_launches.restype = C.c_uint64
@@ -133,6 +135,19 @@ def fold_decoder_tail(weights_path: str = ""):
     if rc != 0:
         raise RuntimeError("vqvdb_b200_debug_fold_decoder_tail failed (%d): %s" % (rc, L.vqvdb_b200_last_error(None).decode()))
     return w, b
+
+
+def fold_encoder_vq(weights_path: str = ""):
+    """The tensor-core encoder's `proj x codebook` fold: (M [256][32], esq [256], norm [257]) as fp32 numpy arrays.  Host-only."""
+    import numpy as np
+    L = load_library()
+    m = np.empty((256, 32), dtype=np.float32)
+    esq = np.empty((256,), dtype=np.float32)
+    norm = np.empty((257,), dtype=np.float32)
+    rc = L.vqvdb_b200_debug_fold_encoder_vq(os.fspath(weights_path).encode(), m.ctypes.data, esq.ctypes.data, norm.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("vqvdb_b200_debug_fold_encoder_vq failed (%d): %s" % (rc, L.vqvdb_b200_last_error(None).decode()))
+    return m, esq, norm
 
 
 def convert_onnx(encoder_onnx: str, decoder_onnx: str, out_pack: str) -> None:

@@ -745,6 +745,23 @@ int vqvdb_b200_debug_fold_decoder_tail(const char* weights_path, float* weights_
 	return VQVDB_B200_OK;
 }
 
+int vqvdb_b200_debug_fold_encoder_vq(const char* weights_path, float* m_out, float* esq_out, float* norm_out) {
+	if (!m_out || !esq_out || !norm_out) return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "debug_fold_encoder_vq: null output");
+	try {
+		WeightPack pack;
+		if (weights_path && weights_path[0]) pack.load_file(weights_path);
+		else pack.parse(vqvdb::vqvdb_b200_embedded_pack, (size_t)(vqvdb::vqvdb_b200_embedded_pack_end - vqvdb::vqvdb_b200_embedded_pack));
+		std::vector<float> m, esq, mno;
+		vqvdb::build_encoder_vq_fold(pack, m, esq, mno);
+		std::memcpy(m_out, m.data(), m.size() * sizeof(float));
+		std::memcpy(esq_out, esq.data(), esq.size() * sizeof(float));
+		std::memcpy(norm_out, mno.data(), mno.size() * sizeof(float));
+	} catch (const std::exception& e) {
+		return fail(nullptr, VQVDB_B200_ERR_BAD_WEIGHTS, e.what());
+	}
+	return VQVDB_B200_OK;
+}
+
 const char* vqvdb_b200_decode_path(const vqvdb_b200_codec* c) { return c ? c->decode_path.c_str() : ""; }
 const char* vqvdb_b200_encode_path(const vqvdb_b200_codec* c) { return c ? c->encode_path.c_str() : ""; }
 
