@@ -33,3 +33,4 @@ for i, nm in enumerate(names):
     print("%-36s %8.0f cyc/leaf" % (nm, c))
 print("%-36s %8.0f cyc/leaf" % ("row thread total", tot))
 print("issuer: wait a_ready %.0f  wait w_full %.0f  issue+commit %.0f  total %.0f cyc/leaf" % tuple(p[:, 32 + i].mean() / leaves for i in range(4)))
+print("issuer weight waits by phase: 8^3 convs %.0f  down %.0f  4^3 convs %.0f  VQ %.0f cyc/leaf" % tuple(p[:, 36 + i].mean() / leaves for i in range(4)))

@@ -411,6 +411,8 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 		if (lane == 0) {
 			uint32_t unit = 0, a_count = 0;
 			long long t_wait_a = 0, t_wait_w = 0, t_issue = 0;
+			long long t_wait_w_phase[4] = {0, 0, 0, 0};  // kProf: weight waits per phase (8^3 convs, down, 4^3 convs, VQ)
+			int w_phase = 0;
 			const long long t_start = prof_clock<kProf>();
 			const uint64_t a8_d = make_desc(a8 + kA8Margin * 16, kA8Plane, 128);
 			const uint64_t y_d = make_desc(yb, kYPlane, 128);
@@ -428,7 +430,11 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				const uint32_t s = unit % kStages;
 				mbar_wait(bar_w_full(bars, s), (unit / kStages) & 1u);
 				tc_fence_after();
-				if (kProf) t_wait_w += prof_clock<kProf>() - c0;
+				if (kProf) {
+					const long long dt = prof_clock<kProf>() - c0;
+					t_wait_w += dt;
+					t_wait_w_phase[w_phase] += dt;
+				}
 				return ring + s * kStageBytes;
 			};
 			auto release_w = [&]() {
@@ -440,6 +446,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				// ---- res16 conv1, conv2: 5 tiles x 9 (kd, kh) x {N = 96, N = 48}, in two tile groups (0-2, 3-4) with their own
 				//      completion signal: the row threads drain the first group while the second group's MMAs run ----
 #pragma unroll 1
+				w_phase = 0;
 				for (int layer = 0; layer < 2; ++layer) {
 					wait_a();
 #pragma unroll 1
@@ -471,6 +478,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				//      epilogue).  The tensor core truncates its fp32 accumulator after every MMA, a bias that grows with
 				//      the length of the accumulation chain; every tap pair therefore has its own accumulator
 				//      (kDownChains chains of 8 steps) and the epilogue adds them in fp32. ----
+				w_phase = 1;
 				wait_a();
 #pragma unroll 1
 				for (int u = 0; u < 8; ++u) {  // u = (td, th) tap pair * 2 + half of the parity classes
@@ -492,6 +500,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				tc_commit(bar_d_full(bars));
 				// ---- res32 conv1, conv2: 9 (kd, kh) x 2 k-steps x {N = 192, N = 96} ----
 #pragma unroll 1
+				w_phase = 2;
 				for (int layer = 0; layer < 2; ++layer) {
 					wait_a();
 #pragma unroll 1
@@ -513,6 +522,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				}
 				// ---- VQ scores straight from the attention output (proj folded into the codebook): 2 k-steps x
 				//      {x_hi.M_hi -> cols 0..255 ; x_hi.M_lo + x_lo.M_hi -> cols 256..511}, N = 256 ----
+				w_phase = 3;
 				wait_a();
 #pragma unroll 1
 				for (int ks = 0; ks < 2; ++ks) {
@@ -531,6 +541,8 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			if (kProf && tap_out) {
 				float* o = tap_out + (size_t)blockIdx.x * 64 + 32;
 				o[0] = (float)t_wait_a; o[1] = (float)t_wait_w; o[2] = (float)t_issue; o[3] = (float)(prof_clock<kProf>() - t_start);
+#pragma unroll
+				for (int i = 0; i < 4; ++i) o[4 + i] = (float)t_wait_w_phase[i];
 			}
 		}
 		__syncwarp();
