@@ -34,6 +34,11 @@ FLOP_DECODE = 114.14e6
 FLOP_DECODE_FOLDED = (128 * 64 + 3 * 64 * 64) * 27 * 64 * 2.0
 
 
+# ncu --set full, 59 200 leaves: encode_tc_kernel read 122.51 MB + wrote 7.90 MB; decode_tc2_kernel<fold> read 5.05 MB + wrote 69.74 MB
+NCU_DRAM_BYTES_PER_LEAF = {"encode": (122.509312e6 + 7.897856e6) / 59200, "decode": (5.050880e6 + 69.744896e6) / 59200}
+NCU_DRAM_SOURCE = {"encode": "profiles/r1e_encode_tc_ncu_summary.txt", "decode": "profiles/r1d_decode_tc2_ncu_summary.txt"}
+
+
 def dec_kernel_name(path: str) -> str:
     return {"bf16_tcgen05_n192_fold": "decode_tc2_kernel<fold>", "bf16_tcgen05_n192": "decode_tc2_kernel", "bf16_tcgen05": "decode_tc_kernel",
             "bf16_mma": "decode_mma_kernel"}.get(path, "decode_fp32_kernel")
@@ -401,6 +406,7 @@ def main():
         dec_peak = peak if dec_tc else hmma_peak if tensor_path else ffma_peak
         dec_issued_flop = FLOP_DECODE_FOLDED if codec.decode_path.endswith("_fold") else FLOP_DECODE
         dec_issued_tf = dec_issued_flop * L / (dec_ms / 1e3) / 1e12
+        ncu_applies = (dom == "encode" and enc_tc) or (dom == "decode" and codec.decode_path == "bf16_tcgen05_n192_fold")
         # tensor-core encoder: every GEMM is three fp16 products (hi*hi, hi*lo, lo*hi); pre.0 (221 184 MAC) stays on FFMA and
         # proj (262 144 MAC) is folded into the codebook, whose score GEMM shrinks from 64x128x256 to 64x32x256 (524 288 MAC):
         # MACs issued to the tensor pipe per leaf = 3 * (13 197 824 - 221 184 - 262 144 + 524 288)
@@ -441,7 +447,11 @@ def main():
             "parts": {"encode_ms": enc_ms, "decode_ms": dec_ms,
                       "encode_leaves_per_s": L / (enc_ms / 1e3), "decode_leaves_per_s": L / (dec_ms / 1e3)},
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak,
+                         # DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full captures
+                         # (dram__bytes_read.sum + dram__bytes_write.sum per leaf, scaled to this launch's L leaves)
+                         "traffic": (NCU_DRAM_BYTES_PER_LEAF[dom] * L) if ncu_applies else None, "traffic_source": NCU_DRAM_SOURCE[dom] if ncu_applies else None,
+                         "algorithmic_bytes": (BYTES_DECODE if dom == "decode" else BYTES_ENCODE) * L,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % peaks["source"],
                          "hbm_gbs_nonbinding": (BYTES_DECODE if dom == "decode" else BYTES_ENCODE) * L / (dom_ms / 1e3) / 1e9,
                          "note": "compute-bound path (34 kFLOP/B); achieved = ALGORITHMIC flops / time; %s kernel runs on %s" % (dom, "tensor cores (the encoder issues 3 fp16 products per algorithmic MAC, see kernels.*.issued_tflops)" if dom_on_tensor else "fp32 FFMA (measured CUDA-core peak 71 TFLOP/s, so frac of ITS pipe is %.2f)" % (achieved / ffma_peak)),
