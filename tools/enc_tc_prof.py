@@ -22,9 +22,9 @@ for _ in range(2):
 torch.cuda.synchronize()
 p = prof.cpu().numpy()
 leaves = n / 148.0
-names = ["stage next leaf (+ clear Y)", "pre.0 FFMA + GN pre.1", "gn1 + split -> A8", "wait conv1 MMA", "conv1 epilogue (GN, split)",
+names = ["stage next leaf (+ clear Y)", "pre.0 FFMA + GN pre.1", "gn1 + split -> A8", "wait conv1 MMA", "conv1 epilogue: normalise, split, store",
          "wait conv2 MMA", "conv2 epilogue (residual, -> Y)", "wait down MMA", "down epilogue (GN, -> H32)", "wait res32.c1 MMA",
-         "res32.c1 epilogue", "wait res32.c2 MMA", "res32.c2 epilogue + attention", "(proj: folded into the codebook)", "(proj epilogue: none)",
+         "res32.c1 epilogue", "wait res32.c2 MMA", "res32.c2 epilogue + attention", "  conv1 epilogue: accumulator reads (incl. wait for tile group 2)", "  conv1 epilogue: GroupNorm statistics",
          "wait VQ MMA", "VQ scores -> bounds, two smallest", "VQ decision (+ near-tie rows: z, shortlist, exact re-scoring)", "clear Y"]
 tot = 0.0
 for i, nm in enumerate(names):

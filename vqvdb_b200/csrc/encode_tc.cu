@@ -719,8 +719,10 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 						for (int c = 0; c < 4; ++c) tap_out[(leaf * 16 + g * 4 + c) * 512 + d * 64 + h * 8 + w8] = v[t][c];
 					}
 				}
+				lap(13);
 				float mean[2], rstd[2];
 				gn_stats_regs<5, 4, 2>(v, valid8, 1.f / 1024.f, rc, mean, rstd);
+				lap(14);
 				float ga[4], be[4];
 #pragma unroll
 				for (int c = 0; c < 4; ++c) {
