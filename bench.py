@@ -382,6 +382,22 @@ def main():
     e2e_s = time.perf_counter() - t0
     e2e_checksum = float(hvox[:: max(1, L // 1024)].double().sum())
 
+    # the reference's SOPs call the backend with 64 leaves at a time (their default batch): the same host-pointer calls at
+    # that size, synchronous, one after the other — what a drop-in replacement sees before its caller batches more
+    small = {}
+    if rank == 0:
+        for nb in (64, 8192):
+            reps = max(4, min(400, 131072 // nb))
+            for _ in range(3):
+                codec.encode_into(hx[:nb], nb, hidx[:nb])
+                codec.decode_into(hidx[:nb], nb, hvox[:nb])
+            t0 = time.perf_counter()
+            for i in range(reps):
+                lo = (i * nb) % (L - nb)
+                codec.encode_into(hx[lo:lo + nb], nb, hidx[lo:lo + nb])
+                codec.decode_into(hidx[lo:lo + nb], nb, hvox[lo:lo + nb])
+            small["batch_%d" % nb] = reps * nb / (time.perf_counter() - t0)
+
     t = torch.tensor([ms, e2e_s * 1e3, enc_ms, dec_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -461,6 +477,8 @@ def main():
                     "api": "vqvdb_b200_encode + vqvdb_b200_decode on pinned host buffers", "checksum": e2e_checksum},
             "gpu_launches": launches,
             "clocks": clocks,
+            "e2e_small_batches": {"unit": "leaves/s", **small,
+                                  "note": "roundtrip through the same host-pointer calls, 64 / 8192 leaves per call (the reference SOPs' default batch is 64); compare reference_gpu_backend"},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
