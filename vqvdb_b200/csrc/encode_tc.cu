@@ -99,7 +99,7 @@ constexpr uint32_t kOffCb = kOffAtt + (128 + 8 + 32) * 4;       // emb_sq [256],
 constexpr uint32_t kOffPar = kOffCb + 3088;                     // fold_norm has a 257th entry: its maximum                     // per-channel parameter vectors (ParOff), 1008 floats
 constexpr uint32_t kOffXq = kOffPar + 1008 * 4;                 // `down` epilogue: lane-0 values handed to the previous quadrant [4][4][8]
 constexpr uint32_t kOffBar = kOffXq + 512;                      // mbarriers
-constexpr uint32_t kNumBars = 2 * kStages + 2;
+constexpr uint32_t kNumBars = 2 * kStages + 3;
 constexpr uint32_t kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemSlot + 16;
 static_assert(kOffXh + kXhBytes <= kOffY + kYBytes && kOffXh % 16 == 0, "the VQ overlays fit inside the Y region");
@@ -109,7 +109,10 @@ static_assert(kOffBar % 8 == 0 && kOffA8 % 1024 == 0 && kOffY % 1024 == 0 && kOf
 __device__ __forceinline__ uint32_t bar_w_full(uint32_t bars, uint32_t s) { return bars + s * 8; }
 __device__ __forceinline__ uint32_t bar_w_empty(uint32_t bars, uint32_t s) { return bars + (kStages + s) * 8; }
 __device__ __forceinline__ uint32_t bar_a_ready(uint32_t bars) { return bars + 2 * kStages * 8; }
-__device__ __forceinline__ uint32_t bar_d_full(uint32_t bars) { return bars + (2 * kStages + 1) * 8; }
+// Two accumulator hand-over barriers, used alternately (8 hand-overs per leaf): a waiter may lag the barrier by one phase
+// only, and the two tile groups of an 8^3 conv are committed back to back — with the next leaf's conv1 running under the
+// VQ of this one, both of its commits can land before the row threads get to their first wait.
+__device__ __forceinline__ uint32_t bar_d_full(uint32_t bars, uint32_t which) { return bars + (2 * kStages + 1 + which) * 8; }
 
 // ---- tcgen05 wrappers ----
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -190,7 +193,7 @@ struct RowCtx {
 	float* red;
 };
 __device__ __forceinline__ void wait_accumulator(RowCtx& rc) {
-	mbar_wait(bar_d_full(rc.bars), rc.d_count & 1u);
+	mbar_wait(bar_d_full(rc.bars, rc.d_count & 1u), (rc.d_count >> 1) & 1u);
 	tc_fence_after();
 	++rc.d_count;
 }
@@ -380,7 +383,8 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			mbar_init(bar_w_empty(bars, s), 1);
 		}
 		mbar_init(bar_a_ready(bars), kRowWarps);
-		mbar_init(bar_d_full(bars), 1);
+		mbar_init(bar_d_full(bars, 0), 1);
+		mbar_init(bar_d_full(bars, 1), 1);
 		mbar_fence_init();
 	}
 	if (warp == kIssuerWarp) {
@@ -409,7 +413,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 	} else if (warp == kIssuerWarp) {
 		// ===================== MMA issuer =====================
 		if (lane == 0) {
-			uint32_t unit = 0, a_count = 0;
+			uint32_t unit = 0, a_count = 0, d_commits = 0;
 			long long t_wait_a = 0, t_wait_w = 0, t_issue = 0;
 			long long t_wait_w_phase[4] = {0, 0, 0, 0};  // kProf: weight waits per phase (8^3 convs, down, 4^3 convs, VQ)
 			int w_phase = 0;
@@ -436,6 +440,10 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					t_wait_w_phase[w_phase] += dt;
 				}
 				return ring + s * kStageBytes;
+			};
+			auto commit_d = [&]() {
+				tc_commit(bar_d_full(bars, d_commits & 1u));
+				++d_commits;
 			};
 			auto release_w = [&]() {
 				tc_commit(bar_w_empty(bars, unit % kStages));
@@ -470,7 +478,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 							release_w();
 							if (kProf) t_issue += prof_clock<kProf>() - c0;
 						}
-						tc_commit(bar_d_full(bars));
+						commit_d();
 					}
 				}
 				// ---- down: 4 (td, th) tap pairs x 8 parity classes x {N = 128, N = 64}; the two tw taps of a pair are
@@ -497,7 +505,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					release_w();
 					if (kProf) t_issue += prof_clock<kProf>() - c0;
 				}
-				tc_commit(bar_d_full(bars));
+				commit_d();
 				// ---- res32 conv1, conv2: 9 (kd, kh) x 2 k-steps x {N = 192, N = 96} ----
 #pragma unroll 1
 				w_phase = 2;
@@ -518,7 +526,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 						release_w();
 						if (kProf) t_issue += prof_clock<kProf>() - c0;
 					}
-					tc_commit(bar_d_full(bars));
+					commit_d();
 				}
 				// ---- VQ scores straight from the attention output (proj folded into the codebook): 2 k-steps x
 				//      {x_hi.M_hi -> cols 0..255 ; x_hi.M_lo + x_lo.M_hi -> cols 256..511}, N = 256 ----
@@ -536,7 +544,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					release_w();
 					if (kProf) t_issue += prof_clock<kProf>() - c0;
 				}
-				tc_commit(bar_d_full(bars));
+				commit_d();
 			}
 			if (kProf && tap_out) {
 				float* o = tap_out + (size_t)blockIdx.x * 64 + 32;
@@ -947,10 +955,10 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			//  2. one pass over the scores keeps, per thread, the two smallest a_k and the code of the smallest.  With
 			//     Bmax = max_k B_k, every code that can be the fp32 arg-min has a_k <= min_j a_j + 2 Bmax; a row whose
 			//     second-smallest score exceeds that has exactly one such code: done (~99 % of the rows).
-			//  3. otherwise (near-tie): z = W x + b in fp32 for that row, every code with a_k - B_k <= min_j a_j + Bmax
-			//     (a superset of {a_k - B_k <= min_j (a_j + B_j)}) is re-scored with the reference's fp32 formula, sequential
-			//     in d; the fp32 arg-min and all its ties are in that shortlist.  The step is entered by the whole CTA when
-			//     any of its 64 rows needs it.
+			//  3. otherwise (near-tie): z = W x + b in fp32 for that row, every code with a_k <= min_j a_j + 2 Bmax that is also
+			//     within 2 Bmax of its own thread's minimum (a superset of {a_k - B_k <= min_j (a_j + B_j)}) is re-scored with
+			//     the reference's fp32 formula, sequential in d; the fp32 arg-min and all its ties are in that shortlist.  The
+			//     step is entered by the whole CTA when any of its 64 rows needs it.
 			//  GEMM row r = latent position r & 63; the eight threads of a position (4 channel groups x 2 row copies) take 32
 			//  codes each, ascending with o8 = (r >> 6) * 4 + g.  tcgen05.ld is warp-collective, so every lane runs the loads.
 			const int vp = row & 63, o8 = (row >> 6) * 4 + g, kb = o8 * 32;
@@ -964,6 +972,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				const float bmax = fmaf(cb, s_mno[256], 1e-4f);
 				float a1 = INFINITY, a2 = INFINITY;
 				int k1 = 0;
+				uint32_t near_mask = 0u;  // this thread's codes within 2 Bmax of its smallest score
 				{
 					float hh[2][16], mx[2][16];
 					tmem_ld16_nowait(rc.tlane + kb, hh[0]);
@@ -971,14 +980,22 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					tmem_ld16_nowait(rc.tlane + kb + 16, hh[1]);
 					tmem_ld16_nowait(rc.tlane + 256 + kb + 16, mx[1]);
 					tmem_wait_ld();
+					// The scores are in registers and nothing below reads TMEM again: the accumulators are drained, so the
+					// next leaf's conv1 — its input has been in A8 since the res32 phase — starts under the rest of the VQ.
+					if (has_next) signal_a_ready(bars, lane);
 #pragma unroll
 					for (int j = 0; j < 32; ++j) {
 						const int k = kb + j;
 						const float a = s_esq2[k] - 2.f * fmaf(mx[j >> 4][j & 15], kLoInv, hh[j >> 4][j & 15]);
+						hh[j >> 4][j & 15] = a;
 						k1 = a < a1 ? k : k1;  // codes ascend: strict < keeps the lowest code among equal scores
 						a2 = fminf(a2, fmaxf(a1, a));
 						a1 = fminf(a1, a);
 					}
+					const float near = a1 + 2.f * bmax;
+#pragma unroll
+					for (int j = 0; j < 32; ++j)
+						if (!(hh[j >> 4][j & 15] > near)) near_mask |= 1u << j;
 				}
 				vq_lo1[o8 * 64 + vp] = a1;
 				vq_lo2[o8 * 64 + vp] = a2;
@@ -1036,21 +1053,10 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 						}
 						zs[vp * kZsPitch + 128 + g] = zzp;
 					}
-					uint32_t mask = 0u;
-					if (__any_sync(0xffffffffu, amb)) {  // the scores are read again rather than kept in registers
-						float hh[2][16], mx[2][16];
-						tmem_ld16_nowait(rc.tlane + kb, hh[0]);
-						tmem_ld16_nowait(rc.tlane + 256 + kb, mx[0]);
-						tmem_ld16_nowait(rc.tlane + kb + 16, hh[1]);
-						tmem_ld16_nowait(rc.tlane + 256 + kb + 16, mx[1]);
-						tmem_wait_ld();
-#pragma unroll
-						for (int j = 0; j < 32; ++j) {
-							const int k = kb + j;
-							const float a = s_esq2[k] - 2.f * fmaf(mx[j >> 4][j & 15], kLoInv, hh[j >> 4][j & 15]);
-							if (!(a - fmaf(cb, s_mno[k], 1e-4f) > umin)) mask |= 1u << j;
-						}
-					}
+					// Shortlist of a near-tie row: every code that can be the fp32 arg-min has a_k <= min_j a_j + 2 Bmax, hence lies
+					// within 2 Bmax of the smallest score of ITS thread, whose own minimum must lie in the row's window too —
+					// a superset of {a_k - B_k <= min_j (a_j + B_j)} that needs no second look at the (released) accumulators.
+					uint32_t mask = !(a1 > umin + bmax) ? near_mask : 0u;
 					if (!amb) mask = 0u;
 					row_bar();
 					const float* zrow = zs + vp * kZsPitch;
@@ -1111,10 +1117,9 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			// ---- leaf done: Y (dirtied by the VQ overlays) is cleared for the next conv2 epilogue, and the next leaf's conv1 —
 			//      its input has been in A8 since the res32 phase — may start now that the accumulators are drained ----
 			if (has_next) {
-				row_bar();  // every row thread is done with z and with the TMEM scores
-				signal_a_ready(bars, lane);
-				// the clear runs under conv1's MMAs; the GroupNorm barriers of the conv1 epilogue order it before the conv2
-				// epilogue's stores into Y
+				row_bar();  // every row thread is done with the VQ overlays
+				// conv1 has been running since the scores left TMEM; the clear runs under its MMAs, and the GroupNorm barriers
+				// of the conv1 epilogue order it before the conv2 epilogue's stores into Y
 				for (uint32_t i = tid; i < (kOffXh - kOffY + kXhBytes) / 16; i += kRowThreads) reinterpret_cast<uint4*>(smem + kOffY)[i] = make_uint4(0, 0, 0, 0);
 			}
 			lap(18);
