@@ -209,7 +209,8 @@ __device__ __forceinline__ void group_allreduce(float (&s)[NG], const RowCtx& rc
 #pragma unroll
 		for (int i = 0; i < NG; ++i) red[rc.warp * 2 + i] = s[i];
 	}
-	row_bar();
+	// only the group's own four warps (one per SM sub-partition) meet: named barriers 2 .. 5, 128 threads
+	asm volatile("bar.sync %0, 128;" ::"r"(2 + rc.g) : "memory");
 	const float* r = red + rc.g * 8;  // warps 4g .. 4g+3
 #pragma unroll
 	for (int i = 0; i < NG; ++i) s[i] = (r[i] + r[2 + i]) + (r[4 + i] + r[6 + i]);
