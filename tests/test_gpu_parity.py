@@ -362,6 +362,28 @@ def test_tc_encoder_stage_taps_match_oracle(codec, c_oracle, stage):
     assert np.array_equal(idx.cpu().numpy().reshape(n, 4, 4, 4), _encode(codec, x))   # the tap launch encodes too
 
 
+def test_tc_encoder_exact_path_equals_shortlist_path(codec):
+    # The VQ decides ~99 % of the latents from the tensor-core scores alone (one code inside the error bound) and runs the
+    # exact fp32 path (z = W x + b, reference distance formula) only on near-ties.  Stage-5 taps force the exact path on
+    # EVERY latent: both must give the same index everywhere, on smooth, sparse, noisy, scaled and constant inputs.
+    import torch
+    x = np.concatenate([synth.smoke_leaves(6000, seed=51), synth.smoke_leaves(6000, seed=52, sparse=True),
+                        synth.noise_leaves(3000, seed=53), 1e3 * synth.smoke_leaves(500, seed=54),
+                        1e-3 * synth.smoke_leaves(500, seed=55), np.full((64, 1, 8, 8, 8), 0.37, np.float32)]).astype(np.float32)
+    n = x.shape[0]
+    xd = torch.from_numpy(x).cuda()
+    tap = torch.empty((n, 128, 64), dtype=torch.float32, device="cuda")
+    idx_exact = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
+    idx_fast = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
+    sp = torch.cuda.current_stream().cuda_stream
+    codec.debug_encode_tap(xd, n, 5, tap, idx_exact, sp)
+    codec.encode_device(xd, n, idx_fast, sp)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(tap).all())
+    n_diff = int((idx_exact != idx_fast).sum())
+    assert n_diff == 0, "%d of %d latents differ between the exact and the shortlist path" % (n_diff, n * 64)
+
+
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json's full sizes (configs[1] decode-only and configs[2] roundtrip: 1 M leaves), through properties that do
 # not need a 1 M-leaf oracle run: the two independent encoders (tcgen05 split-fp16 vs CUDA-core fp32) agree, the
