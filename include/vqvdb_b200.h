@@ -53,16 +53,14 @@ typedef enum vqvdb_b200_status {
  * (index parity with the reference is a bit-exactness requirement); the decoder may
  * use BF16 tensor-core operands with fp32 accumulation. */
 typedef enum vqvdb_b200_decode_precision {
-	VQVDB_B200_DECODE_DEFAULT = 0, /* fastest path that meets the 0.1 dB PSNR budget */
-	VQVDB_B200_DECODE_FP32 = 1,    /* CUDA-core fp32 path (bring-up / checking) */
-	VQVDB_B200_DECODE_BF16_TC = 2, /* tcgen05.mma + TMEM accumulators: bf16 operands, fp32 accumulation */
-	VQVDB_B200_DECODE_BF16_MMA = 3, /* same arithmetic on the legacy warp-level mma.sync path */
-	VQVDB_B200_DECODE_BF16_TC2 = 4, /* tcgen05.mma, kw taps concatenated along N (N = 192): a third of the operand staging */
-	VQVDB_B200_DECODE_BF16_TC2_FOLD = 5 /* the same, with up_conv -> PixelShuffle3D -> final folded on the host into one
-	                                      * 64 -> 64 convolution + an 8-term gather per voxel (exact algebra, zero padding
-	                                      * at both resolutions included; weights folded in double, rounded to bf16 once) */
+	VQVDB_B200_DECODE_DEFAULT = 0, /* the tensor-core path: meets the 0.1 dB PSNR budget */
+	VQVDB_B200_DECODE_FP32 = 1,    /* CUDA-core fp32 path (checking path: agrees with the reference reconstruction to 2e-5) */
+	VQVDB_B200_DECODE_BF16_TC = 2  /* tcgen05.mma + TMEM accumulators, bf16 operands, fp32 accumulation; kw taps concatenated
+	                                * along N (N = 192); up_conv -> PixelShuffle3D -> final folded on the host into one 64 -> 64
+	                                * convolution + an 8-term gather per voxel (exact algebra, zero padding at both resolutions
+	                                * included; weights folded in double, rounded to bf16 once) */
 } vqvdb_b200_decode_precision;
-#define VQVDB_B200_DECODE_DEFAULT_KIND VQVDB_B200_DECODE_BF16_TC2_FOLD
+#define VQVDB_B200_DECODE_DEFAULT_KIND VQVDB_B200_DECODE_BF16_TC
 
 /* Encoder arithmetic.  Both paths are fp32-faithful (index parity with the reference is a bit-exactness requirement):
  * the tensor-core path splits every operand into two fp16 planes (22 significant bits, three products, fp32
@@ -115,7 +113,10 @@ VQVDB_B200_API int vqvdb_b200_decode(vqvdb_b200_codec* codec, const uint8_t* hos
 
 /* Device-pointer variants for the pipelined batch loop and the multi-GPU path: buffers live
  * on the codec's device, work is enqueued on `cuda_stream` (a cudaStream_t, used exactly as given:
- * NULL is the CUDA legacy default stream) and the call returns without synchronising. */
+ * NULL is the CUDA legacy default stream) and the call returns without synchronising.
+ * Alignment: dev_leaves and dev_voxels 16 bytes (the kernels move leaves as 128-bit vectors), dev_indices 4 bytes;
+ * anything cudaMalloc returns, offset by whole leaves, qualifies.  Calls on ONE codec must be serialised by the
+ * caller even when they target different streams (the vec3 model's kernels share one per-codec scratch area). */
 VQVDB_B200_API int vqvdb_b200_encode_device(vqvdb_b200_codec* codec, const float* dev_leaves, int64_t n_leaves,
                                             uint8_t* dev_indices, void* cuda_stream);
 VQVDB_B200_API int vqvdb_b200_decode_device(vqvdb_b200_codec* codec, const uint8_t* dev_indices, int64_t n_leaves,
@@ -138,7 +139,7 @@ VQVDB_B200_API int vqvdb_b200_peer_buffer_close(vqvdb_b200_codec* codec, void* d
 
 /* Kernel launches issued by this codec since creation (bench.py's gpu_launches). */
 VQVDB_B200_API uint64_t vqvdb_b200_kernel_launches(const vqvdb_b200_codec* codec);
-/* Name of the decode path actually in use: "fp32", "bf16_tcgen05_n192_fold", "bf16_tcgen05_n192", "bf16_tcgen05" or "bf16_mma". */
+/* Name of the decode path actually in use: "bf16_tcgen05_n192_fold", "fp32", or "fp32_generic" (vec3 model). */
 VQVDB_B200_API const char* vqvdb_b200_decode_path(const vqvdb_b200_codec* codec);
 
 /* Bring-up aid for the tensor-core decoder: runs it and also writes the fp32 activation after stage
@@ -148,7 +149,7 @@ VQVDB_B200_API int vqvdb_b200_debug_decode_tap(vqvdb_b200_codec* codec, const ui
 
 /* Host-only checker hook (no device needed): the folded decoder tail of the weight pack at `weights_path` (NULL or ""
  * = the embedded pack) — conv weights [64 (r*8+eps)][64 cin][27 taps] and bias [64] in fp32, exactly what the
- * *_FOLD decode path rounds to bf16 (see VQVDB_B200_DECODE_BF16_TC2_FOLD; tests/test_decoder_fold.py compares it with
+ * tensor-core decode path rounds to bf16 (see VQVDB_B200_DECODE_BF16_TC; tests/test_decoder_fold.py compares it with
  * up_conv -> PixelShuffle3D -> final of python/VQVAE_v2.py:266-275 evaluated layer by layer). */
 VQVDB_B200_API int vqvdb_b200_debug_fold_decoder_tail(const char* weights_path, float* weights_out, float* bias_out);
 

@@ -47,6 +47,22 @@ VQVDB_HOST_API int vqvdb_host_compress(int cuda_device, const char* out_path, in
 VQVDB_HOST_API int vqvdb_host_decompress(int cuda_device, const char* in_path, int* n_grids, int64_t* counts, int counts_cap,
                                          int32_t* const* origins, float* const* voxels, int64_t batch_size, int fp32_decode);
 
+/* ---- the backend interface itself, for hosts that are not C++ (bench.py's e2e_pageable; needs a GPU) ----
+ * A handle owns one IVQVAECodec created as the reference's SOP caches create theirs (SOP_VQVDB_Encoder.cpp:62-72):
+ * CodecConfig{Device::CUDA, EmbeddedModel}, BackendType::B200.  encode / decode make the VIRTUAL calls of
+ * IVQVAECodec.hpp:121,130 exactly as the orchestrator does (VQVAECodec.cpp:114-120,172-178): a TensorView over the
+ * caller's (pageable) memory in, an owning Tensor out.  The Tensor stays inside the handle until the next call;
+ * vqvdb_host_backend_result() exposes its bytes.  *seconds receives the wall time of the virtual call alone.
+ * The *_into forms are B200Backend::encodeInto / decodeInto: results written straight into caller memory. */
+typedef struct vqvdb_host_backend vqvdb_host_backend;
+VQVDB_HOST_API int vqvdb_host_backend_create(int cuda_device, vqvdb_host_backend** out);
+VQVDB_HOST_API void vqvdb_host_backend_destroy(vqvdb_host_backend* b);
+VQVDB_HOST_API int vqvdb_host_backend_encode(vqvdb_host_backend* b, const float* leaves, int64_t n_leaves, double* seconds);
+VQVDB_HOST_API int vqvdb_host_backend_decode(vqvdb_host_backend* b, const uint8_t* indices, int64_t n_leaves, double* seconds);
+VQVDB_HOST_API const void* vqvdb_host_backend_result(const vqvdb_host_backend* b, uint64_t* bytes);
+VQVDB_HOST_API int vqvdb_host_backend_encode_into(vqvdb_host_backend* b, const float* leaves, int64_t n_leaves, uint8_t* indices_out, double* seconds);
+VQVDB_HOST_API int vqvdb_host_backend_decode_into(vqvdb_host_backend* b, const uint8_t* indices, int64_t n_leaves, float* voxels_out, double* seconds);
+
 VQVDB_HOST_API const char* vqvdb_host_last_error(void);
 
 #ifdef __cplusplus

@@ -185,3 +185,89 @@ class RefCodec:
     def decode(self, indices: np.ndarray) -> np.ndarray:
         idx = np.ascontiguousarray(indices, dtype=np.uint8)
         return self._call("decode", idx, (idx.shape[0], 1, 8, 8, 8), np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# Format oracle: the reference's own VDBStreamWriter / VDBStreamReader (src/Utils/VQVDB_Reader.cpp), compiled
+# unmodified against oracle/stub/openvdb/Types.h into oracle/_ref/libvqvdb_fmt.so (oracle/Makefile: fmt).
+# ---------------------------------------------------------------------------------------------
+FMT_LIB = os.path.join(HERE, "_ref", "libvqvdb_fmt.so")
+
+
+def fmt_available() -> bool:
+    return os.path.exists(FMT_LIB)
+
+
+class RefFormat:
+    """Write / read .vqvdb v3 files with the reference's own code.  Grids are (name, origins int32 [n,3],
+    indices uint8 [n,64], transform float32 [16]) tuples."""
+
+    def __init__(self):
+        import ctypes as C
+        self.C = C
+        L = C.CDLL(FMT_LIB)
+        L.reffmt_last_error.restype = C.c_char_p
+        L.reffmt_write.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int64]
+        L.reffmt_reader_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.reffmt_reader_close.argtypes = [C.c_void_p]
+        L.reffmt_reader_close.restype = None
+        L.reffmt_reader_has_next_grid.argtypes = [C.c_void_p]
+        L.reffmt_reader_has_next.argtypes = [C.c_void_p]
+        L.reffmt_reader_next_grid.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
+                                              C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]
+        L.reffmt_reader_next_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.reffmt_reader_next_batch.restype = C.c_int64
+        self.L = L
+
+    def write(self, path, grids, num_embeddings=256, latent_shape=(4, 4, 4), batch=64):
+        C, L = self.C, self.L
+        names = (C.c_char_p * max(1, len(grids)))(*[g[0].encode() for g in grids])
+        tr = (np.ascontiguousarray(np.stack([np.asarray(g[3], np.float32).reshape(16) for g in grids]))
+              if grids else np.zeros((1, 16), np.float32))
+        counts = np.array([len(g[1]) for g in grids], dtype=np.int64)
+        og = [np.ascontiguousarray(g[1], dtype=np.int32) for g in grids]
+        ix = [np.ascontiguousarray(g[2], dtype=np.uint8).reshape(len(g[1]), -1) for g in grids]
+        lat = np.array(latent_shape, dtype=np.int64)
+        po = (C.c_void_p * max(1, len(grids)))(*[a.ctypes.data for a in og])
+        pi = (C.c_void_p * max(1, len(grids)))(*[a.ctypes.data for a in ix])
+        rc = L.reffmt_write(os.fspath(path).encode(), len(grids), names, tr.ctypes.data, lat.ctypes.data, len(latent_shape),
+                            num_embeddings, counts.ctypes.data, po, pi, batch)
+        if rc != 0:
+            raise RuntimeError("reference writer: " + L.reffmt_last_error().decode())
+
+    def read(self, path, batch=1 << 20, stop_on_empty_batch=True):
+        """Every grid through VDBStreamReader exactly as the reference's decompress loop drives it
+        (VQVAECodec.cpp:147-196): `while hasNextGrid: meta; while hasNext: nextBatch(batch)`."""
+        C, L = self.C, self.L
+        h = C.c_void_p()
+        if L.reffmt_reader_open(os.fspath(path).encode(), C.byref(h)) != 0:
+            raise RuntimeError("reference reader: " + L.reffmt_last_error().decode())
+        out = []
+        try:
+            while L.reffmt_reader_has_next_grid(h):
+                name = C.create_string_buffer(4096)
+                tr = np.zeros(16, np.float32)
+                lat = np.zeros(8, np.int64)
+                rank, n, k = C.c_int(), C.c_int64(), C.c_uint32()
+                if L.reffmt_reader_next_grid(h, name, 4096, tr.ctypes.data, lat.ctypes.data, C.byref(rank), C.byref(n), C.byref(k)) != 0:
+                    raise RuntimeError("reference reader: " + L.reffmt_last_error().decode())
+                bb = int(np.prod(lat[:rank.value])) if rank.value else 1
+                og_parts, ix_parts = [], []
+                while L.reffmt_reader_has_next(h):
+                    og = np.empty((batch, 3), np.int32)
+                    ix = np.empty((batch, bb), np.uint8)
+                    got = L.reffmt_reader_next_batch(h, batch, og.ctypes.data, ix.ctypes.data)
+                    if got < 0:
+                        raise RuntimeError("reference reader: " + L.reffmt_last_error().decode())
+                    if got == 0 and stop_on_empty_batch:
+                        break
+                    og_parts.append(og[:got].copy())
+                    ix_parts.append(ix[:got].copy())
+                og = np.concatenate(og_parts) if og_parts else np.zeros((0, 3), np.int32)
+                ix = np.concatenate(ix_parts) if ix_parts else np.zeros((0, bb), np.uint8)
+                out.append(dict(name=name.value.decode(), origins=og, indices=ix, transform=tr, latent_shape=[int(v) for v in lat[:rank.value]],
+                                total_blocks=int(n.value), num_embeddings=int(k.value)))
+        finally:
+            L.reffmt_reader_close(h)
+        return out

@@ -1,7 +1,7 @@
 """The folded decoder tail (VQVDB_B200_DECODE_BF16_TC2_FOLD) is the same linear map as the reference's
 up_conv -> PixelShuffle3D(2) -> final (python/VQVAE_v2.py:172-187, 266-275), zero padding at both resolutions included.
 
-Host-only: the product's fold (csrc/decode_mma_host.cpp, through vqvdb_b200_debug_fold_decoder_tail) against the three
+Host-only: the product's fold (csrc/decode_tc_host.cpp, through vqvdb_b200_debug_fold_decoder_tail) against the three
 layers evaluated one after the other in float64 with the pack's own weights."""
 import os
 import sys

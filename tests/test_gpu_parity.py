@@ -161,14 +161,13 @@ TC_MIN_PSNR_VS_REF = 55.0
 TC_MAX_ABS = 2e-2
 
 
-@pytest.fixture(scope="module", params=["bf16_tc2_fold", "bf16_tc2", "bf16_tc", "bf16_mma"])
-def codec_tc(request):
-    """The tensor-core decoders: tcgen05/TMEM with kw taps along N ("bf16_tc2"), one unit per tap ("bf16_tc"), and warp-level
-    mma.sync ("bf16_mma")."""
+@pytest.fixture(scope="module")
+def codec_tc():
+    """The tensor-core decoder (tcgen05/TMEM, kw taps along N, folded tail): the default decode path."""
     from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec
-    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, decode_precision=request.param), BackendType.B200)
+    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA), BackendType.B200)
     assert c is not None
-    assert c.decode_path == {"bf16_tc2_fold": "bf16_tcgen05_n192_fold", "bf16_tc2": "bf16_tcgen05_n192", "bf16_tc": "bf16_tcgen05", "bf16_mma": "bf16_mma"}[request.param]
+    assert c.decode_path == "bf16_tcgen05_n192_fold"
     yield c
     c.close()
 

@@ -1,5 +1,6 @@
-""".vqvdb v3 container: the C++ writer/reader against an independent Python statement of the byte layout
-(reference src/Utils/VQVDB_Reader.hpp:30-43, VQVDB_Reader.cpp:81-150)."""
+""".vqvdb v3 container: the C++ writer/reader against (1) the reference's own VDBStreamWriter / VDBStreamReader
+(src/Utils/VQVDB_Reader.cpp:20-162,168-335, compiled unmodified into oracle/_ref/libvqvdb_fmt.so: the format oracle)
+and (2) an independent Python statement of the byte layout (VQVDB_Reader.hpp:30-43)."""
 import os
 import struct
 import subprocess
@@ -117,6 +118,91 @@ def test_multi_grid_file_larger_than_any_read_buffer(tmp_path):
     hostlib.write_file(p, [g0, g1])
     back = hostlib.read_file(p, batch=1 << 18)
     same(back, [g0, g1])
+
+
+# ---------------------------------------------------------------------------------------------
+# Format oracle: the reference's own reader and writer.  Built by `make -C oracle fmt` where /root/reference exists
+# (the dev container); the prebuilt library travels with the repo snapshot, so these also run on the GPU box.
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ref_fmt():
+    from oracle import pyoracle
+    if not pyoracle.fmt_available() and os.path.isdir("/root/reference/src"):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(REPO, "oracle"), "fmt"])
+    if not pyoracle.fmt_available():
+        pytest.skip("oracle/_ref/libvqvdb_fmt.so not built (needs the reference tree)")
+    return pyoracle.RefFormat()
+
+
+def _tuples(grids):
+    return [(g.name, g.origins, g.indices.reshape(len(g.origins), -1), np.asarray(g.transform, np.float32).reshape(16)) for g in grids]
+
+
+def _same_as_ref(ref_grids, grids):
+    assert len(ref_grids) == len(grids)
+    for r, g in zip(ref_grids, grids):
+        assert r["name"] == g.name and r["total_blocks"] == len(g.origins)
+        assert r["latent_shape"] == [4, 4, 4] and r["num_embeddings"] == 256
+        assert np.array_equal(r["origins"], g.origins)
+        assert np.array_equal(r["indices"], g.indices.reshape(len(g.origins), -1))
+        assert np.array_equal(r["transform"], np.asarray(g.transform, np.float32).reshape(16))
+
+
+@pytest.mark.parametrize("sizes", [[302], [1], [1000, 5, 77], [64, 64, 1]])
+def test_reference_reader_reads_files_written_here(tmp_path, ref_fmt, sizes):
+    rng = np.random.default_rng(10)
+    grids = make_grids(rng, sizes)
+    p = str(tmp_path / "ours.vqvdb")
+    hostlib.write_file(p, grids)
+    for batch in (64, 8192):                            # the decoder SOP's default and maximum batch
+        _same_as_ref(ref_fmt.read(p, batch=batch), grids)
+
+
+@pytest.mark.parametrize("sizes", [[302], [1000, 5, 77]])
+def test_reader_here_reads_reference_written_files_and_bytes_agree(tmp_path, ref_fmt, sizes):
+    rng = np.random.default_rng(11)
+    grids = make_grids(rng, sizes)
+    p_ref, p_cpp = str(tmp_path / "ref.vqvdb"), str(tmp_path / "ours.vqvdb")
+    ref_fmt.write(p_ref, _tuples(grids), batch=64)       # VDBStreamWriter, fed 64 leaves at a time like compress()
+    hostlib.write_file(p_cpp, grids)
+    assert open(p_ref, "rb").read() == open(p_cpp, "rb").read()
+    same(hostlib.read_file(p_ref), grids)
+    same(hostlib.read_file(p_ref, batch=100), grids)
+
+
+def test_reference_writer_empty_file_header(tmp_path, ref_fmt):
+    # no grids: the reference leaves its placeholder header (numGrids = 0, K = 0, latent rank 0: VQVDB_Reader.cpp:58-61)
+    p_ref, p_cpp = str(tmp_path / "ref.vqvdb"), str(tmp_path / "ours.vqvdb")
+    ref_fmt.write(p_ref, [])
+    hostlib.write_file(p_cpp, [])
+    assert open(p_ref, "rb").read() == open(p_cpp, "rb").read()
+    assert hostlib.read_file(p_ref) == [] and ref_fmt.read(p_cpp) == []
+
+
+def test_large_first_grid_divergence_is_the_documented_one(tmp_path, ref_fmt):
+    # VDBStreamReader decrements remainingDataBytes_ twice (VQVDB_Reader.cpp:297 and :322).  With a
+    # first grid larger than its 64 MiB buffer the budget wraps around, the second refill swallows the rest of the
+    # file — the next grid's metadata included — into grid 0's record buffer, and the reader then fails on grid 1.
+    # The file itself is fine: the reference WRITER produces the same bytes as ours, and this reader reads both grids.
+    rng = np.random.default_rng(12)
+    n0 = 900_000                                         # 68.4 MB of records > 64 MiB
+    g0 = LeafGrid("big", np.arange(n0 * 3, dtype=np.int32).reshape(n0, 3), None, rng.integers(0, 256, size=(n0, 64), dtype=np.uint8))
+    g1 = make_grids(rng, [10])[0]
+    p_ref, p_cpp = str(tmp_path / "ref.vqvdb"), str(tmp_path / "ours.vqvdb")
+    ref_fmt.write(p_ref, _tuples([g0, g1]), batch=8192)
+    hostlib.write_file(p_cpp, [g0, g1])
+    import hashlib
+    assert hashlib.sha256(open(p_ref, "rb").read()).digest() == hashlib.sha256(open(p_cpp, "rb").read()).digest()
+    same(hostlib.read_file(p_ref, batch=1 << 18), [g0, g1])
+    try:
+        got = ref_fmt.read(p_ref, batch=8192)
+    except RuntimeError as e:
+        assert "grid name length" in str(e) or "truncated" in str(e).lower(), str(e)
+    else:                                                # did not throw: then it must have mis-read the second grid
+        assert len(got) != 2 or not np.array_equal(got[1]["indices"], g1.indices.reshape(10, -1))
+    # the single-grid form of the same size reads fine through the reference reader (wrap-around is harmless there)
+    hostlib.write_file(p_cpp, [g0])
+    _same_as_ref(ref_fmt.read(p_cpp, batch=8192), [g0])
 
 
 def test_empty_file_and_empty_grid(tmp_path):

@@ -15,7 +15,7 @@ from vqvdb_b200 import BackendType, CodecConfig, DataType, IVQVAECodec, TensorVi
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 x = synth.smoke_leaves(n, seed=5)
-for dec in ("default", "bf16_tc2"):
+for dec in ("default",):
     c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, encode_precision="fp16x2_tc", decode_precision=dec), BackendType.B200)
     idx = c.encode(TensorView(x, list(x.shape), DataType.FLOAT32)).buffer
     rec = c.decode(TensorView(idx, list(idx.shape), DataType.UINT8)).buffer

@@ -168,7 +168,7 @@ class CodecConfig:
     source: Union[EmbeddedModel, "OnnxModelPaths", str, os.PathLike] = field(default_factory=EmbeddedModel)
     device_index: int = 0            # extension: which GPU (the reference hard-codes 0)
     chunk_leaves: int = 0            # extension: pipeline chunk of the host-pointer calls
-    decode_precision: str = "default"  # "default" | "fp32" | "bf16_tc" (tcgen05) | "bf16_mma" (mma.sync)
+    decode_precision: str = "default"  # "default" | "fp32" (checking path) | "bf16_tc" (tcgen05, the default)
     encode_precision: str = "default"  # "default" | "fp32" (FFMA) | "fp16x2_tc" (tcgen05, split-fp16 operands)
 
     def __post_init__(self):
@@ -195,7 +195,7 @@ class Tensor:
         return self.buffer
 
 
-_PRECISION = {"default": 0, "fp32": 1, "bf16_tc": 2, "bf16_mma": 3, "bf16_tc2": 4, "bf16_tc2_fold": 5}
+_PRECISION = {"default": 0, "fp32": 1, "bf16_tc": 2}
 _ENC_PRECISION = {"default": 0, "fp32": 1, "fp16x2_tc": 2}
 
 

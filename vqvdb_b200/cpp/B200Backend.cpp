@@ -1,10 +1,13 @@
 #include "B200Backend.hpp"
 
+#include <cstdlib>
 #include <iostream>
+#include <mutex>
+#include <optional>
 #include <stdexcept>
 #include <string>
 
-#include "../../include/vqvdb_b200.h"
+#include "vqvdb_b200.h"
 
 namespace {
 int64_t leadingDim(const TensorView& v, const char* what) {
@@ -12,17 +15,61 @@ int64_t leadingDim(const TensorView& v, const char* what) {
 	if (v.shape[0] > 0 && v.data == nullptr) throw std::runtime_error(std::string(what) + ": null data pointer");
 	return v.shape[0];
 }
+
+// The reference builds a torch tensor from the view's shape and the model rejects anything but [B,C,8,8,8] /
+// [B,4,4,4] (TorchBackend.cpp:141-149,173-180); here the raw pointer is all the C ABI sees, so the shape is
+// checked before it is trusted.
+void expectShape(const TensorView& v, const std::vector<int64_t>& tail, const char* what) {
+	bool ok = v.shape.size() == tail.size() + 1;
+	for (size_t i = 0; ok && i < tail.size(); ++i) ok = v.shape[i + 1] == tail[i];
+	if (ok) return;
+	std::string want = "[B";
+	for (int64_t d : tail) want += "," + std::to_string(d);
+	std::string got = "[";
+	for (size_t i = 0; i < v.shape.size(); ++i) got += (i ? "," : "") + std::to_string(v.shape[i]);
+	throw std::runtime_error(std::string(what) + ": expected shape " + want + "], got " + got + "]");
+}
+
+std::mutex g_optMutex;
+std::optional<B200Options> g_defaultOptions;
+
+bool envIs(const char* name, const char* value) {
+	const char* v = std::getenv(name);
+	return v && std::string(v) == value;
+}
 }  // namespace
 
-B200Backend::B200Backend(const CodecConfig& config) {
+B200Options B200Options::fromEnvironment() {
+	B200Options o;
+	if (const char* v = std::getenv("VQVDB_B200_DEVICE")) o.cudaDevice = std::atoi(v);
+	if (const char* v = std::getenv("VQVDB_B200_CHUNK_LEAVES")) o.chunkLeaves = (uint32_t)std::strtoul(v, nullptr, 10);
+	o.fp32Decode = envIs("VQVDB_B200_DECODE", "fp32");
+	o.fp32Encode = envIs("VQVDB_B200_ENCODE", "fp32");
+	return o;
+}
+
+void B200Backend::setDefaultOptions(const B200Options& options) {
+	std::lock_guard<std::mutex> lock(g_optMutex);
+	g_defaultOptions = options;
+}
+
+B200Options B200Backend::defaultOptions() {
+	std::lock_guard<std::mutex> lock(g_optMutex);
+	return g_defaultOptions ? *g_defaultOptions : B200Options::fromEnvironment();
+}
+
+B200Backend::B200Backend(const CodecConfig& config) { init(config, defaultOptions()); }
+B200Backend::B200Backend(const CodecConfig& config, const B200Options& options) { init(config, options); }
+
+void B200Backend::init(const CodecConfig& config, const B200Options& options) {
 	if (config.device != CodecConfig::Device::CUDA)
 		throw std::runtime_error("B200 backend needs CodecConfig::Device::CUDA (no CPU path exists)");
 	vqvdb_b200_config c{};
 	c.struct_size = sizeof(c);
-	c.device = config.cudaDevice;
-	c.chunk_leaves = config.chunkLeaves;
-	c.decode_precision = config.fp32Decode ? VQVDB_B200_DECODE_FP32 : VQVDB_B200_DECODE_DEFAULT;
-	c.encode_precision = config.fp32Encode ? VQVDB_B200_ENCODE_FP32 : VQVDB_B200_ENCODE_DEFAULT;
+	c.device = options.cudaDevice;
+	c.chunk_leaves = options.chunkLeaves;
+	c.decode_precision = options.fp32Decode ? VQVDB_B200_DECODE_FP32 : VQVDB_B200_DECODE_DEFAULT;
+	c.encode_precision = options.fp32Encode ? VQVDB_B200_ENCODE_FP32 : VQVDB_B200_ENCODE_DEFAULT;
 	std::string path, path2;
 	if (std::holds_alternative<std::filesystem::path>(config.source)) {
 		path = std::get<std::filesystem::path>(config.source).string();   // a VQVDBW01 pack, or a directory with encoder.onnx + decoder.onnx
@@ -58,6 +105,7 @@ void B200Backend::decodeInto(const uint8_t* hostIndices, int64_t n, float* hostV
 Tensor B200Backend::encode(const TensorView& leafBatch) const {
 	if (leafBatch.dtype != DataType::FLOAT32) throw std::runtime_error("encode expects FLOAT32 data.");
 	const int64_t n = leadingDim(leafBatch, "encode");
+	expectShape(leafBatch, {channels_, 8, 8, 8}, "encode");
 	Tensor out;
 	out.dtype = DataType::UINT8;
 	out.shape = {n, latentShape_[0], latentShape_[1], latentShape_[2]};
@@ -69,21 +117,11 @@ Tensor B200Backend::encode(const TensorView& leafBatch) const {
 Tensor B200Backend::decode(const TensorView& indices) const {
 	if (indices.dtype != DataType::UINT8) throw std::runtime_error("decode expects UINT8 data.");
 	const int64_t n = leadingDim(indices, "decode");
+	expectShape(indices, latentShape_, "decode");
 	Tensor out;
 	out.dtype = DataType::FLOAT32;
 	out.shape = {n, channels_, 8, 8, 8};
 	out.buffer.resize((size_t)n * channels_ * 512 * sizeof(float));
 	decodeInto(static_cast<const uint8_t*>(indices.data), n, out.getData<float>());
 	return out;
-}
-
-// Factory.  Same contract as the reference (src/core/IVQVAECodec.cpp:76-110): swallow, log, return null.
-std::unique_ptr<IVQVAECodec> IVQVAECodec::create(const CodecConfig& config, BackendType type) {
-	try {
-		if (type == BackendType::B200) return std::make_unique<B200Backend>(config);
-		throw std::runtime_error("Requested backend type is not available or disabled in the build configuration.");
-	} catch (const std::exception& e) {
-		std::cerr << "Failed to create VQ-VAE backend: " << e.what() << std::endl;
-		return nullptr;
-	}
 }

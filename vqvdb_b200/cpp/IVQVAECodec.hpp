@@ -4,7 +4,9 @@
 // written against /root/reference/src/core/IVQVAECodec.hpp:21-137 compiles against this one unchanged:
 //   BackendType, EmbeddedModel, OnnxModelPaths, ModelSource, DataType, TensorView, Tensor, CodecConfig,
 //   IVQVAECodec::{create, encode, decode, getLatentShape}.
-// Additions are strictly additive: BackendType::B200, and optional CodecConfig fields with defaults.
+// The ONLY addition is the BackendType::B200 enumerator: CodecConfig is the reference's, field for field (B200-only
+// knobs — device ordinal, chunk size, checking paths — travel through B200Options in B200Backend.hpp, not through it),
+// so B200Backend.cpp compiles against the reference's own header with that one token added (tests/test_boundary.py).
 // The reference's own LibTorch / ONNX backends are not part of this repository; asking create() for them
 // yields nullptr exactly as a reference build without ENABLE_*_BACKEND does (IVQVAECodec.cpp:99-103).
 #pragma once
@@ -52,11 +54,6 @@ struct CodecConfig {
 	enum class Device { CPU, CUDA };
 	Device device = Device::CPU;
 	ModelSource source = EmbeddedModel{};
-	// --- B200 backend only (ignored by the reference's backends) ---
-	int cudaDevice = 0;             // the reference hard-codes device 0 (OnnxBackend_Cuda.cpp:21)
-	uint32_t chunkLeaves = 0;       // leaves per internal pipeline chunk, 0 = default
-	bool fp32Decode = false;        // CUDA-core fp32 decoder instead of the bf16 tensor-core one
-	bool fp32Encode = false;        // CUDA-core fp32 FFMA encoder instead of the split-fp16 tensor-core one
 };
 
 class IVQVAECodec {

@@ -14,6 +14,11 @@ constexpr size_t kLeafVoxels = 512;
 
 VQVAECodec::VQVAECodec(std::unique_ptr<IVQVAECodec> backend) : backend_(std::move(backend)) {
 	if (!backend_) throw std::runtime_error("VQVAECodec: Backend cannot be null.");
+	// The orchestrator is FloatGrid-only, like the reference's (VQVAECodec.hpp:40,49): every buffer below is sized
+	// 512 floats per leaf.  A vec3 weight pack behind the backend would make it read / write 3x that.
+	if (const auto* b200 = dynamic_cast<const B200Backend*>(backend_.get()); b200 && b200->channels() != 1)
+		throw std::runtime_error("VQVAECodec: the loaded model has " + std::to_string(b200->channels()) +
+		                         " channels; compress/decompress handle FloatGrid (1-channel) models only.");
 }
 
 Tensor VQVAECodec::encodeBatch(const TensorView& cpuBatch) const { return backend_->encode(cpuBatch); }

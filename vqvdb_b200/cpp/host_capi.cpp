@@ -1,10 +1,12 @@
 // C ABI of the host layer (include/vqvdb_b200_host.h).
-#include "../../include/vqvdb_b200_host.h"
+#include "vqvdb_b200_host.h"
 
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include <string>
 
+#include "B200Backend.hpp"
 #include "VQVAECodec.hpp"
 #include "vqvdb_file.hpp"
 
@@ -13,6 +15,25 @@ thread_local std::string g_err;
 int fail(const std::exception& e) {
 	g_err = e.what();
 	return -1;
+}
+}  // namespace
+
+struct vqvdb_host_backend {
+	std::unique_ptr<IVQVAECodec> codec;
+	Tensor last;
+};
+
+namespace {
+template <class F>
+int timed(double* seconds, F&& f) {
+	try {
+		const auto t0 = std::chrono::steady_clock::now();
+		f();
+		if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		return 0;
+	} catch (const std::exception& e) {
+		return fail(e);
+	}
 }
 }  // namespace
 
@@ -100,8 +121,9 @@ int vqvdb_host_compress(int cuda_device, const char* out_path, int n_grids, cons
 	try {
 		CodecConfig cfg;
 		cfg.device = CodecConfig::Device::CUDA;
-		cfg.cudaDevice = cuda_device;
-		VQVAECodec codec(IVQVAECodec::create(cfg, BackendType::B200));
+		B200Options opt = B200Backend::defaultOptions();
+		opt.cudaDevice = cuda_device;
+		VQVAECodec codec(std::make_unique<B200Backend>(cfg, opt));
 		std::vector<LeafGrid> grids((size_t)n_grids);
 		for (int g = 0; g < n_grids; ++g) {
 			grids[g].name = names[g];
@@ -136,9 +158,10 @@ int vqvdb_host_decompress(int cuda_device, const char* in_path, int* n_grids, in
 		}
 		CodecConfig cfg;
 		cfg.device = CodecConfig::Device::CUDA;
-		cfg.cudaDevice = cuda_device;
-		cfg.fp32Decode = fp32_decode != 0;
-		VQVAECodec codec(IVQVAECodec::create(cfg, BackendType::B200));
+		B200Options opt = B200Backend::defaultOptions();
+		opt.cudaDevice = cuda_device;
+		opt.fp32Decode = fp32_decode != 0;
+		VQVAECodec codec(std::make_unique<B200Backend>(cfg, opt));
 		std::vector<LeafGrid> grids;
 		codec.decompress(in_path, grids, (size_t)batch_size);
 		*n_grids = (int)grids.size();
@@ -151,6 +174,51 @@ int vqvdb_host_decompress(int cuda_device, const char* in_path, int* n_grids, in
 	} catch (const std::exception& e) {
 		return fail(e);
 	}
+}
+
+int vqvdb_host_backend_create(int cuda_device, vqvdb_host_backend** out) {
+	try {
+		*out = nullptr;
+		CodecConfig cfg;
+		cfg.device = CodecConfig::Device::CUDA;
+		B200Options opt = B200Backend::defaultOptions();
+		opt.cudaDevice = cuda_device;
+		auto b = std::make_unique<vqvdb_host_backend>();
+		b->codec = std::make_unique<B200Backend>(cfg, opt);
+		*out = b.release();
+		return 0;
+	} catch (const std::exception& e) {
+		return fail(e);
+	}
+}
+
+void vqvdb_host_backend_destroy(vqvdb_host_backend* b) { delete b; }
+
+int vqvdb_host_backend_encode(vqvdb_host_backend* b, const float* leaves, int64_t n, double* seconds) {
+	return timed(seconds, [&] {
+		const TensorView view{leaves, {n, 1, 8, 8, 8}, DataType::FLOAT32};
+		b->last = b->codec->encode(view);
+	});
+}
+
+int vqvdb_host_backend_decode(vqvdb_host_backend* b, const uint8_t* indices, int64_t n, double* seconds) {
+	return timed(seconds, [&] {
+		const TensorView view{indices, {n, 4, 4, 4}, DataType::UINT8};
+		b->last = b->codec->decode(view);
+	});
+}
+
+const void* vqvdb_host_backend_result(const vqvdb_host_backend* b, uint64_t* bytes) {
+	if (bytes) *bytes = b ? b->last.buffer.size() : 0;
+	return b ? b->last.buffer.data() : nullptr;
+}
+
+int vqvdb_host_backend_encode_into(vqvdb_host_backend* b, const float* leaves, int64_t n, uint8_t* indices_out, double* seconds) {
+	return timed(seconds, [&] { static_cast<const B200Backend&>(*b->codec).encodeInto(leaves, n, indices_out); });
+}
+
+int vqvdb_host_backend_decode_into(vqvdb_host_backend* b, const uint8_t* indices, int64_t n, float* voxels_out, double* seconds) {
+	return timed(seconds, [&] { static_cast<const B200Backend&>(*b->codec).decodeInto(indices, n, voxels_out); });
 }
 
 }  // extern "C"

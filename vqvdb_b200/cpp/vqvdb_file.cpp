@@ -1,5 +1,6 @@
 #include "vqvdb_file.hpp"
 
+#include <algorithm>
 #include <cstring>
 #include <iostream>
 #include <stdexcept>
@@ -122,6 +123,9 @@ VqvdbReader::VqvdbReader(const std::string& path) {
 	numGrids_ = (uint8_t)h[6];
 	std::memcpy(&sharedNumEmbeddings_, h + 7, 4);
 	sharedLatentDims_ = (uint8_t)h[11];
+	in_.seekg(0, std::ios::end);
+	fileBytes_ = (uint64_t)in_.tellg();
+	in_.seekg((std::streamoff)kHeaderBytes, std::ios::beg);
 }
 
 void VqvdbReader::readExact(void* dst, size_t n, const char* what) {
@@ -151,6 +155,11 @@ GridMetadata VqvdbReader::nextGridMetadata() {
 	uint32_t total = 0;
 	readExact(&total, 4, "block count");
 	m.totalBlocks = total;
+	// a corrupt count must not turn into a multi-terabyte resize() in the caller: the records have to be in the file
+	const uint64_t here = (uint64_t)in_.tellg();
+	if ((uint64_t)total * (sizeof(LeafOrigin) + m.blockBytes()) > fileBytes_ - std::min(here, fileBytes_))
+		throw std::runtime_error("Unexpected end of file while reading block records (grid '" + m.name + "' declares " +
+		                         std::to_string(total) + " blocks)");
 	m.numEmbeddings = sharedNumEmbeddings_;
 	m.fileVersion = 3;
 	current_ = m;

@@ -79,6 +79,7 @@ class VqvdbReader {
 	std::ifstream in_;
 	uint32_t numGrids_ = 0, gridIndex_ = 0, sharedNumEmbeddings_ = 0;
 	uint8_t sharedLatentDims_ = 0;
+	uint64_t fileBytes_ = 0;
 	GridMetadata current_;
 	size_t blocksRead_ = 0;
 	std::vector<char> scratch_;

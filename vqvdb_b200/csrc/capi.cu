@@ -6,7 +6,11 @@
 #include <algorithm>
 #include <cmath>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <filesystem>
 #include <fstream>
@@ -16,7 +20,7 @@
 #include <vector>
 
 #include "../../include/vqvdb_b200.h"
-#include "decode_mma.cuh"
+#include "decode_tc.cuh"
 #include "encode_tc.cuh"
 #include "generic_model.cuh"
 #include "model.cuh"
@@ -39,6 +43,84 @@ struct CudaError : std::runtime_error {
 
 constexpr int kSlots = 3;                   // pipeline depth of the host-pointer calls
 constexpr uint32_t kDefaultChunk = 16384;   // leaves per chunk: 32 MiB of voxels, 1 MiB of indices
+
+// Pageable caller memory (the reference's callers hand over std::vector storage: VQVAECodec.cpp:48,114) cannot be DMA'd
+// directly, so it is staged through the slots' pinned buffers.  One memcpy thread moves ~10 GB/s, a quarter of what the
+// PCIe link takes and less than the decode kernel produces (2 KB x 15 M leaves/s = 31 GB/s); the staging copies are
+// therefore split over a small pool of threads that lives as long as the codec.
+class CopyPool {
+   public:
+	explicit CopyPool(int n_threads) {
+		for (int i = 1; i < n_threads; ++i) workers_.emplace_back([this, i] { run(i); });
+	}
+	~CopyPool() {
+		{
+			std::lock_guard<std::mutex> lk(m_);
+			stop_ = true;
+			++generation_;
+		}
+		wake_.notify_all();
+		for (auto& t : workers_) t.join();
+	}
+	int threads() const { return (int)workers_.size() + 1; }
+	// memcpy(dst, src, bytes) by every thread of the pool (the caller is thread 0); returns when all slices are done.
+	void copy(void* dst, const void* src, size_t bytes) {
+		const int n = threads();
+		if (n == 1 || bytes < (size_t)(1u << 20)) {
+			std::memcpy(dst, src, bytes);
+			return;
+		}
+		{
+			std::lock_guard<std::mutex> lk(m_);
+			dst_ = static_cast<char*>(dst);
+			src_ = static_cast<const char*>(src);
+			bytes_ = bytes;
+			pending_ = n - 1;
+			++generation_;
+		}
+		wake_.notify_all();
+		slice(0);
+		std::unique_lock<std::mutex> lk(m_);
+		done_.wait(lk, [this] { return pending_ == 0; });
+	}
+
+   private:
+	void slice(int i) {
+		const size_t n = (size_t)threads();
+		const size_t per = ((bytes_ + n - 1) / n + 4095) & ~size_t(4095);  // page-sized slices
+		const size_t lo = std::min(bytes_, per * (size_t)i), hi = std::min(bytes_, lo + per);
+		if (hi > lo) std::memcpy(dst_ + lo, src_ + lo, hi - lo);
+	}
+	void run(int i) {
+		uint64_t seen = 0;
+		for (;;) {
+			{
+				std::unique_lock<std::mutex> lk(m_);
+				wake_.wait(lk, [&] { return generation_ != seen; });
+				seen = generation_;
+				if (stop_) return;
+			}
+			slice(i);
+			std::lock_guard<std::mutex> lk(m_);
+			if (--pending_ == 0) done_.notify_one();
+		}
+	}
+	std::vector<std::thread> workers_;
+	std::mutex m_;
+	std::condition_variable wake_, done_;
+	uint64_t generation_ = 0;
+	int pending_ = 0;
+	bool stop_ = false;
+	char* dst_ = nullptr;
+	const char* src_ = nullptr;
+	size_t bytes_ = 0;
+};
+
+int default_copy_threads() {
+	if (const char* v = std::getenv("VQVDB_B200_COPY_THREADS")) return std::max(1, std::min(64, std::atoi(v)));
+	const unsigned hw = std::thread::hardware_concurrency();
+	return (int)std::max(1u, std::min(8u, hw / 2));
+}
 
 struct Slot {
 	cudaStream_t stream = nullptr;
@@ -64,7 +146,7 @@ struct vqvdb_b200_codec {
 	cudaStream_t compute = nullptr;
 	float* arena = nullptr;  // every fp32 device weight table lives in this one allocation
 	uint8_t* mma_arena = nullptr;  // bf16 weight-unit stream + bf16 codebook of the tensor-core decoder
-	int decode_kind = 2;  // 1 = fp32 FFMA, 2 = bf16 tcgen05/TMEM, 3 = bf16 mma.sync
+	int decode_kind = 2;  // 1 = fp32 FFMA (checking path), 2 = bf16 tcgen05/TMEM
 	int encode_kind = 2;  // 1 = fp32 FFMA, 2 = fp16x2 split on tcgen05/TMEM (fp32-level accuracy)
 	std::string encode_path = "fp32";
 	uint8_t* enc_tc_arena = nullptr;  // fp16 hi/lo weight-unit stream of the tensor-core encoder
@@ -79,6 +161,7 @@ struct vqvdb_b200_codec {
 	vqvdb::DecoderWeights dec{};
 	Slot slots[kSlots];
 	bool staging_ready = false;
+	std::unique_ptr<CopyPool> copier;  // created with the staging buffers, on the first host-pointer call
 
 	~vqvdb_b200_codec() {
 		cudaSetDevice(device);
@@ -132,9 +215,9 @@ struct ArenaBuilder {
 	}
 };
 
-void expect_dims(const WeightPack& p, const char* name, std::initializer_list<int> dims) {
+void expect_dims(const WeightPack& p, const std::string& name, std::initializer_list<int> dims) {
 	const PackTensor& t = p.get(name);
-	if (t.dims != std::vector<int>(dims)) throw std::runtime_error(std::string("weight pack: unexpected shape for ") + name);
+	if (t.dims != std::vector<int>(dims)) throw std::runtime_error("weight pack: unexpected shape for " + name);
 }
 
 void add_res(ArenaBuilder& ab, const WeightPack& p, const std::string& prefix, vqvdb::ResWeights& r) {
@@ -304,6 +387,13 @@ void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
 	const bool vec3 = m.cin != 1;
 	const std::string down = vec3 ? "encoder.down1" : "encoder.down";
 	const PackTensor& dw = p.get(down + ".weight");
+	auto rank_of = [&](const char* name, size_t rank) {
+		if (p.get(name).dims.size() != rank) throw std::runtime_error(std::string("weight pack: unexpected rank for ") + name);
+	};
+	if (dw.dims.size() != 5) throw std::runtime_error("weight pack: unexpected rank for " + down + ".weight");
+	rank_of("encoder.attn.fc.0.weight", 2);
+	rank_of("decoder.stem.0.weight", 5);
+	rank_of("decoder.attn.fc.0.weight", 2);
 	m.e_c0 = dw.dims[1];
 	m.e_c1 = dw.dims[0];
 	m.e_down_k = dw.dims[2];
@@ -313,9 +403,48 @@ void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
 	m.d_c = p.get("decoder.stem.0.weight").dims[0];
 	m.d_nres = vec3 ? 2 : 1;
 	m.d_red = p.get("decoder.attn.fc.0.weight").dims[0];
-	if (m.e_c0 > 64 || m.e_c1 > 128 || m.D > 128 || m.d_c > 128 || m.K % 4 || m.K > 256 || m.e_red > 64 || m.d_red > 64 ||
-	    p.get("decoder.up_conv.weight").dims[0] != 256)
+	if (m.e_c0 > 64 || m.e_c1 > 128 || m.D > 128 || m.d_c > 128 || m.e_red > 64 || m.d_red > 64)
 		throw std::runtime_error("weight pack: architecture outside the generic kernels' limits");
+	// uint8 indices address the whole codebook: with K < 256 an index from an untrusted .vqvdb file could read past it
+	// (F.embedding in the reference raises on such an index; save_for_inference.py:63-64)
+	if (m.K != 256) throw std::runtime_error("weight pack: the generic kernels need a 256-entry codebook (uint8 indices)");
+	// every tensor's shape against the architecture the kernels index by (python/VQVAE_v2.py:278-325)
+	const int e0 = m.e_c0, e1 = m.e_c1, dc = m.d_c, dk = m.e_down_k;
+	expect_dims(p, "encoder.pre.0.weight", {e0, m.cin, 3, 3, 3});
+	expect_dims(p, "encoder.pre.0.bias", {e0});
+	expect_dims(p, "encoder.pre.1.weight", {e0});
+	expect_dims(p, "encoder.pre.1.bias", {e0});
+	auto expect_res = [&](const std::string& prefix, int ch) {
+		for (const char* gn : {".gn1", ".gn2"}) {
+			expect_dims(p, prefix + gn + ".weight", {ch});
+			expect_dims(p, prefix + gn + ".bias", {ch});
+		}
+		for (const char* cv : {".conv1", ".conv2"}) {
+			expect_dims(p, prefix + cv + ".weight", {ch, ch, 3, 3, 3});
+			expect_dims(p, prefix + cv + ".bias", {ch});
+		}
+	};
+	expect_res("encoder.pre.3", e0);
+	expect_dims(p, down + ".weight", {e1, e0, dk, dk, dk});
+	expect_dims(p, down + ".bias", {e1});
+	if (dk != 3 && dk != 4) throw std::runtime_error("weight pack: unsupported kernel size of the stride-2 conv");
+	for (int r = 0; r < m.e_nres; ++r) expect_res("encoder.res_stack." + std::to_string(r), e1);
+	expect_dims(p, "encoder.attn.fc.0.weight", {m.e_red, e1});
+	expect_dims(p, "encoder.attn.fc.2.weight", {e1, m.e_red});
+	expect_dims(p, "encoder.proj.weight", {m.D, e1, 1, 1, 1});
+	expect_dims(p, "encoder.proj.bias", {m.D});
+	expect_dims(p, "quantizer.embedding", {m.K, m.D});
+	expect_dims(p, "decoder.stem.0.weight", {dc, m.D, 3, 3, 3});
+	expect_dims(p, "decoder.stem.0.bias", {dc});
+	expect_dims(p, "decoder.stem.1.weight", {dc});
+	expect_dims(p, "decoder.stem.1.bias", {dc});
+	for (int r = 0; r < m.d_nres; ++r) expect_res("decoder.res_stack." + std::to_string(r), dc);
+	expect_dims(p, "decoder.attn.fc.0.weight", {m.d_red, dc});
+	expect_dims(p, "decoder.attn.fc.2.weight", {dc, m.d_red});
+	expect_dims(p, "decoder.up_conv.weight", {256, dc, 3, 3, 3});
+	expect_dims(p, "decoder.up_conv.bias", {256});
+	expect_dims(p, "decoder.final.weight", {m.cin, 32, 3, 3, 3});
+	expect_dims(p, "decoder.final.bias", {m.cin});
 	ArenaBuilder ab;
 	ab.add(&m.e_pre_w, vqvdb::transpose_conv_weight(p.get("encoder.pre.0.weight")));
 	ab.add(&m.e_pre_b, p.get("encoder.pre.0.bias"));
@@ -360,14 +489,15 @@ void ensure_staging(vqvdb_b200_codec& c) {
 	if (c.staging_ready) return;
 	const size_t vox_bytes = (size_t)c.chunk * c.channels * 512 * sizeof(float);
 	const size_t idx_bytes = (size_t)c.chunk * 64;
-	for (auto& s : c.slots) {
-		CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-		CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-		CUDA_TRY(cudaMalloc(&s.d_vox, vox_bytes));
-		CUDA_TRY(cudaMalloc(&s.d_idx, idx_bytes));
-		CUDA_TRY(cudaMallocHost(&s.h_vox, vox_bytes));
-		CUDA_TRY(cudaMallocHost(&s.h_idx, idx_bytes));
+	for (auto& s : c.slots) {  // a failed attempt (out of memory part-way) is resumed, not repeated over live handles
+		if (!s.stream) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+		if (!s.done) CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+		if (!s.d_vox) CUDA_TRY(cudaMalloc(&s.d_vox, vox_bytes));
+		if (!s.d_idx) CUDA_TRY(cudaMalloc(&s.d_idx, idx_bytes));
+		if (!s.h_vox) CUDA_TRY(cudaMallocHost(&s.h_vox, vox_bytes));
+		if (!s.h_idx) CUDA_TRY(cudaMallocHost(&s.h_idx, idx_bytes));
 	}
+	if (!c.copier) c.copier = std::make_unique<CopyPool>(default_copy_threads());
 	c.staging_ready = true;
 }
 
@@ -411,21 +541,19 @@ void launch_decode(vqvdb_b200_codec& c, const uint8_t* d_idx, int64_t n, float* 
 		if (n > 0) c.launches.fetch_add(1, std::memory_order_relaxed);
 		return;
 	}
-	if (c.decode_kind >= 4) CUDA_TRY(vqvdb::launch_decode_tc2(c.dec_mma, d_idx, n, d_vox, c.num_sms, st, c.decode_kind == 5));
-	else if (c.decode_kind == 2) CUDA_TRY(vqvdb::launch_decode_tc(c.dec_mma, d_idx, n, d_vox, c.num_sms, st));
-	else if (c.decode_kind == 3) CUDA_TRY(vqvdb::launch_decode_mma(c.dec_mma, d_idx, n, d_vox, c.num_sms, st));
+	if (c.decode_kind == 2) CUDA_TRY(vqvdb::launch_decode_tc(c.dec_mma, d_idx, n, d_vox, c.num_sms, st));
 	else CUDA_TRY(vqvdb::launch_decode_fp32(c.dec, d_idx, n, d_vox, c.num_sms, st));
 	if (n > 0) c.launches.fetch_add(1, std::memory_order_relaxed);
 }
 
 // Drains a slot: waits for its chunk and, if results were staged, copies them to the caller's buffer.
 template <class T>
-void retire(Slot& s, T* user_out, size_t elems_per_leaf, const T* staged, bool direct) {
+void retire(CopyPool& cp, Slot& s, T* user_out, size_t elems_per_leaf, const T* staged, bool direct) {
 	if (s.pending_first < 0) return;
 	CUDA_TRY(cudaEventSynchronize(s.done));
 	if (!direct)
-		std::memcpy(user_out + (size_t)s.pending_first * elems_per_leaf, staged,
-		            (size_t)s.pending_count * elems_per_leaf * sizeof(T));
+		cp.copy(user_out + (size_t)s.pending_first * elems_per_leaf, staged,
+		        (size_t)s.pending_count * elems_per_leaf * sizeof(T));
 	s.pending_first = -1;
 	s.pending_count = 0;
 }
@@ -488,21 +616,19 @@ int vqvdb_b200_create(const vqvdb_b200_config* cfg, vqvdb_b200_codec** out) {
 		} catch (const std::exception& e) {
 			return fail(nullptr, VQVDB_B200_ERR_BAD_WEIGHTS, e.what());
 		}
-		if (conf.decode_precision > VQVDB_B200_DECODE_BF16_TC2_FOLD)
+		if (conf.decode_precision > VQVDB_B200_DECODE_BF16_TC)
 			return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "unknown decode_precision");
 		c->decode_kind = conf.decode_precision == VQVDB_B200_DECODE_DEFAULT ? (int)VQVDB_B200_DECODE_DEFAULT_KIND : (int)conf.decode_precision;
 		if (conf.encode_precision > VQVDB_B200_ENCODE_FP16X2_TC)
 			return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "unknown encode_precision");
 		c->encode_kind = conf.encode_precision == VQVDB_B200_ENCODE_DEFAULT ? (int)VQVDB_B200_ENCODE_DEFAULT_KIND : (int)conf.encode_precision;
 		c->encode_path = c->generic ? "fp32_generic" : c->encode_kind == 2 ? "fp16x2_tcgen05" : "fp32";
-		c->decode_path = c->generic ? "fp32_generic" : c->decode_kind == 5 ? "bf16_tcgen05_n192_fold" : c->decode_kind == 4 ? "bf16_tcgen05_n192" : c->decode_kind == 2 ? "bf16_tcgen05" : c->decode_kind == 3 ? "bf16_mma" : "fp32";
+		c->decode_path = c->generic ? "fp32_generic" : c->decode_kind == 2 ? "bf16_tcgen05_n192_fold" : "fp32";
 		CUDA_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
 		CUDA_TRY(vqvdb::configure_encode_fp32());
 		CUDA_TRY(vqvdb::configure_encode_tc());
 		CUDA_TRY(vqvdb::configure_decode_fp32());
-		CUDA_TRY(vqvdb::configure_decode_mma());
 		CUDA_TRY(vqvdb::configure_decode_tc());
-		CUDA_TRY(vqvdb::configure_decode_tc2());
 	} catch (const std::exception& e) {
 		return translate(nullptr, e);
 	}
@@ -572,11 +698,11 @@ int vqvdb_b200_encode(vqvdb_b200_codec* c, const float* host_leaves, int64_t n, 
 		int64_t done = 0;
 		for (int i = 0; done < n; ++i) {
 			Slot& s = c->slots[i % kSlots];
-			retire<uint8_t>(s, host_indices, 64, s.h_idx, out_direct);
+			retire<uint8_t>(*c->copier, s, host_indices, 64, s.h_idx, out_direct);
 			const int64_t cnt = std::min<int64_t>(c->chunk, n - done);
 			const float* src = host_leaves + (size_t)done * leaf_elems;
 			if (!in_direct) {
-				std::memcpy(s.h_vox, src, (size_t)cnt * leaf_elems * sizeof(float));
+				c->copier->copy(s.h_vox, src, (size_t)cnt * leaf_elems * sizeof(float));
 				src = s.h_vox;
 			}
 			CUDA_TRY(cudaMemcpyAsync(s.d_vox, src, (size_t)cnt * leaf_elems * sizeof(float), cudaMemcpyHostToDevice, s.stream));
@@ -588,7 +714,7 @@ int vqvdb_b200_encode(vqvdb_b200_codec* c, const float* host_leaves, int64_t n, 
 			s.pending_count = cnt;
 			done += cnt;
 		}
-		for (auto& s : c->slots) retire<uint8_t>(s, host_indices, 64, s.h_idx, out_direct);
+		for (auto& s : c->slots) retire<uint8_t>(*c->copier, s, host_indices, 64, s.h_idx, out_direct);
 	} catch (const std::exception& e) {
 		for (auto& s : c->slots) s.pending_first = -1;
 		return translate(c, e);
@@ -608,11 +734,11 @@ int vqvdb_b200_decode(vqvdb_b200_codec* c, const uint8_t* host_indices, int64_t 
 		int64_t done = 0;
 		for (int i = 0; done < n; ++i) {
 			Slot& s = c->slots[i % kSlots];
-			retire<float>(s, host_voxels, leaf_elems, s.h_vox, out_direct);
+			retire<float>(*c->copier, s, host_voxels, leaf_elems, s.h_vox, out_direct);
 			const int64_t cnt = std::min<int64_t>(c->chunk, n - done);
 			const uint8_t* src = host_indices + (size_t)done * 64;
 			if (!in_direct) {
-				std::memcpy(s.h_idx, src, (size_t)cnt * 64);
+				c->copier->copy(s.h_idx, src, (size_t)cnt * 64);
 				src = s.h_idx;
 			}
 			CUDA_TRY(cudaMemcpyAsync(s.d_idx, src, (size_t)cnt * 64, cudaMemcpyHostToDevice, s.stream));
@@ -624,7 +750,7 @@ int vqvdb_b200_decode(vqvdb_b200_codec* c, const uint8_t* host_indices, int64_t 
 			s.pending_count = cnt;
 			done += cnt;
 		}
-		for (auto& s : c->slots) retire<float>(s, host_voxels, leaf_elems, s.h_vox, out_direct);
+		for (auto& s : c->slots) retire<float>(*c->copier, s, host_voxels, leaf_elems, s.h_vox, out_direct);
 	} catch (const std::exception& e) {
 		for (auto& s : c->slots) s.pending_first = -1;
 		return translate(c, e);
@@ -637,11 +763,10 @@ int vqvdb_b200_debug_decode_tap(vqvdb_b200_codec* c, const uint8_t* dev_indices,
 	if (!c) return VQVDB_B200_ERR_INVALID_ARGUMENT;
 	if (n < 0 || stage < 0 || (stage > 2 && stage != 100) || (n > 0 && (!dev_indices || !dev_tap || !dev_voxels)))
 		return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "debug_decode_tap: bad arguments");
+	if (c->generic) return fail(c, VQVDB_B200_ERR_UNSUPPORTED, "debug_decode_tap: float model only");
 	try {
 		CUDA_TRY(cudaSetDevice(c->device));
-		if (c->decode_kind == 3) CUDA_TRY(vqvdb::launch_decode_mma(c->dec_mma, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
-		else if (c->decode_kind >= 4) CUDA_TRY(vqvdb::launch_decode_tc2(c->dec_mma, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, c->decode_kind == 5, stage, dev_tap));
-		else CUDA_TRY(vqvdb::launch_decode_tc(c->dec_mma, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
+		CUDA_TRY(vqvdb::launch_decode_tc(c->dec_mma, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
 	} catch (const std::exception& e) {
 		return translate(c, e);
 	}

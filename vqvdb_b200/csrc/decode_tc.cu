@@ -1,31 +1,29 @@
-// Tensor-core decoder on the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators, the gathered
-// (im2col) A operand written into TMEM by the threads themselves, weights streamed by TMA.
+// Tensor-core decoder (tcgen05.mma, TMEM accumulators, bf16 operands, fp32 accumulation): 64 uint8 indices in, 512 voxels
+// out, one kernel.  Reference: python/save_for_inference.py:91-104 (gather + permute) + python/VQVAE_v2.py:253-275
+// (DecoderFloat.forward); weight stream and the folded tail are described in decode_tc.cuh.
 //
-// Same arithmetic contract as decode_mma.cu (bf16 operands, fp32 accumulate; reference:
-// python/save_for_inference.py:91-104 + python/VQVAE_v2.py:253-275), different machine mapping:
-//
-//   * GEMM tile = 128 rows x 64 columns: the 64 latent positions of TWO leaves x 64 output channels,
-//     one tcgen05.mma.cta_group::1.kind::f16 per 16 input channels.  A CTA keeps 4 such tiles (8 leaves) in flight;
-//     their fp32 accumulators live in TMEM (4 x 64 columns), never in registers.
-//   * a 3x3x3 convolution over a 4^3 leaf cannot be described to the tensor core by a shared-memory descriptor
-//     (rows of 4 voxels, zero padding), so the A operand goes through TMEM: for every (tap, 64-channel) unit each
-//     of a tile's 128 threads loads ITS row — the shifted neighbour's 64 channels, or zeros outside the leaf — from
-//     the channels-last bf16 activation buffer in shared memory and writes it to its TMEM lane (tcgen05.st).
-//     A is double-buffered per tile (2 x 32 columns), so staging unit u+1 overlaps the MMAs of unit u.
-//   * B (weights) is the same stream of 216 pre-swizzled 8 KB units [64 n][64 k] as decode_mma.cu: exactly the
-//     canonical SWIZZLE_128B K-major layout a UMMA shared-memory descriptor expects.  An 8-stage ring is filled by
-//     1-D TMA bulk copies; all 8 leaves share every unit.
-//   * warp roles: 16 worker warps (4 per tile = the four TMEM lane quadrants) stage A and run the epilogues
-//     (GroupNorm, residual, channel attention, pixel-shuffle + final conv on FFMA, sigmoid, stores); 4 control
-//     warps, one elected lane each, issue the MMAs of one tile and signal completion with tcgen05.commit, so the
-//     tiles run out of phase and one tile's epilogue hides behind the others' MMAs; one more lane issues the TMA.
-//     (Letting a worker thread issue its tile's MMAs after a tile barrier was measured 27 % slower.)
-//   * synchronisation is mbarrier-only on the MMA path: w_full/w_empty per ring stage, a_full/a_empty per (tile,
-//     A buffer), d_full per tile; the two warps that share a leaf meet on a 64-thread named barrier for the
-//     per-leaf reductions.
+//   * the gathered A operand goes through TMEM (TS-mode MMA): each of a tile's 128 rows (the 64 latent positions of two
+//     leaves) is staged by its own threads — the tap-shifted neighbour's channels, or a zero row outside the leaf —
+//     from the channels-last bf16 activation buffer into its TMEM lane (tcgen05.st).
+//   * a unit is one (kd, kh) tap PAIR: the A rows are shifted along d and h only, and the three kw taps ride along N —
+//     B = [3 kw x 64 cout][64 cin] = three consecutive 8 KB tiles of the weight stream, N = 192 (96 cycles per MMA, the
+//     pipe's floor).  The accumulator holds three partial convolutions per row; the kw shift is applied when it is read:
+//     out(w) = P0(w-1) + P1(w) + P2(w+1), a lane shuffle that never leaves the warp (w = lane & 3) and supplies the zero
+//     padding along w.  (First generation, one unit per tap and N = 64: 5.5 M leaves/s, tensor pipe 28 % busy,
+//     profiles/r1d_decode_tc_pipeline.txt; this scheme: 9.0 M before the fold below.)
+//   * the accumulator is 192 columns, so a CTA holds 2 tiles (2 x 2 leaves): TMEM = 2 x 192 (D) + 2 x 2 x 32 (A,
+//     double-buffered).  Each 128-row tile is served by EIGHT warps: warp = (TMEM lane quadrant, channel half) — a thread
+//     owns 32 of the 64 channels of its row for staging and for every epilogue, GroupNorm groups never straddle the
+//     halves, and the two halves of a leaf only meet for the channel attention and the final store.
+//   * up_conv -> PixelShuffle3D -> final is one linear map, folded on the host into a 64 -> 64 convolution G + an 8-term
+//     gather per output voxel (decode_tc.cuh): 45 units per group of leaves and no CUDA-core convolution at all.  G is
+//     parked as fp32 [64 ch][64 pos] (channel-major, skewed so the gather is bank-conflict free) over the leaf's by
+//     then idle activation region; thread (row R, channel half) sums the in-grid neighbours for its four voxels,
+//     applies the sigmoid and stores 16 bytes.
+// Measured (1 M leaves, B200): 15.4 M leaves/s.
 #include <cuda_bf16.h>
 
-#include "decode_mma.cuh"
+#include "decode_tc.cuh"
 #include "leaf_ops.cuh"
 #include "ptx_utils.cuh"
 
@@ -33,32 +31,46 @@ namespace vqvdb {
 
 namespace {
 
-constexpr int kTiles = 4;
-constexpr int kLeavesPerCta = 2 * kTiles;
-constexpr int kWorkWarps = 4 * kTiles;
-constexpr int kCtrlWarps = kTiles;               // one MMA issuer per tile
-constexpr int kThreads = (kWorkWarps + kCtrlWarps) * 32;  // 640
-constexpr int kStages = 8;
-constexpr uint32_t kUnitBytes = 8192;
+constexpr int kTiles = 2;
+constexpr int kLeavesPerCta = 2 * kTiles;                  // 4
+constexpr int kWorkWarps = 8 * kTiles;                     // 16: (tile, channel half, lane quadrant)
+constexpr int kCtrlWarps = kTiles + 1;                     // one MMA issuer per tile + the TMA producer
+constexpr int kThreads = (kWorkWarps + kCtrlWarps) * 32;   // 608
+constexpr int kStages = 4;
+constexpr uint32_t kSrcUnitBytes = 8192;                   // one [64 n][64 k] tile of the weight stream
+constexpr uint32_t kUnitBytes = 3 * kSrcUnitBytes;         // [3 kw x 64 n][64 k]
+// units per group of leaves: stem (2 input halves), res conv1, res conv2, the folded tail conv (decode_tc.cuh:
+// up_conv -> PixelShuffle3D -> final as one 64 -> 64 conv + an 8-term gather)
+constexpr int kUnitsPerGroup = 18 + 9 + 9 + 9;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColD = 0;      // tile t accumulator: columns [t*64, t*64+64)
-constexpr uint32_t kColA = 256;    // tile t A buffers:   columns 256 + t*64 + buf*32
+constexpr uint32_t kDCols = 192;                           // tile t accumulator: columns [t*192, t*192 + 192)
+constexpr uint32_t kColA = kTiles * kDCols;                // tile t A buffers: columns 384 + t*64 + buf*32
 
-// instruction descriptor: D=f32, A=B=bf16, both K-major, N=64, M=128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D = f32, A = B = bf16, both K-major, N = 192, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((192u >> 3) << 17) | ((128u >> 4) << 24);
+
+// per-channel parameters staged in shared memory (float offsets)
+namespace par {
+constexpr int stem_b = 0, stem_gn_w = 64, stem_gn_b = 128, gn1_w = 192, gn1_b = 256, c1_b = 320, gn2_w = 384, gn2_b = 448,
+              c2_b = 512, fin_b = 576, fc0 = 580, fc2 = fc0 + 16 * 72, fold_b = fc2 + 64 * 17, total = fold_b + 64;
+constexpr int fc0_pitch = 72, fc2_pitch = 17;
+}
 
 // shared memory map (bytes)
 constexpr uint32_t kOffRing = 0;
-constexpr uint32_t kOffLeaf = kOffRing + kStages * kUnitBytes;           // 8 x 16 KB
-constexpr uint32_t kLeafBytes = 16384;
-constexpr uint32_t kOffBar = kOffLeaf + kLeavesPerCta * kLeafBytes;      // mbarriers
-constexpr uint32_t kNumBars = 2 * kStages + 4 * kTiles + kTiles;         // w_full, w_empty, a_full[t][2], a_empty[t][2], d_full[t]
+constexpr uint32_t kOffLeaf = kOffRing + kStages * kUnitBytes;            // 4 x 16 KB
+constexpr uint32_t kLeafBytes = 16384 + 16;                               // + the 3-word skew of the fp32 G planes (see the folded tail)
+constexpr uint32_t kOffZero = kOffLeaf + kLeavesPerCta * kLeafBytes;      // 128 zero bytes: the source row of out-of-leaf taps
+constexpr uint32_t kOffBar = kOffZero + 128;
+constexpr uint32_t kNumBars = 2 * kStages + 4 * kTiles + kTiles;          // w_full, w_empty, a_full[t][2], a_empty[t][2], d_full[t]
 constexpr uint32_t kOffTmemSlot = kOffBar + kNumBars * 8;
-constexpr uint32_t kOffFinW = kOffTmemSlot + 16;                         // 864 floats
-constexpr uint32_t kOffScratch = kOffFinW + 864 * 4;                     // per leaf: 256 floats
-constexpr uint32_t kScratchFloats = 256;
+constexpr uint32_t kOffPar = kOffTmemSlot + 16;
+constexpr uint32_t kOffScratch = kOffPar + par::total * 4;
+// per-leaf scratch (floats): exch [2 slots][2 warps][2 halves][8], part [2][64], scale [64], hid [16], idx [16 words]
+constexpr uint32_t kScrExch = 0, kScrPart = 64, kScrScale = 192, kScrHid = 256, kScrIdx = 272, kScratchFloats = 288;
 constexpr uint32_t kSmemBytes = kOffScratch + kLeavesPerCta * kScratchFloats * 4;
 static_assert(kSmemBytes <= 227 * 1024, "decode_tc smem budget");
+static_assert(kOffBar % 8 == 0 && kOffPar % 16 == 0 && kOffScratch % 16 == 0, "alignment");
 
 __device__ __forceinline__ uint32_t bar_w_full(uint32_t bars, uint32_t s) { return bars + s * 8; }
 __device__ __forceinline__ uint32_t bar_w_empty(uint32_t bars, uint32_t s) { return bars + (kStages + s) * 8; }
@@ -71,7 +83,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
 	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem_d] (+)= A[tmem_a] (128 x 16 bf16, TMEM) * B[desc] (64 x 16 bf16, shared)^T
+// D[tmem_d] (+)= A[tmem_a] (128 x 16 bf16, TMEM) * B[desc] (192 x 16 bf16, shared)^T
 __device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
 	asm volatile(
 	    "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
@@ -84,67 +96,71 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 	return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
 	       ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
 	asm volatile(
-	    "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-	    ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-	    "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
-	    "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
-	    "r"(r[30]), "r"(r[31])
+	    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+	    "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+	    "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
 	    : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-	uint32_t o[32];
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+	uint32_t o[16];
 	asm volatile(
-	    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-	    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+	    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
 	    : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]), "=r"(o[9]),
-	      "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15]), "=r"(o[16]), "=r"(o[17]), "=r"(o[18]), "=r"(o[19]),
-	      "=r"(o[20]), "=r"(o[21]), "=r"(o[22]), "=r"(o[23]), "=r"(o[24]), "=r"(o[25]), "=r"(o[26]), "=r"(o[27]), "=r"(o[28]), "=r"(o[29]),
-	      "=r"(o[30]), "=r"(o[31])
+	      "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15])
 	    : "r"(taddr));
-	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-	for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(o[j]);
+	for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(o[j]);
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 	asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+	uint4 v;
+	asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+	asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 
-// Per-thread view of the work: which tile / TMEM lane quadrant / leaf / latent position this thread is.
+// Per-thread view of the work: which tile / TMEM lane quadrant / channel half / leaf / latent position this thread is.
 struct Worker {
-	int tile, quad, lane, row;      // row = quad*32 + lane in [0,128)
-	int leaf_slot;                  // tile*2 + (row >> 6)
-	int pos, d, h, w;               // latent position within the leaf
-	int wil;                        // warp-in-leaf: 0 or 1
-	uint32_t unit = 0;              // units staged so far (same sequence in every worker and in the control thread)
-	uint32_t passes = 0;            // accumulator hand-overs so far (parity of d_full)
-	uint32_t bars, tmem_lane;       // mbarrier base; tmem base + (quad*32 << 16)
-	long long t_wait = 0, t_stage = 0, t_acc = 0;  // kProf only: cycles waiting for a free A buffer / staging / waiting for d_full
+	int tile, quad, chalf, lane, row;  // row = quad*32 + lane in [0,128)
+	int leaf_slot;                     // tile*2 + (row >> 6)
+	int pos, d, h, w;                  // latent position within the leaf
+	int wil;                           // warp-in-leaf along the rows: 0 or 1
+	uint32_t unit = 0;                 // units staged so far (same sequence in every worker of the tile and in its issuer)
+	uint32_t passes = 0;               // accumulator hand-overs so far (parity of d_full)
+	uint32_t reds = 0;                 // half-leaf reductions so far (alternates the exchange slot)
+	uint32_t bars, tmem_lane, zero_row;
+	long long t_wait = 0, t_stage = 0, t_acc = 0;  // kProf only
 };
 template <bool P> __device__ __forceinline__ long long prof_clock() { return P ? clock64() : 0; }
 
-// Stage one A unit: this thread's row (64 bf16 channels = 32 words) -> its TMEM lane, then hand the buffer to the MMA.
+__device__ __forceinline__ void leaf_bar(const Worker& wk) { named_bar_sync(1 + wk.leaf_slot, 128); }
+__device__ __forceinline__ void half_bar(const Worker& wk) { named_bar_sync(1 + kLeavesPerCta + wk.leaf_slot * 2 + wk.chalf, 64); }
+
+// Stage one A unit: this thread's 32 channels (16 words) of the source row -> its TMEM lane, then hand the buffer to
+// the MMA.  `seg` = shared address of the 128-byte (64-channel) segment of the source row, chunks swizzled by `swz`;
+// out-of-leaf taps pass the zero row.  The loads are issued before the wait for the free buffer.
 template <bool kProf>
-__device__ __forceinline__ void stage_unit(Worker& wk, bool valid, uint32_t src_row /*smem addr of the 128-B half row*/, uint32_t swz) {
+__device__ __forceinline__ void stage_unit(Worker& wk, uint32_t seg, uint32_t swz) {
 	const uint32_t buf = wk.unit & 1u;
+	uint32_t r[16];
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		const uint4 v = lds128(seg + ((((uint32_t)(wk.chalf * 4 + q)) ^ swz) << 4));
+		r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+	}
 	const long long c0 = prof_clock<kProf>();
 	if (wk.lane == 0) mbar_wait(bar_a_empty(wk.bars, wk.tile, buf), ((wk.unit >> 1) & 1u) ^ 1u);
 	__syncwarp();
 	tc_fence_after();
 	const long long c1 = prof_clock<kProf>();
-	uint32_t r[32];
-	if (valid) {
-#pragma unroll
-		for (int q = 0; q < 8; ++q) {
-			const uint32_t a = src_row + (((uint32_t)q ^ swz) << 4);
-			asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[4 * q]), "=r"(r[4 * q + 1]), "=r"(r[4 * q + 2]), "=r"(r[4 * q + 3]) : "r"(a));
-		}
-	} else {
-#pragma unroll
-		for (int j = 0; j < 32; ++j) r[j] = 0u;
-	}
-	tmem_st32(wk.tmem_lane + kColA + wk.tile * 64 + buf * 32, r);
+	tmem_st16(wk.tmem_lane + kColA + wk.tile * 64 + buf * 32 + wk.chalf * 16, r);
 	asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 	tc_fence_before();
 	__syncwarp();
@@ -156,18 +172,21 @@ __device__ __forceinline__ void stage_unit(Worker& wk, bool valid, uint32_t src_
 	}
 }
 
-// One 3x3x3 conv: stage 27 * HALVES units from the leaf's activation rows (ROW_BYTES = HALVES * 128).
+// The (kd, kh) = t tap pair of a conv whose input rows are HALVES * 128 bytes: HALVES units.
+template <int HALVES, bool kProf>
+__device__ __forceinline__ void stage_tap_pair(Worker& wk, uint32_t act_base, int t) {
+	const int td = t / 3, th = t - td * 3;
+	const bool ok = (unsigned)(wk.d + td - 1) < 4u && (unsigned)(wk.h + th - 1) < 4u;
+	const int p2 = wk.pos + (td - 1) * 16 + (th - 1) * 4;
+	const uint32_t row = ok ? act_base + (uint32_t)p2 * (HALVES * 128) : wk.zero_row;
+	const uint32_t swz = ok ? ((uint32_t)p2 & 7u) : 0u;
+#pragma unroll
+	for (int half = 0; half < HALVES; ++half) stage_unit<kProf>(wk, row + (ok ? half * 128 : 0), swz);
+}
 template <int HALVES, bool kProf>
 __device__ __forceinline__ void stage_conv(Worker& wk, uint32_t act_base) {
-	constexpr uint32_t ROW_BYTES = HALVES * 128;
 #pragma unroll 1
-	for (int tap = 0; tap < 27; ++tap) {
-		const int td = tap / 9, th = (tap / 3) % 3, tw = tap % 3;
-		const bool ok = (unsigned)(wk.d + td - 1) < 4u && (unsigned)(wk.h + th - 1) < 4u && (unsigned)(wk.w + tw - 1) < 4u;
-		const int p2 = wk.pos + (td - 1) * 16 + (th - 1) * 4 + (tw - 1);
-#pragma unroll
-		for (int half = 0; half < HALVES; ++half) stage_unit<kProf>(wk, ok, act_base + (uint32_t)p2 * ROW_BYTES + half * 128, (uint32_t)p2 & 7u);
-	}
+	for (int t = 0; t < 9; ++t) stage_tap_pair<HALVES, kProf>(wk, act_base, t);
 }
 
 // Wait until this tile's accumulator holds the finished layer.
@@ -180,78 +199,98 @@ __device__ __forceinline__ void wait_accumulator(Worker& wk) {
 	if (kProf) wk.t_acc += prof_clock<kProf>() - c0;
 }
 
-// Sum `n` per-thread values over the 64 rows of this thread's leaf (2 warps): butterfly + one exchange.
-template <int N>
-__device__ __forceinline__ void leaf_allreduce(float (&v)[N], const Worker& wk, float* exch /*[2][N] per leaf*/) {
+// This thread's 32 output channels of the finished conv: the three kw partials combined across neighbouring rows.
+__device__ __forceinline__ void load_conv32(const Worker& wk, float (&v)[32]) {
+	const uint32_t base = wk.tmem_lane + wk.tile * kDCols + wk.chalf * 32;
+	const bool has_lo = wk.w > 0, has_hi = wk.w < 3;
 #pragma unroll
-	for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
-	if (wk.lane == 0) {
+	for (int part = 0; part < 2; ++part) {
+		float a[16], b[16], c[16];
+		tmem_ld16_nowait(base + part * 16, a);        // kw = 0: belongs to the row at w + 1
+		tmem_ld16_nowait(base + 64 + part * 16, b);   // kw = 1
+		tmem_ld16_nowait(base + 128 + part * 16, c);  // kw = 2: belongs to the row at w - 1
+		tmem_wait_ld();
 #pragma unroll
-		for (int i = 0; i < N; ++i) exch[wk.wil * N + i] = v[i];
-	}
-	named_bar_sync(1 + wk.leaf_slot, 64);
-#pragma unroll
-	for (int i = 0; i < N; ++i) v[i] = exch[i] + exch[N + i];
-	named_bar_sync(1 + wk.leaf_slot, 64);  // exch may be reused right away
-}
-
-// row-major [64 pos][64 ch] bf16 buffer, 128-B rows, 16-B chunks swizzled by pos & 7: store this thread's 32 values
-// (channels c0..c0+31) of its row.
-__device__ __forceinline__ void store_row_half(uint32_t buf_base, int pos, int half, const float (&v)[32]) {
-#pragma unroll
-	for (int q = 0; q < 4; ++q) {
-		const uint32_t chunk = (uint32_t)(half * 4 + q) ^ ((uint32_t)pos & 7u);
-		const uint32_t a = buf_base + (uint32_t)pos * 128 + (chunk << 4);
-		asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(pack_bf16(v[8 * q], v[8 * q + 1])),
-		             "r"(pack_bf16(v[8 * q + 2], v[8 * q + 3])), "r"(pack_bf16(v[8 * q + 4], v[8 * q + 5])),
-		             "r"(pack_bf16(v[8 * q + 6], v[8 * q + 7])));
-	}
-}
-__device__ __forceinline__ void load_row_half(uint32_t buf_base, int pos, int half, float (&v)[32]) {
-#pragma unroll
-	for (int q = 0; q < 4; ++q) {
-		const uint32_t chunk = (uint32_t)(half * 4 + q) ^ ((uint32_t)pos & 7u);
-		const uint32_t a = buf_base + (uint32_t)pos * 128 + (chunk << 4);
-		uint32_t w0, w1, w2, w3;
-		asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(a));
-		float2 f;
-		f = unpack_bf16(w0); v[8 * q] = f.x; v[8 * q + 1] = f.y;
-		f = unpack_bf16(w1); v[8 * q + 2] = f.x; v[8 * q + 3] = f.y;
-		f = unpack_bf16(w2); v[8 * q + 4] = f.x; v[8 * q + 5] = f.y;
-		f = unpack_bf16(w3); v[8 * q + 6] = f.x; v[8 * q + 7] = f.y;
-	}
-}
-
-// GroupNorm(8, 64) statistics of (accumulator + bias) over the leaf: mean/rstd per group.
-__device__ __forceinline__ void gn_stats_from_tmem(const Worker& wk, const float* __restrict__ bias, float* exch, float (&mean)[8],
-                                                   float (&rstd)[8]) {
-	float st[16];
-#pragma unroll
-	for (int i = 0; i < 16; ++i) st[i] = 0.f;
-#pragma unroll
-	for (int half = 0; half < 2; ++half) {
-		float v[32];
-		tmem_ld32(wk.tmem_lane + kColD + wk.tile * 64 + half * 32, v);
-#pragma unroll
-		for (int j = 0; j < 32; ++j) {
-			const float x = v[j] + (bias ? __ldg(bias + half * 32 + j) : 0.f);
-			st[half * 4 + (j >> 3)] += x;
-			st[8 + half * 4 + (j >> 3)] = fmaf(x, x, st[8 + half * 4 + (j >> 3)]);
+		for (int j = 0; j < 16; ++j) {
+			const float lo = __shfl_up_sync(0xffffffffu, a[j], 1);
+			const float hi = __shfl_down_sync(0xffffffffu, c[j], 1);
+			v[part * 16 + j] = b[j] + (has_lo ? lo : 0.f) + (has_hi ? hi : 0.f);
 		}
 	}
-	leaf_allreduce<16>(st, wk, exch);
+}
+
+// Sum N per-thread values over the 64 rows of this thread's leaf, among the threads of its channel half (2 warps).
+template <int N>
+__device__ __forceinline__ void half_allreduce(float (&v)[N], Worker& wk, float* exch /* [2 slots][2 warps][2 halves][8] */) {
+	static_assert(N <= 8, "exchange slot size");
 #pragma unroll
-	for (int g = 0; g < 8; ++g) {
-		mean[g] = st[g] * (1.f / 512.f);
-		const float var = fmaxf(st[8 + g] * (1.f / 512.f) - mean[g] * mean[g], 0.f);
-		rstd[g] = 1.f / sqrtf(var + kGnEps);
+	for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+	float* e = exch + (wk.reds & 1u) * 32;
+	if (wk.lane == 0) {
+#pragma unroll
+		for (int i = 0; i < N; ++i) e[(wk.wil * 2 + wk.chalf) * 8 + i] = v[i];
 	}
+	half_bar(wk);
+#pragma unroll
+	for (int i = 0; i < N; ++i) v[i] = e[wk.chalf * 8 + i] + e[(2 + wk.chalf) * 8 + i];
+	++wk.reds;  // the next reduction uses the other slot; this one is rewritten only after another barrier has been passed
+}
+
+// GroupNorm(8, 64) over the leaf for this thread's four groups: v -> statistics.
+__device__ __forceinline__ void gn_stats(const float (&v)[32], Worker& wk, float* exch, float (&mean)[4], float (&rstd)[4]) {
+	float st[8];
+#pragma unroll
+	for (int i = 0; i < 8; ++i) st[i] = 0.f;
+#pragma unroll
+	for (int j = 0; j < 32; ++j) {
+		st[j >> 3] += v[j];
+		st[4 + (j >> 3)] = fmaf(v[j], v[j], st[4 + (j >> 3)]);
+	}
+	half_allreduce<8>(st, wk, exch);
+#pragma unroll
+	for (int g = 0; g < 4; ++g) {
+		mean[g] = st[g] * (1.f / 512.f);
+		rstd[g] = 1.f / sqrtf(fmaxf(st[4 + g] * (1.f / 512.f) - mean[g] * mean[g], 0.f) + kGnEps);
+	}
+}
+
+// row-major [64 pos][64 ch] bf16 buffer, 128-B rows, 16-B chunks swizzled by pos & 7: this thread's 32 channels
+__device__ __forceinline__ void store_row_half(uint32_t buf_base, const Worker& wk, const float (&v)[32]) {
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		const uint32_t a = buf_base + (uint32_t)wk.pos * 128 + ((((uint32_t)(wk.chalf * 4 + q)) ^ ((uint32_t)wk.pos & 7u)) << 4);
+		sts128(a, pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]), pack_bf16(v[8 * q + 4], v[8 * q + 5]),
+		       pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+	}
+}
+__device__ __forceinline__ void load_row_chunk(uint32_t buf_base, const Worker& wk, int q, float (&x)[8]) {
+	const uint4 raw = lds128(buf_base + (uint32_t)wk.pos * 128 + ((((uint32_t)(wk.chalf * 4 + q)) ^ ((uint32_t)wk.pos & 7u)) << 4));
+	float2 f;
+	f = unpack_bf16(raw.x); x[0] = f.x; x[1] = f.y;
+	f = unpack_bf16(raw.y); x[2] = f.x; x[3] = f.y;
+	f = unpack_bf16(raw.z); x[4] = f.x; x[5] = f.y;
+	f = unpack_bf16(raw.w); x[6] = f.x; x[7] = f.y;
+}
+
+// Transposing butterfly: afterwards v[0] of lane L = sum over the warp's 32 lanes of the original v[L].  Destroys v.
+__device__ __forceinline__ float column_sums(float (&v)[32], int lane) {
+#pragma unroll
+	for (int step = 16; step >= 1; step >>= 1) {
+		const bool upper = (lane & step) != 0;
+#pragma unroll
+		for (int i = 0; i < step; ++i) {
+			const float send = upper ? v[i] : v[i + step];
+			const float keep = upper ? v[i + step] : v[i];
+			v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+		}
+	}
+	return v[0];
 }
 
 template <bool kProf>
 __global__ void __launch_bounds__(kThreads, 1)
 decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices, int64_t n_leaves, float* __restrict__ voxels,
-                 int tap_stage, float* __restrict__ tap_out) {
+                  int tap_stage, float* __restrict__ tap_out) {
 	extern __shared__ __align__(1024) uint8_t smem[];
 	const uint32_t s_base = smem_u32(smem);
 	const uint32_t ring = s_base + kOffRing;
@@ -259,8 +298,27 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int64_t n_groups = (n_leaves + kLeavesPerCta - 1) / kLeavesPerCta;
 	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmemSlot);
+	float* s_par = reinterpret_cast<float*>(smem + kOffPar);
 
-	for (int i = threadIdx.x; i < 864; i += kThreads) reinterpret_cast<float*>(smem + kOffFinW)[i] = __ldg(w.fin_w + i);
+	// ---- per-channel parameters, final-conv and attention weights -> shared memory ----
+	for (int i = threadIdx.x; i < 64; i += kThreads) {
+		s_par[par::stem_b + i] = __ldg(w.stem_b + i);
+		s_par[par::stem_gn_w + i] = __ldg(w.stem_gn_w + i);
+		s_par[par::stem_gn_b + i] = __ldg(w.stem_gn_b + i);
+		s_par[par::gn1_w + i] = __ldg(w.res.gn1_w + i);
+		s_par[par::gn1_b + i] = __ldg(w.res.gn1_b + i);
+		s_par[par::c1_b + i] = __ldg(w.res.c1_b + i);
+		s_par[par::gn2_w + i] = __ldg(w.res.gn2_w + i);
+		s_par[par::gn2_b + i] = __ldg(w.res.gn2_b + i);
+		s_par[par::c2_b + i] = __ldg(w.res.c2_b + i);
+		s_par[par::fold_b + i] = __ldg(w.fold_b + i);
+	}
+	for (int i = threadIdx.x; i < 1024; i += kThreads) {
+		s_par[par::fc0 + (i >> 6) * par::fc0_pitch + (i & 63)] = __ldg(w.fc0 + i);  // [16][64]
+		s_par[par::fc2 + (i >> 4) * par::fc2_pitch + (i & 15)] = __ldg(w.fc2 + i);  // [64][16]
+	}
+	if (threadIdx.x == 0) s_par[par::fin_b] = __ldg(w.fin_b);
+	if (threadIdx.x < 32) reinterpret_cast<uint32_t*>(smem + kOffZero)[threadIdx.x] = 0u;
 	if (threadIdx.x == 0) {
 		for (uint32_t s = 0; s < kStages; ++s) {
 			mbar_init(bar_w_full(bars, s), 1);
@@ -268,7 +326,7 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 		}
 		for (uint32_t t = 0; t < kTiles; ++t) {
 			for (uint32_t b = 0; b < 2; ++b) {
-				mbar_init(bar_a_full(bars, t, b), 4);   // one arrival per worker warp of the tile
+				mbar_init(bar_a_full(bars, t, b), 8);   // one arrival per worker warp of the tile
 				mbar_init(bar_a_empty(bars, t, b), 1);  // tcgen05.commit
 			}
 			mbar_init(bar_d_full(bars, t), 1);
@@ -286,62 +344,77 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 	const int64_t my_groups = blockIdx.x < n_groups ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
 	if (warp >= kWorkWarps) {
-		// ===================== control warps: one MMA issuer per tile (lane 0 of warp 16+t) =====================
-		// Issuers are independent of each other, so tiles drift apart and one tile's epilogue overlaps the other
-		// tiles' MMAs.  Lane 1 of the first control warp is the TMA producer for the ring all four tiles share.
-		const uint32_t total = (uint32_t)(my_groups * kDecUnitsTotal);
-		if (lane == 0) {
-			const uint32_t t = warp - kWorkWarps;
-			uint32_t unit = 0;
-			long long tw = 0, ta = 0, ti = 0;
-			const long long tstart = prof_clock<kProf>();
-			for (int64_t g = 0; g < my_groups; ++g) {
+		// ===================== control warps =====================
+		if (warp < kWorkWarps + kTiles) {
+			if (lane == 0) {
+				// MMA issuer of tile t.  The issuers are independent, so the tiles drift apart and one tile's epilogue
+				// overlaps the other tile's MMAs.
+				const uint32_t t = warp - kWorkWarps;
+				uint32_t unit = 0;
+				long long tw = 0, ta = 0, ti = 0;
+				const long long tstart = prof_clock<kProf>();
+				for (int64_t g = 0; g < my_groups; ++g) {
 #pragma unroll 1
-				for (int u = 0; u < kDecUnitsTotal; ++u) {
-					const uint32_t s = unit % kStages, buf = unit & 1u;
-					// position of this unit inside its layer pass: stem = 54 units, then six passes of 27
-					const int in_pass = u < 54 ? u : (u - 54) % 27;
-					const bool last = u < 54 ? (u == 53) : (in_pass == 26);
-					const long long c0 = prof_clock<kProf>();
-					mbar_wait(bar_w_full(bars, s), (unit / kStages) & 1u);
-					const long long c1 = prof_clock<kProf>();
-					mbar_wait(bar_a_full(bars, t, buf), (unit >> 1) & 1u);
-					tc_fence_after();
-					const long long c2 = prof_clock<kProf>();
-					const uint64_t bdesc = make_desc_sw128(ring + s * kUnitBytes);
+					for (int u = 0; u < kUnitsPerGroup; ++u) {
+						const uint32_t s = unit % kStages, buf = unit & 1u;
+						// position of this unit inside its layer pass: stem = 18 units, then six passes of 9
+						const int in_pass = u < 18 ? u : (u - 18) % 9;
+						const bool last = u < 18 ? (u == 17) : (in_pass == 8);
+						const long long c0 = prof_clock<kProf>();
+						mbar_wait(bar_w_full(bars, s), (unit / kStages) & 1u);
+						const long long c1 = prof_clock<kProf>();
+						mbar_wait(bar_a_full(bars, t, buf), (unit >> 1) & 1u);
+						tc_fence_after();
+						const long long c2 = prof_clock<kProf>();
+						const uint64_t bdesc = make_desc_sw128(ring + s * kUnitBytes);
 #pragma unroll
-					for (uint32_t kk = 0; kk < 4; ++kk)
-						tc_mma_ts(tmem + kColD + t * 64, tmem + kColA + t * 64 + buf * 32 + kk * 8, bdesc + (uint64_t)(kk * 2),
-						          (in_pass > 0 || kk > 0) ? 1u : 0u);
-					tc_commit(bar_a_empty(bars, t, buf));
-					if (last) tc_commit(bar_d_full(bars, t));
-					tc_commit(bar_w_empty(bars, s));
-					++unit;
-					if (kProf) {
-						tw += c1 - c0;
-						ta += c2 - c1;
-						ti += prof_clock<kProf>() - c2;
+						for (uint32_t kk = 0; kk < 4; ++kk)
+							tc_mma_ts(tmem + t * kDCols, tmem + kColA + t * 64 + buf * 32 + kk * 8, bdesc + (uint64_t)(kk * 2),
+							          (in_pass > 0 || kk > 0) ? 1u : 0u);
+						tc_commit(bar_a_empty(bars, t, buf));
+						if (last) tc_commit(bar_d_full(bars, t));
+						tc_commit(bar_w_empty(bars, s));
+						++unit;
+						if (kProf) {
+							tw += c1 - c0;
+							ta += c2 - c1;
+							ti += prof_clock<kProf>() - c2;
+						}
 					}
 				}
+				if (kProf && tap_out) {
+					float* o = tap_out + ((size_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+					o[0] = (float)tw; o[1] = (float)ta; o[2] = (float)ti; o[3] = (float)(prof_clock<kProf>() - tstart);
+				}
 			}
-			if (kProf && tap_out) {
-				float* o = tap_out + ((size_t)blockIdx.x * kThreads + threadIdx.x) * 4;
-				o[0] = (float)tw; o[1] = (float)ta; o[2] = (float)ti; o[3] = (float)(prof_clock<kProf>() - tstart);
-			}
-		} else if (lane == 1 && warp == kWorkWarps) {
+		} else if (lane == 0) {
+			// TMA producer: one 24 KB unit per (kd, kh) pair = three consecutive 8 KB tiles of the stream (kw = 0, 1, 2);
+			// the stem's stream interleaves its two input-channel halves, so its units are gathered by three copies.
+			const uint32_t total = (uint32_t)(my_groups * kUnitsPerGroup);
 #pragma unroll 1
 			for (uint32_t issued = 0; issued < total; ++issued) {
-				const uint32_t s = issued % kStages;
+				const uint32_t s = issued % kStages, u = issued % kUnitsPerGroup;
 				mbar_wait(bar_w_empty(bars, s), ((issued / kStages) & 1u) ^ 1u);
 				mbar_arrive_expect_tx(bar_w_full(bars, s), kUnitBytes);
-				tma_load_1d(ring + s * kUnitBytes, w.units + (size_t)(issued % kDecUnitsTotal) * kUnitBytes, kUnitBytes, bar_w_full(bars, s));
+				const uint32_t dst = ring + s * kUnitBytes;
+				if (u < 18) {
+					const uint32_t pair = u >> 1, half = u & 1u;
+#pragma unroll
+					for (uint32_t kw = 0; kw < 3; ++kw)
+						tma_load_1d(dst + kw * kSrcUnitBytes, w.units + (size_t)((pair * 3 + kw) * 2 + half) * kSrcUnitBytes, kSrcUnitBytes,
+						            bar_w_full(bars, s));
+				} else {
+					const uint32_t src = u >= 36 ? (uint32_t)kDecUnitsTotal + (u - 36) * 3 : 54 + (u - 18) * 3;
+					tma_load_1d(dst, w.units + (size_t)src * kSrcUnitBytes, kUnitBytes, bar_w_full(bars, s));
+				}
 			}
 		}
 		__syncwarp();
 	} else {
 		// ===================== worker warps: A staging + epilogues =====================
 		Worker wk;
-		wk.tile = warp >> 2;
+		wk.tile = warp >> 3;
+		wk.chalf = (warp >> 2) & 1;
 		wk.quad = warp & 3;
 		wk.lane = lane;
 		wk.row = wk.quad * 32 + lane;
@@ -353,17 +426,19 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 		wk.w = wk.pos & 3;
 		wk.bars = bars;
 		wk.tmem_lane = tmem + ((uint32_t)(wk.quad * 32) << 16);
+		wk.zero_row = s_base + kOffZero;
 		uint8_t* region = smem + kOffLeaf + wk.leaf_slot * kLeafBytes;
 		const uint32_t a_base = s_base + kOffLeaf + wk.leaf_slot * kLeafBytes;  // Q [64][128] for the stem, then A [64][64]
-		const uint32_t x_base = a_base + 8192;                                   // residual x [64][64] bf16; later the up_conv pass output
+		const uint32_t x_base = a_base + 8192;                                   // residual x [64][64] bf16; later the pixel-shuffled planes
 		float* scratch = reinterpret_cast<float*>(smem + kOffScratch) + wk.leaf_slot * kScratchFloats;
-		float* exch = scratch;            // [2][32]
-		float* s_mean = scratch + 64;     // [64] channel means, then [64] channel scales
-		float* s_hid = scratch + 128;     // [16]
-		uint32_t* s_idx = reinterpret_cast<uint32_t*>(scratch + 160);  // 16 words
-		const float* s_finw = reinterpret_cast<const float*>(smem + kOffFinW);
-		const int tl = wk.wil * 32 + lane;  // thread index within the leaf, 0..63 (== pos)
-		long long ep[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // kProf only: cycles per epilogue section of this thread
+		float* exch = scratch + kScrExch;
+		float* s_part = scratch + kScrPart;
+		float* s_scale = scratch + kScrScale;
+		float* s_hid = scratch + kScrHid;
+		uint32_t* s_idx = reinterpret_cast<uint32_t*>(scratch + kScrIdx);
+		const int tl = wk.chalf * 64 + wk.pos;  // thread index within the leaf, 0..127
+		const int c0 = wk.chalf * 32;           // first of this thread's 32 channels
+		long long ep[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // kProf only: cycles per section of this thread
 		long long ep0 = prof_clock<kProf>();
 		auto lap = [&](int slot) {
 			if (kProf) {
@@ -379,241 +454,179 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 			const bool leaf_ok = leaf < n_leaves;
 
 			lap(7);
-			// ---- gather: Q[pos][0..127] = codebook_bf16[idx[pos]] (64 threads per leaf; spare slots decode code 0) ----
+			// ---- gather: Q[pos][0..127] = codebook_bf16[idx[pos]] (spare slots decode code 0) ----
 			if (tl < 16) s_idx[tl] = leaf_ok ? __ldcs(reinterpret_cast<const uint32_t*>(indices + leaf * 64) + tl) : 0u;
-			named_bar_sync(1 + wk.leaf_slot, 64);
+			leaf_bar(wk);  // also: every thread of the leaf is done with the previous group's planes
 			{
 				const uint8_t* idx8 = reinterpret_cast<const uint8_t*>(s_idx);
 #pragma unroll 4
-				for (int i = tl; i < 64 * 16; i += 64) {
+				for (int i = tl; i < 64 * 16; i += 128) {
 					const int pos = i >> 4, c = i & 15;
 					const uint4 v = __ldg(reinterpret_cast<const uint4*>(w.emb_bf16 + (size_t)idx8[pos] * 128) + c);
 					const uint32_t pc = (c & 8) | ((c & 7) ^ (pos & 7));
 					*reinterpret_cast<uint4*>(region + pos * 256 + pc * 16) = v;
 				}
 			}
-			named_bar_sync(1 + wk.leaf_slot, 64);
-
-			float mean[8], rstd[8];
+			leaf_bar(wk);
 			lap(0);
+
+			float v[32];
+			float mean[4], rstd[4];
 			// ---- stem.0 (128->64) ; stem.1 GroupNorm + ReLU -> x ; gn1 + ReLU -> conv1 input ----
 			stage_conv<2, kProf>(wk, a_base);
 			wait_accumulator<kProf>(wk);  // all stem MMAs done => every read of Q is done too
 			lap(6);
-			gn_stats_from_tmem(wk, w.stem_b, exch, mean, rstd);
-			{
-				float st[16];
+			load_conv32(wk, v);
 #pragma unroll
-				for (int i = 0; i < 16; ++i) st[i] = 0.f;
+			for (int j = 0; j < 32; ++j) v[j] += s_par[par::stem_b + c0 + j];
+			gn_stats(v, wk, exch, mean, rstd);
 #pragma unroll
-				for (int half = 0; half < 2; ++half) {
-					float v[32];
-					tmem_ld32(wk.tmem_lane + kColD + wk.tile * 64 + half * 32, v);
+			for (int j = 0; j < 32; ++j)
+				v[j] = fmaxf((v[j] - mean[j >> 3]) * rstd[j >> 3] * s_par[par::stem_gn_w + c0 + j] + s_par[par::stem_gn_b + c0 + j], 0.f);
+			if (tap_stage == 0 && leaf_ok) {
 #pragma unroll
-					for (int j = 0; j < 32; ++j) {
-						const int c = half * 32 + j, gi = c >> 3;
-						const float x = fmaxf(((v[j] + __ldg(w.stem_b + c)) - mean[gi]) * rstd[gi] * __ldg(w.stem_gn_w + c) + __ldg(w.stem_gn_b + c), 0.f);
-						v[j] = x;
-						st[gi] += x;
-						st[8 + gi] = fmaf(x, x, st[8 + gi]);
-					}
-					if (tap_stage == 0 && leaf_ok) {
-#pragma unroll
-						for (int j = 0; j < 32; ++j) tap_out[leaf * 4096 + (half * 32 + j) * 64 + wk.pos] = v[j];
-					}
-					store_row_half(x_base, wk.pos, half, v);  // residual x (thread-private row)
-				}
-				leaf_allreduce<16>(st, wk, exch);
-#pragma unroll
-				for (int gi = 0; gi < 8; ++gi) {
-					mean[gi] = st[gi] * (1.f / 512.f);
-					rstd[gi] = 1.f / sqrtf(fmaxf(st[8 + gi] * (1.f / 512.f) - mean[gi] * mean[gi], 0.f) + kGnEps);
-				}
-#pragma unroll
-				for (int half = 0; half < 2; ++half) {
-					float v[32];
-					load_row_half(x_base, wk.pos, half, v);
-#pragma unroll
-					for (int j = 0; j < 32; ++j) {
-						const int c = half * 32 + j, gi = c >> 3;
-						v[j] = fmaxf((v[j] - mean[gi]) * rstd[gi] * __ldg(w.res.gn1_w + c) + __ldg(w.res.gn1_b + c), 0.f);
-					}
-					store_row_half(a_base, wk.pos, half, v);
-				}
+				for (int j = 0; j < 32; ++j) tap_out[leaf * 4096 + (c0 + j) * 64 + wk.pos] = v[j];
 			}
-			tc_fence_before();
-			named_bar_sync(1 + wk.leaf_slot, 64);  // both warps' rows of the conv input are in place
-
+			store_row_half(x_base, wk, v);  // residual x (thread-private half row)
+			gn_stats(v, wk, exch, mean, rstd);
+#pragma unroll
+			for (int j = 0; j < 32; ++j)
+				v[j] = fmaxf((v[j] - mean[j >> 3]) * rstd[j >> 3] * s_par[par::gn1_w + c0 + j] + s_par[par::gn1_b + c0 + j], 0.f);
+			store_row_half(a_base, wk, v);
+			half_bar(wk);  // the rows of this channel half are in place (staging reads its own half only)
 			lap(1);
+
 			// ---- res conv1 ; gn2 + ReLU -> conv2 input ----
 			stage_conv<1, kProf>(wk, a_base);
 			wait_accumulator<kProf>(wk);
 			lap(6);
-			gn_stats_from_tmem(wk, w.res.c1_b, exch, mean, rstd);
+			load_conv32(wk, v);
 #pragma unroll
-			for (int half = 0; half < 2; ++half) {
-				float v[32];
-				tmem_ld32(wk.tmem_lane + kColD + wk.tile * 64 + half * 32, v);
+			for (int j = 0; j < 32; ++j) v[j] += s_par[par::c1_b + c0 + j];
+			gn_stats(v, wk, exch, mean, rstd);
 #pragma unroll
-				for (int j = 0; j < 32; ++j) {
-					const int c = half * 32 + j, gi = c >> 3;
-					v[j] = fmaxf(((v[j] + __ldg(w.res.c1_b + c)) - mean[gi]) * rstd[gi] * __ldg(w.res.gn2_w + c) + __ldg(w.res.gn2_b + c), 0.f);
-				}
-				store_row_half(a_base, wk.pos, half, v);
-			}
-			tc_fence_before();
-			named_bar_sync(1 + wk.leaf_slot, 64);
-
+			for (int j = 0; j < 32; ++j)
+				v[j] = fmaxf((v[j] - mean[j >> 3]) * rstd[j >> 3] * s_par[par::gn2_w + c0 + j] + s_par[par::gn2_b + c0 + j], 0.f);
+			store_row_half(a_base, wk, v);
+			half_bar(wk);
 			lap(2);
+
 			// ---- res conv2 ; x + 0.1 * (.) ; ChannelAttention(64) -> up_conv input ----
 			stage_conv<1, kProf>(wk, a_base);
 			wait_accumulator<kProf>(wk);
 			lap(6);
-			{
-				// x' = x + 0.1 (acc + b), written back into this thread's x row
+			load_conv32(wk, v);
 #pragma unroll
-				for (int half = 0; half < 2; ++half) {
-					float v[32], xr[32];
-					tmem_ld32(wk.tmem_lane + kColD + wk.tile * 64 + half * 32, v);
-					load_row_half(x_base, wk.pos, half, xr);
+			for (int q = 0; q < 4; ++q) {
+				float xr[8];
+				load_row_chunk(x_base, wk, q, xr);
 #pragma unroll
-					for (int j = 0; j < 32; ++j) v[j] = xr[j] + kResScale * (v[j] + __ldg(w.res.c2_b + half * 32 + j));
-					if (tap_stage == 1 && leaf_ok) {
-#pragma unroll
-						for (int j = 0; j < 32; ++j) tap_out[leaf * 4096 + (half * 32 + j) * 64 + wk.pos] = v[j];
-					}
-					store_row_half(x_base, wk.pos, half, v);
-				}
-				named_bar_sync(1 + wk.leaf_slot, 64);
-				// channel means: thread tl sums column tl of the leaf's 64 rows
-				{
-					float s = 0.f;
-					const uint32_t cchunk = (uint32_t)tl >> 3, cin = ((uint32_t)tl & 7u) * 2;
-#pragma unroll 8
-					for (int p = 0; p < 64; ++p) {
-						uint16_t hv;
-						asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(x_base + (uint32_t)p * 128 + ((cchunk ^ ((uint32_t)p & 7u)) << 4) + cin));
-						s += __uint_as_float((uint32_t)hv << 16);
-					}
-					s_mean[tl] = s * (1.f / 64.f);
-				}
-				named_bar_sync(1 + wk.leaf_slot, 64);
-				if (tl < 16) {
-					float s = 0.f;
-#pragma unroll 8
-					for (int c = 0; c < 64; ++c) s = fmaf(__ldg(w.fc0 + tl * 64 + c), s_mean[c], s);
-					s_hid[tl] = fmaxf(s, 0.f);
-				}
-				named_bar_sync(1 + wk.leaf_slot, 64);
-				{
-					float s = 0.f;
-#pragma unroll
-					for (int j = 0; j < 16; ++j) s = fmaf(__ldg(w.fc2 + tl * 16 + j), s_hid[j], s);
-					named_bar_sync(1 + wk.leaf_slot, 64);  // everyone has read s_mean before it becomes the scale table
-					s_mean[tl] = sigmoid_f(s);
-				}
-				named_bar_sync(1 + wk.leaf_slot, 64);
-#pragma unroll
-				for (int half = 0; half < 2; ++half) {
-					float v[32];
-					load_row_half(x_base, wk.pos, half, v);
-#pragma unroll
-					for (int j = 0; j < 32; ++j) v[j] *= s_mean[half * 32 + j];
-					if (tap_stage == 2 && leaf_ok) {
-#pragma unroll
-						for (int j = 0; j < 32; ++j) tap_out[leaf * 4096 + (half * 32 + j) * 64 + wk.pos] = v[j];
-					}
-					store_row_half(a_base, wk.pos, half, v);
-				}
+				for (int i = 0; i < 8; ++i) v[8 * q + i] = xr[i] + kResScale * (v[8 * q + i] + s_par[par::c2_b + c0 + 8 * q + i]);
 			}
-			tc_fence_before();
-			named_bar_sync(1 + wk.leaf_slot, 64);
-
-			// ---- up_conv in four 64-channel passes ; PixelShuffle3D on the store ; final conv accumulated on FFMA ----
-			// thread tl owns output row R = tl of the 8^3 leaf (D = R>>3, H = R&7): 8 voxels along W.
-			float out[8];
+			if (tap_stage == 1 && leaf_ok) {
 #pragma unroll
-			for (int j = 0; j < 8; ++j) out[j] = 0.f;
-			lap(3);
-#pragma unroll 1
-			for (int np = 0; np < 4; ++np) {
-				stage_conv<1, kProf>(wk, a_base);
-				wait_accumulator<kProf>(wk);
-				lap(6);
-				// channel c = np*64 + cc = oc*8 + rd*4 + rh*2 + rw  ->  oc_local = cc>>3, (rd, rh, rw) = bits of cc&7
-				// P[oc_local][(2d+rd)][(2h+rh)][(2w+rw)] bf16 in the x region (8 KB per leaf)
+				for (int j = 0; j < 32; ++j) tap_out[leaf * 4096 + (c0 + j) * 64 + wk.pos] = v[j];
+			}
+			store_row_half(x_base, wk, v);  // x' (thread-private), re-read below once the channel scales are known
+			{
+				const float cs = column_sums(v, lane);  // channel c0 + lane over this warp's 32 rows
+				s_part[wk.wil * 64 + c0 + lane] = cs;
+			}
+			leaf_bar(wk);
+			{
+				// hidden = relu(fc0 [16][64] . mean): 8 threads per hidden unit, 8 channels each
+				const int unit = tl >> 3, part = tl & 7;
+				float s = 0.f;
 #pragma unroll
-				for (int half = 0; half < 2; ++half) {
-					float v[32];
-					tmem_ld32(wk.tmem_lane + kColD + wk.tile * 64 + half * 32, v);
-#pragma unroll
-					for (int j = 0; j < 32; j += 2) {
-						const int cc = half * 32 + j, ocl = cc >> 3, rd = (cc >> 2) & 1, rh = (cc >> 1) & 1;
-						const float b0 = __ldg(w.up_b + np * 64 + cc), b1 = __ldg(w.up_b + np * 64 + cc + 1);
-						const uint32_t p0 = ocl * 512 + ((2 * wk.d + rd) * 8 + 2 * wk.h + rh) * 8 + 2 * wk.w;
-						asm volatile("st.shared.b32 [%0], %1;" ::"r"(x_base + p0 * 2), "r"(pack_bf16(v[j] + b0, v[j + 1] + b1)));
-					}
+				for (int i = 0; i < 8; ++i) {
+					const int c = i * 8 + part;
+					s = fmaf(s_par[par::fc0 + unit * par::fc0_pitch + c], (s_part[c] + s_part[64 + c]) * (1.f / 64.f), s);
 				}
-				tc_fence_before();
-				named_bar_sync(1 + wk.leaf_slot, 64);
-				lap(4);
-				{
-					const int D = tl >> 3, H = tl & 7;
-#pragma unroll 1
-					for (int oc = 0; oc < 8; ++oc) {
-						const float* wf = s_finw + (np * 8 + oc) * 27;
+				s += __shfl_xor_sync(0xffffffffu, s, 1);
+				s += __shfl_xor_sync(0xffffffffu, s, 2);
+				s += __shfl_xor_sync(0xffffffffu, s, 4);
+				if (part == 0) s_hid[unit] = fmaxf(s, 0.f);
+			}
+			leaf_bar(wk);
+			if (tl < 64) {
+				float s = 0.f;
 #pragma unroll
-						for (int kd = 0; kd < 3; ++kd) {
-							const int Dp = D + kd - 1;
-							if ((unsigned)Dp >= 8u) continue;
+				for (int j = 0; j < 16; ++j) s = fmaf(s_par[par::fc2 + tl * par::fc2_pitch + j], s_hid[j], s);
+				s_scale[tl] = sigmoid_f(s);
+			}
+			leaf_bar(wk);
 #pragma unroll
-							for (int kh = 0; kh < 3; ++kh) {
-								const int Hp = H + kh - 1;
-								if ((unsigned)Hp >= 8u) continue;
-								uint4 raw;
-								asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-								             : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
-								             : "r"(x_base + (oc * 512 + (Dp * 8 + Hp) * 8) * 2));
-								float xr[10];
-								xr[0] = 0.f;
-								xr[9] = 0.f;
-								float2 f;
-								f = unpack_bf16(raw.x); xr[1] = f.x; xr[2] = f.y;
-								f = unpack_bf16(raw.y); xr[3] = f.x; xr[4] = f.y;
-								f = unpack_bf16(raw.z); xr[5] = f.x; xr[6] = f.y;
-								f = unpack_bf16(raw.w); xr[7] = f.x; xr[8] = f.y;
-								const float wk0 = wf[(kd * 3 + kh) * 3], wk1 = wf[(kd * 3 + kh) * 3 + 1], wk2 = wf[(kd * 3 + kh) * 3 + 2];
+			for (int q = 0; q < 4; ++q) {
+				float xr[8];
+				load_row_chunk(x_base, wk, q, xr);
 #pragma unroll
-								for (int j = 0; j < 8; ++j) {
-									float o = out[j];
-									if (j > 0) o = fmaf(xr[j], wk0, o);
-									o = fmaf(xr[j + 1], wk1, o);
-									if (j < 7) o = fmaf(xr[j + 2], wk2, o);
-									out[j] = o;
-								}
-							}
+				for (int i = 0; i < 8; ++i) v[8 * q + i] = xr[i] * s_scale[c0 + 8 * q + i];
+			}
+			if (tap_stage == 2 && leaf_ok) {
+#pragma unroll
+				for (int j = 0; j < 32; ++j) tap_out[leaf * 4096 + (c0 + j) * 64 + wk.pos] = v[j];
+			}
+			store_row_half(a_base, wk, v);
+			half_bar(wk);
+			lap(3);
+
+			// ---- folded tail: G = conv(a; Wg) + bg, then out[2p + r] = sigmoid(fin_b + sum over the in-grid cells
+			// p + e(r, eps) of G[p + e][r*8 + eps]) ----
+			stage_conv<1, kProf>(wk, a_base);
+			wait_accumulator<kProf>(wk);  // all reads of the conv input are done: the whole leaf region is free
+			lap(6);
+			load_conv32(wk, v);
+			// The accumulator hand-over already orders every staging read of this leaf's rows before the stores below (a
+			// unit's loads feed the tcgen05.st that precedes its a_full arrival); the barrier states the same thing in
+			// terms compute-sanitizer's racecheck can follow, and costs nothing: all 128 threads just left the same wait.
+			leaf_bar(wk);
+			// G as fp32 [64 ch][64 pos] over the leaf region, channel c at word c*64 + ((c >> 4) & 3): a warp's store of one
+			// channel is 32 consecutive words, and in the gather below the lanes of a warp — (rd, rh) x (pd & 1, ph) — land in
+			// 32 different banks: (pd, ph) walk the multiples of 4 words, the skew separates the four (rd, rh) classes.
+			// (The position-major layout this replaces put the 32 lanes of every gather load into 2 banks.)
+#pragma unroll
+			for (int j = 0; j < 32; ++j) {
+				const int c = c0 + j;
+				const uint32_t a = a_base + (uint32_t)(c * 64 + ((c >> 4) & 3) + wk.pos) * 4;
+				asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v[j] + s_par[par::fold_b + c]) : "memory");
+			}
+			leaf_bar(wk);
+			lap(4);
+			// this thread: output row R = pos (D = R>>3, H = R&7), voxels W = chalf*4 .. +3
+			{
+				const int D = wk.pos >> 3, H = wk.pos & 7;
+				const int rd = D & 1, rh = H & 1, pd = D >> 1, ph = H >> 1;
+				const float fb = s_par[par::fin_b];
+				float o[4];
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const int rw = j & 1, pw = wk.chalf * 2 + (j >> 1);
+					const int r = rd * 4 + rh * 2 + rw;
+					float sum = fb;
+#pragma unroll
+					for (int eps = 0; eps < 8; ++eps) {
+						const int ed = (eps >> 2) & 1, eh = (eps >> 1) & 1, ew = eps & 1;
+						const int qd = pd + (ed ? (rd ? 1 : -1) : 0), qh = ph + (eh ? (rh ? 1 : -1) : 0), qw = pw + (ew ? (rw ? 1 : -1) : 0);
+						const bool ok = (unsigned)qd < 4u && (unsigned)qh < 4u && (unsigned)qw < 4u;
+						const int c = r * 8 + eps;
+						const uint32_t a = a_base + (uint32_t)(c * 64 + (r >> 1) + qd * 16 + qh * 4 + qw) * 4;  // (c >> 4) & 3 == r >> 1
+						if (ok) {
+							float g;
+							asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g) : "r"(a));
+							sum += g;
 						}
 					}
+					o[j] = sigmoid_f(sum);
 				}
-				named_bar_sync(1 + wk.leaf_slot, 64);  // all reads of this pass's P are done before the next pass overwrites it
-				lap(5);
+				if (leaf_ok) __stcs(reinterpret_cast<float4*>(voxels + leaf * 512 + wk.pos * 8 + wk.chalf * 4), make_float4(o[0], o[1], o[2], o[3]));
 			}
-
-			// ---- sigmoid + store: one 32-byte row segment per thread ----
-			if (leaf_ok) {
-				const float fb = __ldg(w.fin_b);
-				float4 o0, o1;
-				o0.x = sigmoid_f(out[0] + fb); o0.y = sigmoid_f(out[1] + fb); o0.z = sigmoid_f(out[2] + fb); o0.w = sigmoid_f(out[3] + fb);
-				o1.x = sigmoid_f(out[4] + fb); o1.y = sigmoid_f(out[5] + fb); o1.z = sigmoid_f(out[6] + fb); o1.w = sigmoid_f(out[7] + fb);
-				float4* dst = reinterpret_cast<float4*>(voxels + leaf * 512 + tl * 8);
-				__stcs(dst, o0);
-				__stcs(dst + 1, o1);
-			}
+			lap(5);
 		}
+		lap(7);
 		if (kProf && tap_out) {
 			float* o = tap_out + ((size_t)blockIdx.x * kThreads + threadIdx.x) * 4;
 			o[0] = (float)wk.t_wait; o[1] = (float)wk.t_stage; o[2] = (float)wk.t_acc; o[3] = 0.f;
-			if (threadIdx.x == 0) {  // epilogue sections of thread 0, behind the per-thread records
+			if (threadIdx.x == 0) {  // sections of thread 0, behind the per-thread records
 				float* e = tap_out + (size_t)gridDim.x * kThreads * 4 + (size_t)blockIdx.x * 8;
 #pragma unroll
 				for (int i = 0; i < 8; ++i) e[i] = (float)ep[i];
@@ -631,8 +644,8 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 
 cudaError_t configure_decode_tc() {
 	cudaError_t e = cudaFuncSetAttribute(decode_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-	if (e != cudaSuccess) return e;
-	return cudaFuncSetAttribute(decode_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+	return e;
 }
 
 cudaError_t launch_decode_tc(const DecoderMmaWeights& w, const uint8_t* dev_indices, int64_t n_leaves, float* dev_voxels,
@@ -640,7 +653,7 @@ cudaError_t launch_decode_tc(const DecoderMmaWeights& w, const uint8_t* dev_indi
 	if (n_leaves <= 0) return cudaSuccess;
 	const int64_t groups = (n_leaves + kLeavesPerCta - 1) / kLeavesPerCta;
 	const int grid = (int)(groups < (int64_t)num_sms ? groups : (int64_t)num_sms);
-	if (tap_stage == 100)  // timing instrumentation: tap_out receives 4 floats per thread (see tools/tc_pipeline_prof.py)
+	if (tap_stage == 100)  // timing instrumentation: 4 floats per thread + 8 per CTA (tools/tc_pipeline_prof.py)
 		decode_tc_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, -1, tap_out);
 	else
 		decode_tc_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, tap_stage, tap_out);

@@ -1,4 +1,4 @@
-// Weight tables and launcher of the tensor-core (warp-level MMA, bf16) decoder.
+// Weight tables and launcher of the tensor-core decoder (decode_tc.cu: tcgen05.mma, bf16 operands, fp32 accumulation).
 #pragma once
 
 #include <cuda_bf16.h>
@@ -17,8 +17,8 @@ namespace vqvdb {
 //   stem.0    27 taps x 2 input-channel halves      54 units
 //   res conv1 27 taps                                27
 //   res conv2 27 taps                                27
-//   up_conv   4 output passes (64 ch) x 27 taps     108
-//   folded tail 27 taps (decode_tc2.cu, see below)   27
+//   up_conv   4 output passes (64 ch) x 27 taps     108   (the reference factorisation; kept in the stream, not consumed)
+//   folded tail 27 taps (see below)                  27
 constexpr int kDecUnitsTotal = 216;
 constexpr int kDecUnitsWithFold = kDecUnitsTotal + 27;
 // The decoder's tail up_conv -> PixelShuffle3D(2) -> final has no nonlinearity in it (python/VQVAE_v2.py:272-275), so it
@@ -50,25 +50,13 @@ std::vector<uint16_t> build_codebook_bf16(const WeightPack& pack);
 // tensor-core VQ shortlist pass: same tile format as the decoder's units.
 std::vector<uint8_t> build_codebook_units(const WeightPack& pack);
 
-cudaError_t configure_decode_mma();
+// kw taps concatenated along N (one A unit per (kd, kh) pair, N = 192), eight worker warps per 128-row tile, the tail run
+// as the folded conv + gather described above (45 units per group of 4 leaves).
+cudaError_t configure_decode_tc();
 // tap_stage >= 0 additionally writes the activation after stage {0: stem+GN+ReLU, 1: residual block,
 // 2: attention} as fp32 [leaf][64 ch][64 pos] to tap_out (bring-up aid; -1 in production).
-cudaError_t launch_decode_mma(const DecoderMmaWeights& w, const uint8_t* dev_indices, int64_t n_leaves,
-                              float* dev_voxels, int num_sms, cudaStream_t stream, int tap_stage = -1,
-                              float* tap_out = nullptr);
-
-// tcgen05 / TMEM version of the same decoder (decode_tc.cu); same weights, same arguments.
-cudaError_t configure_decode_tc();
 cudaError_t launch_decode_tc(const DecoderMmaWeights& w, const uint8_t* dev_indices, int64_t n_leaves,
                              float* dev_voxels, int num_sms, cudaStream_t stream, int tap_stage = -1,
                              float* tap_out = nullptr);
-
-// Second-generation tcgen05 decoder (decode_tc2.cu): kw taps concatenated along N (one A unit per (kd, kh) pair, N = 192),
-// eight worker warps per 128-row tile; same weights, same arguments.
-cudaError_t configure_decode_tc2();
-// fold = true runs the tail as the folded conv + gather described above (45 units per group instead of 72).
-cudaError_t launch_decode_tc2(const DecoderMmaWeights& w, const uint8_t* dev_indices, int64_t n_leaves,
-                              float* dev_voxels, int num_sms, cudaStream_t stream, bool fold, int tap_stage = -1,
-                              float* tap_out = nullptr);
 
 }  // namespace vqvdb

@@ -1,4 +1,4 @@
-// Host-side preparation of the tensor-core decoder's weight stream (see decode_mma.cuh).
+// Host-side preparation of the tensor-core decoder's weight stream (see decode_tc.cuh).
 #include <cstring>
 #include <stdexcept>
 
@@ -6,7 +6,7 @@
 
 namespace vqvdb {
 
-static constexpr int kDecUnitsWithFold = 216 + 27;  // == decode_mma.cuh (checked where the stream is uploaded)
+static constexpr int kDecUnitsWithFold = 216 + 27;  // == decode_tc.cuh (checked where the stream is uploaded)
 
 static uint16_t f32_to_bf16_rn(float f) {
 	uint32_t u;
@@ -28,7 +28,7 @@ static void fill_unit(uint8_t* unit, const float* w, int cout_total, int cin_tot
 		}
 }
 
-// up_conv -> PixelShuffle3D(2) -> final, folded (decode_mma.cuh).  Along one axis an output voxel V = 2p + r reads the
+// up_conv -> PixelShuffle3D(2) -> final, folded (decode_tc.cuh).  Along one axis an output voxel V = 2p + r reads the
 // shuffled volume at U = V + s2, s2 in {-1, 0, 1}: U lies in cell p + e, e = floor((r + s2) / 2), at sub-position
 // rU = (r + s2) mod 2.  Terms are grouped by (r, eps) with eps = (e != 0) per axis.
 void build_decoder_fold(const WeightPack& p, std::vector<float>& wg /*[64][64][27]*/, std::vector<float>& bg /*[64]*/);

@@ -16,6 +16,8 @@ HOST_EXPORTS = [
     "vqvdb_host_write_file", "vqvdb_host_reader_open", "vqvdb_host_reader_close", "vqvdb_host_reader_num_grids",
     "vqvdb_host_reader_num_embeddings", "vqvdb_host_reader_next_grid", "vqvdb_host_reader_next_batch",
     "vqvdb_host_compress", "vqvdb_host_decompress", "vqvdb_host_last_error",
+    "vqvdb_host_backend_create", "vqvdb_host_backend_destroy", "vqvdb_host_backend_encode", "vqvdb_host_backend_decode",
+    "vqvdb_host_backend_result", "vqvdb_host_backend_encode_into", "vqvdb_host_backend_decode_into",
 ]
 
 _lib = None
@@ -43,6 +45,15 @@ def load_host_library() -> C.CDLL:
                                           C.c_void_p, C.c_int64]
         L.vqvdb_host_decompress.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.c_void_p,
                                             C.c_void_p, C.c_int64, C.c_int]
+        L.vqvdb_host_backend_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.vqvdb_host_backend_destroy.argtypes = [C.c_void_p]
+        L.vqvdb_host_backend_destroy.restype = None
+        for fn in ("vqvdb_host_backend_encode", "vqvdb_host_backend_decode"):
+            getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
+        for fn in ("vqvdb_host_backend_encode_into", "vqvdb_host_backend_decode_into"):
+            getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_double)]
+        L.vqvdb_host_backend_result.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.vqvdb_host_backend_result.restype = C.c_void_p
         _lib = L
     return _lib
 
@@ -140,3 +151,54 @@ def decompress(in_path: str, batch_size: int = 0, device: int = 0, fp32_decode: 
     meta = read_file(in_path)
     return [LeafGrid(meta[g].name, og[g], vx[g].reshape(-1, 1, 8, 8, 8), meta[g].indices, meta[g].transform)
             for g in range(n.value)]
+
+
+class HostBackend:
+    """The C++ IVQVAECodec (B200Backend) driven through its virtual encode / decode, as the reference's orchestrator
+    drives its backend: TensorView over caller memory in, owning Tensor out (GPU required)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_host_library()
+        self.h = C.c_void_p()
+        if self.L.vqvdb_host_backend_create(device, C.byref(self.h)) != 0:
+            _err(self.L, "backend_create")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vqvdb_host_backend_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _result(self, dtype, shape):
+        nbytes = C.c_uint64()
+        p = self.L.vqvdb_host_backend_result(self.h, C.byref(nbytes))
+        buf = (C.c_char * nbytes.value).from_address(p)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)   # a view of the Tensor held by the handle
+
+    def encode(self, leaves: np.ndarray):
+        """-> (indices view [n,4,4,4] uint8, seconds of the virtual call)"""
+        n = leaves.shape[0]
+        sec = C.c_double()
+        if self.L.vqvdb_host_backend_encode(self.h, leaves.ctypes.data, n, C.byref(sec)) != 0:
+            _err(self.L, "backend_encode")
+        return self._result(np.uint8, (n, 4, 4, 4)), sec.value
+
+    def decode(self, indices: np.ndarray):
+        n = indices.shape[0]
+        sec = C.c_double()
+        if self.L.vqvdb_host_backend_decode(self.h, indices.ctypes.data, n, C.byref(sec)) != 0:
+            _err(self.L, "backend_decode")
+        return self._result(np.float32, (n, 1, 8, 8, 8)), sec.value
+
+    def encode_into(self, leaves: np.ndarray, indices_out: np.ndarray) -> float:
+        sec = C.c_double()
+        if self.L.vqvdb_host_backend_encode_into(self.h, leaves.ctypes.data, leaves.shape[0], indices_out.ctypes.data, C.byref(sec)) != 0:
+            _err(self.L, "backend_encode_into")
+        return sec.value
+
+    def decode_into(self, indices: np.ndarray, voxels_out: np.ndarray) -> float:
+        sec = C.c_double()
+        if self.L.vqvdb_host_backend_decode_into(self.h, indices.ctypes.data, indices.shape[0], voxels_out.ctypes.data, C.byref(sec)) != 0:
+            _err(self.L, "backend_decode_into")
+        return sec.value
