@@ -382,13 +382,13 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
-    json_fd = None
+    # NCCL prints its version banner on stdout when NCCL_DEBUG is set, and the C++ host layer logs like the reference's
+    # backends do (std::cout): park fd 1 on stderr for the run and print the one JSON line through the saved
+    # descriptor, so stdout carries that line only
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL prints its version banner on stdout when NCCL_DEBUG is set: park fd 1 on stderr for the run and print
-        # the one JSON line through the saved descriptor, so stdout carries that line only
-        sys.stdout.flush()
-        json_fd = os.dup(1)
-        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K = max(1, args.steps)
@@ -727,10 +727,7 @@ def main():
                                         "kind": "port", "sample": "%d vec3 smoke leaves, encode+decode (the reference ships no C++ vec3 path)" % args.ref_sample}
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "leaves/s", "cores": 0, "kind": "port", "sample": "failed: %s" % str(e)[:200]}
-        if json_fd is not None:
-            os.write(json_fd, (json.dumps(line) + "\n").encode())
-        else:
-            print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if peer is not None:
         peer.close()
     codec.close()

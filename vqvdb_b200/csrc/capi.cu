@@ -43,6 +43,11 @@ struct CudaError : std::runtime_error {
 
 constexpr int kSlots = 3;                   // pipeline depth of the host-pointer calls
 constexpr uint32_t kDefaultChunk = 16384;   // leaves per chunk: 32 MiB of voxels, 1 MiB of indices
+// Calls of at most this many leaves (the reference's SOPs hand over 64 at a time by default, 1024 / 8192 at most:
+// SOP_VQVDB_Encoder.cpp:36, SOP_VQVDB_Decoder.cpp:32) skip the copy engines: the kernel reads its input from, and
+// writes its result to, pinned HOST memory directly (mapped, over PCIe) — one launch and one synchronisation instead
+// of copy + launch + copy + event, which is most of a 64-leaf call's time.
+constexpr int64_t kZeroCopyLeaves = 2048;
 
 // Pageable caller memory (the reference's callers hand over std::vector storage: VQVAECodec.cpp:48,114) cannot be DMA'd
 // directly, so it is staged through the slots' pinned buffers.  One memcpy thread moves ~10 GB/s, a quarter of what the
@@ -510,6 +515,18 @@ bool is_pinned_host(const void* p) {
 	return a.type == cudaMemoryTypeHost;
 }
 
+// Device-side alias of pinned host memory (cudaMallocHost / cudaHostRegister'd / torch pin_memory), or null.
+template <class T>
+T* device_alias(T* host_ptr, size_t align) {
+	if (reinterpret_cast<uintptr_t>(host_ptr) & (align - 1)) return nullptr;
+	void* d = nullptr;
+	if (cudaHostGetDevicePointer(&d, const_cast<void*>(static_cast<const void*>(host_ptr)), 0) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return static_cast<T*>(d);
+}
+
 int fail(vqvdb_b200_codec* c, int code, const std::string& msg) {
 	if (c) c->last_error = msg;
 	else g_create_error = msg;
@@ -695,6 +712,23 @@ int vqvdb_b200_encode(vqvdb_b200_codec* c, const float* host_leaves, int64_t n, 
 		ensure_staging(*c);
 		const size_t leaf_elems = (size_t)c->channels * 512;
 		const bool in_direct = is_pinned_host(host_leaves), out_direct = is_pinned_host(host_indices);
+		if (!c->generic && n <= std::min<int64_t>(kZeroCopyLeaves, c->chunk)) {  // small call: no copy engines (see kZeroCopyLeaves)
+			Slot& s = c->slots[0];
+			const float* src = in_direct ? device_alias(host_leaves, 16) : nullptr;
+			if (!src) {
+				std::memcpy(s.h_vox, host_leaves, (size_t)n * leaf_elems * sizeof(float));
+				src = device_alias(static_cast<const float*>(s.h_vox), 16);
+			}
+			uint8_t* dst = out_direct ? device_alias(host_indices, 1) : nullptr;
+			const bool staged_out = dst == nullptr;
+			if (staged_out) dst = device_alias(s.h_idx, 1);
+			if (src && dst) {
+				launch_encode(*c, src, n, dst, s.stream, 0);
+				CUDA_TRY(cudaStreamSynchronize(s.stream));
+				if (staged_out) std::memcpy(host_indices, s.h_idx, (size_t)n * 64);
+				return VQVDB_B200_OK;
+			}
+		}
 		int64_t done = 0;
 		for (int i = 0; done < n; ++i) {
 			Slot& s = c->slots[i % kSlots];
@@ -731,6 +765,23 @@ int vqvdb_b200_decode(vqvdb_b200_codec* c, const uint8_t* host_indices, int64_t 
 		ensure_staging(*c);
 		const size_t leaf_elems = (size_t)c->channels * 512;
 		const bool in_direct = is_pinned_host(host_indices), out_direct = is_pinned_host(host_voxels);
+		if (!c->generic && n <= std::min<int64_t>(kZeroCopyLeaves, c->chunk)) {  // small call: no copy engines (see kZeroCopyLeaves)
+			Slot& s = c->slots[0];
+			const uint8_t* src = in_direct ? device_alias(host_indices, 4) : nullptr;
+			if (!src) {
+				std::memcpy(s.h_idx, host_indices, (size_t)n * 64);
+				src = device_alias(static_cast<const uint8_t*>(s.h_idx), 4);
+			}
+			float* dst = out_direct ? device_alias(host_voxels, 16) : nullptr;
+			const bool staged_out = dst == nullptr;
+			if (staged_out) dst = device_alias(s.h_vox, 16);
+			if (src && dst) {
+				launch_decode(*c, src, n, dst, s.stream, 0);
+				CUDA_TRY(cudaStreamSynchronize(s.stream));
+				if (staged_out) std::memcpy(host_voxels, s.h_vox, (size_t)n * leaf_elems * sizeof(float));
+				return VQVDB_B200_OK;
+			}
+		}
 		int64_t done = 0;
 		for (int i = 0; done < n; ++i) {
 			Slot& s = c->slots[i % kSlots];

@@ -290,13 +290,16 @@ __device__ __forceinline__ float column_sums(float (&v)[32], int lane) {
 template <bool kProf>
 __global__ void __launch_bounds__(kThreads, 1)
 decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices, int64_t n_leaves, float* __restrict__ voxels,
-                  int tap_stage, float* __restrict__ tap_out) {
+                 int active_tiles, int tap_stage, float* __restrict__ tap_out) {
 	extern __shared__ __align__(1024) uint8_t smem[];
 	const uint32_t s_base = smem_u32(smem);
 	const uint32_t ring = s_base + kOffRing;
 	const uint32_t bars = s_base + kOffBar;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int64_t n_groups = (n_leaves + kLeavesPerCta - 1) / kLeavesPerCta;
+	// active_tiles = 2: a group is 4 leaves (two 128-row tiles side by side).  Small calls (<= 2 leaves per SM) run with
+	// ONE tile per CTA — twice the CTAs, each with half the work and the tensor pipe to itself; tile 1's warps idle.
+	const int leaves_per_group = 2 * active_tiles;
+	const int64_t n_groups = (n_leaves + leaves_per_group - 1) / leaves_per_group;
 	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmemSlot);
 	float* s_par = reinterpret_cast<float*>(smem + kOffPar);
 
@@ -322,7 +325,7 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 	if (threadIdx.x == 0) {
 		for (uint32_t s = 0; s < kStages; ++s) {
 			mbar_init(bar_w_full(bars, s), 1);
-			mbar_init(bar_w_empty(bars, s), kTiles);  // one tcgen05.commit per tile issuer
+			mbar_init(bar_w_empty(bars, s), active_tiles);  // one tcgen05.commit per active tile issuer
 		}
 		for (uint32_t t = 0; t < kTiles; ++t) {
 			for (uint32_t b = 0; b < 2; ++b) {
@@ -346,7 +349,7 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 	if (warp >= kWorkWarps) {
 		// ===================== control warps =====================
 		if (warp < kWorkWarps + kTiles) {
-			if (lane == 0) {
+			if (lane == 0 && warp - kWorkWarps < active_tiles) {
 				// MMA issuer of tile t.  The issuers are independent, so the tiles drift apart and one tile's epilogue
 				// overlaps the other tile's MMAs.
 				const uint32_t t = warp - kWorkWarps;
@@ -448,9 +451,9 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 			}
 		};
 
-		for (int64_t g = 0; g < my_groups; ++g) {
+		for (int64_t g = 0; g < (wk.tile < active_tiles ? my_groups : 0); ++g) {
 			const int64_t grp = blockIdx.x + g * gridDim.x;
-			const int64_t leaf = grp * kLeavesPerCta + wk.leaf_slot;
+			const int64_t leaf = grp * leaves_per_group + wk.leaf_slot;
 			const bool leaf_ok = leaf < n_leaves;
 
 			lap(7);
@@ -651,12 +654,13 @@ cudaError_t configure_decode_tc() {
 cudaError_t launch_decode_tc(const DecoderMmaWeights& w, const uint8_t* dev_indices, int64_t n_leaves, float* dev_voxels,
                              int num_sms, cudaStream_t stream, int tap_stage, float* tap_out) {
 	if (n_leaves <= 0) return cudaSuccess;
-	const int64_t groups = (n_leaves + kLeavesPerCta - 1) / kLeavesPerCta;
+	const int tiles = n_leaves <= 2 * (int64_t)num_sms ? 1 : kTiles;
+	const int64_t groups = (n_leaves + 2 * tiles - 1) / (2 * tiles);
 	const int grid = (int)(groups < (int64_t)num_sms ? groups : (int64_t)num_sms);
 	if (tap_stage == 100)  // timing instrumentation: 4 floats per thread + 8 per CTA (tools/tc_pipeline_prof.py)
-		decode_tc_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, -1, tap_out);
+		decode_tc_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, tiles, -1, tap_out);
 	else
-		decode_tc_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, tap_stage, tap_out);
+		decode_tc_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(w, dev_indices, n_leaves, dev_voxels, tiles, tap_stage, tap_out);
 	return cudaGetLastError();
 }
 
