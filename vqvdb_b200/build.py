@@ -17,16 +17,20 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(REPO, "build", "obj")
-LIB = os.path.join(HERE, "libvqvdb_b200.so")
+# Tuning builds: VQVDB_B200_DEFINES="A=1,B=2" adds -DA=1 -DB=2 to every compile, VQVDB_B200_VARIANT=name writes
+# build/variants/libvqvdb_b200_name.so instead of the product library (load it with VQVDB_B200_LIB=<path>; tools/ab_encode.py).
+VARIANT = os.environ.get("VQVDB_B200_VARIANT", "")
+DEFINES = ["-D" + d for d in os.environ.get("VQVDB_B200_DEFINES", "").split(",") if d]
+OBJ = os.path.join(REPO, "build", "obj" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(REPO, "build", "variants", "libvqvdb_b200_%s.so" % VARIANT) if VARIANT else os.path.join(HERE, "libvqvdb_b200.so")
 PACK = os.path.join(HERE, "weights", "vqvae_float.vqw")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr", "-Xptxas", "-v",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unknown-pragmas"] + ARCH
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall"]
-if os.environ.get("VQVDB_ENC_LEAVES"):  # tuning knob: leaves per encoder CTA (2 or 3); the source default is used otherwise
-    NVCC_FLAGS.append("-DVQVDB_ENC_LEAVES=" + os.environ["VQVDB_ENC_LEAVES"])
+NVCC_FLAGS += DEFINES
+CXX_FLAGS += DEFINES
 
 
 def _nvcc() -> str:
@@ -64,6 +68,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
     nvcc = _nvcc()
     cu, cpp, asm = _sources()
     log: list[str] = []

@@ -16,7 +16,7 @@ from typing import Optional, Sequence, Union
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvqvdb_b200.so")
+LIB_PATH = os.environ.get("VQVDB_B200_LIB") or os.path.join(HERE, "libvqvdb_b200.so")   # the override is for tuning builds (vqvdb_b200/build.py)
 
 EXPORTS = [  # every symbol include/vqvdb_b200.h declares
     "vqvdb_b200_create", "vqvdb_b200_destroy", "vqvdb_b200_latent_shape", "vqvdb_b200_in_channels",

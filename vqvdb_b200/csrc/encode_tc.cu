@@ -99,7 +99,8 @@ constexpr uint32_t kOffCb = kOffAtt + (128 + 8 + 32) * 4;       // emb_sq [256],
 constexpr uint32_t kOffPar = kOffCb + 3088;                     // fold_norm has a 257th entry: its maximum                     // per-channel parameter vectors (ParOff), 1008 floats
 constexpr uint32_t kOffXq = kOffPar + 1008 * 4;                 // `down` epilogue: lane-0 values handed to the previous quadrant [4][4][8]
 constexpr uint32_t kOffBar = kOffXq + 512;                      // mbarriers
-constexpr uint32_t kNumBars = 2 * kStages + 3;
+constexpr int kConvGroups = kEncTcConvGroups;                   // tile groups of an 8^3 conv, each with its own completion barrier
+constexpr uint32_t kNumBars = 2 * kStages + 3 + kConvGroups;
 constexpr uint32_t kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemSlot + 16;
 static_assert(kOffXh + kXhBytes <= kOffY + kYBytes && kOffXh % 16 == 0, "the VQ overlays fit inside the Y region");
@@ -109,10 +110,12 @@ static_assert(kOffBar % 8 == 0 && kOffA8 % 1024 == 0 && kOffY % 1024 == 0 && kOf
 __device__ __forceinline__ uint32_t bar_w_full(uint32_t bars, uint32_t s) { return bars + s * 8; }
 __device__ __forceinline__ uint32_t bar_w_empty(uint32_t bars, uint32_t s) { return bars + (kStages + s) * 8; }
 __device__ __forceinline__ uint32_t bar_a_ready(uint32_t bars) { return bars + 2 * kStages * 8; }
-// Two accumulator hand-over barriers, used alternately (8 hand-overs per leaf): a waiter may lag the barrier by one phase
-// only, and the two tile groups of an 8^3 conv are committed back to back — with the next leaf's conv1 running under the
-// VQ of this one, both of its commits can land before the row threads get to their first wait.
+// Accumulator hand-over barriers.  down / res32.c1 / res32.c2 / VQ use two barriers alternately (4 hand-overs per leaf): a
+// waiter may lag a barrier by one phase only.  The tile groups of an 8^3 conv are committed back to back — with the next
+// leaf's conv1 running under the VQ of this one, all of its commits can land before the row threads get to their first
+// wait — so every group has its own barrier (two phases per leaf: conv1, conv2).
 __device__ __forceinline__ uint32_t bar_d_full(uint32_t bars, uint32_t which) { return bars + (2 * kStages + 1 + which) * 8; }
+__device__ __forceinline__ uint32_t bar_d8_full(uint32_t bars, uint32_t group) { return bars + (2 * kStages + 3 + group) * 8; }
 
 // ---- tcgen05 wrappers ----
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -189,13 +192,23 @@ __device__ __forceinline__ void signal_a_ready(uint32_t bars, int lane) {
 struct RowCtx {
 	int warp, lane, g;      // g = channel group of this warp (warp >> 2); TMEM lane quadrant = warp & 3
 	uint32_t bars, tlane;   // mbarrier base; TMEM base + (quadrant * 32 << 16)
-	uint32_t d_count = 0;   // accumulator hand-overs so far (parity of d_full)
+	uint32_t d_count = 0;   // down / 4^3 / VQ accumulator hand-overs so far (parity of d_full)
+	uint32_t d8_count = 0;  // 8^3 convs finished so far (parity of every d8_full)
 	float* red;
 };
 __device__ __forceinline__ void wait_accumulator(RowCtx& rc) {
 	mbar_wait(bar_d_full(rc.bars, rc.d_count & 1u), (rc.d_count >> 1) & 1u);
 	tc_fence_after();
 	++rc.d_count;
+}
+// tile t of the current 8^3 conv: waits for its group when t is the group's first tile
+__device__ __forceinline__ void wait_conv_tile(const RowCtx& rc, int t) {
+#pragma unroll
+	for (int g = 0; g < kConvGroups; ++g)
+		if (t == enc_tc_group_first(g)) {
+			mbar_wait(bar_d8_full(rc.bars, g), rc.d8_count & 1u);
+			tc_fence_after();
+		}
 }
 
 // Sum NG (<= 2) per-thread values over the 128 row threads of this thread's channel group: warp shuffle, then the
@@ -386,6 +399,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 		mbar_init(bar_a_ready(bars), kRowWarps);
 		mbar_init(bar_d_full(bars, 0), 1);
 		mbar_init(bar_d_full(bars, 1), 1);
+		for (int g = 0; g < kConvGroups; ++g) mbar_init(bar_d8_full(bars, g), 1);
 		mbar_fence_init();
 	}
 	if (warp == kIssuerWarp) {
@@ -452,15 +466,15 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			};
 #pragma unroll 1
 			for (int64_t it = 0; it < my_leaves; ++it) {
-				// ---- res16 conv1, conv2: 5 tiles x 9 (kd, kh) x {N = 96, N = 48}, in two tile groups (0-2, 3-4) with their own
-				//      completion signal: the row threads drain the first group while the second group's MMAs run ----
-#pragma unroll 1
+				// ---- res16 conv1, conv2: 5 tiles x 9 (kd, kh) x {N = 96, N = 48}, in kConvGroups tile groups with their own
+				//      completion signal: the row threads drain a group while the next group's MMAs run ----
 				w_phase = 0;
+#pragma unroll 1
 				for (int layer = 0; layer < 2; ++layer) {
 					wait_a();
 #pragma unroll 1
-					for (int tg = 0; tg < 2; ++tg) {
-						const int t0 = tg ? 3 : 0, t1 = tg ? 5 : 3;
+					for (int tg = 0; tg < kConvGroups; ++tg) {
+						const int t0 = enc_tc_group_first(tg), t1 = enc_tc_group_first(tg + 1);
 #pragma unroll 1
 						for (int kd = 0; kd < 3; ++kd) {
 							const uint32_t wb = wait_w();
@@ -479,7 +493,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 							release_w();
 							if (kProf) t_issue += prof_clock<kProf>() - c0;
 						}
-						commit_d();
+						tc_commit(bar_d8_full(bars, tg));
 					}
 				}
 				// ---- down: 4 (td, th) tap pairs x 8 parity classes x {N = 128, N = 64}; the two tw taps of a pair are
@@ -708,7 +722,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				for (int c = 0; c < 4; ++c) xr[t][c] = xn[t][c];
 
 			// ---- conv1 epilogue: + bias, res16.gn2 + ReLU -> A8 (conv2 input) ----
-			wait_accumulator(rc);
+			wait_conv_tile(rc, 0);
 			lap(3);
 			{
 				float v[5][4];
@@ -717,7 +731,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				for (int c = 0; c < 4; ++c) bs[c] = sp_c[par::r16_c1_b + g * 4 + c];
 #pragma unroll
 				for (int t = 0; t < 5; ++t) {
-					if (t == 3) wait_accumulator(rc);  // second tile group
+					if (t > 0) wait_conv_tile(rc, t);  // the later tile groups
 					conv16_tile_out(rc.tlane + t * 96, g, lane & 7, v[t]);
 #pragma unroll
 					for (int c = 0; c < 4; ++c) v[t][c] += bs[c];
@@ -728,6 +742,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 						for (int c = 0; c < 4; ++c) tap_out[(leaf * 16 + g * 4 + c) * 512 + d * 64 + h * 8 + w8] = v[t][c];
 					}
 				}
+				++rc.d8_count;
 				lap(13);
 				float mean[2], rstd[2];
 				gn_stats_regs<5, 4, 2>(v, valid8, 1.f / 1024.f, rc, mean, rstd);
@@ -751,7 +766,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			lap(4);
 
 			// ---- conv2 epilogue: x2 = x + 0.1 (conv2 + b) -> Y, the space-to-depth input of `down` ----
-			wait_accumulator(rc);
+			wait_conv_tile(rc, 0);
 			lap(5);
 			{
 				float bs[4];
@@ -759,7 +774,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				for (int c = 0; c < 4; ++c) bs[c] = sp_c[par::r16_c2_b + g * 4 + c];
 #pragma unroll
 				for (int t = 0; t < 5; ++t) {
-					if (t == 3) wait_accumulator(rc);  // second tile group
+					if (t > 0) wait_conv_tile(rc, t);  // the later tile groups
 					float o[4];
 					conv16_tile_out(rc.tlane + t * 96, g, lane & 7, o);
 					int d, h, w8;
@@ -776,6 +791,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 						store_split4(yb + (uint32_t)(pcl * 2 + (g >> 1)) * kYPlane + (uint32_t)qy * 16 + (uint32_t)(g & 1) * 8, kYPrec, o);
 					}
 				}
+				++rc.d8_count;
 			}
 			signal_a_ready(bars, lane);
 			lap(6);

@@ -106,12 +106,23 @@ std::vector<uint8_t> build_encoder_tc_units(const WeightPack& p, EncoderTcStream
 		++nu;
 		return out.data() + off;
 	};
+	auto alias_unit = [&](int src) {  // a later pass over bytes that are already in the stream
+		if (nu >= kEncTcUnits) throw std::logic_error("encoder tc unit table overflow");
+		tab.off[nu] = tab.off[src];
+		tab.bytes[nu] = tab.bytes[src];
+		++nu;
+	};
 	out.reserve(512 * 1024);
 	// res16 conv1 / conv2: weight [16][16][3][3][3]
 	for (const char* name : {"encoder.pre.3.conv1.weight", "encoder.pre.3.conv2.weight"}) {
 		const float* w = p.get(name).data;
-		for (int pass = 0; pass < 2; ++pass)  // one pass per tile group
+		const int first = nu;
+		for (int pass = 1; pass <= kEncTcConvGroups; ++pass)  // one pass per tile group; passes 2.. re-read pass 1's bytes
 		for (int kd = 0; kd < 3; ++kd) {
+			if (pass > 1) {
+				alias_unit(first + kd);
+				continue;
+			}
 			uint8_t* u = begin_unit(3 * 3072);
 			for (int kh = 0; kh < 3; ++kh)
 				for (int part = 0; part < 2; ++part)

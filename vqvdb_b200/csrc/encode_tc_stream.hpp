@@ -12,8 +12,10 @@ namespace vqvdb {
 // The encoder's GEMM-shaped layers consume their weights as a fixed stream of "units" (<= 16 KB) through a
 // shared-memory ring.  Every unit is a sequence of B operands in the canonical no-swizzle K-major UMMA layout
 // [k-chunk (2)][n][8 elements = 16 B]; conv weights are split into two fp16 planes, w ~= w_hi + w_lo / 2048:
-//   res16 conv1 / conv2 : 3 units (one per kd) = 3 (kh) x [2][96][16 B], n = part*48 + kw*16 + cout; streamed TWICE per conv
-//                         (tiles 0-2, then tiles 3-4, so the first group's epilogue overlaps the second group's MMAs)
+//   res16 conv1 / conv2 : 3 units (one per kd) = 3 (kh) x [2][96][16 B], n = part*48 + kw*16 + cout; streamed once per TILE
+//                         GROUP of the conv (kEncTcConvGroups groups of the five 128-row tiles, each with its own
+//                         completion signal, so a group's epilogue overlaps the next group's MMAs); the table entries of
+//                         the later groups alias the bytes of the first
 //   down                : 8 units (2x2x2-tap space-to-depth form; one per (td, th) tap pair and half of the 8 input
 //                         parity classes) = 4 parity classes x [2][128][16 B], n = part*64 + tw*32 + cout
 //   res32 conv1 / conv2 : 9 units each (one per (kd, kh)) = 2 k-steps x [2][192][16 B], n = part*96 + kw*32 + cout
@@ -26,7 +28,20 @@ namespace vqvdb {
 // folded in double precision on the host (build_encoder_vq_fold).  The tensor-core scores only SHORTLIST (rigorous error
 // bound in encode_tc.cu); rows whose shortlist has more than one code compute z = W x + b in fp32 and are re-scored
 // with the reference's own formula (python/save_for_inference.py:55-61) exactly as before.
-constexpr int kEncTcUnits = 40;
+// Measured (592 k leaves, B200, profiles/r2_encode_tile_groups.txt): 2 groups 5.36 M leaves/s, 3 groups 5.22 M, 5 groups
+// 5.01 M.  Finer groups do shorten the exposed MMA waits (conv2: 4.2 k -> 2.2 k cycles per leaf) but the convs are
+// shared-memory-bandwidth bound (operand reads of 134 B/cycle), so epilogue stores that run under more of the MMAs slow
+// the MMAs down by more than the overlap buys, and the weights are re-streamed once per group.
+#ifndef VQVDB_ENC_TILE_GROUPS
+#define VQVDB_ENC_TILE_GROUPS 2
+#endif
+constexpr int kEncTcConvGroups = VQVDB_ENC_TILE_GROUPS;    // 5: one tile per group; 3: {0,1},{2,3},{4}; 2: {0,1,2},{3,4}
+static_assert(kEncTcConvGroups == 2 || kEncTcConvGroups == 3 || kEncTcConvGroups == 5, "tile groups of the 8^3 convs");
+// first tile of group g (g == kEncTcConvGroups gives 5)
+constexpr int enc_tc_group_first(int g) {
+	return kEncTcConvGroups == 5 ? g : kEncTcConvGroups == 3 ? (g * 2 < 5 ? g * 2 : 5) : (g == 0 ? 0 : g == 1 ? 3 : 5);
+}
+constexpr int kEncTcUnits = 2 * 3 * kEncTcConvGroups + 8 + 18 + 2;
 constexpr uint32_t kEncTcStageBytes = 16384;
 
 struct EncoderTcStream {
