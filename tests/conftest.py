@@ -24,7 +24,13 @@ def golden(name):
     return np.load(os.path.join(REPO, "tests", "golden", name + ".npz"))
 
 
-def assert_indices_match(got, gold_idx, gold_margin, max_frac=2e-3):
+# Measured on the committed goldens (profiles/r2_parity_report.json, both encoders): the worst set is the fog sphere with
+# 10 of 19 328 latents (5.2e-4; 508 of its latents are near-ties, most of them the same constant leaf repeated), the
+# worst reference margin at any mismatch is 1.5e-5, and the known-answer vector has none.  max_frac is 3x the worst case.
+MAX_MISMATCH_FRAC = 1.6e-3
+
+
+def assert_indices_match(got, gold_idx, gold_margin, max_frac=MAX_MISMATCH_FRAC):
     """Bit-exact except at reference near-ties; returns the mismatch count."""
     import numpy as np
     mm = got != gold_idx

@@ -84,3 +84,29 @@ def test_reference_backend_matches_golden_if_built():
         assert np.abs(rec - g["recon"][:32]).max() <= 1e-6
     finally:
         ref.close()
+
+
+def test_c_oracle_vec3_matches_the_reference_classes():
+    # config 4: the C restatement with the seeded vec3 pack against goldens made by the reference's own EncoderVec3 /
+    # DecoderVec3 classes (tools/make_goldens.py); this is the checker of the vec3 GPU path and of bench.py --workload vec3
+    import os
+    import subprocess
+    import sys
+    from conftest import REPO
+    from oracle.pyoracle import COracle
+    pack = os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw")
+    if not os.path.exists(pack):
+        subprocess.check_call([sys.executable, os.path.join(REPO, "tools", "weights_pack.py"), "vec3"], stdout=subprocess.DEVNULL)
+    o = COracle(pack, threads=os.cpu_count() or 1)
+    g = golden("vec3_noise64_seed6")
+    x = synth.noise_leaves(64, seed=6, channels=3)
+    assert hashlib.sha256(x.tobytes()).hexdigest() == str(g["input_sha256"])
+    idx, margins = o.encode(x, with_margins=True)
+    assert_indices_match(idx, g["indices"], g["margins"])
+    m = len(g["recon"])
+    assert np.abs(o.decode(g["indices"][:m]) - g["recon"]).max() <= 5e-5
+    big = golden("vec3_sparse1024_seed7")
+    xb = synth.smoke_leaves(1024, seed=7, channels=3, sparse=True)
+    assert hashlib.sha256(xb.tobytes()).hexdigest() == str(big["input_sha256"])
+    idx_b, _ = o.encode(xb[:96], with_margins=True)
+    assert_indices_match(idx_b, big["indices"][:96], big["margins"][:96])

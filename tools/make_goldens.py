@@ -15,7 +15,7 @@ Each golden holds:
     recon             float32 [m,1,8,8,8] reference decode(indices[:m])
     recon_sum         float64 sum of decode over all n leaves
 
-Run:  python tools/make_goldens.py        (needs /root/reference; ~1 min on 8 cores)
+Run:  python tools/make_goldens.py [name ...]   (needs /root/reference; ~3 min on 8 cores; names restrict what is rewritten)
 """
 from __future__ import annotations
 
@@ -53,6 +53,7 @@ def reference_outputs(mod, x: np.ndarray, n_recon: int):
 
 
 def main():
+    only = set(sys.argv[1:])
     torch.set_num_threads(os.cpu_count() or 1)
     mod = wp.load_reference_module()
     out_dir = os.path.join(REPO, "tests", "golden")
@@ -67,6 +68,8 @@ def main():
         "zeros4": (np.zeros((4, 1, 8, 8, 8), np.float32), 4),
     }
     for name, (x, n_recon) in cases.items():
+        if only and name not in only:
+            continue
         idx, margins, recon, rsum = reference_outputs(mod, x, n_recon)
         path = os.path.join(out_dir, name + ".npz")
         np.savez_compressed(path, input_sha256=np.array(hashlib.sha256(x.tobytes()).hexdigest()),
@@ -81,13 +84,19 @@ def main():
         wp.main(["vec3"])
     vmod = wp.load_vec3_reference_module(vec3_pack)
     vmeta, _ = wp.read_pack(vec3_pack)
-    for name, x, n_recon in (("vec3_smoke256_seed5", synth.smoke_leaves(256, seed=5, channels=3), 32),
-                             ("vec3_noise64_seed6", synth.noise_leaves(64, seed=6, channels=3), 16)):
+    for name, gen, n_recon in (("vec3_smoke256_seed5", lambda: synth.smoke_leaves(256, seed=5, channels=3), 32),
+                               ("vec3_noise64_seed6", lambda: synth.noise_leaves(64, seed=6, channels=3), 16),
+                               ("vec3_sparse1024_seed7", lambda: synth.smoke_leaves(1024, seed=7, channels=3, sparse=True), 16)):
+        if only and name not in only:
+            continue
+        x = gen()
         idx, margins, recon, rsum = reference_outputs(vmod, x, n_recon)
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), input_sha256=np.array(hashlib.sha256(x.tobytes()).hexdigest()),
                             indices=idx, margins=margins, recon=recon, recon_sum=np.array(rsum), n=np.array(x.shape[0]),
                             pack_sha256=np.array(vmeta["sha256"]))
         print("%-20s n=%5d codes=%3d min_margin=%.3e" % (name, x.shape[0], len(np.unique(idx)), float(margins.min())))
+    if only and "decode_random128_seed1234" not in only:
+        return
     # decode-only golden: random indices straight into the reference decoder (config 2)
     ridx = synth.random_indices(128, seed=1234)
     with torch.no_grad():

@@ -33,6 +33,7 @@ FLOAT_CASES = {
 VEC3_CASES = {
     "vec3_smoke256_seed5": lambda: synth.smoke_leaves(256, seed=5, channels=3),
     "vec3_noise64_seed6": lambda: synth.noise_leaves(64, seed=6, channels=3),
+    "vec3_sparse1024_seed7": lambda: synth.smoke_leaves(1024, seed=7, channels=3, sparse=True),
 }
 
 
