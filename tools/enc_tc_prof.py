@@ -34,3 +34,5 @@ for i, nm in enumerate(names):
 print("%-36s %8.0f cyc/leaf" % ("row thread total", tot))
 print("issuer: wait a_ready %.0f  wait w_full %.0f  issue+commit %.0f  total %.0f cyc/leaf" % tuple(p[:, 32 + i].mean() / leaves for i in range(4)))
 print("issuer weight waits by phase: 8^3 convs %.0f  down %.0f  4^3 convs %.0f  VQ %.0f cyc/leaf" % tuple(p[:, 36 + i].mean() / leaves for i in range(4)))
+print("issuer, operands ready -> layer's MMAs complete: 8^3 convs (2) %.0f  down %.0f  4^3 convs (2) %.0f  VQ %.0f cyc/leaf" % tuple(p[:, 40 + i].mean() / leaves for i in range(4)))
+print("issuer, time inside the issue loops: 8^3 convs (180 MMAs) %.0f  down (64) %.0f  4^3 convs (72) %.0f  VQ (6) %.0f cyc/leaf" % tuple(p[:, 44 + i].mean() / leaves for i in range(4)))

@@ -114,6 +114,12 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16])
 	for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(o[j]);
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// One lane of a converged warp (the same one every time).
+__device__ __forceinline__ bool elect_one() {
+	uint32_t pred;
+	asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+	return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 	asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -349,7 +355,15 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 	if (warp >= kWorkWarps) {
 		// ===================== control warps =====================
 		if (warp < kWorkWarps + kTiles) {
+#ifdef VQVDB_DEC_ISSUER_LANE0
+			const bool leader = true;
 			if (lane == 0 && warp - kWorkWarps < active_tiles) {
+#else
+			// The whole warp runs the issue loop, one elected lane executes the tcgen05 instructions: warp-uniform control
+			// flow keeps descriptors and loop state in uniform registers (see encode_tc.cu's issuer for the measurement).
+			const bool leader = elect_one();
+			if (warp - kWorkWarps < active_tiles) {
+#endif
 				// MMA issuer of tile t.  The issuers are independent, so the tiles drift apart and one tile's epilogue
 				// overlaps the other tile's MMAs.
 				const uint32_t t = warp - kWorkWarps;
@@ -372,11 +386,11 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 						const uint64_t bdesc = make_desc_sw128(ring + s * kUnitBytes);
 #pragma unroll
 						for (uint32_t kk = 0; kk < 4; ++kk)
-							tc_mma_ts(tmem + t * kDCols, tmem + kColA + t * 64 + buf * 32 + kk * 8, bdesc + (uint64_t)(kk * 2),
+							if (leader) tc_mma_ts(tmem + t * kDCols, tmem + kColA + t * 64 + buf * 32 + kk * 8, bdesc + (uint64_t)(kk * 2),
 							          (in_pass > 0 || kk > 0) ? 1u : 0u);
-						tc_commit(bar_a_empty(bars, t, buf));
-						if (last) tc_commit(bar_d_full(bars, t));
-						tc_commit(bar_w_empty(bars, s));
+						if (leader) tc_commit(bar_a_empty(bars, t, buf));
+						if (last && leader) tc_commit(bar_d_full(bars, t));
+						if (leader) tc_commit(bar_w_empty(bars, s));
 						++unit;
 						if (kProf) {
 							tw += c1 - c0;
@@ -385,7 +399,7 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 						}
 					}
 				}
-				if (kProf && tap_out) {
+				if (kProf && tap_out && leader) {
 					float* o = tap_out + ((size_t)blockIdx.x * kThreads + threadIdx.x) * 4;
 					o[0] = (float)tw; o[1] = (float)ta; o[2] = (float)ti; o[3] = (float)(prof_clock<kProf>() - tstart);
 				}

@@ -93,8 +93,8 @@ constexpr uint32_t kOffH = kOffY + kYBytes;                     // 182 272
 constexpr uint32_t kOffIn = kOffH + kHBytes;                    // in_halo [10][10][10] fp32 (4096 reserved)
 constexpr uint32_t kOffPreW = kOffIn + 4096;                    // pre.0 weights [27][16] fp32
 constexpr uint32_t kOffX32 = kOffPreW + 1728;                   // residual of the 4^3 block [64][36] fp32; later the VQ exchange
-constexpr uint32_t kOffRed = kOffX32 + 64 * kX32Pitch * 4;      // GroupNorm partials [2 slots][16 warps][2]
-constexpr uint32_t kOffAtt = kOffRed + 256;                     // attention: part [16 warps][8], hid [8], scale [32]
+constexpr uint32_t kOffRed = kOffX32 + 64 * kX32Pitch * 4;      // GroupNorm partials [2 slots][16 warps][2], then the one-pass form's [16 warps][4]
+constexpr uint32_t kOffAtt = kOffRed + 512;                     // attention: part [16 warps][8], hid [8], scale [32]
 constexpr uint32_t kOffCb = kOffAtt + (128 + 8 + 32) * 4;       // emb_sq [256], fold_esq [256], fold_norm [256]
 constexpr uint32_t kOffPar = kOffCb + 3088;                     // fold_norm has a 257th entry: its maximum                     // per-channel parameter vectors (ParOff), 1008 floats
 constexpr uint32_t kOffXq = kOffPar + 1008 * 4;                 // `down` epilogue: lane-0 values handed to the previous quadrant [4][4][8]
@@ -164,6 +164,12 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16])
 	for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(o[j]);
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// One lane of a converged warp (the same one every time).
+__device__ __forceinline__ bool elect_one() {
+	uint32_t pred;
+	asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+	return pred != 0;
+}
 __device__ __forceinline__ void row_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
 	asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -196,8 +202,18 @@ struct RowCtx {
 	uint32_t d8_count = 0;  // 8^3 convs finished so far (parity of every d8_full)
 	float* red;
 };
+// All 512 row threads wait for the same barrier: by default each one parks on it (hardware-assisted try_wait); with
+// VQVDB_ENC_WAIT_LANE0 only lane 0 of every warp does and the rest of the warp waits at a __syncwarp.
+__device__ __forceinline__ void row_wait(const RowCtx& rc, uint32_t bar, uint32_t parity) {
+#ifdef VQVDB_ENC_WAIT_LANE0
+	if (rc.lane == 0) mbar_wait(bar, parity);
+	__syncwarp();
+#else
+	mbar_wait(bar, parity);
+#endif
+}
 __device__ __forceinline__ void wait_accumulator(RowCtx& rc) {
-	mbar_wait(bar_d_full(rc.bars, rc.d_count & 1u), (rc.d_count >> 1) & 1u);
+	row_wait(rc, bar_d_full(rc.bars, rc.d_count & 1u), (rc.d_count >> 1) & 1u);
 	tc_fence_after();
 	++rc.d_count;
 }
@@ -206,7 +222,7 @@ __device__ __forceinline__ void wait_conv_tile(const RowCtx& rc, int t) {
 #pragma unroll
 	for (int g = 0; g < kConvGroups; ++g)
 		if (t == enc_tc_group_first(g)) {
-			mbar_wait(bar_d8_full(rc.bars, g), rc.d8_count & 1u);
+			row_wait(rc, bar_d8_full(rc.bars, g), rc.d8_count & 1u);
 			tc_fence_after();
 		}
 }
@@ -263,6 +279,50 @@ __device__ __forceinline__ void gn_stats_regs(const float (&v)[R][C], uint32_t v
 #pragma unroll
 	for (int i = 0; i < NG; ++i) rstd[i] = 1.f / sqrtf(s[i] * inv_cnt + kGnEps);
 }
+
+// One-pass variant for the GroupNorms that sit on the critical path between two MMA phases (their inputs are conv
+// outputs of normalised activations: |mean| is of the order of the standard deviation, so E[x^2] - mean^2 loses no more
+// than a few ulps): sums and sums of squares travel through ONE group reduction instead of two.
+template <int R, int C, int CPG>
+__device__ __forceinline__ void gn_stats_regs_onepass(const float (&v)[R][C], uint32_t valid, float inv_cnt, const RowCtx& rc,
+                                                      float (&mean)[C / CPG], float (&rstd)[C / CPG]) {
+	constexpr int NG = C / CPG;
+	static_assert(NG == 2, "two groups per thread");
+	float s[2 * NG];
+#pragma unroll
+	for (int i = 0; i < 2 * NG; ++i) s[i] = 0.f;
+#pragma unroll
+	for (int t = 0; t < R; ++t)
+		if (valid & (1u << t)) {
+#pragma unroll
+			for (int c = 0; c < C; ++c) {
+				s[c / CPG] += v[t][c];
+				s[NG + c / CPG] = fmaf(v[t][c], v[t][c], s[NG + c / CPG]);
+			}
+		}
+#pragma unroll
+	for (int i = 0; i < 2 * NG; ++i) s[i] = warp_sum(s[i]);
+	// [16 warps][4], its own buffer: the two-pass reductions of the next leaf's front run between two calls of this one
+	// and alternate between the two slots in front of it; consecutive calls of this one are always separated by a
+	// barrier of all row threads or by an MMA phase (which starts only after every row warp has arrived)
+	float* red = rc.red + 64;
+	if (rc.lane == 0) *reinterpret_cast<float4*>(red + rc.warp * 4) = make_float4(s[0], s[1], s[2], s[3]);
+	asm volatile("bar.sync %0, 128;" ::"r"(2 + rc.g) : "memory");
+	const float4 r0 = *reinterpret_cast<const float4*>(red + rc.g * 16), r1 = *reinterpret_cast<const float4*>(red + rc.g * 16 + 4);
+	const float4 r2 = *reinterpret_cast<const float4*>(red + rc.g * 16 + 8), r3 = *reinterpret_cast<const float4*>(red + rc.g * 16 + 12);
+	const float sum[2] = {(r0.x + r1.x) + (r2.x + r3.x), (r0.y + r1.y) + (r2.y + r3.y)};
+	const float sq[2] = {(r0.z + r1.z) + (r2.z + r3.z), (r0.w + r1.w) + (r2.w + r3.w)};
+#pragma unroll
+	for (int i = 0; i < NG; ++i) {
+		mean[i] = sum[i] * inv_cnt;
+		rstd[i] = 1.f / sqrtf(fmaxf(fmaf(-mean[i], mean[i], sq[i] * inv_cnt), 0.f) + kGnEps);
+	}
+}
+#ifdef VQVDB_ENC_GN_ONEPASS
+#define GN_STATS_CRITICAL gn_stats_regs_onepass
+#else
+#define GN_STATS_CRITICAL gn_stats_regs
+#endif
 
 // Flattened 8^3 row q -> voxel; false for halo / padding rows.
 __device__ __forceinline__ bool row8(int q, int& d, int& h, int& w) {
@@ -427,10 +487,25 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 		__syncwarp();
 	} else if (warp == kIssuerWarp) {
 		// ===================== MMA issuer =====================
+		// The WHOLE warp runs the issue loop and one elected lane executes the tcgen05 instructions: with warp-uniform
+		// control flow the descriptors and loop state live in uniform registers, so an MMA costs the issuing warp a
+		// handful of instructions.  (A single-lane branch keeps them in vector registers and moves them to uniform
+		// registers before every MMA; sharing its scheduler with four busy row warps, that issuer could not feed the
+		// tensor pipe: measured 93 - 165 cycles per MMA inside the kernel against 50 in isolation.)
+#ifdef VQVDB_ENC_ISSUER_LANE0
+		const bool leader = true;
 		if (lane == 0) {
+#else
+		const bool leader = elect_one();
+		{
+#endif
 			uint32_t unit = 0, a_count = 0, d_commits = 0;
 			long long t_wait_a = 0, t_wait_w = 0, t_issue = 0;
 			long long t_wait_w_phase[4] = {0, 0, 0, 0};  // kProf: weight waits per phase (8^3 convs, down, 4^3 convs, VQ)
+			long long t_exec_phase[4] = {0, 0, 0, 0};    // kProf: operands handed over -> last MMA of the layer complete
+			long long t_phase0 = 0;
+			long long t_issue_phase[4] = {0, 0, 0, 0};   // kProf: time inside the issue loops, per phase
+			uint32_t convs_done = 0;
 			int w_phase = 0;
 			const long long t_start = prof_clock<kProf>();
 			const uint64_t a8_d = make_desc(a8 + kA8Margin * 16, kA8Plane, 128);
@@ -442,7 +517,10 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				mbar_wait(bar_a_ready(bars), a_count & 1u);
 				tc_fence_after();
 				++a_count;
-				if (kProf) t_wait_a += prof_clock<kProf>() - c0;
+				if (kProf) {
+					t_phase0 = prof_clock<kProf>();
+					t_wait_a += t_phase0 - c0;
+				}
 			};
 			auto wait_w = [&]() -> uint32_t {
 				const long long c0 = prof_clock<kProf>();
@@ -457,11 +535,15 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				return ring + s * kStageBytes;
 			};
 			auto commit_d = [&]() {
-				tc_commit(bar_d_full(bars, d_commits & 1u));
+				if (leader) tc_commit(bar_d_full(bars, d_commits & 1u));
+				if (kProf) {  // the issuer has nothing to do before the row threads have read this result anyway
+					mbar_wait(bar_d_full(bars, d_commits & 1u), (d_commits >> 1) & 1u);
+					t_exec_phase[w_phase] += prof_clock<kProf>() - t_phase0;
+				}
 				++d_commits;
 			};
 			auto release_w = [&]() {
-				tc_commit(bar_w_empty(bars, unit % kStages));
+				if (leader) tc_commit(bar_w_empty(bars, unit % kStages));
 				++unit;
 			};
 #pragma unroll 1
@@ -486,15 +568,24 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 									const int s = (kd - 1) * 72 + (kh - 1) * 8 + 128 * t;
 									const uint64_t ad = a8_d + (uint64_t)(int64_t)s;
 									const uint64_t bd = make_desc(wb + kh * 3072, 96 * 16, 128);
-									mma_ss(tmem + t * 96, ad, bd, idesc_f16(96), (kd > 0 || kh > 0) ? 1u : 0u);
-									mma_ss(tmem + t * 96 + 48, ad + (kA8Prec >> 4), bd, idesc_f16(48), 1u);
+									if (leader) mma_ss(tmem + t * 96, ad, bd, idesc_f16(96), (kd > 0 || kh > 0) ? 1u : 0u);
+									if (leader) mma_ss(tmem + t * 96 + 48, ad + (kA8Prec >> 4), bd, idesc_f16(48), 1u);
 								}
 							}
 							release_w();
-							if (kProf) t_issue += prof_clock<kProf>() - c0;
+							if (kProf) {
+								const long long dt = prof_clock<kProf>() - c0;
+								t_issue += dt;
+								t_issue_phase[w_phase] += dt;
+							}
 						}
-						tc_commit(bar_d8_full(bars, tg));
+						if (leader) tc_commit(bar_d8_full(bars, tg));
+						if (kProf && tg == kConvGroups - 1) {
+							mbar_wait(bar_d8_full(bars, tg), convs_done & 1u);
+							t_exec_phase[0] += prof_clock<kProf>() - t_phase0;
+						}
 					}
+					++convs_done;
 				}
 				// ---- down: 4 (td, th) tap pairs x 8 parity classes x {N = 128, N = 64}; the two tw taps of a pair are
 				//      concatenated along N like the kw taps of the 3x3x3 convs (their row shift of 1 is applied in the
@@ -514,11 +605,15 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					for (int pcl = 0; pcl < 4; ++pcl) {
 						const uint64_t ad = y_d + (uint64_t)(s + (half * 4 + pcl) * 2 * (int)(kYPlane >> 4));
 						const uint64_t bd = make_desc(wb + pcl * 4096, 128 * 16, 128);
-						mma_ss(dcol, ad, bd, idesc_f16(128), (half > 0 || pcl > 0) ? 1u : 0u);
-						mma_ss(dcol + 64, ad + (kYPrec >> 4), bd, idesc_f16(64), 1u);
+						if (leader) mma_ss(dcol, ad, bd, idesc_f16(128), (half > 0 || pcl > 0) ? 1u : 0u);
+						if (leader) mma_ss(dcol + 64, ad + (kYPrec >> 4), bd, idesc_f16(64), 1u);
 					}
 					release_w();
-					if (kProf) t_issue += prof_clock<kProf>() - c0;
+					if (kProf) {
+								const long long dt = prof_clock<kProf>() - c0;
+								t_issue += dt;
+								t_issue_phase[w_phase] += dt;
+							}
 				}
 				commit_d();
 				// ---- res32 conv1, conv2: 9 (kd, kh) x 2 k-steps x {N = 192, N = 96} ----
@@ -535,11 +630,15 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 						for (int ks = 0; ks < 2; ++ks) {
 							const uint64_t ad = h_d + (uint64_t)(int64_t)(s + ks * 2 * (int)(kHPlane >> 4));
 							const uint64_t bd = make_desc(wb + ks * 6144, 192 * 16, 128);
-							mma_ss(tmem, ad, bd, idesc_f16(192), (kk > 0 || ks > 0) ? 1u : 0u);
-							mma_ss(tmem + 96, ad + (kHPrec >> 4), bd, idesc_f16(96), 1u);
+							if (leader) mma_ss(tmem, ad, bd, idesc_f16(192), (kk > 0 || ks > 0) ? 1u : 0u);
+							if (leader) mma_ss(tmem + 96, ad + (kHPrec >> 4), bd, idesc_f16(96), 1u);
 						}
 						release_w();
-						if (kProf) t_issue += prof_clock<kProf>() - c0;
+						if (kProf) {
+								const long long dt = prof_clock<kProf>() - c0;
+								t_issue += dt;
+								t_issue_phase[w_phase] += dt;
+							}
 					}
 					commit_d();
 				}
@@ -553,19 +652,27 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					const long long c0 = prof_clock<kProf>();
 					const uint64_t ad = xh_d + (uint64_t)(ks * 2 * (int)(kXhPlane >> 4));
 					const uint64_t bh = make_desc(wb, 256 * 16, 128), bl = make_desc(wb + 8192, 256 * 16, 128);
-					mma_ss(tmem, ad, bh, idesc_f16(256), ks > 0 ? 1u : 0u);
-					mma_ss(tmem + 256, ad, bl, idesc_f16(256), ks > 0 ? 1u : 0u);
-					mma_ss(tmem + 256, ad + (kXhPrec >> 4), bh, idesc_f16(256), 1u);
+					if (leader) mma_ss(tmem, ad, bh, idesc_f16(256), ks > 0 ? 1u : 0u);
+					if (leader) mma_ss(tmem + 256, ad, bl, idesc_f16(256), ks > 0 ? 1u : 0u);
+					if (leader) mma_ss(tmem + 256, ad + (kXhPrec >> 4), bh, idesc_f16(256), 1u);
 					release_w();
-					if (kProf) t_issue += prof_clock<kProf>() - c0;
+					if (kProf) {
+								const long long dt = prof_clock<kProf>() - c0;
+								t_issue += dt;
+								t_issue_phase[w_phase] += dt;
+							}
 				}
 				commit_d();
 			}
-			if (kProf && tap_out) {
+			if (kProf && tap_out && leader) {
 				float* o = tap_out + (size_t)blockIdx.x * 64 + 32;
 				o[0] = (float)t_wait_a; o[1] = (float)t_wait_w; o[2] = (float)t_issue; o[3] = (float)(prof_clock<kProf>() - t_start);
 #pragma unroll
 				for (int i = 0; i < 4; ++i) o[4 + i] = (float)t_wait_w_phase[i];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) o[8 + i] = (float)t_exec_phase[i];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) o[12 + i] = (float)t_issue_phase[i];
 			}
 		}
 		__syncwarp();
@@ -745,7 +852,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				++rc.d8_count;
 				lap(13);
 				float mean[2], rstd[2];
-				gn_stats_regs<5, 4, 2>(v, valid8, 1.f / 1024.f, rc, mean, rstd);
+				GN_STATS_CRITICAL<5, 4, 2>(v, valid8, 1.f / 1024.f, rc, mean, rstd);
 				lap(14);
 				float ga[4], be[4];
 #pragma unroll
@@ -855,7 +962,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					}
 				}
 				float mean[2], rstd[2];
-				gn_stats_regs<1, 8, 4>(v, validd ? 1u : 0u, 1.f / 256.f, rc, mean, rstd);
+				GN_STATS_CRITICAL<1, 8, 4>(v, validd ? 1u : 0u, 1.f / 256.f, rc, mean, rstd);
 				if (validd) {
 #pragma unroll
 					for (int c = 0; c < 8; ++c)
@@ -884,7 +991,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					for (int c = 0; c < 8; ++c) tap_out[(leaf * 32 + g * 8 + c) * 64 + p4] = v[0][c];
 				}
 				float mean[2], rstd[2];
-				gn_stats_regs<1, 8, 4>(v, valid4 ? 1u : 0u, 1.f / 256.f, rc, mean, rstd);
+				GN_STATS_CRITICAL<1, 8, 4>(v, valid4 ? 1u : 0u, 1.f / 256.f, rc, mean, rstd);
 				if (valid4) {
 #pragma unroll
 					for (int c = 0; c < 8; ++c)
