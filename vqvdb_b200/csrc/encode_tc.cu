@@ -93,8 +93,8 @@ constexpr uint32_t kOffH = kOffY + kYBytes;                     // 182 272
 constexpr uint32_t kOffIn = kOffH + kHBytes;                    // in_halo [10][10][10] fp32 (4096 reserved)
 constexpr uint32_t kOffPreW = kOffIn + 4096;                    // pre.0 weights [27][16] fp32
 constexpr uint32_t kOffX32 = kOffPreW + 1728;                   // residual of the 4^3 block [64][36] fp32; later the VQ exchange
-constexpr uint32_t kOffRed = kOffX32 + 64 * kX32Pitch * 4;      // GroupNorm partials [2 slots][16 warps][2], then the one-pass form's [16 warps][4]
-constexpr uint32_t kOffAtt = kOffRed + 512;                     // attention: part [16 warps][8], hid [8], scale [32]
+constexpr uint32_t kOffRed = kOffX32 + 64 * kX32Pitch * 4;      // GroupNorm partials [2 slots][16 warps][2]
+constexpr uint32_t kOffAtt = kOffRed + 256;                     // attention: part [16 warps][8], hid [8], scale [32]
 constexpr uint32_t kOffCb = kOffAtt + (128 + 8 + 32) * 4;       // emb_sq [256], fold_esq [256], fold_norm [256]
 constexpr uint32_t kOffPar = kOffCb + 3088;                     // fold_norm has a 257th entry: its maximum                     // per-channel parameter vectors (ParOff), 1008 floats
 constexpr uint32_t kOffXq = kOffPar + 1008 * 4;                 // `down` epilogue: lane-0 values handed to the previous quadrant [4][4][8]
@@ -202,16 +202,9 @@ struct RowCtx {
 	uint32_t d8_count = 0;  // 8^3 convs finished so far (parity of every d8_full)
 	float* red;
 };
-// All 512 row threads wait for the same barrier: by default each one parks on it (hardware-assisted try_wait); with
-// VQVDB_ENC_WAIT_LANE0 only lane 0 of every warp does and the rest of the warp waits at a __syncwarp.
-__device__ __forceinline__ void row_wait(const RowCtx& rc, uint32_t bar, uint32_t parity) {
-#ifdef VQVDB_ENC_WAIT_LANE0
-	if (rc.lane == 0) mbar_wait(bar, parity);
-	__syncwarp();
-#else
-	mbar_wait(bar, parity);
-#endif
-}
+// All 512 row threads park on the barrier themselves (hardware-assisted try_wait); electing one waiter per warp and
+// holding the rest at a __syncwarp was measured 4 % slower (profiles/r2_encode_experiments.txt).
+__device__ __forceinline__ void row_wait(const RowCtx&, uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void wait_accumulator(RowCtx& rc) {
 	row_wait(rc, bar_d_full(rc.bars, rc.d_count & 1u), (rc.d_count >> 1) & 1u);
 	tc_fence_after();
@@ -279,50 +272,6 @@ __device__ __forceinline__ void gn_stats_regs(const float (&v)[R][C], uint32_t v
 #pragma unroll
 	for (int i = 0; i < NG; ++i) rstd[i] = 1.f / sqrtf(s[i] * inv_cnt + kGnEps);
 }
-
-// One-pass variant for the GroupNorms that sit on the critical path between two MMA phases (their inputs are conv
-// outputs of normalised activations: |mean| is of the order of the standard deviation, so E[x^2] - mean^2 loses no more
-// than a few ulps): sums and sums of squares travel through ONE group reduction instead of two.
-template <int R, int C, int CPG>
-__device__ __forceinline__ void gn_stats_regs_onepass(const float (&v)[R][C], uint32_t valid, float inv_cnt, const RowCtx& rc,
-                                                      float (&mean)[C / CPG], float (&rstd)[C / CPG]) {
-	constexpr int NG = C / CPG;
-	static_assert(NG == 2, "two groups per thread");
-	float s[2 * NG];
-#pragma unroll
-	for (int i = 0; i < 2 * NG; ++i) s[i] = 0.f;
-#pragma unroll
-	for (int t = 0; t < R; ++t)
-		if (valid & (1u << t)) {
-#pragma unroll
-			for (int c = 0; c < C; ++c) {
-				s[c / CPG] += v[t][c];
-				s[NG + c / CPG] = fmaf(v[t][c], v[t][c], s[NG + c / CPG]);
-			}
-		}
-#pragma unroll
-	for (int i = 0; i < 2 * NG; ++i) s[i] = warp_sum(s[i]);
-	// [16 warps][4], its own buffer: the two-pass reductions of the next leaf's front run between two calls of this one
-	// and alternate between the two slots in front of it; consecutive calls of this one are always separated by a
-	// barrier of all row threads or by an MMA phase (which starts only after every row warp has arrived)
-	float* red = rc.red + 64;
-	if (rc.lane == 0) *reinterpret_cast<float4*>(red + rc.warp * 4) = make_float4(s[0], s[1], s[2], s[3]);
-	asm volatile("bar.sync %0, 128;" ::"r"(2 + rc.g) : "memory");
-	const float4 r0 = *reinterpret_cast<const float4*>(red + rc.g * 16), r1 = *reinterpret_cast<const float4*>(red + rc.g * 16 + 4);
-	const float4 r2 = *reinterpret_cast<const float4*>(red + rc.g * 16 + 8), r3 = *reinterpret_cast<const float4*>(red + rc.g * 16 + 12);
-	const float sum[2] = {(r0.x + r1.x) + (r2.x + r3.x), (r0.y + r1.y) + (r2.y + r3.y)};
-	const float sq[2] = {(r0.z + r1.z) + (r2.z + r3.z), (r0.w + r1.w) + (r2.w + r3.w)};
-#pragma unroll
-	for (int i = 0; i < NG; ++i) {
-		mean[i] = sum[i] * inv_cnt;
-		rstd[i] = 1.f / sqrtf(fmaxf(fmaf(-mean[i], mean[i], sq[i] * inv_cnt), 0.f) + kGnEps);
-	}
-}
-#ifdef VQVDB_ENC_GN_ONEPASS
-#define GN_STATS_CRITICAL gn_stats_regs_onepass
-#else
-#define GN_STATS_CRITICAL gn_stats_regs
-#endif
 
 // Flattened 8^3 row q -> voxel; false for halo / padding rows.
 __device__ __forceinline__ bool row8(int q, int& d, int& h, int& w) {
@@ -852,7 +801,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				++rc.d8_count;
 				lap(13);
 				float mean[2], rstd[2];
-				GN_STATS_CRITICAL<5, 4, 2>(v, valid8, 1.f / 1024.f, rc, mean, rstd);
+				gn_stats_regs<5, 4, 2>(v, valid8, 1.f / 1024.f, rc, mean, rstd);
 				lap(14);
 				float ga[4], be[4];
 #pragma unroll
@@ -962,7 +911,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					}
 				}
 				float mean[2], rstd[2];
-				GN_STATS_CRITICAL<1, 8, 4>(v, validd ? 1u : 0u, 1.f / 256.f, rc, mean, rstd);
+				gn_stats_regs<1, 8, 4>(v, validd ? 1u : 0u, 1.f / 256.f, rc, mean, rstd);
 				if (validd) {
 #pragma unroll
 					for (int c = 0; c < 8; ++c)
@@ -991,7 +940,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					for (int c = 0; c < 8; ++c) tap_out[(leaf * 32 + g * 8 + c) * 64 + p4] = v[0][c];
 				}
 				float mean[2], rstd[2];
-				GN_STATS_CRITICAL<1, 8, 4>(v, valid4 ? 1u : 0u, 1.f / 256.f, rc, mean, rstd);
+				gn_stats_regs<1, 8, 4>(v, valid4 ? 1u : 0u, 1.f / 256.f, rc, mean, rstd);
 				if (valid4) {
 #pragma unroll
 					for (int c = 0; c < 8; ++c)
