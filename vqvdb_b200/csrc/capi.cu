@@ -711,15 +711,14 @@ int vqvdb_b200_encode(vqvdb_b200_codec* c, const float* host_leaves, int64_t n, 
 		CUDA_TRY(cudaSetDevice(c->device));
 		ensure_staging(*c);
 		const size_t leaf_elems = (size_t)c->channels * 512;
-		const bool in_direct = is_pinned_host(host_leaves), out_direct = is_pinned_host(host_indices);
 		if (!c->generic && n <= std::min<int64_t>(kZeroCopyLeaves, c->chunk)) {  // small call: no copy engines (see kZeroCopyLeaves)
 			Slot& s = c->slots[0];
-			const float* src = in_direct ? device_alias(host_leaves, 16) : nullptr;
+			const float* src = device_alias(host_leaves, 16);  // null for pageable memory
 			if (!src) {
 				std::memcpy(s.h_vox, host_leaves, (size_t)n * leaf_elems * sizeof(float));
 				src = device_alias(static_cast<const float*>(s.h_vox), 16);
 			}
-			uint8_t* dst = out_direct ? device_alias(host_indices, 1) : nullptr;
+			uint8_t* dst = device_alias(host_indices, 1);
 			const bool staged_out = dst == nullptr;
 			if (staged_out) dst = device_alias(s.h_idx, 1);
 			if (src && dst) {
@@ -729,6 +728,7 @@ int vqvdb_b200_encode(vqvdb_b200_codec* c, const float* host_leaves, int64_t n, 
 				return VQVDB_B200_OK;
 			}
 		}
+		const bool in_direct = is_pinned_host(host_leaves), out_direct = is_pinned_host(host_indices);
 		int64_t done = 0;
 		for (int i = 0; done < n; ++i) {
 			Slot& s = c->slots[i % kSlots];
@@ -764,15 +764,14 @@ int vqvdb_b200_decode(vqvdb_b200_codec* c, const uint8_t* host_indices, int64_t 
 		CUDA_TRY(cudaSetDevice(c->device));
 		ensure_staging(*c);
 		const size_t leaf_elems = (size_t)c->channels * 512;
-		const bool in_direct = is_pinned_host(host_indices), out_direct = is_pinned_host(host_voxels);
 		if (!c->generic && n <= std::min<int64_t>(kZeroCopyLeaves, c->chunk)) {  // small call: no copy engines (see kZeroCopyLeaves)
 			Slot& s = c->slots[0];
-			const uint8_t* src = in_direct ? device_alias(host_indices, 4) : nullptr;
+			const uint8_t* src = device_alias(host_indices, 4);  // null for pageable memory
 			if (!src) {
 				std::memcpy(s.h_idx, host_indices, (size_t)n * 64);
 				src = device_alias(static_cast<const uint8_t*>(s.h_idx), 4);
 			}
-			float* dst = out_direct ? device_alias(host_voxels, 16) : nullptr;
+			float* dst = device_alias(host_voxels, 16);
 			const bool staged_out = dst == nullptr;
 			if (staged_out) dst = device_alias(s.h_vox, 16);
 			if (src && dst) {
@@ -782,6 +781,7 @@ int vqvdb_b200_decode(vqvdb_b200_codec* c, const uint8_t* host_indices, int64_t 
 				return VQVDB_B200_OK;
 			}
 		}
+		const bool in_direct = is_pinned_host(host_indices), out_direct = is_pinned_host(host_voxels);
 		int64_t done = 0;
 		for (int i = 0; done < n; ++i) {
 			Slot& s = c->slots[i % kSlots];

@@ -53,6 +53,10 @@ constexpr int kStages = 3;
 constexpr uint32_t kStageBytes = kEncTcStageBytes;
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 constexpr int kDownChains = 4;                    // independent accumulators of `down` (see the issuer)
+#ifndef VQVDB_ENC_PRE0_SPLIT_AT
+#define VQVDB_ENC_PRE0_SPLIT_AT 3   // measured: 0 (all under `down`) 6.422 M leaves/s, 1: 6.461 M, 2: 6.497 M, 3: 6.531 M
+#endif
+constexpr int kPre0Split = VQVDB_ENC_PRE0_SPLIT_AT;  // kd taps of the next leaf's pre.0 that run inside conv2's MMA wait
 // offsets (floats) of the per-channel parameter vectors staged in shared memory: a global (L2) load at the head of
 // every epilogue costs ~300 cycles of exposed latency, there being almost no L1 left beside 222 KB of shared memory
 namespace par {
@@ -366,6 +370,11 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 	float* zs = reinterpret_cast<float*>(smem + kOffZs);
 	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmemSlot);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+	// The first leaf's voxels are requested before anything else: for a small host-pointer call they come from pinned
+	// host memory over PCIe (capi.cu: kZeroCopyLeaves), ~2 us away, and the setup below does not depend on them.
+	float4 v_first = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (tid < 128 && (int64_t)blockIdx.x < n_leaves) v_first = __ldcs(reinterpret_cast<const float4*>(leaves + (int64_t)blockIdx.x * 512) + tid);
 
 	// ---- one-time setup: zero the operand buffers (halo rows stay zero for the whole kernel), small tables ----
 	for (uint32_t i = tid; i < (kA8Bytes + kYBytes + kHBytes + 4096) / 16; i += kThreads)
@@ -685,13 +694,16 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			row_bar();
 		};
 		// (b) pre.0: Conv3d(1,16,k3) on FFMA, channels 4g..4g+3, + bias
-		auto front_pre0 = [&](float (&x)[5][4]) {
+		// kd taps [kd0, kd1) of the filter; the first part zeroes the accumulators, the last one adds the bias
+		auto front_pre0_part = [&](float (&x)[5][4], int kd0, int kd1) {
+			if (kd0 == 0) {
 #pragma unroll
-			for (int t = 0; t < 5; ++t)
+				for (int t = 0; t < 5; ++t)
 #pragma unroll
-				for (int c = 0; c < 4; ++c) x[t][c] = 0.f;
+					for (int c = 0; c < 4; ++c) x[t][c] = 0.f;
+			}
 #pragma unroll 1
-			for (int kd = 0; kd < 3; ++kd) {
+			for (int kd = kd0; kd < kd1; ++kd) {
 #pragma unroll
 				for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
@@ -708,13 +720,16 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 					}
 				}
 			}
+			if (kd1 == 3) {
 #pragma unroll
-			for (int c = 0; c < 4; ++c) {
-				const float b = sp_c[par::pre_b + g * 4 + c];
+				for (int c = 0; c < 4; ++c) {
+					const float b = sp_c[par::pre_b + g * 4 + c];
 #pragma unroll
-				for (int t = 0; t < 5; ++t) x[t][c] += b;
+					for (int t = 0; t < 5; ++t) x[t][c] += b;
+				}
 			}
 		};
+		auto front_pre0 = [&](float (&x)[5][4]) { front_pre0_part(x, 0, 3); };
 		// (c) pre.1: GroupNorm(4,16) + ReLU -> x (the residual, kept in registers)
 		auto front_gn_pre1 = [&](float (&x)[5][4]) {
 			float mean[1], rstd[1];  // this thread's 4 channels are exactly GroupNorm group g
@@ -755,9 +770,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 
 		float xn[5][4];  // x of the leaf whose front is in progress
 		if (my_leaves > 0) {
-			float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
-			if (tid < 128) v0 = __ldcs(reinterpret_cast<const float4*>(leaves + (int64_t)blockIdx.x * 512) + tid);
-			front_load(v0);
+			front_load(v_first);
 			front_pre0(xn);
 			front_gn_pre1(xn);
 			front_gn1_to_a8(xn, blockIdx.x);
@@ -820,6 +833,15 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			}
 			signal_a_ready(bars, lane);
 			lap(4);
+#if VQVDB_ENC_PRE0_SPLIT_AT > 0
+			// conv2's first tile group takes ~3 k cycles in which the row threads would only wait: stage the next leaf and
+			// run the first kPre0Split kd-slices of its pre.0 here; the rest runs under the `down` MMAs
+			if (has_next) {
+				front_load(nx_v);
+				front_pre0_part(xn, 0, kPre0Split);
+			}
+			lap(0);
+#endif
 
 			// ---- conv2 epilogue: x2 = x + 0.1 (conv2 + b) -> Y, the space-to-depth input of `down` ----
 			wait_conv_tile(rc, 0);
@@ -851,10 +873,14 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			}
 			signal_a_ready(bars, lane);
 			lap(6);
+#if VQVDB_ENC_PRE0_SPLIT_AT > 0
+			if (has_next && kPre0Split < 3) front_pre0_part(xn, kPre0Split, 3);
+#else
 			if (has_next) {  // the `down` MMAs run for ~6 k cycles: stage the next leaf and run its pre.0
 				front_load(nx_v);
 				front_pre0(xn);
 			}
+#endif
 			lap(0);
 
 			// ---- down epilogue: sum the accumulation chains, + bias -> x32 (residual, to shared memory) ; res32.gn1 + ReLU -> H32 ----
