@@ -157,8 +157,20 @@ class ValueAccessor {
 
 using FloatTree = tree::Tree<float>;
 
+class GridBase {
+   public:
+	using Ptr = std::shared_ptr<GridBase>;
+	using ConstPtr = std::shared_ptr<const GridBase>;
+	virtual ~GridBase() = default;
+	std::string getName() const { return name_; }
+	void setName(const std::string& n) { name_ = n; }
+
+   private:
+	std::string name_;
+};
+
 template <typename TreeT>
-class Grid {
+class Grid : public GridBase {
    public:
 	using Ptr = std::shared_ptr<Grid>;
 	using ConstPtr = std::shared_ptr<const Grid>;
@@ -166,8 +178,6 @@ class Grid {
 	using Accessor = tree::ValueAccessor<TreeT>;
 	explicit Grid(const typename TreeT::ValueType& background) : tree_(background), xform_(std::make_shared<math::Transform>()) {}
 	static Ptr create(const typename TreeT::ValueType& background = typename TreeT::ValueType()) { return std::make_shared<Grid>(background); }
-	std::string getName() const { return name_; }
-	void setName(const std::string& n) { name_ = n; }
 	const math::Transform& transform() const { return *xform_; }
 	void setTransform(math::Transform::Ptr t) { xform_ = std::move(t); }
 	TreeT& tree() { return tree_; }
@@ -177,9 +187,13 @@ class Grid {
    private:
 	TreeT tree_;
 	math::Transform::Ptr xform_;
-	std::string name_;
 };
 using FloatGrid = Grid<FloatTree>;
+
+template <typename GridType>
+inline typename GridType::Ptr gridPtrCast(const GridBase::Ptr& grid) { return std::dynamic_pointer_cast<GridType>(grid); }
+template <typename GridType>
+inline typename GridType::ConstPtr gridConstPtrCast(const GridBase::ConstPtr& grid) { return std::dynamic_pointer_cast<const GridType>(grid); }
 
 inline void initialize() {}
 

@@ -3,7 +3,7 @@
     compute-sanitizer --tool memcheck  python tools/sanitizer_run.py 300
     compute-sanitizer --tool racecheck python tools/sanitizer_run.py 300
 
-Also drives the encoder's near-tie path on every row (debug tap stage 5) and the unfolded N = 192 decoder."""
+Also drives the encoder near-tie path on every row (debug tap stage 5).  n <= 296 runs the decoder with one tile per CTA, larger n with two."""
 import os
 import sys
 

@@ -24,7 +24,8 @@ VQVAECodec::VQVAECodec(std::unique_ptr<IVQVAECodec> backend) : backend_(std::mov
 Tensor VQVAECodec::encodeBatch(const TensorView& cpuBatch) const { return backend_->encode(cpuBatch); }
 Tensor VQVAECodec::decodeBatch(const TensorView& cpuBatch) const { return backend_->decode(cpuBatch); }
 
-void VQVAECodec::compress(const std::vector<LeafGrid>& grids, const std::filesystem::path& outPath, size_t batchSize) const {
+void VQVAECodec::compress(const std::vector<LeafGrid>& grids, const std::filesystem::path& outPath, size_t batchSize,
+                          const InterruptFn& interrupted) const {
 	const auto t0 = std::chrono::steady_clock::now();
 	vqvdb::VqvdbWriter writer(outPath.string());
 	const auto* fast = dynamic_cast<const B200Backend*>(backend_.get());
@@ -46,6 +47,7 @@ void VQVAECodec::compress(const std::vector<LeafGrid>& grids, const std::filesys
 		writer.startGrid(meta);
 		const size_t step = batchSize ? batchSize : n;
 		for (size_t lo = 0; lo < n; lo += step) {
+			if (interrupted && interrupted()) throw std::runtime_error("Interrupted.");
 			const size_t cnt = std::min(step, n - lo);
 			const float* src = grid.voxels.data() + lo * kLeafVoxels;  // leaves are already contiguous: no per-batch copy
 			if (fast) {
@@ -66,7 +68,8 @@ void VQVAECodec::compress(const std::vector<LeafGrid>& grids, const std::filesys
 	std::printf("Grid Compression Complete: %zu leaves in %lld ms.\n", total, (long long)ms);
 }
 
-void VQVAECodec::decompress(const std::filesystem::path& inPath, std::vector<LeafGrid>& grids, size_t batchSize) const {
+void VQVAECodec::decompress(const std::filesystem::path& inPath, std::vector<LeafGrid>& grids, size_t batchSize,
+                            const InterruptFn& interrupted) const {
 	const auto t0 = std::chrono::steady_clock::now();
 	vqvdb::VqvdbReader reader(inPath.string());
 	grids.clear();
@@ -86,6 +89,7 @@ void VQVAECodec::decompress(const std::filesystem::path& inPath, std::vector<Lea
 		const size_t step = batchSize ? batchSize : std::max<size_t>(meta.totalBlocks, 1);
 		size_t done = 0;
 		while (reader.hasNext()) {
+			if (interrupted && interrupted()) throw std::runtime_error("Interrupted.");
 			const size_t cnt = reader.nextBatch(step, indices, origins);
 			if (cnt == 0) break;
 			float* dst = grid.voxels.data() + done * kLeafVoxels;  // decoded straight into the grid's storage

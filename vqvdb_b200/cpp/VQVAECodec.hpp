@@ -11,6 +11,7 @@
 #pragma once
 
 #include <filesystem>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -30,8 +31,16 @@ class VQVAECodec {
    public:
 	explicit VQVAECodec(std::unique_ptr<IVQVAECodec> backend);  // throws on nullptr (VQVAECodec.cpp:71-75)
 
-	void compress(const std::vector<LeafGrid>& grids, const std::filesystem::path& outPath, size_t batchSize) const;
-	void decompress(const std::filesystem::path& inPath, std::vector<LeafGrid>& grids, size_t batchSize) const;
+	// `interrupted` is polled between backend calls (the reference documents a Houdini interrupt handler for progress
+	// and cancellation on both entry points — VQVAECodec.hpp:38,47 — but never implemented it); a true return aborts
+	// with std::runtime_error("Interrupted.").  With batchSize 0 a grid is one backend call; callers that want to be
+	// interruptible inside a grid pass a batch size (kInterruptibleBatch is a good one: ~0.25 s of GPU work).
+	using InterruptFn = std::function<bool()>;
+	static constexpr size_t kInterruptibleBatch = size_t(1) << 20;
+	void compress(const std::vector<LeafGrid>& grids, const std::filesystem::path& outPath, size_t batchSize,
+	              const InterruptFn& interrupted = {}) const;
+	void decompress(const std::filesystem::path& inPath, std::vector<LeafGrid>& grids, size_t batchSize,
+	                const InterruptFn& interrupted = {}) const;
 
 	const IVQVAECodec& backend() const { return *backend_; }
 

@@ -104,17 +104,20 @@ inline openvdb::FloatGrid::Ptr toFloatGrid(const LeafGrid& lg, float background 
 }
 
 // The reference's entry points, on OpenVDB grids: compress a set of float grids to a .vqvdb v3 file / read one back.
-inline void compress(const VQVAECodec& codec, const std::vector<openvdb::FloatGrid::ConstPtr>& grids, const std::filesystem::path& outPath) {
+// batchSize 0 = the whole grid per backend call (the backend pipelines internally); `interrupted` as in VQVAECodec.hpp.
+inline void compress(const VQVAECodec& codec, const std::vector<openvdb::FloatGrid::ConstPtr>& grids, const std::filesystem::path& outPath,
+                     size_t batchSize = 0, const VQVAECodec::InterruptFn& interrupted = {}) {
 	std::vector<LeafGrid> flat;
 	flat.reserve(grids.size());
 	for (const auto& g : grids)
 		if (g) flat.push_back(toLeafGrid(*g));
-	codec.compress(flat, outPath, /*batchSize=*/0);  // the whole grid per backend call; the backend pipelines internally
+	codec.compress(flat, outPath, batchSize, interrupted);
 }
 
-inline std::vector<openvdb::FloatGrid::Ptr> decompress(const VQVAECodec& codec, const std::filesystem::path& inPath, float background = 0.0f) {
+inline std::vector<openvdb::FloatGrid::Ptr> decompress(const VQVAECodec& codec, const std::filesystem::path& inPath, float background = 0.0f,
+                                                        size_t batchSize = 0, const VQVAECodec::InterruptFn& interrupted = {}) {
 	std::vector<LeafGrid> flat;
-	codec.decompress(inPath, flat, /*batchSize=*/0);
+	codec.decompress(inPath, flat, batchSize, interrupted);
 	std::vector<openvdb::FloatGrid::Ptr> grids;
 	grids.reserve(flat.size());
 	for (const LeafGrid& lg : flat) grids.push_back(toFloatGrid(lg, background));

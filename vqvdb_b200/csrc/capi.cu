@@ -515,16 +515,18 @@ bool is_pinned_host(const void* p) {
 	return a.type == cudaMemoryTypeHost;
 }
 
-// Device-side alias of pinned host memory (cudaMallocHost / cudaHostRegister'd / torch pin_memory), or null.
+// Device-side alias of pinned host memory (cudaMallocHost / cudaHostRegister'd / torch pin_memory), or null for
+// pageable memory.  One attribute query, which is not an error for an unregistered pointer.
 template <class T>
 T* device_alias(T* host_ptr, size_t align) {
 	if (reinterpret_cast<uintptr_t>(host_ptr) & (align - 1)) return nullptr;
-	void* d = nullptr;
-	if (cudaHostGetDevicePointer(&d, const_cast<void*>(static_cast<const void*>(host_ptr)), 0) != cudaSuccess) {
+	cudaPointerAttributes a{};
+	if (cudaPointerGetAttributes(&a, host_ptr) != cudaSuccess) {
 		cudaGetLastError();
 		return nullptr;
 	}
-	return static_cast<T*>(d);
+	if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+	return static_cast<T*>(a.devicePointer);
 }
 
 int fail(vqvdb_b200_codec* c, int code, const std::string& msg) {
