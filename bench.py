@@ -47,10 +47,10 @@ BYTES_DECODE = 64 + 2048
 # is tied to the git blob hash of the kernel source it was captured from: a changed kernel reports traffic = null
 # ("stale") instead of a number that no longer describes it.
 NCU_DRAM = {
-    "encode": {"bytes_per_leaf": (122.509312e6 + 7.897856e6) / 59200, "source": "profiles/r1e_encode_tc_ncu_summary.txt",
-               "file": "vqvdb_b200/csrc/encode_tc.cu", "blob": "40b4d5f4a2a7a4f6d0d8c5c2e0a9a1b5b2f0f6a3"},
-    "decode": {"bytes_per_leaf": (5.050880e6 + 69.744896e6) / 59200, "source": "profiles/r1d_decode_tc2_ncu_summary.txt",
-               "file": "vqvdb_b200/csrc/decode_tc.cu", "blob": "0000000000000000000000000000000000000000"},
+    "encode": {"bytes_per_leaf": (122.270464e6 + 8.901888e6) / 59200, "source": "profiles/r2_encode_tc_ncu_summary.txt",
+               "file": "vqvdb_b200/csrc/encode_tc.cu", "blob": "6b9b558831a5f8f2c05ce28b0dd7e031a2afd782"},
+    "decode": {"bytes_per_leaf": (5.091584e6 + 64.778240e6) / 59200, "source": "profiles/r2_decode_tc_ncu_summary.txt",
+               "file": "vqvdb_b200/csrc/decode_tc.cu", "blob": "e8c2e6e6f19bd3bd43957df758d9210aa8b7e51c"},
 }
 
 
@@ -364,7 +364,7 @@ def main():
     if args.leaves is None:
         args.leaves = 500_000 if args.workload == "vec3" else 1_000_000
     if args.workload == "vec3":
-        args.ref_sample = min(args.ref_sample, 1024)   # 892 MFLOP per leaf on host cores
+        args.ref_sample = min(args.ref_sample, 256)    # 892 MFLOP per leaf on host cores (the C restatement runs ~20-80 leaves/s)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -500,33 +500,36 @@ def main():
     dec_ms = time_kernel(lambda: codec.decode_device(idx, L, vox, sp), K)
 
     # ---- end to end through the C-ABI with HOST buffers (pinned), H2D + D2H inside the timed region ----
-    hx = torch.empty((L, CH, 8, 8, 8), dtype=torch.float32, pin_memory=True)
-    hx.copy_(x)
-    hidx = torch.empty((L, 4, 4, 4), dtype=torch.uint8, pin_memory=True)
-    hvox = torch.empty((L, CH, 8, 8, 8), dtype=torch.float32, pin_memory=True)
+    # (a rank's share above 4 M leaves is measured on its first 4 M: 2 x 8 GB of pinned host memory is enough to be
+    # bandwidth-, not latency-bound, and a 10 M-leaf single-GPU run would otherwise pin 41 GB)
+    Le = min(L, 4_000_000)
+    hx = torch.empty((Le, CH, 8, 8, 8), dtype=torch.float32, pin_memory=True)
+    hx.copy_(x[:Le])
+    hidx = torch.empty((Le, 4, 4, 4), dtype=torch.uint8, pin_memory=True)
+    hvox = torch.empty((Le, CH, 8, 8, 8), dtype=torch.float32, pin_memory=True)
     torch.cuda.synchronize()
 
     for _ in range(2):
-        codec.encode_into(hx, L, hidx)
-        codec.decode_into(hidx, L, hvox)
+        codec.encode_into(hx, Le, hidx)
+        codec.decode_into(hidx, Le, hvox)
     barrier()
     t_enc = t_dec = 0.0
     t0 = time.perf_counter()
     for _ in range(K):
         ta = time.perf_counter()
-        codec.encode_into(hx, L, hidx)
+        codec.encode_into(hx, Le, hidx)
         tb = time.perf_counter()
-        codec.decode_into(hidx, L, hvox)
+        codec.decode_into(hidx, Le, hvox)
         t_enc += tb - ta
         t_dec += time.perf_counter() - tb
     barrier()
     e2e_s = time.perf_counter() - t0
-    e2e_checksum = float(hvox[:: max(1, L // 1024)].double().sum())
+    e2e_checksum = float(hvox[:: max(1, Le // 1024)].double().sum())
 
     # ---- what the links give when every rank copies at once (the host-fed ceiling on this box) ----
     link = None
     if not args.no_extras:
-        nbytes = min(L, 1 << 19) * CH * 2048
+        nbytes = min(Le, 1 << 19) * CH * 2048
         src_h, dst_d = hvox.view(-1)[: nbytes // 4], vox.view(-1)[: nbytes // 4]
         res = []
         for direction in ("h2d", "d2h"):
@@ -564,9 +567,9 @@ def main():
             from vqvdb_b200.hostlib import HostBackend
             hb = HostBackend(local)
             px = hx.numpy().copy()                    # pageable
-            pvox = np.empty((L, 1, 8, 8, 8), np.float32)
+            pvox = np.empty((Le, 1, 8, 8, 8), np.float32)
             pvox.fill(0)                              # pre-faulted, as a caller-owned grid buffer is
-            pidx = np.empty((L, 4, 4, 4), np.uint8)
+            pidx = np.empty((Le, 4, 4, 4), np.uint8)
             pidx.fill(0)
             hb.encode_into(px, pidx); hb.decode_into(pidx, pvox)        # warm-up (staging buffers, copy threads)
             reps = max(2, min(K, 5))
@@ -579,10 +582,10 @@ def main():
                 te += s_e; td += s_d
             tv = te + td
             same = bool(np.array_equal(iv, pidx))
-            pageable = {"value": L * reps / tv, "unit": "leaves/s",
+            pageable = {"value": Le * reps / tv, "unit": "leaves/s",
                         "api": "IVQVAECodec::encode/decode(TensorView over pageable memory) -> owning Tensor (libvqvdb_b200_host.so)",
-                        "encode_leaves_per_s": L * reps / te, "decode_leaves_per_s": L * reps / td,
-                        "into_value": L * reps / ti,
+                        "encode_leaves_per_s": Le * reps / te, "decode_leaves_per_s": Le * reps / td,
+                        "into_value": Le * reps / ti,
                         "into_api": "B200Backend::encodeInto/decodeInto on caller-owned pageable buffers (the batch loop's form: no Tensor allocation)",
                         "copy_threads": int(os.environ.get("VQVDB_B200_COPY_THREADS", "0")) or min(8, max(1, (os.cpu_count() or 2) // 2)),
                         "indices_equal_pinned_path": same,
@@ -597,12 +600,12 @@ def main():
     small = {}
     if rank == 0 and not args.no_extras:
         for nb in (64, 1024, 8192):
-            if nb >= L:
+            if nb >= Le:
                 continue
             reps = max(4, min(400, 131072 // nb))
             # raw addresses into the pinned buffers: the loop times the C-ABI calls, not Python tensor slicing
             ax, ai, av = hx.data_ptr(), hidx.data_ptr(), hvox.data_ptr()
-            offs = [(i * nb) % (L - nb) for i in range(reps)]
+            offs = [(i * nb) % (Le - nb) for i in range(reps)]
             for _ in range(3):
                 codec.encode_into(ax, nb, ai)
                 codec.decode_into(ai, nb, av)
@@ -692,12 +695,13 @@ def main():
                          "hbm_gbs_nonbinding": (bytes_dec if dom == "decode" else bytes_enc) * L / (dom_ms / 1e3) / 1e9,
                          "note": "compute-bound path (34 kFLOP/B); achieved = ALGORITHMIC flops / time; %s kernel runs on %s" % (dom, "tensor cores (the encoder issues 3 fp16 products per algorithmic MAC, see kernels.*.issued_tflops)" if dom_on_tensor else "fp32 FFMA (measured CUDA-core peak 71 TFLOP/s, so frac of ITS pipe is %.2f)" % (achieved / ffma_peak)),
                          "kernels": kernels},
-            "e2e": {"value": total * K / (e2e_ms / 1e3), "unit": "leaves/s",
-                    "h2d_bytes_per_step": L * (CH * 2048 + 64), "d2h_bytes_per_step": L * (64 + CH * 2048),
+            # every rank times the same number of leaves (Le = its share, capped at 4 M): whole-job rate = ranks x Le / time
+            "e2e": {"value": Le * world * K / (e2e_ms / 1e3), "unit": "leaves/s", "leaves_per_rank_per_step": Le,
+                    "h2d_bytes_per_step": Le * (CH * 2048 + 64), "d2h_bytes_per_step": Le * (64 + CH * 2048),
                     "api": "vqvdb_b200_encode + vqvdb_b200_decode on pinned host buffers", "checksum": e2e_checksum,
                     "encode_ms_per_step": e2e_enc_ms / K, "decode_ms_per_step": e2e_dec_ms / K,
-                    "h2d_gbs_per_rank_during_encode": L * CH * 2048 / (e2e_enc_ms / K / 1e3) / 1e9,
-                    "d2h_gbs_per_rank_during_decode": L * CH * 2048 / (e2e_dec_ms / K / 1e3) / 1e9,
+                    "h2d_gbs_per_rank_during_encode": Le * CH * 2048 / (e2e_enc_ms / K / 1e3) / 1e9,
+                    "d2h_gbs_per_rank_during_decode": Le * CH * 2048 / (e2e_dec_ms / K / 1e3) / 1e9,
                     "link": link},
             "parity": parity,
             "gpu_launches": launches,

@@ -38,3 +38,21 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["metric"] == "leaves_per_sec_encode_decode" and d["unit"] == "leaves/s"
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_ncu_traffic_is_tied_to_the_kernel_source():
+    # roofline.traffic comes from a committed ncu capture and must not outlive the kernel it was taken from
+    import bench
+    for k, e in bench.NCU_DRAM.items():
+        assert os.path.exists(os.path.join(REPO, e["source"])) and len(e["blob"]) == 40
+        traffic, why = bench.ncu_traffic(k, 1000)
+        if bench.git_blob_hash(e["file"]) == e["blob"]:
+            assert traffic == e["bytes_per_leaf"] * 1000 and why == e["source"]
+        else:
+            assert traffic is None and why.startswith("stale")
+    saved = dict(bench.NCU_DRAM["encode"])
+    try:
+        bench.NCU_DRAM["encode"]["blob"] = "0" * 40
+        assert bench.ncu_traffic("encode", 1000)[0] is None
+    finally:
+        bench.NCU_DRAM["encode"].update(saved)

@@ -22,7 +22,7 @@ for _ in range(2):
 torch.cuda.synchronize()
 p = prof.cpu().numpy()
 leaves = n / 148.0
-names = ["stage next leaf (+ clear Y)", "pre.0 FFMA + GN pre.1", "gn1 + split -> A8", "wait conv1 MMA", "conv1 epilogue: normalise, split, store",
+names = ["stage next leaf + its pre.0 (inside the conv2 MMA wait)", "GN pre.1 of the next leaf", "gn1 + split -> A8", "wait conv1 MMA", "conv1 epilogue: normalise, split, store",
          "wait conv2 MMA", "conv2 epilogue (residual, -> Y)", "wait down MMA", "down epilogue (GN, -> H32)", "wait res32.c1 MMA",
          "res32.c1 epilogue", "wait res32.c2 MMA", "res32.c2 epilogue + attention", "  conv1 epilogue: accumulator reads (incl. wait for tile group 2)", "  conv1 epilogue: GroupNorm statistics",
          "wait VQ MMA", "VQ scores -> bounds, two smallest", "VQ decision (+ near-tie rows: z, shortlist, exact re-scoring)", "clear Y"]
@@ -30,8 +30,8 @@ tot = 0.0
 for i, nm in enumerate(names):
     c = p[:, i].mean() / leaves
     tot += c
-    print("%-36s %8.0f cyc/leaf" % (nm, c))
-print("%-36s %8.0f cyc/leaf" % ("row thread total", tot))
+    print("%-58s %8.0f cyc/leaf" % (nm, c))
+print("%-58s %8.0f cyc/leaf" % ("row thread total", tot))
 print("issuer: wait a_ready %.0f  wait w_full %.0f  issue+commit %.0f  total %.0f cyc/leaf" % tuple(p[:, 32 + i].mean() / leaves for i in range(4)))
 print("issuer weight waits by phase: 8^3 convs %.0f  down %.0f  4^3 convs %.0f  VQ %.0f cyc/leaf" % tuple(p[:, 36 + i].mean() / leaves for i in range(4)))
 print("issuer, operands ready -> layer's MMAs complete: 8^3 convs (2) %.0f  down %.0f  4^3 convs (2) %.0f  VQ %.0f cyc/leaf" % tuple(p[:, 40 + i].mean() / leaves for i in range(4)))

@@ -30,7 +30,7 @@ units = groups * upg
 w = p[:, :512, :]
 iss = p[:, 512:576:32, :]
 print("%s: groups per CTA: %.0f (4 leaves each, %d units)" % (prec, groups, upg))
-print("worker per unit: wait a_empty %.0f  stage %.0f  | wait d_full per group (7 passes) %.0f" % (
+print("worker per unit: wait a_empty %.0f  stage %.0f  | wait d_full per group (4 layers) %.0f" % (
     w[..., 0].mean() / units, w[..., 1].mean() / units, w[..., 2].mean() / groups))
 print("issuer per unit: wait w_full %.0f  wait a_full %.0f  issue %.0f  total %.0f" % (
     iss[..., 0].mean() / units, iss[..., 1].mean() / units, iss[..., 2].mean() / units, iss[..., 3].mean() / units))
