@@ -554,7 +554,12 @@ def main():
         if world > 1:
             dist.all_reduce(lmin, op=dist.ReduceOp.MIN)
             dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
-        link = {"unit": "GB/s", "h2d_per_rank_min": float(lmin[0]), "d2h_per_rank_min": float(lmin[1]),
+        # what host feeding allows on this box: a step cannot be shorter than its kernels, nor than its 2 KB/leaf transfers
+        # at the rate every rank gets when all ranks copy at once
+        t_enc_floor = max(enc_ms / 1e3 * Le / L, Le * CH * 2048 / (float(lmin[0]) * 1e9))
+        t_dec_floor = max(dec_ms / 1e3 * Le / L, Le * CH * 2048 / (float(lmin[1]) * 1e9))
+        link = {"unit": "GB/s", "host_fed_ceiling_leaves_per_s": Le * world / (t_enc_floor + t_dec_floor),
+                "h2d_per_rank_min": float(lmin[0]), "d2h_per_rank_min": float(lmin[1]),
                 "h2d_all_ranks": float(lsum[0]), "d2h_all_ranks": float(lsum[1]),
                 "host_memcpy_per_rank_min": float(lmin[2]), "host_memcpy_all_ranks": float(lsum[2]),
                 "note": "pinned-memory cudaMemcpyAsync of %.2f GB and a host memcpy, every rank at the same time" % (nbytes / 1e9)}

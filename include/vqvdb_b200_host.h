@@ -63,6 +63,12 @@ VQVDB_HOST_API const void* vqvdb_host_backend_result(const vqvdb_host_backend* b
 VQVDB_HOST_API int vqvdb_host_backend_encode_into(vqvdb_host_backend* b, const float* leaves, int64_t n_leaves, uint8_t* indices_out, double* seconds);
 VQVDB_HOST_API int vqvdb_host_backend_decode_into(vqvdb_host_backend* b, const uint8_t* indices, int64_t n_leaves, float* voxels_out, double* seconds);
 
+/* Constructs the orchestrator (VQVAECodec) over a B200 backend whose CodecConfig::source is the weight pack at
+ * `pack_path` (NULL or "" = the embedded model) and destroys it again: 0 if it would accept the model, -1 with the
+ * message otherwise.  compress / decompress size every buffer as 512 floats per leaf (FloatGrid only, like the
+ * reference: VQVAECodec.hpp:40,49), so a 3-channel model is refused at construction. */
+VQVDB_HOST_API int vqvdb_host_orchestrator_accepts(int cuda_device, const char* pack_path);
+
 VQVDB_HOST_API const char* vqvdb_host_last_error(void);
 
 #ifdef __cplusplus

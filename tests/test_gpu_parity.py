@@ -154,6 +154,21 @@ def test_wrong_dtype_raises(codec):
         codec.decode(TensorView(x, [2, 4, 4, 4], DataType.FLOAT32))
 
 
+def test_wrong_shape_or_size_raises(codec):
+    # a view whose shape does not match the model, or whose array is shorter than the shape claims, must not reach the kernels
+    from vqvdb_b200 import DataType, TensorView
+    x = synth.kat_leaves(4)
+    with pytest.raises(RuntimeError, match="expected shape"):
+        codec.encode(TensorView(x, [4, 3, 8, 8, 8], DataType.FLOAT32))
+    with pytest.raises(RuntimeError, match="float32 array"):
+        codec.encode(TensorView(x[:2], [4, 1, 8, 8, 8], DataType.FLOAT32))
+    idx = np.zeros((4, 4, 4, 4), np.uint8)
+    with pytest.raises(RuntimeError, match="expected shape"):
+        codec.decode(TensorView(idx, [4, 8, 8], DataType.UINT8))
+    with pytest.raises(RuntimeError, match="uint8 array"):
+        codec.decode(TensorView(idx[:1], [4, 4, 4, 4], DataType.UINT8))
+
+
 def test_device_pointer_api_matches_host_api(codec):
     import torch
     x = synth.smoke_leaves(600, seed=9)

@@ -254,3 +254,45 @@ def test_compress_decompress_fog_sphere_through_host_layer(tmp_path):
     assert np.abs(out.voxels[:len(g["recon"])][same_idx] - g["recon"][same_idx]).max() <= 2e-5
     out_tc = hostlib.decompress(p, batch_size=100)[0]
     assert synth.psnr(out_tc.voxels, out.voxels) >= 55.0
+
+
+@pytest.mark.gpu
+def test_orchestrator_refuses_a_three_channel_model():
+    """compress / decompress are FloatGrid-only (512 floats per leaf, like the reference: VQVAECodec.hpp:40,49); a vec3
+    weight pack behind the backend must be refused when the orchestrator is built, not overflow a buffer later."""
+    import sys
+    L = hostlib.load_host_library()
+    pack = os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw")
+    if not os.path.exists(pack):
+        subprocess.check_call([sys.executable, os.path.join(REPO, "tools", "weights_pack.py"), "vec3"], stdout=subprocess.DEVNULL)
+    assert L.vqvdb_host_orchestrator_accepts(0, None) == 0
+    assert L.vqvdb_host_orchestrator_accepts(0, os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_float.vqw").encode()) == 0
+    assert L.vqvdb_host_orchestrator_accepts(0, pack.encode()) == -1
+    assert b"1-channel" in L.vqvdb_host_last_error()
+
+
+@pytest.mark.gpu
+def test_backend_virtuals_on_pageable_memory_match_the_pointer_api():
+    """IVQVAECodec::encode/decode through the C++ backend (TensorView over pageable numpy memory -> owning Tensor whose
+    buffer is filled without a zero-fill pass) against the C-ABI called directly; also wrong shapes are refused."""
+    from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec, synth
+    x = synth.smoke_leaves(5000, seed=8)                 # > 2048: the chunked pipeline with threaded staging
+    hb = hostlib.HostBackend(0)
+    try:
+        idx, _ = hb.encode(x)
+        idx = np.array(idx)
+        rec, _ = hb.decode(idx)
+        rec = np.array(rec)
+        small_idx, _ = hb.encode(x[:64])                  # <= 2048: the zero-copy path on staged pageable memory
+        assert np.array_equal(np.array(small_idx), idx[:64])
+    finally:
+        hb.close()
+    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA), BackendType.B200)
+    try:
+        idx2 = np.empty((5000, 4, 4, 4), np.uint8)
+        rec2 = np.empty((5000, 1, 8, 8, 8), np.float32)
+        c.encode_into(x, 5000, idx2)
+        c.decode_into(idx2, 5000, rec2)
+    finally:
+        c.close()
+    assert np.array_equal(idx, idx2) and np.array_equal(rec, rec2)

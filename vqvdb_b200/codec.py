@@ -258,6 +258,12 @@ class B200Codec:
             raise RuntimeError("encode expects FLOAT32 data.")     # TorchBackend.cpp:134-136
         x = leafBatch.data
         n = int(leafBatch.shape[0])
+        # the raw pointer is all the C ABI sees: shape, dtype and size are checked here (the reference builds a torch
+        # tensor from the view's shape and fails cleanly on a mismatch, TorchBackend.cpp:141-149)
+        if list(leafBatch.shape[1:]) != [self.channels, 8, 8, 8]:
+            raise RuntimeError("encode: expected shape [B,%d,8,8,8], got %s" % (self.channels, list(leafBatch.shape)))
+        if not isinstance(x, np.ndarray) or x.dtype != np.float32 or x.size != n * self.channels * 512:
+            raise RuntimeError("encode: data must be a float32 array of %d elements" % (n * self.channels * 512))
         out = np.empty((n, *self._latent), dtype=np.uint8)
         self.encode_into(x, n, out)
         return Tensor(out, list(out.shape), DataType.UINT8)
@@ -266,6 +272,10 @@ class B200Codec:
         if indices.dtype != DataType.UINT8:
             raise RuntimeError("decode expects UINT8 data.")       # TorchBackend.cpp:167-169
         n = int(indices.shape[0])
+        if list(indices.shape[1:]) != self._latent:
+            raise RuntimeError("decode: expected shape [B,%d,%d,%d], got %s" % (*self._latent, list(indices.shape)))
+        if not isinstance(indices.data, np.ndarray) or indices.data.dtype != np.uint8 or indices.data.size != n * 64:
+            raise RuntimeError("decode: data must be a uint8 array of %d elements" % (n * 64))
         out = np.empty((n, self.channels, 8, 8, 8), dtype=np.float32)
         self.decode_into(indices.data, n, out)
         return Tensor(out, list(out.shape), DataType.FLOAT32)

@@ -221,4 +221,18 @@ int vqvdb_host_backend_decode_into(vqvdb_host_backend* b, const uint8_t* indices
 	return timed(seconds, [&] { static_cast<const B200Backend&>(*b->codec).decodeInto(indices, n, voxels_out); });
 }
 
+int vqvdb_host_orchestrator_accepts(int cuda_device, const char* pack_path) {
+	try {
+		CodecConfig cfg;
+		cfg.device = CodecConfig::Device::CUDA;
+		if (pack_path && pack_path[0]) cfg.source = std::filesystem::path(pack_path);
+		B200Options opt = B200Backend::defaultOptions();
+		opt.cudaDevice = cuda_device;
+		VQVAECodec codec(std::make_unique<B200Backend>(cfg, opt));
+		return 0;
+	} catch (const std::exception& e) {
+		return fail(e);
+	}
+}
+
 }  // extern "C"

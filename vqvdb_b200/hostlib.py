@@ -18,6 +18,7 @@ HOST_EXPORTS = [
     "vqvdb_host_compress", "vqvdb_host_decompress", "vqvdb_host_last_error",
     "vqvdb_host_backend_create", "vqvdb_host_backend_destroy", "vqvdb_host_backend_encode", "vqvdb_host_backend_decode",
     "vqvdb_host_backend_result", "vqvdb_host_backend_encode_into", "vqvdb_host_backend_decode_into",
+    "vqvdb_host_orchestrator_accepts",
 ]
 
 _lib = None
@@ -52,6 +53,7 @@ def load_host_library() -> C.CDLL:
             getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
         for fn in ("vqvdb_host_backend_encode_into", "vqvdb_host_backend_decode_into"):
             getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_double)]
+        L.vqvdb_host_orchestrator_accepts.argtypes = [C.c_int, C.c_char_p]
         L.vqvdb_host_backend_result.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.vqvdb_host_backend_result.restype = C.c_void_p
         _lib = L
