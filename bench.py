@@ -40,6 +40,8 @@ FLOP_DECODE = 114.14e6
 FLOP_DECODE_FOLDED = (128 * 64 + 3 * 64 * 64) * 27 * 64 * 2.0
 FLOP_VEC3_ENCODE = 488.72e6 + 4.19e6
 FLOP_VEC3_DECODE = 399.03e6
+# vec3 decoder with the folded tail (decode_tc128.cuh): five 128 -> 128 convs + three 128 -> 64 tail convs on the 4^3 grid
+FLOP_VEC3_DECODE_FOLDED = (5 * 128 * 128 + 3 * 128 * 64) * 27 * 64 * 2.0
 BYTES_ENCODE = 2048 + 64
 BYTES_DECODE = 64 + 2048
 
@@ -643,7 +645,7 @@ def main():
         enc_tf = flop_enc * L / (enc_ms / 1e3) / 1e12
         dec_tf = flop_dec * L / (dec_ms / 1e3) / 1e12
         dec_peak = peak if dec_tc else ffma_peak
-        dec_issued_flop = FLOP_DECODE_FOLDED if codec.decode_path.endswith("_fold") else flop_dec
+        dec_issued_flop = ((FLOP_VEC3_DECODE_FOLDED if vec3 else FLOP_DECODE_FOLDED) if codec.decode_path.endswith("_fold") else flop_dec)
         dec_issued_tf = dec_issued_flop * L / (dec_ms / 1e3) / 1e12
         # tensor-core encoder: every GEMM is three fp16 products (hi*hi, hi*lo, lo*hi); pre.0 (221 184 MAC) stays on FFMA and
         # proj (262 144 MAC) is folded into the codebook, whose score GEMM shrinks from 64x128x256 to 64x32x256 (524 288 MAC):
@@ -653,7 +655,7 @@ def main():
         if (dom == "encode" and enc_tc) or (dom == "decode" and codec.decode_path == "bf16_tcgen05_n192_fold"):
             traffic, traffic_source = ncu_traffic(dom, L)
         enc_name = "encode_tc_kernel" if enc_tc else ("generic_encode_kernel" if vec3 else "encode_fp32_kernel")
-        dec_name = "decode_tc_kernel" if dec_tc else ("generic_decode_kernel" if vec3 else "decode_fp32_kernel")
+        dec_name = ("decode_tc128_kernel" if vec3 else "decode_tc_kernel") if dec_tc else ("generic_decode_kernel" if vec3 else "decode_fp32_kernel")
         kernels = {
             enc_name: {
                 "ms": enc_ms, "share_of_step": enc_ms / (enc_ms + dec_ms), "achieved_tflops": enc_tf,

@@ -139,11 +139,13 @@ VQVDB_B200_API int vqvdb_b200_peer_buffer_close(vqvdb_b200_codec* codec, void* d
 
 /* Kernel launches issued by this codec since creation (bench.py's gpu_launches). */
 VQVDB_B200_API uint64_t vqvdb_b200_kernel_launches(const vqvdb_b200_codec* codec);
-/* Name of the decode path actually in use: "bf16_tcgen05_n192_fold", "fp32", or "fp32_generic" (vec3 model). */
+/* Name of the decode path actually in use: "bf16_tcgen05_n192_fold" (float model), "bf16_tcgen05_c128_fold" (the vec3
+ * model's 128-channel decoder), "fp32", or "fp32_generic" (vec3 model with VQVDB_B200_DECODE_FP32). */
 VQVDB_B200_API const char* vqvdb_b200_decode_path(const vqvdb_b200_codec* codec);
 
-/* Bring-up aid for the tensor-core decoder: runs it and also writes the fp32 activation after stage
- * {0: stem+GroupNorm+ReLU, 1: residual block, 2: channel attention} as [n][64 ch][64 pos] to dev_tap. */
+/* Bring-up aid for the tensor-core decoders: runs one and also writes the fp32 activation after stage
+ * {0: stem+GroupNorm+ReLU, 1: residual block(s), 2: channel attention} as [n][64 ch][64 pos] (float model) or
+ * [n][128 ch][64 pos] (vec3 model) to dev_tap. */
 VQVDB_B200_API int vqvdb_b200_debug_decode_tap(vqvdb_b200_codec* codec, const uint8_t* dev_indices, int64_t n_leaves,
                                                int stage, float* dev_tap, float* dev_voxels, void* cuda_stream);
 

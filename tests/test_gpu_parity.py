@@ -88,7 +88,10 @@ def test_parity_report_bounds():
             if path != "fp32":
                 assert r["psnr_db_vs_reference_recon"] >= 55.0, (path, name, r)
     for name, r in rep["vec3"].items():
-        assert r["max_reference_margin_at_mismatch"] <= 1e-4 and r["max_abs_diff"] <= 5e-5, (name, r)
+        assert r["max_reference_margin_at_mismatch"] <= 1e-4, (name, r)
+        assert r["decode"]["fp32_generic"]["max_abs_diff"] <= 5e-5, (name, r)
+        tc = r["decode"]["bf16_tcgen05_c128_fold"]
+        assert tc["max_abs_diff"] <= 4e-2 and tc["psnr_db_vs_reference_recon"] >= 55.0, (name, r)
 
 
 @pytest.mark.parametrize("name", ["kat256", "smoke1024_seed0", "sparse1024_seed1", "fogsphere64", "zeros4"])
@@ -279,10 +282,82 @@ def codec_vec3():
     pack = os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw")
     if not os.path.exists(pack):
         subprocess.check_call([sys.executable, os.path.join(REPO, "tools", "weights_pack.py"), "vec3"])
-    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack), BackendType.B200)
-    assert c is not None and c.channels == 3
+    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack, decode_precision="fp32"), BackendType.B200)
+    assert c is not None and c.channels == 3 and c.decode_path == "fp32_generic"
     yield c
     c.close()
+
+
+@pytest.fixture(scope="module")
+def codec_vec3_tc():
+    """The vec3 model on its default paths: generic fp32 encoder, 128-channel tensor-core decoder (decode_tc128.cu)."""
+    import os
+    import subprocess
+    import sys
+    from conftest import REPO
+    from vqvdb_b200 import BackendType, CodecConfig, IVQVAECodec
+    pack = os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw")
+    if not os.path.exists(pack):
+        subprocess.check_call([sys.executable, os.path.join(REPO, "tools", "weights_pack.py"), "vec3"])
+    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack), BackendType.B200)
+    assert c is not None and c.channels == 3 and c.decode_path == "bf16_tcgen05_c128_fold"
+    yield c
+    c.close()
+
+
+# Tolerance of the bf16 tensor-core vec3 decoder, stated here: tanh outputs in (-1, 1), i.e. twice the float model's range:
+#   PSNR(recon_tc, recon_reference; peak 2) >= 55 dB, max |d| <= 4e-2, and the roundtrip PSNR within 0.1 dB of the reference's.
+VEC3_TC_MAX_ABS = 4e-2
+
+
+def _psnr_peak2(a, b):
+    mse = float(((a.astype(np.float64) - b.astype(np.float64)) ** 2).mean())
+    return 10.0 * np.log10(4.0 / max(mse, 1e-30))
+
+
+@pytest.mark.parametrize("stage", [0, 1, 2])
+def test_vec3_tc_decoder_stage_taps_match_oracle(codec_vec3_tc, stage):
+    import os
+    import torch
+    from conftest import REPO
+    from oracle.pyoracle import COracle
+    o = COracle(os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw"))
+    idx = golden("vec3_sparse1024_seed7")["indices"][:37]            # odd count: the last group has a spare leaf slot
+    want = o.decode_tap(idx, stage, width=128)                        # [n,128,4,4,4] fp32
+    idx_d = torch.from_numpy(idx).cuda()
+    tap_d = torch.zeros((37, 128, 64), dtype=torch.float32, device="cuda")
+    vox_d = torch.empty((37, 3, 8, 8, 8), dtype=torch.float32, device="cuda")
+    codec_vec3_tc.debug_decode_tap(idx_d, 37, stage, tap_d, vox_d, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = tap_d.cpu().numpy().reshape(want.shape)
+    scale = float(np.abs(want).max())
+    err = float(np.abs(got - want).max())
+    assert err <= 0.03 * scale, "stage %d: max err %.4g vs activation scale %.4g" % (stage, err, scale)
+
+
+@pytest.mark.parametrize("name", ["vec3_smoke256_seed5", "vec3_noise64_seed6", "vec3_sparse1024_seed7"])
+def test_vec3_tc_decode_within_tolerance(codec_vec3_tc, name):
+    g = golden(name)
+    m = len(g["recon"])
+    rec = _decode(codec_vec3_tc, g["indices"][:m])
+    assert rec.shape == (m, 3, 8, 8, 8) and np.isfinite(rec).all()
+    assert np.abs(rec - g["recon"]).max() <= VEC3_TC_MAX_ABS
+    assert _psnr_peak2(rec, g["recon"]) >= TC_MIN_PSNR_VS_REF
+
+
+def test_vec3_tc_decode_against_fp32_path_ragged_and_deterministic(codec_vec3_tc, codec_vec3):
+    idx = golden("vec3_sparse1024_seed7")["indices"]
+    full = _decode(codec_vec3_tc, idx)                                # 1024 leaves: 512 groups over 148 CTAs
+    ref32 = _decode(codec_vec3, idx[:300])
+    assert np.abs(full[:300] - ref32).max() <= VEC3_TC_MAX_ABS and _psnr_peak2(full[:300], ref32) >= TC_MIN_PSNR_VS_REF
+    for n in (1, 2, 3, 295, 297):                                      # odd counts leave a spare leaf slot in the last group
+        assert np.array_equal(_decode(codec_vec3_tc, idx[:n]), full[:n])
+    assert np.array_equal(_decode(codec_vec3_tc, idx), full)
+    x = synth.smoke_leaves(64, seed=5, channels=3)
+    rt = _decode(codec_vec3_tc, _encode(codec_vec3_tc, x))            # roundtrip PSNR against the reference's own roundtrip
+    gref = golden("vec3_smoke256_seed5")
+    d = abs(_psnr_peak2(x[:32], rt[:32]) - _psnr_peak2(x[:32], gref["recon"]))
+    assert d <= 0.1, "roundtrip PSNR differs from the reference by %.4f dB" % d
 
 
 @pytest.mark.parametrize("name,gen", [("vec3_smoke256_seed5", lambda: synth.smoke_leaves(256, seed=5, channels=3)),
@@ -313,7 +388,7 @@ def test_vec3_matches_c_oracle_and_chunking(codec_vec3):
     idx = _encode(codec_vec3, x)
     assert_indices_match(idx, idx_o, margins)
     assert np.abs(_decode(codec_vec3, idx_o[:24]) - o.decode(idx_o[:24])).max() <= 5e-5
-    small = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack, chunk_leaves=20), BackendType.B200)
+    small = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack, chunk_leaves=20, decode_precision="fp32"), BackendType.B200)
     try:
         assert np.array_equal(_encode(small, x), idx)           # 5 chunks through 3 slots share no scratch
         assert np.array_equal(_decode(small, idx), _decode(codec_vec3, idx))

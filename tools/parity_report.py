@@ -80,15 +80,20 @@ def main():
         c.close()
     pack = os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw")
     if os.path.exists(pack):
-        c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack), BackendType.B200)
-        for name, gen in VEC3_CASES.items():
-            g = golden(name)
-            row = index_row(enc(c, gen()), g)
-            m = len(g["recon"])
-            row.update(recon_row(dec(c, g["indices"][:m]), g["recon"]))
-            row["paths"] = [c.encode_path, c.decode_path]
-            rep["vec3"][name] = row
-        c.close()
+        for prec in ("default", "fp32"):
+            c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack, decode_precision=prec), BackendType.B200)
+            for name, gen in VEC3_CASES.items():
+                g = golden(name)
+                m = len(g["recon"])
+                rr = recon_row(dec(c, g["indices"][:m]), g["recon"])
+                rr["psnr_db_vs_reference_recon"] += 20.0 * np.log10(2.0)   # tanh outputs span (-1, 1): peak 2
+                if prec == "default":
+                    row = index_row(enc(c, gen()), g)
+                    row["encode_path"] = c.encode_path
+                    row["decode"] = {}
+                    rep["vec3"][name] = row
+                rep["vec3"][name]["decode"][c.decode_path] = rr
+            c.close()
     worst = max(r["mismatch_frac"] for p in rep["encode"].values() for n, r in p.items() if r["latents"] >= 4096)
     rep["summary"] = {
         "kat256_mismatches": {p: r["kat256"]["mismatches"] for p, r in rep["encode"].items()},

@@ -19,7 +19,20 @@ ap.add_argument("--leaves", type=int, default=59200)   # 148 SMs x 400
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--decode-precision", default="default")
 ap.add_argument("--encode-precision", default="default")
+ap.add_argument("--vec3-decode", action="store_true", help="profile the vec3 model's decode_tc128_kernel instead (random indices)")
 a = ap.parse_args()
+if a.vec3_decode:
+    pack = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw")
+    codec = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack), BackendType.B200)
+    assert codec is not None and codec.decode_path == "bf16_tcgen05_c128_fold"
+    idx = torch.randint(0, 256, (a.leaves, 4, 4, 4), dtype=torch.uint8, device="cuda")
+    vox = torch.empty((a.leaves, 3, 8, 8, 8), dtype=torch.float32, device="cuda")
+    for _ in range(a.iters):
+        codec.decode_device(idx, a.leaves, vox, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    print("profiled %d vec3 leaves x %d iters, decode path %s" % (a.leaves, a.iters, codec.decode_path))
+    codec.close()
+    sys.exit(0)
 dev = torch.device("cuda", 0)
 codec = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, decode_precision=a.decode_precision, encode_precision=a.encode_precision), BackendType.B200)
 assert codec is not None

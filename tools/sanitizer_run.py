@@ -28,3 +28,13 @@ for dec in ("default",):
         torch.cuda.synchronize()
         print("forced exact path: indices equal", bool((idx_d.cpu().numpy() == idx).all()))
     c.close()
+
+# the vec3 model's 128-channel tensor-core decoder (decode_tc128.cu), odd leaf count (a spare leaf slot in the last group)
+pack = os.path.join(os.getcwd(), "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw")
+if os.path.exists(pack):
+    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack), BackendType.B200)
+    m = min(n, 75)
+    vidx = np.random.default_rng(3).integers(0, 256, size=(m, 4, 4, 4), dtype=np.uint8)
+    vrec = c.decode(TensorView(vidx, list(vidx.shape), DataType.UINT8)).buffer
+    print(c.decode_path, float(vrec.sum()))
+    c.close()

@@ -21,6 +21,7 @@
 
 #include "../../include/vqvdb_b200.h"
 #include "decode_tc.cuh"
+#include "decode_tc128.cuh"
 #include "encode_tc.cuh"
 #include "generic_model.cuh"
 #include "model.cuh"
@@ -160,6 +161,9 @@ struct vqvdb_b200_codec {
 	bool generic = false;            // architecture-generic kernels (vec3 model) instead of the specialised ones
 	vqvdb::GenericModel gen{};
 	float* gen_scratch = nullptr;
+	bool dec128 = false;             // the 128-channel tensor-core decoder (decode_tc128.cu) serves this model's decode
+	uint8_t* dec128_arena = nullptr;  // its bf16 unit stream, bf16 codebook and fp32 parameter block
+	vqvdb::Decoder128Weights dec128_w{};
 	int gen_grid = 0;
 	vqvdb::EncoderWeights enc{};
 	vqvdb::EncoderUnits enc_units{};
@@ -187,6 +191,7 @@ struct vqvdb_b200_codec {
 		if (mma_arena) cudaFree(mma_arena);
 		if (enc_tc_arena) cudaFree(enc_tc_arena);
 		if (gen_scratch) cudaFree(gen_scratch);
+		if (dec128_arena) cudaFree(dec128_arena);
 	}
 };
 
@@ -488,6 +493,23 @@ void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
 	// one scratch area per pipeline slot plus one for the device-pointer entry points (slot index kSlots)
 	CUDA_TRY(cudaMalloc(&c.gen_scratch, (kSlots + 1) * vqvdb::generic_scratch_floats(c.gen_grid) * sizeof(float)));
 	c.generic = true;
+	// the reference's vec3 decoder (128 channels, two residual blocks) has a tensor-core path of its own
+	if (vqvdb::decoder128_supports(p)) {
+		const std::vector<uint8_t> units = vqvdb::build_decoder128_units(p);
+		const std::vector<uint16_t> cb = vqvdb::build_codebook_bf16(p);
+		const std::vector<float> par = vqvdb::build_decoder128_params(p);
+		const size_t off_cb = units.size(), off_par = (off_cb + cb.size() * 2 + 255) & ~size_t(255);
+		CUDA_TRY(cudaMalloc(&c.dec128_arena, off_par + par.size() * sizeof(float)));
+		CUDA_TRY(cudaMemcpy(c.dec128_arena, units.data(), units.size(), cudaMemcpyHostToDevice));
+		CUDA_TRY(cudaMemcpy(c.dec128_arena + off_cb, cb.data(), cb.size() * 2, cudaMemcpyHostToDevice));
+		CUDA_TRY(cudaMemcpy(c.dec128_arena + off_par, par.data(), par.size() * sizeof(float), cudaMemcpyHostToDevice));
+		c.dec128_w.units = c.dec128_arena;
+		c.dec128_w.emb_bf16 = reinterpret_cast<const __nv_bfloat16*>(c.dec128_arena + off_cb);
+		c.dec128_w.par = reinterpret_cast<const float*>(c.dec128_arena + off_par);
+		c.dec128_w.fc0 = m.d_fc0;
+		c.dec128_w.fc2 = m.d_fc2;
+		c.dec128 = true;
+	}
 }
 
 void ensure_staging(vqvdb_b200_codec& c) {
@@ -554,6 +576,11 @@ void launch_encode(vqvdb_b200_codec& c, const float* d_leaves, int64_t n, uint8_
 }
 
 void launch_decode(vqvdb_b200_codec& c, const uint8_t* d_idx, int64_t n, float* d_vox, cudaStream_t st, int slot = kSlots) {
+	if (c.generic && c.dec128 && c.decode_kind == 2) {
+		CUDA_TRY(vqvdb::launch_decode_tc128(c.dec128_w, d_idx, n, d_vox, c.num_sms, st));
+		if (n > 0) c.launches.fetch_add(1, std::memory_order_relaxed);
+		return;
+	}
 	if (c.generic) {
 		float* scratch = c.gen_scratch + (size_t)slot * vqvdb::generic_scratch_floats(c.gen_grid);
 		CUDA_TRY(vqvdb::launch_decode_generic(c.gen, d_idx, n, d_vox, scratch, c.gen_grid, st));
@@ -642,12 +669,13 @@ int vqvdb_b200_create(const vqvdb_b200_config* cfg, vqvdb_b200_codec** out) {
 			return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "unknown encode_precision");
 		c->encode_kind = conf.encode_precision == VQVDB_B200_ENCODE_DEFAULT ? (int)VQVDB_B200_ENCODE_DEFAULT_KIND : (int)conf.encode_precision;
 		c->encode_path = c->generic ? "fp32_generic" : c->encode_kind == 2 ? "fp16x2_tcgen05" : "fp32";
-		c->decode_path = c->generic ? "fp32_generic" : c->decode_kind == 2 ? "bf16_tcgen05_n192_fold" : "fp32";
+		c->decode_path = c->generic ? (c->dec128 && c->decode_kind == 2 ? "bf16_tcgen05_c128_fold" : "fp32_generic") : c->decode_kind == 2 ? "bf16_tcgen05_n192_fold" : "fp32";
 		CUDA_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
 		CUDA_TRY(vqvdb::configure_encode_fp32());
 		CUDA_TRY(vqvdb::configure_encode_tc());
 		CUDA_TRY(vqvdb::configure_decode_fp32());
 		CUDA_TRY(vqvdb::configure_decode_tc());
+		CUDA_TRY(vqvdb::configure_decode_tc128());
 	} catch (const std::exception& e) {
 		return translate(nullptr, e);
 	}
@@ -816,10 +844,11 @@ int vqvdb_b200_debug_decode_tap(vqvdb_b200_codec* c, const uint8_t* dev_indices,
 	if (!c) return VQVDB_B200_ERR_INVALID_ARGUMENT;
 	if (n < 0 || stage < 0 || (stage > 2 && stage != 100) || (n > 0 && (!dev_indices || !dev_tap || !dev_voxels)))
 		return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "debug_decode_tap: bad arguments");
-	if (c->generic) return fail(c, VQVDB_B200_ERR_UNSUPPORTED, "debug_decode_tap: float model only");
+	if (c->generic && !c->dec128) return fail(c, VQVDB_B200_ERR_UNSUPPORTED, "debug_decode_tap: no tensor-core decoder for this model");
 	try {
 		CUDA_TRY(cudaSetDevice(c->device));
-		CUDA_TRY(vqvdb::launch_decode_tc(c->dec_mma, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
+		if (c->generic) CUDA_TRY(vqvdb::launch_decode_tc128(c->dec128_w, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
+		else CUDA_TRY(vqvdb::launch_decode_tc(c->dec_mma, dev_indices, n, dev_voxels, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
 	} catch (const std::exception& e) {
 		return translate(c, e);
 	}
