@@ -542,14 +542,22 @@ def test_full_size_roundtrip_properties(c_oracle):
         diff = (idx != idx2).reshape(FULL_N, -1)
         n_diff = int(diff.sum())
         print("full size: %d of %d latents differ between the tcgen05 and the FFMA encoder" % (n_diff, FULL_N * 64))
-        assert n_diff <= 64e6 * 5e-5
-        bad_leaves = torch.nonzero(diff.any(dim=1)).flatten()[:256].cpu().numpy()
-        # (2) the oracle on a strided sample + every leaf where the two encoders differ
-        sample = np.unique(np.concatenate([np.arange(0, FULL_N, FULL_N // 2048), bad_leaves]))
-        xs = x[torch.from_numpy(sample).cuda()].cpu().numpy()
+        assert n_diff <= 1800                            # 3x the measured 578 (9e-6 of the latents)
+        bad_leaves = torch.nonzero(diff.any(dim=1)).flatten()[:1024].cpu().numpy()   # every disagreeing leaf goes to the oracle
+        # (2) the oracle on a strided sample (unbiased: the usual mismatch-fraction bound applies) ...
+        strided = np.arange(0, FULL_N, FULL_N // 2048)
+        xs = x[torch.from_numpy(strided).cuda()].cpu().numpy()
         idx_o, margins = c_oracle.encode(xs, with_margins=True)
-        assert_indices_match(idx[torch.from_numpy(sample).cuda()].cpu().numpy(), idx_o, margins)
-        assert_indices_match(idx2[torch.from_numpy(sample).cuda()].cpu().numpy(), idx_o, margins)
+        assert_indices_match(idx[torch.from_numpy(strided).cuda()].cpu().numpy(), idx_o, margins)
+        assert_indices_match(idx2[torch.from_numpy(strided).cuda()].cpu().numpy(), idx_o, margins)
+        # ... and on EVERY leaf where the two encoders differ (a sample made of near-ties: only the margin rule applies —
+        # each mismatch against the oracle must sit at a latent whose own fp32 top-2 margin is <= 1e-4)
+        sample = np.unique(np.concatenate([strided, bad_leaves]))
+        if len(bad_leaves):
+            xb = x[torch.from_numpy(bad_leaves).cuda()].cpu().numpy()
+            idx_b, margins_b = c_oracle.encode(xb, with_margins=True)
+            assert_indices_match(idx[torch.from_numpy(bad_leaves).cuda()].cpu().numpy(), idx_b, margins_b, max_frac=1.0)
+            assert_indices_match(idx2[torch.from_numpy(bad_leaves).cuda()].cpu().numpy(), idx_b, margins_b, max_frac=1.0)
         # (3) determinism and split invariance of the encoder at full size
         fast.encode_device(x[:500_003], 500_003, idx2[:500_003], sp)
         fast.encode_device(x[500_003:], FULL_N - 500_003, idx2[500_003:], sp)

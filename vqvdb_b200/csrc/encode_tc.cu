@@ -104,9 +104,19 @@ constexpr uint32_t kOffPar = kOffCb + 3088;                     // fold_norm has
 constexpr uint32_t kOffXq = kOffPar + 1008 * 4;                 // `down` epilogue: lane-0 values handed to the previous quadrant [4][4][8]
 constexpr uint32_t kOffBar = kOffXq + 512;                      // mbarriers
 constexpr int kConvGroups = kEncTcConvGroups;                   // tile groups of an 8^3 conv, each with its own completion barrier
-constexpr uint32_t kNumBars = 2 * kStages + 3 + kConvGroups;
+constexpr uint32_t kNumBars = 2 * kStages + 3 + kConvGroups + 1;  // ... + the leaf-staging barrier
 constexpr uint32_t kOffTmemSlot = kOffBar + kNumBars * 8;
-constexpr uint32_t kSmemBytes = kOffTmemSlot + 16;
+// Leaf staging.  Default (0): 128 row threads issue one coalesced 128-bit ld.global.cs each for the NEXT leaf at the top of a
+// leaf's loop and scatter the registers into the haloed fp32 buffer pre.0 reads when its turn comes.  VQVDB_ENC_LEAF_TMA=1:
+// the producer warp requests the next leaf (2 KB, one cp.async.bulk) into a staging buffer and the row threads pick it up
+// with 128-bit shared loads.  Both are built and give identical indices; measured on 592 k leaves the TMA form is 2 %
+// slower (6.38 M vs 6.51 M leaves/s, profiles/r2_encode_experiments.txt) — the copy is 2 KB per 45 k cycles, nothing a bulk
+// engine can speed up, and it adds a barrier wait and a shared-memory round trip to the row threads' critical path.
+#ifndef VQVDB_ENC_LEAF_TMA
+#define VQVDB_ENC_LEAF_TMA 0
+#endif
+constexpr uint32_t kOffLeafStage = (kOffTmemSlot + 16 + 15) & ~15u;
+constexpr uint32_t kSmemBytes = kOffLeafStage + 2048;
 static_assert(kOffXh + kXhBytes <= kOffY + kYBytes && kOffXh % 16 == 0, "the VQ overlays fit inside the Y region");
 static_assert(kSmemBytes <= 227 * 1024, "encode_tc smem budget");
 static_assert(kOffBar % 8 == 0 && kOffA8 % 1024 == 0 && kOffY % 1024 == 0 && kOffH % 1024 == 0, "alignment");
@@ -120,6 +130,7 @@ __device__ __forceinline__ uint32_t bar_a_ready(uint32_t bars) { return bars + 2
 // wait — so every group has its own barrier (two phases per leaf: conv1, conv2).
 __device__ __forceinline__ uint32_t bar_d_full(uint32_t bars, uint32_t which) { return bars + (2 * kStages + 1 + which) * 8; }
 __device__ __forceinline__ uint32_t bar_d8_full(uint32_t bars, uint32_t group) { return bars + (2 * kStages + 3 + group) * 8; }
+__device__ __forceinline__ uint32_t bar_leaf(uint32_t bars) { return bars + (2 * kStages + 3 + kConvGroups) * 8; }
 
 // ---- tcgen05 wrappers ----
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -373,8 +384,20 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 
 	// The first leaf's voxels are requested before anything else: for a small host-pointer call they come from pinned
 	// host memory over PCIe (capi.cu: kZeroCopyLeaves), ~2 us away, and the setup below does not depend on them.
+#if VQVDB_ENC_LEAF_TMA
+	const uint32_t leaf_stage = s_base + kOffLeafStage;
+	if (warp == kProducerWarp && lane == 0) {  // this thread owns the staging barrier: nobody else touches it before the block-wide sync below
+		mbar_init(bar_leaf(bars), 1);
+		mbar_fence_init();
+		if ((int64_t)blockIdx.x < n_leaves) {
+			mbar_arrive_expect_tx(bar_leaf(bars), 2048);
+			tma_load_1d(leaf_stage, leaves + (int64_t)blockIdx.x * 512, 2048, bar_leaf(bars));
+		}
+	}
+#else
 	float4 v_first = make_float4(0.f, 0.f, 0.f, 0.f);
 	if (tid < 128 && (int64_t)blockIdx.x < n_leaves) v_first = __ldcs(reinterpret_cast<const float4*>(leaves + (int64_t)blockIdx.x * 512) + tid);
+#endif
 
 	// ---- one-time setup: zero the operand buffers (halo rows stay zero for the whole kernel), small tables ----
 	for (uint32_t i = tid; i < (kA8Bytes + kYBytes + kHBytes + 4096) / 16; i += kThreads)
@@ -438,6 +461,18 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			for (uint32_t issued = 0; issued < total; ++issued) {
 				const uint32_t s = issued % kStages, u = issued % kEncTcUnits;
 				mbar_wait(bar_w_empty(bars, s), ((issued / kStages) & 1u) ^ 1u);
+#if VQVDB_ENC_LEAF_TMA
+				if (u == kStages) {
+					// Request this CTA's next leaf.  The staging buffer still holds the current leaf until its front has read it;
+					// the ring slot of unit kStages was just released by the MMAs of this leaf's unit 0, and a leaf's first MMA
+					// starts only after its front (load, pre.0, GroupNorms) is complete.
+					const int64_t nxt = (int64_t)(issued / kEncTcUnits) + 1;
+					if (nxt < my_leaves) {
+						mbar_arrive_expect_tx(bar_leaf(bars), 2048);
+						tma_load_1d(leaf_stage, leaves + ((int64_t)blockIdx.x + nxt * gridDim.x) * 512, 2048, bar_leaf(bars));
+					}
+				}
+#endif
 				mbar_arrive_expect_tx(bar_w_full(bars, s), ws.bytes[u]);
 				tma_load_1d(ring + s * kStageBytes, ws.units + ws.off[u], ws.bytes[u], bar_w_full(bars, s));
 			}
@@ -685,8 +720,16 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 
 		// ---- the front of a leaf, software-pipelined into the MMA waits of the previous leaf ----
 		// (a) stage the leaf (2048 B, 128-bit coalesced) into the haloed fp32 buffer
+#if VQVDB_ENC_LEAF_TMA
+		auto front_load = [&](int64_t ordinal) {  // ordinal = index of the leaf among this CTA's leaves
+			if (tid < 128) {
+				mbar_wait(bar_leaf(bars), (uint32_t)ordinal & 1u);
+				float4 v;
+				asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(leaf_stage + (uint32_t)tid * 16));
+#else
 		auto front_load = [&](const float4& v) {
 			if (tid < 128) {
+#endif
 				const int p = tid * 4, d = p >> 6, h = (p >> 3) & 7, w0 = p & 7;
 				float* dst = in_halo + (d + 1) * 100 + (h + 1) * 10 + w0 + 1;
 				dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
@@ -770,7 +813,11 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 
 		float xn[5][4];  // x of the leaf whose front is in progress
 		if (my_leaves > 0) {
+#if VQVDB_ENC_LEAF_TMA
+			front_load(0);
+#else
 			front_load(v_first);
+#endif
 			front_pre0(xn);
 			front_gn_pre1(xn);
 			front_gn1_to_a8(xn, blockIdx.x);
@@ -782,8 +829,10 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 		for (int64_t it = 0; it < my_leaves; ++it) {
 			const int64_t leaf = blockIdx.x + it * gridDim.x;
 			const bool has_next = it + 1 < my_leaves;
+#if !VQVDB_ENC_LEAF_TMA
 			float4 nx_v = make_float4(0.f, 0.f, 0.f, 0.f);  // the next leaf's voxels: in flight while this leaf's 8^3 layers run
 			if (has_next && tid < 128) nx_v = __ldcs(reinterpret_cast<const float4*>(leaves + (leaf + gridDim.x) * 512) + tid);
+#endif
 			float xr[5][4];
 #pragma unroll
 			for (int t = 0; t < 5; ++t)
@@ -837,7 +886,11 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			// conv2's first tile group takes ~3 k cycles in which the row threads would only wait: stage the next leaf and
 			// run the first kPre0Split kd-slices of its pre.0 here; the rest runs under the `down` MMAs
 			if (has_next) {
+#if VQVDB_ENC_LEAF_TMA
+				front_load(it + 1);
+#else
 				front_load(nx_v);
+#endif
 				front_pre0_part(xn, 0, kPre0Split);
 			}
 			lap(0);
@@ -877,7 +930,11 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			if (has_next && kPre0Split < 3) front_pre0_part(xn, kPre0Split, 3);
 #else
 			if (has_next) {  // the `down` MMAs run for ~6 k cycles: stage the next leaf and run its pre.0
+#if VQVDB_ENC_LEAF_TMA
+				front_load(it + 1);
+#else
 				front_load(nx_v);
+#endif
 				front_pre0(xn);
 			}
 #endif
