@@ -49,7 +49,7 @@ constexpr int kRowWarps = 4 * kGroups;            // 16
 constexpr int kRowThreads = 32 * kRowWarps;       // 512
 constexpr int kIssuerWarp = kRowWarps, kProducerWarp = kRowWarps + 1;
 constexpr int kThreads = kRowThreads + 64;        // + MMA issuer warp + TMA producer warp
-constexpr int kStages = 3;
+constexpr int kStages = kEncTcRingStages;
 constexpr uint32_t kStageBytes = kEncTcStageBytes;
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 constexpr int kDownChains = 4;                    // independent accumulators of `down` (see the issuer)
@@ -527,6 +527,12 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				}
 				return ring + s * kStageBytes;
 			};
+			auto wait_w_ahead = [&](uint32_t ahead) -> uint32_t {  // the unit `ahead` positions after the current one
+				const uint32_t un = unit + ahead, s = un % kStages;
+				mbar_wait(bar_w_full(bars, s), (un / kStages) & 1u);
+				tc_fence_after();
+				return ring + s * kStageBytes;
+			};
 			auto commit_d = [&]() {
 				if (leader) tc_commit(bar_d_full(bars, d_commits & 1u));
 				if (kProf) {  // the issuer has nothing to do before the row threads have read this result anyway
@@ -588,15 +594,17 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				w_phase = 1;
 				wait_a();
 #pragma unroll 1
-				for (int u = 0; u < 8; ++u) {  // u = (td, th) tap pair * 2 + half of the parity classes
+				constexpr int kPclPerUnit = 32 / kEncTcDownUnits;  // parity classes per weight unit: 4 (8 units) or 2 (16 units)
+#pragma unroll 1
+				for (int u = 0; u < kEncTcDownUnits; ++u) {  // u = (td, th) tap pair * units per pair + slice of the parity classes
 					const uint32_t wb = wait_w();
 					const long long c0 = prof_clock<kProf>();
-					const int pair = u >> 1, half = u & 1;
+					const int pair = u / (kEncTcDownUnits / 4), half = u % (kEncTcDownUnits / 4);
 					const int s = (pair >> 1) * 25 + (pair & 1) * 5;
 					const uint32_t dcol = tmem + (uint32_t)pair * 128;
 #pragma unroll
-					for (int pcl = 0; pcl < 4; ++pcl) {
-						const uint64_t ad = y_d + (uint64_t)(s + (half * 4 + pcl) * 2 * (int)(kYPlane >> 4));
+					for (int pcl = 0; pcl < kPclPerUnit; ++pcl) {
+						const uint64_t ad = y_d + (uint64_t)(s + (half * kPclPerUnit + pcl) * 2 * (int)(kYPlane >> 4));
 						const uint64_t bd = make_desc(wb + pcl * 4096, 128 * 16, 128);
 						if (leader) mma_ss(dcol, ad, bd, idesc_f16(128), (half > 0 || pcl > 0) ? 1u : 0u);
 						if (leader) mma_ss(dcol + 64, ad + (kYPrec >> 4), bd, idesc_f16(64), 1u);
@@ -642,13 +650,15 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 #pragma unroll 1
 				for (int ks = 0; ks < 2; ++ks) {
 					const uint32_t wb = wait_w();
+					const uint32_t wl = kEncTcVqUnits == 2 ? wb + 8192 : wait_w_ahead(1);  // M_lo: second half of the unit, or the next unit
 					const long long c0 = prof_clock<kProf>();
 					const uint64_t ad = xh_d + (uint64_t)(ks * 2 * (int)(kXhPlane >> 4));
-					const uint64_t bh = make_desc(wb, 256 * 16, 128), bl = make_desc(wb + 8192, 256 * 16, 128);
+					const uint64_t bh = make_desc(wb, 256 * 16, 128), bl = make_desc(wl, 256 * 16, 128);
 					if (leader) mma_ss(tmem, ad, bh, idesc_f16(256), ks > 0 ? 1u : 0u);
 					if (leader) mma_ss(tmem + 256, ad, bl, idesc_f16(256), ks > 0 ? 1u : 0u);
 					if (leader) mma_ss(tmem + 256, ad + (kXhPrec >> 4), bh, idesc_f16(256), 1u);
 					release_w();
+					if (kEncTcVqUnits == 4) release_w();
 					if (kProf) {
 								const long long dt = prof_clock<kProf>() - c0;
 								t_issue += dt;

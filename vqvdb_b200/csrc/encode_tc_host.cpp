@@ -137,12 +137,13 @@ std::vector<uint8_t> build_encoder_tc_units(const WeightPack& p, EncoderTcStream
 	// The two tw taps of a (td, th) pair are concatenated along N; one unit = 4 of the 8 parity classes of a pair.
 	{
 		const float* w = p.get("encoder.down.weight").data;
+		constexpr int kPerUnit = 8 / (kEncTcDownUnits / 4);  // parity classes per unit: 4, or 2 with the four-stage ring
 		for (int pair = 0; pair < 4; ++pair) {
 			const int td = pair >> 1, th = pair & 1;
-			for (int half = 0; half < 2; ++half) {
-				uint8_t* u = begin_unit(4 * 4096);
-				for (int pcl = 0; pcl < 4; ++pcl) {
-					const int pc = half * 4 + pcl, rd = pc >> 2, rh = (pc >> 1) & 1, rw = pc & 1;
+			for (int half = 0; half < 8 / kPerUnit; ++half) {
+				uint8_t* u = begin_unit(kPerUnit * 4096);
+				for (int pcl = 0; pcl < kPerUnit; ++pcl) {
+					const int pc = half * kPerUnit + pcl, rd = pc >> 2, rh = (pc >> 1) & 1, rw = pc & 1;
 					for (int part = 0; part < 2; ++part)
 						for (int tw = 0; tw < 2; ++tw) {
 							const int kd = 2 * td + rd, kh = 2 * th + rh, kw = 2 * tw + rw;
@@ -175,10 +176,12 @@ std::vector<uint8_t> build_encoder_tc_units(const WeightPack& p, EncoderTcStream
 		std::vector<float> m, esq, mno;
 		build_encoder_vq_fold(p, m, esq, mno);
 		for (int ks = 0; ks < 2; ++ks) {
-			uint8_t* u = begin_unit(2 * 8192);
-			for (int part = 0; part < 2; ++part)
+			uint8_t* u = kEncTcVqUnits == 2 ? begin_unit(2 * 8192) : nullptr;
+			for (int part = 0; part < 2; ++part) {
+				uint8_t* blk = kEncTcVqUnits == 2 ? u + part * 8192 : begin_unit(8192);  // four-stage ring: M_hi and M_lo are units of their own
 				for (int code = 0; code < 256; ++code)
-					for (int k = 0; k < 16; ++k) put(u + part * 8192, 256, code, k, split_part(m[code * 32 + ks * 16 + k], part));
+					for (int k = 0; k < 16; ++k) put(blk, 256, code, k, split_part(m[code * 32 + ks * 16 + k], part));
+			}
 		}
 	}
 	if (nu != kEncTcUnits) throw std::logic_error("encoder tc unit count mismatch");

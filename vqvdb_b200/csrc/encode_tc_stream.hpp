@@ -16,10 +16,10 @@ namespace vqvdb {
 //                         GROUP of the conv (kEncTcConvGroups groups of the five 128-row tiles, each with its own
 //                         completion signal, so a group's epilogue overlaps the next group's MMAs); the table entries of
 //                         the later groups alias the bytes of the first
-//   down                : 8 units (2x2x2-tap space-to-depth form; one per (td, th) tap pair and half of the 8 input
-//                         parity classes) = 4 parity classes x [2][128][16 B], n = part*64 + tw*32 + cout
+//   down                : 16 units (2x2x2-tap space-to-depth form; one per (td, th) tap pair and quarter of the 8 input
+//                         parity classes) = 2 parity classes x [2][128][16 B], n = part*64 + tw*32 + cout
 //   res32 conv1 / conv2 : 9 units each (one per (kd, kh)) = 2 k-steps x [2][192][16 B], n = part*96 + kw*32 + cout
-//   proj x codebook     : 2 units (one per 16-channel k-step) = [2][256][16 B] M_hi then [2][256][16 B] M_lo, n = code
+//   proj x codebook     : 4 units (M_hi, M_lo per 16-channel k-step), each [2][256][16 B], n = code
 // (part 0 = w_hi, part 1 = w_lo).
 //
 // proj (1x1 conv, 32 -> 128) feeds nothing but the codebook distances, and z.e_k = (W x + b).e_k = x.(W^T e_k) + b.e_k, so
@@ -41,8 +41,19 @@ static_assert(kEncTcConvGroups == 2 || kEncTcConvGroups == 3 || kEncTcConvGroups
 constexpr int enc_tc_group_first(int g) {
 	return kEncTcConvGroups == 5 ? g : kEncTcConvGroups == 3 ? (g * 2 < 5 ? g * 2 : 5) : (g == 0 ? 0 : g == 1 ? 3 : 5);
 }
-constexpr int kEncTcUnits = 2 * 3 * kEncTcConvGroups + 8 + 18 + 2;
-constexpr uint32_t kEncTcStageBytes = 16384;
+// Ring geometry.  VQVDB_ENC_RING4 = 0: three 16 KB stages (`down` as 8 units of 4 parity classes, the VQ as 2 units of
+// M_hi + M_lo); = 1: four 12 KB stages — one more unit in flight for the 9 KB / 12 KB units of the 3x3x3 convs, whose ~300-cycle
+// units outrun an L2 round trip with three stages — with `down` cut into 16 units of 2 parity classes and the VQ into 4
+// units (M_hi, M_lo per k-step).
+// Measured (592 k leaves): three stages 6.520 M leaves/s, four stages 6.585 M (profiles/r2_encode_experiments.txt).
+#ifndef VQVDB_ENC_RING4
+#define VQVDB_ENC_RING4 1
+#endif
+constexpr int kEncTcRingStages = VQVDB_ENC_RING4 ? 4 : 3;
+constexpr uint32_t kEncTcStageBytes = VQVDB_ENC_RING4 ? 12288 : 16384;
+constexpr int kEncTcDownUnits = VQVDB_ENC_RING4 ? 16 : 8;
+constexpr int kEncTcVqUnits = VQVDB_ENC_RING4 ? 4 : 2;
+constexpr int kEncTcUnits = 2 * 3 * kEncTcConvGroups + kEncTcDownUnits + 18 + kEncTcVqUnits;
 
 struct EncoderTcStream {
 	const uint8_t* units;            // device pointer, 16-byte aligned
