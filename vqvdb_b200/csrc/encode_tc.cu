@@ -13,7 +13,7 @@
 // Machine mapping
 //   * one leaf per CTA pass.  16 "row" warps: warp = g * 4 + quadrant owns TMEM lanes quadrant * 32 .. + 31 (one GEMM
 //     row per lane and 128-row tile) and channel group g of 4 (4 of 16 channels at 8^3, 8 of 32 at 4^3, 32 of the
-//     128 latent dims, 64 of the 256 codes).  One elected thread issues every tcgen05.mma; one more streams weights by TMA.
+//     128 latent dims, 64 of the 256 codes).  One warp issues every tcgen05.mma through an elected lane; one thread streams weights by TMA.
 //   * im2col is never materialised and nothing is gathered: activations live in shared memory FLATTENED with zero
 //     halos — 8^3: q = d*72 + h*8 + w (a ninth all-zero row block per d slab, zero slabs around the leaf);
 //     4^3: q = d*20 + h*4 + w; the stride-2 conv in its space-to-depth form (2x2x2 taps over a 5^3 grid of 8 parity
@@ -31,8 +31,8 @@
 //     (K = 32 instead of 128 + the proj GEMM), with a rigorous error bound, then — only for rows whose shortlist holds
 //     more than one code (near-ties, ~1 % of the rows) — z = W x + b in fp32 and exact re-scoring with the reference's
 //     formula and tie-break: the two-stage scheme of encode_fp32.cu with a 500x tighter first stage.
-//   * weights (548 KB per leaf as fp16 hi/lo planes, L2-resident) stream through a 3 x 16 KB shared-memory ring as
-//     40 units by 1-D TMA bulk copies; ring slots are released by tcgen05.commit.
+//   * weights (548 KB per leaf as fp16 hi/lo planes, L2-resident) stream through a 4 x 12 KB shared-memory ring as
+//     50 units by 1-D TMA bulk copies; ring slots are released by tcgen05.commit.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
