@@ -23,6 +23,7 @@
 #include "decode_tc.cuh"
 #include "decode_tc128.cuh"
 #include "encode_tc.cuh"
+#include "encode_tc128.cuh"
 #include "generic_model.cuh"
 #include "model.cuh"
 #include "weights.hpp"
@@ -43,6 +44,12 @@ struct CudaError : std::runtime_error {
 	} while (0)
 
 constexpr int kSlots = 3;                   // pipeline depth of the host-pointer calls
+#ifdef VQVDB_ENC128_GENERIC_FRONT
+constexpr bool kEnc128GenericFront = true;   // bring-up aid: the 8^3 stage on the fp32 generic kernel
+#else
+constexpr bool kEnc128GenericFront = false;
+#endif
+constexpr int64_t kEnc128Batch = 4096;        // leaves per front/back kernel pair of the vec3 encoder (128 MiB handed over)
 constexpr uint32_t kDefaultChunk = 16384;   // leaves per chunk: 32 MiB of voxels, 1 MiB of indices
 // Calls of at most this many leaves (the reference's SOPs hand over 64 at a time by default, 1024 / 8192 at most:
 // SOP_VQVDB_Encoder.cpp:36, SOP_VQVDB_Decoder.cpp:32) skip the copy engines: the kernel reads its input from, and
@@ -165,6 +172,12 @@ struct vqvdb_b200_codec {
 	uint8_t* dec128_arena = nullptr;  // its bf16 unit stream, bf16 codebook and fp32 parameter block
 	vqvdb::Decoder128Weights dec128_w{};
 	int gen_grid = 0;
+	bool enc128 = false;             // the tensor-core vec3 encoder (encode_tc128.cu) serves this model's encode
+	uint8_t* enc128_arena = nullptr;  // its fp16 hi/lo unit streams, transposed codebook and fp32 parameter blocks
+	float* enc128_y = nullptr;        // per pipeline slot: the stride-2 conv's output of one batch of leaves
+	vqvdb::Encoder128BackWeights enc128_back{};
+	vqvdb::Encoder128FrontWeights enc128_front{};
+	float* enc128_scratch = nullptr;  // per pipeline slot: the front kernel's per-CTA fp32 scratch
 	vqvdb::EncoderWeights enc{};
 	vqvdb::EncoderUnits enc_units{};
 	vqvdb::DecoderWeights dec{};
@@ -192,6 +205,9 @@ struct vqvdb_b200_codec {
 		if (enc_tc_arena) cudaFree(enc_tc_arena);
 		if (gen_scratch) cudaFree(gen_scratch);
 		if (dec128_arena) cudaFree(dec128_arena);
+		if (enc128_arena) cudaFree(enc128_arena);
+		if (enc128_y) cudaFree(enc128_y);
+		if (enc128_scratch) cudaFree(enc128_scratch);
 	}
 };
 
@@ -510,6 +526,35 @@ void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
 		c.dec128_w.fc2 = m.d_fc2;
 		c.dec128 = true;
 	}
+	// ... and so has its encoder (64 / 128 channels, one + two residual blocks)
+	if (vqvdb::encoder128_supports(p)) {
+		const std::vector<uint8_t> back = vqvdb::build_encoder128_back_units(p);
+		const std::vector<float> back_par = vqvdb::build_encoder128_back_params(p);
+		const std::vector<float> emb_t = vqvdb::build_embedding_transposed(p);
+		const std::vector<uint8_t> front = vqvdb::build_encoder128_front_units(p);
+		const std::vector<float> front_par = vqvdb::build_encoder128_front_params(p);
+		const size_t off_par = back.size(), off_emb = (off_par + back_par.size() * sizeof(float) + 255) & ~size_t(255);
+		const size_t off_front = (off_emb + emb_t.size() * sizeof(float) + 1023) & ~size_t(1023), off_fpar = off_front + front.size();
+		CUDA_TRY(cudaMalloc(&c.enc128_arena, off_fpar + front_par.size() * sizeof(float)));
+		CUDA_TRY(cudaMemcpy(c.enc128_arena + off_front, front.data(), front.size(), cudaMemcpyHostToDevice));
+		CUDA_TRY(cudaMemcpy(c.enc128_arena + off_fpar, front_par.data(), front_par.size() * sizeof(float), cudaMemcpyHostToDevice));
+		CUDA_TRY(cudaMalloc(&c.enc128_scratch, (size_t)(kSlots + 1) * vqvdb::encode_tc128_front_scratch_floats(c.num_sms) * sizeof(float)));
+		c.enc128_front.units = c.enc128_arena + off_front;
+		c.enc128_front.par = reinterpret_cast<const float*>(c.enc128_arena + off_fpar);
+		c.enc128_front.pre_wt = m.e_pre_w;
+		CUDA_TRY(cudaMemcpy(c.enc128_arena, back.data(), back.size(), cudaMemcpyHostToDevice));
+		CUDA_TRY(cudaMemcpy(c.enc128_arena + off_par, back_par.data(), back_par.size() * sizeof(float), cudaMemcpyHostToDevice));
+		CUDA_TRY(cudaMemcpy(c.enc128_arena + off_emb, emb_t.data(), emb_t.size() * sizeof(float), cudaMemcpyHostToDevice));
+		CUDA_TRY(cudaMalloc(&c.enc128_y, (size_t)(kSlots + 1) * kEnc128Batch * 8192 * sizeof(float)));
+		c.enc128_back.units = c.enc128_arena;
+		c.enc128_back.par = reinterpret_cast<const float*>(c.enc128_arena + off_par);
+		c.enc128_back.fc0 = m.e_fc0;
+		c.enc128_back.fc2 = m.e_fc2;
+		c.enc128_back.proj_wt = m.e_proj_w;
+		c.enc128_back.emb_t = reinterpret_cast<const float*>(c.enc128_arena + off_emb);
+		c.enc128_back.emb_sq = m.emb_sq;
+		c.enc128 = true;
+	}
 }
 
 void ensure_staging(vqvdb_b200_codec& c) {
@@ -564,6 +609,21 @@ int translate(vqvdb_b200_codec* c, const std::exception& e) {
 }
 
 void launch_encode(vqvdb_b200_codec& c, const float* d_leaves, int64_t n, uint8_t* d_idx, cudaStream_t st, int slot = kSlots) {
+	if (c.generic && c.enc128 && c.encode_kind == 2) {
+		// two kernels per batch of leaves, the stride-2 conv's output (32 KB per leaf) handed over in global memory
+		float* scratch = c.enc128_scratch + (size_t)slot * vqvdb::encode_tc128_front_scratch_floats(c.num_sms);
+		float* y = c.enc128_y + (size_t)slot * kEnc128Batch * 8192;
+		for (int64_t first = 0; first < n; first += kEnc128Batch) {
+			const int64_t nb = std::min<int64_t>(kEnc128Batch, n - first);
+			if (kEnc128GenericFront) {
+				float* gscratch = c.gen_scratch + (size_t)slot * vqvdb::generic_scratch_floats(c.gen_grid);
+				CUDA_TRY(vqvdb::launch_encode_generic_front(c.gen, d_leaves + first * 1536, nb, y, gscratch, c.gen_grid, st));
+			} else CUDA_TRY(vqvdb::launch_encode_tc128_front(c.enc128_front, d_leaves + first * 1536, nb, y, scratch, c.num_sms, st));
+			CUDA_TRY(vqvdb::launch_encode_tc128_back(c.enc128_back, y, nb, d_idx + first * 64, c.num_sms, st));
+			c.launches.fetch_add(2, std::memory_order_relaxed);
+		}
+		return;
+	}
 	if (c.generic) {
 		float* scratch = c.gen_scratch + (size_t)slot * vqvdb::generic_scratch_floats(c.gen_grid);
 		CUDA_TRY(vqvdb::launch_encode_generic(c.gen, d_leaves, n, d_idx, scratch, c.gen_grid, st));
@@ -668,7 +728,7 @@ int vqvdb_b200_create(const vqvdb_b200_config* cfg, vqvdb_b200_codec** out) {
 		if (conf.encode_precision > VQVDB_B200_ENCODE_FP16X2_TC)
 			return fail(nullptr, VQVDB_B200_ERR_INVALID_ARGUMENT, "unknown encode_precision");
 		c->encode_kind = conf.encode_precision == VQVDB_B200_ENCODE_DEFAULT ? (int)VQVDB_B200_ENCODE_DEFAULT_KIND : (int)conf.encode_precision;
-		c->encode_path = c->generic ? "fp32_generic" : c->encode_kind == 2 ? "fp16x2_tcgen05" : "fp32";
+		c->encode_path = c->generic ? (c->enc128 && c->encode_kind == 2 ? "fp16x2_tcgen05_c128" : "fp32_generic") : c->encode_kind == 2 ? "fp16x2_tcgen05" : "fp32";
 		c->decode_path = c->generic ? (c->dec128 && c->decode_kind == 2 ? "bf16_tcgen05_c128_fold" : "fp32_generic") : c->decode_kind == 2 ? "bf16_tcgen05_n192_fold" : "fp32";
 		CUDA_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
 		CUDA_TRY(vqvdb::configure_encode_fp32());
@@ -676,6 +736,8 @@ int vqvdb_b200_create(const vqvdb_b200_config* cfg, vqvdb_b200_codec** out) {
 		CUDA_TRY(vqvdb::configure_decode_fp32());
 		CUDA_TRY(vqvdb::configure_decode_tc());
 		CUDA_TRY(vqvdb::configure_decode_tc128());
+		CUDA_TRY(vqvdb::configure_encode_tc128());
+		CUDA_TRY(vqvdb::configure_encode_tc128_front());
 	} catch (const std::exception& e) {
 		return translate(nullptr, e);
 	}
@@ -860,9 +922,23 @@ int vqvdb_b200_debug_encode_tap(vqvdb_b200_codec* c, const float* dev_leaves, in
 	if (!c) return VQVDB_B200_ERR_INVALID_ARGUMENT;
 	if (n < 0 || stage < 0 || (stage > 7 && stage != 100) || (n > 0 && (!dev_leaves || !dev_tap || !dev_indices)))
 		return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "debug_encode_tap: bad arguments");
-	if (c->generic) return fail(c, VQVDB_B200_ERR_UNSUPPORTED, "debug_encode_tap: float model only");
+	if (c->generic && !c->enc128) return fail(c, VQVDB_B200_ERR_UNSUPPORTED, "debug_encode_tap: no tensor-core encoder for this model");
 	try {
 		CUDA_TRY(cudaSetDevice(c->device));
+		if (c->generic) {  // vec3: stages 0..3 = res_stack.0, res_stack.1, attention, proj, each [leaf][128][64]
+			// ... 4, 5 = pre (GroupNorm + ReLU), the 8^3 residual block, each [leaf][64][512]; 6 = down1 [leaf][128][64]
+			if (stage > 6 || n > kEnc128Batch) return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "debug_encode_tap: bad stage or too many leaves");
+			float* scratch = c->enc128_scratch + (size_t)kSlots * vqvdb::encode_tc128_front_scratch_floats(c->num_sms);
+			float* y = c->enc128_y + (size_t)kSlots * kEnc128Batch * 8192;
+			const cudaStream_t st = (cudaStream_t)stream;
+			if (kEnc128GenericFront) {
+				float* gscratch = c->gen_scratch + (size_t)kSlots * vqvdb::generic_scratch_floats(c->gen_grid);
+				CUDA_TRY(vqvdb::launch_encode_generic_front(c->gen, dev_leaves, n, y, gscratch, c->gen_grid, st));
+			} else CUDA_TRY(vqvdb::launch_encode_tc128_front(c->enc128_front, dev_leaves, n, y, scratch, c->num_sms, st, stage >= 4 ? stage - 4 : -1, dev_tap));
+			if (stage == 6) CUDA_TRY(cudaMemcpyAsync(dev_tap, y, (size_t)n * 8192 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+			CUDA_TRY(vqvdb::launch_encode_tc128_back(c->enc128_back, y, n, dev_indices, c->num_sms, st, stage <= 3 ? stage : -1, dev_tap));
+			return VQVDB_B200_OK;
+		}
 		CUDA_TRY(vqvdb::launch_encode_tc(c->enc, c->enc_tc, dev_leaves, n, dev_indices, c->num_sms, (cudaStream_t)stream, stage, dev_tap));
 	} catch (const std::exception& e) {
 		return translate(c, e);

@@ -1,0 +1,564 @@
+// Front half of the tensor-core vec3 encoder (EncoderVec3, python/VQVAE_v2.py:278-299): the 8^3 stage
+//     pre.0 (3 -> 64) -> GroupNorm(8, 64) -> ReLU -> ResidualBlock(64) -> down1 (64 -> 128, 3x3x3, stride 2)
+// 3 x 512 voxels in, 128 x 64 fp32 out (continued by encode_tc128.cu).  BASELINE.json configs[3].
+//
+// One leaf per CTA pass.  pre.0 is 2.5 % of the arithmetic with raw, unbounded voxel values as its operand: it stays on
+// the fp32 pipes, bit-identical to the oracle's conv3d (oracle/vqvae_oracle.c).  The two 64 -> 64 convolutions and the
+// stride-2 conv run on tcgen05 in the split-fp16 scheme (encode_tc128.cuh):
+//   * the conv input lives in shared memory as channels-last fp16 planes [512 pos][64 ch] (hi, lo; 128-byte rows,
+//     16-byte chunks XOR-swizzled by pos & 7); a GEMM tile is 128 positions (two d slices); the tap-shifted rows go
+//     through TMEM (TS-mode MMA), copied by 8 stager warps;
+//   * a 64 -> 64 conv is 4 tiles x 9 (kd, kh) steps with the kw taps along N (N = 192), recombined when the
+//     accumulators are read; the stride-2 conv is one tile (64 output positions, rows 64..127 idle) x 27 taps, N = 128,
+//     its hi.hi products alternating between two accumulators (the tensor core truncates its fp32 accumulator after
+//     every MMA: shorter chains, smaller bias);
+//   * GroupNorm needs the whole leaf: conv outputs and the residual stream go through a per-CTA fp32 scratch in global
+//     memory (L2-resident, every element private to one thread between barriers) and are normalised / split into the
+//     planes once all four tiles are done.
+// Warp roles (576 threads): 0-7 epilogue, 8-15 stagers, 16 MMA issuer, 17 TMA producer; pre.0 is computed by all 16
+// worker warps, one position per thread.
+#include "encode_tc128.cuh"
+#include "leaf_ops.cuh"
+#include "tc128_ops.cuh"
+
+namespace vqvdb {
+
+namespace {
+
+using namespace tc128;
+
+constexpr int kEpiWarps = 8, kStageWarps = 8, kWorkers = (kEpiWarps + kStageWarps) * 32;
+constexpr int kIssuerWarp = kEpiWarps + kStageWarps, kProducerWarp = kIssuerWarp + 1;
+constexpr int kThreads = (kProducerWarp + 1) * 32;  // 576
+constexpr int kStages = 3;
+constexpr uint32_t kSlotBytes = kEnc128UnitBytes;    // ring slot: one 24 KB conv unit or one 16 KB down unit
+constexpr uint32_t kDownUnitBytes = 16384;           // [128 n][64 k] fp16
+constexpr int kConvSteps = 9, kTiles = 4, kDownSteps = 27;
+constexpr int kPassesPerLeaf = 2 * kTiles + 1;       // accumulator hand-overs per leaf
+constexpr int kUnitsPerLeaf = 2 * kTiles * kConvSteps * 2 + kDownSteps * 2;  // 198 ring loads per leaf
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColHH = 0, kColMix = 192;        // 64 -> 64 convs: N = 192
+constexpr uint32_t kColDownHH = 0, kColDownMix = 256;  // down: two hh chains of N = 128, then mix
+constexpr uint32_t kColA = 384;                      // A buffers: hi at 384 + buf*64, lo at + 32
+constexpr uint32_t kIdescConv = idesc_f16(192), kIdescDown = idesc_f16(128);
+
+// shared memory map (bytes)
+constexpr uint32_t kOffRing = 0;
+constexpr uint32_t kPlaneBytes = 512 * 128;          // [512 pos][64 ch] fp16
+constexpr uint32_t kOffPlanes = kOffRing + kStages * kSlotBytes;  // hi plane, lo plane
+constexpr uint32_t kOffIn = kOffPlanes + 2 * kPlaneBytes;         // the input leaf with a zero halo: [3][10][10][10] fp32
+constexpr uint32_t kInFloats = 3000;
+constexpr uint32_t kOffZero = kOffIn + kInFloats * 4;
+constexpr uint32_t kOffBar = kOffZero + 128;
+constexpr uint32_t kNumBars = 2 * kStages + 2 + 2 + 1 + 1 + 1;
+constexpr uint32_t kOffTmemSlot = kOffBar + kNumBars * 8;
+constexpr uint32_t kOffPar = (kOffTmemSlot + 16 + 15) & ~15u;
+constexpr uint32_t kOffRed = kOffPar + par128f::total * 4;        // [2 slots][16 warps][8] block reductions, then [2 slots][8 warps][4]
+constexpr uint32_t kSmemBytes = kOffRed + (2 * 16 * 8 + 2 * 8 * 4) * 4;
+static_assert(kSmemBytes <= 227 * 1024, "encode_tc128 front smem budget");
+static_assert(kOffBar % 8 == 0 && kOffPar % 16 == 0 && kOffIn % 16 == 0, "alignment");
+
+__device__ __forceinline__ uint32_t bar_w_full(uint32_t bars, uint32_t s) { return bars + s * 8; }
+__device__ __forceinline__ uint32_t bar_w_empty(uint32_t bars, uint32_t s) { return bars + (kStages + s) * 8; }
+__device__ __forceinline__ uint32_t bar_a_full(uint32_t bars, uint32_t b) { return bars + (2 * kStages + b) * 8; }
+__device__ __forceinline__ uint32_t bar_a_empty(uint32_t bars, uint32_t b) { return bars + (2 * kStages + 2 + b) * 8; }
+__device__ __forceinline__ uint32_t bar_d_full(uint32_t bars) { return bars + (2 * kStages + 4) * 8; }
+__device__ __forceinline__ uint32_t bar_d_empty(uint32_t bars) { return bars + (2 * kStages + 5) * 8; }
+__device__ __forceinline__ uint32_t bar_in_ready(uint32_t bars) { return bars + (2 * kStages + 6) * 8; }
+constexpr int kBarWorkers = 1;   // all 16 worker warps
+constexpr int kBarEpiHalf = 2;   // + chalf: the 4 epilogue warps of one channel half
+
+// byte offset of the 16-byte chunk with channels 8*c8 .. 8*c8+7 of row pos inside a [512][64] fp16 plane
+__device__ __forceinline__ uint32_t chunk_off(int pos, int c8) { return (uint32_t)pos * 128u + ((uint32_t)(c8 ^ (pos & 7)) << 4); }
+
+// Sum of 8 per-thread values over the 512 worker threads (every one of them calls this).
+__device__ __forceinline__ void workers_allreduce8(float (&v)[8], float* red, uint32_t& count, int warp, int lane) {
+#pragma unroll
+	for (int i = 0; i < 8; ++i) v[i] = warp_sum(v[i]);
+	float* x = red + (count & 1u) * 128;
+	if (lane == 0) {
+#pragma unroll
+		for (int i = 0; i < 8; ++i) x[warp * 8 + i] = v[i];
+	}
+	named_bar_sync(kBarWorkers, kWorkers);
+#pragma unroll
+	for (int i = 0; i < 8; ++i) {
+		float s = 0.f;
+#pragma unroll
+		for (int wi = 0; wi < 16; ++wi) s += x[wi * 8 + i];
+		v[i] = s;
+	}
+	++count;  // the other slot next time: this one is rewritten only after one more barrier has been passed
+}
+
+// Sum of 4 per-thread values over the 128 epilogue threads of one channel half (4 warps).
+__device__ __forceinline__ void epi_allreduce4(float (&v)[4], float* red, uint32_t& count, int quad, int chalf, int lane) {
+#pragma unroll
+	for (int i = 0; i < 4; ++i) v[i] = warp_sum(v[i]);
+	float* x = red + 256 + (count & 1u) * 32;
+	if (lane == 0) {
+#pragma unroll
+		for (int i = 0; i < 4; ++i) x[(quad * 2 + chalf) * 4 + i] = v[i];
+	}
+	named_bar_sync(kBarEpiHalf + chalf, 128);
+#pragma unroll
+	for (int i = 0; i < 4; ++i) v[i] = x[chalf * 4 + i] + x[(2 + chalf) * 4 + i] + x[(4 + chalf) * 4 + i] + x[(6 + chalf) * 4 + i];
+	++count;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restrict__ leaves, int64_t n_leaves, float* __restrict__ y,
+                          float* __restrict__ scratch, int tap_stage, float* __restrict__ tap_out) {
+	extern __shared__ __align__(1024) uint8_t smem[];
+	const uint32_t s_base = smem_u32(smem);
+	const uint32_t ring = s_base + kOffRing;
+	const uint32_t bars = s_base + kOffBar;
+	const uint32_t plane_hi = s_base + kOffPlanes, plane_lo = plane_hi + kPlaneBytes;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmemSlot);
+	float* s_par = reinterpret_cast<float*>(smem + kOffPar);
+	float* s_in = reinterpret_cast<float*>(smem + kOffIn);
+	float* s_red = reinterpret_cast<float*>(smem + kOffRed);
+
+	for (int i = threadIdx.x; i < par128f::total; i += kThreads) s_par[i] = __ldg(w.par + i);
+	for (int i = threadIdx.x; i < (int)kInFloats; i += kThreads) s_in[i] = 0.f;  // the halo stays zero
+	if (threadIdx.x < 32) reinterpret_cast<uint32_t*>(smem + kOffZero)[threadIdx.x] = 0u;
+	if (threadIdx.x == 0) {
+		for (uint32_t s = 0; s < kStages; ++s) {
+			mbar_init(bar_w_full(bars, s), 1);
+			mbar_init(bar_w_empty(bars, s), 1);
+		}
+		for (uint32_t b = 0; b < 2; ++b) {
+			mbar_init(bar_a_full(bars, b), kStageWarps);
+			mbar_init(bar_a_empty(bars, b), 1);
+		}
+		mbar_init(bar_d_full(bars), 1);
+		mbar_init(bar_d_empty(bars), kEpiWarps);
+		mbar_init(bar_in_ready(bars), kEpiWarps);
+		mbar_fence_init();
+	}
+	if (warp == kIssuerWarp) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+	}
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem = *tmem_slot;
+	const int64_t my_leaves = blockIdx.x < n_leaves ? (n_leaves - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+	if (warp == kProducerWarp) {
+		// ===================== TMA producer =====================
+		// per leaf: conv1's 18 units for each of the 4 tiles, conv2's likewise, then the 54 units of down
+		if (lane == 0) {
+			uint32_t issued = 0;
+#pragma unroll 1
+			for (int64_t g = 0; g < my_leaves; ++g) {
+#pragma unroll 1
+				for (int i = 0; i < kUnitsPerLeaf; ++i, ++issued) {
+					const uint32_t s = issued % kStages;
+					uint32_t u, bytes = kSlotBytes;
+					if (i < 2 * kTiles * 18) u = (uint32_t)(i / (kTiles * 18)) * 18 + (uint32_t)(i % 18);
+					else {
+						u = 36 + (uint32_t)(i - 2 * kTiles * 18);
+						bytes = kDownUnitBytes;
+					}
+					mbar_wait(bar_w_empty(bars, s), ((issued / kStages) & 1u) ^ 1u);
+					mbar_arrive_expect_tx(bar_w_full(bars, s), bytes);
+					tma_load_1d(ring + s * kSlotBytes, w.units + (size_t)u * kSlotBytes, bytes, bar_w_full(bars, s));
+				}
+			}
+		}
+		__syncwarp();
+	} else if (warp == kIssuerWarp) {
+		// ===================== MMA issuer (whole warp, one elected lane issues) =====================
+		const bool leader = elect_one();
+		uint32_t unit = 0, step = 0, pass = 0;
+#pragma unroll 1
+		for (int64_t g = 0; g < my_leaves; ++g) {
+#pragma unroll 1
+			for (int p = 0; p < kPassesPerLeaf; ++p, ++pass) {
+				const bool down = p == kPassesPerLeaf - 1;
+				const int steps = down ? kDownSteps : kConvSteps;
+				const uint32_t idesc = down ? kIdescDown : kIdescConv;
+				mbar_wait(bar_d_empty(bars), (pass & 1u) ^ 1u);
+				tc_fence_after();
+#pragma unroll 1
+				for (int u = 0; u < steps; ++u, ++step) {
+					const uint32_t ab = step & 1u;
+					const uint32_t a_hi = tmem + kColA + ab * 64, a_lo = a_hi + 32;
+					const uint32_t s_hi = unit % kStages, ph_hi = (unit / kStages) & 1u;
+					++unit;
+					const uint32_t s_lo = unit % kStages, ph_lo = (unit / kStages) & 1u;
+					++unit;
+					// down: the hi.hi products alternate between two accumulators
+					const uint32_t d_hh = tmem + (down ? kColDownHH + (uint32_t)(u & 1) * 128 : kColHH);
+					const uint32_t d_mix = tmem + (down ? kColDownMix : kColMix);
+					const uint32_t acc_hh = (down ? u > 1 : u > 0) ? 1u : 0u, acc_mix = u > 0 ? 1u : 0u;
+					mbar_wait(bar_w_full(bars, s_hi), ph_hi);
+					mbar_wait(bar_a_full(bars, ab), (step >> 1) & 1u);
+					tc_fence_after();
+					const uint64_t b_hi = make_desc_sw128(ring + s_hi * kSlotBytes);
+#pragma unroll
+					for (uint32_t kk = 0; kk < 4; ++kk)
+						if (leader) tc_mma_ts(d_hh, a_hi + kk * 8, b_hi + (uint64_t)(kk * 2), idesc, kk > 0 ? 1u : acc_hh);
+#pragma unroll
+					for (uint32_t kk = 0; kk < 4; ++kk)
+						if (leader) tc_mma_ts(d_mix, a_lo + kk * 8, b_hi + (uint64_t)(kk * 2), idesc, kk > 0 ? 1u : acc_mix);
+					if (leader) tc_commit(bar_w_empty(bars, s_hi));
+					mbar_wait(bar_w_full(bars, s_lo), ph_lo);
+					tc_fence_after();
+					const uint64_t b_lo = make_desc_sw128(ring + s_lo * kSlotBytes);
+#pragma unroll
+					for (uint32_t kk = 0; kk < 4; ++kk)
+						if (leader) tc_mma_ts(d_mix, a_hi + kk * 8, b_lo + (uint64_t)(kk * 2), idesc, 1u);
+					if (leader) tc_commit(bar_a_empty(bars, ab));
+					if (leader) tc_commit(bar_w_empty(bars, s_lo));
+					if (u == steps - 1 && leader) tc_commit(bar_d_full(bars));
+				}
+			}
+		}
+		__syncwarp();
+	} else {
+		// ===================== worker warps =====================
+		const bool is_stager = warp >= kEpiWarps;
+		const int quad = warp & 3, chalf = (warp >> 2) & 1;
+		const int row = quad * 32 + lane;
+		const int wt = threadIdx.x;  // 0..511: this thread's position in the pre phase
+		const uint32_t tmem_lane = tmem + ((uint32_t)(quad * 32) << 16);
+		const uint32_t zero_row = s_base + kOffZero;
+		float* xs = scratch + (size_t)blockIdx.x * (2 * 64 * 512);  // residual stream x, [64 ch][512 pos] fp32
+		float* cs = xs + 64 * 512;                                   // conv1's output before GroupNorm
+		uint32_t n_red = 0, n_ered = 0, step = 0, layer = 0, passes = 0;
+
+#pragma unroll 1
+		for (int64_t g = 0; g < my_leaves; ++g) {
+			const int64_t leaf = blockIdx.x + g * gridDim.x;
+
+			// ---------- pre phase, all workers: pre.0 + GroupNorm + ReLU -> x ; res.gn1 + ReLU -> planes ----------
+			{
+				const float* src = leaves + leaf * 1536;
+#pragma unroll
+				for (int i = 0; i < 3; ++i) {
+					const int e = wt + i * 512, c = e >> 9, p = e & 511;
+					s_in[c * 1000 + ((p >> 6) + 1) * 100 + (((p >> 3) & 7) + 1) * 10 + (p & 7) + 1] = __ldcs(src + e);
+				}
+				named_bar_sync(kBarWorkers, kWorkers);
+				const int pd = wt >> 6, ph = (wt >> 3) & 7, pw = wt & 7;
+				const float* ip = s_in + pd * 100 + ph * 10 + pw;
+				float gsum[8];
+				// out[c] = b[c] + sum_{ic, kd, kh, kw} in * w, ascending, as conv3d of the oracle (halo taps add an exact 0)
+#pragma unroll 1
+				for (int cb = 0; cb < 8; ++cb) {
+					float acc[8];
+#pragma unroll
+					for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+					const float4* wp = reinterpret_cast<const float4*>(w.pre_wt + cb * 8);
+#pragma unroll 1
+					for (int ic = 0; ic < 3; ++ic) {
+#pragma unroll
+						for (int tap = 0; tap < 27; ++tap) {
+							const float xv = ip[ic * 1000 + (tap / 9) * 100 + ((tap / 3) % 3) * 10 + tap % 3];
+							const float4 w0 = __ldg(wp + (ic * 27 + tap) * 16), w1 = __ldg(wp + (ic * 27 + tap) * 16 + 1);
+							acc[0] = fmaf(xv, w0.x, acc[0]);
+							acc[1] = fmaf(xv, w0.y, acc[1]);
+							acc[2] = fmaf(xv, w0.z, acc[2]);
+							acc[3] = fmaf(xv, w0.w, acc[3]);
+							acc[4] = fmaf(xv, w1.x, acc[4]);
+							acc[5] = fmaf(xv, w1.y, acc[5]);
+							acc[6] = fmaf(xv, w1.z, acc[6]);
+							acc[7] = fmaf(xv, w1.w, acc[7]);
+						}
+					}
+					float s = 0.f;
+#pragma unroll
+					for (int j = 0; j < 8; ++j) {
+						const float v = acc[j] + s_par[par128f::pre_b + cb * 8 + j];
+						xs[(cb * 8 + j) * 512 + wt] = v;  // stash (private to this thread until the barrier below)
+						s += v;
+					}
+					gsum[cb] = s;  // GroupNorm(8, 64): group cb = channels 8cb .. 8cb + 7
+				}
+				float v[64];
+#pragma unroll
+				for (int c = 0; c < 64; ++c) v[c] = xs[c * 512 + wt];
+				// pre.1 GroupNorm + ReLU (two-pass variance over 8 channels x 512 positions)
+				workers_allreduce8(gsum, s_red, n_red, warp, lane);
+				float mean[8], q[8];
+#pragma unroll
+				for (int gI = 0; gI < 8; ++gI) {
+					mean[gI] = gsum[gI] * (1.f / 4096.f);
+					float t = 0.f;
+#pragma unroll
+					for (int j = 0; j < 8; ++j) {
+						const float d = v[gI * 8 + j] - mean[gI];
+						t = fmaf(d, d, t);
+					}
+					q[gI] = t;
+				}
+				workers_allreduce8(q, s_red, n_red, warp, lane);
+#pragma unroll
+				for (int gI = 0; gI < 8; ++gI) {
+					const float rstd = 1.f / sqrtf(q[gI] * (1.f / 4096.f) + kGnEps);
+					float t = 0.f;
+#pragma unroll
+					for (int j = 0; j < 8; ++j) {
+						const int c = gI * 8 + j;
+						v[c] = fmaxf((v[c] - mean[gI]) * rstd * s_par[par128f::pre_gn_w + c] + s_par[par128f::pre_gn_b + c], 0.f);
+						xs[c * 512 + wt] = v[c];
+						t += v[c];
+					}
+					gsum[gI] = t;
+				}
+				if (tap_stage == 0) {
+#pragma unroll
+					for (int c = 0; c < 64; ++c) tap_out[leaf * 32768 + c * 512 + wt] = v[c];
+				}
+				// res.gn1 + ReLU -> conv1's input
+				workers_allreduce8(gsum, s_red, n_red, warp, lane);
+#pragma unroll
+				for (int gI = 0; gI < 8; ++gI) {
+					mean[gI] = gsum[gI] * (1.f / 4096.f);
+					float t = 0.f;
+#pragma unroll
+					for (int j = 0; j < 8; ++j) {
+						const float d = v[gI * 8 + j] - mean[gI];
+						t = fmaf(d, d, t);
+					}
+					q[gI] = t;
+				}
+				workers_allreduce8(q, s_red, n_red, warp, lane);
+#pragma unroll
+				for (int gI = 0; gI < 8; ++gI) {
+					const float rstd = 1.f / sqrtf(q[gI] * (1.f / 4096.f) + kGnEps);
+					float a[8];
+#pragma unroll
+					for (int j = 0; j < 8; ++j) {
+						const int c = gI * 8 + j;
+						a[j] = fmaxf((v[c] - mean[gI]) * rstd * s_par[par128f::gn1_w + c] + s_par[par128f::gn1_b + c], 0.f);
+					}
+					uint4 hi, lo;
+					split8(a, hi, lo);
+					const uint32_t off = chunk_off(wt, gI);
+					sts128(plane_hi + off, hi);
+					sts128(plane_lo + off, lo);
+				}
+				named_bar_sync(kBarWorkers, kWorkers);  // planes and x complete (x is read by other threads from here on)
+			}
+
+			if (is_stager) {
+				// ---------- stagers: tap-shifted rows of the planes -> TMEM A buffers ----------
+#pragma unroll 1
+				for (int l = 0; l < 3; ++l, ++layer) {
+					if (lane == 0) mbar_wait(bar_in_ready(bars), layer & 1u);
+					__syncwarp();
+					const int n_steps = l < 2 ? kTiles * kConvSteps : kDownSteps;
+#pragma unroll 1
+					for (int su = 0; su < n_steps; ++su, ++step) {
+						bool ok;
+						int p2;
+						if (l < 2) {
+							const int tile = su / kConvSteps, t = su - tile * kConvSteps, td = t / 3, th = t - td * 3;
+							const int pos = tile * 128 + row, pd = pos >> 6, ph = (pos >> 3) & 7;
+							ok = (unsigned)(pd + td - 1) < 8u && (unsigned)(ph + th - 1) < 8u;
+							p2 = pos + (td - 1) * 64 + (th - 1) * 8;
+						} else {
+							const int td = su / 9, th = (su / 3) % 3, tw = su % 3;
+							const int id = 2 * ((row >> 4) & 3) - 1 + td, ih = 2 * ((row >> 2) & 3) - 1 + th, iw = 2 * (row & 3) - 1 + tw;
+							ok = row < 64 && (unsigned)id < 8u && (unsigned)ih < 8u && (unsigned)iw < 8u;
+							p2 = id * 64 + ih * 8 + iw;
+						}
+						uint32_t rh[16], rl[16];
+#pragma unroll
+						for (int q = 0; q < 4; ++q) {
+							const uint32_t off = ok ? chunk_off(p2, chalf * 4 + q) : 0u;
+							const uint4 vh = lds128(ok ? plane_hi + off : zero_row + q * 16);
+							const uint4 vl = lds128(ok ? plane_lo + off : zero_row + q * 16);
+							rh[4 * q] = vh.x; rh[4 * q + 1] = vh.y; rh[4 * q + 2] = vh.z; rh[4 * q + 3] = vh.w;
+							rl[4 * q] = vl.x; rl[4 * q + 1] = vl.y; rl[4 * q + 2] = vl.z; rl[4 * q + 3] = vl.w;
+						}
+						const uint32_t ab = step & 1u;
+						if (lane == 0) mbar_wait(bar_a_empty(bars, ab), ((step >> 1) & 1u) ^ 1u);
+						__syncwarp();
+						tc_fence_after();
+						tmem_st16(tmem_lane + kColA + ab * 64 + chalf * 16, rh);
+						tmem_st16(tmem_lane + kColA + ab * 64 + 32 + chalf * 16, rl);
+						tmem_wait_st();
+						tc_fence_before();
+						__syncwarp();
+						if (lane == 0) mbar_arrive(bar_a_full(bars, ab));
+					}
+				}
+			} else {
+				// ---------- epilogue warps ----------
+				const int w8 = row & 7;  // w coordinate of this thread's row in every tile
+				const bool has_lo = w8 > 0, has_hi = w8 < 7;
+				const int c0 = chalf * 32;
+				auto signal_input_ready = [&]() {
+					__syncwarp();
+					if (lane == 0) mbar_arrive(bar_in_ready(bars));
+				};
+				// this thread's 32 output channels of a finished N = 192 tile: hh + mix / 2048, kw partials combined
+				auto take_conv_tile = [&](float (&v)[32]) {
+					mbar_wait(bar_d_full(bars), passes & 1u);
+					tc_fence_after();
+					const uint32_t base = tmem_lane + c0;
+#pragma unroll
+					for (int part = 0; part < 2; ++part) {
+#pragma unroll
+						for (int kw = 0; kw < 3; ++kw) {
+							float h[16], m[16];
+							tmem_ld16_nowait(base + kColHH + kw * 64 + part * 16, h);
+							tmem_ld16_nowait(base + kColMix + kw * 64 + part * 16, m);
+							tmem_wait_ld();
+#pragma unroll
+							for (int j = 0; j < 16; ++j) {
+								const float t = fmaf(m[j], kLoInv, h[j]);
+								if (kw == 0) {
+									const float lo = __shfl_up_sync(0xffffffffu, t, 1);
+									v[part * 16 + j] = has_lo ? lo : 0.f;
+								} else if (kw == 1) {
+									v[part * 16 + j] += t;
+								} else {
+									const float hi = __shfl_down_sync(0xffffffffu, t, 1);
+									v[part * 16 + j] += has_hi ? hi : 0.f;
+								}
+							}
+						}
+					}
+					tc_fence_before();
+					__syncwarp();
+					if (lane == 0) mbar_arrive(bar_d_empty(bars));
+					++passes;
+				};
+				signal_input_ready();  // layer 0: the planes were completed before the workers' barrier above
+
+				float v[32];
+				// ---- conv1 + bias -> scratch, group sums ; after the 4 tiles: gn2 + ReLU -> planes ----
+				float gs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+				for (int tile = 0; tile < kTiles; ++tile) {
+					take_conv_tile(v);
+					const int pos = tile * 128 + row;
+#pragma unroll
+					for (int j = 0; j < 32; ++j) {
+						v[j] += s_par[par128f::c1_b + c0 + j];
+						cs[(c0 + j) * 512 + pos] = v[j];
+						gs[j >> 3] += v[j];
+					}
+				}
+				epi_allreduce4(gs, s_red, n_ered, quad, chalf, lane);
+				float mean[4], q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+				for (int i = 0; i < 4; ++i) mean[i] = gs[i] * (1.f / 4096.f);
+#pragma unroll 1
+				for (int tile = 0; tile < kTiles; ++tile) {
+					const int pos = tile * 128 + row;
+#pragma unroll
+					for (int j = 0; j < 32; ++j) {
+						const float d = cs[(c0 + j) * 512 + pos] - mean[j >> 3];
+						q[j >> 3] = fmaf(d, d, q[j >> 3]);
+					}
+				}
+				epi_allreduce4(q, s_red, n_ered, quad, chalf, lane);
+#pragma unroll
+				for (int i = 0; i < 4; ++i) q[i] = 1.f / sqrtf(q[i] * (1.f / 4096.f) + kGnEps);
+#pragma unroll 1
+				for (int tile = 0; tile < kTiles; ++tile) {
+					const int pos = tile * 128 + row;
+#pragma unroll
+					for (int c8 = 0; c8 < 4; ++c8) {
+						float a[8];
+#pragma unroll
+						for (int j = 0; j < 8; ++j) {
+							const int c = c0 + c8 * 8 + j;
+							a[j] = fmaxf((cs[c * 512 + pos] - mean[c8]) * q[c8] * s_par[par128f::gn2_w + c] + s_par[par128f::gn2_b + c], 0.f);
+						}
+						uint4 hi, lo;
+						split8(a, hi, lo);
+						const uint32_t off = chunk_off(pos, chalf * 4 + c8);
+						sts128(plane_hi + off, hi);
+						sts128(plane_lo + off, lo);
+					}
+				}
+				signal_input_ready();  // layer 1: conv2's input
+
+				// ---- conv2: x' = x + 0.1 * (conv2 + bias), in place in the scratch ; after the 4 tiles: x' split -> planes ----
+#pragma unroll 1
+				for (int tile = 0; tile < kTiles; ++tile) {
+					take_conv_tile(v);
+					const int pos = tile * 128 + row;
+#pragma unroll
+					for (int j = 0; j < 32; ++j) {
+						const float xn = xs[(c0 + j) * 512 + pos] + kResScale * (v[j] + s_par[par128f::c2_b + c0 + j]);
+						xs[(c0 + j) * 512 + pos] = xn;
+						if (tap_stage == 1) tap_out[leaf * 32768 + (c0 + j) * 512 + pos] = xn;
+					}
+				}
+#pragma unroll 1
+				for (int tile = 0; tile < kTiles; ++tile) {
+					const int pos = tile * 128 + row;
+#pragma unroll
+					for (int c8 = 0; c8 < 4; ++c8) {
+						float a[8];
+#pragma unroll
+						for (int j = 0; j < 8; ++j) a[j] = xs[(c0 + c8 * 8 + j) * 512 + pos];
+						uint4 hi, lo;
+						split8(a, hi, lo);
+						const uint32_t off = chunk_off(pos, chalf * 4 + c8);
+						sts128(plane_hi + off, hi);
+						sts128(plane_lo + off, lo);
+					}
+				}
+				signal_input_ready();  // layer 2: down1's input
+
+				// ---- down1: rows 0..63 are the 4^3 output positions; this thread: output channels 64 chalf .. + 63 ----
+				mbar_wait(bar_d_full(bars), passes & 1u);
+				tc_fence_after();
+				if (row < 64) {
+#pragma unroll
+					for (int part = 0; part < 4; ++part) {
+						float h0[16], h1[16], m[16];
+						const uint32_t col = tmem_lane + chalf * 64 + part * 16;
+						tmem_ld16_nowait(col + kColDownHH, h0);
+						tmem_ld16_nowait(col + kColDownHH + 128, h1);
+						tmem_ld16_nowait(col + kColDownMix, m);
+						tmem_wait_ld();
+#pragma unroll
+						for (int j = 0; j < 16; ++j) {
+							const int c = chalf * 64 + part * 16 + j;
+							y[leaf * 8192 + c * 64 + row] = fmaf(m[j], kLoInv, h0[j] + h1[j]) + s_par[par128f::down_b + c];
+						}
+					}
+				}
+				tc_fence_before();
+				__syncwarp();
+				if (lane == 0) mbar_arrive(bar_d_empty(bars));
+				++passes;
+			}
+		}
+	}
+
+	// ---- teardown: everybody is done with TMEM before the owner frees it ----
+	tc_fence_before();
+	__syncthreads();
+	if (warp == kIssuerWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+}
+
+}  // namespace
+
+cudaError_t configure_encode_tc128_front() {
+	return cudaFuncSetAttribute(encode_tc128_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+}
+
+size_t encode_tc128_front_scratch_floats(int num_sms) { return (size_t)num_sms * 2 * 64 * 512; }
+
+cudaError_t launch_encode_tc128_front(const Encoder128FrontWeights& w, const float* dev_leaves, int64_t n_leaves, float* dev_y, float* dev_scratch,
+                                      int num_sms, cudaStream_t stream, int tap_stage, float* tap_out) {
+	if (n_leaves <= 0) return cudaSuccess;
+	const int grid = (int)(n_leaves < (int64_t)num_sms ? n_leaves : (int64_t)num_sms);
+	encode_tc128_front_kernel<<<grid, kThreads, kSmemBytes, stream>>>(w, dev_leaves, n_leaves, dev_y, dev_scratch, tap_stage, tap_out);
+	return cudaGetLastError();
+}
+
+}  // namespace vqvdb

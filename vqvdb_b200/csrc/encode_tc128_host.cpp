@@ -1,0 +1,195 @@
+// Host-side preparation of the tensor-core vec3 encoder's weight streams and parameter blocks (encode_tc128.cuh).
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "encode_tc128_stream.hpp"
+
+namespace vqvdb {
+
+namespace {
+
+constexpr size_t kUnitBytes = kEnc128UnitBytes;
+
+// IEEE binary32 -> binary16, round to nearest even, subnormals kept.
+uint16_t f32_to_f16_rn(float f) {
+	uint32_t x;
+	std::memcpy(&x, &f, 4);
+	const uint32_t sign = (x >> 16) & 0x8000u;
+	const uint32_t abs = x & 0x7fffffffu;
+	if (abs >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (abs > 0x7f800000u ? 0x200u : 0u));
+	if (abs >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);  // >= 65520 rounds to infinity
+	if (abs <= 0x33000000u) return (uint16_t)sign;              // <= 2^-25 rounds to zero
+	const int exp = (int)(abs >> 23) - 127;
+	const uint32_t mant = (abs & 0x7fffffu) | 0x800000u;
+	if (exp < -14) {  // subnormal result: units of 2^-24
+		const int shift = (-14 - exp) + 13;
+		uint32_t q = mant >> shift;
+		const uint32_t rem = mant & ((1u << shift) - 1u), half = 1u << (shift - 1);
+		if (rem > half || (rem == half && (q & 1u))) ++q;
+		return (uint16_t)(sign | q);
+	}
+	uint32_t q = ((uint32_t)(exp + 15) << 10) | ((mant & 0x7fffffu) >> 13);
+	const uint32_t rem = mant & 0x1fffu;
+	if (rem > 0x1000u || (rem == 0x1000u && (q & 1u))) ++q;
+	return (uint16_t)(sign | q);
+}
+
+float f16_to_f32(uint16_t h) {
+	const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+	uint32_t exp = (h >> 10) & 0x1fu, mant = h & 0x3ffu, out;
+	if (exp == 0) {
+		if (mant == 0) out = sign;
+		else {
+			int e = -1;
+			do {
+				mant <<= 1;
+				++e;
+			} while (!(mant & 0x400u));
+			out = sign | ((uint32_t)(127 - 15 - e) << 23) | ((mant & 0x3ffu) << 13);
+		}
+	} else if (exp == 31) out = sign | 0x7f800000u | (mant << 13);
+	else out = sign | ((exp - 15 + 127) << 23) | (mant << 13);
+	float f;
+	std::memcpy(&f, &out, 4);
+	return f;
+}
+
+// part 0: fp16(w); part 1: fp16((w - fp16(w)) * 2048)
+uint16_t split_part(float w, int part) {
+	const uint16_t hi = f32_to_f16_rn(w);
+	if (part == 0) return hi;
+	return f32_to_f16_rn((w - f16_to_f32(hi)) * 2048.f);
+}
+
+bool dims_are(const WeightPack& p, const std::string& name, std::initializer_list<int> dims) {
+	const auto it = p.tensors.find(name);
+	return it != p.tensors.end() && it->second.dims == std::vector<int>(dims);
+}
+
+// One [64 n][64 k] tile of a unit: element (n, k) at byte n*128 + (((k>>3) ^ (n&7)) << 4) + (k&7)*2.
+// w is [cout][cin_total][27]; the tile takes output channels oc0.., input channels ic0.., filter tap `tap`.
+void fill_tile(uint8_t* tile, const float* w, int cin_total, int oc0, int ic0, int tap, int part) {
+	for (int n = 0; n < 64; ++n)
+		for (int k = 0; k < 64; ++k) {
+			const uint16_t b = split_part(w[((size_t)(oc0 + n) * cin_total + (ic0 + k)) * 27 + tap], part);
+			const size_t off = (size_t)n * 128 + ((size_t)((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
+			std::memcpy(tile + off, &b, 2);
+		}
+}
+
+// The 18 steps of one pass of a 128 -> 128 conv on the 4^3 grid: 9 (kd, kh) pairs x 2 input-channel halves, each the hi
+// unit then the lo unit, a unit = [3 kw] tiles of output channels oc0 .. oc0 + 63.
+uint8_t* fill_pass128(uint8_t* u, const float* w, int oc0) {
+	for (int pair = 0; pair < 9; ++pair)
+		for (int khalf = 0; khalf < 2; ++khalf)
+			for (int part = 0; part < 2; ++part, u += kUnitBytes)
+				for (int kw = 0; kw < 3; ++kw) fill_tile(u + (size_t)kw * 8192, w, 128, oc0, khalf * 64, pair * 3 + kw, part);
+	return u;
+}
+
+// One [128 n][64 k] tile (the stride-2 conv: all 128 output channels, one filter tap), same row layout.
+void fill_tile_down(uint8_t* tile, const float* w, int tap, int part) {
+	for (int n = 0; n < 128; ++n)
+		for (int k = 0; k < 64; ++k) {
+			const uint16_t b = split_part(w[((size_t)n * 64 + k) * 27 + tap], part);
+			const size_t off = (size_t)n * 128 + ((size_t)((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
+			std::memcpy(tile + off, &b, 2);
+		}
+}
+
+}  // namespace
+
+bool encoder128_supports(const WeightPack& p) {
+	if (p.embedding_dim != 128 || p.num_embeddings != 256 || p.in_channels != 3) return false;
+	bool ok = dims_are(p, "quantizer.embedding", {256, 128}) && dims_are(p, "encoder.pre.0.weight", {64, 3, 3, 3, 3}) &&
+	          dims_are(p, "encoder.pre.0.bias", {64}) && dims_are(p, "encoder.pre.1.weight", {64}) && dims_are(p, "encoder.pre.1.bias", {64}) &&
+	          dims_are(p, "encoder.down1.weight", {128, 64, 3, 3, 3}) && dims_are(p, "encoder.down1.bias", {128}) &&
+	          dims_are(p, "encoder.attn.fc.0.weight", {32, 128}) && dims_are(p, "encoder.attn.fc.2.weight", {128, 32}) &&
+	          dims_are(p, "encoder.proj.weight", {128, 128, 1, 1, 1}) && dims_are(p, "encoder.proj.bias", {128}) &&
+	          p.tensors.find("encoder.res_stack.2.conv1.weight") == p.tensors.end();
+	for (const char* v : {".gn1.weight", ".gn1.bias", ".gn2.weight", ".gn2.bias", ".conv1.bias", ".conv2.bias"})
+		ok = ok && dims_are(p, std::string("encoder.pre.3") + v, {64});
+	ok = ok && dims_are(p, "encoder.pre.3.conv1.weight", {64, 64, 3, 3, 3}) && dims_are(p, "encoder.pre.3.conv2.weight", {64, 64, 3, 3, 3});
+	for (int r = 0; r < 2 && ok; ++r) {
+		const std::string pre = "encoder.res_stack." + std::to_string(r);
+		for (const char* v : {".gn1.weight", ".gn1.bias", ".gn2.weight", ".gn2.bias", ".conv1.bias", ".conv2.bias"}) ok = ok && dims_are(p, pre + v, {128});
+		ok = ok && dims_are(p, pre + ".conv1.weight", {128, 128, 3, 3, 3}) && dims_are(p, pre + ".conv2.weight", {128, 128, 3, 3, 3});
+	}
+	return ok;
+}
+
+std::vector<uint8_t> build_encoder128_back_units(const WeightPack& p) {
+	if (!encoder128_supports(p)) throw std::runtime_error("encoder128 units: unsupported architecture");
+	std::vector<uint8_t> out((size_t)kEnc128BackUnits * kUnitBytes);
+	uint8_t* u = out.data();
+	for (const char* name : {"encoder.res_stack.0.conv1.weight", "encoder.res_stack.0.conv2.weight", "encoder.res_stack.1.conv1.weight",
+	                         "encoder.res_stack.1.conv2.weight"}) {
+		const float* w = p.get(name).data;
+		for (int h = 0; h < 2; ++h) u = fill_pass128(u, w, h * 64);
+	}
+	if (u != out.data() + out.size()) throw std::logic_error("encoder128 back unit stream size mismatch");
+	return out;
+}
+
+std::vector<float> build_encoder128_back_params(const WeightPack& p) {
+	if (!encoder128_supports(p)) throw std::runtime_error("encoder128 params: unsupported architecture");
+	std::vector<float> out;
+	auto put = [&](const std::string& name, size_t n) {
+		const PackTensor& t = p.get(name);
+		if (t.numel() != n) throw std::runtime_error("encoder128 params: unexpected size of " + name);
+		out.insert(out.end(), t.data, t.data + n);
+	};
+	for (int r = 0; r < 2; ++r) {
+		const std::string pre = "encoder.res_stack." + std::to_string(r);
+		for (const char* v : {".gn1.weight", ".gn1.bias", ".conv1.bias", ".gn2.weight", ".gn2.bias", ".conv2.bias"}) put(pre + v, 128);
+	}
+	put("encoder.proj.bias", 128);
+	if (out.size() != (size_t)par128e::total) throw std::logic_error("encoder128 back parameter block size mismatch");
+	return out;
+}
+
+std::vector<uint8_t> build_encoder128_front_units(const WeightPack& p) {
+	if (!encoder128_supports(p)) throw std::runtime_error("encoder128 units: unsupported architecture");
+	std::vector<uint8_t> out((size_t)kEnc128FrontUnits * kUnitBytes, 0);
+	uint8_t* u = out.data();
+	for (const char* name : {"encoder.pre.3.conv1.weight", "encoder.pre.3.conv2.weight"}) {
+		const float* w = p.get(name).data;
+		for (int pair = 0; pair < 9; ++pair)
+			for (int part = 0; part < 2; ++part, u += kUnitBytes)
+				for (int kw = 0; kw < 3; ++kw) fill_tile(u + (size_t)kw * 8192, w, 64, 0, 0, pair * 3 + kw, part);
+	}
+	const float* dw = p.get("encoder.down1.weight").data;
+	for (int tap = 0; tap < 27; ++tap)
+		for (int part = 0; part < 2; ++part, u += kUnitBytes) fill_tile_down(u, dw, tap, part);
+	if (u != out.data() + out.size()) throw std::logic_error("encoder128 front unit stream size mismatch");
+	return out;
+}
+
+std::vector<float> build_encoder128_front_params(const WeightPack& p) {
+	if (!encoder128_supports(p)) throw std::runtime_error("encoder128 params: unsupported architecture");
+	std::vector<float> out;
+	auto put = [&](const std::string& name, size_t n) {
+		const PackTensor& t = p.get(name);
+		if (t.numel() != n) throw std::runtime_error("encoder128 params: unexpected size of " + name);
+		out.insert(out.end(), t.data, t.data + n);
+	};
+	put("encoder.pre.0.bias", 64);
+	put("encoder.pre.1.weight", 64);
+	put("encoder.pre.1.bias", 64);
+	for (const char* v : {".gn1.weight", ".gn1.bias", ".conv1.bias", ".gn2.weight", ".gn2.bias", ".conv2.bias"}) put(std::string("encoder.pre.3") + v, 64);
+	put("encoder.down1.bias", 128);
+	if (out.size() != (size_t)par128f::total) throw std::logic_error("encoder128 front parameter block size mismatch");
+	return out;
+}
+
+std::vector<float> build_embedding_transposed(const WeightPack& p) {
+	const PackTensor& e = p.get("quantizer.embedding");
+	const int K = e.dims[0], D = e.dims[1];
+	std::vector<float> out((size_t)K * D);
+	for (int k = 0; k < K; ++k)
+		for (int d = 0; d < D; ++d) out[(size_t)d * K + k] = e.data[(size_t)k * D + d];
+	return out;
+}
+
+}  // namespace vqvdb

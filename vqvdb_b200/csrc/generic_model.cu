@@ -200,7 +200,7 @@ __device__ void attn_g(float* x, int C, int nsp, const float* __restrict__ fc0, 
 
 __global__ void __launch_bounds__(kGThreads)
 encode_generic_kernel(const GenericModel m, const float* __restrict__ leaves, int64_t n_leaves, uint8_t* __restrict__ indices,
-                      float* __restrict__ scratch) {
+                      float* __restrict__ scratch, float* __restrict__ down_out) {
 	__shared__ float s_tmp[320];
 	__shared__ float s_best[4 * 64];
 	__shared__ int s_bi[4 * 64];
@@ -215,6 +215,10 @@ encode_generic_kernel(const GenericModel m, const float* __restrict__ leaves, in
 		conv_g(leaves + leaf * leaf_sz, m.cin, 8, m.e_pre_w, m.e_pre_b, m.e_c0, 3, 1, s0);
 		gn_g(s0, m.e_c0, 512, m.e_gn0, m.e_gn_w, m.e_gn_b, true);
 		res_g(s0, m.e_c0, 8, m.e_res0, s1, s2, s_in);
+		if (down_out) {  // front half only: the stride-2 conv's output [e_c1][64] is the result (encode_tc128.cu continues)
+			conv_any_g(s0, m.e_c0, 8, m.e_down_w, m.e_down_b, m.e_c1, m.e_down_k, 2, down_out + leaf * (int64_t)(m.e_c1 * 64), s_in);
+			continue;
+		}
 		conv_any_g(s0, m.e_c0, 8, m.e_down_w, m.e_down_b, m.e_c1, m.e_down_k, 2, s1, s_in);
 		for (int r = 0; r < m.e_nres; ++r) res_g(s1, m.e_c1, 4, m.e_res[r], s0, s2, s_in);
 		attn_g(s1, m.e_c1, 64, m.e_fc0, m.e_fc2, m.e_red, s_tmp);
@@ -296,7 +300,15 @@ cudaError_t launch_encode_generic(const GenericModel& m, const float* leaves, in
                                   cudaStream_t stream) {
 	if (n <= 0) return cudaSuccess;
 	const int g = (int)(n < grid ? n : grid);
-	encode_generic_kernel<<<g, kGThreads, 0, stream>>>(m, leaves, n, indices, scratch);
+	encode_generic_kernel<<<g, kGThreads, 0, stream>>>(m, leaves, n, indices, scratch, nullptr);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_encode_generic_front(const GenericModel& m, const float* leaves, int64_t n, float* down_out, float* scratch, int grid,
+                                        cudaStream_t stream) {
+	if (n <= 0) return cudaSuccess;
+	const int g = (int)(n < grid ? n : grid);
+	encode_generic_kernel<<<g, kGThreads, 0, stream>>>(m, leaves, n, nullptr, scratch, down_out);
 	return cudaGetLastError();
 }
 

@@ -31,6 +31,9 @@ struct GenericModel {
 size_t generic_scratch_floats(int grid);
 cudaError_t launch_encode_generic(const GenericModel& m, const float* leaves, int64_t n, uint8_t* indices, float* scratch, int grid,
                                   cudaStream_t stream);
+// The encoder up to and including the stride-2 conv: down_out [n][e_c1][64] fp32.
+cudaError_t launch_encode_generic_front(const GenericModel& m, const float* leaves, int64_t n, float* down_out, float* scratch, int grid,
+                                        cudaStream_t stream);
 cudaError_t launch_decode_generic(const GenericModel& m, const uint8_t* indices, int64_t n, float* voxels, float* scratch, int grid,
                                   cudaStream_t stream);
 
