@@ -530,7 +530,11 @@ void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
 	if (vqvdb::encoder128_supports(p)) {
 		const std::vector<uint8_t> back = vqvdb::build_encoder128_back_units(p);
 		const std::vector<float> back_par = vqvdb::build_encoder128_back_params(p);
-		const std::vector<float> emb_t = vqvdb::build_embedding_transposed(p);
+		std::vector<float> emb_t = vqvdb::build_proj_transposed(p);  // proj^T, then the codebook^T: one contiguous stream
+		{
+			const std::vector<float> et = vqvdb::build_embedding_transposed(p);
+			emb_t.insert(emb_t.end(), et.begin(), et.end());
+		}
 		const std::vector<uint8_t> front = vqvdb::build_encoder128_front_units(p);
 		const std::vector<float> front_par = vqvdb::build_encoder128_front_params(p);
 		const size_t off_par = back.size(), off_emb = (off_par + back_par.size() * sizeof(float) + 255) & ~size_t(255);
@@ -550,8 +554,7 @@ void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
 		c.enc128_back.par = reinterpret_cast<const float*>(c.enc128_arena + off_par);
 		c.enc128_back.fc0 = m.e_fc0;
 		c.enc128_back.fc2 = m.e_fc2;
-		c.enc128_back.proj_wt = m.e_proj_w;
-		c.enc128_back.emb_t = reinterpret_cast<const float*>(c.enc128_arena + off_emb);
+		c.enc128_back.vq_stream = reinterpret_cast<const float*>(c.enc128_arena + off_emb);
 		c.enc128_back.emb_sq = m.emb_sq;
 		c.enc128 = true;
 	}

@@ -41,6 +41,12 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColHH = 0, kColMix = 192;        // accumulators
 constexpr uint32_t kColA = 384;                      // A buffers: hi at 384 + buf*64, lo at 384 + buf*64 + 32
 constexpr uint32_t kIdesc = idesc_f16(192);
+// After the conv units of a pair of leaves the same ring carries the fp32 operands of proj and of the distance
+// computation to the worker warps: proj.weight^T [128 c][128 d] as 4 chunks of 32 c rows, then the codebook transposed
+// [128 d][256 k] as 8 chunks of 16 d rows (16 KB each).
+constexpr uint32_t kVqChunkBytes = 16384;
+constexpr int kProjChunks = 4, kEmbChunks = 8;
+constexpr int kRingLoadsPerPair = kEnc128BackUnits + kProjChunks + kEmbChunks;  // 300
 
 // shared memory map (bytes)
 constexpr uint32_t kOffRing = 0;
@@ -172,29 +178,39 @@ __device__ __forceinline__ void store_row32_split(uint32_t buf, int pos, int c16
 }
 
 // proj + distances + argmin for one leaf by its 256 worker threads: t = (quarter q of the outputs / codes) * 64 + position p.
-// x: fp32 [128 c][64 pos] (attention output), z: fp32 [128 d][64 pos] scratch, both in shared memory.
-__device__ __forceinline__ void project_and_quantize(const Encoder128BackWeights& w, const float* s_par, uint32_t x, uint32_t z, float* s_best,
-                                                     int* s_bi, int t, int64_t leaf, bool leaf_ok, uint8_t* __restrict__ indices,
-                                                     int tap_stage, float* __restrict__ tap_out) {
+// x: fp32 [128 c][64 pos] (attention output), z: fp32 [128 d][64 pos] scratch, both in shared memory.  The weights arrive
+// through the ring (first_load = index of the pair's first fp32 chunk among all ring loads of this CTA); every lane of
+// a warp reads the same weight address (a broadcast).
+__device__ __forceinline__ void project_and_quantize(const Encoder128BackWeights& w, const float* s_par, uint32_t bars, uint32_t ring, uint32_t first_load,
+                                                     uint32_t x, uint32_t z, float* s_best, int* s_bi, int t, bool releaser, int64_t leaf, bool leaf_ok,
+                                                     uint8_t* __restrict__ indices, int tap_stage, float* __restrict__ tap_out) {
 	const int p = t & 63, q = t >> 6;
+	uint32_t load = first_load;
 	named_bar_sync(kBarWorkers, kWorkers);  // x is complete
 	{
 		// z[d][p] = b[d] + sum_c x[c][p] * W[d][c], c ascending from 0 (conv3d of the oracle with k = 1), d = 32q .. 32q + 31
 		float acc[32];
 #pragma unroll
 		for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-		const float4* wp = reinterpret_cast<const float4*>(w.proj_wt + q * 32);
-#pragma unroll 2
-		for (int c = 0; c < 128; ++c) {
-			const float xv = lds32(x + (uint32_t)(c * 64 + p) * 4);
+#pragma unroll 1
+		for (int ch = 0; ch < kProjChunks; ++ch, ++load) {
+			const uint32_t slot = load % kStages;
+			mbar_wait(bar_w_full(bars, slot), (load / kStages) & 1u);
+			const uint32_t wbase = ring + slot * kUnitBytes + (uint32_t)q * 128;
+#pragma unroll 4
+			for (int cl = 0; cl < 32; ++cl) {
+				const float xv = lds32(x + (uint32_t)((ch * 32 + cl) * 64 + p) * 4);
 #pragma unroll
-			for (int j4 = 0; j4 < 8; ++j4) {
-				const float4 w4 = __ldg(wp + c * 32 + j4);
-				acc[4 * j4] = fmaf(xv, w4.x, acc[4 * j4]);
-				acc[4 * j4 + 1] = fmaf(xv, w4.y, acc[4 * j4 + 1]);
-				acc[4 * j4 + 2] = fmaf(xv, w4.z, acc[4 * j4 + 2]);
-				acc[4 * j4 + 3] = fmaf(xv, w4.w, acc[4 * j4 + 3]);
+				for (int j4 = 0; j4 < 8; ++j4) {
+					const uint4 raw = lds128(wbase + (uint32_t)cl * 512 + j4 * 16);
+					acc[4 * j4] = fmaf(xv, __uint_as_float(raw.x), acc[4 * j4]);
+					acc[4 * j4 + 1] = fmaf(xv, __uint_as_float(raw.y), acc[4 * j4 + 1]);
+					acc[4 * j4 + 2] = fmaf(xv, __uint_as_float(raw.z), acc[4 * j4 + 2]);
+					acc[4 * j4 + 3] = fmaf(xv, __uint_as_float(raw.w), acc[4 * j4 + 3]);
+				}
 			}
+			named_bar_sync(kBarWorkers, kWorkers);  // every worker is done with the slot
+			if (releaser) mbar_arrive(bar_w_empty(bars, slot));
 		}
 #pragma unroll
 		for (int j = 0; j < 32; ++j) {
@@ -205,41 +221,41 @@ __device__ __forceinline__ void project_and_quantize(const Encoder128BackWeights
 	}
 	named_bar_sync(kBarWorkers, kWorkers);  // z is complete
 	{
-		// dist_k = (sum_d z_d^2 + |e_k|^2) - 2 * sum_d z_d e_kd, every sum sequential in d; first minimum wins
+		// dist_k = (sum_d z_d^2 + |e_k|^2) - 2 * sum_d z_d e_kd, every sum sequential in d; first minimum wins.
+		// This thread: codes 64q .. 64q + 63, all 64 dot products carried through the 8 chunks.
+		float dot[64];
+#pragma unroll
+		for (int j = 0; j < 64; ++j) dot[j] = 0.f;
 		float zz = 0.f;
-#pragma unroll 8
-		for (int d = 0; d < 128; ++d) {
-			const float zv = lds32(z + (uint32_t)(d * 64 + p) * 4);
-			zz = fmaf(zv, zv, zz);
+#pragma unroll 1
+		for (int ch = 0; ch < kEmbChunks; ++ch, ++load) {
+			const uint32_t slot = load % kStages;
+			mbar_wait(bar_w_full(bars, slot), (load / kStages) & 1u);
+			const uint32_t ebase = ring + slot * kUnitBytes + (uint32_t)q * 256;
+#pragma unroll 2
+			for (int dl = 0; dl < 16; ++dl) {
+				const float zv = lds32(z + (uint32_t)((ch * 16 + dl) * 64 + p) * 4);
+				zz = fmaf(zv, zv, zz);
+#pragma unroll
+				for (int j4 = 0; j4 < 16; ++j4) {
+					const uint4 raw = lds128(ebase + (uint32_t)dl * 1024 + j4 * 16);
+					dot[4 * j4] = fmaf(zv, __uint_as_float(raw.x), dot[4 * j4]);
+					dot[4 * j4 + 1] = fmaf(zv, __uint_as_float(raw.y), dot[4 * j4 + 1]);
+					dot[4 * j4 + 2] = fmaf(zv, __uint_as_float(raw.z), dot[4 * j4 + 2]);
+					dot[4 * j4 + 3] = fmaf(zv, __uint_as_float(raw.w), dot[4 * j4 + 3]);
+				}
+			}
+			named_bar_sync(kBarWorkers, kWorkers);
+			if (releaser) mbar_arrive(bar_w_empty(bars, slot));
 		}
 		float best = INFINITY;
 		int bi = 0;
-#pragma unroll 1
-		for (int k0 = q * 64; k0 < q * 64 + 64; k0 += 8) {
-			float dot[8];
 #pragma unroll
-			for (int j = 0; j < 8; ++j) dot[j] = 0.f;
-			const float4* ep = reinterpret_cast<const float4*>(w.emb_t + k0);
-#pragma unroll 4
-			for (int d = 0; d < 128; ++d) {
-				const float zv = lds32(z + (uint32_t)(d * 64 + p) * 4);
-				const float4 e0 = __ldg(ep + d * 64), e1 = __ldg(ep + d * 64 + 1);
-				dot[0] = fmaf(zv, e0.x, dot[0]);
-				dot[1] = fmaf(zv, e0.y, dot[1]);
-				dot[2] = fmaf(zv, e0.z, dot[2]);
-				dot[3] = fmaf(zv, e0.w, dot[3]);
-				dot[4] = fmaf(zv, e1.x, dot[4]);
-				dot[5] = fmaf(zv, e1.y, dot[5]);
-				dot[6] = fmaf(zv, e1.z, dot[6]);
-				dot[7] = fmaf(zv, e1.w, dot[7]);
-			}
-#pragma unroll
-			for (int j = 0; j < 8; ++j) {
-				const float dist = (zz + __ldg(w.emb_sq + k0 + j)) - 2.f * dot[j];
-				if (dist < best) {
-					best = dist;
-					bi = k0 + j;
-				}
+		for (int j = 0; j < 64; ++j) {
+			const float dist = (zz + __ldg(w.emb_sq + q * 64 + j)) - 2.f * dot[j];
+			if (dist < best) {
+				best = dist;
+				bi = q * 64 + j;
 			}
 		}
 		s_best[q * 64 + p] = best;
@@ -300,13 +316,17 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 	if (warp == kProducerWarp) {
 		// ===================== TMA producer: one contiguous 24 KB unit per (pass, step, hi | lo) =====================
 		if (lane == 0) {
-			const uint32_t total = (uint32_t)(my_groups * kEnc128BackUnits);
+			const uint32_t total = (uint32_t)(my_groups * kRingLoadsPerPair);
 #pragma unroll 1
 			for (uint32_t issued = 0; issued < total; ++issued) {
-				const uint32_t s = issued % kStages, u = issued % kEnc128BackUnits;
+				const uint32_t s = issued % kStages, u = issued % kRingLoadsPerPair;
+				const bool conv = u < (uint32_t)kEnc128BackUnits;
+				const uint32_t bytes = conv ? kUnitBytes : kVqChunkBytes;
+				const uint8_t* src = conv ? w.units + (size_t)u * kUnitBytes
+				                          : reinterpret_cast<const uint8_t*>(w.vq_stream) + (size_t)(u - kEnc128BackUnits) * kVqChunkBytes;
 				mbar_wait(bar_w_empty(bars, s), ((issued / kStages) & 1u) ^ 1u);
-				mbar_arrive_expect_tx(bar_w_full(bars, s), kUnitBytes);
-				tma_load_1d(ring + s * kUnitBytes, w.units + (size_t)u * kUnitBytes, kUnitBytes, bar_w_full(bars, s));
+				mbar_arrive_expect_tx(bar_w_full(bars, s), bytes);
+				tma_load_1d(ring + s * kUnitBytes, src, bytes, bar_w_full(bars, s));
 			}
 		}
 		__syncwarp();
@@ -352,6 +372,7 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 					if (u == kSteps - 1 && leader) tc_commit(bar_d_full(bars));
 				}
 			}
+			unit += kProjChunks + kEmbChunks;  // ring loads consumed by the worker warps
 		}
 		__syncwarp();
 	} else {
@@ -406,8 +427,8 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 						if (lane == 0) mbar_arrive(bar_a_full(bars, ab));
 					}
 				}
-				project_and_quantize(w, s_par, bufP, bufQ, scratch + kScrBest, reinterpret_cast<int*>(scratch + kScrBi), t256, leaf, leaf < n_leaves,
-				                     indices, tap_stage, tap_out);
+				project_and_quantize(w, s_par, bars, ring, (uint32_t)g * kRingLoadsPerPair + kEnc128BackUnits, bufP, bufQ, scratch + kScrBest,
+				                     reinterpret_cast<int*>(scratch + kScrBi), t256, false, leaf, leaf < n_leaves, indices, tap_stage, tap_out);
 			}
 		} else {
 			// ---------- epilogue warps ----------
@@ -533,8 +554,8 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 						if (tap_stage == 2 && leaf_ok) tap_out[leaf * 8192 + (c0 + j) * 64 + pos] = xv;
 					}
 				}
-				project_and_quantize(w, s_par, bufP, bufQ, scratch + kScrBest, reinterpret_cast<int*>(scratch + kScrBi), t256, leaf, leaf_ok, indices,
-				                     tap_stage, tap_out);
+				project_and_quantize(w, s_par, bars, ring, (uint32_t)g * kRingLoadsPerPair + kEnc128BackUnits, bufP, bufQ, scratch + kScrBest,
+				                     reinterpret_cast<int*>(scratch + kScrBi), t256, threadIdx.x == 0, leaf, leaf_ok, indices, tap_stage, tap_out);
 			}
 		}
 	}

@@ -28,8 +28,7 @@ struct Encoder128BackWeights {
 	const float* par;       // par128e::total floats
 	const float* fc0;       // encoder.attn.fc.0.weight [32][128]
 	const float* fc2;       // encoder.attn.fc.2.weight [128][32]
-	const float* proj_wt;   // encoder.proj.weight transposed to [128 c][128 d]
-	const float* emb_t;     // quantizer.embedding transposed to [128 d][256 k]
+	const float* vq_stream; // encoder.proj.weight transposed to [128 c][128 d], then quantizer.embedding transposed to [128 d][256 k]
 	const float* emb_sq;    // [256] sum_d e_kd^2 (fp32, sequential in d as the oracle's)
 };
 

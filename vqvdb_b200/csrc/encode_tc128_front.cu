@@ -243,6 +243,9 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 					const int e = wt + i * 512, c = e >> 9, p = e & 511;
 					s_in[c * 1000 + ((p >> 6) + 1) * 100 + (((p >> 3) & 7) + 1) * 10 + (p & 7) + 1] = __ldcs(src + e);
 				}
+				named_bar_sync(kBarWorkers, kWorkers);  // also: nobody reads the previous leaf's planes any more
+				// pre.0's weights [3][27][64] fp32 (20 KB) over the start of the (idle) hi plane: broadcast reads from shared memory
+				for (int i = wt; i < 81 * 16; i += kWorkers) sts128(plane_hi + (uint32_t)i * 16, __ldg(reinterpret_cast<const uint4*>(w.pre_wt) + i));
 				named_bar_sync(kBarWorkers, kWorkers);
 				const int pd = wt >> 6, ph = (wt >> 3) & 7, pw = wt & 7;
 				const float* ip = s_in + pd * 100 + ph * 10 + pw;
@@ -253,21 +256,21 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 					float acc[8];
 #pragma unroll
 					for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-					const float4* wp = reinterpret_cast<const float4*>(w.pre_wt + cb * 8);
+					const uint32_t wp = plane_hi + (uint32_t)cb * 32;
 #pragma unroll 1
 					for (int ic = 0; ic < 3; ++ic) {
 #pragma unroll
 						for (int tap = 0; tap < 27; ++tap) {
 							const float xv = ip[ic * 1000 + (tap / 9) * 100 + ((tap / 3) % 3) * 10 + tap % 3];
-							const float4 w0 = __ldg(wp + (ic * 27 + tap) * 16), w1 = __ldg(wp + (ic * 27 + tap) * 16 + 1);
-							acc[0] = fmaf(xv, w0.x, acc[0]);
-							acc[1] = fmaf(xv, w0.y, acc[1]);
-							acc[2] = fmaf(xv, w0.z, acc[2]);
-							acc[3] = fmaf(xv, w0.w, acc[3]);
-							acc[4] = fmaf(xv, w1.x, acc[4]);
-							acc[5] = fmaf(xv, w1.y, acc[5]);
-							acc[6] = fmaf(xv, w1.z, acc[6]);
-							acc[7] = fmaf(xv, w1.w, acc[7]);
+							const uint4 w0 = lds128(wp + (uint32_t)(ic * 27 + tap) * 256), w1 = lds128(wp + (uint32_t)(ic * 27 + tap) * 256 + 16);
+							acc[0] = fmaf(xv, __uint_as_float(w0.x), acc[0]);
+							acc[1] = fmaf(xv, __uint_as_float(w0.y), acc[1]);
+							acc[2] = fmaf(xv, __uint_as_float(w0.z), acc[2]);
+							acc[3] = fmaf(xv, __uint_as_float(w0.w), acc[3]);
+							acc[4] = fmaf(xv, __uint_as_float(w1.x), acc[4]);
+							acc[5] = fmaf(xv, __uint_as_float(w1.y), acc[5]);
+							acc[6] = fmaf(xv, __uint_as_float(w1.z), acc[6]);
+							acc[7] = fmaf(xv, __uint_as_float(w1.w), acc[7]);
 						}
 					}
 					float s = 0.f;

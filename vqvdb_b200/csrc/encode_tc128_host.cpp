@@ -183,6 +183,15 @@ std::vector<float> build_encoder128_front_params(const WeightPack& p) {
 	return out;
 }
 
+std::vector<float> build_proj_transposed(const WeightPack& p) {
+	const PackTensor& t = p.get("encoder.proj.weight");  // [D][C][1][1][1]
+	const int D = t.dims[0], C = t.dims[1];
+	std::vector<float> out((size_t)D * C);
+	for (int d = 0; d < D; ++d)
+		for (int c = 0; c < C; ++c) out[(size_t)c * D + d] = t.data[(size_t)d * C + c];
+	return out;
+}
+
 std::vector<float> build_embedding_transposed(const WeightPack& p) {
 	const PackTensor& e = p.get("quantizer.embedding");
 	const int K = e.dims[0], D = e.dims[1];

@@ -48,5 +48,6 @@ std::vector<float> build_encoder128_back_params(const WeightPack& pack);
 std::vector<uint8_t> build_encoder128_front_units(const WeightPack& pack);
 std::vector<float> build_encoder128_front_params(const WeightPack& pack);
 std::vector<float> build_embedding_transposed(const WeightPack& pack);  // [D][K]
+std::vector<float> build_proj_transposed(const WeightPack& pack);       // encoder.proj.weight as [c][d]
 
 }  // namespace vqvdb
