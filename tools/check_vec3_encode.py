@@ -49,6 +49,17 @@ def main():
         got = tap.cpu().numpy().reshape(want.shape)
         print("tap %d: max |err| %.3e  rms %.3e  scale %.3e" % (stage, np.abs(got - want).max(), np.sqrt(((got - want) ** 2).mean()), np.abs(want).max()))
 
+    # phase timestamps of the second leaf / pair of CTA 0 (cycles since the leaf / pair started)
+    nprof = 148 * 6
+    xp = torch.from_numpy(np.tile(x, (1, 1, 1, 1, 1))[:nprof]).cuda()
+    ip = torch.empty((nprof, 64), dtype=torch.uint8, device="cuda")
+    tap = torch.zeros((64,), dtype=torch.float32, device="cuda")
+    tc.debug_encode_tap(xp, nprof, 100, tap, ip, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    t = tap.cpu().numpy()
+    print("front stamps [pre conv | pre end | conv1 tiles | gn2 sweeps | conv2 tiles | split sweep | down]:", [int(v) for v in t[:8]])
+    print("back stamps [prep | r0c1 | r0c2 | r1c1 | r1c2 | attention | proj+vq]:", [int(v) for v in t[16:24]])
+
     for name, xs in (("sparse1024", x), ("smoke256", synth.smoke_leaves(256, seed=5, channels=3)), ("noise64", synth.noise_leaves(64, seed=6, channels=3))):
         gg = np.load(os.path.join(REPO, "tests", "golden", "vec3_%s_seed%d.npz" % (name, {"sparse1024": 7, "smoke256": 5, "noise64": 6}[name])))
         m = gg["indices"].shape[0]

@@ -930,16 +930,16 @@ int vqvdb_b200_debug_encode_tap(vqvdb_b200_codec* c, const float* dev_leaves, in
 		CUDA_TRY(cudaSetDevice(c->device));
 		if (c->generic) {  // vec3: stages 0..3 = res_stack.0, res_stack.1, attention, proj, each [leaf][128][64]
 			// ... 4, 5 = pre (GroupNorm + ReLU), the 8^3 residual block, each [leaf][64][512]; 6 = down1 [leaf][128][64]
-			if (stage > 6 || n > kEnc128Batch) return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "debug_encode_tap: bad stage or too many leaves");
+			if ((stage > 6 && stage != 100) || n > kEnc128Batch) return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "debug_encode_tap: bad stage or too many leaves");
 			float* scratch = c->enc128_scratch + (size_t)kSlots * vqvdb::encode_tc128_front_scratch_floats(c->num_sms);
 			float* y = c->enc128_y + (size_t)kSlots * kEnc128Batch * 8192;
 			const cudaStream_t st = (cudaStream_t)stream;
 			if (kEnc128GenericFront) {
 				float* gscratch = c->gen_scratch + (size_t)kSlots * vqvdb::generic_scratch_floats(c->gen_grid);
 				CUDA_TRY(vqvdb::launch_encode_generic_front(c->gen, dev_leaves, n, y, gscratch, c->gen_grid, st));
-			} else CUDA_TRY(vqvdb::launch_encode_tc128_front(c->enc128_front, dev_leaves, n, y, scratch, c->num_sms, st, stage >= 4 ? stage - 4 : -1, dev_tap));
+			} else CUDA_TRY(vqvdb::launch_encode_tc128_front(c->enc128_front, dev_leaves, n, y, scratch, c->num_sms, st, stage == 100 ? 100 : stage >= 4 ? stage - 4 : -1, dev_tap));
 			if (stage == 6) CUDA_TRY(cudaMemcpyAsync(dev_tap, y, (size_t)n * 8192 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-			CUDA_TRY(vqvdb::launch_encode_tc128_back(c->enc128_back, y, n, dev_indices, c->num_sms, st, stage <= 3 ? stage : -1, dev_tap));
+			CUDA_TRY(vqvdb::launch_encode_tc128_back(c->enc128_back, y, n, dev_indices, c->num_sms, st, stage <= 3 || stage == 100 ? stage : -1, dev_tap));
 			return VQVDB_B200_OK;
 		}
 		CUDA_TRY(vqvdb::launch_encode_tc(c->enc, c->enc_tc, dev_leaves, n, dev_indices, c->num_sms, (cudaStream_t)stream, stage, dev_tap));

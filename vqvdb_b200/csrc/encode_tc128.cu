@@ -60,8 +60,8 @@ constexpr uint32_t kNumBars = 2 * kStages + 2 + 2 + 1 + 1 + 1;  // w_full, w_emp
 constexpr uint32_t kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr uint32_t kOffPar = (kOffTmemSlot + 16 + 15) & ~15u;
 constexpr uint32_t kOffScratch = kOffPar + par128e::total * 4;
-// per-leaf scratch (floats): exch [2 slots][2 warps][2 halves][8], part [2 wil][128], scale [128], hid [32], best [4][64], best index [4][64]
-constexpr uint32_t kScrExch = 0, kScrPart = 64, kScrScale = 320, kScrHid = 448, kScrBest = 480, kScrBi = 736, kScratchFloats = 992;
+// per-leaf scratch (floats): exch [2 slots][2 warps][2 halves][8], part [2 wil][128], scale [128], hid [32], best [16][64], best index [16][64]
+constexpr uint32_t kScrExch = 0, kScrPart = 64, kScrScale = 320, kScrHid = 448, kScrBest = 480, kScrBi = 1504, kScratchFloats = 2528;
 constexpr uint32_t kSmemBytes = kOffScratch + 2 * kScratchFloats * 4;
 static_assert(kSmemBytes <= 227 * 1024, "encode_tc128 back smem budget");
 static_assert(kOffBar % 8 == 0 && kOffPar % 16 == 0 && kOffScratch % 16 == 0, "alignment");
@@ -177,99 +177,125 @@ __device__ __forceinline__ void store_row32_split(uint32_t buf, int pos, int c16
 	}
 }
 
-// proj + distances + argmin for one leaf by its 256 worker threads: t = (quarter q of the outputs / codes) * 64 + position p.
+// proj + distances + argmin for one leaf by its 256 worker threads.  A thread owns FOUR positions (4 pq .. 4 pq + 3, pq = t & 15)
+// and one of 16 groups (grp = t >> 4) of 8 projected dims / 16 codes, so that every weight it fetches from shared memory
+// feeds four FMAs (the phase is bound by shared-memory instruction issue otherwise).
 // x: fp32 [128 c][64 pos] (attention output), z: fp32 [128 d][64 pos] scratch, both in shared memory.  The weights arrive
-// through the ring (first_load = index of the pair's first fp32 chunk among all ring loads of this CTA); every lane of
-// a warp reads the same weight address (a broadcast).
+// through the ring (first_load = index of the pair's first fp32 chunk among all ring loads of this CTA).
 __device__ __forceinline__ void project_and_quantize(const Encoder128BackWeights& w, const float* s_par, uint32_t bars, uint32_t ring, uint32_t first_load,
                                                      uint32_t x, uint32_t z, float* s_best, int* s_bi, int t, bool releaser, int64_t leaf, bool leaf_ok,
                                                      uint8_t* __restrict__ indices, int tap_stage, float* __restrict__ tap_out) {
-	const int p = t & 63, q = t >> 6;
+	const int pq = t & 15, grp = t >> 4;
 	uint32_t load = first_load;
 	named_bar_sync(kBarWorkers, kWorkers);  // x is complete
 	{
-		// z[d][p] = b[d] + sum_c x[c][p] * W[d][c], c ascending from 0 (conv3d of the oracle with k = 1), d = 32q .. 32q + 31
-		float acc[32];
+		// z[d][p] = b[d] + sum_c x[c][p] * W[d][c], c ascending from 0 (conv3d of the oracle with k = 1), d = 8 grp .. 8 grp + 7
+		float acc[8][4];
 #pragma unroll
-		for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+		for (int j = 0; j < 8; ++j)
+#pragma unroll
+			for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 #pragma unroll 1
 		for (int ch = 0; ch < kProjChunks; ++ch, ++load) {
 			const uint32_t slot = load % kStages;
 			mbar_wait(bar_w_full(bars, slot), (load / kStages) & 1u);
-			const uint32_t wbase = ring + slot * kUnitBytes + (uint32_t)q * 128;
+			const uint32_t wbase = ring + slot * kUnitBytes + (uint32_t)grp * 32;
 #pragma unroll 4
 			for (int cl = 0; cl < 32; ++cl) {
-				const float xv = lds32(x + (uint32_t)((ch * 32 + cl) * 64 + p) * 4);
+				const uint4 xr = lds128(x + (uint32_t)((ch * 32 + cl) * 64 + pq * 4) * 4);
+				const float xv[4] = {__uint_as_float(xr.x), __uint_as_float(xr.y), __uint_as_float(xr.z), __uint_as_float(xr.w)};
 #pragma unroll
-				for (int j4 = 0; j4 < 8; ++j4) {
+				for (int j4 = 0; j4 < 2; ++j4) {
 					const uint4 raw = lds128(wbase + (uint32_t)cl * 512 + j4 * 16);
-					acc[4 * j4] = fmaf(xv, __uint_as_float(raw.x), acc[4 * j4]);
-					acc[4 * j4 + 1] = fmaf(xv, __uint_as_float(raw.y), acc[4 * j4 + 1]);
-					acc[4 * j4 + 2] = fmaf(xv, __uint_as_float(raw.z), acc[4 * j4 + 2]);
-					acc[4 * j4 + 3] = fmaf(xv, __uint_as_float(raw.w), acc[4 * j4 + 3]);
+					const float wv[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
+#pragma unroll
+					for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+						for (int i = 0; i < 4; ++i) acc[4 * j4 + jj][i] = fmaf(xv[i], wv[jj], acc[4 * j4 + jj][i]);
 				}
 			}
 			named_bar_sync(kBarWorkers, kWorkers);  // every worker is done with the slot
 			if (releaser) mbar_arrive(bar_w_empty(bars, slot));
 		}
 #pragma unroll
-		for (int j = 0; j < 32; ++j) {
-			const float zv = acc[j] + s_par[par128e::proj_b + q * 32 + j];
-			sts32(z + (uint32_t)((q * 32 + j) * 64 + p) * 4, zv);
-			if (tap_stage == 3 && leaf_ok) tap_out[leaf * 8192 + (q * 32 + j) * 64 + p] = zv;
+		for (int j = 0; j < 8; ++j) {
+			const int d = grp * 8 + j;
+			const float b = s_par[par128e::proj_b + d];
+			uint4 o;
+			o.x = __float_as_uint(acc[j][0] + b);
+			o.y = __float_as_uint(acc[j][1] + b);
+			o.z = __float_as_uint(acc[j][2] + b);
+			o.w = __float_as_uint(acc[j][3] + b);
+			sts128(z + (uint32_t)(d * 64 + pq * 4) * 4, o);
+			if (tap_stage == 3 && leaf_ok) {
+#pragma unroll
+				for (int i = 0; i < 4; ++i) tap_out[leaf * 8192 + d * 64 + pq * 4 + i] = acc[j][i] + b;
+			}
 		}
 	}
 	named_bar_sync(kBarWorkers, kWorkers);  // z is complete
 	{
 		// dist_k = (sum_d z_d^2 + |e_k|^2) - 2 * sum_d z_d e_kd, every sum sequential in d; first minimum wins.
-		// This thread: codes 64q .. 64q + 63, all 64 dot products carried through the 8 chunks.
-		float dot[64];
+		// This thread: codes 16 grp .. 16 grp + 15 for its four positions, all 64 dot products carried through the 8 chunks.
+		float dot[16][4];
 #pragma unroll
-		for (int j = 0; j < 64; ++j) dot[j] = 0.f;
-		float zz = 0.f;
+		for (int j = 0; j < 16; ++j)
+#pragma unroll
+			for (int i = 0; i < 4; ++i) dot[j][i] = 0.f;
+		float zz[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
 		for (int ch = 0; ch < kEmbChunks; ++ch, ++load) {
 			const uint32_t slot = load % kStages;
 			mbar_wait(bar_w_full(bars, slot), (load / kStages) & 1u);
-			const uint32_t ebase = ring + slot * kUnitBytes + (uint32_t)q * 256;
+			const uint32_t ebase = ring + slot * kUnitBytes + (uint32_t)grp * 64;
 #pragma unroll 2
 			for (int dl = 0; dl < 16; ++dl) {
-				const float zv = lds32(z + (uint32_t)((ch * 16 + dl) * 64 + p) * 4);
-				zz = fmaf(zv, zv, zz);
+				const uint4 zr = lds128(z + (uint32_t)((ch * 16 + dl) * 64 + pq * 4) * 4);
+				const float zv[4] = {__uint_as_float(zr.x), __uint_as_float(zr.y), __uint_as_float(zr.z), __uint_as_float(zr.w)};
 #pragma unroll
-				for (int j4 = 0; j4 < 16; ++j4) {
+				for (int i = 0; i < 4; ++i) zz[i] = fmaf(zv[i], zv[i], zz[i]);
+#pragma unroll
+				for (int j4 = 0; j4 < 4; ++j4) {
 					const uint4 raw = lds128(ebase + (uint32_t)dl * 1024 + j4 * 16);
-					dot[4 * j4] = fmaf(zv, __uint_as_float(raw.x), dot[4 * j4]);
-					dot[4 * j4 + 1] = fmaf(zv, __uint_as_float(raw.y), dot[4 * j4 + 1]);
-					dot[4 * j4 + 2] = fmaf(zv, __uint_as_float(raw.z), dot[4 * j4 + 2]);
-					dot[4 * j4 + 3] = fmaf(zv, __uint_as_float(raw.w), dot[4 * j4 + 3]);
+					const float ev[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
+#pragma unroll
+					for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+						for (int i = 0; i < 4; ++i) dot[4 * j4 + jj][i] = fmaf(zv[i], ev[jj], dot[4 * j4 + jj][i]);
 				}
 			}
 			named_bar_sync(kBarWorkers, kWorkers);
 			if (releaser) mbar_arrive(bar_w_empty(bars, slot));
 		}
-		float best = INFINITY;
-		int bi = 0;
+		float best[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+		int bi[4] = {0, 0, 0, 0};
 #pragma unroll
-		for (int j = 0; j < 64; ++j) {
-			const float dist = (zz + __ldg(w.emb_sq + q * 64 + j)) - 2.f * dot[j];
-			if (dist < best) {
-				best = dist;
-				bi = q * 64 + j;
+		for (int j = 0; j < 16; ++j) {
+			const float esq = __ldg(w.emb_sq + grp * 16 + j);
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				const float dist = (zz[i] + esq) - 2.f * dot[j][i];
+				if (dist < best[i]) {
+					best[i] = dist;
+					bi[i] = grp * 16 + j;
+				}
 			}
 		}
-		s_best[q * 64 + p] = best;
-		s_bi[q * 64 + p] = bi;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			s_best[grp * 64 + pq * 4 + i] = best[i];
+			s_bi[grp * 64 + pq * 4 + i] = bi[i];
+		}
 	}
 	named_bar_sync(kBarWorkers, kWorkers);
 	if (t < 64) {
 		float best = s_best[t];
 		int bi = s_bi[t];
 #pragma unroll
-		for (int qq = 1; qq < 4; ++qq)
-			if (s_best[qq * 64 + t] < best) {
-				best = s_best[qq * 64 + t];
-				bi = s_bi[qq * 64 + t];
+		for (int gg = 1; gg < 16; ++gg)  // ascending code order, strict <: the first minimum wins
+			if (s_best[gg * 64 + t] < best) {
+				best = s_best[gg * 64 + t];
+				bi = s_bi[gg * 64 + t];
 			}
 		if (leaf_ok) indices[leaf * 64 + t] = (uint8_t)bi;
 	}
@@ -457,6 +483,12 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 			for (int64_t g = 0; g < my_groups; ++g) {
 				const int64_t leaf = (blockIdx.x + g * gridDim.x) * 2 + leaf_slot;
 				const bool leaf_ok = leaf < n_leaves;
+				const bool prof = tap_stage == 100 && threadIdx.x == 0 && blockIdx.x == 0 && g == 1;  // phase timestamps (tools/check_vec3_encode.py)
+				const long long prof_t0 = prof ? clock64() : 0;
+				int prof_n = 16;
+				auto stamp = [&]() {
+					if (prof) tap_out[prof_n++] = (float)(clock64() - prof_t0);
+				};
 				float* xg = y + (leaf_ok ? leaf : 0) * 8192;  // the residual stream x, [128 ch][64 pos] fp32, updated in place
 
 				float v[32];
@@ -470,6 +502,7 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 					store_row32_split(bufP, pos, c0 >> 3, v);
 				}
 				signal_input_ready();  // the mbarrier's release/acquire orders the stores above before the stagers' loads
+				stamp();
 
 #pragma unroll 1
 				for (int r = 0; r < 2; ++r) {
@@ -485,6 +518,7 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 						store_row32_split(bufQ, pos, c0 >> 3, v);
 					}
 					signal_input_ready();  // conv2's input
+					stamp();
 					// conv2 -> x' = x + 0.1 * (conv2 + bias)
 #pragma unroll 1
 					for (int hh = 0; hh < 2; ++hh) {
@@ -519,6 +553,7 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 						}
 					}
 					if (r == 0) signal_input_ready();  // res_stack.1.conv1's input
+					stamp();
 				}
 
 				// ---- ChannelAttention(128): mean over the leaf -> 128 -> 32 -> 128 -> sigmoid ; x'' * scale in place ----
@@ -554,8 +589,10 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 						if (tap_stage == 2 && leaf_ok) tap_out[leaf * 8192 + (c0 + j) * 64 + pos] = xv;
 					}
 				}
+				stamp();
 				project_and_quantize(w, s_par, bars, ring, (uint32_t)g * kRingLoadsPerPair + kEnc128BackUnits, bufP, bufQ, scratch + kScrBest,
 				                     reinterpret_cast<int*>(scratch + kScrBi), t256, threadIdx.x == 0, leaf, leaf_ok, indices, tap_stage, tap_out);
+				stamp();
 			}
 		}
 	}

@@ -81,13 +81,11 @@ __device__ __forceinline__ void workers_allreduce8(float (&v)[8], float* red, ui
 		for (int i = 0; i < 8; ++i) x[warp * 8 + i] = v[i];
 	}
 	named_bar_sync(kBarWorkers, kWorkers);
+	float s = 0.f;  // lane i (mod 8) adds up column i, in the same order in every warp
 #pragma unroll
-	for (int i = 0; i < 8; ++i) {
-		float s = 0.f;
+	for (int wi = 0; wi < 16; ++wi) s += x[wi * 8 + (lane & 7)];
 #pragma unroll
-		for (int wi = 0; wi < 16; ++wi) s += x[wi * 8 + i];
-		v[i] = s;
-	}
+	for (int i = 0; i < 8; ++i) v[i] = __shfl_sync(0xffffffffu, s, i);
 	++count;  // the other slot next time: this one is rewritten only after one more barrier has been passed
 }
 
@@ -234,6 +232,12 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 #pragma unroll 1
 		for (int64_t g = 0; g < my_leaves; ++g) {
 			const int64_t leaf = blockIdx.x + g * gridDim.x;
+			const bool prof = tap_stage == 100 && threadIdx.x == 0 && blockIdx.x == 0 && g == 1;  // phase timestamps (tools/check_vec3_encode.py)
+			const long long prof_t0 = prof ? clock64() : 0;
+			int prof_n = 0;
+			auto stamp = [&]() {
+				if (prof) tap_out[prof_n++] = (float)(clock64() - prof_t0);
+			};
 
 			// ---------- pre phase, all workers: pre.0 + GroupNorm + ReLU -> x ; res.gn1 + ReLU -> planes ----------
 			{
@@ -247,44 +251,69 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 				// pre.0's weights [3][27][64] fp32 (20 KB) over the start of the (idle) hi plane: broadcast reads from shared memory
 				for (int i = wt; i < 81 * 16; i += kWorkers) sts128(plane_hi + (uint32_t)i * 16, __ldg(reinterpret_cast<const uint4*>(w.pre_wt) + i));
 				named_bar_sync(kBarWorkers, kWorkers);
-				const int pd = wt >> 6, ph = (wt >> 3) & 7, pw = wt & 7;
-				const float* ip = s_in + pd * 100 + ph * 10 + pw;
-				float gsum[8];
-				// out[c] = b[c] + sum_{ic, kd, kh, kw} in * w, ascending, as conv3d of the oracle (halo taps add an exact 0)
+				{
+					// out[c] = b[c] + sum_{ic, kd, kh, kw} in * w, ascending, as conv3d of the oracle (halo taps add an exact 0).
+					// A thread owns four consecutive positions along w and, in two rounds, 8 of the 16 channels of its warp's
+					// channel group: every weight fetched from shared memory feeds four FMAs, every input value up to three taps.
+					const int pq = wt & 127, pd = pq >> 4, ph = (pq >> 1) & 7, w0 = (pq & 1) * 4, cgrp = wt >> 7;
+					const uint32_t in0 = s_base + kOffIn + (uint32_t)(pd * 100 + ph * 10 + w0) * 4;
 #pragma unroll 1
-				for (int cb = 0; cb < 8; ++cb) {
-					float acc[8];
+					for (int r = 0; r < 2; ++r) {
+						const int c0 = (cgrp * 2 + r) * 8;
+						float acc[8][4];
 #pragma unroll
-					for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-					const uint32_t wp = plane_hi + (uint32_t)cb * 32;
+						for (int j = 0; j < 8; ++j)
+#pragma unroll
+							for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 #pragma unroll 1
-					for (int ic = 0; ic < 3; ++ic) {
+						for (int ic = 0; ic < 3; ++ic) {
+#pragma unroll 1
+							for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
-						for (int tap = 0; tap < 27; ++tap) {
-							const float xv = ip[ic * 1000 + (tap / 9) * 100 + ((tap / 3) % 3) * 10 + tap % 3];
-							const uint4 w0 = lds128(wp + (uint32_t)(ic * 27 + tap) * 256), w1 = lds128(wp + (uint32_t)(ic * 27 + tap) * 256 + 16);
-							acc[0] = fmaf(xv, __uint_as_float(w0.x), acc[0]);
-							acc[1] = fmaf(xv, __uint_as_float(w0.y), acc[1]);
-							acc[2] = fmaf(xv, __uint_as_float(w0.z), acc[2]);
-							acc[3] = fmaf(xv, __uint_as_float(w0.w), acc[3]);
-							acc[4] = fmaf(xv, __uint_as_float(w1.x), acc[4]);
-							acc[5] = fmaf(xv, __uint_as_float(w1.y), acc[5]);
-							acc[6] = fmaf(xv, __uint_as_float(w1.z), acc[6]);
-							acc[7] = fmaf(xv, __uint_as_float(w1.w), acc[7]);
+								for (int kh = 0; kh < 3; ++kh) {
+									const uint32_t ia = in0 + (uint32_t)(ic * 1000 + kd * 100 + kh * 10) * 4;
+									float in[6];
+#pragma unroll
+									for (int i2 = 0; i2 < 3; ++i2) {
+										float2 v2;
+										asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v2.x), "=f"(v2.y) : "r"(ia + i2 * 8));
+										in[2 * i2] = v2.x;
+										in[2 * i2 + 1] = v2.y;
+									}
+#pragma unroll
+									for (int kw = 0; kw < 3; ++kw) {
+										const uint32_t wa = plane_hi + (uint32_t)((ic * 27 + (kd * 3 + kh) * 3 + kw) * 64 + c0) * 4;
+										const uint4 w0r = lds128(wa), w1r = lds128(wa + 16);
+										const float wv[8] = {__uint_as_float(w0r.x), __uint_as_float(w0r.y), __uint_as_float(w0r.z), __uint_as_float(w0r.w),
+										                     __uint_as_float(w1r.x), __uint_as_float(w1r.y), __uint_as_float(w1r.z), __uint_as_float(w1r.w)};
+#pragma unroll
+										for (int j = 0; j < 8; ++j)
+#pragma unroll
+											for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(in[i + kw], wv[j], acc[j][i]);
+									}
+								}
+							}
+						}
+						const int pos0 = pd * 64 + ph * 8 + w0;
+#pragma unroll
+						for (int j = 0; j < 8; ++j) {
+							const float bj = s_par[par128f::pre_b + c0 + j];
+							*reinterpret_cast<float4*>(xs + (c0 + j) * 512 + pos0) = make_float4(acc[j][0] + bj, acc[j][1] + bj, acc[j][2] + bj, acc[j][3] + bj);
 						}
 					}
-					float s = 0.f;
-#pragma unroll
-					for (int j = 0; j < 8; ++j) {
-						const float v = acc[j] + s_par[par128f::pre_b + cb * 8 + j];
-						xs[(cb * 8 + j) * 512 + wt] = v;  // stash (private to this thread until the barrier below)
-						s += v;
-					}
-					gsum[cb] = s;  // GroupNorm(8, 64): group cb = channels 8cb .. 8cb + 7
 				}
-				float v[64];
+				named_bar_sync(kBarWorkers, kWorkers);  // the conv output is complete in the scratch
+				stamp();
+				float v[64], gsum[8];
 #pragma unroll
 				for (int c = 0; c < 64; ++c) v[c] = xs[c * 512 + wt];
+#pragma unroll
+				for (int gI = 0; gI < 8; ++gI) {
+					float t = 0.f;
+#pragma unroll
+					for (int j = 0; j < 8; ++j) t += v[gI * 8 + j];
+					gsum[gI] = t;  // GroupNorm(8, 64): group = 8 consecutive channels
+				}
 				// pre.1 GroupNorm + ReLU (two-pass variance over 8 channels x 512 positions)
 				workers_allreduce8(gsum, s_red, n_red, warp, lane);
 				float mean[8], q[8];
@@ -347,6 +376,7 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 					sts128(plane_lo + off, lo);
 				}
 				named_bar_sync(kBarWorkers, kWorkers);  // planes and x complete (x is read by other threads from here on)
+				stamp();
 			}
 
 			if (is_stager) {
@@ -450,6 +480,7 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 						gs[j >> 3] += v[j];
 					}
 				}
+				stamp();
 				epi_allreduce4(gs, s_red, n_ered, quad, chalf, lane);
 				float mean[4], q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -485,6 +516,7 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 					}
 				}
 				signal_input_ready();  // layer 1: conv2's input
+				stamp();
 
 				// ---- conv2: x' = x + 0.1 * (conv2 + bias), in place in the scratch ; after the 4 tiles: x' split -> planes ----
 #pragma unroll 1
@@ -498,6 +530,7 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 						if (tap_stage == 1) tap_out[leaf * 32768 + (c0 + j) * 512 + pos] = xn;
 					}
 				}
+				stamp();
 #pragma unroll 1
 				for (int tile = 0; tile < kTiles; ++tile) {
 					const int pos = tile * 128 + row;
@@ -514,6 +547,7 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 					}
 				}
 				signal_input_ready();  // layer 2: down1's input
+				stamp();
 
 				// ---- down1: rows 0..63 are the 4^3 output positions; this thread: output channels 64 chalf .. + 63 ----
 				mbar_wait(bar_d_full(bars), passes & 1u);
@@ -538,6 +572,7 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 				__syncwarp();
 				if (lane == 0) mbar_arrive(bar_d_empty(bars));
 				++passes;
+				stamp();
 			}
 		}
 	}
