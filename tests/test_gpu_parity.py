@@ -282,15 +282,15 @@ def codec_vec3():
     pack = os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw")
     if not os.path.exists(pack):
         subprocess.check_call([sys.executable, os.path.join(REPO, "tools", "weights_pack.py"), "vec3"])
-    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack, decode_precision="fp32"), BackendType.B200)
-    assert c is not None and c.channels == 3 and c.decode_path == "fp32_generic"
+    c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack, decode_precision="fp32", encode_precision="fp32"), BackendType.B200)
+    assert c is not None and c.channels == 3 and c.decode_path == "fp32_generic" and c.encode_path == "fp32_generic"
     yield c
     c.close()
 
 
 @pytest.fixture(scope="module")
 def codec_vec3_tc():
-    """The vec3 model on its default paths: generic fp32 encoder, 128-channel tensor-core decoder (decode_tc128.cu)."""
+    """The vec3 model on its default paths: split-fp16 tensor-core encoder (encode_tc128*.cu), bf16 tensor-core decoder (decode_tc128.cu)."""
     import os
     import subprocess
     import sys
@@ -300,7 +300,7 @@ def codec_vec3_tc():
     if not os.path.exists(pack):
         subprocess.check_call([sys.executable, os.path.join(REPO, "tools", "weights_pack.py"), "vec3"])
     c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack), BackendType.B200)
-    assert c is not None and c.channels == 3 and c.decode_path == "bf16_tcgen05_c128_fold"
+    assert c is not None and c.channels == 3 and c.decode_path == "bf16_tcgen05_c128_fold" and c.encode_path == "fp16x2_tcgen05_c128"
     yield c
     c.close()
 
@@ -394,6 +394,72 @@ def test_vec3_matches_c_oracle_and_chunking(codec_vec3):
         assert np.array_equal(_decode(small, idx), _decode(codec_vec3, idx))
     finally:
         small.close()
+
+
+# The tensor-core vec3 encoder (encode_tc128_front.cu + encode_tc128.cu): split-fp16 operands, fp32-level accuracy.
+# Stage taps against the C oracle; measured max |err| is 2.4e-6 of the activation scale (profiles/r2_vec3_encode.txt),
+# the bound here is 2e-5 of it.
+@pytest.mark.parametrize("stage,oracle_stage,shape", [(4, 0, (64, 512)), (5, 1, (64, 512)), (6, 2, (128, 64)), (1, 3, (128, 64)),
+                                                      (2, 4, (128, 64)), (3, -1, (128, 64))])
+def test_vec3_tc_encoder_stage_taps_match_oracle(codec_vec3_tc, stage, oracle_stage, shape):
+    import os
+    import torch
+    from conftest import REPO
+    from oracle.pyoracle import COracle
+    o = COracle(os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw"))
+    n = 37                                                              # odd count: the last pair has a spare leaf slot
+    x = synth.smoke_leaves(64, seed=7, channels=3, sparse=True)[:n]
+    want = o.latents(x) if oracle_stage < 0 else o.encode_tap(x, oracle_stage, 64, 128)
+    xd = torch.from_numpy(x).cuda()
+    tap_d = torch.zeros((n,) + shape, dtype=torch.float32, device="cuda")
+    idx_d = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
+    codec_vec3_tc.debug_encode_tap(xd, n, stage, tap_d, idx_d, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = tap_d.cpu().numpy().reshape(want.shape)
+    scale = float(np.abs(want).max())
+    err = float(np.abs(got - want).max())
+    assert err <= 2e-5 * scale, "stage %d: max err %.4g vs activation scale %.4g" % (stage, err, scale)
+    assert np.array_equal(idx_d.cpu().numpy().reshape(n, 4, 4, 4), _encode(codec_vec3_tc, x))
+
+
+@pytest.mark.parametrize("name,gen", [("vec3_smoke256_seed5", lambda: synth.smoke_leaves(256, seed=5, channels=3)),
+                                      ("vec3_noise64_seed6", lambda: synth.noise_leaves(64, seed=6, channels=3)),
+                                      ("vec3_sparse1024_seed7", lambda: synth.smoke_leaves(1024, seed=7, channels=3, sparse=True))])
+def test_vec3_tc_encoder_matches_reference_classes(codec_vec3_tc, name, gen):
+    g = golden(name)
+    idx = _encode(codec_vec3_tc, gen())
+    assert_indices_match(idx, g["indices"], g["margins"])
+
+
+def test_vec3_tc_encoder_against_fp32_path_ragged_batches_and_deterministic(codec_vec3_tc, codec_vec3):
+    import torch
+    from oracle.pyoracle import COracle
+    import os
+    from conftest import REPO
+    x = synth.smoke_leaves(1024, seed=7, channels=3, sparse=True)
+    full = _encode(codec_vec3_tc, x)
+    for n in (1, 2, 3, 149, 297):                                       # odd counts; fewer leaves / pairs than CTAs
+        assert np.array_equal(_encode(codec_vec3_tc, x[:n]), full[:n]), n
+    assert np.array_equal(_encode(codec_vec3_tc, x), full)
+    # more than one front/back batch (148 SMs x 28 leaves) in one device call, against the fp32 kernel on a sample
+    reps = 5
+    big = np.tile(x, (reps, 1, 1, 1, 1))[: 4144 + 37]
+    bd = torch.from_numpy(big).cuda()
+    out = torch.empty((big.shape[0], 64), dtype=torch.uint8, device="cuda")
+    codec_vec3_tc.encode_device(bd, big.shape[0], out, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(-1, 4, 4, 4)
+    assert np.array_equal(got, np.tile(full, (reps, 1, 1, 1))[: big.shape[0]])
+    # different data: mixed fields, against the fp32 kernel and (where they differ) the oracle's margins
+    y = np.concatenate([synth.smoke_leaves(2048, seed=31, channels=3), synth.noise_leaves(512, seed=32, channels=3),
+                        synth.smoke_leaves(1536, seed=33, channels=3, sparse=True)])
+    a, b = _encode(codec_vec3_tc, y), _encode(codec_vec3, y)
+    diff = np.argwhere((a != b).reshape(len(y), -1).any(axis=1)).ravel()
+    assert len(diff) <= 8, "%d of %d leaves differ between the tensor-core and the fp32 encoder" % (len(diff), len(y))
+    if len(diff):
+        o = COracle(os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw"))
+        idx_o, margins = o.encode(y[diff], with_margins=True)
+        assert_indices_match(a[diff], idx_o, margins, max_frac=1.0)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -49,7 +49,7 @@ constexpr bool kEnc128GenericFront = true;   // bring-up aid: the 8^3 stage on t
 #else
 constexpr bool kEnc128GenericFront = false;
 #endif
-constexpr int64_t kEnc128Batch = 4096;        // leaves per front/back kernel pair of the vec3 encoder (128 MiB handed over)
+constexpr int kEnc128LeavesPerCta = 28;       // vec3 encoder: leaves per CTA and front/back kernel pair (a batch = num_sms x 28: both grids end level)
 constexpr uint32_t kDefaultChunk = 16384;   // leaves per chunk: 32 MiB of voxels, 1 MiB of indices
 // Calls of at most this many leaves (the reference's SOPs hand over 64 at a time by default, 1024 / 8192 at most:
 // SOP_VQVDB_Encoder.cpp:36, SOP_VQVDB_Decoder.cpp:32) skip the copy engines: the kernel reads its input from, and
@@ -175,6 +175,7 @@ struct vqvdb_b200_codec {
 	bool enc128 = false;             // the tensor-core vec3 encoder (encode_tc128.cu) serves this model's encode
 	uint8_t* enc128_arena = nullptr;  // its fp16 hi/lo unit streams, transposed codebook and fp32 parameter blocks
 	float* enc128_y = nullptr;        // per pipeline slot: the stride-2 conv's output of one batch of leaves
+	int64_t enc128_batch = 0;         // leaves per batch
 	vqvdb::Encoder128BackWeights enc128_back{};
 	vqvdb::Encoder128FrontWeights enc128_front{};
 	float* enc128_scratch = nullptr;  // per pipeline slot: the front kernel's per-CTA fp32 scratch
@@ -549,7 +550,8 @@ void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
 		CUDA_TRY(cudaMemcpy(c.enc128_arena, back.data(), back.size(), cudaMemcpyHostToDevice));
 		CUDA_TRY(cudaMemcpy(c.enc128_arena + off_par, back_par.data(), back_par.size() * sizeof(float), cudaMemcpyHostToDevice));
 		CUDA_TRY(cudaMemcpy(c.enc128_arena + off_emb, emb_t.data(), emb_t.size() * sizeof(float), cudaMemcpyHostToDevice));
-		CUDA_TRY(cudaMalloc(&c.enc128_y, (size_t)(kSlots + 1) * kEnc128Batch * 8192 * sizeof(float)));
+		c.enc128_batch = (int64_t)c.num_sms * kEnc128LeavesPerCta;
+		CUDA_TRY(cudaMalloc(&c.enc128_y, (size_t)(kSlots + 1) * c.enc128_batch * 8192 * sizeof(float)));
 		c.enc128_back.units = c.enc128_arena;
 		c.enc128_back.par = reinterpret_cast<const float*>(c.enc128_arena + off_par);
 		c.enc128_back.fc0 = m.e_fc0;
@@ -615,9 +617,9 @@ void launch_encode(vqvdb_b200_codec& c, const float* d_leaves, int64_t n, uint8_
 	if (c.generic && c.enc128 && c.encode_kind == 2) {
 		// two kernels per batch of leaves, the stride-2 conv's output (32 KB per leaf) handed over in global memory
 		float* scratch = c.enc128_scratch + (size_t)slot * vqvdb::encode_tc128_front_scratch_floats(c.num_sms);
-		float* y = c.enc128_y + (size_t)slot * kEnc128Batch * 8192;
-		for (int64_t first = 0; first < n; first += kEnc128Batch) {
-			const int64_t nb = std::min<int64_t>(kEnc128Batch, n - first);
+		float* y = c.enc128_y + (size_t)slot * c.enc128_batch * 8192;
+		for (int64_t first = 0; first < n; first += c.enc128_batch) {
+			const int64_t nb = std::min<int64_t>(c.enc128_batch, n - first);
 			if (kEnc128GenericFront) {
 				float* gscratch = c.gen_scratch + (size_t)slot * vqvdb::generic_scratch_floats(c.gen_grid);
 				CUDA_TRY(vqvdb::launch_encode_generic_front(c.gen, d_leaves + first * 1536, nb, y, gscratch, c.gen_grid, st));
@@ -930,9 +932,9 @@ int vqvdb_b200_debug_encode_tap(vqvdb_b200_codec* c, const float* dev_leaves, in
 		CUDA_TRY(cudaSetDevice(c->device));
 		if (c->generic) {  // vec3: stages 0..3 = res_stack.0, res_stack.1, attention, proj, each [leaf][128][64]
 			// ... 4, 5 = pre (GroupNorm + ReLU), the 8^3 residual block, each [leaf][64][512]; 6 = down1 [leaf][128][64]
-			if ((stage > 6 && stage != 100) || n > kEnc128Batch) return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "debug_encode_tap: bad stage or too many leaves");
+			if ((stage > 6 && stage != 100) || n > c->enc128_batch) return fail(c, VQVDB_B200_ERR_INVALID_ARGUMENT, "debug_encode_tap: bad stage or too many leaves");
 			float* scratch = c->enc128_scratch + (size_t)kSlots * vqvdb::encode_tc128_front_scratch_floats(c->num_sms);
-			float* y = c->enc128_y + (size_t)kSlots * kEnc128Batch * 8192;
+			float* y = c->enc128_y + (size_t)kSlots * c->enc128_batch * 8192;
 			const cudaStream_t st = (cudaStream_t)stream;
 			if (kEnc128GenericFront) {
 				float* gscratch = c->gen_scratch + (size_t)kSlots * vqvdb::generic_scratch_floats(c->gen_grid);
