@@ -636,7 +636,7 @@ def main():
         dom = "decode" if dec_ms >= enc_ms else "encode"
         dom_ms = max(dec_ms, enc_ms)
         flop = flop_dec if dom == "decode" else flop_enc
-        enc_tc = codec.encode_path == "fp16x2_tcgen05"
+        enc_tc = codec.encode_path.startswith("fp16x2_tcgen05")
         dec_tc = codec.decode_path.startswith("bf16_tcgen05")
         dom_on_tensor = (dom == "decode" and dec_tc) or (dom == "encode" and enc_tc)
         achieved = flop * L / (dom_ms / 1e3) / 1e12
@@ -650,11 +650,14 @@ def main():
         # tensor-core encoder: every GEMM is three fp16 products (hi*hi, hi*lo, lo*hi); pre.0 (221 184 MAC) stays on FFMA and
         # proj (262 144 MAC) is folded into the codebook, whose score GEMM shrinks from 64x128x256 to 64x32x256 (524 288 MAC):
         # MACs issued to the tensor pipe per leaf = 3 * (13 197 824 - 221 184 - 262 144 + 524 288)
-        enc_issued_tf = (3 * (13197824 - 221184 - 262144 + 524288) * 2 if enc_tc else flop_enc) * L / (enc_ms / 1e3) / 1e12
+        # vec3 (encode_tc128*.cu): the 64 -> 64, 64 -> 128 (stride 2) and 128 -> 128 convs run as three fp16 products each;
+        # pre.0, proj and the distances (5.8 M of the 246.4 M MACs) stay on FFMA
+        enc_tc_macs = (2 * 64 * 64 * 27 * 512 + 64 * 128 * 27 * 64 + 4 * 128 * 128 * 27 * 64) if vec3 else (13197824 - 221184 - 262144 + 524288)
+        enc_issued_tf = (3 * enc_tc_macs * 2 if enc_tc else flop_enc) * L / (enc_ms / 1e3) / 1e12
         traffic, traffic_source = (None, "no capture for this path")
-        if (dom == "encode" and enc_tc) or (dom == "decode" and codec.decode_path == "bf16_tcgen05_n192_fold"):
+        if (dom == "encode" and enc_tc and not vec3) or (dom == "decode" and codec.decode_path == "bf16_tcgen05_n192_fold"):
             traffic, traffic_source = ncu_traffic(dom, L)
-        enc_name = "encode_tc_kernel" if enc_tc else ("generic_encode_kernel" if vec3 else "encode_fp32_kernel")
+        enc_name = ("encode_tc128_front_kernel + encode_tc128_back_kernel" if vec3 else "encode_tc_kernel") if enc_tc else ("generic_encode_kernel" if vec3 else "encode_fp32_kernel")
         dec_name = ("decode_tc128_kernel" if vec3 else "decode_tc_kernel") if dec_tc else ("generic_decode_kernel" if vec3 else "decode_fp32_kernel")
         kernels = {
             enc_name: {

@@ -89,6 +89,9 @@ def test_parity_report_bounds():
                 assert r["psnr_db_vs_reference_recon"] >= 55.0, (path, name, r)
     for name, r in rep["vec3"].items():
         assert r["max_reference_margin_at_mismatch"] <= 1e-4, (name, r)
+        assert set(r["encoders"]) == {"fp16x2_tcgen05_c128", "fp32_generic"}
+        for er in r["encoders"].values():
+            assert er["max_reference_margin_at_mismatch"] <= 1e-4 and er["mismatch_frac"] <= MAX_MISMATCH_FRAC, (name, er)
         assert r["decode"]["fp32_generic"]["max_abs_diff"] <= 5e-5, (name, r)
         tc = r["decode"]["bf16_tcgen05_c128_fold"]
         assert tc["max_abs_diff"] <= 4e-2 and tc["psnr_db_vs_reference_recon"] >= 55.0, (name, r)

@@ -81,7 +81,7 @@ def main():
     pack = os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw")
     if os.path.exists(pack):
         for prec in ("default", "fp32"):
-            c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack, decode_precision=prec), BackendType.B200)
+            c = IVQVAECodec.create(CodecConfig(device=CodecConfig.Device.CUDA, source=pack, decode_precision=prec, encode_precision=prec), BackendType.B200)
             for name, gen in VEC3_CASES.items():
                 g = golden(name)
                 m = len(g["recon"])
@@ -91,7 +91,9 @@ def main():
                     row = index_row(enc(c, gen()), g)
                     row["encode_path"] = c.encode_path
                     row["decode"] = {}
+                    row["encoders"] = {}
                     rep["vec3"][name] = row
+                rep["vec3"][name]["encoders"][c.encode_path] = index_row(enc(c, gen()), g)
                 rep["vec3"][name]["decode"][c.decode_path] = rr
             c.close()
     worst = max(r["mismatch_frac"] for p in rep["encode"].values() for n, r in p.items() if r["latents"] >= 4096)
