@@ -37,4 +37,8 @@ if os.path.exists(pack):
     vidx = np.random.default_rng(3).integers(0, 256, size=(m, 4, 4, 4), dtype=np.uint8)
     vrec = c.decode(TensorView(vidx, list(vidx.shape), DataType.UINT8)).buffer
     print(c.decode_path, float(vrec.sum()))
+    # ... and its tensor-core encoder (encode_tc128_front.cu + encode_tc128.cu), same odd count
+    vx = synth.smoke_leaves(m, seed=9, channels=3, sparse=True)
+    venc = c.encode(TensorView(vx, list(vx.shape), DataType.FLOAT32)).buffer
+    print(c.encode_path, int(venc.astype(np.int64).sum()))
     c.close()

@@ -410,16 +410,45 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 		const uint32_t bufP = leaf_base, bufQ = leaf_base + kBufBytes;
 		float* scratch = reinterpret_cast<float*>(smem + kOffScratch) + leaf_slot * kScratchFloats;
 		const int t256 = (is_stager ? 128 : 0) + chalf * 64 + pos;  // thread index among the leaf's 256 workers
+		const uint32_t tmem_lane = tmem + ((uint32_t)(quad * 32) << 16);
 
-		if (is_stager) {
-			// ---------- stagers: tap-shifted activation rows (hi and lo planes) -> TMEM A buffers ----------
-			const int pd = pos >> 4, ph = (pos >> 2) & 3;
-			const uint32_t zero_row = s_base + kOffZero;
-			const uint32_t tmem_lane = tmem + ((uint32_t)(quad * 32) << 16);
-			uint32_t step = 0, layer = 0;
+		// stager state: tap-shifted activation rows (hi and lo planes) -> TMEM A buffers
+		const int pd = pos >> 4, ph = (pos >> 2) & 3;
+		const uint32_t zero_row = s_base + kOffZero;
+		uint32_t step = 0, layer = 0;
+		// epilogue state
+		Epi e;
+		e.quad = quad;
+		e.chalf = chalf;
+		e.lane = lane;
+		e.row = row;
+		e.leaf_slot = leaf_slot;
+		e.wil = (row >> 5) & 1;
+		e.pos = pos;
+		e.w = pos & 3;
+		e.bars = bars;
+		e.tmem_lane = tmem_lane;
+		float* exch = scratch + kScrExch;
+		float* s_part = scratch + kScrPart;
+		float* s_scale = scratch + kScrScale;
+		float* s_hid = scratch + kScrHid;
+		const int tl = chalf * 64 + pos;  // thread index among the leaf's 128 epilogue threads
+		auto signal_input_ready = [&]() {
+			__syncwarp();
+			if (lane == 0) mbar_arrive(bar_in_ready(bars));
+		};
+
 #pragma unroll 1
-			for (int64_t g = 0; g < my_groups; ++g) {
-				const int64_t leaf = (blockIdx.x + g * gridDim.x) * 2 + leaf_slot;
+		for (int64_t g = 0; g < my_groups; ++g) {
+			const int64_t leaf = (blockIdx.x + g * gridDim.x) * 2 + leaf_slot;
+			const bool leaf_ok = leaf < n_leaves;
+			const bool prof = tap_stage == 100 && threadIdx.x == 0 && blockIdx.x == 0 && g == 1;  // phase timestamps (tools/check_vec3_encode.py)
+			const long long prof_t0 = prof ? clock64() : 0;
+			int prof_n = 16;
+			auto stamp = [&]() {
+				if (prof) tap_out[prof_n++] = (float)(clock64() - prof_t0);
+			};
+			if (is_stager) {
 #pragma unroll 1
 				for (int l = 0; l < kConvs; ++l, ++layer) {
 					// the layer's input (P for conv1, Q for conv2) is complete
@@ -453,42 +482,7 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 						if (lane == 0) mbar_arrive(bar_a_full(bars, ab));
 					}
 				}
-				project_and_quantize(w, s_par, bars, ring, (uint32_t)g * kRingLoadsPerPair + kEnc128BackUnits, bufP, bufQ, scratch + kScrBest,
-				                     reinterpret_cast<int*>(scratch + kScrBi), t256, false, leaf, leaf < n_leaves, indices, tap_stage, tap_out);
-			}
-		} else {
-			// ---------- epilogue warps ----------
-			Epi e;
-			e.quad = quad;
-			e.chalf = chalf;
-			e.lane = lane;
-			e.row = row;
-			e.leaf_slot = leaf_slot;
-			e.wil = (row >> 5) & 1;
-			e.pos = pos;
-			e.w = pos & 3;
-			e.bars = bars;
-			e.tmem_lane = tmem + ((uint32_t)(quad * 32) << 16);
-			float* exch = scratch + kScrExch;
-			float* s_part = scratch + kScrPart;
-			float* s_scale = scratch + kScrScale;
-			float* s_hid = scratch + kScrHid;
-			const int tl = chalf * 64 + pos;  // thread index among the leaf's 128 epilogue threads
-			auto signal_input_ready = [&]() {
-				__syncwarp();
-				if (lane == 0) mbar_arrive(bar_in_ready(bars));
-			};
-
-#pragma unroll 1
-			for (int64_t g = 0; g < my_groups; ++g) {
-				const int64_t leaf = (blockIdx.x + g * gridDim.x) * 2 + leaf_slot;
-				const bool leaf_ok = leaf < n_leaves;
-				const bool prof = tap_stage == 100 && threadIdx.x == 0 && blockIdx.x == 0 && g == 1;  // phase timestamps (tools/check_vec3_encode.py)
-				const long long prof_t0 = prof ? clock64() : 0;
-				int prof_n = 16;
-				auto stamp = [&]() {
-					if (prof) tap_out[prof_n++] = (float)(clock64() - prof_t0);
-				};
+			} else {
 				float* xg = y + (leaf_ok ? leaf : 0) * 8192;  // the residual stream x, [128 ch][64 pos] fp32, updated in place
 
 				float v[32];
@@ -589,11 +583,12 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 						if (tap_stage == 2 && leaf_ok) tap_out[leaf * 8192 + (c0 + j) * 64 + pos] = xv;
 					}
 				}
-				stamp();
-				project_and_quantize(w, s_par, bars, ring, (uint32_t)g * kRingLoadsPerPair + kEnc128BackUnits, bufP, bufQ, scratch + kScrBest,
-				                     reinterpret_cast<int*>(scratch + kScrBi), t256, threadIdx.x == 0, leaf, leaf_ok, indices, tap_stage, tap_out);
-				stamp();
 			}
+			// every worker warp, one call site: proj + distances + argmin
+			stamp();
+			project_and_quantize(w, s_par, bars, ring, (uint32_t)g * kRingLoadsPerPair + kEnc128BackUnits, bufP, bufQ, scratch + kScrBest,
+			                     reinterpret_cast<int*>(scratch + kScrBi), t256, threadIdx.x == 0, leaf, leaf_ok, indices, tap_stage, tap_out);
+			stamp();
 		}
 	}
 
