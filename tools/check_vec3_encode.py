@@ -67,6 +67,17 @@ def main():
         mm = a != gg["indices"]
         print("%s: tc vs golden %d / %d differ (worst margin %.3e), fp32 vs golden %d, tc vs fp32 %d" % (
             name, mm.sum(), a.size, gg["margins"][mm].max() if mm.any() else 0.0, (b != gg["indices"]).sum(), (a != b).sum()))
+    # census on mixed data: the tensor-core encoder against the fp32 kernel, oracle margins where they differ
+    y = np.concatenate([synth.smoke_leaves(4096, seed=41, channels=3), synth.noise_leaves(1024, seed=42, channels=3),
+                        synth.smoke_leaves(3072, seed=43, channels=3, sparse=True)])
+    a, b = encode_dev(tc, y), encode_dev(f32, y)
+    bad = np.argwhere((a != b).reshape(len(y), -1).any(axis=1)).ravel()
+    line = "census: %d of %d latents differ (tc vs fp32) in %d leaves" % (int((a != b).sum()), a.size, len(bad))
+    if len(bad):
+        io, mo = o.encode(y[bad], with_margins=True)
+        line += "; vs oracle: tc %d, fp32 %d; worst oracle margin at a tc mismatch %.3e" % (
+            int((a[bad] != io).sum()), int((b[bad] != io).sum()), float(mo[a[bad] != io].max()) if (a[bad] != io).any() else 0.0)
+    print(line)
     for nn in (1, 2, 3, 297, 1023):
         assert np.array_equal(encode_dev(tc, x[:nn]), encode_dev(tc, x)[:nn]), nn
     print("ragged counts agree")

@@ -555,8 +555,8 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 				{
 					const int unit = tl >> 2, part = tl & 3;
 					float s = 0.f;
-#pragma unroll 8
-					for (int i = 0; i < 32; ++i) {
+#pragma unroll
+					for (int i = 0; i < 32; ++i) {  // fully unrolled: the 32 loads are in flight together
 						const int c = i * 4 + part;
 						s = fmaf(__ldg(w.fc0 + unit * 128 + c), (s_part[c] + s_part[128 + c]) * (1.f / 64.f), s);
 					}
@@ -567,7 +567,7 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 				leaf_bar(e);
 				{
 					float s = 0.f;
-#pragma unroll 8
+#pragma unroll
 					for (int j = 0; j < 32; ++j) s = fmaf(__ldg(w.fc2 + tl * 32 + j), s_hid[j], s);
 					s_scale[tl] = sigmoid_f(s);
 				}

@@ -10,8 +10,9 @@
 //     through TMEM (TS-mode MMA), copied by 8 stager warps;
 //   * a 64 -> 64 conv is 4 tiles x 9 (kd, kh) steps with the kw taps along N (N = 192), recombined when the
 //     accumulators are read; the stride-2 conv is one tile (64 output positions, rows 64..127 idle) x 27 taps, N = 128,
-//     its hi.hi products alternating between two accumulators (the tensor core truncates its fp32 accumulator after
-//     every MMA: shorter chains, smaller bias);
+//     its hi.hi products alternating between two accumulators and drained after 14 of the 27 taps (the tensor core
+//     truncates its fp32 accumulator after every MMA: four chains of <= 7 taps keep that bias at the level of the
+//     other layers);
 //   * GroupNorm needs the whole leaf: conv outputs and the residual stream go through a per-CTA fp32 scratch in global
 //     memory (L2-resident, every element private to one thread between barriers) and are normalised / split into the
 //     planes once all four tiles are done.
@@ -34,7 +35,8 @@ constexpr int kStages = 3;
 constexpr uint32_t kSlotBytes = kEnc128UnitBytes;    // ring slot: one 24 KB conv unit or one 16 KB down unit
 constexpr uint32_t kDownUnitBytes = 16384;           // [128 n][64 k] fp16
 constexpr int kConvSteps = 9, kTiles = 4, kDownSteps = 27;
-constexpr int kPassesPerLeaf = 2 * kTiles + 1;       // accumulator hand-overs per leaf
+constexpr int kDownSplit = 14;                       // down1's taps are accumulated in two halves (0..13, 14..26), drained separately
+constexpr int kPassesPerLeaf = 2 * kTiles + 2;       // accumulator hand-overs per leaf
 constexpr int kUnitsPerLeaf = 2 * kTiles * kConvSteps * 2 + kDownSteps * 2;  // 198 ring loads per leaf
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColHH = 0, kColMix = 192;        // 64 -> 64 convs: N = 192
@@ -176,8 +178,8 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 		for (int64_t g = 0; g < my_leaves; ++g) {
 #pragma unroll 1
 			for (int p = 0; p < kPassesPerLeaf; ++p, ++pass) {
-				const bool down = p == kPassesPerLeaf - 1;
-				const int steps = down ? kDownSteps : kConvSteps;
+				const bool down = p >= 2 * kTiles;
+				const int steps = !down ? kConvSteps : p == 2 * kTiles ? kDownSplit : kDownSteps - kDownSplit;
 				const uint32_t idesc = down ? kIdescDown : kIdescConv;
 				mbar_wait(bar_d_empty(bars), (pass & 1u) ^ 1u);
 				tc_fence_after();
@@ -549,29 +551,35 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 				signal_input_ready();  // layer 2: down1's input
 				stamp();
 
-				// ---- down1: rows 0..63 are the 4^3 output positions; this thread: output channels 64 chalf .. + 63 ----
-				mbar_wait(bar_d_full(bars), passes & 1u);
-				tc_fence_after();
-				if (row < 64) {
+				// ---- down1: rows 0..63 are the 4^3 output positions; this thread: output channels 64 chalf .. + 63.  The taps
+				//      arrive as two separately drained halves (four accumulation chains of <= 7 taps in all) ----
+#pragma unroll 1
+				for (int half = 0; half < 2; ++half) {
+					mbar_wait(bar_d_full(bars), passes & 1u);
+					tc_fence_after();
+					if (row < 64) {
 #pragma unroll
-					for (int part = 0; part < 4; ++part) {
-						float h0[16], h1[16], m[16];
-						const uint32_t col = tmem_lane + chalf * 64 + part * 16;
-						tmem_ld16_nowait(col + kColDownHH, h0);
-						tmem_ld16_nowait(col + kColDownHH + 128, h1);
-						tmem_ld16_nowait(col + kColDownMix, m);
-						tmem_wait_ld();
+						for (int part = 0; part < 4; ++part) {
+							float h0[16], h1[16], m[16];
+							const uint32_t col = tmem_lane + chalf * 64 + part * 16;
+							tmem_ld16_nowait(col + kColDownHH, h0);
+							tmem_ld16_nowait(col + kColDownHH + 128, h1);
+							tmem_ld16_nowait(col + kColDownMix, m);
+							tmem_wait_ld();
 #pragma unroll
-						for (int j = 0; j < 16; ++j) {
-							const int c = chalf * 64 + part * 16 + j;
-							y[leaf * 8192 + c * 64 + row] = fmaf(m[j], kLoInv, h0[j] + h1[j]) + s_par[par128f::down_b + c];
+							for (int j = 0; j < 16; ++j) {
+								const int c = chalf * 64 + part * 16 + j;
+								float* dst = y + leaf * 8192 + c * 64 + row;
+								const float part_sum = fmaf(m[j], kLoInv, h0[j] + h1[j]);
+								*dst = half == 0 ? part_sum : (*dst + part_sum) + s_par[par128f::down_b + c];  // thread-private element
+							}
 						}
 					}
+					tc_fence_before();
+					__syncwarp();
+					if (lane == 0) mbar_arrive(bar_d_empty(bars));
+					++passes;
 				}
-				tc_fence_before();
-				__syncwarp();
-				if (lane == 0) mbar_arrive(bar_d_empty(bars));
-				++passes;
 				stamp();
 			}
 		}
