@@ -49,10 +49,16 @@ BYTES_DECODE = 64 + 2048
 # is tied to the git blob hash of the kernel source it was captured from: a changed kernel reports traffic = null
 # ("stale") instead of a number that no longer describes it.
 NCU_DRAM = {
-    "encode": {"bytes_per_leaf": (122.270464e6 + 8.901888e6) / 59200, "source": "profiles/r2_encode_tc_ncu_summary.txt",
-               "file": "vqvdb_b200/csrc/encode_tc.cu", "blob": "6b9b558831a5f8f2c05ce28b0dd7e031a2afd782"},
+    "encode": {"bytes_per_leaf": (122.019840e6 + 7.470336e6) / 59200, "source": "profiles/r2_encode_tc_ncu_summary.txt",
+               "file": "vqvdb_b200/csrc/encode_tc.cu", "blob": "b230dfd4377bf9ec4235ba2a5f2f867484911adc"},
     "decode": {"bytes_per_leaf": (5.091584e6 + 64.778240e6) / 59200, "source": "profiles/r2_decode_tc_ncu_summary.txt",
                "file": "vqvdb_b200/csrc/decode_tc.cu", "blob": "e8c2e6e6f19bd3bd43957df758d9210aa8b7e51c"},
+    # vec3 encoder = two kernels per batch (front: 28.2 MB read + 316.5 MB written, back: 190.5 + 94.1, per 4 144 leaves —
+    # the 32 KB-per-leaf hand-over array and the front kernel's per-CTA scratch are what reaches DRAM)
+    "encode_vec3": {"bytes_per_leaf": (28.231936e6 + 316.458496e6 + 190.531584e6 + 94.121984e6) / 4144,
+                    "source": "profiles/r2_encode_tc128_front_ncu_summary.txt + profiles/r2_encode_tc128_back_ncu_summary.txt",
+                    "file": ["vqvdb_b200/csrc/encode_tc128_front.cu", "vqvdb_b200/csrc/encode_tc128.cu"],
+                    "blob": ["09b50b35ab8a22f4121a6fbe3082bca6a842ae84", "560dc78e72e6a3cb2cb50d9a22a17fea630f2662"]},
 }
 
 
@@ -64,9 +70,12 @@ def git_blob_hash(path: str) -> str:
 def ncu_traffic(kernel: str, leaves: int):
     """(bytes per launch, source) from the committed capture, or (None, why) when it does not describe this build."""
     e = NCU_DRAM[kernel]
+    files = e["file"] if isinstance(e["file"], list) else [e["file"]]
+    blobs = e["blob"] if isinstance(e["blob"], list) else [e["blob"]]
     try:
-        if git_blob_hash(e["file"]) != e["blob"]:
-            return None, "stale: %s changed since %s was captured" % (e["file"], e["source"])
+        for f, b in zip(files, blobs):
+            if git_blob_hash(f) != b:
+                return None, "stale: %s changed since %s was captured" % (f, e["source"])
     except OSError:
         return None, "kernel source not found"
     return e["bytes_per_leaf"] * leaves, e["source"]
@@ -655,8 +664,8 @@ def main():
         enc_tc_macs = (2 * 64 * 64 * 27 * 512 + 64 * 128 * 27 * 64 + 4 * 128 * 128 * 27 * 64) if vec3 else (13197824 - 221184 - 262144 + 524288)
         enc_issued_tf = (3 * enc_tc_macs * 2 if enc_tc else flop_enc) * L / (enc_ms / 1e3) / 1e12
         traffic, traffic_source = (None, "no capture for this path")
-        if (dom == "encode" and enc_tc and not vec3) or (dom == "decode" and codec.decode_path == "bf16_tcgen05_n192_fold"):
-            traffic, traffic_source = ncu_traffic(dom, L)
+        if (dom == "encode" and enc_tc) or (dom == "decode" and codec.decode_path == "bf16_tcgen05_n192_fold"):
+            traffic, traffic_source = ncu_traffic("encode_vec3" if vec3 else dom, L)
         enc_name = ("encode_tc128_front_kernel + encode_tc128_back_kernel" if vec3 else "encode_tc_kernel") if enc_tc else ("generic_encode_kernel" if vec3 else "encode_fp32_kernel")
         dec_name = ("decode_tc128_kernel" if vec3 else "decode_tc_kernel") if dec_tc else ("generic_decode_kernel" if vec3 else "decode_fp32_kernel")
         kernels = {

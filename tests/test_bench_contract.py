@@ -66,9 +66,12 @@ def test_ncu_traffic_is_tied_to_the_kernel_source():
     # roofline.traffic comes from a committed ncu capture and must not outlive the kernel it was taken from
     import bench
     for k, e in bench.NCU_DRAM.items():
-        assert os.path.exists(os.path.join(REPO, e["source"])) and len(e["blob"]) == 40
+        files = e["file"] if isinstance(e["file"], list) else [e["file"]]      # a path made of two kernels lists both sources
+        blobs = e["blob"] if isinstance(e["blob"], list) else [e["blob"]]
+        assert all(os.path.exists(os.path.join(REPO, src)) for src in e["source"].split(" + "))
+        assert len(files) == len(blobs) and all(len(b) == 40 for b in blobs)
         traffic, why = bench.ncu_traffic(k, 1000)
-        if bench.git_blob_hash(e["file"]) == e["blob"]:
+        if all(bench.git_blob_hash(f) == b for f, b in zip(files, blobs)):
             assert traffic == e["bytes_per_leaf"] * 1000 and why == e["source"]
         else:
             assert traffic is None and why.startswith("stale")
