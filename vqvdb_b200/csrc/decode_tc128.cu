@@ -23,11 +23,23 @@
 
 #include "decode_tc128.cuh"
 #include "leaf_ops.cuh"
-#include "ptx_utils.cuh"
+#include "tc128_ops.cuh"
 
 namespace vqvdb {
 
 namespace {
+
+using tc128::column_sums;
+using tc128::elect_one;
+using tc128::lds128;
+using tc128::make_desc_sw128;
+using tc128::named_bar_sync;
+using tc128::tc_commit;
+using tc128::tc_fence_after;
+using tc128::tc_fence_before;
+using tc128::tmem_ld16_nowait;
+using tc128::tmem_st16;
+using tc128::tmem_wait_ld;
 
 constexpr int kEpiWarps = 8, kStageWarps = 8;
 constexpr int kIssuerWarp = kEpiWarps + kStageWarps, kProducerWarp = kIssuerWarp + 1;
@@ -70,58 +82,11 @@ __device__ __forceinline__ uint32_t bar_d_full(uint32_t bars, uint32_t b) { retu
 __device__ __forceinline__ uint32_t bar_d_empty(uint32_t bars, uint32_t b) { return bars + (2 * kStages + 6 + b) * 8; }
 __device__ __forceinline__ uint32_t bar_in_ready(uint32_t bars) { return bars + (2 * kStages + 8) * 8; }
 
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 // D[tmem_d] (+)= A[tmem_a] (128 x 16 bf16, TMEM) * B[desc] (192 x 16 bf16, shared)^T
 __device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
-	asm volatile(
-	    "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-	    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
-	    "r"(tmem_a), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
-	    : "memory");
+	tc128::tc_mma_ts(tmem_d, tmem_a, bdesc, kIdesc, accumulate);
 }
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-	// K-major SWIZZLE_128B: 128-byte rows, 8-row groups 1024 B apart
-	return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-	       ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-	asm volatile(
-	    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-	    "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-	    "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-	    : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
-	uint32_t o[16];
-	asm volatile(
-	    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-	    : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]), "=r"(o[9]),
-	      "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15])
-	    : "r"(taddr));
-#pragma unroll
-	for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(o[j]);
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ bool elect_one() {
-	uint32_t pred;
-	asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
-	return pred != 0;
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-	asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-	uint4 v;
-	asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-	return v;
-}
-__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-	asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) { tc128::sts128(a, make_uint4(x, y, z, w)); }
 
 // Physical byte offset, inside a [64 pos][128 ch] bf16 buffer, of the 16-byte chunk holding channels 8*c16 .. 8*c16+7 of row pos.
 __device__ __forceinline__ uint32_t chunk_off(int pos, int c16) {
@@ -218,21 +183,6 @@ __device__ __forceinline__ void load_row32(uint32_t buf, int pos, int c16_0, flo
 		f = unpack_bf16(raw.z); x[8 * q + 4] = f.x; x[8 * q + 5] = f.y;
 		f = unpack_bf16(raw.w); x[8 * q + 6] = f.x; x[8 * q + 7] = f.y;
 	}
-}
-
-// Transposing butterfly: afterwards v[0] of lane L = sum over the warp's 32 lanes of the original v[L].  Destroys v.
-__device__ __forceinline__ float column_sums(float (&v)[32], int lane) {
-#pragma unroll
-	for (int step = 16; step >= 1; step >>= 1) {
-		const bool upper = (lane & step) != 0;
-#pragma unroll
-		for (int i = 0; i < step; ++i) {
-			const float send = upper ? v[i] : v[i + step];
-			const float keep = upper ? v[i + step] : v[i];
-			v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
-		}
-	}
-	return v[0];
 }
 
 __global__ void __launch_bounds__(kThreads, 1)

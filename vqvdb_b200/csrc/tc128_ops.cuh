@@ -1,6 +1,6 @@
-// Device helpers shared by the vec3 encoder kernels (encode_tc128.cu, encode_tc128_front.cu): tcgen05 / TMEM wrappers for
-// TS-mode MMAs (A operand in tensor memory, B through a SWIZZLE_128B shared-memory descriptor), fp16 hi/lo splitting,
-// the swizzled channels-last activation layout.
+// Device helpers shared by the vec3 model's tensor-core kernels (decode_tc128.cu, encode_tc128.cu, encode_tc128_front.cu):
+// tcgen05 / TMEM wrappers for TS-mode MMAs (A operand in tensor memory, B through a SWIZZLE_128B shared-memory
+// descriptor), fp16 hi/lo splitting, small shared-memory accessors.
 #pragma once
 
 #include <cuda_fp16.h>
