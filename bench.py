@@ -489,7 +489,7 @@ def main():
     parity = None
     if rank == 0 and args.parity_sample > 0:
         try:
-            parity = parity_block(codec, x, idx, L, sp, args.parity_sample if not vec3 else min(args.parity_sample, 256), CH)
+            parity = parity_block(codec, x, idx, L, sp, args.parity_sample if not vec3 else min(args.parity_sample, 1024), CH)
         except Exception as e:  # noqa: BLE001
             parity = {"unavailable": str(e)[:300]}
     barrier()
