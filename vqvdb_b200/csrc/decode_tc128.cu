@@ -52,6 +52,11 @@ constexpr int kLayers = kDec128ConvLayers + 1;           // 5 convs + the folded
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kDCols = 192;                         // accumulator b: columns [b*192, b*192 + 192)
 constexpr uint32_t kColA = 2 * kDCols;                   // A buffers: columns 384 + buf*32
+#ifndef VQVDB_DEC128_A_BUFS
+#define VQVDB_DEC128_A_BUFS 2  // 4 fit TMEM and were measured: 3.07 M vs 3.06 M leaves/s — the stager -> issuer hand-over is not the limiter
+#endif
+constexpr uint32_t kABufs = VQVDB_DEC128_A_BUFS;         // staged-A units in flight (the hand-over latency stager -> issuer hides behind them)
+static_assert((kABufs & (kABufs - 1)) == 0 && kColA + kABufs * 32 <= kTmemCols, "A buffers: a power of two that fits TMEM");
 
 // instruction descriptor: D = f32, A = B = bf16, both K-major, N = 192, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((192u >> 3) << 17) | ((128u >> 4) << 24);
@@ -64,7 +69,7 @@ constexpr uint32_t kLeafBytes = 2 * kBufBytes + kXBytes;
 constexpr uint32_t kOffLeaf = kOffRing + kStages * kUnitBytes;
 constexpr uint32_t kOffZero = kOffLeaf + 2 * kLeafBytes; // 256 zero bytes: the source row of out-of-leaf taps
 constexpr uint32_t kOffBar = kOffZero + 256;
-constexpr uint32_t kNumBars = 2 * kStages + 2 + 2 + 2 + 2 + 1;  // w_full, w_empty, a_full[2], a_empty[2], d_full[2], d_empty[2], in_ready
+constexpr uint32_t kNumBars = 2 * kStages + 2 * kABufs + 2 + 2 + 1;  // w_full, w_empty, a_full[], a_empty[], d_full[2], d_empty[2], in_ready
 constexpr uint32_t kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr uint32_t kOffPar = (kOffTmemSlot + 16 + 15) & ~15u;
 constexpr uint32_t kOffScratch = kOffPar + par128::total * 4;
@@ -77,10 +82,10 @@ static_assert(kOffBar % 8 == 0 && kOffPar % 16 == 0 && kOffScratch % 16 == 0 && 
 __device__ __forceinline__ uint32_t bar_w_full(uint32_t bars, uint32_t s) { return bars + s * 8; }
 __device__ __forceinline__ uint32_t bar_w_empty(uint32_t bars, uint32_t s) { return bars + (kStages + s) * 8; }
 __device__ __forceinline__ uint32_t bar_a_full(uint32_t bars, uint32_t b) { return bars + (2 * kStages + b) * 8; }
-__device__ __forceinline__ uint32_t bar_a_empty(uint32_t bars, uint32_t b) { return bars + (2 * kStages + 2 + b) * 8; }
-__device__ __forceinline__ uint32_t bar_d_full(uint32_t bars, uint32_t b) { return bars + (2 * kStages + 4 + b) * 8; }
-__device__ __forceinline__ uint32_t bar_d_empty(uint32_t bars, uint32_t b) { return bars + (2 * kStages + 6 + b) * 8; }
-__device__ __forceinline__ uint32_t bar_in_ready(uint32_t bars) { return bars + (2 * kStages + 8) * 8; }
+__device__ __forceinline__ uint32_t bar_a_empty(uint32_t bars, uint32_t b) { return bars + (2 * kStages + kABufs + b) * 8; }
+__device__ __forceinline__ uint32_t bar_d_full(uint32_t bars, uint32_t b) { return bars + (2 * kStages + 2 * kABufs + b) * 8; }
+__device__ __forceinline__ uint32_t bar_d_empty(uint32_t bars, uint32_t b) { return bars + (2 * kStages + 2 * kABufs + 2 + b) * 8; }
+__device__ __forceinline__ uint32_t bar_in_ready(uint32_t bars) { return bars + (2 * kStages + 2 * kABufs + 4) * 8; }
 
 // D[tmem_d] (+)= A[tmem_a] (128 x 16 bf16, TMEM) * B[desc] (192 x 16 bf16, shared)^T
 __device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
@@ -204,9 +209,11 @@ decode_tc128_kernel(const Decoder128Weights w, const uint8_t* __restrict__ indic
 			mbar_init(bar_w_full(bars, s), 1);
 			mbar_init(bar_w_empty(bars, s), 1);
 		}
-		for (uint32_t b = 0; b < 2; ++b) {
+		for (uint32_t b = 0; b < kABufs; ++b) {
 			mbar_init(bar_a_full(bars, b), kStageWarps);
 			mbar_init(bar_a_empty(bars, b), 1);
+		}
+		for (uint32_t b = 0; b < 2; ++b) {
 			mbar_init(bar_d_full(bars, b), 1);
 			mbar_init(bar_d_empty(bars, b), kEpiWarps);
 		}
@@ -250,9 +257,9 @@ decode_tc128_kernel(const Decoder128Weights w, const uint8_t* __restrict__ indic
 				tc_fence_after();
 #pragma unroll 1
 				for (int u = 0; u < kUnitsPerPass; ++u, ++unit) {
-					const uint32_t s = unit % kStages, ab = unit & 1u;
+					const uint32_t s = unit % kStages, ab = unit % kABufs;
 					mbar_wait(bar_w_full(bars, s), (unit / kStages) & 1u);
-					mbar_wait(bar_a_full(bars, ab), (unit >> 1) & 1u);
+					mbar_wait(bar_a_full(bars, ab), (unit / kABufs) & 1u);
 					tc_fence_after();
 					const uint64_t bdesc = make_desc_sw128(ring + s * kUnitBytes);
 #pragma unroll
@@ -295,8 +302,8 @@ decode_tc128_kernel(const Decoder128Weights w, const uint8_t* __restrict__ indic
 						const uint4 v = lds128(ok ? in_buf + chunk_off(p2, khalf * 8 + chalf * 4 + q) : zero_row + q * 16);
 						r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
 					}
-					const uint32_t ab = unit & 1u;
-					if (lane == 0) mbar_wait(bar_a_empty(bars, ab), ((unit >> 1) & 1u) ^ 1u);
+					const uint32_t ab = unit % kABufs;
+					if (lane == 0) mbar_wait(bar_a_empty(bars, ab), ((unit / kABufs) & 1u) ^ 1u);
 					__syncwarp();
 					tc_fence_after();
 					tmem_st16(tmem_lane + kColA + ab * 32 + chalf * 16, r);
