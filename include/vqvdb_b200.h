@@ -64,7 +64,8 @@ typedef enum vqvdb_b200_decode_precision {
 
 /* Encoder arithmetic.  Both paths are fp32-faithful (index parity with the reference is a bit-exactness requirement):
  * the tensor-core path splits every operand into two fp16 planes (22 significant bits, three products, fp32
- * accumulation) and re-scores the codebook shortlist in exact fp32. */
+ * accumulation); the float model re-scores the codebook shortlist in exact fp32, the vec3 model (two kernels,
+ * csrc/encode_tc128_front.cu + csrc/encode_tc128.cu) computes proj and all distances as exact fp32 FMA chains. */
 typedef enum vqvdb_b200_encode_precision {
 	VQVDB_B200_ENCODE_DEFAULT = 0,
 	VQVDB_B200_ENCODE_FP32 = 1,      /* CUDA-core fp32 FFMA path */
@@ -161,12 +162,16 @@ VQVDB_B200_API int vqvdb_b200_debug_fold_decoder_tail(const char* weights_path, 
  * |W x + b - e_k|^2 - |W x + b|^2 == esq_k - 2 x.M_k against python/save_for_inference.py:55-61 evaluated directly). */
 VQVDB_B200_API int vqvdb_b200_debug_fold_encoder_vq(const char* weights_path, float* m_out, float* esq_out, float* norm_out);
 
-/* Name of the encode path in use: "fp32" or "fp16x2_tcgen05". */
+/* Name of the encode path in use: "fp16x2_tcgen05" or "fp32" (float model); "fp16x2_tcgen05_c128" or "fp32_generic"
+ * (vec3 model). */
 VQVDB_B200_API const char* vqvdb_b200_encode_path(const vqvdb_b200_codec* codec);
 /* Bring-up aid for the tensor-core encoder: runs it and also writes an fp32 activation to dev_tap — stage 0: pre
  * (GroupNorm+ReLU) [n][16][512], 6: first residual block's conv1 [n][16][512], 1: first residual block [n][16][512],
  * 2: down [n][32][64], 7: res_stack.0 conv1 [n][32][64], 3: residual stack [n][32][64], 4: channel attention
- * [n][32][64], 5: z [n][128][64]. */
+ * [n][32][64], 5: z [n][128][64].
+ * vec3 model (at most one batch = SM count x 28 leaves): stage 4: pre (GroupNorm+ReLU) [n][64][512], 5: the 8^3 residual
+ * block [n][64][512], 6: down1 [n][128][64], 0: res_stack.0 [n][128][64], 1: res_stack.1, 2: channel attention, 3: z;
+ * 100: phase timestamps of both kernels (tools/check_vec3_encode.py). */
 VQVDB_B200_API int vqvdb_b200_debug_encode_tap(vqvdb_b200_codec* codec, const float* dev_leaves, int64_t n_leaves, int stage,
                                                float* dev_tap, uint8_t* dev_indices, void* cuda_stream);
 
