@@ -727,3 +727,20 @@ def test_vec3_full_size_roundtrip_properties(codec_vec3_tc, codec_vec3):
     codec_vec3_tc.decode_device(idx[33_333:m], m - 33_333, rec2[33_333:], sp)
     torch.cuda.synchronize()
     assert torch.equal(rec, rec2)
+
+
+@pytest.mark.parametrize("scale", [1e-4, 1.0e3])
+def test_vec3_tc_encoder_on_scaled_fields(codec_vec3_tc, codec_vec3, scale):
+    """Velocity fields far from unit scale: pre.0 runs in fp32 and GroupNorm follows it, so nothing that reaches the fp16
+    operand planes depends on the input's magnitude."""
+    import os
+    from conftest import REPO
+    from oracle.pyoracle import COracle
+    x = (synth.smoke_leaves(768, seed=51, channels=3) * scale).astype(np.float32)
+    a, b = _encode(codec_vec3_tc, x), _encode(codec_vec3, x)
+    diff = np.argwhere((a != b).reshape(len(x), -1).any(axis=1)).ravel()
+    assert len(diff) <= 4, "%d of %d leaves differ between the tensor-core and the fp32 encoder at scale %g" % (len(diff), len(x), scale)
+    o = COracle(os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw"))
+    pick = np.unique(np.concatenate([np.arange(0, len(x), 16), diff]))
+    idx_o, margins = o.encode(x[pick], with_margins=True)
+    assert_indices_match(a[pick], idx_o, margins, max_frac=1.0)
