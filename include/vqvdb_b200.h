@@ -159,7 +159,9 @@ VQVDB_B200_API int vqvdb_b200_debug_fold_decoder_tail(const char* weights_path, 
 /* Host-only checker hook (no device needed): the tensor-core encoder's `proj x codebook` fold of the weight pack at
  * `weights_path` (NULL or "" = the embedded pack) — m_out [256][32] = E . proj.weight, esq_out [256] = |e_k|^2 - 2 proj.bias.e_k,
  * norm_out [257] = |M_k| rounded up and their maximum (csrc/encode_tc_stream.hpp; tests/test_encoder_fold.py checks
- * |W x + b - e_k|^2 - |W x + b|^2 == esq_k - 2 x.M_k against python/save_for_inference.py:55-61 evaluated directly). */
+ * |W x + b - e_k|^2 - |W x + b|^2 == esq_k - 2 x.M_k against python/save_for_inference.py:55-61 evaluated directly).
+ * For a vec3 pack (csrc/encode_tc128_stream.hpp): m_out [256][128], esq_out [256], norm_out [257] with [0] = max_k |M_k|,
+ * [1] = an upper bound of |proj.weight|_2, [2] = |proj.bias| + max_k |e_k|, the rest 0. */
 VQVDB_B200_API int vqvdb_b200_debug_fold_encoder_vq(const char* weights_path, float* m_out, float* esq_out, float* norm_out);
 
 /* Name of the encode path in use: "fp16x2_tcgen05" or "fp32" (float model); "fp16x2_tcgen05_c128" or "fp32_generic"

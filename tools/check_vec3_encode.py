@@ -58,7 +58,8 @@ def main():
     torch.cuda.synchronize()
     t = tap.cpu().numpy()
     print("front stamps [pre conv | pre end | conv1 tiles | gn2 sweeps | conv2 tiles | split sweep | down]:", [int(v) for v in t[:8]])
-    print("back stamps [prep | r0c1 | r0c2 | r1c1 | r1c2 | attention | proj+vq]:", [int(v) for v in t[16:24]])
+    print("back stamps [prep | r0c1 | r0c2 | r1c1 | r1c2 | fc0 | fc2 | scale + split | score GEMM | scores read, decided | (near-tie rows: z | re-scored) | done]:",
+          [int(v) for v in t[16:30]])
 
     for name, xs in (("sparse1024", x), ("smoke256", synth.smoke_leaves(256, seed=5, channels=3)), ("noise64", synth.noise_leaves(64, seed=6, channels=3))):
         gg = np.load(os.path.join(REPO, "tests", "golden", "vec3_%s_seed%d.npz" % (name, {"sparse1024": 7, "smoke256": 5, "noise64": 6}[name])))
@@ -78,6 +79,16 @@ def main():
         line += "; vs oracle: tc %d, fp32 %d; worst oracle margin at a tc mismatch %.3e" % (
             int((a[bad] != io).sum()), int((b[bad] != io).sum()), float(mo[a[bad] != io].max()) if (a[bad] != io).any() else 0.0)
     print(line)
+    # the codebook search's two paths: stage 3 sends EVERY row through the exact fp32 re-scoring (and taps z); the default
+    # decides ~99.9 % of the rows from the tensor-core scores alone.  Same indices, or the shortlist bound is wrong.
+    nf = 4096
+    yd = torch.from_numpy(y[:nf]).cuda()
+    forced = torch.empty((nf, 64), dtype=torch.uint8, device="cuda")
+    ztap = torch.zeros((nf, 128 * 64), dtype=torch.float32, device="cuda")
+    tc.debug_encode_tap(yd, nf, 3, ztap, forced, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    print("exact path forced on every row vs shortlist: %d of %d latents differ" % (
+        int((forced.cpu().numpy().reshape(-1, 4, 4, 4) != a[:nf]).sum()), nf * 64))
     for nn in (1, 2, 3, 297, 1023):
         assert np.array_equal(encode_dev(tc, x[:nn]), encode_dev(tc, x)[:nn]), nn
     print("ragged counts agree")

@@ -137,11 +137,12 @@ def fold_decoder_tail(weights_path: str = ""):
     return w, b
 
 
-def fold_encoder_vq(weights_path: str = ""):
-    """The tensor-core encoder's `proj x codebook` fold: (M [256][32], esq [256], norm [257]) as fp32 numpy arrays.  Host-only."""
+def fold_encoder_vq(weights_path: str = "", channels: int = 32):
+    """The tensor-core encoders' `proj x codebook` fold: (M [256][channels], esq [256], norm [257]) as fp32 numpy arrays;
+    channels = 32 for the float model, 128 for the vec3 model (norm[:3] = the bound's constants there).  Host-only."""
     import numpy as np
     L = load_library()
-    m = np.empty((256, 32), dtype=np.float32)
+    m = np.empty((256, channels), dtype=np.float32)
     esq = np.empty((256,), dtype=np.float32)
     norm = np.empty((257,), dtype=np.float32)
     rc = L.vqvdb_b200_debug_fold_encoder_vq(os.fspath(weights_path).encode(), m.ctypes.data, esq.ctypes.data, norm.ctypes.data)

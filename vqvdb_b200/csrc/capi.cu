@@ -531,15 +531,11 @@ void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
 	if (vqvdb::encoder128_supports(p)) {
 		const std::vector<uint8_t> back = vqvdb::build_encoder128_back_units(p);
 		const std::vector<float> back_par = vqvdb::build_encoder128_back_params(p);
-		std::vector<float> emb_t = vqvdb::build_proj_transposed(p);  // proj^T, then the codebook^T: one contiguous stream
-		{
-			const std::vector<float> et = vqvdb::build_embedding_transposed(p);
-			emb_t.insert(emb_t.end(), et.begin(), et.end());
-		}
+		const std::vector<uint8_t> vq_units = vqvdb::build_encoder128_vq_units(p);  // proj folded into the codebook, fp16 hi / lo
 		const std::vector<uint8_t> front = vqvdb::build_encoder128_front_units(p);
 		const std::vector<float> front_par = vqvdb::build_encoder128_front_params(p);
 		const size_t off_par = back.size(), off_emb = (off_par + back_par.size() * sizeof(float) + 255) & ~size_t(255);
-		const size_t off_front = (off_emb + emb_t.size() * sizeof(float) + 1023) & ~size_t(1023), off_fpar = off_front + front.size();
+		const size_t off_front = (off_emb + vq_units.size() + 1023) & ~size_t(1023), off_fpar = off_front + front.size();
 		CUDA_TRY(cudaMalloc(&c.enc128_arena, off_fpar + front_par.size() * sizeof(float)));
 		CUDA_TRY(cudaMemcpy(c.enc128_arena + off_front, front.data(), front.size(), cudaMemcpyHostToDevice));
 		CUDA_TRY(cudaMemcpy(c.enc128_arena + off_fpar, front_par.data(), front_par.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -549,14 +545,16 @@ void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
 		c.enc128_front.pre_wt = m.e_pre_w;
 		CUDA_TRY(cudaMemcpy(c.enc128_arena, back.data(), back.size(), cudaMemcpyHostToDevice));
 		CUDA_TRY(cudaMemcpy(c.enc128_arena + off_par, back_par.data(), back_par.size() * sizeof(float), cudaMemcpyHostToDevice));
-		CUDA_TRY(cudaMemcpy(c.enc128_arena + off_emb, emb_t.data(), emb_t.size() * sizeof(float), cudaMemcpyHostToDevice));
+		CUDA_TRY(cudaMemcpy(c.enc128_arena + off_emb, vq_units.data(), vq_units.size(), cudaMemcpyHostToDevice));
 		c.enc128_batch = (int64_t)c.num_sms * kEnc128LeavesPerCta;
 		CUDA_TRY(cudaMalloc(&c.enc128_y, (size_t)(kSlots + 1) * c.enc128_batch * 8192 * sizeof(float)));
 		c.enc128_back.units = c.enc128_arena;
 		c.enc128_back.par = reinterpret_cast<const float*>(c.enc128_arena + off_par);
 		c.enc128_back.fc0 = m.e_fc0;
 		c.enc128_back.fc2 = m.e_fc2;
-		c.enc128_back.vq_stream = reinterpret_cast<const float*>(c.enc128_arena + off_emb);
+		c.enc128_back.vq_units = c.enc128_arena + off_emb;
+		c.enc128_back.proj_t = m.e_proj_w;
+		c.enc128_back.emb = m.emb;
 		c.enc128_back.emb_sq = m.emb_sq;
 		c.enc128 = true;
 	}
@@ -1040,7 +1038,14 @@ int vqvdb_b200_debug_fold_encoder_vq(const char* weights_path, float* m_out, flo
 		if (weights_path && weights_path[0]) pack.load_file(weights_path);
 		else pack.parse(vqvdb::vqvdb_b200_embedded_pack, (size_t)(vqvdb::vqvdb_b200_embedded_pack_end - vqvdb::vqvdb_b200_embedded_pack));
 		std::vector<float> m, esq, mno;
-		vqvdb::build_encoder_vq_fold(pack, m, esq, mno);
+		if (vqvdb::encoder128_supports(pack)) {  // vec3 model: M [256][128]; esq and the bound's three constants from the parameter block
+			m = vqvdb::build_encoder128_vq_fold(pack);
+			const std::vector<float> par = vqvdb::build_encoder128_back_params(pack);
+			esq.assign(par.begin() + vqvdb::par128e::vq_esq2, par.begin() + vqvdb::par128e::vq_esq2 + 256);
+			mno.assign(257, 0.f);
+			for (int i = 0; i < 3; ++i) mno[i] = par[vqvdb::par128e::vq_const + i];
+		} else
+			vqvdb::build_encoder_vq_fold(pack, m, esq, mno);
 		std::memcpy(m_out, m.data(), m.size() * sizeof(float));
 		std::memcpy(esq_out, esq.data(), esq.size() * sizeof(float));
 		std::memcpy(norm_out, mno.data(), mno.size() * sizeof(float));

@@ -57,6 +57,12 @@ constexpr int kDownChains = 4;                    // independent accumulators of
 #define VQVDB_ENC_PRE0_SPLIT_AT 3   // measured: 0 (all under `down`) 6.422 M leaves/s, 1: 6.461 M, 2: 6.497 M, 3: 6.531 M
 #endif
 constexpr int kPre0Split = VQVDB_ENC_PRE0_SPLIT_AT;  // kd taps of the next leaf's pre.0 that run inside conv2's MMA wait
+// pre.0's FMAs as packed fp32 pairs (FFMA2: one instruction per two channels, each half an IEEE fma: bit-identical results)
+#ifndef VQVDB_ENC_PRE0_FFMA2
+#define VQVDB_ENC_PRE0_FFMA2 1
+#endif
+// (Registers: __launch_bounds__(576, 1) makes ptxas stop at 96 per thread with 88 bytes of spills; asking for 112 with
+// __maxnreg__ compiles to 52 bytes of spills but the launch fails — "too many resources requested" — on the B200.)
 // offsets (floats) of the per-channel parameter vectors staged in shared memory: a global (L2) load at the head of
 // every epilogue costs ~300 cycles of exposed latency, there being almost no L1 left beside 222 KB of shared memory
 namespace par {
@@ -748,6 +754,49 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 		};
 		// (b) pre.0: Conv3d(1,16,k3) on FFMA, channels 4g..4g+3, + bias
 		// kd taps [kd0, kd1) of the filter; the first part zeroes the accumulators, the last one adds the bias
+#if VQVDB_ENC_PRE0_FFMA2
+		// The accumulators are packed fp32 pairs (FFMA2, channel pairs 4g + {0,1}, 4g + {2,3}; each half an IEEE fma).
+		auto front_pre0_part = [&](float (&x)[5][4], int kd0, int kd1) {
+			uint64_t x2[5][2];
+#pragma unroll
+			for (int t = 0; t < 5; ++t) {
+				x2[t][0] = kd0 == 0 ? 0ull : pack_f32x2(x[t][0], x[t][1]);
+				x2[t][1] = kd0 == 0 ? 0ull : pack_f32x2(x[t][2], x[t][3]);
+			}
+#pragma unroll 1
+			for (int kd = kd0; kd < kd1; ++kd) {
+#pragma unroll
+				for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+					for (int kw = 0; kw < 3; ++kw) {
+						const int tap = (kd * 3 + kh) * 3 + kw;
+						const float4 f = *reinterpret_cast<const float4*>(s_prew + tap * 16 + g * 4);
+						const uint64_t w01 = pack_f32x2(f.x, f.y), w23 = pack_f32x2(f.z, f.w);
+#pragma unroll
+						for (int t = 0; t < 5; ++t) {
+							const float xv = in_halo[base8[t] + kd * 100 + kh * 10 + kw];
+							const uint64_t xx = pack_f32x2(xv, xv);
+							x2[t][0] = fma_f32x2(xx, w01, x2[t][0]);
+							x2[t][1] = fma_f32x2(xx, w23, x2[t][1]);
+						}
+					}
+				}
+			}
+#pragma unroll
+			for (int t = 0; t < 5; ++t) {
+				unpack_f32x2(x2[t][0], x[t][0], x[t][1]);
+				unpack_f32x2(x2[t][1], x[t][2], x[t][3]);
+			}
+			if (kd1 == 3) {
+#pragma unroll
+				for (int c = 0; c < 4; ++c) {
+					const float b = sp_c[par::pre_b + g * 4 + c];
+#pragma unroll
+					for (int t = 0; t < 5; ++t) x[t][c] += b;
+				}
+			}
+		};
+#else
 		auto front_pre0_part = [&](float (&x)[5][4], int kd0, int kd1) {
 			if (kd0 == 0) {
 #pragma unroll
@@ -782,6 +831,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				}
 			}
 		};
+#endif
 		auto front_pre0 = [&](float (&x)[5][4]) { front_pre0_part(x, 0, 3); };
 		// (c) pre.1: GroupNorm(4,16) + ReLU -> x (the residual, kept in registers)
 		auto front_gn_pre1 = [&](float (&x)[5][4]) {

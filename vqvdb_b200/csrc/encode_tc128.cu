@@ -14,9 +14,12 @@
 //     pair of leaves, L2-resident);
 //   * 8 epilogue warps own GroupNorm / residual / attention; the residual stream x stays in fp32 (global memory, the
 //     leaf's own 32 KB of the input array, thread-private elements).
-// proj and the distances are exact fp32 FMA chains in the oracle's order (oracle/vqvae_oracle.c conv3d / quantize),
-// computed by all 16 worker warps after the last convolution; with the same z they give the same index as the fp32
-// kernel (generic_model.cu) — a difference in z (summation order of the convolutions) can only move near-ties.
+// proj + codebook search: proj feeds nothing but the distances, so it is folded into the codebook on the host (M = E W,
+// encode_tc128_stream.hpp) and the scores of all 256 codes come from ONE more split-fp16 GEMM on the attention output
+// ([128 rows][128 c] x [128 c][256 k], SS mode: the A operand is written by the epilogue threads in the UMMA layout), with
+// an error bound; a row whose two best scores are further apart than twice that bound is decided.  The others (near-ties,
+// ~0.1 % of the rows) get z = W x + b and the distances of their shortlisted codes as exact fp32 FMA chains in the oracle's
+// order (oracle/vqvae_oracle.c conv3d / quantize: sequential sums, first minimum wins), the index the all-fp32 path gives.
 // Warp roles (576 threads): 0-7 epilogue (TMEM lane quadrant, channel half of the pass), 8-15 stagers (quadrant, channel
 // half of the step), 16 MMA issuer (whole warp, one elected lane), 17 TMA producer.
 #include "encode_tc128.cuh"
@@ -41,12 +44,16 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColHH = 0, kColMix = 192;        // accumulators
 constexpr uint32_t kColA = 384;                      // A buffers: hi at 384 + buf*64, lo at 384 + buf*64 + 32
 constexpr uint32_t kIdesc = idesc_f16(192);
-// After the conv units of a pair of leaves the same ring carries the fp32 operands of proj and of the distance
-// computation to the worker warps: proj.weight^T [128 c][128 d] as 4 chunks of 32 c rows, then the codebook transposed
-// [128 d][256 k] as 8 chunks of 16 d rows (16 KB each).
-constexpr uint32_t kVqChunkBytes = 16384;
-constexpr int kProjChunks = 4, kEmbChunks = 8;
-constexpr int kRingLoadsPerPair = kEnc128BackUnits + kProjChunks + kEmbChunks;  // 300
+// After the conv units of a pair of leaves the same ring carries the folded codebook (encode_tc128_stream.hpp): for each
+// input-channel half, for each half of the codes, M_hi then M_lo as [128 codes][64 c] fp16 units of 16 KB.
+constexpr int kVqUnits = kEnc128VqUnits;
+constexpr uint32_t kVqUnitBytes = kEnc128VqUnitBytes;
+constexpr int kRingLoadsPerPair = kEnc128BackUnits + kVqUnits;  // 296
+constexpr uint32_t kColVqHH = 0, kColVqMix = 256;    // score accumulators: x_hi.M_hi | x_lo.M_hi + x_hi.M_lo, 256 codes each (all of TMEM)
+constexpr uint32_t kIdescVq = idesc_f16(128);
+// Error bound of a score (see quantize_rows): kVqCb |x| max_k |M_k| for the split-fp16 GEMM, kVqCn (|W| |x| + |b| + max |e|)^2
+// + kVqC0 for the fp32 evaluation noise of the exact formula itself (measured <= 8.6e-8 of that square on mixed fields).
+constexpr float kVqCb = 1e-5f, kVqCn = 1e-6f, kVqC0 = 1e-4f;
 
 // shared memory map (bytes)
 constexpr uint32_t kOffRing = 0;
@@ -56,13 +63,18 @@ constexpr uint32_t kLeafBytes = 2 * kBufBytes;       // buffers P and Q
 constexpr uint32_t kOffLeaf = kOffRing + kStages * kUnitBytes;
 constexpr uint32_t kOffZero = kOffLeaf + 2 * kLeafBytes;
 constexpr uint32_t kOffBar = kOffZero + 256;
-constexpr uint32_t kNumBars = 2 * kStages + 2 + 2 + 1 + 1 + 1;  // w_full, w_empty, a_full[2], a_empty[2], d_full, d_empty, in_ready
+constexpr uint32_t kNumBars = 2 * kStages + 2 + 2 + 1 + 1 + 1 + 1;  // w_full, w_empty, a_full[2], a_empty[2], d_full, d_empty, in_ready, x_ready
 constexpr uint32_t kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr uint32_t kOffPar = (kOffTmemSlot + 16 + 15) & ~15u;
 constexpr uint32_t kOffScratch = kOffPar + par128e::total * 4;
-// per-leaf scratch (floats): exch [2 slots][2 warps][2 halves][8], part [2 wil][128], scale [128], hid [32], best [16][64], best index [16][64]
-constexpr uint32_t kScrExch = 0, kScrPart = 64, kScrScale = 320, kScrHid = 448, kScrBest = 480, kScrBi = 1504, kScratchFloats = 2528;
-constexpr uint32_t kSmemBytes = kOffScratch + 2 * kScratchFloats * 4;
+// per-leaf scratch (floats): exch [2 slots][2 warps][2 halves][8], part [2 wil][128], scale [128], hid [32]
+constexpr uint32_t kScrExch = 0, kScrPart = 64, kScrScale = 320, kScrHid = 448, kScratchFloats = 480;
+// codebook-search scratch of the pair (floats): |x|^2 partials [2 channel halves][128 rows]; per code quarter and row the
+// smallest / second-smallest score and the smallest's code [4][128] each; the re-scored minima and codes [4][128] each;
+// the list of near-tie rows [128] and its length
+constexpr uint32_t kVqXx = 0, kVqLo1 = 256, kVqLo2 = 768, kVqK1 = 1280, kVqBest = 1792, kVqBi = 2304, kVqAmb = 2816, kVqNamb = 2944, kVqFloats = 2948;
+constexpr uint32_t kOffVq = kOffScratch + 2 * kScratchFloats * 4;
+constexpr uint32_t kSmemBytes = kOffVq + kVqFloats * 4;
 static_assert(kSmemBytes <= 227 * 1024, "encode_tc128 back smem budget");
 static_assert(kOffBar % 8 == 0 && kOffPar % 16 == 0 && kOffScratch % 16 == 0, "alignment");
 
@@ -73,6 +85,7 @@ __device__ __forceinline__ uint32_t bar_a_empty(uint32_t bars, uint32_t b) { ret
 __device__ __forceinline__ uint32_t bar_d_full(uint32_t bars) { return bars + (2 * kStages + 4) * 8; }
 __device__ __forceinline__ uint32_t bar_d_empty(uint32_t bars) { return bars + (2 * kStages + 5) * 8; }
 __device__ __forceinline__ uint32_t bar_in_ready(uint32_t bars) { return bars + (2 * kStages + 6) * 8; }
+__device__ __forceinline__ uint32_t bar_x_ready(uint32_t bars) { return bars + (2 * kStages + 7) * 8; }
 
 // Physical byte offset, inside a [64 pos][128 ch] fp16 plane, of the 16-byte chunk holding channels 8*c16 .. 8*c16+7 of row pos.
 __device__ __forceinline__ uint32_t chunk_off(int pos, int c16) {
@@ -177,127 +190,196 @@ __device__ __forceinline__ void store_row32_split(uint32_t buf, int pos, int c16
 	}
 }
 
-// proj + distances + argmin for one leaf by its 256 worker threads.  A thread owns FOUR positions (4 pq .. 4 pq + 3, pq = t & 15)
-// and one of 16 groups (grp = t >> 4) of 8 projected dims / 16 codes, so that every weight it fetches from shared memory
-// feeds four FMAs (the phase is bound by shared-memory instruction issue otherwise).
-// x: fp32 [128 c][64 pos] (attention output), z: fp32 [128 d][64 pos] scratch, both in shared memory.  The weights arrive
-// through the ring (first_load = index of the pair's first fp32 chunk among all ring loads of this CTA).
-__device__ __forceinline__ void project_and_quantize(const Encoder128BackWeights& w, const float* s_par, uint32_t bars, uint32_t ring, uint32_t first_load,
-                                                     uint32_t x, uint32_t z, float* s_best, int* s_bi, int t, bool releaser, int64_t leaf, bool leaf_ok,
-                                                     uint8_t* __restrict__ indices, int tap_stage, float* __restrict__ tap_out) {
-	const int pq = t & 15, grp = t >> 4;
-	uint32_t load = first_load;
-	named_bar_sync(kBarWorkers, kWorkers);  // x is complete
-	{
-		// z[d][p] = b[d] + sum_c x[c][p] * W[d][c], c ascending from 0 (conv3d of the oracle with k = 1), d = 8 grp .. 8 grp + 7
-		float acc[8][4];
+// Codebook search for the pair's 128 GEMM rows by all 512 worker threads (InferenceVectorQuantizer.get_indices,
+// python/save_for_inference.py:55-61: argmin_k (|z|^2 + |e_k|^2) - 2 z.e_k, first minimum wins; z = W x + b).
+//  1. a_k = (|e_k|^2 - 2 b.e_k) - 2 (x_hi.M_hi + (x_lo.M_hi + x_hi.M_lo) / 2048) from the accumulators = dist_k - |z|^2 up to
+//     |error| <= B = kVqCb |x| max_k |M_k| (operand split 3 * 2^-22, accumulator truncation over 8 k-steps; x 2)
+//                  + kVqCn (|W| |x| + |b| + max |e|)^2 + kVqC0 (the fp32 noise of the reference formula itself).
+//     A thread owns one row and a quarter of the codes (cq): one pass keeps its two smallest scores and the smallest's code.
+//  2. every code that can be the fp32 arg-min has a_k <= min_j a_j + 2 B: a row whose second-smallest score exceeds that
+//     is decided (~99.9 % of the rows; z is never formed).
+//  3. the others: z = W x + b as an fp32 FMA chain (c ascending, bias last: conv3d of the oracle with k = 1), then every
+//     code inside the window is re-scored with (sum_d z_d^2 + |e_k|^2) - 2 sum_d z_d e_kd, every sum sequential in d,
+//     codes ascending, strict <: the index of the all-fp32 path.  tap_stage 3 sends every row this way (and taps z).
+// x: the attention output as fp32 [128 c][64 pos] in each leaf's buffer P; z rows go over the (consumed) A operand in Q.
+struct VqCtx {
+	uint32_t s_base, tmem_lane;
+	const float* s_par;
+	float* s_vq;
+	int t, row, cq, lane;
+};
+__device__ __forceinline__ uint32_t vq_zrow(uint32_t s_base, int r) {
+	return s_base + kOffLeaf + (uint32_t)(r >> 6) * kLeafBytes + kBufBytes + (uint32_t)(r & 63) * 512u;
+}
+template <class Stamp>
+__device__ __forceinline__ void quantize_rows(const Encoder128BackWeights& w, const VqCtx& q, int64_t pair_first_leaf, bool leaf_ok,
+                                              uint8_t* __restrict__ indices, int tap_stage, float* __restrict__ tap_out, Stamp&& stamp) {
+	float* s_xx = q.s_vq + kVqXx;
+	float* s_lo1 = q.s_vq + kVqLo1;
+	float* s_lo2 = q.s_vq + kVqLo2;
+	int* s_k1 = reinterpret_cast<int*>(q.s_vq + kVqK1);
+	float* s_best = q.s_vq + kVqBest;
+	int* s_bi = reinterpret_cast<int*>(q.s_vq + kVqBi);
+	int* s_amb = reinterpret_cast<int*>(q.s_vq + kVqAmb);
+	int* s_namb = reinterpret_cast<int*>(q.s_vq + kVqNamb);
+	const float* s_esq2 = q.s_par + par128e::vq_esq2;
+	const int row = q.row, kb = q.cq * 64;
+	const int64_t leaf = pair_first_leaf + (row >> 6);
+	if (q.t == 0) *s_namb = 0;  // read again only after the barriers below
+
+	const float xx = s_xx[row] + s_xx[128 + row];
+	const float xn = sqrtf(xx);
+	const float zb = fmaf(q.s_par[par128e::vq_const + 1], xn, q.s_par[par128e::vq_const + 2]);  // >= |z| + |e_k|
+	const float bmax = fmaf(kVqCb * xn, q.s_par[par128e::vq_const], fmaf(kVqCn * zb, zb, kVqC0));
+	float a1 = INFINITY, a2 = INFINITY;
+	int k1 = 0;
 #pragma unroll
-		for (int j = 0; j < 8; ++j)
-#pragma unroll
-			for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-#pragma unroll 1
-		for (int ch = 0; ch < kProjChunks; ++ch, ++load) {
-			const uint32_t slot = load % kStages;
-			mbar_wait(bar_w_full(bars, slot), (load / kStages) & 1u);
-			const uint32_t wbase = ring + slot * kUnitBytes + (uint32_t)grp * 32;
-#pragma unroll 4
-			for (int cl = 0; cl < 32; ++cl) {
-				const uint4 xr = lds128(x + (uint32_t)((ch * 32 + cl) * 64 + pq * 4) * 4);
-				const float xv[4] = {__uint_as_float(xr.x), __uint_as_float(xr.y), __uint_as_float(xr.z), __uint_as_float(xr.w)};
-#pragma unroll
-				for (int j4 = 0; j4 < 2; ++j4) {
-					const uint4 raw = lds128(wbase + (uint32_t)cl * 512 + j4 * 16);
-					const float wv[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
-#pragma unroll
-					for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-						for (int i = 0; i < 4; ++i) acc[4 * j4 + jj][i] = fmaf(xv[i], wv[jj], acc[4 * j4 + jj][i]);
-				}
-			}
-			named_bar_sync(kBarWorkers, kWorkers);  // every worker is done with the slot
-			if (releaser) mbar_arrive(bar_w_empty(bars, slot));
-		}
-#pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			const int d = grp * 8 + j;
-			const float b = s_par[par128e::proj_b + d];
-			uint4 o;
-			o.x = __float_as_uint(acc[j][0] + b);
-			o.y = __float_as_uint(acc[j][1] + b);
-			o.z = __float_as_uint(acc[j][2] + b);
-			o.w = __float_as_uint(acc[j][3] + b);
-			sts128(z + (uint32_t)(d * 64 + pq * 4) * 4, o);
-			if (tap_stage == 3 && leaf_ok) {
-#pragma unroll
-				for (int i = 0; i < 4; ++i) tap_out[leaf * 8192 + d * 64 + pq * 4 + i] = acc[j][i] + b;
-			}
-		}
-	}
-	named_bar_sync(kBarWorkers, kWorkers);  // z is complete
-	{
-		// dist_k = (sum_d z_d^2 + |e_k|^2) - 2 * sum_d z_d e_kd, every sum sequential in d; first minimum wins.
-		// This thread: codes 16 grp .. 16 grp + 15 for its four positions, all 64 dot products carried through the 8 chunks.
-		float dot[16][4];
-#pragma unroll
-		for (int j = 0; j < 16; ++j)
-#pragma unroll
-			for (int i = 0; i < 4; ++i) dot[j][i] = 0.f;
-		float zz[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-		for (int ch = 0; ch < kEmbChunks; ++ch, ++load) {
-			const uint32_t slot = load % kStages;
-			mbar_wait(bar_w_full(bars, slot), (load / kStages) & 1u);
-			const uint32_t ebase = ring + slot * kUnitBytes + (uint32_t)grp * 64;
-#pragma unroll 2
-			for (int dl = 0; dl < 16; ++dl) {
-				const uint4 zr = lds128(z + (uint32_t)((ch * 16 + dl) * 64 + pq * 4) * 4);
-				const float zv[4] = {__uint_as_float(zr.x), __uint_as_float(zr.y), __uint_as_float(zr.z), __uint_as_float(zr.w)};
-#pragma unroll
-				for (int i = 0; i < 4; ++i) zz[i] = fmaf(zv[i], zv[i], zz[i]);
-#pragma unroll
-				for (int j4 = 0; j4 < 4; ++j4) {
-					const uint4 raw = lds128(ebase + (uint32_t)dl * 1024 + j4 * 16);
-					const float ev[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
-#pragma unroll
-					for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-						for (int i = 0; i < 4; ++i) dot[4 * j4 + jj][i] = fmaf(zv[i], ev[jj], dot[4 * j4 + jj][i]);
-				}
-			}
-			named_bar_sync(kBarWorkers, kWorkers);
-			if (releaser) mbar_arrive(bar_w_empty(bars, slot));
-		}
-		float best[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-		int bi[4] = {0, 0, 0, 0};
+	for (int b = 0; b < 4; ++b) {
+		float hh[16], mx[16];
+		tmem_ld16_nowait(q.tmem_lane + kColVqHH + kb + b * 16, hh);
+		tmem_ld16_nowait(q.tmem_lane + kColVqMix + kb + b * 16, mx);
+		tmem_wait_ld();
 #pragma unroll
 		for (int j = 0; j < 16; ++j) {
-			const float esq = __ldg(w.emb_sq + grp * 16 + j);
-#pragma unroll
-			for (int i = 0; i < 4; ++i) {
-				const float dist = (zz[i] + esq) - 2.f * dot[j][i];
-				if (dist < best[i]) {
-					best[i] = dist;
-					bi[i] = grp * 16 + j;
-				}
-			}
+			const int k = kb + b * 16 + j;
+			const float a = s_esq2[k] - 2.f * fmaf(mx[j], kLoInv, hh[j]);
+			k1 = a < a1 ? k : k1;  // codes ascend: strict < keeps the lowest code among equal scores
+			a2 = fminf(a2, fmaxf(a1, a));
+			a1 = fminf(a1, a);
 		}
+	}
+	s_lo1[q.cq * 128 + row] = a1;
+	s_lo2[q.cq * 128 + row] = a2;
+	s_k1[q.cq * 128 + row] = k1;
+	tc_fence_before();
+	named_bar_sync(kBarWorkers, kWorkers);
+	float l1 = INFINITY, l2 = INFINITY;
+	int kbest = 0;
 #pragma unroll
-		for (int i = 0; i < 4; ++i) {
-			s_best[grp * 64 + pq * 4 + i] = best[i];
-			s_bi[grp * 64 + pq * 4 + i] = bi[i];
+	for (int o = 0; o < 4; ++o) {  // ascending code ranges
+		const float b1 = s_lo1[o * 128 + row], b2 = s_lo2[o * 128 + row];
+		if (b1 < l1) {
+			l2 = l1;
+			l1 = b1;
+			kbest = s_k1[o * 128 + row];
+		} else {
+			l2 = fminf(l2, b1);
+		}
+		l2 = fminf(l2, b2);
+	}
+	// a non-finite row (inf / nan inputs; fminf would skip a nan score) takes the exact path; the spare slot of an odd call none
+	const bool amb = leaf_ok && (!(l2 > l1 + 2.f * bmax) || !(xx < INFINITY) || tap_stage == 3);
+	if (q.cq == 0) {
+		if (amb) s_amb[atomicAdd(s_namb, 1)] = row;
+		else if (leaf_ok) indices[leaf * 64 + (row & 63)] = (uint8_t)kbest;  // pos = (d*4+h)*4+w == view(B,4,4,4)
+	}
+	named_bar_sync(kBarWorkers, kWorkers);
+	const int n_amb = *s_namb;
+	stamp();
+	if (n_amb == 0) return;  // uniform over the CTA
+
+	// ---- z rows of the near-tie rows: thread = (one of four rows per round, projected dim d) ----
+#pragma unroll 1
+	for (int i0 = 0; i0 < n_amb; i0 += 4) {
+		const int rs = i0 + (q.t >> 7);
+		if (rs < n_amb) {
+			const int r = s_amb[rs], d = q.t & 127;
+			const uint32_t xb = q.s_base + kOffLeaf + (uint32_t)(r >> 6) * kLeafBytes + (uint32_t)(r & 63) * 4u;  // x[c][pos] of that leaf
+			const float* wt = w.proj_t + d;
+			float acc = 0.f;
+#pragma unroll 1
+			for (int c0 = 0; c0 < 128; c0 += 32) {  // 32 L2 loads in flight: the chain is latency-bound
+				float wv[32];
+#pragma unroll
+				for (int c = 0; c < 32; ++c) wv[c] = __ldg(wt + (c0 + c) * 128);
+#pragma unroll
+				for (int c = 0; c < 32; ++c) acc = fmaf(lds32(xb + (uint32_t)(c0 + c) * 256u), wv[c], acc);
+			}
+			const float zv = acc + q.s_par[par128e::proj_b + d];
+			sts32(vq_zrow(q.s_base, r) + (uint32_t)d * 4u, zv);
+			if (tap_stage == 3) tap_out[(pair_first_leaf + (r >> 6)) * 8192 + d * 64 + (r & 63)] = zv;
 		}
 	}
 	named_bar_sync(kBarWorkers, kWorkers);
-	if (t < 64) {
-		float best = s_best[t];
-		int bi = s_bi[t];
+	stamp();
+
+	// ---- re-score this thread's codes inside the row's window (a second look at the accumulators: tcgen05.ld is
+	//      warp-collective, so a warp with a near-tie row runs the loads with all its lanes) ----
+	float best = INFINITY;
+	int bi = 0x7fffffff;
+	if (__any_sync(0xffffffffu, amb)) {
+		const float near = l1 + 2.f * bmax;
+		uint32_t mask[2] = {0u, 0u};
 #pragma unroll
-		for (int gg = 1; gg < 16; ++gg)  // ascending code order, strict <: the first minimum wins
-			if (s_best[gg * 64 + t] < best) {
-				best = s_best[gg * 64 + t];
-				bi = s_bi[gg * 64 + t];
+		for (int b = 0; b < 4; ++b) {
+			float hh[16], mx[16];
+			tmem_ld16_nowait(q.tmem_lane + kColVqHH + kb + b * 16, hh);
+			tmem_ld16_nowait(q.tmem_lane + kColVqMix + kb + b * 16, mx);
+			tmem_wait_ld();
+#pragma unroll
+			for (int j = 0; j < 16; ++j) {
+				const float a = s_esq2[kb + b * 16 + j] - 2.f * fmaf(mx[j], kLoInv, hh[j]);
+				if (!(a > near)) mask[b >> 1] |= 1u << ((b & 1) * 16 + j);
 			}
-		if (leaf_ok) indices[leaf * 64 + t] = (uint8_t)bi;
+		}
+		if (amb) {
+			const uint32_t zr = vq_zrow(q.s_base, row);
+			float zz = 0.f;
+#pragma unroll 4
+			for (int d4 = 0; d4 < 32; ++d4) {
+				const uint4 zq = lds128(zr + (uint32_t)d4 * 16u);
+				zz = fmaf(__uint_as_float(zq.x), __uint_as_float(zq.x), zz);
+				zz = fmaf(__uint_as_float(zq.y), __uint_as_float(zq.y), zz);
+				zz = fmaf(__uint_as_float(zq.z), __uint_as_float(zq.z), zz);
+				zz = fmaf(__uint_as_float(zq.w), __uint_as_float(zq.w), zz);
+			}
+#pragma unroll 1
+			for (int half = 0; half < 2; ++half) {
+				uint32_t m = mask[half];
+				while (m) {
+					const int code = kb + half * 32 + __ffs((int)m) - 1;
+					m &= m - 1;
+					const float4* e = reinterpret_cast<const float4*>(w.emb + (size_t)code * 128);
+					float dot = 0.f;
+#pragma unroll 1
+					for (int d0 = 0; d0 < 32; d0 += 8) {  // 8 x 16 B of the code in flight (L2)
+						float4 ev[8];
+#pragma unroll
+						for (int i = 0; i < 8; ++i) ev[i] = __ldg(e + d0 + i);
+#pragma unroll
+						for (int i = 0; i < 8; ++i) {
+							const uint4 zq = lds128(zr + (uint32_t)(d0 + i) * 16u);
+							dot = fmaf(__uint_as_float(zq.x), ev[i].x, dot);
+							dot = fmaf(__uint_as_float(zq.y), ev[i].y, dot);
+							dot = fmaf(__uint_as_float(zq.z), ev[i].z, dot);
+							dot = fmaf(__uint_as_float(zq.w), ev[i].w, dot);
+						}
+					}
+					const float dist = (zz + __ldg(w.emb_sq + code)) - 2.f * dot;
+					if (dist < best) {  // codes ascend, so strict < keeps the first minimum
+						best = dist;
+						bi = code;
+					}
+				}
+			}
+		}
+	}
+	s_best[q.cq * 128 + row] = best;
+	s_bi[q.cq * 128 + row] = bi;
+	tc_fence_before();
+	named_bar_sync(kBarWorkers, kWorkers);
+	stamp();
+	if (q.cq == 0 && amb) {
+#pragma unroll
+		for (int o = 1; o < 4; ++o) {  // ascending code ranges: strict < keeps the lowest code among equal distances
+			const float ob = s_best[o * 128 + row];
+			if (ob < best) {
+				best = ob;
+				bi = s_bi[o * 128 + row];
+			}
+		}
+		if (bi == 0x7fffffff) bi = kbest;  // every distance was nan: keep the shortlist's choice
+		indices[leaf * 64 + (row & 63)] = (uint8_t)bi;
 	}
 }
 
@@ -327,6 +409,7 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 		mbar_init(bar_d_full(bars), 1);
 		mbar_init(bar_d_empty(bars), kEpiWarps);
 		mbar_init(bar_in_ready(bars), kEpiWarps);
+		mbar_init(bar_x_ready(bars), kEpiWarps);
 		mbar_fence_init();
 	}
 	if (warp == kIssuerWarp) {
@@ -347,9 +430,8 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 			for (uint32_t issued = 0; issued < total; ++issued) {
 				const uint32_t s = issued % kStages, u = issued % kRingLoadsPerPair;
 				const bool conv = u < (uint32_t)kEnc128BackUnits;
-				const uint32_t bytes = conv ? kUnitBytes : kVqChunkBytes;
-				const uint8_t* src = conv ? w.units + (size_t)u * kUnitBytes
-				                          : reinterpret_cast<const uint8_t*>(w.vq_stream) + (size_t)(u - kEnc128BackUnits) * kVqChunkBytes;
+				const uint32_t bytes = conv ? kUnitBytes : kVqUnitBytes;
+				const uint8_t* src = conv ? w.units + (size_t)u * kUnitBytes : w.vq_units + (size_t)(u - kEnc128BackUnits) * kVqUnitBytes;
 				mbar_wait(bar_w_empty(bars, s), ((issued / kStages) & 1u) ^ 1u);
 				mbar_arrive_expect_tx(bar_w_full(bars, s), bytes);
 				tma_load_1d(ring + s * kUnitBytes, src, bytes, bar_w_full(bars, s));
@@ -398,7 +480,42 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 					if (u == kSteps - 1 && leader) tc_commit(bar_d_full(bars));
 				}
 			}
-			unit += kProjChunks + kEmbChunks;  // ring loads consumed by the worker warps
+			// ---- codebook scores: [128 rows][128 c] x [128 c][256 k], SS mode, three products into two accumulators ----
+			mbar_wait(bar_d_empty(bars), (pass & 1u) ^ 1u);   // the last conv result has been read out of the accumulators
+			mbar_wait(bar_x_ready(bars), (uint32_t)g & 1u);    // the A operand (attention output, hi / lo planes) is in shared memory
+			tc_fence_after();
+#pragma unroll 1
+			for (uint32_t kh = 0; kh < 2; ++kh) {
+				const uint64_t a_hi = make_desc_sw128(s_base + kOffLeaf + kBufBytes + kh * 16384u);
+				const uint64_t a_lo = make_desc_sw128(s_base + kOffLeaf + kLeafBytes + kBufBytes + kh * 16384u);
+#pragma unroll 1
+				for (uint32_t nh = 0; nh < 2; ++nh) {
+					const uint32_t s_hi = unit % kStages, ph_hi = (unit / kStages) & 1u;
+					++unit;
+					const uint32_t s_lo = unit % kStages, ph_lo = (unit / kStages) & 1u;
+					++unit;
+					const uint32_t d_hh = tmem + kColVqHH + nh * 128, d_mix = tmem + kColVqMix + nh * 128;
+					mbar_wait(bar_w_full(bars, s_hi), ph_hi);
+					tc_fence_after();
+					const uint64_t b_hi = make_desc_sw128(ring + s_hi * kUnitBytes);
+#pragma unroll
+					for (uint32_t kk = 0; kk < 4; ++kk)
+						if (leader) tc_mma_ss(d_hh, a_hi + (uint64_t)(kk * 2), b_hi + (uint64_t)(kk * 2), kIdescVq, (kh | kk) ? 1u : 0u);
+#pragma unroll
+					for (uint32_t kk = 0; kk < 4; ++kk)
+						if (leader) tc_mma_ss(d_mix, a_lo + (uint64_t)(kk * 2), b_hi + (uint64_t)(kk * 2), kIdescVq, (kh | kk) ? 1u : 0u);
+					if (leader) tc_commit(bar_w_empty(bars, s_hi));
+					mbar_wait(bar_w_full(bars, s_lo), ph_lo);
+					tc_fence_after();
+					const uint64_t b_lo = make_desc_sw128(ring + s_lo * kUnitBytes);
+#pragma unroll
+					for (uint32_t kk = 0; kk < 4; ++kk)
+						if (leader) tc_mma_ss(d_mix, a_hi + (uint64_t)(kk * 2), b_lo + (uint64_t)(kk * 2), kIdescVq, 1u);
+					if (leader) tc_commit(bar_w_empty(bars, s_lo));
+				}
+			}
+			if (leader) tc_commit(bar_d_full(bars));
+			++pass;
 		}
 		__syncwarp();
 	} else {
@@ -409,7 +526,15 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 		const uint32_t leaf_base = s_base + kOffLeaf + (uint32_t)leaf_slot * kLeafBytes;
 		const uint32_t bufP = leaf_base, bufQ = leaf_base + kBufBytes;
 		float* scratch = reinterpret_cast<float*>(smem + kOffScratch) + leaf_slot * kScratchFloats;
-		const int t256 = (is_stager ? 128 : 0) + chalf * 64 + pos;  // thread index among the leaf's 256 workers
+		VqCtx vq;
+		vq.s_base = s_base;
+		vq.tmem_lane = tmem + ((uint32_t)(quad * 32) << 16);
+		vq.s_par = s_par;
+		vq.s_vq = reinterpret_cast<float*>(smem + kOffVq);
+		vq.t = threadIdx.x;                       // 0..511 among the worker threads
+		vq.row = row;
+		vq.cq = (is_stager ? 2 : 0) + chalf;      // this thread's quarter of the codes
+		vq.lane = lane;
 		const uint32_t tmem_lane = tmem + ((uint32_t)(quad * 32) << 16);
 
 		// stager state: tap-shifted activation rows (hi and lo planes) -> TMEM A buffers
@@ -565,6 +690,7 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 					if (part == 0) s_hid[unit] = fmaxf(s, 0.f);
 				}
 				leaf_bar(e);
+				stamp();
 				{
 					float s = 0.f;
 #pragma unroll
@@ -572,22 +698,54 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 					s_scale[tl] = sigmoid_f(s);
 				}
 				leaf_bar(e);
+				stamp();
+				// x'' * scale: kept as fp32 [c][pos] in P (near-tie rows), split into the score GEMM's A operand — SWIZZLE_128B
+				// K-major tiles [128 rows][64 c] over the two leaves' (consumed) Q buffers: hi planes in leaf slot 0's, lo planes
+				// in leaf slot 1's, one 16 KB tile per input-channel half — and its squared norm for the error bound
+				float xxp = 0.f;
 #pragma unroll 1
 				for (int hh = 0; hh < 2; ++hh) {
 					const int c0 = hh * 64 + chalf * 32;
+					float xv[32];
 #pragma unroll
 					for (int j = 0; j < 32; ++j) {
 						const uint32_t a = bufP + (uint32_t)((c0 + j) * 64 + pos) * 4;
-						const float xv = lds32(a) * s_scale[c0 + j];
-						sts32(a, xv);
-						if (tap_stage == 2 && leaf_ok) tap_out[leaf * 8192 + (c0 + j) * 64 + pos] = xv;
+						xv[j] = lds32(a) * s_scale[c0 + j];
+						sts32(a, xv[j]);
+						xxp = fmaf(xv[j], xv[j], xxp);
+						if (tap_stage == 2 && leaf_ok) tap_out[leaf * 8192 + (c0 + j) * 64 + pos] = xv[j];
+					}
+					const uint32_t a_hi = s_base + kOffLeaf + kBufBytes + (uint32_t)hh * 16384u, a_lo = a_hi + kLeafBytes;
+#pragma unroll
+					for (int q = 0; q < 4; ++q) {
+						uint4 hi, lo;
+						split8(xv + 8 * q, hi, lo);
+						const uint32_t off = (uint32_t)row * 128u + ((uint32_t)((chalf * 4 + q) ^ (row & 7)) << 4);
+						sts128(a_hi + off, hi);
+						sts128(a_lo + off, lo);
 					}
 				}
+				vq.s_vq[kVqXx + chalf * 128 + row] = xxp;
+				fence_proxy_async_smem();
+				__syncwarp();
+				if (lane == 0) mbar_arrive(bar_x_ready(bars));
+				stamp();
+				// the scores of the pair's 128 rows are in the accumulators
+				mbar_wait(bar_d_full(bars), e.passes & 1u);
+				tc_fence_after();
+				tc_fence_before();
 			}
-			// every worker warp, one call site: proj + distances + argmin
+			// every worker warp, one call site: scores -> indices
 			stamp();
-			project_and_quantize(w, s_par, bars, ring, (uint32_t)g * kRingLoadsPerPair + kEnc128BackUnits, bufP, bufQ, scratch + kScrBest,
-			                     reinterpret_cast<int*>(scratch + kScrBi), t256, threadIdx.x == 0, leaf, leaf_ok, indices, tap_stage, tap_out);
+			named_bar_sync(kBarWorkers, kWorkers);  // the epilogue warps have seen the score GEMM complete; |x|^2 partials are in place
+			tc_fence_after();
+			quantize_rows(w, vq, (blockIdx.x + g * gridDim.x) * 2, leaf_ok, indices, tap_stage, tap_out, stamp);
+			if (!is_stager) {  // every worker passed a barrier after its last look at the accumulators: hand them back
+				tc_fence_before();
+				__syncwarp();
+				if (lane == 0) mbar_arrive(bar_d_empty(bars));
+				++e.passes;
+			}
 			stamp();
 		}
 	}

@@ -5,8 +5,9 @@
 // Index parity needs fp32-level accuracy, so every 3x3x3 convolution runs in the split-fp16 scheme of the
 // float encoder (encode_tc.cu): a = a_hi + a_lo / 2048, w = w_hi + w_lo / 2048, three fp16 products
 //     a_hi * w_hi  ->  accumulator "hh" ;  a_lo * w_hi + a_hi * w_lo  ->  accumulator "mix" (weighted 1 / 2048)
-// with fp32 accumulation in TMEM.  The 1x1 projection and the distance computation stay on the fp32 pipes with the
-// summation order of oracle/vqvae_oracle.c.
+// with fp32 accumulation in TMEM.  The 1x1 projection is folded into the codebook and the distances of all 256 codes come
+// from one more split-fp16 GEMM with a rigorous error bound; rows whose two best codes are closer than that bound
+// (near-ties) are re-scored on the fp32 pipes with the summation order of oracle/vqvae_oracle.c.
 //
 // Two kernels, one per spatial resolution, with the stride-2 output (128 channels at 4^3, fp32, 32 KB per leaf) handed
 // over in global memory:
@@ -28,7 +29,9 @@ struct Encoder128BackWeights {
 	const float* par;       // par128e::total floats
 	const float* fc0;       // encoder.attn.fc.0.weight [32][128]
 	const float* fc2;       // encoder.attn.fc.2.weight [128][32]
-	const float* vq_stream; // encoder.proj.weight transposed to [128 c][128 d], then quantizer.embedding transposed to [128 d][256 k]
+	const uint8_t* vq_units; // kEnc128VqUnits * kEnc128VqUnitBytes: the codebook with proj folded in, fp16 hi / lo planes
+	const float* proj_t;    // encoder.proj.weight transposed to [128 c][128 d]   (near-tie rows: z = W x + b in fp32)
+	const float* emb;       // quantizer.embedding [256 k][128 d]                 (near-tie rows: exact re-scoring)
 	const float* emb_sq;    // [256] sum_d e_kd^2 (fp32, sequential in d as the oracle's)
 };
 

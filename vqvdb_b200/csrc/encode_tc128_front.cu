@@ -262,11 +262,12 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 #pragma unroll 1
 					for (int r = 0; r < 2; ++r) {
 						const int c0 = (cgrp * 2 + r) * 8;
-						float acc[8][4];
+						// packed fp32 pairs (FFMA2): acc2[jp][i] = channels c0 + 2 jp, c0 + 2 jp + 1 of position i
+						uint64_t acc2[4][4];
 #pragma unroll
-						for (int j = 0; j < 8; ++j)
+						for (int jp = 0; jp < 4; ++jp)
 #pragma unroll
-							for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+							for (int i = 0; i < 4; ++i) acc2[jp][i] = 0ull;
 #pragma unroll 1
 						for (int ic = 0; ic < 3; ++ic) {
 #pragma unroll 1
@@ -274,28 +275,33 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 #pragma unroll
 								for (int kh = 0; kh < 3; ++kh) {
 									const uint32_t ia = in0 + (uint32_t)(ic * 1000 + kd * 100 + kh * 10) * 4;
-									float in[6];
+									uint64_t in2[6];  // the input value in both halves
 #pragma unroll
 									for (int i2 = 0; i2 < 3; ++i2) {
 										float2 v2;
 										asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v2.x), "=f"(v2.y) : "r"(ia + i2 * 8));
-										in[2 * i2] = v2.x;
-										in[2 * i2 + 1] = v2.y;
+										in2[2 * i2] = pack_f32x2(v2.x, v2.x);
+										in2[2 * i2 + 1] = pack_f32x2(v2.y, v2.y);
 									}
 #pragma unroll
 									for (int kw = 0; kw < 3; ++kw) {
 										const uint32_t wa = plane_hi + (uint32_t)((ic * 27 + (kd * 3 + kh) * 3 + kw) * 64 + c0) * 4;
 										const uint4 w0r = lds128(wa), w1r = lds128(wa + 16);
-										const float wv[8] = {__uint_as_float(w0r.x), __uint_as_float(w0r.y), __uint_as_float(w0r.z), __uint_as_float(w0r.w),
-										                     __uint_as_float(w1r.x), __uint_as_float(w1r.y), __uint_as_float(w1r.z), __uint_as_float(w1r.w)};
+										const uint64_t wp[4] = {pack_f32x2(__uint_as_float(w0r.x), __uint_as_float(w0r.y)), pack_f32x2(__uint_as_float(w0r.z), __uint_as_float(w0r.w)),
+										                        pack_f32x2(__uint_as_float(w1r.x), __uint_as_float(w1r.y)), pack_f32x2(__uint_as_float(w1r.z), __uint_as_float(w1r.w))};
 #pragma unroll
-										for (int j = 0; j < 8; ++j)
+										for (int jp = 0; jp < 4; ++jp)
 #pragma unroll
-											for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(in[i + kw], wv[j], acc[j][i]);
+											for (int i = 0; i < 4; ++i) acc2[jp][i] = fma_f32x2(in2[i + kw], wp[jp], acc2[jp][i]);
 									}
 								}
 							}
 						}
+						float acc[8][4];
+#pragma unroll
+						for (int jp = 0; jp < 4; ++jp)
+#pragma unroll
+							for (int i = 0; i < 4; ++i) unpack_f32x2(acc2[jp][i], acc[2 * jp][i], acc[2 * jp + 1][i]);
 						const int pos0 = pd * 64 + ph * 8 + w0;
 #pragma unroll
 						for (int j = 0; j < 8; ++j) {

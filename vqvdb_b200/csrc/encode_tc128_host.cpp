@@ -1,4 +1,6 @@
 // Host-side preparation of the tensor-core vec3 encoder's weight streams and parameter blocks (encode_tc128.cuh).
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -48,6 +50,19 @@ void fill_tile_down(uint8_t* tile, const float* w, int tap, int part) {
 		}
 }
 
+// M[k][c] = sum_d e_kd W_dc in double
+std::vector<double> fold_proj_into_codebook(const WeightPack& p) {
+	const PackTensor& e = p.get("quantizer.embedding");  // [256][128]
+	const PackTensor& w = p.get("encoder.proj.weight");  // [128 d][128 c][1][1][1]
+	std::vector<double> m((size_t)256 * 128, 0.0);
+	for (int k = 0; k < 256; ++k)
+		for (int d = 0; d < 128; ++d) {
+			const double ev = e.data[(size_t)k * 128 + d];
+			for (int c = 0; c < 128; ++c) m[(size_t)k * 128 + c] += ev * (double)w.data[(size_t)d * 128 + c];
+		}
+	return m;
+}
+
 }  // namespace
 
 bool encoder128_supports(const WeightPack& p) {
@@ -95,6 +110,45 @@ std::vector<float> build_encoder128_back_params(const WeightPack& p) {
 		for (const char* v : {".gn1.weight", ".gn1.bias", ".conv1.bias", ".gn2.weight", ".gn2.bias", ".conv2.bias"}) put(pre + v, 128);
 	}
 	put("encoder.proj.bias", 128);
+	// the codebook search's constants (encode_tc128.cu): per-code offsets of the folded scores and what bounds their error
+	{
+		const PackTensor& e = p.get("quantizer.embedding");
+		const PackTensor& w = p.get("encoder.proj.weight");
+		const PackTensor& b = p.get("encoder.proj.bias");
+		const std::vector<double> m = fold_proj_into_codebook(p);
+		double m_max = 0.0, e_max = 0.0, b2 = 0.0;
+		for (int k = 0; k < 256; ++k) {
+			double e2 = 0.0, be = 0.0, m2 = 0.0;
+			for (int d = 0; d < 128; ++d) {
+				e2 += (double)e.data[(size_t)k * 128 + d] * e.data[(size_t)k * 128 + d];
+				be += (double)e.data[(size_t)k * 128 + d] * b.data[d];
+			}
+			for (int c = 0; c < 128; ++c) m2 += m[(size_t)k * 128 + c] * m[(size_t)k * 128 + c];
+			out.push_back((float)(e2 - 2.0 * be));
+			m_max = std::max(m_max, std::sqrt(m2));
+			e_max = std::max(e_max, std::sqrt(e2));
+		}
+		// |W|_2 <= min(|W|_F, sqrt(|W|_1 |W|_inf))
+		double fro2 = 0.0, n1 = 0.0, ninf = 0.0;
+		std::vector<double> col(128, 0.0);
+		for (int d = 0; d < 128; ++d) {
+			double rowsum = 0.0;
+			for (int c = 0; c < 128; ++c) {
+				const double v = std::fabs((double)w.data[(size_t)d * 128 + c]);
+				fro2 += v * v;
+				rowsum += v;
+				col[c] += v;
+			}
+			ninf = std::max(ninf, rowsum);
+		}
+		for (int c = 0; c < 128; ++c) n1 = std::max(n1, col[c]);
+		for (int d = 0; d < 128; ++d) b2 += (double)b.data[d] * b.data[d];
+		const double w_norm = std::min(std::sqrt(fro2), std::sqrt(n1 * ninf));
+		out.push_back(std::nextafter((float)m_max, INFINITY));
+		out.push_back(std::nextafter((float)w_norm, INFINITY));
+		out.push_back(std::nextafter((float)(std::sqrt(b2) + e_max), INFINITY));
+		out.push_back(0.f);
+	}
 	if (out.size() != (size_t)par128e::total) throw std::logic_error("encoder128 back parameter block size mismatch");
 	return out;
 }
@@ -133,21 +187,25 @@ std::vector<float> build_encoder128_front_params(const WeightPack& p) {
 	return out;
 }
 
-std::vector<float> build_proj_transposed(const WeightPack& p) {
-	const PackTensor& t = p.get("encoder.proj.weight");  // [D][C][1][1][1]
-	const int D = t.dims[0], C = t.dims[1];
-	std::vector<float> out((size_t)D * C);
-	for (int d = 0; d < D; ++d)
-		for (int c = 0; c < C; ++c) out[(size_t)c * D + d] = t.data[(size_t)d * C + c];
-	return out;
+std::vector<float> build_encoder128_vq_fold(const WeightPack& p) {
+	if (!encoder128_supports(p)) throw std::runtime_error("encoder128 VQ fold: unsupported architecture");
+	const std::vector<double> m = fold_proj_into_codebook(p);
+	return std::vector<float>(m.begin(), m.end());
 }
 
-std::vector<float> build_embedding_transposed(const WeightPack& p) {
-	const PackTensor& e = p.get("quantizer.embedding");
-	const int K = e.dims[0], D = e.dims[1];
-	std::vector<float> out((size_t)K * D);
-	for (int k = 0; k < K; ++k)
-		for (int d = 0; d < D; ++d) out[(size_t)d * K + k] = e.data[(size_t)k * D + d];
+std::vector<uint8_t> build_encoder128_vq_units(const WeightPack& p) {
+	const std::vector<float> m = build_encoder128_vq_fold(p);
+	std::vector<uint8_t> out((size_t)kEnc128VqUnits * kEnc128VqUnitBytes);
+	uint8_t* u = out.data();
+	for (int khalf = 0; khalf < 2; ++khalf)
+		for (int nhalf = 0; nhalf < 2; ++nhalf)
+			for (int part = 0; part < 2; ++part, u += kEnc128VqUnitBytes)
+				for (int n = 0; n < 128; ++n)
+					for (int k = 0; k < 64; ++k) {
+						const uint16_t b = split_part(m[(size_t)(nhalf * 128 + n) * 128 + khalf * 64 + k], part);
+						const size_t off = (size_t)n * 128 + ((size_t)((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
+						std::memcpy(u + off, &b, 2);
+					}
 	return out;
 }
 

@@ -25,8 +25,19 @@ namespace par128e {
 constexpr int res0 = 0, res_stride = 768;  // per block: gn1_w, gn1_b, c1_b, gn2_w, gn2_b, c2_b (128 each)
 constexpr int gn1_w = 0, gn1_b = 128, c1_b = 256, gn2_w = 384, gn2_b = 512, c2_b = 640;
 constexpr int proj_b = res0 + 2 * res_stride;  // [128]
-constexpr int total = proj_b + 128;            // 1664
+// codebook search on the tensor cores (proj folded into the codebook, see build_encoder128_vq_units):
+constexpr int vq_esq2 = proj_b + 128;          // [256] |e_k|^2 - 2 b.e_k
+constexpr int vq_const = vq_esq2 + 256;        // max_k |M_k| ; an upper bound of |proj.weight|_2 ; |proj.bias| + max_k |e_k| ; 0
+constexpr int total = vq_const + 4;            // 1924
 }  // namespace par128e
+
+// proj + codebook distances as ONE contraction (the scheme of the float encoder, encode_tc_stream.hpp): z.e_k =
+// (W x + b).e_k = x.(W^T e_k) + b.e_k, so the scores of all 256 codes come from a [128 rows][128 c] x [128 c][256 k] GEMM
+// on the attention output with M = E W folded in double precision and split into fp16 hi / lo planes.  Eight units of
+// 16 KB follow the conv units of a pair of leaves: for each input-channel half, for each half of the codes: M_hi, M_lo,
+// a unit = [128 codes][64 c] fp16 in the conv units' row layout (128-byte rows, 16-byte chunks XOR-swizzled by n & 7).
+constexpr int kEnc128VqUnits = 8;
+constexpr uint32_t kEnc128VqUnitBytes = 16384;
 
 // ---- front kernel: the 8^3 stage -------------------------------------------------------------------------------------
 // A GEMM tile is 128 positions of one leaf (two d slices).  The two 64 -> 64 convolutions are 4 tiles x 9 (kd, kh) steps,
@@ -47,7 +58,8 @@ std::vector<uint8_t> build_encoder128_back_units(const WeightPack& pack);
 std::vector<float> build_encoder128_back_params(const WeightPack& pack);
 std::vector<uint8_t> build_encoder128_front_units(const WeightPack& pack);
 std::vector<float> build_encoder128_front_params(const WeightPack& pack);
-std::vector<float> build_embedding_transposed(const WeightPack& pack);  // [D][K]
-std::vector<float> build_proj_transposed(const WeightPack& pack);       // encoder.proj.weight as [c][d]
+std::vector<uint8_t> build_encoder128_vq_units(const WeightPack& pack);  // kEnc128VqUnits * kEnc128VqUnitBytes
+// M = E W as fp32 [256 k][128 c] (what the units hold, before the split), for tests of the fold
+std::vector<float> build_encoder128_vq_fold(const WeightPack& pack);
 
 }  // namespace vqvdb

@@ -55,6 +55,19 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
 	             "l"(src), "r"(bytes), "r"(bar)
 	             : "memory");
 }
+// Packed fp32 pairs (sm_100: FFMA2): d = a * b + c on both halves, each an IEEE fma — bit-identical to two fmaf().  When
+// both halves of `a` hold the same value ptxas uses the instruction's scalar-broadcast operand form.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+	uint64_t r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+	uint64_t d;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+	return d;
+}
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
 	asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
 	             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)

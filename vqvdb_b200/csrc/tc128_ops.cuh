@@ -30,6 +30,16 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint
 	    "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
 	    : "memory");
 }
+// D[tmem_d] (+)= A[desc] (128 x 16 fp16, shared) * B[desc] (N x 16 fp16, shared)^T
+__device__ __forceinline__ void tc_mma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+	    "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+	    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+	    "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+	    : "memory");
+}
+// generic-proxy shared-memory writes -> visible to the tensor core's (async proxy) operand reads
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // K-major SWIZZLE_128B operand: 128-byte rows, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 	return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
