@@ -483,6 +483,15 @@ void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
 	for (int r = 0; r < m.e_nres; ++r) add_gres(ab, p, "encoder.res_stack." + std::to_string(r), m.e_res[r]);
 	ab.add(&m.e_fc0, p.get("encoder.attn.fc.0.weight"));
 	ab.add(&m.e_fc2, p.get("encoder.attn.fc.2.weight"));
+	auto transposed2d = [](const PackTensor& t) {  // [rows][cols] -> [cols][rows]
+		const int rows = t.dims[0], cols = t.dims[1];
+		std::vector<float> out((size_t)rows * cols);
+		for (int r = 0; r < rows; ++r)
+			for (int c2 = 0; c2 < cols; ++c2) out[(size_t)c2 * rows + r] = t.data[(size_t)r * cols + c2];
+		return out;
+	};
+	ab.add(&m.e_fc2_t, transposed2d(p.get("encoder.attn.fc.2.weight")));
+	ab.add(&m.d_fc2_t, transposed2d(p.get("decoder.attn.fc.2.weight")));
 	ab.add(&m.e_proj_w, vqvdb::transpose_conv_weight(p.get("encoder.proj.weight")));
 	ab.add(&m.e_proj_b, p.get("encoder.proj.bias"));
 	const PackTensor& emb = p.get("quantizer.embedding");
@@ -524,7 +533,7 @@ void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
 		c.dec128_w.emb_bf16 = reinterpret_cast<const __nv_bfloat16*>(c.dec128_arena + off_cb);
 		c.dec128_w.par = reinterpret_cast<const float*>(c.dec128_arena + off_par);
 		c.dec128_w.fc0 = m.d_fc0;
-		c.dec128_w.fc2 = m.d_fc2;
+		c.dec128_w.fc2_t = m.d_fc2_t;
 		c.dec128 = true;
 	}
 	// ... and so has its encoder (64 / 128 channels, one + two residual blocks)
@@ -551,7 +560,7 @@ void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
 		c.enc128_back.units = c.enc128_arena;
 		c.enc128_back.par = reinterpret_cast<const float*>(c.enc128_arena + off_par);
 		c.enc128_back.fc0 = m.e_fc0;
-		c.enc128_back.fc2 = m.e_fc2;
+		c.enc128_back.fc2_t = m.e_fc2_t;
 		c.enc128_back.vq_units = c.enc128_arena + off_emb;
 		c.enc128_back.proj_t = m.e_proj_w;
 		c.enc128_back.emb = m.emb;

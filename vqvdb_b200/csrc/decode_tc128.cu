@@ -441,7 +441,7 @@ decode_tc128_kernel(const Decoder128Weights w, const uint8_t* __restrict__ indic
 			{
 				float s = 0.f;
 #pragma unroll 8
-				for (int j = 0; j < 32; ++j) s = fmaf(__ldg(w.fc2 + tl * 32 + j), s_hid[j], s);
+				for (int j = 0; j < 32; ++j) s = fmaf(__ldg(w.fc2_t + j * 128 + tl), s_hid[j], s);  // [hidden][channel]: a warp reads one line
 				s_scale[tl] = sigmoid_f(s);
 			}
 			leaf_bar(e);

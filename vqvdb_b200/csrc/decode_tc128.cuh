@@ -45,7 +45,7 @@ struct Decoder128Weights {
 	const __nv_bfloat16* emb_bf16;  // quantizer.embedding [256][128] as bf16
 	const float* par;               // par128::total floats
 	const float* fc0;               // decoder.attn.fc.0.weight [32][128]
-	const float* fc2;               // decoder.attn.fc.2.weight [128][32]
+	const float* fc2_t;             // decoder.attn.fc.2.weight [128][32] transposed to [32][128]
 };
 
 // True when the pack is the architecture this kernel is written for: D = 128, K = 256, decoder width 128, two residual

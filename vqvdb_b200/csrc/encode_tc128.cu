@@ -694,7 +694,7 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 				{
 					float s = 0.f;
 #pragma unroll
-					for (int j = 0; j < 32; ++j) s = fmaf(__ldg(w.fc2 + tl * 32 + j), s_hid[j], s);
+					for (int j = 0; j < 32; ++j) s = fmaf(__ldg(w.fc2_t + j * 128 + tl), s_hid[j], s);  // [hidden][channel]: a warp reads one line
 					s_scale[tl] = sigmoid_f(s);
 				}
 				leaf_bar(e);

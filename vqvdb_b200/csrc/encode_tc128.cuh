@@ -28,7 +28,7 @@ struct Encoder128BackWeights {
 	const uint8_t* units;   // kEnc128BackUnits * kEnc128UnitBytes
 	const float* par;       // par128e::total floats
 	const float* fc0;       // encoder.attn.fc.0.weight [32][128]
-	const float* fc2;       // encoder.attn.fc.2.weight [128][32]
+	const float* fc2_t;     // encoder.attn.fc.2.weight [128][32] transposed to [32][128]
 	const uint8_t* vq_units; // kEnc128VqUnits * kEnc128VqUnitBytes: the codebook with proj folded in, fp16 hi / lo planes
 	const float* proj_t;    // encoder.proj.weight transposed to [128 c][128 d]   (near-tie rows: z = W x + b in fp32)
 	const float* emb;       // quantizer.embedding [256 k][128 d]                 (near-tie rows: exact re-scoring)

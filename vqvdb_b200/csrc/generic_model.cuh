@@ -21,6 +21,7 @@ struct GenericModel {
 	const float *e_down_w, *e_down_b;
 	GenericRes e_res[2];
 	const float *e_fc0, *e_fc2, *e_proj_w, *e_proj_b;
+	const float *e_fc2_t, *d_fc2_t;  // attn.fc.2.weight transposed to [hidden][channels] (coalesced reads in the tensor-core kernels)
 	const float *emb, *emb_sq;
 	int d_c, d_nres, d_red;
 	const float *d_stem_w, *d_stem_b, *d_gn_w, *d_gn_b;
