@@ -49,6 +49,19 @@ def main():
         got = tap.cpu().numpy().reshape(want.shape)
         print("tap %d: max |err| %.3e  rms %.3e  scale %.3e" % (stage, np.abs(got - want).max(), np.sqrt(((got - want) ** 2).mean()), np.abs(want).max()))
 
+    # more leaves than CTAs: from a CTA's second leaf on, pre.0 is computed ahead by the epilogue warps (encode_tc128_front.cu)
+    n2 = 600
+    xd2 = torch.from_numpy(x[:n2]).cuda()
+    idx2 = torch.empty((n2, 64), dtype=torch.uint8, device="cuda")
+    for stage, want in ((4, o.encode_tap(x[:n2], 0, 64, 128)), (3, o.latents(x[:n2]))):
+        tap = torch.zeros((n2, 64 * 512 if stage == 4 else 128 * 64), dtype=torch.float32, device="cuda")
+        tc.debug_encode_tap(xd2, n2, stage, tap, idx2, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = tap.cpu().numpy().reshape(want.shape)
+        per_leaf = np.abs(got - want).reshape(n2, -1).max(axis=1)
+        print("tap %d on %d leaves: max |err| %.3e (first leaf of a CTA: %.3e, later leaves: %.3e)" % (
+            stage, n2, per_leaf.max(), per_leaf[:148].max(), per_leaf[148:].max()))
+
     # phase timestamps of the second leaf / pair of CTA 0 (cycles since the leaf / pair started)
     nprof = 148 * 6
     xp = torch.from_numpy(np.tile(x, (1, 1, 1, 1, 1))[:nprof]).cuda()

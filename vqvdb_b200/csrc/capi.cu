@@ -178,6 +178,7 @@ struct vqvdb_b200_codec {
 	int64_t enc128_batch = 0;         // leaves per batch
 	vqvdb::Encoder128BackWeights enc128_back{};
 	vqvdb::Encoder128FrontWeights enc128_front{};
+	vqvdb::Encoder128PreWeights enc128_pre{};   // pre.0 weights, passed to the front kernel by value
 	float* enc128_scratch = nullptr;  // per pipeline slot: the front kernel's per-CTA fp32 scratch
 	vqvdb::EncoderWeights enc{};
 	vqvdb::EncoderUnits enc_units{};
@@ -551,7 +552,11 @@ void upload_generic_model(vqvdb_b200_codec& c, const WeightPack& p) {
 		CUDA_TRY(cudaMalloc(&c.enc128_scratch, (size_t)(kSlots + 1) * vqvdb::encode_tc128_front_scratch_floats(c.num_sms) * sizeof(float)));
 		c.enc128_front.units = c.enc128_arena + off_front;
 		c.enc128_front.par = reinterpret_cast<const float*>(c.enc128_arena + off_fpar);
-		c.enc128_front.pre_wt = m.e_pre_w;
+		{
+			const std::vector<float> pw = vqvdb::transpose_conv_weight(p.get("encoder.pre.0.weight"));  // [3 ic][27][64 c]
+			if (pw.size() != sizeof(c.enc128_pre.w) / sizeof(float)) throw std::logic_error("encoder128: pre.0 weight size mismatch");
+			std::memcpy(c.enc128_pre.w, pw.data(), sizeof(c.enc128_pre.w));
+		}
 		CUDA_TRY(cudaMemcpy(c.enc128_arena, back.data(), back.size(), cudaMemcpyHostToDevice));
 		CUDA_TRY(cudaMemcpy(c.enc128_arena + off_par, back_par.data(), back_par.size() * sizeof(float), cudaMemcpyHostToDevice));
 		CUDA_TRY(cudaMemcpy(c.enc128_arena + off_emb, vq_units.data(), vq_units.size(), cudaMemcpyHostToDevice));
@@ -630,7 +635,7 @@ void launch_encode(vqvdb_b200_codec& c, const float* d_leaves, int64_t n, uint8_
 			if (kEnc128GenericFront) {
 				float* gscratch = c.gen_scratch + (size_t)slot * vqvdb::generic_scratch_floats(c.gen_grid);
 				CUDA_TRY(vqvdb::launch_encode_generic_front(c.gen, d_leaves + first * 1536, nb, y, gscratch, c.gen_grid, st));
-			} else CUDA_TRY(vqvdb::launch_encode_tc128_front(c.enc128_front, d_leaves + first * 1536, nb, y, scratch, c.num_sms, st));
+			} else CUDA_TRY(vqvdb::launch_encode_tc128_front(c.enc128_front, c.enc128_pre, d_leaves + first * 1536, nb, y, scratch, c.num_sms, st));
 			CUDA_TRY(vqvdb::launch_encode_tc128_back(c.enc128_back, y, nb, d_idx + first * 64, c.num_sms, st));
 			c.launches.fetch_add(2, std::memory_order_relaxed);
 		}
@@ -946,7 +951,7 @@ int vqvdb_b200_debug_encode_tap(vqvdb_b200_codec* c, const float* dev_leaves, in
 			if (kEnc128GenericFront) {
 				float* gscratch = c->gen_scratch + (size_t)kSlots * vqvdb::generic_scratch_floats(c->gen_grid);
 				CUDA_TRY(vqvdb::launch_encode_generic_front(c->gen, dev_leaves, n, y, gscratch, c->gen_grid, st));
-			} else CUDA_TRY(vqvdb::launch_encode_tc128_front(c->enc128_front, dev_leaves, n, y, scratch, c->num_sms, st, stage == 100 ? 100 : stage >= 4 ? stage - 4 : -1, dev_tap));
+			} else CUDA_TRY(vqvdb::launch_encode_tc128_front(c->enc128_front, c->enc128_pre, dev_leaves, n, y, scratch, c->num_sms, st, stage == 100 ? 100 : stage >= 4 ? stage - 4 : -1, dev_tap));
 			if (stage == 6) CUDA_TRY(cudaMemcpyAsync(dev_tap, y, (size_t)n * 8192 * sizeof(float), cudaMemcpyDeviceToDevice, st));
 			CUDA_TRY(vqvdb::launch_encode_tc128_back(c->enc128_back, y, n, dev_indices, c->num_sms, st, stage <= 3 || stage == 100 ? stage : -1, dev_tap));
 			return VQVDB_B200_OK;

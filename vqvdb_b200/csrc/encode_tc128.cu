@@ -708,10 +708,11 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 					const int c0 = hh * 64 + chalf * 32;
 					float xv[32];
 #pragma unroll
+					for (int j = 0; j < 32; ++j) xv[j] = lds32(bufP + (uint32_t)((c0 + j) * 64 + pos) * 4);  // 32 loads in flight
+#pragma unroll
 					for (int j = 0; j < 32; ++j) {
-						const uint32_t a = bufP + (uint32_t)((c0 + j) * 64 + pos) * 4;
-						xv[j] = lds32(a) * s_scale[c0 + j];
-						sts32(a, xv[j]);
+						xv[j] *= s_scale[c0 + j];
+						sts32(bufP + (uint32_t)((c0 + j) * 64 + pos) * 4, xv[j]);
 						xxp = fmaf(xv[j], xv[j], xxp);
 						if (tap_stage == 2 && leaf_ok) tap_out[leaf * 8192 + (c0 + j) * 64 + pos] = xv[j];
 					}

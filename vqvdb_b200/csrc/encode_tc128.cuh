@@ -38,7 +38,11 @@ struct Encoder128BackWeights {
 struct Encoder128FrontWeights {
 	const uint8_t* units;   // kEnc128FrontUnits * kEnc128UnitBytes
 	const float* par;       // par128f::total floats
-	const float* pre_wt;    // encoder.pre.0.weight transposed to [3 ic][27 taps][64 c], 16-byte aligned
+};
+// encoder.pre.0.weight transposed to [3 ic][27 taps][64 c]: passed to the front kernel BY VALUE (a 20 KB kernel parameter),
+// so that its FFMAs read the weights from the constant bank instead of spending shared-memory or L2 loads on them
+struct alignas(16) Encoder128PreWeights {
+	float w[81 * 64];
 };
 
 cudaError_t configure_encode_tc128();
@@ -46,8 +50,9 @@ cudaError_t configure_encode_tc128_front();
 size_t encode_tc128_front_scratch_floats(int num_sms);
 // leaves [n][3][512] fp32 -> y [n][128 ch][64 pos] fp32 (the output of down1).  tap_stage >= 0 additionally writes the
 // fp32 activation after {0: pre (GroupNorm + ReLU), 1: the residual block} as [leaf][64][512] to tap_out.
-cudaError_t launch_encode_tc128_front(const Encoder128FrontWeights& w, const float* dev_leaves, int64_t n_leaves, float* dev_y,
-                                      float* dev_scratch, int num_sms, cudaStream_t stream, int tap_stage = -1, float* tap_out = nullptr);
+cudaError_t launch_encode_tc128_front(const Encoder128FrontWeights& w, const Encoder128PreWeights& pw, const float* dev_leaves, int64_t n_leaves,
+                                      float* dev_y, float* dev_scratch, int num_sms, cudaStream_t stream, int tap_stage = -1,
+                                      float* tap_out = nullptr);
 // y: [n][128 ch][64 pos] fp32, the output of down1; the kernel uses it as the residual stream and overwrites it.  tap_stage >= 0 additionally writes the fp32 activation after
 // {0: res_stack.0, 1: res_stack.1, 2: attention, 3: proj (z)} as [leaf][128][64] to tap_out (bring-up aid).
 cudaError_t launch_encode_tc128_back(const Encoder128BackWeights& w, float* dev_y, int64_t n_leaves, uint8_t* dev_indices,

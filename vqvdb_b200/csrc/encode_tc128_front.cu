@@ -3,8 +3,11 @@
 // 3 x 512 voxels in, 128 x 64 fp32 out (continued by encode_tc128.cu).  BASELINE.json configs[3].
 //
 // One leaf per CTA pass.  pre.0 is 2.5 % of the arithmetic with raw, unbounded voxel values as its operand: it stays on
-// the fp32 pipes, bit-identical to the oracle's conv3d (oracle/vqvae_oracle.c).  The two 64 -> 64 convolutions and the
-// stride-2 conv run on tcgen05 in the split-fp16 scheme (encode_tc128.cuh):
+// the fp32 pipes, bit-identical to the oracle's conv3d (oracle/vqvae_oracle.c) — as packed FFMA2 with the weights read
+// straight from the constant bank (they travel as a kernel parameter), and, from a CTA's second leaf on, computed for
+// the NEXT leaf by the epilogue warps inside the MMA phases of the current one (they have the lowest issue priority of
+// the CTA's warps and are idle there for ~80 % of the time).  The two 64 -> 64 convolutions and the stride-2 conv run on
+// tcgen05 in the split-fp16 scheme (encode_tc128.cuh):
 //   * the conv input lives in shared memory as channels-last fp16 planes [512 pos][64 ch] (hi, lo; 128-byte rows,
 //     16-byte chunks XOR-swizzled by pos & 7); a GEMM tile is 128 positions (two d slices); the tap-shifted rows go
 //     through TMEM (TS-mode MMA), copied by 8 stager warps;
@@ -16,8 +19,8 @@
 //   * GroupNorm needs the whole leaf: conv outputs and the residual stream go through a per-CTA fp32 scratch in global
 //     memory (L2-resident, every element private to one thread between barriers) and are normalised / split into the
 //     planes once all four tiles are done.
-// Warp roles (576 threads): 0-7 epilogue, 8-15 stagers, 16 MMA issuer, 17 TMA producer; pre.0 is computed by all 16
-// worker warps, one position per thread.
+// Warp roles (576 threads): 0-7 epilogue, 8-15 stagers, 16 MMA issuer, 17 TMA producer; a CTA's first pre.0 is computed
+// by all 16 worker warps.
 #include "encode_tc128.cuh"
 #include "leaf_ops.cuh"
 #include "tc128_ops.cuh"
@@ -69,6 +72,7 @@ __device__ __forceinline__ uint32_t bar_d_empty(uint32_t bars) { return bars + (
 __device__ __forceinline__ uint32_t bar_in_ready(uint32_t bars) { return bars + (2 * kStages + 6) * 8; }
 constexpr int kBarWorkers = 1;   // all 16 worker warps
 constexpr int kBarEpiHalf = 2;   // + chalf: the 4 epilogue warps of one channel half
+constexpr int kBarEpi = 4;       // the 8 epilogue warps
 
 // byte offset of the 16-byte chunk with channels 8*c8 .. 8*c8+7 of row pos inside a [512][64] fp16 plane
 __device__ __forceinline__ uint32_t chunk_off(int pos, int c8) { return (uint32_t)pos * 128u + ((uint32_t)(c8 ^ (pos & 7)) << 4); }
@@ -106,9 +110,86 @@ __device__ __forceinline__ void epi_allreduce4(float (&v)[4], float* red, uint32
 	++count;
 }
 
+// pre.0 for four w-adjacent positions x eight output channels c0 .. c0 + 7 of the leaf staged (with a zero halo) at s_in:
+// out[c] = b[c] + sum_{ic, kd, kh, kw} in * w, ascending, as conv3d of the oracle (halo taps add an exact 0).  Packed fp32
+// pairs (FFMA2, each half an IEEE fma) over channel pairs; every input value feeds up to three taps, every weight — read
+// from the constant bank — four positions.  pq = the thread's position quad: (d, h, half of the w row).
+// Input channels [ic0, ic1): a call with ic0 > 0 continues the partial sums a previous call left in xs (same chain of
+// FMAs, same order); the call that ends with the last input channel adds the bias.
+__device__ __forceinline__ void pre0_chunk(const Encoder128PreWeights& pw, uint32_t s_in_addr, const float* s_par, float* __restrict__ xs, int pq, int c0,
+                                           int ic0, int ic1) {
+	const int pd = pq >> 4, ph = (pq >> 1) & 7, w0 = (pq & 1) * 4;
+	const uint32_t in0 = s_in_addr + (uint32_t)(pd * 100 + ph * 10 + w0) * 4;
+	const int pos0 = pd * 64 + ph * 8 + w0;
+	uint64_t acc2[4][4];  // [channel pair][position]
+#pragma unroll
+	for (int jp = 0; jp < 4; ++jp) {
+		float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+		if (ic0 > 0) {
+			lo = *reinterpret_cast<const float4*>(xs + (c0 + 2 * jp) * 512 + pos0);
+			hi = *reinterpret_cast<const float4*>(xs + (c0 + 2 * jp + 1) * 512 + pos0);
+		}
+		acc2[jp][0] = pack_f32x2(lo.x, hi.x);
+		acc2[jp][1] = pack_f32x2(lo.y, hi.y);
+		acc2[jp][2] = pack_f32x2(lo.z, hi.z);
+		acc2[jp][3] = pack_f32x2(lo.w, hi.w);
+	}
+#pragma unroll 1
+	for (int ic = ic0; ic < ic1; ++ic) {
+#pragma unroll 1
+		for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+			for (int kh = 0; kh < 3; ++kh) {
+				const uint32_t ia = in0 + (uint32_t)(ic * 1000 + kd * 100 + kh * 10) * 4;
+				uint64_t in2[6];  // the input value in both halves
+#pragma unroll
+				for (int i2 = 0; i2 < 3; ++i2) {
+					float2 v2;
+					asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v2.x), "=f"(v2.y) : "r"(ia + i2 * 8));
+					in2[2 * i2] = pack_f32x2(v2.x, v2.x);
+					in2[2 * i2 + 1] = pack_f32x2(v2.y, v2.y);
+				}
+#pragma unroll
+				for (int kw = 0; kw < 3; ++kw) {
+					const float4* wp = reinterpret_cast<const float4*>(pw.w + (ic * 27 + (kd * 3 + kh) * 3 + kw) * 64 + c0);
+					const float4 wa = wp[0], wb = wp[1];
+					const uint64_t w2[4] = {pack_f32x2(wa.x, wa.y), pack_f32x2(wa.z, wa.w), pack_f32x2(wb.x, wb.y), pack_f32x2(wb.z, wb.w)};
+#pragma unroll
+					for (int jp = 0; jp < 4; ++jp)
+#pragma unroll
+						for (int i = 0; i < 4; ++i) acc2[jp][i] = fma_f32x2(in2[i + kw], w2[jp], acc2[jp][i]);
+				}
+			}
+		}
+	}
+#pragma unroll
+	for (int jp = 0; jp < 4; ++jp) {
+		float lo[4], hi[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i) unpack_f32x2(acc2[jp][i], lo[i], hi[i]);
+		if (ic1 == 3) {  // (a partial sum is stored as it is: adding a zero would turn a -0 into +0)
+			const float b0 = s_par[par128f::pre_b + c0 + 2 * jp], b1 = s_par[par128f::pre_b + c0 + 2 * jp + 1];
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				lo[i] += b0;
+				hi[i] += b1;
+			}
+		}
+		*reinterpret_cast<float4*>(xs + (c0 + 2 * jp) * 512 + pos0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+		*reinterpret_cast<float4*>(xs + (c0 + 2 * jp + 1) * 512 + pos0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+	}
+}
+// The leaf's 3 x 512 voxels into the haloed staging buffer, by `nthreads` threads (t = 0 .. nthreads - 1).
+__device__ __forceinline__ void stage_leaf(float* s_in, const float* __restrict__ src, int t, int nthreads) {
+	for (int e = t; e < 1536; e += nthreads) {
+		const int c = e >> 9, p = e & 511;
+		s_in[c * 1000 + ((p >> 6) + 1) * 100 + (((p >> 3) & 7) + 1) * 10 + (p & 7) + 1] = __ldcs(src + e);
+	}
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
-encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restrict__ leaves, int64_t n_leaves, float* __restrict__ y,
-                          float* __restrict__ scratch, int tap_stage, float* __restrict__ tap_out) {
+encode_tc128_front_kernel(const Encoder128FrontWeights w, const __grid_constant__ Encoder128PreWeights pw, const float* __restrict__ leaves,
+                          int64_t n_leaves, float* __restrict__ y, float* __restrict__ scratch, int tap_stage, float* __restrict__ tap_out) {
 	extern __shared__ __align__(1024) uint8_t smem[];
 	const uint32_t s_base = smem_u32(smem);
 	const uint32_t ring = s_base + kOffRing;
@@ -227,8 +308,12 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 		const int wt = threadIdx.x;  // 0..511: this thread's position in the pre phase
 		const uint32_t tmem_lane = tmem + ((uint32_t)(quad * 32) << 16);
 		const uint32_t zero_row = s_base + kOffZero;
-		float* xs = scratch + (size_t)blockIdx.x * (2 * 64 * 512);  // residual stream x, [64 ch][512 pos] fp32
-		float* cs = xs + 64 * 512;                                   // conv1's output before GroupNorm
+		// per-CTA scratch: the residual stream x [64 ch][512 pos] fp32 of the current leaf and of the next one (whose pre.0
+		// is computed ahead), and conv1's output before GroupNorm
+		float* xs = scratch + (size_t)blockIdx.x * (3 * 64 * 512);
+		float* xs_next = xs + 64 * 512;
+		float* cs = xs + 2 * 64 * 512;
+		const uint32_t s_in_addr = s_base + kOffIn;
 		uint32_t n_red = 0, n_ered = 0, step = 0, layer = 0, passes = 0;
 
 #pragma unroll 1
@@ -242,75 +327,16 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 			};
 
 			// ---------- pre phase, all workers: pre.0 + GroupNorm + ReLU -> x ; res.gn1 + ReLU -> planes ----------
+			const bool has_next = g + 1 < my_leaves;
 			{
-				const float* src = leaves + leaf * 1536;
-#pragma unroll
-				for (int i = 0; i < 3; ++i) {
-					const int e = wt + i * 512, c = e >> 9, p = e & 511;
-					s_in[c * 1000 + ((p >> 6) + 1) * 100 + (((p >> 3) & 7) + 1) * 10 + (p & 7) + 1] = __ldcs(src + e);
+				if (g == 0) {
+					// the CTA's first leaf: pre.0 by all 512 workers, two chunks of 8 channels each (later leaves: see the epilogue warps)
+					stage_leaf(s_in, leaves + leaf * 1536, wt, kWorkers);
+					named_bar_sync(kBarWorkers, kWorkers);
+#pragma unroll 1
+					for (int r = 0; r < 2; ++r) pre0_chunk(pw, s_in_addr, s_par, xs, wt & 127, ((wt >> 7) * 2 + r) * 8, 0, 3);
 				}
-				named_bar_sync(kBarWorkers, kWorkers);  // also: nobody reads the previous leaf's planes any more
-				// pre.0's weights [3][27][64] fp32 (20 KB) over the start of the (idle) hi plane: broadcast reads from shared memory
-				for (int i = wt; i < 81 * 16; i += kWorkers) sts128(plane_hi + (uint32_t)i * 16, __ldg(reinterpret_cast<const uint4*>(w.pre_wt) + i));
-				named_bar_sync(kBarWorkers, kWorkers);
-				{
-					// out[c] = b[c] + sum_{ic, kd, kh, kw} in * w, ascending, as conv3d of the oracle (halo taps add an exact 0).
-					// A thread owns four consecutive positions along w and, in two rounds, 8 of the 16 channels of its warp's
-					// channel group: every weight fetched from shared memory feeds four FMAs, every input value up to three taps.
-					const int pq = wt & 127, pd = pq >> 4, ph = (pq >> 1) & 7, w0 = (pq & 1) * 4, cgrp = wt >> 7;
-					const uint32_t in0 = s_base + kOffIn + (uint32_t)(pd * 100 + ph * 10 + w0) * 4;
-#pragma unroll 1
-					for (int r = 0; r < 2; ++r) {
-						const int c0 = (cgrp * 2 + r) * 8;
-						// packed fp32 pairs (FFMA2): acc2[jp][i] = channels c0 + 2 jp, c0 + 2 jp + 1 of position i
-						uint64_t acc2[4][4];
-#pragma unroll
-						for (int jp = 0; jp < 4; ++jp)
-#pragma unroll
-							for (int i = 0; i < 4; ++i) acc2[jp][i] = 0ull;
-#pragma unroll 1
-						for (int ic = 0; ic < 3; ++ic) {
-#pragma unroll 1
-							for (int kd = 0; kd < 3; ++kd) {
-#pragma unroll
-								for (int kh = 0; kh < 3; ++kh) {
-									const uint32_t ia = in0 + (uint32_t)(ic * 1000 + kd * 100 + kh * 10) * 4;
-									uint64_t in2[6];  // the input value in both halves
-#pragma unroll
-									for (int i2 = 0; i2 < 3; ++i2) {
-										float2 v2;
-										asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v2.x), "=f"(v2.y) : "r"(ia + i2 * 8));
-										in2[2 * i2] = pack_f32x2(v2.x, v2.x);
-										in2[2 * i2 + 1] = pack_f32x2(v2.y, v2.y);
-									}
-#pragma unroll
-									for (int kw = 0; kw < 3; ++kw) {
-										const uint32_t wa = plane_hi + (uint32_t)((ic * 27 + (kd * 3 + kh) * 3 + kw) * 64 + c0) * 4;
-										const uint4 w0r = lds128(wa), w1r = lds128(wa + 16);
-										const uint64_t wp[4] = {pack_f32x2(__uint_as_float(w0r.x), __uint_as_float(w0r.y)), pack_f32x2(__uint_as_float(w0r.z), __uint_as_float(w0r.w)),
-										                        pack_f32x2(__uint_as_float(w1r.x), __uint_as_float(w1r.y)), pack_f32x2(__uint_as_float(w1r.z), __uint_as_float(w1r.w))};
-#pragma unroll
-										for (int jp = 0; jp < 4; ++jp)
-#pragma unroll
-											for (int i = 0; i < 4; ++i) acc2[jp][i] = fma_f32x2(in2[i + kw], wp[jp], acc2[jp][i]);
-									}
-								}
-							}
-						}
-						float acc[8][4];
-#pragma unroll
-						for (int jp = 0; jp < 4; ++jp)
-#pragma unroll
-							for (int i = 0; i < 4; ++i) unpack_f32x2(acc2[jp][i], acc[2 * jp][i], acc[2 * jp + 1][i]);
-						const int pos0 = pd * 64 + ph * 8 + w0;
-#pragma unroll
-						for (int j = 0; j < 8; ++j) {
-							const float bj = s_par[par128f::pre_b + c0 + j];
-							*reinterpret_cast<float4*>(xs + (c0 + j) * 512 + pos0) = make_float4(acc[j][0] + bj, acc[j][1] + bj, acc[j][2] + bj, acc[j][3] + bj);
-						}
-					}
-				}
-				named_bar_sync(kBarWorkers, kWorkers);  // the conv output is complete in the scratch
+				named_bar_sync(kBarWorkers, kWorkers);  // the conv output is complete in the scratch; nobody reads the previous leaf's planes any more
 				stamp();
 				float v[64], gsum[8];
 #pragma unroll
@@ -473,6 +499,20 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 					++passes;
 				};
 				signal_input_ready();  // layer 0: the planes were completed before the workers' barrier above
+				// The next leaf's pre.0 runs in the shadow of this leaf's MMAs: its voxels go into the staging buffer now (this
+				// leaf's pre.0 is long done with it) and its 12 sub-chunks (four channel-slice pairs x three input channels, ~4 k
+				// cycles each) follow the epilogues of conv1's and conv2's tiles 0..2 and fill the two halves of down1 (three each), partial
+				// sums parked in the other x buffer.  (Measured, cycles per leaf: serial pre.0 199 k; whole 81-tap chunks after the
+				// tile epilogues or under down1 188 k — they delay the next accumulator hand-over; this placement 172 k; two
+				// sub-chunks per tile epilogue and one per half of down1 185 k.)
+				if (has_next) {
+					stage_leaf(s_in, leaves + (leaf + gridDim.x) * 1536, wt, kEpiWarps * 32);
+					named_bar_sync(kBarEpi, kEpiWarps * 32);
+				}
+				// sub-chunk sc = 0 .. 11 of the next leaf's pre.0: channel slice pair sc / 3 (8 channels per 128 threads), input channel sc % 3
+				auto next_pre0 = [&](int sc) {
+					if (has_next) pre0_chunk(pw, s_in_addr, s_par, xs_next, wt & 127, ((sc / 3) * 2 + (wt >> 7)) * 8, sc % 3, sc % 3 + 1);
+				};
 
 				float v[32];
 				// ---- conv1 + bias -> scratch, group sums ; after the 4 tiles: gn2 + ReLU -> planes ----
@@ -487,6 +527,7 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 						cs[(c0 + j) * 512 + pos] = v[j];
 						gs[j >> 3] += v[j];
 					}
+					if (tile < 3) next_pre0(tile);  // the last tile's epilogue is followed by the GroupNorm sweeps: nothing in their way
 				}
 				stamp();
 				epi_allreduce4(gs, s_red, n_ered, quad, chalf, lane);
@@ -508,13 +549,16 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 #pragma unroll 1
 				for (int tile = 0; tile < kTiles; ++tile) {
 					const int pos = tile * 128 + row;
+					float cv[32];  // the tile's 32 loads in flight together (the shared-memory stores below are compiler barriers)
+#pragma unroll
+					for (int j = 0; j < 32; ++j) cv[j] = cs[(c0 + j) * 512 + pos];
 #pragma unroll
 					for (int c8 = 0; c8 < 4; ++c8) {
 						float a[8];
 #pragma unroll
 						for (int j = 0; j < 8; ++j) {
 							const int c = c0 + c8 * 8 + j;
-							a[j] = fmaxf((cs[c * 512 + pos] - mean[c8]) * q[c8] * s_par[par128f::gn2_w + c] + s_par[par128f::gn2_b + c], 0.f);
+							a[j] = fmaxf((cv[c8 * 8 + j] - mean[c8]) * q[c8] * s_par[par128f::gn2_w + c] + s_par[par128f::gn2_b + c], 0.f);
 						}
 						uint4 hi, lo;
 						split8(a, hi, lo);
@@ -531,22 +575,27 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 				for (int tile = 0; tile < kTiles; ++tile) {
 					take_conv_tile(v);
 					const int pos = tile * 128 + row;
+					float xo[32];  // all 32 loads before the first store (the compiler cannot prove the stores do not alias them)
+#pragma unroll
+					for (int j = 0; j < 32; ++j) xo[j] = xs[(c0 + j) * 512 + pos];
 #pragma unroll
 					for (int j = 0; j < 32; ++j) {
-						const float xn = xs[(c0 + j) * 512 + pos] + kResScale * (v[j] + s_par[par128f::c2_b + c0 + j]);
+						const float xn = xo[j] + kResScale * (v[j] + s_par[par128f::c2_b + c0 + j]);
 						xs[(c0 + j) * 512 + pos] = xn;
 						if (tap_stage == 1) tap_out[leaf * 32768 + (c0 + j) * 512 + pos] = xn;
 					}
+					if (tile < 3) next_pre0(3 + tile);
 				}
 				stamp();
 #pragma unroll 1
 				for (int tile = 0; tile < kTiles; ++tile) {
 					const int pos = tile * 128 + row;
+					float xv[32];  // as above: all loads of the tile before its first shared-memory store
+#pragma unroll
+					for (int j = 0; j < 32; ++j) xv[j] = xs[(c0 + j) * 512 + pos];
 #pragma unroll
 					for (int c8 = 0; c8 < 4; ++c8) {
-						float a[8];
-#pragma unroll
-						for (int j = 0; j < 8; ++j) a[j] = xs[(c0 + c8 * 8 + j) * 512 + pos];
+						const float* a = xv + c8 * 8;
 						uint4 hi, lo;
 						split8(a, hi, lo);
 						const uint32_t off = chunk_off(pos, chalf * 4 + c8);
@@ -561,6 +610,9 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 				//      arrive as two separately drained halves (four accumulation chains of <= 7 taps in all) ----
 #pragma unroll 1
 				for (int half = 0; half < 2; ++half) {
+					// three more sub-chunks of the next leaf's pre.0 under each half of down1's MMAs (~15 k cycles each)
+#pragma unroll 1
+					for (int k = 0; k < 3; ++k) next_pre0(6 + half * 3 + k);
 					mbar_wait(bar_d_full(bars), passes & 1u);
 					tc_fence_after();
 					if (row < 64) {
@@ -588,6 +640,11 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const float* __restric
 				}
 				stamp();
 			}
+			{  // the next leaf's x (pre.0 output) was written into the other buffer
+				float* t = xs;
+				xs = xs_next;
+				xs_next = t;
+			}
 		}
 	}
 
@@ -603,13 +660,13 @@ cudaError_t configure_encode_tc128_front() {
 	return cudaFuncSetAttribute(encode_tc128_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
 }
 
-size_t encode_tc128_front_scratch_floats(int num_sms) { return (size_t)num_sms * 2 * 64 * 512; }
+size_t encode_tc128_front_scratch_floats(int num_sms) { return (size_t)num_sms * 3 * 64 * 512; }
 
-cudaError_t launch_encode_tc128_front(const Encoder128FrontWeights& w, const float* dev_leaves, int64_t n_leaves, float* dev_y, float* dev_scratch,
-                                      int num_sms, cudaStream_t stream, int tap_stage, float* tap_out) {
+cudaError_t launch_encode_tc128_front(const Encoder128FrontWeights& w, const Encoder128PreWeights& pw, const float* dev_leaves, int64_t n_leaves,
+                                      float* dev_y, float* dev_scratch, int num_sms, cudaStream_t stream, int tap_stage, float* tap_out) {
 	if (n_leaves <= 0) return cudaSuccess;
 	const int grid = (int)(n_leaves < (int64_t)num_sms ? n_leaves : (int64_t)num_sms);
-	encode_tc128_front_kernel<<<grid, kThreads, kSmemBytes, stream>>>(w, dev_leaves, n_leaves, dev_y, dev_scratch, tap_stage, tap_out);
+	encode_tc128_front_kernel<<<grid, kThreads, kSmemBytes, stream>>>(w, pw, dev_leaves, n_leaves, dev_y, dev_scratch, tap_stage, tap_out);
 	return cudaGetLastError();
 }
 
