@@ -41,4 +41,15 @@ if os.path.exists(pack):
     vx = synth.smoke_leaves(m, seed=9, channels=3, sparse=True)
     venc = c.encode(TensorView(vx, list(vx.shape), DataType.FLOAT32)).buffer
     print(c.encode_path, int(venc.astype(np.int64).sum()))
+    # more leaves than CTAs (from a CTA's second leaf on, pre.0 is computed ahead under the previous leaf's MMAs), and the
+    # codebook search's exact path forced on every row (debug tap stage 3)
+    m2 = min(n, 301)
+    vx2 = synth.smoke_leaves(m2, seed=10, channels=3)
+    venc2 = c.encode(TensorView(vx2, list(vx2.shape), DataType.FLOAT32)).buffer
+    xd = torch.from_numpy(vx2).cuda()
+    tap = torch.zeros((m2, 128, 64), dtype=torch.float32, device="cuda")
+    idx_d = torch.empty((m2, 4, 4, 4), dtype=torch.uint8, device="cuda")
+    c.debug_encode_tap(xd, m2, 3, tap, idx_d, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    print("vec3, %d leaves, forced exact path: indices equal" % m2, bool((idx_d.cpu().numpy() == venc2).all()))
     c.close()
