@@ -49,16 +49,17 @@ BYTES_DECODE = 64 + 2048
 # is tied to the git blob hash of the kernel source it was captured from: a changed kernel reports traffic = null
 # ("stale") instead of a number that no longer describes it.
 NCU_DRAM = {
-    "encode": {"bytes_per_leaf": (122.019840e6 + 7.470336e6) / 59200, "source": "profiles/r2_encode_tc_ncu_summary.txt",
-               "file": "vqvdb_b200/csrc/encode_tc.cu", "blob": "b230dfd4377bf9ec4235ba2a5f2f867484911adc"},
+    "encode": {"bytes_per_leaf": (122.022912e6 + 4.907776e6) / 59200, "source": "profiles/r2b_encode_tc_ncu_summary.txt",
+               "file": "vqvdb_b200/csrc/encode_tc.cu", "blob": "f647fc4255f23f966882e86eae377102563d25dd"},
     "decode": {"bytes_per_leaf": (5.091584e6 + 64.778240e6) / 59200, "source": "profiles/r2_decode_tc_ncu_summary.txt",
                "file": "vqvdb_b200/csrc/decode_tc.cu", "blob": "e8c2e6e6f19bd3bd43957df758d9210aa8b7e51c"},
-    # vec3 encoder = two kernels per batch (front: 28.2 MB read + 316.5 MB written, back: 190.5 + 94.1, per 4 144 leaves —
-    # the 32 KB-per-leaf hand-over array and the front kernel's per-CTA scratch are what reaches DRAM)
-    "encode_vec3": {"bytes_per_leaf": (28.231936e6 + 316.458496e6 + 190.531584e6 + 94.121984e6) / 4144,
-                    "source": "profiles/r2_encode_tc128_front_ncu_summary.txt + profiles/r2_encode_tc128_back_ncu_summary.txt",
+    # vec3 encoder = two kernels per batch (front: 31.6 MB read + 1 149.7 MB written, back: 192.3 + 112.0, per 4 144 leaves —
+    # the 32 KB-per-leaf hand-over array and the write-backs of the front kernel's per-CTA scratch (x, the look-ahead
+    # pre.0's partial sums, conv1's output: 384 KB per CTA, rewritten ~2 MB per leaf in L2) are what reaches DRAM)
+    "encode_vec3": {"bytes_per_leaf": (31.575296e6 + 1149.698e6 + 192.294400e6 + 111.996e6) / 4144,
+                    "source": "profiles/r2b_encode_tc128_ncu_summary.txt",
                     "file": ["vqvdb_b200/csrc/encode_tc128_front.cu", "vqvdb_b200/csrc/encode_tc128.cu"],
-                    "blob": ["09b50b35ab8a22f4121a6fbe3082bca6a842ae84", "560dc78e72e6a3cb2cb50d9a22a17fea630f2662"]},
+                    "blob": ["8c512e7a0d7737e3008325f83d27fe42c152afa9", "d7706a1fe5e6fc43331477df756fb480475014a5"]},
 }
 
 
