@@ -465,19 +465,28 @@ decode_tc_kernel(const DecoderMmaWeights w, const uint8_t* __restrict__ indices,
 			}
 		};
 
-		for (int64_t g = 0; g < (wk.tile < active_tiles ? my_groups : 0); ++g) {
+		// The leaf's 64 indices (16 words) come from HBM, ~2 k cycles away: the words of the NEXT group's leaf are requested
+		// at the top of a group and have long arrived when that group's gather needs them.
+		const int64_t my_tile_groups = wk.tile < active_tiles ? my_groups : 0;
+		auto load_index_word = [&](int64_t g) -> uint32_t {
+			const int64_t lf = (blockIdx.x + g * gridDim.x) * leaves_per_group + wk.leaf_slot;
+			return (tl < 16 && g < my_tile_groups && lf < n_leaves) ? __ldcs(reinterpret_cast<const uint32_t*>(indices + lf * 64) + tl) : 0u;
+		};
+		uint32_t idx_word = load_index_word(0);
+		for (int64_t g = 0; g < my_tile_groups; ++g) {
 			const int64_t grp = blockIdx.x + g * gridDim.x;
 			const int64_t leaf = grp * leaves_per_group + wk.leaf_slot;
 			const bool leaf_ok = leaf < n_leaves;
 
 			lap(7);
 			// ---- gather: Q[pos][0..127] = codebook_bf16[idx[pos]] (spare slots decode code 0) ----
-			if (tl < 16) s_idx[tl] = leaf_ok ? __ldcs(reinterpret_cast<const uint32_t*>(indices + leaf * 64) + tl) : 0u;
+			if (tl < 16) s_idx[tl] = idx_word;
+			idx_word = load_index_word(g + 1);
 			leaf_bar(wk);  // also: every thread of the leaf is done with the previous group's planes
 			{
 				const uint8_t* idx8 = reinterpret_cast<const uint8_t*>(s_idx);
-#pragma unroll 4
-				for (int i = tl; i < 64 * 16; i += 128) {
+#pragma unroll
+				for (int i = tl; i < 64 * 16; i += 128) {  // eight L2 loads per thread, all in flight
 					const int pos = i >> 4, c = i & 15;
 					const uint4 v = __ldg(reinterpret_cast<const uint4*>(w.emb_bf16 + (size_t)idx8[pos] * 128) + c);
 					const uint32_t pc = (c & 8) | ((c & 7) ^ (pos & 7));

@@ -345,6 +345,12 @@ decode_tc128_kernel(const Decoder128Weights w, const uint8_t* __restrict__ indic
 			if (lane == 0) mbar_arrive(bar_in_ready(bars));
 		};
 
+		// the index words of the NEXT group's leaf are requested at the top of a group (HBM, ~2 k cycles away)
+		auto load_index_word = [&](int64_t g) -> uint32_t {
+			const int64_t lf = (blockIdx.x + g * gridDim.x) * 2 + e.leaf_slot;
+			return (tl < 16 && g < my_groups && lf < n_leaves) ? __ldcs(reinterpret_cast<const uint32_t*>(indices + lf * 64) + tl) : 0u;
+		};
+		uint32_t idx_word = load_index_word(0);
 #pragma unroll 1
 		for (int64_t g = 0; g < my_groups; ++g) {
 			const int64_t grp = blockIdx.x + g * gridDim.x;
@@ -352,12 +358,13 @@ decode_tc128_kernel(const Decoder128Weights w, const uint8_t* __restrict__ indic
 			const bool leaf_ok = leaf < n_leaves;
 
 			// ---- gather: Q[pos][0..127] = codebook_bf16[idx[pos]] -> buffer 0 (a spare slot decodes code 0) ----
-			if (tl < 16) s_idx[tl] = leaf_ok ? __ldcs(reinterpret_cast<const uint32_t*>(indices + leaf * 64) + tl) : 0u;
+			if (tl < 16) s_idx[tl] = idx_word;
+			idx_word = load_index_word(g + 1);
 			leaf_bar(e);  // also: every thread of the leaf is done with the previous group's G planes and buffers
 			{
 				const uint8_t* idx8 = reinterpret_cast<const uint8_t*>(s_idx);
-#pragma unroll 4
-				for (int i = tl; i < 64 * 16; i += 128) {
+#pragma unroll
+				for (int i = tl; i < 64 * 16; i += 128) {  // eight L2 loads per thread, all in flight
 					const int pos = i >> 4, c = i & 15;
 					const uint4 v = __ldg(reinterpret_cast<const uint4*>(w.emb_bf16 + (size_t)idx8[pos] * 128) + c);
 					*reinterpret_cast<uint4*>(buf0_g + chunk_off(pos, c)) = v;
