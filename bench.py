@@ -49,14 +49,14 @@ BYTES_DECODE = 64 + 2048
 # is tied to the git blob hash of the kernel source it was captured from: a changed kernel reports traffic = null
 # ("stale") instead of a number that no longer describes it.
 NCU_DRAM = {
-    "encode": {"bytes_per_leaf": (122.022912e6 + 4.907776e6) / 59200, "source": "profiles/r2b_encode_tc_ncu_summary.txt",
+    "encode": {"bytes_per_leaf": (122.161920e6 + 5.829120e6) / 59200, "source": "profiles/r2b_encode_tc_ncu_summary.txt",
                "file": "vqvdb_b200/csrc/encode_tc.cu", "blob": "f647fc4255f23f966882e86eae377102563d25dd"},
-    "decode": {"bytes_per_leaf": (5.091584e6 + 64.778240e6) / 59200, "source": "profiles/r2_decode_tc_ncu_summary.txt",
-               "file": "vqvdb_b200/csrc/decode_tc.cu", "blob": "e8c2e6e6f19bd3bd43957df758d9210aa8b7e51c"},
-    # vec3 encoder = two kernels per batch (front: 31.6 MB read + 1 149.7 MB written, back: 192.3 + 112.0, per 4 144 leaves —
+    "decode": {"bytes_per_leaf": (5.199616e6 + 64.842240e6) / 59200, "source": "profiles/r2b_decode_tc_ncu_summary.txt",
+               "file": "vqvdb_b200/csrc/decode_tc.cu", "blob": "6c350ada0246889c8a60decaef8450ae63d90b86"},
+    # vec3 encoder = two kernels per batch (front: 32.3 MB read + 1 154.4 MB written, back: 201.9 + 111.9, per 4 144 leaves —
     # the 32 KB-per-leaf hand-over array and the write-backs of the front kernel's per-CTA scratch (x, the look-ahead
     # pre.0's partial sums, conv1's output: 384 KB per CTA, rewritten ~2 MB per leaf in L2) are what reaches DRAM)
-    "encode_vec3": {"bytes_per_leaf": (31.575296e6 + 1149.698e6 + 192.294400e6 + 111.996e6) / 4144,
+    "encode_vec3": {"bytes_per_leaf": (32.259584e6 + 1154.424e6 + 201.855744e6 + 111.861e6) / 4144,
                     "source": "profiles/r2b_encode_tc128_ncu_summary.txt",
                     "file": ["vqvdb_b200/csrc/encode_tc128_front.cu", "vqvdb_b200/csrc/encode_tc128.cu"],
                     "blob": ["8c512e7a0d7737e3008325f83d27fe42c152afa9", "d7706a1fe5e6fc43331477df756fb480475014a5"]},

@@ -6,6 +6,7 @@ O=gpurun_out/fin
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; tail -3 $O/pytest_gpu.log
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 --leaves 100000 --no-cpu-baseline --parity-sample 0 > $O/launches_bench.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:encode_tc_kernel -s 2 -c 1 -o $O/prof_encode python tools/profile_kernels.py --leaves 59200 > $O/prof_encode.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:decode_tc_kernel -s 2 -c 1 -o $O/prof_decode python tools/profile_kernels.py --leaves 59200 > $O/prof_decode.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:encode_tc128 -c 2 -o $O/prof_vec3_encode python tools/time_vec3_encode.py 4144 1 > $O/prof_vec3_encode.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:decode_tc128 -s 1 -c 1 -o $O/prof_vec3_decode python tools/profile_kernels.py --vec3-decode --leaves 29600 > $O/prof_vec3_decode.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/launches_vec3.csv python bench.py --workload vec3 --steps 1 --warmup 3 --leaves 41440 --no-cpu-baseline --parity-sample 0 > $O/launches_vec3_bench.log 2>&1
