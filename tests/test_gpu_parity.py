@@ -363,47 +363,6 @@ def test_vec3_tc_decode_against_fp32_path_ragged_and_deterministic(codec_vec3_tc
     assert d <= 0.1, "roundtrip PSNR differs from the reference by %.4f dB" % d
 
 
-def test_vec3_tc_encoder_exact_codebook_path_equals_shortlist(codec_vec3_tc):
-    # The codebook search decides a row from the tensor-core scores when its two best codes are further apart than twice
-    # the scores' error bound, and re-scores the others with the reference formula as fp32 FMA chains.  Debug tap stage 3
-    # sends EVERY row through that exact path (and taps z): same indices on mixed fields, or the bound is wrong.
-    import torch
-    y = np.concatenate([synth.smoke_leaves(1024, seed=51, channels=3), synth.noise_leaves(256, seed=52, channels=3),
-                        synth.smoke_leaves(768, seed=53, channels=3, sparse=True), 1e3 * synth.smoke_leaves(128, seed=54, channels=3),
-                        1e-4 * synth.noise_leaves(128, seed=55, channels=3)])
-    n = len(y)
-    want = _encode(codec_vec3_tc, y)
-    yd = torch.from_numpy(y).cuda()
-    forced = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
-    ztap = torch.zeros((n, 128 * 64), dtype=torch.float32, device="cuda")
-    codec_vec3_tc.debug_encode_tap(yd, n, 3, ztap, forced, torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
-    assert np.array_equal(forced.cpu().numpy().reshape(n, 4, 4, 4), want)
-    assert np.isfinite(ztap.cpu().numpy()).all()
-
-
-def test_vec3_tc_encoder_lookahead_pre0_matches_oracle(codec_vec3_tc):
-    # more leaves than CTAs: from a CTA's second leaf on, pre.0 is computed ahead by the epilogue warps under the previous
-    # leaf's MMAs (12 sub-chunks with partial sums parked in global memory); its output must not depend on that
-    import os
-    import torch
-    from conftest import REPO
-    from oracle.pyoracle import COracle
-    o = COracle(os.path.join(REPO, "vqvdb_b200", "weights", "vqvae_vec3_seed0.vqw"), threads=os.cpu_count() or 1)
-    n = 333
-    x = synth.smoke_leaves(n, seed=61, channels=3)
-    want = o.encode_tap(x, 0, 64, 128).reshape(n, -1)                   # pre (GroupNorm + ReLU) [n][64][512]
-    xd = torch.from_numpy(x).cuda()
-    tap = torch.zeros((n, 64 * 512), dtype=torch.float32, device="cuda")
-    idx = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
-    codec_vec3_tc.debug_encode_tap(xd, n, 4, tap, idx, torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
-    err = np.abs(tap.cpu().numpy() - want).max(axis=1)
-    scale = float(np.abs(want).max())
-    assert err.max() <= 2e-5 * scale, "first leaves of a CTA %.3g, later leaves %.3g (scale %.3g)" % (err[:148].max(), err[148:].max(), scale)
-    assert np.array_equal(idx.cpu().numpy().reshape(n, 4, 4, 4), _encode(codec_vec3_tc, x))
-
-
 @pytest.mark.parametrize("name,gen", [("vec3_smoke256_seed5", lambda: synth.smoke_leaves(256, seed=5, channels=3)),
                                       ("vec3_noise64_seed6", lambda: synth.noise_leaves(64, seed=6, channels=3)),
                                       ("vec3_sparse1024_seed7", lambda: synth.smoke_leaves(1024, seed=7, channels=3, sparse=True))])
@@ -464,6 +423,28 @@ def test_vec3_tc_encoder_stage_taps_match_oracle(codec_vec3_tc, stage, oracle_st
     err = float(np.abs(got - want).max())
     assert err <= 2e-5 * scale, "stage %d: max err %.4g vs activation scale %.4g" % (stage, err, scale)
     assert np.array_equal(idx_d.cpu().numpy().reshape(n, 4, 4, 4), _encode(codec_vec3_tc, x))
+
+
+def _check_non_finite_leaves(codec, ch):
+    # A NaN or inf voxel poisons its whole leaf (the GroupNorms spread it, every distance becomes NaN) and torch.argmin /
+    # the oracle's strict `<` scan then return code 0 for all 64 latents; the neighbouring leaves must not notice.
+    x = synth.smoke_leaves(150, seed=3, channels=ch)                    # more leaves than CTAs for the one-leaf-per-CTA kernels
+    clean = _encode(codec, x)
+    bad = x.copy()
+    bad[1, 0, 2, 3, 4] = np.nan
+    bad[2, ch - 1, 7, 7, 7] = np.inf
+    bad[149, 0, 0, 0, 0] = -np.inf
+    got = _encode(codec, bad)
+    for i in (1, 2, 149):
+        assert not got[i].any(), "leaf %d: %s" % (i, np.unique(got[i])[:8])
+    keep = np.ones(150, dtype=bool)
+    keep[[1, 2, 149]] = False
+    assert np.array_equal(got[keep], clean[keep])
+
+
+def test_vec3_non_finite_leaves_encode_like_the_reference(codec_vec3_tc, codec_vec3):
+    _check_non_finite_leaves(codec_vec3_tc, 3)
+    _check_non_finite_leaves(codec_vec3, 3)
 
 
 def test_vec3_tc_encoder_exact_codebook_path_equals_shortlist(codec_vec3_tc):
@@ -572,6 +553,10 @@ def test_both_encoders_match_reference_goldens(codec_enc, name):
     idx = _encode(codec_enc, CASES[name]())
     n_mm = assert_indices_match(idx, g["indices"], g["margins"])
     print("%s / %s: %d of %d indices differ (reference near-ties)" % (codec_enc.encode_path, name, n_mm, idx.size))
+
+
+def test_non_finite_leaves_encode_like_the_reference(codec_enc):
+    _check_non_finite_leaves(codec_enc, 1)
 
 
 def test_both_encoders_ragged_sizes_and_determinism(codec_enc):

@@ -206,7 +206,7 @@ __device__ __forceinline__ void gn8(float (&v)[8][8], const float* __restrict__ 
 		const int c = och * 8 + n, gi = n / CPG;
 		const float ga = __ldg(gamma + c), be = __ldg(beta + c);
 #pragma unroll
-		for (int j = 0; j < 8; ++j) v[n][j] = fmaxf((v[n][j] - mean[gi]) * rstd[gi] * ga + be, 0.f);
+		for (int j = 0; j < 8; ++j) v[n][j] = relu_f((v[n][j] - mean[gi]) * rstd[gi] * ga + be);
 	}
 }
 
@@ -241,7 +241,7 @@ __device__ __forceinline__ void gn4_relu(float (&v)[4][4], const float* __restri
 	for (int n = 0; n < 4; ++n) {
 		const float ga = __ldg(gamma + og * 4 + n), be = __ldg(beta + og * 4 + n);
 #pragma unroll
-		for (int j = 0; j < 4; ++j) v[n][j] = fmaxf((v[n][j] - mean) * rstd * ga + be, 0.f);
+		for (int j = 0; j < 4; ++j) v[n][j] = relu_f((v[n][j] - mean) * rstd * ga + be);
 	}
 }
 
@@ -328,7 +328,7 @@ __device__ __forceinline__ void add_recomputed_residual(float (&v)[8][8], const 
 		const float bias = __ldg(w.pre_b + c), ga = __ldg(w.pre_gn_w + c), be = __ldg(w.pre_gn_b + c);
 		const float m = mean[n >> 2], r = rstd[n >> 2];
 #pragma unroll
-		for (int j = 0; j < 8; ++j) v[n][j] += fmaxf(((t[j] + bias) - m) * r * ga + be, 0.f);
+		for (int j = 0; j < 8; ++j) v[n][j] += relu_f(((t[j] + bias) - m) * r * ga + be);
 	}
 }
 
@@ -549,7 +549,7 @@ encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* 
 			float s = 0.f;
 #pragma unroll 8
 			for (int c = 0; c < 32; ++c) s = fmaf(__ldg(w.fc0 + j * 32 + c), att_mean[l * 32 + c], s);
-			att_hid[l * 8 + j] = fmaxf(s, 0.f);
+			att_hid[l * 8 + j] = relu_f(s);
 		}
 		__syncthreads();
 #pragma unroll
@@ -773,6 +773,9 @@ encode_fp32_kernel(const EncoderWeights w, const EncoderUnits tab, const float* 
 					ob = xch_d[pw * 16 + g + 8];
 					if (ob < best1) bi1 = xch_i[pw * 16 + g + 8];
 					const int64_t l0 = grp * kLeaves + (p0 >> 6), l1 = grp * kLeaves + (p1 >> 6);
+					// every distance NaN (a non-finite voxel poisons its leaf): no candidate won; torch.argmin's answer is code 0
+					if (bi0 == 0x7fffffff) bi0 = 0;
+					if (bi1 == 0x7fffffff) bi1 = 0;
 					if (l0 < n_leaves) indices[l0 * 64 + (p0 & 63)] = (uint8_t)bi0;  // p = (d*4+h)*4+w == view(B,4,4,4)
 					if (l1 < n_leaves) indices[l1 * 64 + (p1 & 63)] = (uint8_t)bi1;
 				}

@@ -841,7 +841,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 			for (int c = 0; c < 4; ++c) {
 				const float ga = sp_c[par::pre_gn_w + g * 4 + c], be = sp_c[par::pre_gn_b + g * 4 + c];
 #pragma unroll
-				for (int t = 0; t < 5; ++t) x[t][c] = fmaxf((x[t][c] - mean[0]) * rstd[0] * ga + be, 0.f);
+				for (int t = 0; t < 5; ++t) x[t][c] = relu_f((x[t][c] - mean[0]) * rstd[0] * ga + be);
 			}
 		};
 		// (d) res16.gn1 + ReLU -> A8 (conv1 input)
@@ -859,7 +859,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				if (valid8 & (1u << t)) {
 					float a[4];
 #pragma unroll
-					for (int c = 0; c < 4; ++c) a[c] = fmaxf((x[t][c] - mean[c >> 1]) * rstd[c >> 1] * ga[c] + be[c], 0.f);
+					for (int c = 0; c < 4; ++c) a[c] = relu_f((x[t][c] - mean[c >> 1]) * rstd[c >> 1] * ga[c] + be[c]);
 					store_split4(a8_mine + t * 2048, kA8Prec, a);
 					if (tap_stage == 0) {
 						int d, h, w8;
@@ -935,7 +935,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				for (int t = 0; t < 5; ++t) {
 					if (valid8 & (1u << t)) {
 #pragma unroll
-						for (int c = 0; c < 4; ++c) v[t][c] = fmaxf((v[t][c] - mean[c >> 1]) * rstd[c >> 1] * ga[c] + be[c], 0.f);
+						for (int c = 0; c < 4; ++c) v[t][c] = relu_f((v[t][c] - mean[c >> 1]) * rstd[c >> 1] * ga[c] + be[c]);
 						store_split4(a8_mine + t * 2048, kA8Prec, v[t]);
 					}
 				}
@@ -1058,7 +1058,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				if (validd) {
 #pragma unroll
 					for (int c = 0; c < 8; ++c)
-						v[0][c] = fmaxf((v[0][c] - mean[c >> 2]) * rstd[c >> 2] * sp_c[par::r32_gn1_w + g * 8 + c] + sp_c[par::r32_gn1_b + g * 8 + c], 0.f);
+						v[0][c] = relu_f((v[0][c] - mean[c >> 2]) * rstd[c >> 2] * sp_c[par::r32_gn1_w + g * 8 + c] + sp_c[par::r32_gn1_b + g * 8 + c]);
 					store_split8(hb + (uint32_t)g * kHPlane + (uint32_t)(kHMargin + jd * 20 + jh * 4 + jw) * 16, kHPrec, v[0]);
 				}
 			}
@@ -1087,7 +1087,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 				if (valid4) {
 #pragma unroll
 					for (int c = 0; c < 8; ++c)
-						v[0][c] = fmaxf((v[0][c] - mean[c >> 2]) * rstd[c >> 2] * sp_c[par::r32_gn2_w + g * 8 + c] + sp_c[par::r32_gn2_b + g * 8 + c], 0.f);
+						v[0][c] = relu_f((v[0][c] - mean[c >> 2]) * rstd[c >> 2] * sp_c[par::r32_gn2_w + g * 8 + c] + sp_c[par::r32_gn2_b + g * 8 + c]);
 					store_split8(h_mine, kHPrec, v[0]);
 				}
 			}
@@ -1130,7 +1130,7 @@ encode_tc_kernel(const EncoderWeights w, const EncoderTcStream ws, const float* 
 						const float m = ((pp[0] + pp[8]) + (pp[16] + pp[24])) * (1.f / 64.f);
 						s = fmaf(sp_c[par::fc0 + tid * 32 + c], m, s);
 					}
-					hid[tid] = fmaxf(s, 0.f);
+					hid[tid] = relu_f(s);
 				}
 				row_bar();
 				if (tid < 32) {

@@ -174,7 +174,7 @@ __device__ __forceinline__ void group_norm_relu(float (&v)[32], Epi& e, float* e
 	for (int g = 0; g < 2; ++g) {
 		const float rstd = 1.f / sqrtf(q[g] * (1.f / 1024.f) + kGnEps);
 #pragma unroll
-		for (int j = 0; j < 16; ++j) v[g * 16 + j] = fmaxf((v[g * 16 + j] - mean[g]) * rstd * gamma[g * 16 + j] + beta[g * 16 + j], 0.f);
+		for (int j = 0; j < 16; ++j) v[g * 16 + j] = relu_f((v[g * 16 + j] - mean[g]) * rstd * gamma[g * 16 + j] + beta[g * 16 + j]);
 	}
 }
 
@@ -687,7 +687,7 @@ encode_tc128_back_kernel(const Encoder128BackWeights w, float* __restrict__ y, i
 					}
 					s += __shfl_xor_sync(0xffffffffu, s, 1);
 					s += __shfl_xor_sync(0xffffffffu, s, 2);
-					if (part == 0) s_hid[unit] = fmaxf(s, 0.f);
+					if (part == 0) s_hid[unit] = relu_f(s);
 				}
 				leaf_bar(e);
 				stamp();

@@ -370,7 +370,7 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const __grid_constant_
 #pragma unroll
 					for (int j = 0; j < 8; ++j) {
 						const int c = gI * 8 + j;
-						v[c] = fmaxf((v[c] - mean[gI]) * rstd * s_par[par128f::pre_gn_w + c] + s_par[par128f::pre_gn_b + c], 0.f);
+						v[c] = relu_f((v[c] - mean[gI]) * rstd * s_par[par128f::pre_gn_w + c] + s_par[par128f::pre_gn_b + c]);
 						xs[c * 512 + wt] = v[c];
 						t += v[c];
 					}
@@ -401,7 +401,7 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const __grid_constant_
 #pragma unroll
 					for (int j = 0; j < 8; ++j) {
 						const int c = gI * 8 + j;
-						a[j] = fmaxf((v[c] - mean[gI]) * rstd * s_par[par128f::gn1_w + c] + s_par[par128f::gn1_b + c], 0.f);
+						a[j] = relu_f((v[c] - mean[gI]) * rstd * s_par[par128f::gn1_w + c] + s_par[par128f::gn1_b + c]);
 					}
 					uint4 hi, lo;
 					split8(a, hi, lo);
@@ -558,7 +558,7 @@ encode_tc128_front_kernel(const Encoder128FrontWeights w, const __grid_constant_
 #pragma unroll
 						for (int j = 0; j < 8; ++j) {
 							const int c = c0 + c8 * 8 + j;
-							a[j] = fmaxf((cv[c8 * 8 + j] - mean[c8]) * q[c8] * s_par[par128f::gn2_w + c] + s_par[par128f::gn2_b + c], 0.f);
+							a[j] = relu_f((cv[c8 * 8 + j] - mean[c8]) * q[c8] * s_par[par128f::gn2_w + c] + s_par[par128f::gn2_b + c]);
 						}
 						uint4 hi, lo;
 						split8(a, hi, lo);

@@ -150,7 +150,7 @@ __device__ void gn_g(float* x, int C, int nsp, int groups, const float* __restri
 		for (int i = lane; i < cnt; i += 32) {
 			const int c = g * cg + i / nsp;
 			float v = (p[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-			p[i] = relu ? fmaxf(v, 0.f) : v;
+			p[i] = relu ? relu_f(v) : v;
 		}
 	}
 	__syncthreads();
@@ -185,7 +185,7 @@ __device__ void attn_g(float* x, int C, int nsp, const float* __restrict__ fc0, 
 		float s = 0.f;
 		for (int c = lane; c < C; c += 32) s = fmaf(__ldg(fc0 + j * C + c), s_mean[c], s);
 		s = warp_sum(s);
-		if (lane == 0) s_hid[j] = fmaxf(s, 0.f);
+		if (lane == 0) s_hid[j] = relu_f(s);
 	}
 	__syncthreads();
 	for (int c = threadIdx.x; c < C; c += kGThreads) {

@@ -13,6 +13,8 @@
 
 #include <cstdint>
 
+#include "ptx_utils.cuh"
+
 namespace vqvdb {
 
 constexpr float kGnEps = 1e-5f;        // nn.GroupNorm default eps (VQVAE_v2.py:196,198,236,258)
@@ -137,7 +139,7 @@ __device__ __forceinline__ void gn_relu_to_halo(const float* src, float* dst_hal
 		const int d = p / (S * S), h = (p / S) % S, w = p % S;
 		const int g = c / CG;
 		float v = (src[i] - s_mean[g]) * s_rstd[g] * __ldg(gamma + c) + __ldg(beta + c);
-		dst_halo[((c * HP + d + 1) * HP + h + 1) * HP + w + 1] = fmaxf(v, 0.f);
+		dst_halo[((c * HP + d + 1) * HP + h + 1) * HP + w + 1] = relu_f(v);
 	}
 }
 
@@ -149,7 +151,7 @@ __device__ __forceinline__ void gn_relu_inplace(float* buf, const float* s_mean,
 	for (int i = threadIdx.x; i < C * NSP; i += blockDim.x) {
 		const int c = i / NSP, g = c / CG;
 		const float v = (buf[i] - s_mean[g]) * s_rstd[g] * __ldg(gamma + c) + __ldg(beta + c);
-		buf[i] = fmaxf(v, 0.f);
+		buf[i] = relu_f(v);
 	}
 }
 
@@ -191,7 +193,7 @@ __device__ __forceinline__ void channel_attention(float* x, const float* __restr
 		float s = 0.f;
 		for (int c = lane; c < C; c += 32) s = fmaf(__ldg(fc0 + j * C + c), s_mean[c], s);
 		s = warp_sum(s);
-		if (lane == 0) s_hid[j] = fmaxf(s, 0.f);
+		if (lane == 0) s_hid[j] = relu_f(s);
 	}
 	__syncthreads();
 	for (int i = threadIdx.x; i < C * NSP; i += blockDim.x) {

@@ -68,6 +68,13 @@ __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c
 	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
 	return d;
 }
+// ReLU that propagates NaN, as torch.relu does (fmaxf(v, 0) returns 0 for a NaN): a leaf with a non-finite voxel must come
+// out of the encoder as NaN everywhere — the reference's argmin then yields code 0 for all of its latents.
+__device__ __forceinline__ float relu_f(float v) {
+	float r;
+	asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+	return r;
+}
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
 	asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
 	             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
