@@ -49,17 +49,17 @@ BYTES_DECODE = 64 + 2048
 # is tied to the git blob hash of the kernel source it was captured from: a changed kernel reports traffic = null
 # ("stale") instead of a number that no longer describes it.
 NCU_DRAM = {
-    "encode": {"bytes_per_leaf": (122.161920e6 + 5.829120e6) / 59200, "source": "profiles/r2b_encode_tc_ncu_summary.txt",
-               "file": "vqvdb_b200/csrc/encode_tc.cu", "blob": "f647fc4255f23f966882e86eae377102563d25dd"},
+    "encode": {"bytes_per_leaf": (122.116608e6 + 6.356736e6) / 59200, "source": "profiles/r2b_encode_tc_ncu_summary.txt",
+               "file": "vqvdb_b200/csrc/encode_tc.cu", "blob": "c2b96d5a4d10c266ef6a30518121785e48b555f7"},
     "decode": {"bytes_per_leaf": (5.199616e6 + 64.842240e6) / 59200, "source": "profiles/r2b_decode_tc_ncu_summary.txt",
                "file": "vqvdb_b200/csrc/decode_tc.cu", "blob": "6c350ada0246889c8a60decaef8450ae63d90b86"},
-    # vec3 encoder = two kernels per batch (front: 32.3 MB read + 1 154.4 MB written, back: 201.9 + 111.9, per 4 144 leaves —
+    # vec3 encoder = two kernels per batch (front: 31.5 MB read + 1 150.7 MB written, back: 202.1 + 111.0, per 4 144 leaves —
     # the 32 KB-per-leaf hand-over array and the write-backs of the front kernel's per-CTA scratch (x, the look-ahead
     # pre.0's partial sums, conv1's output: 384 KB per CTA, rewritten ~2 MB per leaf in L2) are what reaches DRAM)
-    "encode_vec3": {"bytes_per_leaf": (32.259584e6 + 1154.424e6 + 201.855744e6 + 111.861e6) / 4144,
+    "encode_vec3": {"bytes_per_leaf": (31.483136e6 + 1150.738e6 + 202.092288e6 + 110.995e6) / 4144,
                     "source": "profiles/r2b_encode_tc128_ncu_summary.txt",
                     "file": ["vqvdb_b200/csrc/encode_tc128_front.cu", "vqvdb_b200/csrc/encode_tc128.cu"],
-                    "blob": ["8c512e7a0d7737e3008325f83d27fe42c152afa9", "d7706a1fe5e6fc43331477df756fb480475014a5"]},
+                    "blob": ["a02744ea43039dd728f757eee8d2b4db1f603502", "ff73f49e251ea4b22012bb906024aebdb4eec5ce"]},
 }
 
 
