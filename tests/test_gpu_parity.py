@@ -425,6 +425,15 @@ def test_vec3_tc_encoder_stage_taps_match_oracle(codec_vec3_tc, stage, oracle_st
     assert np.array_equal(idx_d.cpu().numpy().reshape(n, 4, 4, 4), _encode(codec_vec3_tc, x))
 
 
+def _check_non_finite_golden(codec, name, seed, ch):
+    g = golden(name)
+    x = synth.nonfinite_leaves(8, seed=seed, channels=ch)
+    poisoned = np.isnan(g["margins"]).reshape(8, -1).all(axis=1)
+    idx = _encode(codec, x)
+    assert np.array_equal(idx[poisoned], g["indices"][poisoned])        # code 0 everywhere, as the reference answers
+    assert_indices_match(idx[~poisoned], g["indices"][~poisoned], g["margins"][~poisoned])
+
+
 def _check_non_finite_leaves(codec, ch):
     # A NaN or inf voxel poisons its whole leaf (the GroupNorms spread it, every distance becomes NaN) and torch.argmin /
     # the oracle's strict `<` scan then return code 0 for all 64 latents; the neighbouring leaves must not notice.
@@ -443,8 +452,9 @@ def _check_non_finite_leaves(codec, ch):
 
 
 def test_vec3_non_finite_leaves_encode_like_the_reference(codec_vec3_tc, codec_vec3):
-    _check_non_finite_leaves(codec_vec3_tc, 3)
-    _check_non_finite_leaves(codec_vec3, 3)
+    for c in (codec_vec3_tc, codec_vec3):
+        _check_non_finite_golden(c, "vec3_nonfinite8_seed12", 12, 3)       # against the reference classes' own output
+        _check_non_finite_leaves(c, 3)
 
 
 def test_vec3_tc_encoder_exact_codebook_path_equals_shortlist(codec_vec3_tc):
@@ -556,6 +566,7 @@ def test_both_encoders_match_reference_goldens(codec_enc, name):
 
 
 def test_non_finite_leaves_encode_like_the_reference(codec_enc):
+    _check_non_finite_golden(codec_enc, "nonfinite8_seed11", 11, 1)        # against the shipped TorchScript model's own output
     _check_non_finite_leaves(codec_enc, 1)
 
 

@@ -110,3 +110,22 @@ def test_c_oracle_vec3_matches_the_reference_classes():
     assert hashlib.sha256(xb.tobytes()).hexdigest() == str(big["input_sha256"])
     idx_b, _ = o.encode(xb[:96], with_margins=True)
     assert_indices_match(idx_b, big["indices"][:96], big["margins"][:96])
+
+
+@pytest.mark.parametrize("name,seed,ch", [("nonfinite8_seed11", 11, 1), ("vec3_nonfinite8_seed12", 12, 3)])
+def test_c_oracle_non_finite_leaves_match_reference(name, seed, ch):
+    # A NaN / +inf / -inf voxel poisons its leaf: the reference (TorchScript blob, the EncoderVec3 class) answers code 0 for
+    # all of its 64 latents; the other leaves are untouched.
+    import os
+    from conftest import REPO
+    from oracle.pyoracle import COracle, VEC3_PACK
+    g = golden(name)
+    x = synth.nonfinite_leaves(8, seed=seed, channels=ch)
+    assert hashlib.sha256(x.tobytes()).hexdigest() == str(g["input_sha256"])
+    poisoned = np.isnan(g["margins"]).reshape(8, -1).all(axis=1)
+    assert poisoned.tolist() == [False, True, True, False, False, True, False, False]
+    assert not g["indices"][poisoned].any()
+    o = COracle(VEC3_PACK) if ch == 3 else COracle()
+    idx = o.encode(x)
+    assert not idx[poisoned].any()
+    assert_indices_match(idx[~poisoned], g["indices"][~poisoned], g["margins"][~poisoned])

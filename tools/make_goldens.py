@@ -66,6 +66,7 @@ def main():
         "noise256_seed2": (synth.noise_leaves(256, seed=2), 32),
         "fogsphere64": (fog, 32),
         "zeros4": (np.zeros((4, 1, 8, 8, 8), np.float32), 4),
+        "nonfinite8_seed11": (synth.nonfinite_leaves(8, seed=11), 8),
     }
     for name, (x, n_recon) in cases.items():
         if only and name not in only:
@@ -86,7 +87,8 @@ def main():
     vmeta, _ = wp.read_pack(vec3_pack)
     for name, gen, n_recon in (("vec3_smoke256_seed5", lambda: synth.smoke_leaves(256, seed=5, channels=3), 32),
                                ("vec3_noise64_seed6", lambda: synth.noise_leaves(64, seed=6, channels=3), 16),
-                               ("vec3_sparse1024_seed7", lambda: synth.smoke_leaves(1024, seed=7, channels=3, sparse=True), 16)):
+                               ("vec3_sparse1024_seed7", lambda: synth.smoke_leaves(1024, seed=7, channels=3, sparse=True), 16),
+                               ("vec3_nonfinite8_seed12", lambda: synth.nonfinite_leaves(8, seed=12, channels=3), 8)):
         if only and name not in only:
             continue
         x = gen()

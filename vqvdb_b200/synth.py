@@ -56,6 +56,16 @@ def noise_leaves(n: int, seed: int = 0, channels: int = 1) -> np.ndarray:
     return v if channels == 1 else 2.0 * v - 1.0
 
 
+def nonfinite_leaves(n: int = 8, seed: int = 11, channels: int = 1) -> np.ndarray:
+    """Smoke leaves with a NaN voxel in leaf 1, +inf in leaf 2 and -inf in leaf n-3: the reference turns such a leaf into
+    code 0 everywhere (torch.relu keeps the NaN, every distance is NaN, torch.argmin answers 0)."""
+    x = smoke_leaves(n, seed=seed, channels=channels)
+    x[1, 0, 2, 3, 4] = np.nan
+    x[2, channels - 1, 7, 7, 7] = np.inf
+    x[n - 3, 0, 0, 0, 0] = -np.inf
+    return x
+
+
 def random_indices(n: int, seed: int = 1234) -> np.ndarray:
     """uint8 i.i.d. uniform[0,255] indices for decode-only throughput."""
     rng = np.random.default_rng(seed)
