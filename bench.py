@@ -615,6 +615,7 @@ def main():
     # the reference's SOPs call the backend with 64 leaves at a time (their default batch; UI maximum 1024 for the encoder
     # SOP, 8192 for the decoder SOP): the same host-pointer calls at those sizes, synchronous, one after the other
     small = {}
+    small_native = {}
     if rank == 0 and not args.no_extras:
         for nb in (64, 1024, 8192):
             if nb >= Le:
@@ -631,6 +632,22 @@ def main():
                 codec.encode_into(ax + o * CH * 2048, nb, ai + o * 64)
                 codec.decode_into(ai + o * 64, nb, av + o * CH * 2048)
             small["batch_%d" % nb] = reps * nb / (time.perf_counter() - t0)
+        # the same calls from a native loop (libvqvdb_b200_host.so: B200Backend::encodeInto / decodeInto per batch) — what a SOP's
+        # C++ loop sees; the reference_gpu_backend numbers below are taken from a native loop too (oracle/ref_worker.py)
+        if not vec3 and world == 1:
+            try:
+                from vqvdb_b200.hostlib import HostBackend
+                hb2 = HostBackend(local)
+                for nb in (64, 1024, 8192):
+                    if nb >= Le:
+                        continue
+                    tot = min(Le, max(4 * nb, 131072))
+                    tot -= tot % nb
+                    hb2.roundtrip_batched(hx.data_ptr(), 4 * nb, nb, hidx.data_ptr(), hvox.data_ptr())      # warm-up
+                    small_native["batch_%d" % nb] = tot / hb2.roundtrip_batched(hx.data_ptr(), tot, nb, hidx.data_ptr(), hvox.data_ptr())
+                hb2.close()
+            except Exception as e:  # noqa: BLE001
+                small_native = {"unavailable": str(e)[:300]}
 
     t = torch.tensor([ms, e2e_s * 1e3, enc_ms, dec_ms, t_enc * 1e3, t_dec * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -732,7 +749,7 @@ def main():
         if pageable is not None:
             line["e2e_pageable"] = pageable
         if small:
-            line["e2e_small_batches"] = {"unit": "leaves/s", **small,
+            line["e2e_small_batches"] = {"unit": "leaves/s", **small, **({"native_loop": small_native} if small_native else {}),
                                          "note": "roundtrip through the same host-pointer calls, 64 / 1024 / 8192 leaves per call (the reference SOPs' default batch is 64, their UI maxima 1024 and 8192); compare reference_gpu_backend"}
         if world == 1 and not args.no_cpu_baseline and not vec3:
             try:

@@ -62,6 +62,11 @@ VQVDB_HOST_API int vqvdb_host_backend_decode(vqvdb_host_backend* b, const uint8_
 VQVDB_HOST_API const void* vqvdb_host_backend_result(const vqvdb_host_backend* b, uint64_t* bytes);
 VQVDB_HOST_API int vqvdb_host_backend_encode_into(vqvdb_host_backend* b, const float* leaves, int64_t n_leaves, uint8_t* indices_out, double* seconds);
 VQVDB_HOST_API int vqvdb_host_backend_decode_into(vqvdb_host_backend* b, const uint8_t* indices, int64_t n_leaves, float* voxels_out, double* seconds);
+/* The reference SOPs' calling pattern (SOP_VQVDB_Encoder.cpp:36, VQVAECodec.cpp:108-127,166-196: one synchronous backend call
+ * per `batch` leaves) as a native loop: for every batch encodeInto, then decodeInto of its indices.  *seconds = wall time of the
+ * whole loop (bench.py's e2e_small_batches: no interpreter between the calls, as there is none in a SOP). */
+VQVDB_HOST_API int vqvdb_host_backend_roundtrip_batched(vqvdb_host_backend* b, const float* leaves, int64_t n_leaves, int64_t batch,
+                                                        uint8_t* indices_out, float* voxels_out, double* seconds);
 
 /* Constructs the orchestrator (VQVAECodec) over a B200 backend whose CodecConfig::source is the weight pack at
  * `pack_path` (NULL or "" = the embedded model) and destroys it again: 0 if it would accept the model, -1 with the

@@ -1,6 +1,7 @@
 // C ABI of the host layer (include/vqvdb_b200_host.h).
 #include "vqvdb_b200_host.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <memory>
@@ -219,6 +220,19 @@ int vqvdb_host_backend_encode_into(vqvdb_host_backend* b, const float* leaves, i
 
 int vqvdb_host_backend_decode_into(vqvdb_host_backend* b, const uint8_t* indices, int64_t n, float* voxels_out, double* seconds) {
 	return timed(seconds, [&] { static_cast<const B200Backend&>(*b->codec).decodeInto(indices, n, voxels_out); });
+}
+
+int vqvdb_host_backend_roundtrip_batched(vqvdb_host_backend* b, const float* leaves, int64_t n, int64_t batch, uint8_t* indices_out,
+                                         float* voxels_out, double* seconds) {
+	if (!b || batch <= 0 || n < 0) return fail(std::invalid_argument("roundtrip_batched: bad arguments"));
+	return timed(seconds, [&] {
+		const auto& codec = static_cast<const B200Backend&>(*b->codec);
+		for (int64_t first = 0; first < n; first += batch) {  // one synchronous backend call per batch and direction, as the SOPs make them
+			const int64_t nb = std::min<int64_t>(batch, n - first);
+			codec.encodeInto(leaves + first * 512, nb, indices_out + first * 64);
+			codec.decodeInto(indices_out + first * 64, nb, voxels_out + first * 512);
+		}
+	});
 }
 
 int vqvdb_host_orchestrator_accepts(int cuda_device, const char* pack_path) {

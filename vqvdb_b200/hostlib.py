@@ -18,6 +18,7 @@ HOST_EXPORTS = [
     "vqvdb_host_compress", "vqvdb_host_decompress", "vqvdb_host_last_error",
     "vqvdb_host_backend_create", "vqvdb_host_backend_destroy", "vqvdb_host_backend_encode", "vqvdb_host_backend_decode",
     "vqvdb_host_backend_result", "vqvdb_host_backend_encode_into", "vqvdb_host_backend_decode_into",
+    "vqvdb_host_backend_roundtrip_batched",
     "vqvdb_host_orchestrator_accepts",
 ]
 
@@ -53,6 +54,8 @@ def load_host_library() -> C.CDLL:
             getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
         for fn in ("vqvdb_host_backend_encode_into", "vqvdb_host_backend_decode_into"):
             getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_double)]
+        L.vqvdb_host_backend_roundtrip_batched.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                                           C.POINTER(C.c_double)]
         L.vqvdb_host_orchestrator_accepts.argtypes = [C.c_int, C.c_char_p]
         L.vqvdb_host_backend_result.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.vqvdb_host_backend_result.restype = C.c_void_p
@@ -197,6 +200,14 @@ class HostBackend:
         sec = C.c_double()
         if self.L.vqvdb_host_backend_encode_into(self.h, leaves.ctypes.data, leaves.shape[0], indices_out.ctypes.data, C.byref(sec)) != 0:
             _err(self.L, "backend_encode_into")
+        return sec.value
+
+    def roundtrip_batched(self, leaves_addr: int, n: int, batch: int, indices_addr: int, voxels_addr: int) -> float:
+        """encodeInto + decodeInto per `batch` leaves in a native loop over raw host addresses; -> seconds of the loop."""
+        sec = C.c_double()
+        if self.L.vqvdb_host_backend_roundtrip_batched(self.h, C.c_void_p(leaves_addr), n, batch, C.c_void_p(indices_addr),
+                                                       C.c_void_p(voxels_addr), C.byref(sec)) != 0:
+            _err(self.L, "backend_roundtrip_batched")
         return sec.value
 
     def decode_into(self, indices: np.ndarray, voxels_out: np.ndarray) -> float:
