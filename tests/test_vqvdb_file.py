@@ -296,3 +296,24 @@ def test_backend_virtuals_on_pageable_memory_match_the_pointer_api():
     finally:
         c.close()
     assert np.array_equal(idx, idx2) and np.array_equal(rec, rec2)
+
+
+@pytest.mark.gpu
+def test_native_batched_loop_equals_whole_grid_calls():
+    """The SOPs' calling pattern — one synchronous backend call per 64 leaves and direction — as the native loop of
+    vqvdb_host_backend_roundtrip_batched (what bench.py's e2e_small_batches.native_loop times): same indices and voxels as
+    one call over the whole grid, ragged tail included."""
+    from vqvdb_b200 import synth
+    x = synth.smoke_leaves(300, seed=9)                   # 4 full batches of 64 + 44
+    hb = hostlib.HostBackend(0)
+    try:
+        idx1 = np.empty((300, 4, 4, 4), np.uint8)
+        vox1 = np.empty((300, 1, 8, 8, 8), np.float32)
+        hb.encode_into(x, idx1)
+        hb.decode_into(idx1, vox1)
+        idx2 = np.zeros_like(idx1)
+        vox2 = np.zeros_like(vox1)
+        assert hb.roundtrip_batched(x.ctypes.data, 300, 64, idx2.ctypes.data, vox2.ctypes.data) > 0
+        assert np.array_equal(idx1, idx2) and np.array_equal(vox1, vox2)
+    finally:
+        hb.close()
